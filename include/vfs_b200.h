@@ -1,0 +1,127 @@
+/* vfs_b200.h — C ABI of the B200-native momentum RHS + LES path of VFS-Wind.
+ *
+ * Drop-in boundary.  Every entry point replaces one reference function;
+ * citations are relative to the reference tree (Source/...):
+ *
+ *   vfs_form_metrics        <- FormMetrics(UserCtx*)                         metrics.c:12
+ *   vfs_contra2cart         <- Contra2Cart(UserCtx*) / Contra2Cart_2         rhs.c:35,65
+ *   vfs_ib_bc               <- IB_BC(UserCtx*)                               momentum.c:2016
+ *   vfs_formfunction2       <- Formfunction_2(UserCtx*, Vec Rhs, double)     momentum.c:454
+ *   vfs_formfunction_snes   <- FormFunction_SNES(SNES, Vec X, Vec F, void*)  momentum.c:2237
+ *   vfs_les_cs              <- Compute_Smagorinsky_Constant_1(UserCtx*,Vec,Vec)  les.c:75
+ *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
+ *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
+ *
+ * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
+ * the context owns every device buffer; host arrays are borrowed for the duration of a call.
+ * Host arrays use the reference's DA "global Vec" layout restricted to this rank's k-slab:
+ * [nzl][my][mx][dof] doubles, i fastest, dof interleaved (Cmpnts{x,y,z}, variables.h:44).
+ *
+ * There is NO CPU fallback: every compute entry point launches sm_100a kernels and returns
+ * VFS_ERR_CUDA if no device is usable.
+ */
+#ifndef VFS_B200_H
+#define VFS_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFS_OK 0
+#define VFS_ERR_ARG (-1)
+#define VFS_ERR_CUDA (-2)
+#define VFS_ERR_UNSUPPORTED (-3)
+#define VFS_ERR_HALO (-4)
+
+/* Fields a caller can upload / download / exchange.  dof 3 fields are Cmpnts. */
+enum vfs_field {
+  VFS_COOR = 0,     /* node coordinates (dof 3), input of vfs_form_metrics          */
+  VFS_CSI, VFS_ETA, VFS_ZET, /* centre metrics lCsi/lEta/lZet (dof 3)                */
+  VFS_AJ,           /* lAj  (dof 1)                                                  */
+  VFS_NVERT,        /* lNvert (dof 1; 0 fluid, 1 IB node, 3 solid)                   */
+  VFS_UCONT,        /* lUcont  contravariant fluxes (dof 3)                          */
+  VFS_UCAT,         /* Ucat / lUcat Cartesian velocity (dof 3), persistent in/out    */
+  VFS_UCAT_OLD,     /* lUcat_old (dof 3), slip-wall ghost rule rhs.c:466             */
+  VFS_UCONT_O,      /* Ucont_o (dof 3)                                               */
+  VFS_UCONT_RM1,    /* Ucont_rm1 (dof 3), BDF2 only                                  */
+  VFS_RHS_O,        /* RHS_o (dof 3)                                                 */
+  VFS_DP,           /* dP (dof 3)                                                    */
+  VFS_F_EUL,        /* F_eul (dof 3) actuator forcing                                */
+  VFS_RHS,          /* Rhs (dof 3) output                                            */
+  VFS_CS,           /* lCs (dof 1) output of vfs_les_cs                              */
+  VFS_NU_T,         /* lNu_t (dof 1) output of vfs_les_nut                           */
+  VFS_USTAR,        /* lUstar (dof 1) wall-model friction velocity                   */
+  VFS_NFIELDS_PUBLIC
+};
+
+typedef struct vfs_params {
+  int mx, my, mz;        /* DA node counts (IM+1, JM+1, KM+1), init.c:157-160                */
+  int kofs, nzl;         /* this rank owns global planes k in [kofs, kofs+nzl)               */
+  int rank, nranks;      /* k-slab decomposition                                             */
+  int device;            /* CUDA device ordinal                                              */
+  int ii_periodic, jj_periodic, kk_periodic; /* DA-wrap periodicity (main.c:284-288)         */
+  int bctype[6];         /* bcs.dat (init.c:503-510)                                         */
+  int les;               /* 0 off, 1 constant Cs, 2 dynamic                                  */
+  int second_order, laplacian, immersed, clark, central;
+  int testfilter_ik;
+  int viscosity_wallmodel, wallfunction;
+  int rotor_model, nacelle_model, IB_delta;   /* any non-zero => Rhs += F_eul (momentum.c:2329) */
+  int ti, tistart, rstart_flg;
+  int levelset, rans, inviscid, skew, movefsi, rotatefsi; /* must be 0 (out of scope)        */
+  int i_periodic, j_periodic, k_periodic;     /* legacy single-rank periodicity: must be 0   */
+  int i_homo_filter, j_homo_filter, k_homo_filter; /* must be 0 (off in all configs)         */
+  double ren, dt, max_cs;
+} vfs_params;
+
+typedef struct vfs_ctx vfs_ctx;
+
+/* k-halo callback.  Called (only when nranks > 1) whenever the path needs the k-ghost planes of
+ * `nfields` scalar planes refreshed from the neighbouring ranks.  ids are INTERNAL scalar ids;
+ * use vfs_scalar_ptr() to obtain each scalar's device base pointer and vfs_layout() for the
+ * plane geometry.  Must return 0 on success, after the exchange has been enqueued on (or
+ * synchronised with) the context's stream. */
+typedef int (*vfs_halo_fn)(void *user, int nfields, const int *scalar_ids);
+
+int vfs_create(const vfs_params *p, vfs_ctx **out);
+int vfs_destroy(vfs_ctx *c);
+const char *vfs_last_error(vfs_ctx *c);          /* c may be NULL: last create() error      */
+int vfs_set_params(vfs_ctx *c, const vfs_params *p); /* update run-time switches (ti, dt, ...) */
+int vfs_set_stream(vfs_ctx *c, void *cuda_stream);   /* run on a caller stream (cudaStream_t) */
+int vfs_set_halo_callback(vfs_ctx *c, vfs_halo_fn fn, void *user);
+int vfs_sync(vfs_ctx *c);
+
+/* layout[0..7] = G (ghost width), pitch, ny (=my+2G), nzt (=nzl+2G), plane doubles (=ny*pitch),
+ * scalar doubles (=nzt*plane), number of internal scalars, dof-offset convention (=1). */
+int vfs_layout(vfs_ctx *c, long *layout8);
+int vfs_field_scalar_id(vfs_ctx *c, int field, int comp);  /* public field -> internal scalar  */
+void *vfs_scalar_ptr(vfs_ctx *c, int scalar_id);           /* device pointer of padded scalar  */
+
+/* host <-> device, host layout [nzl][my][mx][dof] */
+int vfs_upload(vfs_ctx *c, int field, const double *host);
+int vfs_download(vfs_ctx *c, int field, double *host);
+/* refresh ghosts (i/j wrap + k halo) of one public field, as DAGlobalToLocal would */
+int vfs_halo_exchange(vfs_ctx *c, int field);
+
+int vfs_form_metrics(vfs_ctx *c);
+int vfs_contra2cart(vfs_ctx *c);
+int vfs_ib_bc(vfs_ctx *c);
+int vfs_les_cs(vfs_ctx *c);
+int vfs_les_nut(vfs_ctx *c);
+/* Rhs (device field `rhs_field`, VFS_RHS or VFS_RHS_O) += scale * R(Ucont, Ucat) */
+int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale);
+/* F = residual(X); X, F host arrays [nzl][my][mx][3] (pinned or pageable) */
+int vfs_formfunction_snes(vfs_ctx *c, const double *x_host, double *f_host);
+/* same with X already in VFS_UCONT and F left in VFS_RHS (device resident Krylov vectors) */
+int vfs_formfunction_snes_dev(vfs_ctx *c);
+/* one cell-update unit: vfs_contra2cart + vfs_les_cs + vfs_les_nut + vfs_formfunction_snes_dev */
+int vfs_rhs_les_fused(vfs_ctx *c);
+
+/* number of kernels launched by this context since creation (bench `gpu_launches`) */
+long vfs_launch_count(vfs_ctx *c);
+/* CUDA-event timing of the last compute call's dominant kernel group, in ms (0 if n/a):
+ * which = 0 whole call, 1 flux kernels, 2 les pass2 */
+double vfs_last_ms(vfs_ctx *c, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,176 @@
+"""ctypes driver for oracle/_ref/libvfsref.so (the reference's own sources behind a PETSc shim).
+
+TEST INFRASTRUCTURE ONLY.  Used by tests/ (as the checker), by tests/golden/make_golden.py (to
+generate committed fixtures) and by bench.py's cpu_baseline / --impl reference legs.  The product
+path never imports this module.
+
+The reference keeps its run-time switches in ~95 C globals (Source/main.c:21-356); `RefCase`
+sets them from a flat dict before creating the single-rank DA, because the DA wrap type depends on
+ii/jj/kk_periodic (Source/init.c:145-160).
+"""
+import ctypes as C
+import json
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_ref", "libvfsref.so")
+
+_CT = {"int": C.c_int, "PetscInt": C.c_int, "PetscTruth": C.c_int, "double": C.c_double, "PetscReal": C.c_double}
+_lib = None
+_globals = None
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def lib():
+    global _lib, _globals
+    if _lib is None:
+        _lib = C.CDLL(SO)
+        _globals = json.load(open(os.path.join(HERE, "_ref", "globals.json")))
+        L = _lib
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int] * 3
+        L.ref_vec.restype = C.c_void_p
+        L.ref_vec.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_vec_data.restype = C.POINTER(C.c_double)
+        L.ref_vec_data.argtypes = [C.c_void_p]
+        L.ref_vec_size.restype = C.c_long
+        L.ref_vec_size.argtypes = [C.c_void_p]
+        L.ref_vec_is_local.argtypes = [C.c_void_p]
+        L.ref_vec_dof.argtypes = [C.c_void_p]
+        L.ref_local_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_set_scalars.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_int)]
+        L.ref_global_to_local.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        for f in ("ref_FormMetrics", "ref_Contra2Cart", "ref_IB_BC", "ref_Compute_Smagorinsky_Constant_1",
+                  "ref_Compute_eddy_viscosity_LES"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ref_Formfunction_2.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.ref_FormFunction_SNES.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_Convection.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_Viscous.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_vec_new.restype = C.c_void_p
+        L.ref_vec_new.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_vec_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def set_global(name, value):
+    L = lib()
+    t = _globals[name]
+    _CT[t].in_dll(L, name).value = value
+
+
+def get_global(name):
+    L = lib()
+    return _CT[_globals[name]].in_dll(L, name).value
+
+
+# every switch the hot path reads (SURVEY section 5 "Config / flags"); all default 0 as in main.c
+FLAG_DEFAULTS = dict(
+    les=0, rans=0, levelset=0, levelset_weno=0, inviscid=0, central=0, second_order=0, skew=0, clark=0, laplacian=0,
+    immersed=0, i_periodic=0, j_periodic=0, k_periodic=0, ii_periodic=0, jj_periodic=0, kk_periodic=0,
+    i_homo_filter=0, j_homo_filter=0, k_homo_filter=0, testfilter_ik=0, max_cs=0.5, wallfunction=0,
+    viscosity_wallmodel=0, freesurface_wallmodel=0, movefsi=0, rotatefsi=0, rotor_model=0, nacelle_model=0, IB_delta=0,
+    ti=10, tistart=0, rstart_flg=0, wave_momentum_source=0, air_flow_levelset=0, surface_tension=0, lowRe=0,
+    roughness_size=0.0, dthick=1.5, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
+)
+
+
+class RefCase:
+    """One single-rank reference context.  Arrays are numpy views into the reference's Vecs with
+    shape (nz, ny, nx[, 3]); local (ghosted) Vecs start at index (gzs, gys, gxs) which is -3 in
+    DA-wrapped directions: use `view(name)` for the raw ghosted array or `owned(name)` for the
+    mx*my*mz owned block."""
+
+    def __init__(self, mx, my, mz, flags, ren, dt, bctype):
+        L = lib()
+        fl = dict(FLAG_DEFAULTS)
+        fl.update(flags)
+        fl["periodic"] = sum(fl[k] for k in ("i_periodic", "j_periodic", "k_periodic", "ii_periodic", "jj_periodic", "kk_periodic"))
+        for k, v in fl.items():
+            set_global(k, v)
+        self.flags = fl
+        self.mx, self.my, self.mz = mx, my, mz
+        self.u = L.ref_create(mx, my, mz)
+        bc = (C.c_int * 6)(*bctype)
+        L.ref_set_scalars(self.u, ren, dt, bc)
+        info = (C.c_int * 6)()
+        L.ref_local_info(self.u, info)
+        self.gxs, self.gys, self.gzs, self.gxm, self.gym, self.gzm = list(info)
+        self._extra = {}
+
+    def vec(self, name):
+        if name in self._extra:
+            return self._extra[name]
+        v = lib().ref_vec(self.u, name.encode())
+        if not v:
+            raise KeyError(name)
+        return v
+
+    def new_vec(self, name, dof, local):
+        self._extra[name] = lib().ref_vec_new(self.u, dof, int(local))
+        return self._extra[name]
+
+    def view(self, name):
+        L = lib()
+        v = self.vec(name)
+        n = L.ref_vec_size(v)
+        dof = L.ref_vec_dof(v)
+        loc = L.ref_vec_is_local(v)
+        a = np.ctypeslib.as_array(L.ref_vec_data(v), shape=(n,))
+        shp = (self.gzm, self.gym, self.gxm) if loc else (self.mz, self.my, self.mx)
+        return a.reshape(shp + ((dof,) if dof > 1 else ()))
+
+    def owned(self, name):
+        a = self.view(name)
+        if lib().ref_vec_is_local(self.vec(name)):
+            return a[-self.gzs:-self.gzs + self.mz, -self.gys:-self.gys + self.my, -self.gxs:-self.gxs + self.mx]
+        return a
+
+    def set_owned(self, name, arr):
+        self.owned(name)[...] = arr
+
+    def wrap_fill(self, name):
+        """Fill the DA-wrap ghosts of a local Vec from its owned block (what DALocalToLocal does)."""
+        a = self.view(name)
+        o = np.array(self.owned(name))
+        idx = [np.arange(g, g + n) % m for g, n, m in ((self.gzs, self.gzm, self.mz), (self.gys, self.gym, self.my), (self.gxs, self.gxm, self.mx))]
+        a[...] = o[np.ix_(*idx)]
+
+    def set_coords(self, xyz):
+        """xyz: (mz, my, mx, 3) node coordinates (entries at index m-1 are unused by the reference)."""
+        self.set_owned("coords", xyz)
+        self.wrap_fill("coords")
+
+    def global_to_local(self, g, l):
+        lib().ref_global_to_local(self.u, g.encode(), l.encode())
+
+    def FormMetrics(self):
+        return lib().ref_FormMetrics(self.u)
+
+    def Contra2Cart(self):
+        lib().ref_Contra2Cart(self.u)
+
+    def IB_BC(self):
+        lib().ref_IB_BC(self.u)
+
+    def Formfunction_2(self, rhs_name, scale):
+        return lib().ref_Formfunction_2(self.u, self.vec(rhs_name), scale)
+
+    def FormFunction_SNES(self, x_name, f_name):
+        return lib().ref_FormFunction_SNES(self.u, self.vec(x_name), self.vec(f_name))
+
+    def Compute_Smagorinsky_Constant_1(self):
+        lib().ref_Compute_Smagorinsky_Constant_1(self.u)
+
+    def Compute_eddy_viscosity_LES(self):
+        lib().ref_Compute_eddy_viscosity_LES(self.u)
+
+    def Convection(self, name):
+        return lib().ref_Convection(self.u, self.vec(name))
+
+    def Viscous(self, name):
+        return lib().ref_Viscous(self.u, self.vec(name))

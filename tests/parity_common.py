@@ -1,0 +1,125 @@
+"""Shared parity driver: runs the same seeded case through the oracle (oracle/_ref = the
+reference's own sources) and through a VfsContext, returning per-field relative errors
+max|a-b| / max|b| (SURVEY 8c tolerance: 1e-12 for Rhs, Ucat, Cs, nu_t; masks bit-exact)."""
+import importlib.util
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def load_package():
+    name = "vfs_wind_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "vfs-wind_b200", "__init__.py"),
+                                                  submodule_search_locations=[os.path.join(ROOT, "vfs-wind_b200")])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    den = np.abs(b).max()
+    if den == 0:
+        return float(np.abs(a).max())
+    return float(np.abs(a - b).max() / den)
+
+
+def ref_setup(cfg, refdrv):
+    """Create the reference context, metrics and input state for cfg.  Returns (ref, xyz, fields)."""
+    pkg = load_package()
+    cases = pkg.cases
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    ref = refdrv.RefCase(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"])
+    xyz = cases.make_grid(cfg)
+    ref.set_coords(xyz)
+    ref.FormMetrics()
+    met = dict(csi=np.array(ref.owned("lCsi")), eta=np.array(ref.owned("lEta")), zet=np.array(ref.owned("lZet")), aj=np.array(ref.owned("lAj")))
+    fields = cases.make_fields(cfg, met)
+    ref.set_owned("Nvert", fields["nvert"])
+    ref.global_to_local("Nvert", "lNvert")
+    ref.set_owned("Ucont", fields["ucont"])
+    ref.global_to_local("Ucont", "lUcont")
+    ref.set_owned("Ucat", fields["ucat"])
+    ref.global_to_local("Ucat", "lUcat")
+    ref.set_owned("lUcat_old", fields["ucat_old"])
+    ref.wrap_fill("lUcat_old")
+    ref.set_owned("Ucont_o", fields["ucont_o"])
+    ref.set_owned("Ucont_rm1", fields["ucont_rm1"])
+    ref.set_owned("RHS_o", fields["rhs_o"])
+    ref.set_owned("dP", fields["dp"])
+    ref.set_owned("F_eul", fields["f_eul"])
+    return ref, xyz, fields, met
+
+
+def dev_setup(cfg, xyz, fields, lib=None, device=0):
+    pkg = load_package()
+    capi = pkg.capi
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    p = capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], device=device)
+    ctx = capi.VfsContext(p, lib=lib)
+    ctx.upload("COOR", xyz)
+    ctx.FormMetrics()
+    ctx.upload("NVERT", fields["nvert"])
+    ctx.upload("UCONT", fields["ucont"])
+    ctx.upload("UCAT", fields["ucat"])
+    ctx.upload("UCAT_OLD", fields["ucat_old"])
+    ctx.upload("UCONT_O", fields["ucont_o"])
+    ctx.upload("UCONT_RM1", fields["ucont_rm1"])
+    ctx.upload("RHS_O", fields["rhs_o"])
+    ctx.upload("DP", fields["dp"])
+    ctx.upload("F_EUL", fields["f_eul"])
+    return ctx
+
+
+def run_parity(cfg, refdrv, lib=None, device=0, verbose=False):
+    """Full path comparison.  Returns dict name -> relative error."""
+    ref, xyz, fields, met = ref_setup(cfg, refdrv)
+    ctx = dev_setup(cfg, xyz, fields, lib=lib, device=device)
+    err = {}
+    for nm, key in (("CSI", "csi"), ("ETA", "eta"), ("ZET", "zet"), ("AJ", "aj")):
+        err["metrics_" + nm] = relerr(ctx.download(nm), met[key])
+    # Flow_Solver LES block: Contra2Cart, Cs, nu_t (solvers.c:365-371)
+    ref.Contra2Cart()
+    ctx.Contra2Cart()
+    err["Contra2Cart_ucat"] = relerr(ctx.download("UCAT"), ref.owned("Ucat"))
+    if cfg["flags"].get("les"):
+        ref.Compute_Smagorinsky_Constant_1()
+        ctx.Compute_Smagorinsky_Constant_1()
+        err["Cs"] = relerr(ctx.download("CS"), ref.owned("lCs"))
+        ref.Compute_eddy_viscosity_LES()
+        ctx.Compute_eddy_viscosity_LES()
+        err["nu_t"] = relerr(ctx.download("NU_T"), ref.owned("lNu_t"))
+    # RHS_o = Formfunction_2(U) with scale 1 (solvers.c:628-629)
+    ref.IB_BC()
+    ctx.IB_BC()
+    err["IB_BC_ucont"] = relerr(ctx.download("UCONT"), ref.owned("lUcont"))
+    ref.view("RHS_o")[...] = 0
+    ref.Formfunction_2("RHS_o", 1.0)
+    ctx.upload("RHS_O", np.zeros_like(fields["rhs_o"]))
+    ctx.Formfunction_2("RHS_O", 1.0)
+    rhs_o_ref = np.array(ref.owned("RHS_o"))
+    err["Formfunction_2"] = relerr(ctx.download("RHS_O"), rhs_o_ref)
+    # one Krylov-iteration residual
+    x = fields["ucont"] + 1e-4 * np.abs(fields["ucont"]).max() * np.cos(np.arange(fields["ucont"].size).reshape(fields["ucont"].shape) * 0.37)
+    ref.new_vec("X", 3, False)
+    ref.new_vec("F", 3, False)
+    ref.view("X")[...] = x
+    ref.FormFunction_SNES("X", "F")
+    f_ref = np.array(ref.view("F"))
+    f_dev = ctx.FormFunction_SNES(x)
+    err["FormFunction_SNES"] = relerr(f_dev, f_ref)
+    err["FormFunction_SNES_zero_pattern"] = float(np.count_nonzero((f_dev == 0) != (f_ref == 0)))
+    err["SNES_ucat"] = relerr(ctx.download("UCAT"), ref.owned("Ucat"))
+    if verbose:
+        for k, v in err.items():
+            print("%-32s %.3e" % (k, v))
+    ctx.close()
+    return err

@@ -1,0 +1,6 @@
+"""vfs-wind_b200: B200-native momentum RHS + LES path of VFS-Wind.
+
+The directory name contains a hyphen (it mirrors the reference's repository name), so it is
+loaded by path: `from __graft_entry__ import load_package; pkg = load_package()`.
+"""
+from . import capi, cases  # noqa: F401

@@ -1,0 +1,242 @@
+"""ctypes binding of the C ABI in include/vfs_b200.h (libvfs_b200.so, hand-written sm_100a CUDA).
+
+Host-side mirror of the reference's operator interface for the momentum RHS + LES path: method
+names follow the reference functions they replace (FormMetrics, Contra2Cart, IB_BC,
+Formfunction_2, FormFunction_SNES, Compute_Smagorinsky_Constant_1, Compute_eddy_viscosity_LES;
+Source/variables.h:608-609,628,699-700,1196-1197,1229).  There is no CPU fallback: if the CUDA
+library is missing or no GPU is usable, construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvfs_b200.so")
+
+FIELDS = ["COOR", "CSI", "ETA", "ZET", "AJ", "NVERT", "UCONT", "UCAT", "UCAT_OLD", "UCONT_O", "UCONT_RM1", "RHS_O", "DP", "F_EUL",
+          "RHS", "CS", "NU_T", "USTAR"]
+FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
+FIELD_DOF = {"COOR": 3, "CSI": 3, "ETA": 3, "ZET": 3, "AJ": 1, "NVERT": 1, "UCONT": 3, "UCAT": 3, "UCAT_OLD": 3, "UCONT_O": 3,
+             "UCONT_RM1": 3, "RHS_O": 3, "DP": 3, "F_EUL": 3, "RHS": 3, "CS": 1, "NU_T": 1, "USTAR": 1}
+
+EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs_set_stream", "vfs_set_halo_callback", "vfs_sync",
+           "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
+           "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2",
+           "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms"]
+
+
+class VfsParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("mx", "my", "mz", "kofs", "nzl", "rank", "nranks", "device", "ii_periodic", "jj_periodic", "kk_periodic")] + \
+               [("bctype", C.c_int * 6)] + \
+               [(n, C.c_int) for n in ("les", "second_order", "laplacian", "immersed", "clark", "central", "testfilter_ik",
+                                       "viscosity_wallmodel", "wallfunction", "rotor_model", "nacelle_model", "IB_delta",
+                                       "ti", "tistart", "rstart_flg", "levelset", "rans", "inviscid", "skew", "movefsi", "rotatefsi",
+                                       "i_periodic", "j_periodic", "k_periodic", "i_homo_filter", "j_homo_filter", "k_homo_filter")] + \
+               [(n, C.c_double) for n in ("ren", "dt", "max_cs")]
+
+
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int))
+
+
+class VfsError(RuntimeError):
+    pass
+
+
+def _bind(lib):
+    lib.vfs_create.argtypes = [C.POINTER(VfsParams), C.POINTER(C.c_void_p)]
+    lib.vfs_destroy.argtypes = [C.c_void_p]
+    lib.vfs_last_error.argtypes = [C.c_void_p]
+    lib.vfs_last_error.restype = C.c_char_p
+    lib.vfs_set_params.argtypes = [C.c_void_p, C.POINTER(VfsParams)]
+    lib.vfs_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vfs_set_halo_callback.argtypes = [C.c_void_p, HALO_FN, C.c_void_p]
+    lib.vfs_sync.argtypes = [C.c_void_p]
+    lib.vfs_layout.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+    lib.vfs_field_scalar_id.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.vfs_scalar_ptr.argtypes = [C.c_void_p, C.c_int]
+    lib.vfs_scalar_ptr.restype = C.c_void_p
+    lib.vfs_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.vfs_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.vfs_halo_exchange.argtypes = [C.c_void_p, C.c_int]
+    for f in ("vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused"):
+        getattr(lib, f).argtypes = [C.c_void_p]
+    lib.vfs_formfunction2.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.vfs_formfunction_snes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vfs_launch_count.argtypes = [C.c_void_p]
+    lib.vfs_launch_count.restype = C.c_long
+    lib.vfs_last_ms.argtypes = [C.c_void_p, C.c_int]
+    lib.vfs_last_ms.restype = C.c_double
+    if hasattr(lib, "vfs_set_option"):
+        lib.vfs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VfsError("libvfs_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def make_params(mx, my, mz, flags, ren, dt, bctype, kofs=0, nzl=None, rank=0, nranks=1, device=0):
+    p = VfsParams()
+    p.mx, p.my, p.mz = mx, my, mz
+    p.kofs, p.nzl = kofs, (mz if nzl is None else nzl)
+    p.rank, p.nranks, p.device = rank, nranks, device
+    for q in range(6):
+        p.bctype[q] = int(bctype[q])
+    p.ti, p.tistart, p.max_cs = 10, 0, 0.5
+    for k, v in flags.items():
+        if k == "max_cs":
+            p.max_cs = float(v)
+        elif hasattr(p, k):
+            setattr(p, k, int(v))
+        elif v:
+            raise VfsError("flag %s is not part of the hot-path contract" % k)
+    p.ren, p.dt = float(ren), float(dt)
+    return p
+
+
+def slab_partition(mz, nranks):
+    """Contiguous k-slabs: global planes [kofs, kofs+nzl) per rank, remainder to the low ranks."""
+    base, rem = divmod(mz, nranks)
+    out, k = [], 0
+    for r in range(nranks):
+        n = base + (1 if r < rem else 0)
+        out.append((k, n))
+        k += n
+    return out
+
+
+class VfsContext:
+    """One device context (one GPU / one k-slab)."""
+
+    def __init__(self, params, lib=None):
+        self.lib = lib if lib is not None else load()
+        self.p = params
+        h = C.c_void_p()
+        r = self.lib.vfs_create(C.byref(params), C.byref(h))
+        if r != 0:
+            raise VfsError("vfs_create failed (%d): %s" % (r, self.lib.vfs_last_error(None).decode()))
+        self.h = h
+        L = (C.c_long * 8)()
+        self.lib.vfs_layout(self.h, L)
+        self.G, self.pitch, self.ny, self.nzt, self.plane, self.scalar_len, self.nscalars = [int(x) for x in L[:7]]
+        self._cb = None
+
+    def close(self):
+        if self.h:
+            self.lib.vfs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r):
+        if r != 0:
+            raise VfsError("vfs call failed (%d): %s" % (r, self.lib.vfs_last_error(self.h).decode()))
+
+    @property
+    def shape(self):
+        return (self.p.nzl, self.p.my, self.p.mx)
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self.p, k, v)
+        self._ck(self.lib.vfs_set_params(self.h, C.byref(self.p)))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.vfs_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def set_halo_callback(self, pyfn):
+        """pyfn(list_of_scalar_ids) -> 0 on success."""
+        def tramp(user, n, ids):
+            try:
+                return int(pyfn([ids[q] for q in range(n)]) or 0)
+            except Exception as e:  # noqa
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._cb = HALO_FN(tramp)
+        self._ck(self.lib.vfs_set_halo_callback(self.h, self._cb, None))
+
+    def scalar_ptr(self, sid):
+        return self.lib.vfs_scalar_ptr(self.h, sid)
+
+    def scalar_id(self, field, comp=0):
+        return self.lib.vfs_field_scalar_id(self.h, FIELD_ID[field], comp)
+
+    def upload(self, field, arr):
+        dof = FIELD_DOF[field]
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        want = self.shape + ((3,) if dof == 3 else ())
+        if a.shape != want:
+            raise VfsError("upload %s: shape %s != %s" % (field, a.shape, want))
+        self._ck(self.lib.vfs_upload(self.h, FIELD_ID[field], a.ctypes.data_as(C.c_void_p)))
+
+    def download(self, field):
+        dof = FIELD_DOF[field]
+        out = np.empty(self.shape + ((3,) if dof == 3 else ()), dtype=np.float64)
+        self._ck(self.lib.vfs_download(self.h, FIELD_ID[field], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def halo_exchange(self, field):
+        self._ck(self.lib.vfs_halo_exchange(self.h, FIELD_ID[field]))
+
+    # --- reference-named entry points -------------------------------------------------------
+    def FormMetrics(self):
+        self._ck(self.lib.vfs_form_metrics(self.h))
+
+    def Contra2Cart(self):
+        self._ck(self.lib.vfs_contra2cart(self.h))
+
+    def IB_BC(self):
+        self._ck(self.lib.vfs_ib_bc(self.h))
+
+    def Compute_Smagorinsky_Constant_1(self):
+        self._ck(self.lib.vfs_les_cs(self.h))
+
+    def Compute_eddy_viscosity_LES(self):
+        self._ck(self.lib.vfs_les_nut(self.h))
+
+    def Formfunction_2(self, rhs_field, scale):
+        self._ck(self.lib.vfs_formfunction2(self.h, FIELD_ID[rhs_field], float(scale)))
+
+    def FormFunction_SNES(self, x, f=None):
+        """x: host (nzl,my,mx,3) array; returns F (same shape).  `f` may be a preallocated
+        (e.g. pinned) output array; raw integer addresses are accepted for both."""
+        if isinstance(x, int):
+            self._ck(self.lib.vfs_formfunction_snes(self.h, C.c_void_p(x), C.c_void_p(f)))
+            return None
+        xa = np.ascontiguousarray(x, dtype=np.float64)
+        if f is None:
+            f = np.empty_like(xa)
+        self._ck(self.lib.vfs_formfunction_snes(self.h, xa.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p)))
+        return f
+
+    def FormFunction_SNES_dev(self):
+        self._ck(self.lib.vfs_formfunction_snes_dev(self.h))
+
+    def rhs_les_fused(self):
+        self._ck(self.lib.vfs_rhs_les_fused(self.h))
+
+    def sync(self):
+        self._ck(self.lib.vfs_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.vfs_launch_count(self.h))
+
+    def last_ms(self, which=0):
+        return float(self.lib.vfs_last_ms(self.h, which))
+
+    def set_option(self, key, value):
+        self.lib.vfs_set_option(self.h, key, value)

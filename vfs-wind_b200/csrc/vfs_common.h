@@ -1,0 +1,73 @@
+// vfs_common.h — device-side grid/field model shared by all kernels.
+//
+// HBM layout: every scalar plane set is a padded 3-D array
+//   [nzl + 2G][my + 2G][pitch]   (k slowest, i fastest, FP64)
+// G = 4 ghost layers on every side.  Vector fields (Cmpnts in the reference) are split into three
+// such scalars (SoA), so loads along i are unit-stride and coalesced.  Logical index (i,j,k) with
+// k LOCAL to the rank's slab (global k = k + kofs) maps to ((k+G)*ny + (j+G))*pitch + (i+G).
+// Ghosts hold DA-wrap images in periodic directions / neighbour-rank planes in k, exactly like
+// the reference's ghosted local Vecs (width 3 there, init.c:131-160), so reference index
+// arithmetic such as ucat[k][j][-3] carries over literally.
+#ifndef VFS_COMMON_H
+#define VFS_COMMON_H
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VFS_HD __host__ __device__ __forceinline__
+#else
+#define VFS_HD inline
+#endif
+
+#define VFS_G 4
+
+// internal scalar ids ------------------------------------------------------------------------
+enum {
+  S_X = 0, S_Y, S_Z,                                  // node coordinates
+  S_CSI0, S_CSI1, S_CSI2, S_ETA0, S_ETA1, S_ETA2, S_ZET0, S_ZET1, S_ZET2, S_AJ, S_NV,
+  S_UC0, S_UC1, S_UC2,                                // ucont
+  S_U0, S_U1, S_U2,                                   // ucat
+  S_UO0, S_UO1, S_UO2,                                // ucat_old
+  S_UCO0, S_UCO1, S_UCO2,                             // ucont_o
+  S_UCM0, S_UCM1, S_UCM2,                             // ucont_rm1
+  S_RO0, S_RO1, S_RO2,                                // rhs_o
+  S_DP0, S_DP1, S_DP2,                                // dP
+  S_FE0, S_FE1, S_FE2,                                // F_eul
+  S_R0, S_R1, S_R2,                                   // rhs
+  S_CS, S_NUT, S_USTAR,
+  // work (never cross the ABI)
+  S_FC1, S_FC1b, S_FC1c, S_FC2, S_FC2b, S_FC2c, S_FC3, S_FC3b, S_FC3c,   // convective face fluxes (Div1-3)
+  S_FV1, S_FV1b, S_FV1c, S_FV2, S_FV2b, S_FV2c, S_FV3, S_FV3b, S_FV3c,   // viscous+SGS face fluxes (Visc1-3)
+  S_FP0, S_FP1, S_FP2,                                                   // Fp
+  S_AX0, S_AX1, S_AX2, S_AY0, S_AY1, S_AY2, S_AZ0, S_AZ1, S_AZ2, S_SABS, // LES: grad u, |S|
+  S_UF0, S_UF1, S_UF2,                                                   // LES: test-filtered ucat
+  S_LM, S_MM,
+  S_COUNT
+};
+
+struct VfsDev {
+  // geometry
+  int mx, my, mz, nzl, kofs;
+  int pitch, ny, nzt;
+  long sj, sk;            // strides in doubles: sj = pitch, sk = ny*pitch
+  long org;               // offset of logical (0,0,0)
+  // switches (vfs_params)
+  int perx, pery, perz;
+  int bc[6];
+  int les, second_order, laplacian, immersed, clark, testfilter_ik, visc_wm, wallfunction, has_feul;
+  int ti, tistart, rstart_flg, bdf2, single_rank;
+  double ren, dt, max_cs;
+  double *s[S_COUNT];
+  VFS_HD long idx(int i, int j, int k) const { return org + (long)k * sk + (long)j * sj + i; }
+};
+
+struct Box { int i0, i1, j0, j1, k0, k1; };
+
+// 3-component helpers -------------------------------------------------------------------------
+struct V3 { double x, y, z; };
+VFS_HD V3 ld3(const VfsDev &d, int s0, long p) { V3 v; v.x = d.s[s0][p]; v.y = d.s[s0 + 1][p]; v.z = d.s[s0 + 2][p]; return v; }
+VFS_HD void st3(const VfsDev &d, int s0, long p, const V3 &v) { d.s[s0][p] = v.x; d.s[s0 + 1][p] = v.y; d.s[s0 + 2][p] = v.z; }
+VFS_HD V3 mk3(double x, double y, double z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+VFS_HD double dot3(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+#endif

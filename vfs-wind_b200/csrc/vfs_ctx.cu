@@ -1,0 +1,487 @@
+// vfs_ctx.cu — context, kernel sequencing and the C ABI of include/vfs_b200.h.
+//
+// Built by nvcc for sm_100a into libvfs_b200.so (the product).  The same translation unit can be
+// compiled by g++ with -DVFS_EMU into a host-loop emulation used ONLY by tests/emu (kernel-logic
+// debugging in a GPU-less container); the Python binding never loads that build.
+#include "../../include/vfs_b200.h"
+#include "vfs_common.h"
+#include "vfs_halo_kernels.h"
+#include "vfs_metrics_kernels.h"
+#include "vfs_c2c_kernels.h"
+#include "vfs_rhs_kernels.h"
+#include "vfs_les_kernels.h"
+#include "vfs_fused_kernels.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#ifndef VFS_EMU
+#include <cuda_runtime.h>
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(c, std::string(#call) + ": " + cudaGetErrorString(e_)); return VFS_ERR_CUDA; } } while (0)
+template <class F> __global__ void __launch_bounds__(256) k_box(F f, Box b) {
+  int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = b.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  int k = b.k0 + blockIdx.z * blockDim.z + threadIdx.z;
+  if (i < b.i1 && j < b.j1 && k < b.k1) f(i, j, k);
+}
+#else
+#define CK(call) do { } while (0)
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+#endif
+
+static std::string g_create_err;
+
+struct vfs_ctx {
+  vfs_params prm;
+  VfsDev d;
+  double *pool = nullptr;        // all scalars, contiguous
+  double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
+  long scalar_len = 0;
+  cudaStream_t stream = 0;
+  bool own_stream = false;
+  vfs_halo_fn halo_fn = nullptr; void *halo_user = nullptr;
+  long launches = 0;
+  std::string err;
+  cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
+  bool ev_valid[3] = {false, false, false};
+  int fused = 1;                 // use the fused smem-tiled RHS kernel when applicable
+};
+
+static void set_err(vfs_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_err = m; }
+
+template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
+  if (b.i1 <= b.i0 || b.j1 <= b.j0 || b.k1 <= b.k0) return 0;
+  c->launches++;
+#ifndef VFS_EMU
+  dim3 blk(64, 2, 2);
+  if (b.i1 - b.i0 <= 8) blk = dim3(8, 8, 4);
+  else if (b.j1 - b.j0 == 1) blk = dim3(64, 1, 4);
+  else if (b.k1 - b.k0 == 1) blk = dim3(64, 4, 1);
+  dim3 grd((b.i1 - b.i0 + blk.x - 1) / blk.x, (b.j1 - b.j0 + blk.y - 1) / blk.y, (b.k1 - b.k0 + blk.z - 1) / blk.z);
+  k_box<F><<<grd, blk, 0, c->stream>>>(f, b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(c, std::string("kernel launch: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+#else
+  for (int k = b.k0; k < b.k1; k++) for (int j = b.j0; j < b.j1; j++) for (int i = b.i0; i < b.i1; i++) f(i, j, k);
+#endif
+  return 0;
+}
+#define RUN(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+static void ev_rec(vfs_ctx *c, int n) {
+#ifndef VFS_EMU
+  if (c->ev[n]) cudaEventRecord(c->ev[n], c->stream);
+  c->ev_valid[n / 2] = true;
+#endif
+}
+
+// ---- public field table -----------------------------------------------------------------------
+static const struct { int s0, dof; } FIELD[VFS_NFIELDS_PUBLIC] = {
+  {S_X, 3}, {S_CSI0, 3}, {S_ETA0, 3}, {S_ZET0, 3}, {S_AJ, 1}, {S_NV, 1}, {S_UC0, 3}, {S_U0, 3}, {S_UO0, 3},
+  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}};
+
+static Grp grp(int s0, int n) { Grp g; g.n = n; for (int q = 0; q < n; q++) g.sid[q] = s0 + q; return g; }
+static Grp grp_cat(const Grp &a, const Grp &b) { Grp g = a; for (int q = 0; q < b.n; q++) g.sid[g.n++] = b.sid[q]; return g; }
+
+// owned-node boxes (local k)
+static Box box_owned(const vfs_ctx *c) { Box b = {0, c->d.mx, 0, c->d.my, 0, c->d.nzl}; return b; }
+static int klo(const vfs_ctx *c, int kg) { int k = kg - c->d.kofs; return k < 0 ? 0 : (k > c->d.nzl ? c->d.nzl : k); }
+static Box box_interior(const vfs_ctx *c) { Box b = {1, c->d.mx - 1, 1, c->d.my - 1, klo(c, 1), klo(c, c->d.mz - 1)}; return b; }
+
+// ---- ghost refresh primitives -------------------------------------------------------------------
+static int wrap_ij(vfs_ctx *c, const Grp &g) {
+  const VfsDev &d = c->d;
+  if (d.perx) { WrapFill f = {d, g, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
+  if (d.pery) { WrapFill f = {d, g, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
+  return 0;
+}
+static int halo_k(vfs_ctx *c, const Grp &g) {
+  const VfsDev &d = c->d;
+  if (c->prm.nranks > 1) {
+    if (!c->halo_fn) { set_err(c, "nranks > 1 but no halo callback registered"); return VFS_ERR_HALO; }
+    int r = c->halo_fn(c->halo_user, g.n, g.sid);
+    if (r) { set_err(c, "halo callback failed"); return VFS_ERR_HALO; }
+    return 0;
+  }
+  if (d.perz) { WrapFill f = {d, g, 2}; Box b = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, 0, 2 * VFS_G}; RUN(launch(c, b, f)); }
+  return 0;
+}
+// DAGlobalToLocal / DALocalToLocal
+static int g2l(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return halo_k(c, g); }
+// the "if(periodic) ... f[k][j][i] = f[c][b][a]" loops
+static int node_copy(vfs_ctx *c, const Grp &g) {
+  const VfsDev &d = c->d;
+  NodeCopy f = {d, g};
+  if (d.perx) { Box b0 = {0, 1, 0, d.my, 0, d.nzl}, b1 = {d.mx - 1, d.mx, 0, d.my, 0, d.nzl}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  if (d.pery) { Box b0 = {0, d.mx, 0, 1, 0, d.nzl}, b1 = {0, d.mx, d.my - 1, d.my, 0, d.nzl}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  if (d.perz) {
+    if (d.kofs == 0) { Box b0 = {0, d.mx, 0, d.my, 0, 1}; RUN(launch(c, b0, f)); }
+    if (d.kofs + d.nzl == d.mz) { Box b1 = {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}; RUN(launch(c, b1, f)); }
+  }
+  return 0;
+}
+static bool any_per(const vfs_ctx *c) { return c->d.perx || c->d.pery || c->d.perz; }
+
+// ---- creation -------------------------------------------------------------------------------------
+static int check_params(const vfs_params *p, std::string &why) {
+  if (p->mx < 6 || p->my < 6 || p->mz < 6) { why = "grid too small (need >= 6 nodes per direction)"; return VFS_ERR_ARG; }
+  if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) { why = "bad rank/nranks"; return VFS_ERR_ARG; }
+  if (p->kofs < 0 || p->nzl < 1 || p->kofs + p->nzl > p->mz) { why = "bad k-slab"; return VFS_ERR_ARG; }
+  if (p->nranks == 1 && (p->kofs != 0 || p->nzl != p->mz)) { why = "single rank must own all k planes"; return VFS_ERR_ARG; }
+  if (p->nranks > 1 && p->nzl < VFS_G) { why = "k-slab thinner than the ghost width"; return VFS_ERR_ARG; }
+  if (p->levelset || p->rans || p->inviscid || p->skew || p->movefsi || p->rotatefsi) { why = "levelset/rans/inviscid/skew/movefsi/rotatefsi are outside the hot-path scope"; return VFS_ERR_UNSUPPORTED; }
+  if (p->i_periodic || p->j_periodic || p->k_periodic) { why = "legacy i/j/k_periodic not supported (use ii/jj/kk_periodic)"; return VFS_ERR_UNSUPPORTED; }
+  if (p->i_homo_filter || p->j_homo_filter || p->k_homo_filter) { why = "homogeneous-plane Cs averaging not supported"; return VFS_ERR_UNSUPPORTED; }
+  if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
+  if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
+  if (p->viscosity_wallmodel) { why = "viscosity_wallmodel (Cabot wall law) not built yet"; return VFS_ERR_UNSUPPORTED; }
+  for (int q = 0; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2 || p->bctype[q] == 11) { why = "wall-function / cylinder boundary types (-1,-2,11) not supported"; return VFS_ERR_UNSUPPORTED; }
+  if (!(p->ren > 0) || !(p->dt > 0)) { why = "ren and dt must be positive"; return VFS_ERR_ARG; }
+  return 0;
+}
+
+static void fill_dev(vfs_ctx *c) {
+  const vfs_params &p = c->prm; VfsDev &d = c->d;
+  d.mx = p.mx; d.my = p.my; d.mz = p.mz; d.nzl = p.nzl; d.kofs = p.kofs;
+  d.pitch = ((p.mx + 2 * VFS_G + 15) / 16) * 16; d.ny = p.my + 2 * VFS_G; d.nzt = p.nzl + 2 * VFS_G;
+  d.sj = d.pitch; d.sk = (long)d.ny * d.pitch;
+  d.org = (long)VFS_G * d.sk + (long)VFS_G * d.sj + VFS_G;
+  d.perx = p.ii_periodic != 0; d.pery = p.jj_periodic != 0; d.perz = p.kk_periodic != 0;
+  for (int q = 0; q < 6; q++) d.bc[q] = p.bctype[q];
+  d.les = p.les; d.second_order = p.second_order; d.laplacian = p.laplacian; d.immersed = p.immersed; d.clark = p.clark;
+  d.testfilter_ik = p.testfilter_ik; d.visc_wm = p.viscosity_wallmodel; d.wallfunction = p.wallfunction;
+  d.has_feul = (p.rotor_model || p.nacelle_model || p.IB_delta) ? 1 : 0;
+  d.ti = p.ti; d.tistart = p.tistart; d.rstart_flg = p.rstart_flg; d.bdf2 = 0; d.single_rank = p.nranks == 1;
+  d.ren = p.ren; d.dt = p.dt; d.max_cs = p.max_cs;
+}
+
+extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
+  if (!p || !out) { g_create_err = "null argument"; return VFS_ERR_ARG; }
+  std::string why; int r = check_params(p, why);
+  if (r) { g_create_err = why; return r; }
+  vfs_ctx *c = new vfs_ctx();
+  c->prm = *p; fill_dev(c);
+  c->scalar_len = (long)c->d.nzt * c->d.sk;
+  size_t bytes = (size_t)c->scalar_len * S_COUNT * sizeof(double);
+  size_t sbytes = (size_t)p->nzl * p->my * p->mx * 3 * sizeof(double);
+#ifndef VFS_EMU
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (no CPU fallback exists)"; delete c; return VFS_ERR_CUDA; }
+  e = cudaMalloc((void **)&c->pool, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&c->stage, sbytes);
+  if (e != cudaSuccess) { g_create_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); delete c; return VFS_ERR_CUDA; }
+  cudaMemset(c->pool, 0, bytes);
+  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true;
+  for (int q = 0; q < 6; q++) cudaEventCreate(&c->ev[q]);
+#else
+  c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
+#endif
+  for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
+  *out = c;
+  return 0;
+}
+
+extern "C" int vfs_destroy(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+#ifndef VFS_EMU
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->pool); cudaFree(c->stage);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  for (int q = 0; q < 6; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
+#else
+  free(c->pool); free(c->stage);
+#endif
+  delete c; return 0;
+}
+extern "C" const char *vfs_last_error(vfs_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+extern "C" int vfs_set_params(vfs_ctx *c, const vfs_params *p) {
+  if (!c || !p) return VFS_ERR_ARG;
+  if (p->mx != c->prm.mx || p->my != c->prm.my || p->mz != c->prm.mz || p->nzl != c->prm.nzl || p->kofs != c->prm.kofs || p->nranks != c->prm.nranks) { set_err(c, "geometry cannot change"); return VFS_ERR_ARG; }
+  std::string why; int r = check_params(p, why); if (r) { set_err(c, why); return r; }
+  c->prm = *p; double *sv[S_COUNT]; memcpy(sv, c->d.s, sizeof(sv)); fill_dev(c); memcpy(c->d.s, sv, sizeof(sv)); return 0;
+}
+extern "C" int vfs_set_stream(vfs_ctx *c, void *s) {
+  if (!c) return VFS_ERR_ARG;
+#ifndef VFS_EMU
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->own_stream = false;
+#endif
+  c->stream = (cudaStream_t)s; return 0;
+}
+extern "C" int vfs_set_halo_callback(vfs_ctx *c, vfs_halo_fn fn, void *user) { if (!c) return VFS_ERR_ARG; c->halo_fn = fn; c->halo_user = user; return 0; }
+extern "C" int vfs_sync(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+#ifndef VFS_EMU
+  CK(cudaStreamSynchronize(c->stream));
+#endif
+  return 0;
+}
+extern "C" int vfs_layout(vfs_ctx *c, long *L) {
+  if (!c || !L) return VFS_ERR_ARG;
+  L[0] = VFS_G; L[1] = c->d.pitch; L[2] = c->d.ny; L[3] = c->d.nzt; L[4] = c->d.sk; L[5] = c->scalar_len; L[6] = S_COUNT; L[7] = 1; return 0;
+}
+extern "C" int vfs_field_scalar_id(vfs_ctx *c, int field, int comp) {
+  if (!c || field < 0 || field >= VFS_NFIELDS_PUBLIC || comp < 0 || comp >= FIELD[field].dof) return VFS_ERR_ARG;
+  return FIELD[field].s0 + comp;
+}
+extern "C" void *vfs_scalar_ptr(vfs_ctx *c, int sid) { if (!c || sid < 0 || sid >= S_COUNT) return 0; return c->d.s[sid]; }
+extern "C" long vfs_launch_count(vfs_ctx *c) { return c ? c->launches : 0; }
+extern "C" double vfs_last_ms(vfs_ctx *c, int which) {
+#ifndef VFS_EMU
+  if (!c || which < 0 || which > 2 || !c->ev_valid[which]) return 0;
+  float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[2 * which], c->ev[2 * which + 1]) != cudaSuccess) return 0; return ms;
+#else
+  return 0;
+#endif
+}
+extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) { if (!c) return VFS_ERR_ARG; if (key == 0) c->fused = value; return 0; }
+
+// ---- transfers ------------------------------------------------------------------------------------
+static int h2d_stage(vfs_ctx *c, const double *host, int dof) {
+  size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * dof * sizeof(double);
+#ifndef VFS_EMU
+  CK(cudaMemcpyAsync(c->stage, host, n, cudaMemcpyHostToDevice, c->stream));
+#else
+  memcpy(c->stage, host, n);
+#endif
+  return 0;
+}
+static int d2h_stage(vfs_ctx *c, double *host, int dof) {
+  size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * dof * sizeof(double);
+#ifndef VFS_EMU
+  CK(cudaMemcpyAsync(host, c->stage, n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+#else
+  memcpy(host, c->stage, n);
+#endif
+  return 0;
+}
+extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
+  if (!c || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  return g2l(c, grp(FIELD[field].s0, FIELD[field].dof));
+}
+extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
+  if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  RUN(h2d_stage(c, host, FIELD[field].dof));
+  UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
+  RUN(launch(c, box_owned(c), f));
+  RUN(vfs_halo_exchange(c, field));
+  return vfs_sync(c);
+}
+extern "C" int vfs_download(vfs_ctx *c, int field, double *host) {
+  if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  PackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
+  RUN(launch(c, box_owned(c), f));
+  return d2h_stage(c, host, FIELD[field].dof);
+}
+
+// ---- FormMetrics ------------------------------------------------------------------------------------
+extern "C" int vfs_form_metrics(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  RUN(halo_k(c, grp(S_X, 3)));                       // cell (.,.,k) needs node plane k-1
+  { MetricsCenter f = {d}; RUN(launch(c, box_interior(c), f)); }
+  for (int side = 0; side < 2; side++) { MetricsMirror f = {d, 0, side}; int i = side ? d.mx - 1 : 0; Box b = {i, i + 1, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
+  for (int side = 0; side < 2; side++) { MetricsMirror f = {d, 1, side}; int j = side ? d.my - 1 : 0; Box b = {0, d.mx, j, j + 1, 0, d.nzl}; RUN(launch(c, b, f)); }
+  if (d.kofs == 0) { MetricsMirror f = {d, 2, 0}; Box b = {0, d.mx, 0, d.my, 0, 1}; RUN(launch(c, b, f)); }
+  if (d.kofs + d.nzl == d.mz) { MetricsMirror f = {d, 2, 1}; Box b = {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}; RUN(launch(c, b, f)); }
+  Grp g = grp(S_CSI0, 10);
+  RUN(g2l(c, g));
+  if (any_per(c)) { RUN(node_copy(c, g)); RUN(g2l(c, g)); }
+  return vfs_sync(c);
+}
+
+// ---- Contra2Cart ------------------------------------------------------------------------------------
+struct CopyScalar3 { VfsDev d; int from, to; VFS_HD void operator()(int i, int j, int k) const { long p = d.idx(i, j, k); for (int a = 0; a < 3; a++) d.s[to + a][p] = d.s[from + a][p]; } };
+
+static int for_boundary_planes(vfs_ctx *c, int (*fn)(vfs_ctx *, const Box &, void *), void *arg) {
+  const VfsDev &d = c->d;
+  Box b[6] = {{0, 1, 0, d.my, 0, d.nzl}, {d.mx - 1, d.mx, 0, d.my, 0, d.nzl}, {0, d.mx, 0, 1, 0, d.nzl}, {0, d.mx, d.my - 1, d.my, 0, d.nzl},
+              {0, d.mx, 0, d.my, 0, 1}, {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}};
+  for (int q = 0; q < 6; q++) {
+    if (q == 4 && d.kofs != 0) continue;
+    if (q == 5 && d.kofs + d.nzl != d.mz) continue;
+    RUN(fn(c, b[q], arg));
+  }
+  return 0;
+}
+static int run_snapshot(vfs_ctx *c, const Box &b, void *) { CopyScalar3 f = {c->d, S_U0, S_FP0}; return launch(c, b, f); }
+static int run_ghost_rules(vfs_ctx *c, const Box &b, void *) { C2CGhostRules f = {c->d}; return launch(c, b, f); }
+
+static int contra2cart(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  Grp gu = grp(S_U0, 3);
+  if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // rhs.c:129-156
+  { C2CInterior f = {d}; RUN(launch(c, box_interior(c), f)); }      // rhs.c:158-247
+  RUN(g2l(c, gu));
+  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:254-291
+  RUN(for_boundary_planes(c, run_snapshot, 0));                      // lUcat snapshot read by the rules
+  RUN(for_boundary_planes(c, run_ghost_rules, 0));                   // rhs.c:302-682 (boundary nodes)
+  { C2CInteriorFix f = {d}; RUN(launch(c, box_interior(c), f)); }   // rhs.c:305-308,676-681 (interior nodes)
+  RUN(g2l(c, gu));
+  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:712-748
+  return 0;
+}
+extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return vfs_sync(c); }
+
+// ---- IB_BC ---------------------------------------------------------------------------------------------
+static int ib_bc(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  if (any_per(c)) RUN(node_copy(c, grp(S_U0, 3)));                   // momentum.c:2086-2107
+  if (d.immersed) { IbBcFaces f = {d}; RUN(launch(c, box_interior(c), f)); }
+  IbBcBoundary f = {d};
+  const int m[3] = {d.mx, d.my, d.mz};
+  const int per[3] = {d.perx, d.pery, d.perz};
+  for (int D = 0; D < 3; D++) {
+    int planes[3] = {0, m[D] - 2, m[D] - 1};
+    bool need[3] = {d.bc[2 * D] == 10 || per[D], d.bc[2 * D + 1] == 10, per[D] != 0};
+    for (int q = 0; q < 3; q++) {
+      if (!need[q]) continue;
+      Box b = box_owned(c);
+      if (D == 0) { b.i0 = planes[q]; b.i1 = b.i0 + 1; }
+      else if (D == 1) { b.j0 = planes[q]; b.j1 = b.j0 + 1; }
+      else { int k = planes[q] - d.kofs; if (k < 0 || k >= d.nzl) continue; b.k0 = k; b.k1 = k + 1; }
+      RUN(launch(c, b, f));
+    }
+  }
+  return g2l(c, grp(S_UC0, 3));                                      // momentum.c:2231-2232
+}
+extern "C" int vfs_ib_bc(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(ib_bc(c)); return vfs_sync(c); }
+
+// ---- Formfunction_2 ------------------------------------------------------------------------------------
+// mode 0: rhs[s0] += scale*R, masks (Formfunction_2) ; mode 1: full SNES assembly into S_R0
+static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
+  const VfsDev &d = c->d;
+  if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
+  const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
+  ev_rec(c, 2);
+  if (c->fused && fused_rhs_applicable(d)) {
+    RUN(launch_fused_rhs(c->stream, d, mode, s0, scale, &c->launches));
+    ev_rec(c, 3);
+    return 0;
+  }
+  { FaceFlux<0> f = {d}; Box b = {0, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
+  { FaceFlux<1> f = {d}; Box b = {1, d.mx - 1, 0, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
+  { FaceFlux<2> f = {d}; Box b = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2}; RUN(launch(c, b, f)); }
+  ev_rec(c, 3);
+  Grp gf = grp(S_FC1, 18);
+  RUN(g2l(c, gf));                                                    // momentum.c:1458-1496
+  if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
+  { FpCell f = {d}; RUN(launch(c, box_interior(c), f)); }            // momentum.c:1548-1678
+  Grp gp = grp(S_FP0, 3);
+  RUN(g2l(c, gp));
+  if (any_per(c)) RUN(node_copy(c, gp));                              // momentum.c:1687-1713
+  if (mode == 0) { ProjectAdd f = {d, s0, scale}; RUN(launch(c, box_owned(c), f)); }
+  else { ProjectSNES f = {d}; RUN(launch(c, box_owned(c), f)); }
+  return 0;
+}
+extern "C" int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale) {
+  if (!c || (rhs_field != VFS_RHS && rhs_field != VFS_RHS_O)) return VFS_ERR_ARG;
+  RUN(formfunction2(c, 0, FIELD[rhs_field].s0, scale));
+  return vfs_sync(c);
+}
+
+// ---- FormFunction_SNES -----------------------------------------------------------------------------------
+struct ZeroNormal {   // wall-normal zeroing applied to an Ucont that is already on the device
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    long p = d.idx(i, j, k);
+    double tmp[3] = {d.s[S_UC0][p], d.s[S_UC1][p], d.s[S_UC2][p]};
+    const int mx = d.mx, my = d.my, mz = d.mz, kg = k + d.kofs;
+    const bool jin = (j != 0 && j != my - 1), kin = (kg != 0 && kg != mz - 1), iin = (i != 0 && i != mx - 1);
+    if ((i == 0 && d.bc[0] == 1) || (i == mx - 2 && d.bc[1] == 1)) tmp[0] = 0;
+    if (d.bc[0] == 10 && i == 0 && jin && kin) tmp[0] = 0;
+    if (d.bc[1] == 10 && i == mx - 2 && jin && kin) tmp[0] = 0;
+    if ((j == 0 && d.bc[2] == 1) || (j == my - 2 && d.bc[3] == 1)) tmp[1] = 0;
+    if (j == my - 2 && (d.bc[3] == 2 || d.bc[3] == 12)) tmp[1] = 0;
+    if (j == 0 && d.bc[2] == 12) tmp[1] = 0;
+    if (d.bc[2] == 10 && j == 0 && iin && kin) tmp[1] = 0;
+    if ((d.bc[3] == 10 || d.bc[3] == -10) && j == my - 2 && iin && kin) tmp[1] = 0;
+    if ((kg == 0 && d.bc[4] == 1) || (kg == mz - 2 && d.bc[5] == 1)) tmp[2] = 0;
+    d.s[S_UC0][p] = tmp[0]; d.s[S_UC1][p] = tmp[1]; d.s[S_UC2][p] = tmp[2];
+  }
+};
+static int snes_core(vfs_ctx *c) {
+  RUN(g2l(c, grp(S_UC0, 3)));                                         // momentum.c:2293-2294
+  RUN(contra2cart(c));
+  RUN(ib_bc(c));
+  return formfunction2(c, 1, S_R0, 0.5);
+}
+extern "C" int vfs_formfunction_snes_dev(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+  ev_rec(c, 0);
+  { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+  RUN(snes_core(c));
+  ev_rec(c, 1);
+  return vfs_sync(c);
+}
+extern "C" int vfs_formfunction_snes(vfs_ctx *c, const double *x, double *fout) {
+  if (!c || !x || !fout) return VFS_ERR_ARG;
+  ev_rec(c, 0);
+  RUN(h2d_stage(c, x, 3));
+  { UnpackX f = {c->d, c->stage}; RUN(launch(c, box_owned(c), f)); }
+  RUN(snes_core(c));
+  { PackAoS f = {c->d, c->stage, S_R0, 3}; RUN(launch(c, box_owned(c), f)); }
+  ev_rec(c, 1);
+  return d2h_stage(c, fout, 3);
+}
+
+// ---- LES ---------------------------------------------------------------------------------------------------
+static int zero_scalars(vfs_ctx *c, int s0, int n) {
+#ifndef VFS_EMU
+  CK(cudaMemsetAsync(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double), c->stream));
+#else
+  memset(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double));
+#endif
+  return 0;
+}
+static int les_cs(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
+  if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
+  if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
+  RUN(zero_scalars(c, S_AX0, 13));
+  { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
+  Grp g1 = grp(S_AX0, 13);
+  RUN(g2l(c, g1));                                                    // les.c:254-267
+  if (any_per(c)) RUN(node_copy(c, g1));                              // les.c:275-306
+  ev_rec(c, 4);
+  { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
+  ev_rec(c, 5);
+  Grp g2 = grp(S_LM, 2);
+  RUN(g2l(c, g2));                                                    // les.c:675-678
+  if (any_per(c)) RUN(node_copy(c, g2));
+  { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
+  { LesClip f = {d}; RUN(launch(c, box_owned(c), f)); }              // les.c:967-980
+  Grp g3 = grp(S_CS, 1);
+  RUN(g2l(c, g3));                                                    // les.c:1026-1027
+  if (any_per(c)) RUN(node_copy(c, g3));
+  return 0;
+}
+static int les_nut(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  { NuT f = {d}; RUN(launch(c, box_interior(c), f)); }
+  Grp g = grp(S_NUT, 1);
+  RUN(g2l(c, g));                                                     // les.c:1320-1321
+  if (any_per(c)) RUN(node_copy(c, g));
+  return 0;
+}
+extern "C" int vfs_les_cs(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_cs(c)); return vfs_sync(c); }
+extern "C" int vfs_les_nut(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_nut(c)); return vfs_sync(c); }
+
+// one cell-update unit: Flow_Solver's LES block (solvers.c:365-371) followed by one
+// residual evaluation
+extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+  ev_rec(c, 0);
+  RUN(g2l(c, grp(S_UC0, 3)));
+  RUN(contra2cart(c));
+  if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
+  { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+  RUN(snes_core(c));
+  ev_rec(c, 1);
+  return vfs_sync(c);
+}

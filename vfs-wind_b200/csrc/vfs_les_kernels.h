@@ -1,0 +1,257 @@
+// vfs_les_kernels.h — dynamic Smagorinsky constant and eddy viscosity
+// (Source/les.c:75-1141 Compute_Smagorinsky_Constant_1, :1143-1361 Compute_eddy_viscosity_LES;
+// helpers Source/k-omega.c:313-618 Compute_du_center/Compute_du_dxyz, Source/rhs2.c:499-523
+// integrate_testfilter_simpson, :419-441 integrate_testfilter_ik, :595-611 covariant metrics).
+//
+// The 27-point Simpson filters are accumulated on the fly in the reference's summation order
+// (k-offset outer, j, i inner; term (s*w)*v, rhs2.c:510-520) so no 3x3x3 stack arrays are needed.
+// Clark terms (les.c:420-428) are never used when clark=0 and are not computed.
+#ifndef VFS_LES_KERNELS_H
+#define VFS_LES_KERNELS_H
+#include "vfs_common.h"
+#include "vfs_rhs_kernels.h"
+
+// centre difference along stride s (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
+VFS_HD double dcen(const double *u, const double *nv, long p, long s, int c, int m, int per, int lowc) {
+  if (nv[p + s] > VFS_SOLID || (!per && c == m - 2)) return u[p] - u[p - s];
+  else if (nv[p - s] > VFS_SOLID || (!per && c == lowc)) return u[p + s] - u[p];
+  else return (u[p + s] - u[p - s]) * 0.5;
+}
+
+// velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)
+VFS_HD void grad_center(const VfsDev &d, int su, int i, int j, int kg, long p, double g[3][3]) {
+  const double *nv = d.s[S_NV];
+  const double ajc = d.s[S_AJ][p];
+  const double c0 = d.s[S_CSI0][p], c1 = d.s[S_CSI1][p], c2 = d.s[S_CSI2][p];
+  const double e0 = d.s[S_ETA0][p], e1 = d.s[S_ETA1][p], e2 = d.s[S_ETA2][p];
+  const double z0 = d.s[S_ZET0][p], z1 = d.s[S_ZET1][p], z2 = d.s[S_ZET2][p];
+  for (int a = 0; a < 3; a++) {
+    const double *u = d.s[su + a];
+    const double dc = dcen(u, nv, p, 1, i, d.mx, d.perx, 1);
+    const double de = dcen(u, nv, p, d.sj, j, d.my, d.pery, 1);
+    const double dz = dcen(u, nv, p, d.sk, kg, d.mz, d.perz, 0);
+    g[a][0] = (dc * c0 + de * e0 + dz * z0) * ajc;
+    g[a][1] = (dc * c1 + de * e1 + dz * z1) * ajc;
+    g[a][2] = (dc * c2 + de * e2 + dz * z2) * ajc;
+  }
+}
+
+VFS_HD double sabs_of(const double g[3][3]) {
+  const double Sxx = 0.5 * (g[0][0] + g[0][0]), Sxy = 0.5 * (g[0][1] + g[1][0]), Sxz = 0.5 * (g[0][2] + g[2][0]);
+  const double Syx = Sxy, Syy = 0.5 * (g[1][1] + g[1][1]), Syz = 0.5 * (g[1][2] + g[2][1]);
+  const double Szx = Sxz, Szy = Syz, Szz = 0.5 * (g[2][2] + g[2][2]);
+  return sqrt(2.0 * (Sxx * Sxx + Sxy * Sxy + Sxz * Sxz + Syx * Syx + Syy * Syy + Syz * Syz + Szx * Szx + Szy * Szy + Szz * Szz));
+}
+
+VFS_HD double simpson_w(int r, int q, int pp) {
+  double s = 1.0;
+  if (r == 0) s *= 4.;
+  if (q == 0) s *= 4.;
+  if (pp == 0) s *= 4.;
+  return s;
+}
+
+// les.c:199-246: grad u, |S| and the test-filtered velocity
+struct LesPass1 {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
+    if (nv[p] > 1.1) return;
+    double g[3][3];
+    grad_center(d, S_U0, i, j, kg, p, g);
+    d.s[S_SABS][p] = sabs_of(g);
+    for (int a = 0; a < 3; a++) { d.s[S_AX0 + 3 * a][p] = g[a][0]; d.s[S_AX0 + 3 * a + 1][p] = g[a][1]; d.s[S_AX0 + 3 * a + 2][p] = g[a][2]; }
+    double uf[3];
+    if (d.testfilter_ik) {
+      for (int a = 0; a < 3; a++) {
+        const double *u = d.s[S_U0 + a];
+        uf[a] = ((u[p - d.sk - 1] + u[p + d.sk - 1] + u[p - d.sk + 1] + u[p + d.sk + 1]) + 4. * (u[p - d.sk] + u[p - 1] + u[p + d.sk] + u[p + 1]) + 16. * u[p]) / 36.;
+      }
+    } else {
+      double ws = 0, vs[3] = {0, 0, 0};
+      for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
+        const long n = p + r * d.sk + q * d.sj + pp;
+        const double w = (nv[n] > 0.1) ? 0. : 1. / aj[n];
+        const double sw = simpson_w(r, q, pp) * w;
+        ws += sw;
+        for (int a = 0; a < 3; a++) vs[a] += sw * d.s[S_U0 + a][n];
+      }
+      for (int a = 0; a < 3; a++) uf[a] = vs[a] / ws;
+    }
+    for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = uf[a];
+  }
+};
+
+// les.c:308-669: Germano identity contracted with the covariant metric tensor -> LM, MM
+struct LesPass2 {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
+    if (nv[p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
+    const double ajc = aj[p];
+    const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
+    const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
+    const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
+
+    // filtered products <U_i u_j> (9) and <|S| S_ij> (6 unique), sum of weights and of w*coef
+    double ws = 0, sum_weight = 0, Uu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, SS[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
+      const long n = p + r * d.sk + q * d.sj + pp;
+      const double w = (nv[n] > 0.1) ? 0. : 1. / aj[n];
+      const double sim = simpson_w(r, q, pp);
+      sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));   // coef table les.c:441-451
+      const double u[3] = {d.s[S_U0][n], d.s[S_U1][n], d.s[S_U2][n]};
+      const double U[3] = {u[0] * d.s[S_CSI0][n] + u[1] * d.s[S_CSI1][n] + u[2] * d.s[S_CSI2][n],
+                           u[0] * d.s[S_ETA0][n] + u[1] * d.s[S_ETA1][n] + u[2] * d.s[S_ETA2][n],
+                           u[0] * d.s[S_ZET0][n] + u[1] * d.s[S_ZET1][n] + u[2] * d.s[S_ZET2][n]};
+      const double S = d.s[S_SABS][n];
+      const double ax0 = d.s[S_AX0][n], ax1 = d.s[S_AX1][n], ax2 = d.s[S_AX2][n];
+      const double ay0 = d.s[S_AY0][n], ay1 = d.s[S_AY1][n], ay2 = d.s[S_AY2][n];
+      const double az0 = d.s[S_AZ0][n], az1 = d.s[S_AZ1][n], az2 = d.s[S_AZ2][n];
+      const double s6[6] = {0.5 * (ax0 + ax0), 0.5 * (ax1 + ay0), 0.5 * (ax2 + az0), 0.5 * (ay1 + ay1), 0.5 * (ay2 + az1), 0.5 * (az2 + az2)};
+      if (d.testfilter_ik) {
+        if (q != 0) continue;
+        const double c = (r == 0 ? 4. : 1.) * (pp == 0 ? 4. : 1.);   // 1,4,16 (rhs2.c:440)
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Uu[a][b] += c * (U[a] * u[b]);
+        for (int a = 0; a < 6; a++) SS[a] += c * (s6[a] * S);
+      } else {
+        const double sw = sim * w;
+        ws += sw;
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Uu[a][b] += sw * (U[a] * u[b]);
+        for (int a = 0; a < 6; a++) SS[a] += sw * (s6[a] * S);
+      }
+    }
+    const double fdiv = d.testfilter_ik ? 36. : ws;
+    const double filter = pow(1. / ajc, 1. / 3.);
+    const double test_filter = d.testfilter_ik ? pow(5.0, 1. / 3.) * filter : pow(sum_weight, 1. / 3.);
+
+    const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
+    const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
+    double gh[3][3];
+    grad_center(d, S_UF0, i, j, kg, p, gh);
+    const double Sh[3][3] = {{0.5 * (gh[0][0] + gh[0][0]), 0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[0][2] + gh[2][0])},
+                             {0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[1][1] + gh[1][1]), 0.5 * (gh[1][2] + gh[2][1])},
+                             {0.5 * (gh[0][2] + gh[2][0]), 0.5 * (gh[1][2] + gh[2][1]), 0.5 * (gh[2][2] + gh[2][2])}};
+    const double S_hat = sabs_of(gh);
+    double Lij[3][3], SSh[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = Uu[a][b] / fdiv - _U[a] * _u[b];
+    SSh[0][0] = SS[0] / fdiv; SSh[0][1] = SSh[1][0] = SS[1] / fdiv; SSh[0][2] = SSh[2][0] = SS[2] / fdiv;
+    SSh[1][1] = SS[3] / fdiv; SSh[1][2] = SSh[2][1] = SS[4] / fdiv; SSh[2][2] = SS[5] / fdiv;
+
+    // covariant metric tensor G (les.c:607-622)
+    const double a11 = csi[0], a12 = csi[1], a13 = csi[2], a21 = eta[0], a22 = eta[1], a23 = eta[2], a31 = zet[0], a32 = zet[1], a33 = zet[2];
+    const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+    const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
+    const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
+    const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
+    double G[3][3];
+    G[0][0] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
+    G[1][1] = xeta * xeta + yeta * yeta + zeta * zeta;
+    G[2][2] = xzet * xzet + yzet * yzet + zzet * zzet;
+    G[0][1] = G[1][0] = xeta * xcsi + yeta * ycsi + zeta * zcsi;
+    G[0][2] = G[2][0] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
+    G[1][2] = G[2][1] = xeta * xzet + yeta * yzet + zeta * zzet;
+
+    double Mc[3][3], M[3][3];
+    const double tf2 = pow(test_filter, 2.), f2 = pow(filter, 2.);
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Mc[a][b] = -tf2 * S_hat * Sh[a][b] + f2 * SSh[a][b];
+    for (int a = 0; a < 3; a++) {
+      M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
+      M[a][1] = Mc[a][0] * eta[0] + Mc[a][1] * eta[1] + Mc[a][2] * eta[2];
+      M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
+    }
+    double num = 0, den = 0;
+    for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) num += Lij[b][a] * M[a][q] * G[b][q];
+    for (int m = 0; m < 3; m++) for (int n = 0; n < 3; n++) for (int l = 0; l < 3; l++) den += M[n][m] * M[n][l] * G[m][l];
+    d.s[S_LM][p] = num; d.s[S_MM][p] = den;
+  }
+};
+
+// les.c:716-796: Simpson-filter LM, MM (weights zeroed at solid cells and non-periodic domain
+// ghosts, with the J==0-only quirk of les.c:756), C = 0.5 LM/(MM + 1e-4), Cs = max(C,0)
+struct LesPass3 {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
+    if (nv[p] > 1.1) { d.s[S_CS][p] = 0; return; }
+    double ws = 0, lm = 0, mmv = 0;
+    for (int c = -1; c <= 1; c++) for (int b = -1; b <= 1; b++) for (int a = -1; a <= 1; a++) {
+      int I = i + a, J = j + b, K = kg + c;
+      const long n = p + c * d.sk + b * d.sj + a;
+      double w = 1. / aj[n];
+      if (nv[n] > 1.1) w = 0;
+      int da = a, db = b, dc = c;      // fetch offsets after the periodic remap
+      if (d.perx) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; }
+      else if (I == 0 || I == d.mx - 1) w = 0;
+      if (d.pery) { if (J == 0) db = b - 2; else if (J == d.my - 1) db = b + 2; }
+      else if (J == 0) w = 0;
+      if (d.perz) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; }
+      else if (K == 0 || K == d.mz - 1) w = 0;
+      const long f = p + dc * d.sk + db * d.sj + da;
+      const double sw = simpson_w(c, b, a) * w;
+      ws += sw; lm += sw * d.s[S_LM][f]; mmv += sw * d.s[S_MM][f];
+    }
+    double LM_avg, MM_avg;
+    if (d.testfilter_ik) {
+      // integrate_testfilter_simpson defers to the weight-free i-k rule (rhs2.c:504-506)
+      const double *L = d.s[S_LM], *M = d.s[S_MM];
+      // same remapped fetches, J offset 0 only
+      double l9 = 0, m9 = 0;
+      for (int c = -1; c <= 1; c++) for (int a = -1; a <= 1; a++) {
+        int I = i + a, K = kg + c, da = a, dc = c;
+        if (d.perx) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; }
+        if (d.perz) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; }
+        const long f = p + dc * d.sk + da;
+        const double cf = (c == 0 ? 4. : 1.) * (a == 0 ? 4. : 1.);
+        l9 += cf * L[f]; m9 += cf * M[f];
+      }
+      LM_avg = l9 / 36.; MM_avg = m9 / 36.;
+    } else { LM_avg = lm / ws; MM_avg = mmv / ws; }
+    const double C = 0.5 * LM_avg / (MM_avg + 1.e-4);
+    d.s[S_CS][p] = C > 0 ? C : 0;
+  }
+};
+
+// les.c:967-980 clip chain, over every owned node
+struct LesClip {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double nv = d.s[S_NV][p];
+    double cs = d.s[S_CS][p];
+    if (nv > 1.1 || kg == 0 || kg == d.mz - 1 || j == 0 || j == d.my - 1 || i == 0 || i == d.mx - 1) cs = 0;
+    else {
+      if (nv > 0.1 && nv < 1.1) cs = cs > 0.001 ? cs : 0.001;
+      cs = cs > 0 ? cs : 0;
+      cs = cs < d.max_cs ? cs : d.max_cs;
+    }
+    d.s[S_CS][p] = cs;
+  }
+};
+
+// les.c:1185-1211: nu_t = Cs * Delta^2 * |S|
+struct NuT {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV];
+    if (nv[p] > 1.1) { d.s[S_NUT][p] = 0; return; }
+    double g[3][3];
+    grad_center(d, S_U0, i, j, kg, p, g);
+    const double Sabs = sabs_of(g);
+    const double filter = pow(1. / d.s[S_AJ][p], 1. / 3.);
+    double v = d.s[S_CS][p] * pow(filter, 2.0) * Sabs;
+    if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
+    d.s[S_NUT][p] = v;
+  }
+};
+
+#endif

@@ -1,0 +1,240 @@
+// vfs_rhs_kernels.h — Formfunction_2 (Source/momentum.c:454-2013) and the residual assembly of
+// FormFunction_SNES (Source/momentum.c:2237-2336); difference helpers follow Compute_du_i/j/k
+// (Source/k-omega.c:56-311, global `solid = 0.1`, k-omega.c:19).
+//
+// Staged formulation (round 1): face-flux kernel -> Fp kernel -> projection/assembly kernel with
+// the face fluxes and Fp held in HBM work arrays, ghost refreshes in between exactly where the
+// reference has DALocalToLocal.  Face metrics are recomputed from centre metrics (NEWMETRIC).
+#ifndef VFS_RHS_KERNELS_H
+#define VFS_RHS_KERNELS_H
+#include "vfs_common.h"
+#include "vfs_c2c_kernels.h"
+
+#define VFS_SOLID 0.1
+
+// tangential difference of scalar plane u along stride st at the face between p and pn
+VFS_HD double dtan(const double *u, const double *nv, long p, long pn, long st) {
+  if (nv[p + st] > VFS_SOLID || nv[pn + st] > VFS_SOLID) return (u[pn] + u[p] - u[pn - st] - u[p - st]) * 0.5;
+  else if (nv[p - st] > VFS_SOLID || nv[pn - st] > VFS_SOLID) return (u[pn + st] + u[p + st] - u[pn] - u[p]) * 0.5;
+  else return (u[pn + st] + u[p + st] - u[pn - st] - u[p - st]) * 0.25;
+}
+
+// One face family.  D = 0/1/2 for i-/j-/k-faces; the face sits between node p and p + stride(D)
+// and is stored at p ("upper integer node", momentum.c:508-509).
+template <int D> struct FaceFlux {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long st[3] = {1, d.sj, d.sk};
+    const long sn = st[D];
+    const int c = (D == 0 ? i : (D == 1 ? j : kg));
+    const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
+    const int per = (D == 0 ? d.perx : (D == 1 ? d.pery : d.perz));
+    const long p = d.idx(i, j, k), pn = p + sn;
+    const double *nv = d.s[S_NV];
+    const double *U[3] = {d.s[S_U0], d.s[S_U1], d.s[S_U2]};
+
+    // face metrics (metrics.c:589-592 and j/k twins)
+    const V3 cs = face3(d, S_CSI0, p, pn), et = face3(d, S_ETA0, p, pn), ze = face3(d, S_ZET0, p, pn);
+    const double ajc = 2. / (1. / d.s[S_AJ][p] + 1. / d.s[S_AJ][pn]);
+    const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
+
+    // du[a][b] = d u_a / d xi_b  (b: csi, eta, zet)
+    double du[3][3];
+    for (int a = 0; a < 3; a++) {
+      for (int b = 0; b < 3; b++) {
+        if (b == D) du[a][b] = U[a][pn] - U[a][p];
+        else du[a][b] = dtan(U[a], nv, p, pn, st[b]);
+      }
+    }
+    const double g1 = cs.x * n.x + cs.y * n.y + cs.z * n.z;
+    const double g2 = et.x * n.x + et.y * n.y + et.z * n.z;
+    const double g3 = ze.x * n.x + ze.y * n.y + ze.z * n.z;
+    // r[a][b] = du_a/dx_b * J   (momentum.c:686-696)
+    double r[3][3];
+    for (int a = 0; a < 3; a++) {
+      r[a][0] = du[a][0] * cs.x + du[a][1] * et.x + du[a][2] * ze.x;
+      r[a][1] = du[a][0] * cs.y + du[a][1] * et.y + du[a][2] * ze.y;
+      r[a][2] = du[a][0] * cs.z + du[a][1] * et.z + du[a][2] * ze.z;
+    }
+
+    // ---- convective flux (momentum.c:700-813) ----
+    long pL = p - sn, pR = p + 2 * sn;
+    if (c == 0 || c == m - 2) {
+      if (per && c == m - 2) pR = p + 4 * sn;          // index m+2
+      else if (per && c == 0) pL = p - 3 * sn;         // index -3
+      else pL = p, pR = pn;
+    } else if (nv[pL] + nv[pR] > 0.1) pL = p, pR = pn;
+    if (d.second_order) pL = p, pR = pn;
+
+    const double *UC = d.s[S_UC0 + D];
+    double ucon = UC[p];
+    if (per && c == 0) ucon = UC[p - 2 * sn];
+    if (D == 2 && c == m - 2 && d.bc[5] == 4 && (int)nv[p] == 0) ucon = UC[p - sn];
+    const double up = -0.5 * (ucon + fabs(ucon));
+    const double um = -0.5 * (ucon - fabs(ucon));
+    double fc[3];
+    if (d.immersed && c != m - 2 && nv[p] > 0.1) {
+      for (int a = 0; a < 3; a++)
+        fc[a] = um * (0.125 * (-U[a][p + 2 * sn] - 2. * U[a][pn] + 3. * U[a][p]) + U[a][pn]) +
+                up * (0.125 * (-U[a][p] - 2. * U[a][p] + 3. * U[a][pn]) + U[a][p]);
+    } else if (d.immersed && c != 0 && nv[pn] > 0.1) {
+      for (int a = 0; a < 3; a++)
+        fc[a] = um * (0.125 * (-U[a][pn] - 2. * U[a][pn] + 3. * U[a][p]) + U[a][pn]) +
+                up * (0.125 * (-U[a][p - sn] - 2. * U[a][p] + 3. * U[a][pn]) + U[a][p]);
+    } else if (d.second_order) {
+      for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.5 * (U[a][p] + U[a][pn]);
+    } else {
+      for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.0625 * (-U[a][pL] + 9. * U[a][p] + 9. * U[a][pn] - U[a][pR]);
+    }
+    if (nv[p] + nv[pn] > 0.1 && (d.immersed == 3 || !d.immersed)) fc[0] = fc[1] = fc[2] = 0;
+
+    // ---- viscous + SGS flux (momentum.c:856-902) ----
+    const double nu = 1. / d.ren;
+    double fv[3] = {0, 0, 0};
+    if (d.les) {
+      const double *nt = d.s[S_NUT];
+      double nu_t;
+      if ((c == 0 && !per) || nv[p] > 0.1) nu_t = nt[pn];
+      else if ((c == m - 2 && !per) || nv[pn] > 0.1) nu_t = nt[p];
+      else nu_t = 0.5 * (nt[p] + nt[pn]);
+      for (int a = 0; a < 3; a++)
+        fv[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu_t;
+    }
+    if (d.laplacian) {
+      for (int a = 0; a < 3; a++)
+        fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + 0. * n.x + 0. * n.y + 0. * n.z) * ajc * nu;
+    } else {
+      for (int a = 0; a < 3; a++)
+        fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu;
+    }
+    const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D;
+    for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
+  }
+};
+
+// momentum.c:1548-1678: flux divergence with 4th-order correction + viscous divergence -> Fp
+struct FpCell {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long st[3] = {1, d.sj, d.sk};
+    const int cc[3] = {i, j, kg}, mm[3] = {d.mx, d.my, d.mz}, pp[3] = {d.perx, d.pery, d.perz};
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV];
+    double div[3] = {0, 0, 0}, div4[3] = {0, 0, 0}, vis[3] = {0, 0, 0};
+    // accumulate in the reference's order: i-, j-, k-family
+    for (int a = 0; a < 3; a++) {
+      div[a] = (d.s[S_FC1 + a][p] - d.s[S_FC1 + a][p - 1] + d.s[S_FC2 + a][p] - d.s[S_FC2 + a][p - d.sj] + d.s[S_FC3 + a][p] - d.s[S_FC3 + a][p - d.sk]);
+      vis[a] = (d.s[S_FV1 + a][p] - d.s[S_FV1 + a][p - 1] + d.s[S_FV2 + a][p] - d.s[S_FV2 + a][p - d.sj] + d.s[S_FV3 + a][p] - d.s[S_FV3 + a][p - d.sk]);
+    }
+    if (!d.second_order) {
+      for (int D = 0; D < 3; D++) {
+        const int c = cc[D], m = mm[D], per = pp[D];
+        const long s = st[D];
+        long pR = p + s, pL = p - 2 * s;
+        double den = 3.;
+        if (c == 1) { if (per) pL = p - 4 * s; else pR = p, pL = p - s, den = 1.; }
+        else if (c == 2 || c == m - 3) { if (!per) pR = p, pL = p - s, den = 1.; }
+        else if (c == m - 2) { if (per) pR = p + 3 * s; else pR = p, pL = p - s, den = 1.; }
+        if (nv[p - s] + nv[p] + nv[p + s] > 0.1) pR = p, pL = p - s, den = 1.;
+        const double inv = 1. / den;
+        for (int a = 0; a < 3; a++) div4[a] += (d.s[S_FC1 + 3 * D + a][pR] - d.s[S_FC1 + 3 * D + a][pL]) * inv;
+      }
+      for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = (9. / 8.) * div[a] + (-1. / 8.) * div4[a] + vis[a];
+    } else {
+      for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = div[a] + vis[a];
+    }
+  }
+};
+
+// projection of Fp on the face area vectors (momentum.c:1733-1735) for one node; returns the
+// three contravariant components (before scale and masks)
+VFS_HD V3 project_fp(const VfsDev &d, long p) {
+  const double f0 = d.s[S_FP0][p], f1 = d.s[S_FP1][p], f2 = d.s[S_FP2][p];
+  const double aj = d.s[S_AJ][p];
+  V3 r;
+  {
+    long q = p + 1;
+    double iaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    r.x = (0.5 * (d.s[S_CSI0][p] * f0 + d.s[S_CSI1][p] * f1 + d.s[S_CSI2][p] * f2) +
+           0.5 * (d.s[S_CSI0][q] * d.s[S_FP0][q] + d.s[S_CSI1][q] * d.s[S_FP1][q] + d.s[S_CSI2][q] * d.s[S_FP2][q])) * iaj;
+  }
+  {
+    long q = p + d.sj;
+    double jaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    r.y = (0.5 * (d.s[S_ETA0][p] * f0 + d.s[S_ETA1][p] * f1 + d.s[S_ETA2][p] * f2) +
+           0.5 * (d.s[S_ETA0][q] * d.s[S_FP0][q] + d.s[S_ETA1][q] * d.s[S_FP1][q] + d.s[S_ETA2][q] * d.s[S_FP2][q])) * jaj;
+  }
+  {
+    long q = p + d.sk;
+    double kaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    r.z = (0.5 * (d.s[S_ZET0][p] * f0 + d.s[S_ZET1][p] * f1 + d.s[S_ZET2][p] * f2) +
+           0.5 * (d.s[S_ZET0][q] * d.s[S_FP0][q] + d.s[S_ZET1][q] * d.s[S_FP1][q] + d.s[S_ZET2][q] * d.s[S_FP2][q])) * kaj;
+  }
+  return r;
+}
+
+// masks of momentum.c:1833-1841 + boundary planes :1866-1938.  bit a set => component a zeroed.
+VFS_HD int rhs_mask(const VfsDev &d, int i, int j, int kg, long p) {
+  const int mx = d.mx, my = d.my, mz = d.mz;
+  if (i == 0 || i == mx - 1 || j == 0 || j == my - 1 || kg == 0 || kg == mz - 1) return 7;
+  const double *nv = d.s[S_NV];
+  int m = 0;
+  if (nv[p] + nv[p + 1] > 0.1 || (!d.perx && i == mx - 2)) m |= 1;
+  if (nv[p] + nv[p + d.sj] > 0.1 || (!d.pery && j == my - 2)) m |= 2;
+  if (nv[p] + nv[p + d.sk] > 0.1 || (!d.perz && kg == mz - 2)) m |= 4;
+  return m;
+}
+
+// Formfunction_2 tail: rhs[field s0] += scale * projection, then masks (in place)
+struct ProjectAdd {
+  VfsDev d; int s0; double scale;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const int m = rhs_mask(d, i, j, kg, p);
+    V3 r = mk3(0, 0, 0);
+    if (m != 7) r = project_fp(d, p);
+    d.s[s0][p] = (m & 1) ? 0. : d.s[s0][p] + scale * r.x;
+    d.s[s0 + 1][p] = (m & 2) ? 0. : d.s[s0 + 1][p] + scale * r.y;
+    d.s[s0 + 2][p] = (m & 4) ? 0. : d.s[s0 + 2][p] + scale * r.z;
+  }
+};
+
+// FormFunction_SNES assembly (momentum.c:2297-2331) fused with the projection:
+//   Rhs = mask( (-U + U_o)/dt + 0.5 R(U) ) + 0.5 RHS_o - dP [+ F_eul]        (time_coeff()==1)
+//   Rhs = mask( (-1.5U + 2U_o - 0.5U_rm1)/dt + R(U) ) - dP [+ F_eul]         (BDF2)
+// mask() = the Formfunction_2 zeroing, applied before the last three terms.
+struct ProjectSNES {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const int m = rhs_mask(d, i, j, kg, p);
+    V3 r = mk3(0, 0, 0);
+    if (m != 7) r = project_fp(d, p);
+    const double rr[3] = {r.x, r.y, r.z};
+    const double dt = d.dt;
+    for (int a = 0; a < 3; a++) {
+      double v;
+      if (m & (1 << a)) v = 0.;
+      else if (!d.bdf2) {
+        v = (-1. / dt) * d.s[S_UC0 + a][p];
+        v += (1. / dt) * d.s[S_UCO0 + a][p];
+        v += 0.5 * rr[a];
+      } else {
+        v = (-1.5 / dt) * d.s[S_UC0 + a][p];
+        v += (2. / dt) * d.s[S_UCO0 + a][p];
+        v += (-0.5 / dt) * d.s[S_UCM0 + a][p];
+        v += 1.0 * rr[a];
+      }
+      if (!d.bdf2) v += 0.5 * d.s[S_RO0 + a][p];
+      v += -1. * d.s[S_DP0 + a][p];
+      if (d.has_feul) v += 1. * d.s[S_FE0 + a][p];
+      d.s[S_R0 + a][p] = v;
+    }
+  }
+};
+
+#endif
