@@ -117,9 +117,12 @@ int vfs_rhs_les_fused(vfs_ctx *c);
 
 /* number of kernels launched by this context since creation (bench `gpu_launches`) */
 long vfs_launch_count(vfs_ctx *c);
-/* CUDA-event timing of the last compute call's dominant kernel group, in ms (0 if n/a):
- * which = 0 whole call, 1 flux kernels, 2 les pass2 */
+/* CUDA-event timing (ms, on the context's stream) of the most recent execution of a kernel
+ * group; 0 if it has not run.  Valid after vfs_sync / any synchronous entry point. */
+enum vfs_timer { VFS_T_TOTAL = 0, VFS_T_C2C, VFS_T_FLUX, VFS_T_FP, VFS_T_PROJECT, VFS_T_LES1, VFS_T_LES2, VFS_T_LES3, VFS_T_NUT, VFS_T_COUNT };
 double vfs_last_ms(vfs_ctx *c, int which);
+/* tuning switches: key 0 = use the fused RHS kernel when applicable (default 1) */
+int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,36 @@
+"""CPU (no GPU) checks of the kernel LOGIC: the kernel functors compiled for the host
+(tests/emu, -DVFS_EMU, test-only) against the oracle.  The -m gpu tests repeat these through the
+real CUDA library."""
+import pytest
+import parity_common as pc
+import emu_loader
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def emu(pkg):
+    return emu_loader.load(pkg.capi)
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (21, 17, 19)), ("c1_test10", (14, 10, 12))])
+def test_emulated_path_matches_reference(pkg, refdrv, emu, name, dims):
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = pc.run_parity(cfg, refdrv, lib=emu)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def test_emulated_flag_variants(pkg, refdrv, emu):
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15)
+    for extra in (dict(second_order=1), dict(laplacian=1), dict(immersed=3), dict(les=1), dict(les=0), dict(testfilter_ik=1),
+                  dict(kk_periodic=1, ii_periodic=0), dict(jj_periodic=1)):
+        cfg = dict(base)
+        cfg["flags"] = dict(base["flags"], **extra)
+        if extra.get("kk_periodic") or extra.get("jj_periodic"):
+            cfg["bctype"] = [1, 1, 1, 1, 100, 100] if extra.get("kk_periodic") else [100, 100, 100, 100, 5, 4]
+        err = pc.run_parity(cfg, refdrv, lib=emu)
+        assert err.pop("FormFunction_SNES_zero_pattern") == 0, extra
+        bad = {k: v for k, v in err.items() if not (v <= TOL)}
+        assert not bad, (extra, bad)

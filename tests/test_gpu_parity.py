@@ -1,0 +1,76 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs.  Tolerance (BASELINE.json north_star): relative 1e-12 of the field's max norm for Rhs,
+Ucat, Cs, nu_t; mask-driven zero patterns bit-exact."""
+import numpy as np
+import pytest
+import parity_common as pc
+
+TOL = 1e-12
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("c2_box256", (21, 17, 25)),      # ii+kk periodic, 4th-order central, dynamic Smagorinsky
+    ("c2_box256", (40, 33, 37)),
+    ("c3_turbine", (29, 21, 25)),     # IBM masks, QUICK at IB faces, inflow/outflow in k, F_eul
+    ("c3_turbine", (45, 30, 41)),
+    ("c1_test10", (24, 16, 20)),      # 2nd-order, laplacian (wall model excluded)
+]
+
+
+@pytest.mark.parametrize("name,dims", CASES)
+def test_path_matches_reference(pkg, refdrv, name, dims):
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = pc.run_parity(cfg, refdrv, device=0)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def test_flag_variants(pkg, refdrv):
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 25, 19, 23)
+    for extra in (dict(second_order=1), dict(laplacian=1), dict(immersed=3), dict(les=1), dict(les=0), dict(testfilter_ik=1),
+                  dict(kk_periodic=1, ii_periodic=0), dict(jj_periodic=1)):
+        cfg = dict(base)
+        cfg["flags"] = dict(base["flags"], **extra)
+        if extra.get("kk_periodic") or extra.get("jj_periodic"):
+            cfg["bctype"] = [1, 1, 1, 1, 100, 100] if extra.get("kk_periodic") else [100, 100, 100, 100, 5, 4]
+        err = pc.run_parity(cfg, refdrv, device=0)
+        assert err.pop("FormFunction_SNES_zero_pattern") == 0, extra
+        bad = {k: v for k, v in err.items() if not (v <= TOL)}
+        assert not bad, (extra, bad)
+
+
+def test_unsupported_flags_fail_loudly(pkg):
+    capi = pkg.capi
+    p = capi.make_params(16, 16, 16, dict(les=2, levelset=1), 100.0, 1e-3, [1] * 6)
+    with pytest.raises(capi.VfsError):
+        capi.VfsContext(p)
+
+
+def test_roundtrip_and_idempotence(pkg):
+    """Size-independent properties at a larger size: upload/download round trip is exact and a
+    second residual evaluation on the same X is bitwise identical (no hidden state drift)."""
+    capi, cases = pkg.capi, pkg.cases
+    cfg = cases.scaled(cases.CONFIGS["c2_box256"], 95, 63, 79)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+    xyz = cases.make_grid(cfg)
+    ctx.upload("COOR", xyz)
+    assert np.array_equal(ctx.download("COOR"), xyz)
+    ctx.FormMetrics()
+    met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+    assert np.all(met["aj"][1:-1, 1:-1, 1:-1] > 0)
+    f = cases.make_fields(cfg, met)
+    for k, n in (("nvert", "NVERT"), ("ucont", "UCONT"), ("ucat", "UCAT"), ("ucat_old", "UCAT_OLD"), ("ucont_o", "UCONT_O"), ("rhs_o", "RHS_O"), ("dp", "DP")):
+        ctx.upload(n, f[k])
+    ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+    F1 = ctx.FormFunction_SNES(f["ucont"])
+    F2 = ctx.FormFunction_SNES(f["ucont"])
+    assert np.array_equal(F1, F2)
+    assert np.isfinite(F1).all()
+    # boundary planes carry only 0.5*RHS_o - dP (momentum.c:1866-1938, 2322-2326)
+    exp = 0.5 * f["rhs_o"][0] - f["dp"][0]
+    assert np.allclose(F1[0], exp, rtol=0, atol=1e-15 * np.abs(exp).max())
+    cs = ctx.download("CS")
+    assert cs.min() >= 0 and cs.max() <= cfg["flags"]["max_cs"]
+    ctx.close()

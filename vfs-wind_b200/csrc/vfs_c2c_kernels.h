@@ -59,28 +59,32 @@ struct C2CGhostRules {
     if (!(i == 0 || i == mx - 1 || j == 0 || j == my - 1 || kg == 0 || kg == mz - 1)) return;
     long p = d.idx(i, j, k);
     const int *bc = d.bc;
+    // neighbours of an edge/corner node are boundary nodes themselves: read them from the
+    // snapshot (S_FP0..2) taken before this kernel, as the reference reads its lUcat copy
+    const int nb = (i == 0 || i == mx - 1) + (j == 0 || j == my - 1) + (kg == 0 || kg == mz - 1);
+    const int SU = nb >= 2 ? S_FP0 : S_U0;
     if ((int)(d.s[S_NV][p] + 0.1) == 3) { st3(d, S_U0, p, mk3(0, 0, 0)); return; }
     bool w = false; V3 u = mk3(0, 0, 0);
-    if (bc[3] == 13 && j == my - 1) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(a.x, -a.y, a.z); w = true; }
-    if (bc[3] == 14 && j == my - 1) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(a.x, a.y, -a.z); w = true; }
+    if (bc[3] == 13 && j == my - 1) { V3 a = ld3(d, SU, p - d.sj); u = mk3(a.x, -a.y, a.z); w = true; }
+    if (bc[3] == 14 && j == my - 1) { V3 a = ld3(d, SU, p - d.sj); u = mk3(a.x, a.y, -a.z); w = true; }
     if (bc[0] == 10 && i == 0 && j != 0 && kg != 0) { u = slip_ghost(d, p + 1, 0, -1.); w = true; }
     if (bc[1] == 10 && i == mx - 1 && j != 0 && kg != 0) { u = slip_ghost(d, p - 1, 0, 1.); w = true; }
     if (bc[2] == 10 && j == 0 && i != 0 && kg != 0) { u = slip_ghost(d, p + d.sj, 1, -1.); w = true; }
     if ((bc[3] == 10 || bc[3] == -10) && j == my - 1 && i != 0 && kg != 0) { u = slip_ghost(d, p - d.sj, 1, 1.); w = true; }
     bool solid_flag = false;
-    if (i == 0 && bc[0] == 1 && j != 0 && kg != 0) { V3 a = ld3(d, S_U0, p + 1); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
-    if (i == mx - 1 && bc[1] == 1 && j != 0 && kg != 0) { V3 a = ld3(d, S_U0, p - 1); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
-    if (j == 0 && bc[2] == 1 && i != 0 && kg != 0) { V3 a = ld3(d, S_U0, p + d.sj); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
-    if (j == my - 1 && bc[3] == 1 && i != 0 && kg != 0) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
-    if (kg == 0 && bc[4] == 1 && i != 0 && j != 0) { V3 a = ld3(d, S_U0, p + d.sk); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
-    if (kg == mz - 1 && bc[5] == 1 && i != 0 && j != 0) { V3 a = ld3(d, S_U0, p - d.sk); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (i == 0 && bc[0] == 1 && j != 0 && kg != 0) { V3 a = ld3(d, SU, p + 1); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (i == mx - 1 && bc[1] == 1 && j != 0 && kg != 0) { V3 a = ld3(d, SU, p - 1); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (j == 0 && bc[2] == 1 && i != 0 && kg != 0) { V3 a = ld3(d, SU, p + d.sj); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (j == my - 1 && bc[3] == 1 && i != 0 && kg != 0) { V3 a = ld3(d, SU, p - d.sj); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (kg == 0 && bc[4] == 1 && i != 0 && j != 0) { V3 a = ld3(d, SU, p + d.sk); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
+    if (kg == mz - 1 && bc[5] == 1 && i != 0 && j != 0) { V3 a = ld3(d, SU, p - d.sk); u = mk3(-a.x, -a.y, -a.z); w = true; solid_flag = true; }
     if (j == my - 1 && bc[3] == 2) {   // cavity lid
-      V3 a = solid_flag ? ld3(d, S_UO0, p - d.sj) : ld3(d, S_U0, p - d.sj);
+      V3 a = solid_flag ? ld3(d, S_UO0, p - d.sj) : ld3(d, SU, p - d.sj);
       u = mk3(2.0 - a.x, -a.y, -a.z); w = true;
     }
-    if (j == 0 && bc[2] == 12) { V3 a = ld3(d, S_U0, p + d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
-    if (j == my - 1 && bc[3] == 12) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
-    if (bc[3] == 4 && j == my - 1 && i != 0 && i != mx - 1 && kg != 0 && kg != mz - 1) { u = ld3(d, S_U0, p - d.sj); w = true; }
+    if (j == 0 && bc[2] == 12) { V3 a = ld3(d, SU, p + d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
+    if (j == my - 1 && bc[3] == 12) { V3 a = ld3(d, SU, p - d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
+    if (bc[3] == 4 && j == my - 1 && i != 0 && i != mx - 1 && kg != 0 && kg != mz - 1) { u = ld3(d, SU, p - d.sj); w = true; }
     if (bc[5] == 4 && kg == mz - 1 && i != 0 && i != mx - 1 && j != 0 && j != my - 1) {
       if (d.s[S_NV][p - d.sk] > 0.1 || solid_flag) { u = mk3(0, 0, 0); w = true; }
     }

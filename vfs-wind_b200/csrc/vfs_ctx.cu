@@ -44,8 +44,8 @@ struct vfs_ctx {
   vfs_halo_fn halo_fn = nullptr; void *halo_user = nullptr;
   long launches = 0;
   std::string err;
-  cudaEvent_t ev[6] = {0, 0, 0, 0, 0, 0};
-  bool ev_valid[3] = {false, false, false};
+  cudaEvent_t ev[2 * VFS_T_COUNT] = {0};
+  bool ev_valid[VFS_T_COUNT] = {false};
   int fused = 1;                 // use the fused smem-tiled RHS kernel when applicable
 };
 
@@ -174,7 +174,7 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   if (e != cudaSuccess) { g_create_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); delete c; return VFS_ERR_CUDA; }
   cudaMemset(c->pool, 0, bytes);
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true;
-  for (int q = 0; q < 6; q++) cudaEventCreate(&c->ev[q]);
+  for (int q = 0; q < 2 * VFS_T_COUNT; q++) cudaEventCreate(&c->ev[q]);
 #else
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
 #endif
@@ -189,7 +189,7 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->pool); cudaFree(c->stage);
   if (c->own_stream) cudaStreamDestroy(c->stream);
-  for (int q = 0; q < 6; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
+  for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
   free(c->pool); free(c->stage);
 #endif
@@ -231,7 +231,7 @@ extern "C" void *vfs_scalar_ptr(vfs_ctx *c, int sid) { if (!c || sid < 0 || sid 
 extern "C" long vfs_launch_count(vfs_ctx *c) { return c ? c->launches : 0; }
 extern "C" double vfs_last_ms(vfs_ctx *c, int which) {
 #ifndef VFS_EMU
-  if (!c || which < 0 || which > 2 || !c->ev_valid[which]) return 0;
+  if (!c || which < 0 || which >= VFS_T_COUNT || !c->ev_valid[which]) return 0;
   float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[2 * which], c->ev[2 * which + 1]) != cudaSuccess) return 0; return ms;
 #else
   return 0;
@@ -315,7 +315,9 @@ static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
   Grp gu = grp(S_U0, 3);
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // rhs.c:129-156
+  ev_rec(c, 2 * VFS_T_C2C);
   { C2CInterior f = {d}; RUN(launch(c, box_interior(c), f)); }      // rhs.c:158-247
+  ev_rec(c, 2 * VFS_T_C2C + 1);
   RUN(g2l(c, gu));
   if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:254-291
   RUN(for_boundary_planes(c, run_snapshot, 0));                      // lUcat snapshot read by the rules
@@ -357,25 +359,29 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const VfsDev &d = c->d;
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
-  ev_rec(c, 2);
+  ev_rec(c, 2 * VFS_T_FLUX);
   if (c->fused && fused_rhs_applicable(d)) {
     RUN(launch_fused_rhs(c->stream, d, mode, s0, scale, &c->launches));
-    ev_rec(c, 3);
+    ev_rec(c, 2 * VFS_T_FLUX + 1);
     return 0;
   }
   { FaceFlux<0> f = {d}; Box b = {0, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
   { FaceFlux<1> f = {d}; Box b = {1, d.mx - 1, 0, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
   { FaceFlux<2> f = {d}; Box b = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2}; RUN(launch(c, b, f)); }
-  ev_rec(c, 3);
+  ev_rec(c, 2 * VFS_T_FLUX + 1);
   Grp gf = grp(S_FC1, 18);
   RUN(g2l(c, gf));                                                    // momentum.c:1458-1496
   if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
+  ev_rec(c, 2 * VFS_T_FP);
   { FpCell f = {d}; RUN(launch(c, box_interior(c), f)); }            // momentum.c:1548-1678
+  ev_rec(c, 2 * VFS_T_FP + 1);
   Grp gp = grp(S_FP0, 3);
   RUN(g2l(c, gp));
   if (any_per(c)) RUN(node_copy(c, gp));                              // momentum.c:1687-1713
+  ev_rec(c, 2 * VFS_T_PROJECT);
   if (mode == 0) { ProjectAdd f = {d, s0, scale}; RUN(launch(c, box_owned(c), f)); }
   else { ProjectSNES f = {d}; RUN(launch(c, box_owned(c), f)); }
+  ev_rec(c, 2 * VFS_T_PROJECT + 1);
   return 0;
 }
 extern "C" int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale) {
@@ -412,20 +418,20 @@ static int snes_core(vfs_ctx *c) {
 }
 extern "C" int vfs_formfunction_snes_dev(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
-  ev_rec(c, 0);
+  ev_rec(c, 2 * VFS_T_TOTAL);
   { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
   RUN(snes_core(c));
-  ev_rec(c, 1);
+  ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);
 }
 extern "C" int vfs_formfunction_snes(vfs_ctx *c, const double *x, double *fout) {
   if (!c || !x || !fout) return VFS_ERR_ARG;
-  ev_rec(c, 0);
+  ev_rec(c, 2 * VFS_T_TOTAL);
   RUN(h2d_stage(c, x, 3));
   { UnpackX f = {c->d, c->stage}; RUN(launch(c, box_owned(c), f)); }
   RUN(snes_core(c));
   { PackAoS f = {c->d, c->stage, S_R0, 3}; RUN(launch(c, box_owned(c), f)); }
-  ev_rec(c, 1);
+  ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return d2h_stage(c, fout, 3);
 }
 
@@ -444,17 +450,21 @@ static int les_cs(vfs_ctx *c) {
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   RUN(zero_scalars(c, S_AX0, 13));
+  ev_rec(c, 2 * VFS_T_LES1);
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
+  ev_rec(c, 2 * VFS_T_LES1 + 1);
   Grp g1 = grp(S_AX0, 13);
   RUN(g2l(c, g1));                                                    // les.c:254-267
   if (any_per(c)) RUN(node_copy(c, g1));                              // les.c:275-306
-  ev_rec(c, 4);
+  ev_rec(c, 2 * VFS_T_LES2);
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
-  ev_rec(c, 5);
+  ev_rec(c, 2 * VFS_T_LES2 + 1);
   Grp g2 = grp(S_LM, 2);
   RUN(g2l(c, g2));                                                    // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
+  ev_rec(c, 2 * VFS_T_LES3);
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
+  ev_rec(c, 2 * VFS_T_LES3 + 1);
   { LesClip f = {d}; RUN(launch(c, box_owned(c), f)); }              // les.c:967-980
   Grp g3 = grp(S_CS, 1);
   RUN(g2l(c, g3));                                                    // les.c:1026-1027
@@ -463,7 +473,9 @@ static int les_cs(vfs_ctx *c) {
 }
 static int les_nut(vfs_ctx *c) {
   const VfsDev &d = c->d;
+  ev_rec(c, 2 * VFS_T_NUT);
   { NuT f = {d}; RUN(launch(c, box_interior(c), f)); }
+  ev_rec(c, 2 * VFS_T_NUT + 1);
   Grp g = grp(S_NUT, 1);
   RUN(g2l(c, g));                                                     // les.c:1320-1321
   if (any_per(c)) RUN(node_copy(c, g));
@@ -476,12 +488,12 @@ extern "C" int vfs_les_nut(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_nut
 // residual evaluation
 extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
-  ev_rec(c, 0);
+  ev_rec(c, 2 * VFS_T_TOTAL);
   RUN(g2l(c, grp(S_UC0, 3)));
   RUN(contra2cart(c));
   if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
   { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
   RUN(snes_core(c));
-  ev_rec(c, 1);
+  ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);
 }
