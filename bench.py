@@ -90,6 +90,7 @@ def workload_cfg(cases, name, nranks):
     cfg = dict(cases.CONFIGS[name])
     if nranks > 1:                       # weak scaling: fixed 256-plane slab per GPU
         cfg["KM"] = (cfg["KM"] + 1) * nranks - 1
+        cfg["weak_k"] = True          # keep the cell size: domain length in z grows with N
     return cfg
 
 

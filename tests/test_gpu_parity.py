@@ -74,3 +74,16 @@ def test_roundtrip_and_idempotence(pkg):
     cs = ctx.download("CS")
     assert cs.min() >= 0 and cs.max() <= cfg["flags"]["max_cs"]
     ctx.close()
+
+
+def test_multi_gpu_bitwise_equal_single_gpu():
+    """k-slab decomposition over all visible GPUs (NCCL halos) == single-GPU result, bitwise."""
+    import os, subprocess, sys, torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert "MULTIGPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

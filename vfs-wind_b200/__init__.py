@@ -4,3 +4,10 @@ The directory name contains a hyphen (it mirrors the reference's repository name
 loaded by path: `from __graft_entry__ import load_package; pkg = load_package()`.
 """
 from . import capi, cases  # noqa: F401
+
+
+def __getattr__(name):
+    if name == "halo":            # imports torch; only needed for multi-GPU runs
+        import importlib
+        return importlib.import_module(__name__ + ".halo")
+    raise AttributeError(name)

@@ -38,38 +38,48 @@ def scaled(cfg, IM, JM, KM):
     return c
 
 
-def make_grid(cfg):
-    """Node coordinates, shape (mz, my, mx, 3); the last index in each direction is unused (zero),
-    exactly as the reference leaves it (Source/init.c:340-376 fills only IM*JM*KM nodes)."""
+def make_grid(cfg, kofs=0, nzl=None):
+    """Node coordinates, shape (nzl, my, mx, 3) for the k-planes [kofs, kofs+nzl) (default: all);
+    the last index in each direction is unused (zero), exactly as the reference leaves it
+    (Source/init.c:340-376 fills only IM*JM*KM nodes)."""
     IM, JM, KM = cfg["IM"], cfg["JM"], cfg["KM"]
     mx, my, mz = IM + 1, JM + 1, KM + 1
+    if nzl is None:
+        nzl = mz - kofs
     xi = np.arange(IM) / (IM - 1.0)
     et = np.arange(JM) / (JM - 1.0)
     ze = np.arange(KM) / (KM - 1.0)
+    ksel = np.arange(kofs, min(kofs + nzl, KM))
     if cfg["grid"] == "test10":
         # shipped xyz.dat: x in [-0.6,0.6], y in [0,0.4], z in [0,2], all uniform (file values agree to 3e-15)
         X = -0.6 + 1.2 * xi
         Y = 0.4 * et
         Z = 2.0 * ze
-        x, y, z = np.meshgrid(X, Y, Z, indexing="ij")
+        x, y, z = np.meshgrid(X, Y, Z[ksel], indexing="ij")
     else:
-        Lx, H, Lz = 2.0, 1.0, 3.0
+        Lx, H = 2.0, 1.0
+        Lz = 3.0 * (KM + 1) / 256.0 if cfg.get("weak_k") else 3.0
         beta = 2.0
         X = Lx * xi
         Y = H * (1.0 + np.tanh(beta * (et - 1.0)) / np.tanh(beta))        # wall-clustered at y=0
-        r = 1.02 ** (np.arange(KM) * 64.0 / KM)
+        r = 1.0 + 0.3 * np.sin(2 * np.pi * (np.arange(KM) + 0.5) / KM)      # smooth, periodic stretching in z
         Z = Lz * np.concatenate([[0.0], np.cumsum(0.5 * (r[1:] + r[:-1]))]) / np.sum(0.5 * (r[1:] + r[:-1]))
-        x, y, z = np.meshgrid(X, Y, Z, indexing="ij")
+        x, y, z = np.meshgrid(X, Y, Z[ksel], indexing="ij")
         a = 0.02 * Lx
         # smooth warp so that all nine metric components are non-zero; periodic in x and z
         x = x + a * np.sin(2 * np.pi * y / H) * np.sin(2 * np.pi * z / Lz)
         y = y + 0.01 * H * np.sin(2 * np.pi * x / Lx) * np.sin(np.pi * y / H) * np.cos(2 * np.pi * z / Lz)
         z = z + 0.01 * Lz * np.sin(2 * np.pi * x / Lx) * np.sin(np.pi * y / H)
-    xyz = np.zeros((mz, my, mx, 3))
-    xyz[:KM, :JM, :IM, 0] = x.transpose(2, 1, 0)
-    xyz[:KM, :JM, :IM, 1] = y.transpose(2, 1, 0)
-    xyz[:KM, :JM, :IM, 2] = z.transpose(2, 1, 0)
+    xyz = np.zeros((nzl, my, mx, 3))
+    n = len(ksel)
+    xyz[:n, :JM, :IM, 0] = x.transpose(2, 1, 0)
+    xyz[:n, :JM, :IM, 1] = y.transpose(2, 1, 0)
+    xyz[:n, :JM, :IM, 2] = z.transpose(2, 1, 0)
     return xyz
+
+
+def make_grid_slab(cfg, kofs, nzl):
+    return make_grid(cfg, kofs, nzl)
 
 
 def _smooth121(a, axes=(0, 1, 2)):

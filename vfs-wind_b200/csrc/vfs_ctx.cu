@@ -114,8 +114,12 @@ static int g2l(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return halo_k(c, 
 static int node_copy(vfs_ctx *c, const Grp &g) {
   const VfsDev &d = c->d;
   NodeCopy f = {d, g};
-  if (d.perx) { Box b0 = {0, 1, 0, d.my, 0, d.nzl}, b1 = {d.mx - 1, d.mx, 0, d.my, 0, d.nzl}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-  if (d.pery) { Box b0 = {0, d.mx, 0, 1, 0, d.nzl}, b1 = {0, d.mx, d.my - 1, d.my, 0, d.nzl}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  // k-ghost planes received from a neighbouring rank across an INTERIOR slab boundary are owned
+  // planes in a single-rank run, where this copy updates them; apply it there too so that the
+  // result does not depend on the number of ranks (wrap-around ghosts stay stale, as in 1 rank).
+  const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;
+  if (d.perx) { Box b0 = {0, 1, 0, d.my, ka, kb}, b1 = {d.mx - 1, d.mx, 0, d.my, ka, kb}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  if (d.pery) { Box b0 = {0, d.mx, 0, 1, ka, kb}, b1 = {0, d.mx, d.my - 1, d.my, ka, kb}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
   if (d.perz) {
     if (d.kofs == 0) { Box b0 = {0, d.mx, 0, d.my, 0, 1}; RUN(launch(c, b0, f)); }
     if (d.kofs + d.nzl == d.mz) { Box b1 = {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}; RUN(launch(c, b1, f)); }
