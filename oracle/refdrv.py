@@ -15,6 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_ref", "libvfsref.so")
+_GLOBALS_JSON = os.path.join(HERE, "_ref", "globals.json")
 
 _CT = {"int": C.c_int, "PetscInt": C.c_int, "PetscTruth": C.c_int, "double": C.c_double, "PetscReal": C.c_double}
 _lib = None
@@ -29,7 +30,7 @@ def lib():
     global _lib, _globals
     if _lib is None:
         _lib = C.CDLL(SO)
-        _globals = json.load(open(os.path.join(HERE, "_ref", "globals.json")))
+        _globals = json.load(open(_GLOBALS_JSON))
         L = _lib
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_int] * 3
@@ -59,6 +60,8 @@ def lib():
 
 def set_global(name, value):
     L = lib()
+    if name not in _globals:      # a glue build only defines the switches the product reads
+        return
     t = _globals[name]
     _CT[t].in_dll(L, name).value = value
 

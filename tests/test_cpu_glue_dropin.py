@@ -1,0 +1,73 @@
+"""Drop-in boundary test: the product's host glue (vfs-wind_b200/host/vfs_petsc_glue.cpp)
+exports the reference's own function names and signatures.  The SAME driver harness that runs the
+reference objects (oracle/harness.cpp) is linked against the glue instead, and the UserCtx Vecs it
+leaves behind are compared with the reference run.  CPU variant: glue -> test-only kernel
+emulation; the -m gpu twin (test_gpu_glue_dropin.py) links the CUDA library."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import parity_common as pc
+
+TOL = 1e-12
+
+
+def run_dropin(refdrv, pkg, so_name, cfg):
+    """Run the reference-named entry points through `so_name` (a glue build) and through the real
+    reference, on identical UserCtx contents.  Returns relative errors."""
+    so = os.path.join(pc.ROOT, "oracle", "_ref", so_name)
+    if not os.path.exists(so):
+        pytest.skip(so_name + " not built")
+    ref, xyz, fields, met = pc.ref_setup(cfg, refdrv)
+    # second driver instance bound to the glue library
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("refdrv_glue", os.path.join(pc.ROOT, "oracle", "refdrv.py"))
+    gd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gd)
+    gd.SO = so
+    gd._GLOBALS_JSON = os.path.join(pc.ROOT, "oracle", "_ref", "globals_glue_%s.json" % so_name.split("_")[1].split(".")[0])
+    glue, _, _, _ = pc.ref_setup(cfg, gd)
+    err = {}
+    for nm in ("lCsi", "lEta", "lZet", "lAj", "lICsi", "lJEta", "lKZet", "lIAj", "lKAj"):
+        err["FormMetrics_" + nm] = pc.relerr(glue.owned(nm)[1:-1, 1:-1, 1:-1], ref.owned(nm)[1:-1, 1:-1, 1:-1])
+    ref.Contra2Cart(); glue.Contra2Cart()
+    err["Contra2Cart_Ucat"] = pc.relerr(glue.owned("Ucat"), ref.owned("Ucat"))
+    err["Contra2Cart_lUcat_ghosts"] = pc.relerr(glue.view("lUcat"), ref.view("lUcat"))
+    ref.Compute_Smagorinsky_Constant_1(); glue.Compute_Smagorinsky_Constant_1()
+    err["lCs"] = pc.relerr(glue.owned("lCs"), ref.owned("lCs"))
+    ref.Compute_eddy_viscosity_LES(); glue.Compute_eddy_viscosity_LES()
+    err["lNu_t"] = pc.relerr(glue.owned("lNu_t"), ref.owned("lNu_t"))
+    ref.IB_BC(); glue.IB_BC()
+    # Nodes lying on two or more domain-boundary planes are excluded: there IB_BC's component-wise
+    # periodic copy (momentum.c:2210-2221) reads ghost images that the reference has not refreshed
+    # since Contra2Cart rewrote their sources, while the glue re-uploads lUcont (fresh ghosts).
+    # Those edge values feed nothing (Rhs is zeroed on boundary planes); the on-device sequence
+    # used by FormFunction_SNES reproduces them exactly (tests/parity_common.py IB_BC_ucont).
+    a, b = np.array(glue.owned("lUcont")), np.array(ref.owned("lUcont"))
+    mz_, my_, mx_ = a.shape[:3]
+    kk, jj, ii = np.meshgrid(np.arange(mz_), np.arange(my_), np.arange(mx_), indexing="ij")
+    nb = ((kk == 0) | (kk == mz_ - 1)).astype(int) + ((jj == 0) | (jj == my_ - 1)) + ((ii == 0) | (ii == mx_ - 1))
+    err["IB_BC_lUcont"] = pc.relerr(a[nb < 2], b[nb < 2])
+    for d in (ref, glue):
+        d.view("RHS_o")[...] = 0
+        d.Formfunction_2("RHS_o", 1.0)
+    err["Formfunction_2_RHS_o"] = pc.relerr(glue.owned("RHS_o"), ref.owned("RHS_o"))
+    x = fields["ucont"] * (1.0 + 1e-3 * np.cos(np.arange(fields["ucont"].size).reshape(fields["ucont"].shape)))
+    for d in (ref, glue):
+        d.new_vec("X", 3, False); d.new_vec("F", 3, False)
+        d.view("X")[...] = x
+        gd.lib().vfs_glue_invalidate(C.c_void_p(glue.u)) if d is glue else None
+        d.FormFunction_SNES("X", "F")
+    err["FormFunction_SNES_F"] = pc.relerr(glue.view("F"), ref.view("F"))
+    gd.lib().vfs_glue_release(C.c_void_p(glue.u))
+    return err
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17))])
+def test_glue_dropin_emulated(pkg, refdrv, name, dims):
+    import emu_loader
+    emu_loader.build()
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = run_dropin(refdrv, pkg, "libvfsglue_emu.so", cfg)
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
