@@ -9,7 +9,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity_common as pc  # noqa: E402
-from test_cpu_multirank import FIELDS_IN, run_path  # noqa: E402
+from parity_common import FIELDS_IN, run_path  # noqa: E402
 
 
 def main():

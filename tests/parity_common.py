@@ -123,3 +123,20 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False):
             print("%-32s %.3e" % (k, v))
     ctx.close()
     return err
+
+
+FIELDS_IN = (("nvert", "NVERT"), ("ucont", "UCONT"), ("ucat", "UCAT"), ("ucat_old", "UCAT_OLD"), ("ucont_o", "UCONT_O"),
+             ("ucont_rm1", "UCONT_RM1"), ("rhs_o", "RHS_O"), ("dp", "DP"), ("f_eul", "F_EUL"))
+
+
+def run_path(ctx, x):
+    out = {}
+    ctx.Contra2Cart()
+    ctx.Compute_Smagorinsky_Constant_1()
+    ctx.Compute_eddy_viscosity_LES()
+    out["F"] = ctx.FormFunction_SNES(x)
+    for n in ("UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ"):
+        out[n] = ctx.download(n)
+    return out
+
+

@@ -13,19 +13,7 @@ import torch.multiprocessing as mp
 import parity_common as pc
 import emu_loader
 
-FIELDS_IN = (("nvert", "NVERT"), ("ucont", "UCONT"), ("ucat", "UCAT"), ("ucat_old", "UCAT_OLD"), ("ucont_o", "UCONT_O"),
-             ("ucont_rm1", "UCONT_RM1"), ("rhs_o", "RHS_O"), ("dp", "DP"), ("f_eul", "F_EUL"))
-
-
-def run_path(ctx, x):
-    out = {}
-    ctx.Contra2Cart()
-    ctx.Compute_Smagorinsky_Constant_1()
-    ctx.Compute_eddy_viscosity_LES()
-    out["F"] = ctx.FormFunction_SNES(x)
-    for n in ("UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ"):
-        out[n] = ctx.download(n)
-    return out
+from parity_common import FIELDS_IN, run_path  # noqa: E402
 
 
 def _worker(rank, world, port, tmp, cfgname, dims, flags_extra, bctype):
