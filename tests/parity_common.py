@@ -32,6 +32,11 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / den)
 
 
+def krylov_x(ucont):
+    """A perturbed state like the U + h*v vectors the matrix-free Krylov solver evaluates."""
+    return ucont + 1e-4 * np.abs(ucont).max() * np.cos(np.arange(ucont.size).reshape(ucont.shape) * 0.37)
+
+
 def ref_setup(cfg, refdrv):
     """Create the reference context, metrics and input state for cfg.  Returns (ref, xyz, fields)."""
     pkg = load_package()
@@ -108,7 +113,7 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False):
     rhs_o_ref = np.array(ref.owned("RHS_o"))
     err["Formfunction_2"] = relerr(ctx.download("RHS_O"), rhs_o_ref)
     # one Krylov-iteration residual
-    x = fields["ucont"] + 1e-4 * np.abs(fields["ucont"]).max() * np.cos(np.arange(fields["ucont"].size).reshape(fields["ucont"].shape) * 0.37)
+    x = krylov_x(fields["ucont"])
     ref.new_vec("X", 3, False)
     ref.new_vec("F", 3, False)
     ref.view("X")[...] = x
@@ -140,3 +145,34 @@ def run_path(ctx, x):
     return out
 
 
+
+
+def run_golden(cfg, gold, lib=None, device=0):
+    """Same path as run_parity but checked against a committed fixture (tests/golden/*.npz)
+    generated from the reference by tests/golden/make_golden.py."""
+    pkg = load_package()
+    xyz = gold["xyz"]
+    met = dict(csi=gold["csi"], eta=gold["eta"], zet=gold["zet"], aj=gold["aj"])
+    fields = pkg.cases.make_fields(cfg, met)
+    ctx = dev_setup(cfg, xyz, fields, lib=lib, device=device)
+    err = {}
+    for nm, key in (("CSI", "csi"), ("ETA", "eta"), ("ZET", "zet"), ("AJ", "aj")):
+        err["metrics_" + nm] = relerr(ctx.download(nm), met[key])
+    ctx.Contra2Cart()
+    err["Contra2Cart_ucat"] = relerr(ctx.download("UCAT"), gold["ucat"])
+    if cfg["flags"].get("les"):
+        ctx.Compute_Smagorinsky_Constant_1()
+        err["Cs"] = relerr(ctx.download("CS"), gold["cs"])
+        ctx.Compute_eddy_viscosity_LES()
+        err["nu_t"] = relerr(ctx.download("NU_T"), gold["nu_t"])
+    ctx.IB_BC()
+    err["IB_BC_ucont"] = relerr(ctx.download("UCONT"), gold["ucont_after_ibbc"])
+    ctx.upload("RHS_O", np.zeros_like(fields["rhs_o"]))
+    ctx.Formfunction_2("RHS_O", 1.0)
+    err["Formfunction_2"] = relerr(ctx.download("RHS_O"), gold["formfunction2"])
+    ctx.upload("RHS_O", fields["rhs_o"])
+    f_dev = ctx.FormFunction_SNES(krylov_x(fields["ucont"]))
+    err["FormFunction_SNES"] = relerr(f_dev, gold["snes_f"])
+    err["SNES_ucat"] = relerr(ctx.download("UCAT"), gold["snes_ucat"])
+    ctx.close()
+    return err

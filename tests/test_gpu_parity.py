@@ -87,3 +87,13 @@ def test_multi_gpu_bitwise_equal_single_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                         "--master-port", "29611", os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
     assert "MULTIGPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["c2_small", "c3_small", "c1_small"])
+def test_cuda_matches_golden_fixture(pkg, name):
+    """Against the committed fixtures generated from the reference (no oracle/_ref needed)."""
+    from test_cpu_golden import load_gold
+    g, cfg = load_gold(name, pkg)
+    err = pc.run_golden(cfg, g, device=0)
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
