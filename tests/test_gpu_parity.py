@@ -97,3 +97,25 @@ def test_cuda_matches_golden_fixture(pkg, name):
     err = pc.run_golden(cfg, g, device=0)
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
+
+
+def test_tiled_equals_staged(pkg):
+    """The shared-memory tiled kernels and the one-thread-per-cell staged kernels share their
+    arithmetic and summation order: results must be bitwise identical."""
+    capi, cases = pkg.capi, pkg.cases
+    for cfgname, dims in (("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41))):
+        cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
+        mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+        outs = []
+        for fused in (0, 1):
+            ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+            ctx.set_option(0, fused)
+            ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+            for k, n in pc.FIELDS_IN:
+                ctx.upload(n, f[k])
+            outs.append(pc.run_path(ctx, pc.krylov_x(f["ucont"])))
+            ctx.close()
+        for n in outs[0]:
+            assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)

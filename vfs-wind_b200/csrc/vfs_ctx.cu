@@ -461,6 +461,12 @@ static int les_cs(vfs_ctx *c) {
   RUN(g2l(c, g1));                                                    // les.c:254-267
   if (any_per(c)) RUN(node_copy(c, g1));                              // les.c:275-306
   ev_rec(c, 2 * VFS_T_LES2);
+#ifndef VFS_EMU
+  if (c->fused && !d.testfilter_ik) {
+    Box bi = box_interior(c);
+    if (launch_les2_tile(c->stream, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "k_les2_tile launch failed"); return VFS_ERR_CUDA; }
+  } else
+#endif
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES2 + 1);
   Grp g2 = grp(S_LM, 2);

@@ -84,90 +84,100 @@ struct LesPass1 {
   }
 };
 
+// les.c:354-439 per-node part of pass 2: weight w and the products entering the test filters,
+// v[0] = w, v[1..9] = U_a u_b (a-major), v[10..15] = |S| S_ij (xx,xy,xz,yy,yz,zz)
+#define VFS_LES2_NV 16
+VFS_HD void les2_products(const VfsDev &d, long n, double *v) {
+  v[0] = (d.s[S_NV][n] > 0.1) ? 0. : 1. / d.s[S_AJ][n];
+  const double u[3] = {d.s[S_U0][n], d.s[S_U1][n], d.s[S_U2][n]};
+  const double U[3] = {u[0] * d.s[S_CSI0][n] + u[1] * d.s[S_CSI1][n] + u[2] * d.s[S_CSI2][n],
+                       u[0] * d.s[S_ETA0][n] + u[1] * d.s[S_ETA1][n] + u[2] * d.s[S_ETA2][n],
+                       u[0] * d.s[S_ZET0][n] + u[1] * d.s[S_ZET1][n] + u[2] * d.s[S_ZET2][n]};
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) v[1 + 3 * a + b] = U[a] * u[b];
+  const double S = d.s[S_SABS][n];
+  const double ax0 = d.s[S_AX0][n], ax1 = d.s[S_AX1][n], ax2 = d.s[S_AX2][n];
+  const double ay0 = d.s[S_AY0][n], ay1 = d.s[S_AY1][n], ay2 = d.s[S_AY2][n];
+  const double az0 = d.s[S_AZ0][n], az1 = d.s[S_AZ1][n], az2 = d.s[S_AZ2][n];
+  v[10] = (0.5 * (ax0 + ax0)) * S; v[11] = (0.5 * (ax1 + ay0)) * S; v[12] = (0.5 * (ax2 + az0)) * S;
+  v[13] = (0.5 * (ay1 + ay1)) * S; v[14] = (0.5 * (ay2 + az1)) * S; v[15] = (0.5 * (az2 + az2)) * S;
+}
+
+// les.c:441-669 after the filters: fs[0] = sum of Simpson weights (or 36 for testfilter_ik),
+// fs[1..15] = filtered sums of v[1..15]; sum_weight = sum of w*coef (les.c:441-468)
+VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const double *fs, double sum_weight) {
+  const double ajc = d.s[S_AJ][p];
+  const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
+  const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
+  const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
+  const double fdiv = fs[0];
+  const double filter = pow(1. / ajc, 1. / 3.);
+  const double test_filter = d.testfilter_ik ? pow(5.0, 1. / 3.) * filter : pow(sum_weight, 1. / 3.);
+  const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
+  const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
+  double gh[3][3];
+  grad_center(d, S_UF0, i, j, kg, p, gh);
+  const double Sh[3][3] = {{0.5 * (gh[0][0] + gh[0][0]), 0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[0][2] + gh[2][0])},
+                           {0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[1][1] + gh[1][1]), 0.5 * (gh[1][2] + gh[2][1])},
+                           {0.5 * (gh[0][2] + gh[2][0]), 0.5 * (gh[1][2] + gh[2][1]), 0.5 * (gh[2][2] + gh[2][2])}};
+  const double S_hat = sabs_of(gh);
+  double Lij[3][3], SSh[3][3];
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = fs[1 + 3 * a + b] / fdiv - _U[a] * _u[b];
+  SSh[0][0] = fs[10] / fdiv; SSh[0][1] = SSh[1][0] = fs[11] / fdiv; SSh[0][2] = SSh[2][0] = fs[12] / fdiv;
+  SSh[1][1] = fs[13] / fdiv; SSh[1][2] = SSh[2][1] = fs[14] / fdiv; SSh[2][2] = fs[15] / fdiv;
+  // covariant metric tensor G (les.c:607-622)
+  const double a11 = csi[0], a12 = csi[1], a13 = csi[2], a21 = eta[0], a22 = eta[1], a23 = eta[2], a31 = zet[0], a32 = zet[1], a33 = zet[2];
+  const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+  const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
+  const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
+  const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
+  double G[3][3];
+  G[0][0] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
+  G[1][1] = xeta * xeta + yeta * yeta + zeta * zeta;
+  G[2][2] = xzet * xzet + yzet * yzet + zzet * zzet;
+  G[0][1] = G[1][0] = xeta * xcsi + yeta * ycsi + zeta * zcsi;
+  G[0][2] = G[2][0] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
+  G[1][2] = G[2][1] = xeta * xzet + yeta * yzet + zeta * zzet;
+  double Mc[3][3], M[3][3];
+  const double tf2 = pow(test_filter, 2.), f2 = pow(filter, 2.);
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Mc[a][b] = -tf2 * S_hat * Sh[a][b] + f2 * SSh[a][b];
+  for (int a = 0; a < 3; a++) {
+    M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
+    M[a][1] = Mc[a][0] * eta[0] + Mc[a][1] * eta[1] + Mc[a][2] * eta[2];
+    M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
+  }
+  double num = 0, den = 0;
+  for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) num += Lij[b][a] * M[a][q] * G[b][q];
+  for (int m = 0; m < 3; m++) for (int n = 0; n < 3; n++) for (int l = 0; l < 3; l++) den += M[n][m] * M[n][l] * G[m][l];
+  d.s[S_LM][p] = num; d.s[S_MM][p] = den;
+}
+
 // les.c:308-669: Germano identity contracted with the covariant metric tensor -> LM, MM
+// (straightforward one-thread-per-cell form; the shared-memory tiled form is in vfs_fused_kernels.h)
 struct LesPass2 {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
     const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
-    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
-    if (nv[p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
-    const double ajc = aj[p];
-    const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
-    const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
-    const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
-
-    // filtered products <U_i u_j> (9) and <|S| S_ij> (6 unique), sum of weights and of w*coef
-    double ws = 0, sum_weight = 0, Uu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, SS[6] = {0, 0, 0, 0, 0, 0};
+    if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
+    double fs[VFS_LES2_NV], sum_weight = 0;
+    for (int a = 0; a < VFS_LES2_NV; a++) fs[a] = 0;
     for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
       const long n = p + r * d.sk + q * d.sj + pp;
-      const double w = (nv[n] > 0.1) ? 0. : 1. / aj[n];
-      const double sim = simpson_w(r, q, pp);
-      sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));   // coef table les.c:441-451
-      const double u[3] = {d.s[S_U0][n], d.s[S_U1][n], d.s[S_U2][n]};
-      const double U[3] = {u[0] * d.s[S_CSI0][n] + u[1] * d.s[S_CSI1][n] + u[2] * d.s[S_CSI2][n],
-                           u[0] * d.s[S_ETA0][n] + u[1] * d.s[S_ETA1][n] + u[2] * d.s[S_ETA2][n],
-                           u[0] * d.s[S_ZET0][n] + u[1] * d.s[S_ZET1][n] + u[2] * d.s[S_ZET2][n]};
-      const double S = d.s[S_SABS][n];
-      const double ax0 = d.s[S_AX0][n], ax1 = d.s[S_AX1][n], ax2 = d.s[S_AX2][n];
-      const double ay0 = d.s[S_AY0][n], ay1 = d.s[S_AY1][n], ay2 = d.s[S_AY2][n];
-      const double az0 = d.s[S_AZ0][n], az1 = d.s[S_AZ1][n], az2 = d.s[S_AZ2][n];
-      const double s6[6] = {0.5 * (ax0 + ax0), 0.5 * (ax1 + ay0), 0.5 * (ax2 + az0), 0.5 * (ay1 + ay1), 0.5 * (ay2 + az1), 0.5 * (az2 + az2)};
+      double v[VFS_LES2_NV];
+      les2_products(d, n, v);
+      sum_weight += v[0] * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));   // coef table les.c:441-451
       if (d.testfilter_ik) {
         if (q != 0) continue;
         const double c = (r == 0 ? 4. : 1.) * (pp == 0 ? 4. : 1.);   // 1,4,16 (rhs2.c:440)
-        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Uu[a][b] += c * (U[a] * u[b]);
-        for (int a = 0; a < 6; a++) SS[a] += c * (s6[a] * S);
+        for (int a = 1; a < VFS_LES2_NV; a++) fs[a] += c * v[a];
       } else {
-        const double sw = sim * w;
-        ws += sw;
-        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Uu[a][b] += sw * (U[a] * u[b]);
-        for (int a = 0; a < 6; a++) SS[a] += sw * (s6[a] * S);
+        const double sw = simpson_w(r, q, pp) * v[0];
+        fs[0] += sw;
+        for (int a = 1; a < VFS_LES2_NV; a++) fs[a] += sw * v[a];
       }
     }
-    const double fdiv = d.testfilter_ik ? 36. : ws;
-    const double filter = pow(1. / ajc, 1. / 3.);
-    const double test_filter = d.testfilter_ik ? pow(5.0, 1. / 3.) * filter : pow(sum_weight, 1. / 3.);
-
-    const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
-    const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
-    double gh[3][3];
-    grad_center(d, S_UF0, i, j, kg, p, gh);
-    const double Sh[3][3] = {{0.5 * (gh[0][0] + gh[0][0]), 0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[0][2] + gh[2][0])},
-                             {0.5 * (gh[0][1] + gh[1][0]), 0.5 * (gh[1][1] + gh[1][1]), 0.5 * (gh[1][2] + gh[2][1])},
-                             {0.5 * (gh[0][2] + gh[2][0]), 0.5 * (gh[1][2] + gh[2][1]), 0.5 * (gh[2][2] + gh[2][2])}};
-    const double S_hat = sabs_of(gh);
-    double Lij[3][3], SSh[3][3];
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = Uu[a][b] / fdiv - _U[a] * _u[b];
-    SSh[0][0] = SS[0] / fdiv; SSh[0][1] = SSh[1][0] = SS[1] / fdiv; SSh[0][2] = SSh[2][0] = SS[2] / fdiv;
-    SSh[1][1] = SS[3] / fdiv; SSh[1][2] = SSh[2][1] = SS[4] / fdiv; SSh[2][2] = SS[5] / fdiv;
-
-    // covariant metric tensor G (les.c:607-622)
-    const double a11 = csi[0], a12 = csi[1], a13 = csi[2], a21 = eta[0], a22 = eta[1], a23 = eta[2], a31 = zet[0], a32 = zet[1], a33 = zet[2];
-    const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
-    const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
-    const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
-    const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
-    double G[3][3];
-    G[0][0] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
-    G[1][1] = xeta * xeta + yeta * yeta + zeta * zeta;
-    G[2][2] = xzet * xzet + yzet * yzet + zzet * zzet;
-    G[0][1] = G[1][0] = xeta * xcsi + yeta * ycsi + zeta * zcsi;
-    G[0][2] = G[2][0] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
-    G[1][2] = G[2][1] = xeta * xzet + yeta * yzet + zeta * zzet;
-
-    double Mc[3][3], M[3][3];
-    const double tf2 = pow(test_filter, 2.), f2 = pow(filter, 2.);
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Mc[a][b] = -tf2 * S_hat * Sh[a][b] + f2 * SSh[a][b];
-    for (int a = 0; a < 3; a++) {
-      M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
-      M[a][1] = Mc[a][0] * eta[0] + Mc[a][1] * eta[1] + Mc[a][2] * eta[2];
-      M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
-    }
-    double num = 0, den = 0;
-    for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) num += Lij[b][a] * M[a][q] * G[b][q];
-    for (int m = 0; m < 3; m++) for (int n = 0; n < 3; n++) for (int l = 0; l < 3; l++) den += M[n][m] * M[n][l] * G[m][l];
-    d.s[S_LM][p] = num; d.s[S_MM][p] = den;
+    if (d.testfilter_ik) fs[0] = 36.;
+    les2_finish(d, i, j, kg, p, fs, sum_weight);
   }
 };
 
