@@ -42,6 +42,8 @@ enum {
   S_AX0, S_AX1, S_AX2, S_AY0, S_AY1, S_AY2, S_AZ0, S_AZ1, S_AZ2, S_SABS, // LES: grad u, |S|
   S_UF0, S_UF1, S_UF2,                                                   // LES: test-filtered ucat
   S_LM, S_MM,
+  // LES per-node derived quantities entering the test filters (contiguous: w, U(3), |S|S_ij(6))
+  S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5,
   S_COUNT
 };
 

@@ -46,7 +46,11 @@ struct vfs_ctx {
   std::string err;
   cudaEvent_t ev[2 * VFS_T_COUNT] = {0};
   bool ev_valid[VFS_T_COUNT] = {false};
-  int fused = 1;                 // use the fused smem-tiled RHS kernel when applicable
+  int fused = 1;                 // use the TMA-staged tiled kernels when applicable
+#ifndef VFS_EMU
+  CUtensorMap tmap;              // 4-D map over the scalar pool, box (TX+2, TY+2, 1, 1)
+#endif
+  bool tma_ok = false;
 };
 
 static void set_err(vfs_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_err = m; }
@@ -183,6 +187,9 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
 #endif
   for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
+#ifndef VFS_EMU
+  c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0;
+#endif
   *out = c;
   return 0;
 }
@@ -314,6 +321,8 @@ static int for_boundary_planes(vfs_ctx *c, int (*fn)(vfs_ctx *, const Box &, voi
 }
 static int run_snapshot(vfs_ctx *c, const Box &b, void *) { CopyScalar3 f = {c->d, S_U0, S_FP0}; return launch(c, b, f); }
 static int run_ghost_rules(vfs_ctx *c, const Box &b, void *) { C2CGhostRules f = {c->d}; return launch(c, b, f); }
+
+static int run_les_derive_boundary(vfs_ctx *c, const Box &b, void *) { LesDeriveBoundary f = {c->d}; return launch(c, b, f); }
 
 static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
@@ -453,18 +462,20 @@ static int les_cs(vfs_ctx *c) {
   Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
-  RUN(zero_scalars(c, S_AX0, 13));
   ev_rec(c, 2 * VFS_T_LES1);
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
-  Grp g1 = grp(S_AX0, 13);
+  RUN(for_boundary_planes(c, run_les_derive_boundary, 0));
+  Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
   RUN(g2l(c, g1));                                                    // les.c:254-267
-  if (any_per(c)) RUN(node_copy(c, g1));                              // les.c:275-306
+  // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
+  // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
+  if (any_per(c)) RUN(node_copy(c, grp_cat(grp(S_UF0, 3), grp(S_LU0, 9))));   // les.c:275-306
   ev_rec(c, 2 * VFS_T_LES2);
 #ifndef VFS_EMU
-  if (c->fused && !d.testfilter_ik) {
+  if (c->fused && c->tma_ok && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    if (launch_les2_tile(c->stream, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "k_les2_tile launch failed"); return VFS_ERR_CUDA; }
+    if (launch_les2_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "k_les2_tma launch failed"); return VFS_ERR_CUDA; }
   } else
 #endif
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }

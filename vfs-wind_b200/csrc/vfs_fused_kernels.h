@@ -1,10 +1,13 @@
 // vfs_fused_kernels.h — shared-memory-tiled k-marching kernels (the performance path).
 //
-// A thread block owns an (i,j) tile and marches along k; per-node quantities that the one-thread-
-// per-cell kernels of vfs_les_kernels.h / vfs_rhs_kernels.h recompute for each of a cell's 27
-// neighbours are computed ONCE per node per plane into a ring of shared-memory planes.  The
-// arithmetic is the same device functions in the same summation order as the staged kernels, so
-// both forms are bitwise identical (tests/test_gpu_parity.py::test_tiled_equals_staged).
+// A thread block owns an (i,j) tile and marches along k.  The per-node planes a cell's 27-point
+// neighbourhood needs are staged into a ring of shared-memory planes by TMA
+// (cp.async.bulk.tensor.4d, one box of (TX+2)x(TY+2) doubles per scalar per plane, completion on
+// an mbarrier), STAGES-2 planes ahead of the plane being computed, so HBM/L2 latency is hidden by
+// the prefetch distance instead of by occupancy.  Out-of-range box coordinates (tile overhang) are
+// zero-filled by the TMA unit.  The arithmetic is the same device functions, in the same summation
+// order, as the one-thread-per-cell kernels, so both forms are bitwise identical
+// (tests/test_gpu_parity.py::test_tiled_equals_staged).
 // CUDA only: the host emulation (tests/emu, -DVFS_EMU) always uses the staged kernels.
 #ifndef VFS_FUSED_KERNELS_H
 #define VFS_FUSED_KERNELS_H
@@ -12,14 +15,75 @@
 #include "vfs_les_kernels.h"
 
 #ifndef VFS_EMU
+#include <cuda.h>
 #include <cuda_runtime.h>
 
-// ---- LES pass 2 (les.c:308-669) ------------------------------------------------------------------
-// ring of 3 planes x 16 per-node products x (TX+2)x(TY+2) nodes  (130.6 KB for 32x8)
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX *TY) k_les2_tile(VfsDev d, int kbeg, int kend, int kchunk) {
-  extern __shared__ double sm[];
-  constexpr int NXP = TX + 2, NYP = TY + 2, NN = NXP * NYP, NV = VFS_LES2_NV;
+#define VFS_TILE_TX 32
+#define VFS_TILE_TY 8
+
+// ---- TMA / mbarrier primitives (raw PTX) -------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VFS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VFS_DONE_%=;\n"
+      "bra VFS_WAIT_%=;\n"
+      "VFS_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one (box_x, box_y, 1, 1) tile of scalar `w` at padded coordinates (x, y, z) -> shared memory
+__device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *map, int x, int y, int z, int w, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+               "l"((unsigned long long)map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// host: 4-D tensor map over the whole scalar pool [S_COUNT][nzt][ny][pitch], box (bx, by, 1, 1)
+static inline int vfs_make_tensor_map(CUtensorMap *map, void *pool, const VfsDev &d, long scalar_len, int bx, int by) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = 0;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+  cuuint64_t gdim[4] = {(cuuint64_t)d.pitch, (cuuint64_t)d.ny, (cuuint64_t)d.nzt, (cuuint64_t)S_COUNT};
+  cuuint64_t gstr[3] = {(cuuint64_t)d.pitch * 8, (cuuint64_t)d.sk * 8, (cuuint64_t)scalar_len * 8};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ((encode_fn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, pool, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// ---- generic ring of TMA-staged planes ----------------------------------------------------------------
+// NS scalars per plane, each tile padded to a 128-byte multiple (TMA destination alignment).
+template <int TX, int TY, int NS, int STAGES> struct PlaneRing {
+  static constexpr int NXP = TX + 2, NYP = TY + 2, NN = NXP * NYP;
+  static constexpr int TILE_B = ((NN * 8 + 127) / 128) * 128;
+  static constexpr int TILE_D = TILE_B / 8;                 // doubles per padded scalar tile
+  static constexpr int PLANE_D = TILE_D * NS;
+  static constexpr size_t BYTES = (size_t)STAGES * PLANE_D * 8 + STAGES * 8;
+};
+
+// ---- LES pass 2 (les.c:308-669) --------------------------------------------------------------------------
+// staged scalars per node: ucat(3), w, U(3), |S|S_ij(6)  (vfs_les_kernels.h: les_derive_store)
+template <int TX, int TY, int STAGES>
+__global__ void __launch_bounds__(TX *TY) k_les2_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
+  typedef PlaneRing<TX, TY, 13, STAGES> R;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *sm = reinterpret_cast<double *>(smraw);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw + (size_t)STAGES * R::PLANE_D * 8);
+  constexpr int NXP = R::NXP, TD = R::TILE_D, NV = VFS_LES2_NV;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
   const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
   const int ka = kbeg + blockIdx.z * kchunk;
@@ -27,25 +91,32 @@ __global__ void __launch_bounds__(TX *TY) k_les2_tile(VfsDev d, int kbeg, int ke
   if (ka >= kb) return;
   const int i = i0 + tx, j = j0 + ty;
   const bool active = (i <= d.mx - 2) && (j <= d.my - 2);
+  const int sid[13] = {S_U0, S_U1, S_U2, S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5};
 
-  auto fill = [&](int kk) {
-    const int slot = (kk - (ka - 1)) % 3;
-    double *base = sm + (size_t)slot * NV * NN;
-    for (int n = tid; n < NN; n += TX * TY) {
-      const int jj = n / NXP, ii = n - jj * NXP;
-      const int gi = i0 - 1 + ii, gj = j0 - 1 + jj;
-      double v[NV];
-      if (gi <= d.mx - 1 && gj <= d.my - 1) les2_products(d, d.idx(gi, gj, kk), v);
-      else { for (int a = 0; a < NV; a++) v[a] = 0.; }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // plane kk lives in slot (kk - (ka-1)) % STAGES; its barrier completes phase ((kk-(ka-1))/STAGES)&1
+  auto issue = [&](int kk) {
+    const int n = kk - (ka - 1), slot = n % STAGES;
+    double *dst = sm + (size_t)slot * R::PLANE_D;
+    mbar_expect_tx(&bars[slot], 13 * R::NN * 8);
 #pragma unroll
-      for (int a = 0; a < NV; a++) base[a * NN + n] = v[a];
-    }
+    for (int s = 0; s < 13; s++) tma_load_tile(dst + s * TD, &tmap, i0 - 1 + VFS_G, j0 - 1 + VFS_G, kk + VFS_G, sid[s], &bars[slot]);
   };
-  fill(ka - 1);
-  fill(ka);
+  auto wait_plane = [&](int kk) {
+    const int n = kk - (ka - 1);
+    mbar_wait(&bars[n % STAGES], (n / STAGES) & 1);
+  };
+  if (tid == 0) {
+    for (int kk = ka - 1; kk < ka - 1 + STAGES && kk <= kb; kk++) issue(kk);
+  }
+  wait_plane(ka - 1);
+  wait_plane(ka);
   for (int k = ka; k < kb; k++) {
-    fill(k + 1);
-    __syncthreads();
+    wait_plane(k + 1);
     if (active) {
       const long p = d.idx(i, j, k);
       if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; }
@@ -55,40 +126,49 @@ __global__ void __launch_bounds__(TX *TY) k_les2_tile(VfsDev d, int kbeg, int ke
         for (int a = 0; a < NV; a++) fs[a] = 0;
 #pragma unroll
         for (int r = -1; r <= 1; r++) {
-          const double *pl = sm + (size_t)((k + r - (ka - 1)) % 3) * NV * NN;
+          const double *pl = sm + (size_t)((k + r - (ka - 1)) % STAGES) * R::PLANE_D;
 #pragma unroll
           for (int q = -1; q <= 1; q++) {
 #pragma unroll
             for (int pp = -1; pp <= 1; pp++) {
               const int n = (ty + 1 + q) * NXP + (tx + 1 + pp);
-              const double w = pl[n];
+              const double w = pl[3 * TD + n];
               sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));
               const double sw = simpson_w(r, q, pp) * w;
               fs[0] += sw;
+              const double u0 = pl[n], u1 = pl[TD + n], u2 = pl[2 * TD + n];
+              const double U0 = pl[4 * TD + n], U1 = pl[5 * TD + n], U2 = pl[6 * TD + n];
+              fs[1] += sw * (U0 * u0); fs[2] += sw * (U0 * u1); fs[3] += sw * (U0 * u2);
+              fs[4] += sw * (U1 * u0); fs[5] += sw * (U1 * u1); fs[6] += sw * (U1 * u2);
+              fs[7] += sw * (U2 * u0); fs[8] += sw * (U2 * u1); fs[9] += sw * (U2 * u2);
 #pragma unroll
-              for (int a = 1; a < NV; a++) fs[a] += sw * pl[a * NN + n];
+              for (int a = 0; a < 6; a++) fs[10 + a] += sw * pl[(7 + a) * TD + n];
             }
           }
         }
         les2_finish(d, i, j, k + d.kofs, p, fs, sum_weight);
       }
     }
-    __syncthreads();
+    __syncthreads();                         // everyone is done reading plane k-1: its slot is free
+    if (tid == 0) {
+      const int kn = k - 1 + STAGES;         // next plane for that slot
+      if (kn <= kb) { fence_proxy_async(); issue(kn); }
+    }
   }
 }
 
-static inline int launch_les2_tile(cudaStream_t st, const VfsDev &d, int k0, int k1, long *launches) {
-  constexpr int TX = 32, TY = 8;
+static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *launches) {
+  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = 4;
   if (k1 <= k0) return 0;
-  const size_t smem = (size_t)3 * VFS_LES2_NV * (TX + 2) * (TY + 2) * sizeof(double);
+  const size_t smem = PlaneRing<TX, TY, 13, STAGES>::BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_les2_tile<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(k_les2_tma<TX, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
     attr_set = true;
   }
   const int kchunk = 32;
   dim3 grd((d.mx - 2 + TX - 1) / TX, (d.my - 2 + TY - 1) / TY, (k1 - k0 + kchunk - 1) / kchunk), blk(TX, TY, 1);
-  k_les2_tile<TX, TY><<<grd, blk, smem, st>>>(d, k0, k1, kchunk);
+  k_les2_tma<TX, TY, STAGES><<<grd, blk, smem, st>>>(tmap, d, k0, k1, kchunk);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -11,6 +11,14 @@
 #include "vfs_common.h"
 #include "vfs_rhs_kernels.h"
 
+// pow(x, 1./3.) (les.c:462-468,1208): cbrt on the device (<= 1 ulp apart; the CUDA
+// generic pow costs ~10x more), literal pow in the host emulation
+#if defined(__CUDA_ARCH__)
+#define VFS_CBRT(x) cbrt(x)
+#else
+#define VFS_CBRT(x) pow((x), 1. / 3.)
+#endif
+
 // centre difference along stride s (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
 VFS_HD double dcen(const double *u, const double *nv, long p, long s, int c, int m, int per, int lowc) {
   if (nv[p + s] > VFS_SOLID || (!per && c == m - 2)) return u[p] - u[p - s];
@@ -51,18 +59,46 @@ VFS_HD double simpson_w(int r, int q, int pp) {
   return s;
 }
 
-// les.c:199-246: grad u, |S| and the test-filtered velocity
+// per-node quantities that pass 2 filters over the 27-point neighbourhood (les.c:354-439):
+// w = 1/aj (0 where nvert > 0.1), contravariant U = [csi;eta;zet] u, and |S| S_ij.  Written once
+// per node instead of being recomputed 27 times by every neighbour.
+VFS_HD void les_derive_store(const VfsDev &d, long n, const double g[3][3], double S) {
+  d.s[S_LW][n] = (d.s[S_NV][n] > 0.1) ? 0. : 1. / d.s[S_AJ][n];
+  const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
+  d.s[S_LU0][n] = u0 * d.s[S_CSI0][n] + u1 * d.s[S_CSI1][n] + u2 * d.s[S_CSI2][n];
+  d.s[S_LU1][n] = u0 * d.s[S_ETA0][n] + u1 * d.s[S_ETA1][n] + u2 * d.s[S_ETA2][n];
+  d.s[S_LU2][n] = u0 * d.s[S_ZET0][n] + u1 * d.s[S_ZET1][n] + u2 * d.s[S_ZET2][n];
+  d.s[S_LSS0][n] = (0.5 * (g[0][0] + g[0][0])) * S; d.s[S_LSS1][n] = (0.5 * (g[0][1] + g[1][0])) * S; d.s[S_LSS2][n] = (0.5 * (g[0][2] + g[2][0])) * S;
+  d.s[S_LSS3][n] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][n] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][n] = (0.5 * (g[2][2] + g[2][2])) * S;
+}
+// domain-boundary nodes: grad u and |S| are zero there in the reference (VecSet, les.c:183-186)
+struct LesDeriveBoundary {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    les_derive_store(d, d.idx(i, j, k), z, 0.);
+  }
+};
+
+// les.c:199-246: grad u, |S| and the test-filtered velocity (+ the per-node derived quantities)
 struct LesPass1 {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
     const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
     const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
-    if (nv[p] > 1.1) return;
+    if (nv[p] > 1.1) {   // skipped by the reference: its zero-initialised work vectors keep 0 here
+      const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      d.s[S_SABS][p] = 0;
+      for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = 0;
+      les_derive_store(d, p, z, 0.);
+      return;
+    }
     double g[3][3];
     grad_center(d, S_U0, i, j, kg, p, g);
-    d.s[S_SABS][p] = sabs_of(g);
-    for (int a = 0; a < 3; a++) { d.s[S_AX0 + 3 * a][p] = g[a][0]; d.s[S_AX0 + 3 * a + 1][p] = g[a][1]; d.s[S_AX0 + 3 * a + 2][p] = g[a][2]; }
+    const double S = sabs_of(g);
+    d.s[S_SABS][p] = S;
+    les_derive_store(d, p, g, S);
     double uf[3];
     if (d.testfilter_ik) {
       for (int a = 0; a < 3; a++) {
@@ -88,18 +124,11 @@ struct LesPass1 {
 // v[0] = w, v[1..9] = U_a u_b (a-major), v[10..15] = |S| S_ij (xx,xy,xz,yy,yz,zz)
 #define VFS_LES2_NV 16
 VFS_HD void les2_products(const VfsDev &d, long n, double *v) {
-  v[0] = (d.s[S_NV][n] > 0.1) ? 0. : 1. / d.s[S_AJ][n];
+  v[0] = d.s[S_LW][n];
   const double u[3] = {d.s[S_U0][n], d.s[S_U1][n], d.s[S_U2][n]};
-  const double U[3] = {u[0] * d.s[S_CSI0][n] + u[1] * d.s[S_CSI1][n] + u[2] * d.s[S_CSI2][n],
-                       u[0] * d.s[S_ETA0][n] + u[1] * d.s[S_ETA1][n] + u[2] * d.s[S_ETA2][n],
-                       u[0] * d.s[S_ZET0][n] + u[1] * d.s[S_ZET1][n] + u[2] * d.s[S_ZET2][n]};
+  const double U[3] = {d.s[S_LU0][n], d.s[S_LU1][n], d.s[S_LU2][n]};
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) v[1 + 3 * a + b] = U[a] * u[b];
-  const double S = d.s[S_SABS][n];
-  const double ax0 = d.s[S_AX0][n], ax1 = d.s[S_AX1][n], ax2 = d.s[S_AX2][n];
-  const double ay0 = d.s[S_AY0][n], ay1 = d.s[S_AY1][n], ay2 = d.s[S_AY2][n];
-  const double az0 = d.s[S_AZ0][n], az1 = d.s[S_AZ1][n], az2 = d.s[S_AZ2][n];
-  v[10] = (0.5 * (ax0 + ax0)) * S; v[11] = (0.5 * (ax1 + ay0)) * S; v[12] = (0.5 * (ax2 + az0)) * S;
-  v[13] = (0.5 * (ay1 + ay1)) * S; v[14] = (0.5 * (ay2 + az1)) * S; v[15] = (0.5 * (az2 + az2)) * S;
+  for (int a = 0; a < 6; a++) v[10 + a] = d.s[S_LSS0 + a][n];
 }
 
 // les.c:441-669 after the filters: fs[0] = sum of Simpson weights (or 36 for testfilter_ik),
@@ -110,8 +139,8 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
   const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
   const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
   const double fdiv = fs[0];
-  const double filter = pow(1. / ajc, 1. / 3.);
-  const double test_filter = d.testfilter_ik ? pow(5.0, 1. / 3.) * filter : pow(sum_weight, 1. / 3.);
+  const double filter = VFS_CBRT(1. / ajc);
+  const double test_filter = d.testfilter_ik ? 1.709975946676697 /* pow(5, 1./3.) */ * filter : VFS_CBRT(sum_weight);
   const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
   const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
   double gh[3][3];
@@ -138,7 +167,7 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
   G[0][2] = G[2][0] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
   G[1][2] = G[2][1] = xeta * xzet + yeta * yzet + zeta * zzet;
   double Mc[3][3], M[3][3];
-  const double tf2 = pow(test_filter, 2.), f2 = pow(filter, 2.);
+  const double tf2 = test_filter * test_filter, f2 = filter * filter;   // == pow(x, 2.) (correctly rounded)
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Mc[a][b] = -tf2 * S_hat * Sh[a][b] + f2 * SSh[a][b];
   for (int a = 0; a < 3; a++) {
     M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
@@ -257,8 +286,8 @@ struct NuT {
     double g[3][3];
     grad_center(d, S_U0, i, j, kg, p, g);
     const double Sabs = sabs_of(g);
-    const double filter = pow(1. / d.s[S_AJ][p], 1. / 3.);
-    double v = d.s[S_CS][p] * pow(filter, 2.0) * Sabs;
+    const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
+    double v = d.s[S_CS][p] * (filter * filter) * Sabs;
     if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
     d.s[S_NUT][p] = v;
   }
