@@ -49,6 +49,7 @@ struct vfs_ctx {
   int fused = 1;                 // use the TMA-staged tiled kernels when applicable
 #ifndef VFS_EMU
   CUtensorMap tmap;              // 4-D map over the scalar pool, box (TX+2, TY+2, 1, 1)
+  CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
 #endif
   bool tma_ok = false;
 };
@@ -188,7 +189,8 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
 #endif
   for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
 #ifndef VFS_EMU
-  c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0;
+  c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
+              vfs_make_tensor_map(&c->tmap_flux, c->pool, c->d, c->scalar_len, VFS_TILE_TX + VFS_FLUX_HX, VFS_TILE_TY + VFS_FLUX_HY) == 0;
 #endif
   *out = c;
   return 0;
@@ -378,9 +380,22 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     ev_rec(c, 2 * VFS_T_FLUX + 1);
     return 0;
   }
-  { FaceFlux<0> f = {d}; Box b = {0, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
-  { FaceFlux<1> f = {d}; Box b = {1, d.mx - 1, 0, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
-  { FaceFlux<2> f = {d}; Box b = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2}; RUN(launch(c, b, f)); }
+#ifndef VFS_EMU
+  if (c->fused && c->tma_ok) {
+    // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
+    if (launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, &c->launches)) { set_err(c, "k_flux_tma launch failed"); return VFS_ERR_CUDA; }
+    { FaceFlux<0> f = {d}; Box b0 = {0, 1, 1, d.my - 1, k1, k2}, b1 = {d.mx - 2, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    { FaceFlux<1> f = {d}; Box b0 = {1, d.mx - 1, 0, 1, k1, k2}, b1 = {1, d.mx - 1, d.my - 2, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    { FaceFlux<2> f = {d};
+      Box b0 = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), klo(c, 1)}, b1 = {1, d.mx - 1, 1, d.my - 1, klo(c, d.mz - 2), klo(c, d.mz - 1)};
+      RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  } else
+#endif
+  {
+    { FaceFlux<0> f = {d}; Box b = {0, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
+    { FaceFlux<1> f = {d}; Box b = {1, d.mx - 1, 0, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
+    { FaceFlux<2> f = {d}; Box b = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2}; RUN(launch(c, b, f)); }
+  }
   ev_rec(c, 2 * VFS_T_FLUX + 1);
   Grp gf = grp(S_FC1, 18);
   RUN(g2l(c, gf));                                                    // momentum.c:1458-1496

@@ -13,6 +13,7 @@
 #define VFS_FUSED_KERNELS_H
 #include "vfs_common.h"
 #include "vfs_les_kernels.h"
+#include "vfs_rhs_kernels.h"
 
 #ifndef VFS_EMU
 #include <cuda.h>
@@ -67,8 +68,8 @@ static inline int vfs_make_tensor_map(CUtensorMap *map, void *pool, const VfsDev
 
 // ---- generic ring of TMA-staged planes ----------------------------------------------------------------
 // NS scalars per plane, each tile padded to a 128-byte multiple (TMA destination alignment).
-template <int TX, int TY, int NS, int STAGES> struct PlaneRing {
-  static constexpr int NXP = TX + 2, NYP = TY + 2, NN = NXP * NYP;
+template <int TX, int TY, int NS, int STAGES, int HX = 2, int HY = 2> struct PlaneRing {
+  static constexpr int NXP = TX + HX, NYP = TY + HY, NN = NXP * NYP;
   static constexpr int TILE_B = ((NN * 8 + 127) / 128) * 128;
   static constexpr int TILE_D = TILE_B / 8;                 // doubles per padded scalar tile
   static constexpr int PLANE_D = TILE_D * NS;
@@ -78,7 +79,7 @@ template <int TX, int TY, int NS, int STAGES> struct PlaneRing {
 // ---- LES pass 2 (les.c:308-669) --------------------------------------------------------------------------
 // staged scalars per node: ucat(3), w, U(3), |S|S_ij(6)  (vfs_les_kernels.h: les_derive_store)
 template <int TX, int TY, int STAGES>
-__global__ void __launch_bounds__(TX *TY) k_les2_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
+__global__ void __launch_bounds__(TX *TY, 2) k_les2_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
   typedef PlaneRing<TX, TY, 13, STAGES> R;
   extern __shared__ __align__(128) unsigned char smraw[];
   double *sm = reinterpret_cast<double *>(smraw);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(TX *TY) k_les2_tma(const __grid_constant__ CUt
 }
 
 static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *launches) {
-  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = 4;
+  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = 3;   // 3 x 36.6 KB: two blocks per SM
   if (k1 <= k0) return 0;
   const size_t smem = PlaneRing<TX, TY, 13, STAGES>::BYTES;
   static bool attr_set = false;
@@ -166,9 +167,110 @@ static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, cons
     if (cudaFuncSetAttribute(k_les2_tma<TX, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
     attr_set = true;
   }
-  const int kchunk = 32;
+  const int kchunk = 64;
   dim3 grd((d.mx - 2 + TX - 1) / TX, (d.my - 2 + TY - 1) / TY, (k1 - k0 + kchunk - 1) / kchunk), blk(TX, TY, 1);
   k_les2_tma<TX, TY, STAGES><<<grd, blk, smem, st>>>(tmap, d, k0, k1, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+// ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
+// One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
+// planes P-1..P+2 staged by TMA: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets
+// -1..TX+2 in i (4th-order stencil of the i-face) and -1..TY+1 in j.  Faces with index 0 or m-2 along
+// their normal (domain-end / periodic-end stencils) are left to the staged FaceFlux<D> kernels, which
+// the host runs on those thin slabs only.
+#define VFS_FLUX_HX 4
+#define VFS_FLUX_HY 3
+template <int TX, int TY, int STAGES> struct SmemAcc {
+  typedef PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY> R;
+  const double *sm; int n0, x, y;      // n0: ring index of the node's own plane; (x,y): tile position incl. halo
+  __device__ __forceinline__ double get(int s, int di, int dj, int dk) const {
+    return sm[(size_t)((n0 + dk) % STAGES) * R::PLANE_D + s * R::TILE_D + (y + dj) * R::NXP + (x + di)];
+  }
+  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return get(a, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return get(3, di, dj, dk); }
+};
+
+template <int TX, int TY, int STAGES>
+__global__ void __launch_bounds__(TX *TY, 2) k_flux_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
+  typedef PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY> R;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *sm = reinterpret_cast<double *>(smraw);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw + (size_t)STAGES * R::PLANE_D * 8);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+  const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
+  const int ka = kbeg + blockIdx.z * kchunk;
+  const int kb = min(kend, ka + kchunk);
+  if (ka >= kb) return;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = (i <= d.mx - 2) && (j <= d.my - 2);
+  const int sid[4] = {S_U0, S_U1, S_U2, S_NV};
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // ring index n = kk - (ka-1): plane kk in slot n % STAGES, barrier phase (n / STAGES) & 1
+  auto issue = [&](int kk) {
+    const int n = kk - (ka - 1), slot = n % STAGES;
+    double *dst = sm + (size_t)slot * R::PLANE_D;
+    mbar_expect_tx(&bars[slot], 4 * R::NN * 8);
+#pragma unroll
+    for (int s = 0; s < 4; s++) tma_load_tile(dst + s * R::TILE_D, &tmap, i0 - 1 + VFS_G, j0 - 1 + VFS_G, kk + VFS_G, sid[s], &bars[slot]);
+  };
+  auto wait_plane = [&](int kk) {
+    const int n = kk - (ka - 1);
+    mbar_wait(&bars[n % STAGES], (n / STAGES) & 1);
+  };
+  const int klast = kb - 1 + 2;                   // last plane any step needs
+  if (tid == 0) {
+    for (int kk = ka - 1; kk < ka - 1 + STAGES && kk <= klast; kk++) issue(kk);
+  }
+  wait_plane(ka - 1); wait_plane(ka); wait_plane(ka + 1);
+  for (int k = ka; k < kb; k++) {
+    wait_plane(k + 2);
+    if (active) {
+      const int kg = k + d.kofs;
+      const long p = d.idx(i, j, k);
+      SmemAcc<TX, TY, STAGES> A = {sm, k - (ka - 1), tx + 1, ty + 1};
+      double fc[3], fv[3];
+      if (i <= d.mx - 3) {
+        face_flux_core<0, true>(d, A, p, i, fc, fv);
+#pragma unroll
+        for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
+      }
+      if (j <= d.my - 3) {
+        face_flux_core<1, true>(d, A, p, j, fc, fv);
+#pragma unroll
+        for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
+      }
+      if (kg <= d.mz - 3) {
+        face_flux_core<2, true>(d, A, p, kg, fc, fv);
+#pragma unroll
+        for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
+      }
+    }
+    __syncthreads();                         // plane k-1 is no longer needed by anyone
+    if (tid == 0) {
+      const int kn = k - 1 + STAGES;
+      if (kn <= klast) { fence_proxy_async(); issue(kn); }
+    }
+  }
+}
+
+#define VFS_FLUX_STAGES 5
+static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *launches) {
+  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = VFS_FLUX_STAGES;
+  if (k1 <= k0) return 0;
+  const size_t smem = PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY>::BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_flux_tma<TX, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  const int kchunk = 64;
+  dim3 grd((d.mx - 2 + TX - 1) / TX, (d.my - 2 + TY - 1) / TY, (k1 - k0 + kchunk - 1) / kchunk), blk(TX, TY, 1);
+  k_flux_tma<TX, TY, STAGES><<<grd, blk, smem, st>>>(tmap, d, k0, k1, kchunk);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

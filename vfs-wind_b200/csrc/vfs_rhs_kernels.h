@@ -12,102 +12,138 @@
 
 #define VFS_SOLID 0.1
 
-// tangential difference of scalar plane u along stride st at the face between p and pn
-VFS_HD double dtan(const double *u, const double *nv, long p, long pn, long st) {
-  if (nv[p + st] > VFS_SOLID || nv[pn + st] > VFS_SOLID) return (u[pn] + u[p] - u[pn - st] - u[p - st]) * 0.5;
-  else if (nv[p - st] > VFS_SOLID || nv[pn - st] > VFS_SOLID) return (u[pn + st] + u[p + st] - u[pn] - u[p]) * 0.5;
-  else return (u[pn + st] + u[p + st] - u[pn - st] - u[p - st]) * 0.25;
+// Accessor over the global padded arrays: offsets (di,dj,dk) are relative to the face's node p.
+// The tiled kernels (vfs_fused_kernels.h) supply an accessor over TMA-staged shared-memory planes
+// with the same interface, so both forms run the identical arithmetic below.
+struct GlobalAcc {
+  const VfsDev &d; long p;
+  VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S_U0 + a][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
+};
+
+// tangential difference of component a along unit direction T at the face between node offset
+// (0,0,0) and its neighbour in direction D  (k-omega.c:56-311, `solid` = 0.1)
+template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a) {
+  constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);      // pn = p + n
+  constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
+  if (A.nv(ti, tj, tk) > VFS_SOLID || A.nv(ni + ti, nj + tj, nk + tk) > VFS_SOLID)
+    return (A.u(a, ni, nj, nk) + A.u(a, 0, 0, 0) - A.u(a, ni - ti, nj - tj, nk - tk) - A.u(a, -ti, -tj, -tk)) * 0.5;
+  else if (A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID)
+    return (A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk) - A.u(a, ni, nj, nk) - A.u(a, 0, 0, 0)) * 0.5;
+  else
+    return (A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk) - A.u(a, ni - ti, nj - tj, nk - tk) - A.u(a, -ti, -tj, -tk)) * 0.25;
 }
 
-// One face family.  D = 0/1/2 for i-/j-/k-faces; the face sits between node p and p + stride(D)
-// and is stored at p ("upper integer node", momentum.c:508-509).
+// One face of family D (0/1/2 = i-/j-/k-face) between node p and p + e_D, stored at p ("upper
+// integer node", momentum.c:508-509).  c = index of p along D (global), m = node count along D.
+// REGULAR = true compiles out the domain-end / periodic-end special cases (faces 1..m-3 only).
+// Metrics, nu_t and ucont are read from the global arrays at p and p + e_D.
+template <int D, bool REGULAR, class Acc>
+VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, long p, int c, double fc[3], double fv[3]) {
+  constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);
+  const long sn = (D == 0 ? 1 : (D == 1 ? d.sj : d.sk));
+  const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
+  const int per = (D == 0 ? d.perx : (D == 1 ? d.pery : d.perz));
+  const long pn = p + sn;
+  const double nvp = A.nv(0, 0, 0), nvn = A.nv(ni, nj, nk);
+
+  // face metrics (metrics.c:589-592 and j/k twins)
+  const V3 cs = face3(d, S_CSI0, p, pn), et = face3(d, S_ETA0, p, pn), ze = face3(d, S_ZET0, p, pn);
+  const double ajc = 2. / (1. / d.s[S_AJ][p] + 1. / d.s[S_AJ][pn]);
+  const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
+
+  // du[a][b] = d u_a / d xi_b  (b: csi, eta, zet)
+  double du[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const double dn = A.u(a, ni, nj, nk) - A.u(a, 0, 0, 0);
+    if (D == 0) { du[a][0] = dn; du[a][1] = dtan<D, 1>(A, a); du[a][2] = dtan<D, 2>(A, a); }
+    else if (D == 1) { du[a][0] = dtan<D, 0>(A, a); du[a][1] = dn; du[a][2] = dtan<D, 2>(A, a); }
+    else { du[a][0] = dtan<D, 0>(A, a); du[a][1] = dtan<D, 1>(A, a); du[a][2] = dn; }
+  }
+  const double g1 = cs.x * n.x + cs.y * n.y + cs.z * n.z;
+  const double g2 = et.x * n.x + et.y * n.y + et.z * n.z;
+  const double g3 = ze.x * n.x + ze.y * n.y + ze.z * n.z;
+  // r[a][b] = du_a/dx_b * J   (momentum.c:686-696)
+  double r[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    r[a][0] = du[a][0] * cs.x + du[a][1] * et.x + du[a][2] * ze.x;
+    r[a][1] = du[a][0] * cs.y + du[a][1] * et.y + du[a][2] * ze.y;
+    r[a][2] = du[a][0] * cs.z + du[a][1] * et.z + du[a][2] * ze.z;
+  }
+
+  // ---- convective flux (momentum.c:700-813) ----
+  int oL = -1, oR = 2;                                   // offsets along D of the outer stencil nodes
+  if (!REGULAR && (c == 0 || c == m - 2)) {
+    if (per && c == m - 2) oR = 4;                       // index m+2
+    else if (per && c == 0) oL = -3;                     // index -3
+    else oL = 0, oR = 1;
+  } else if (A.nv(oL * ni, oL * nj, oL * nk) + A.nv(oR * ni, oR * nj, oR * nk) > 0.1) oL = 0, oR = 1;
+  if (d.second_order) oL = 0, oR = 1;
+
+  const double *UC = d.s[S_UC0 + D];
+  double ucon = UC[p];
+  if (!REGULAR) {
+    if (per && c == 0) ucon = UC[p - 2 * sn];
+    if (D == 2 && c == m - 2 && d.bc[5] == 4 && (int)nvp == 0) ucon = UC[p - sn];
+  }
+  const double up = -0.5 * (ucon + fabs(ucon));
+  const double um = -0.5 * (ucon - fabs(ucon));
+  if (d.immersed && (REGULAR || c != m - 2) && nvp > 0.1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const double u0 = A.u(a, 0, 0, 0), u1 = A.u(a, ni, nj, nk), u2 = A.u(a, 2 * ni, 2 * nj, 2 * nk);
+      fc[a] = um * (0.125 * (-u2 - 2. * u1 + 3. * u0) + u1) + up * (0.125 * (-u0 - 2. * u0 + 3. * u1) + u0);
+    }
+  } else if (d.immersed && (REGULAR || c != 0) && nvn > 0.1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const double u0 = A.u(a, 0, 0, 0), u1 = A.u(a, ni, nj, nk), um1 = A.u(a, -ni, -nj, -nk);
+      fc[a] = um * (0.125 * (-u1 - 2. * u1 + 3. * u0) + u1) + up * (0.125 * (-um1 - 2. * u0 + 3. * u1) + u0);
+    }
+  } else if (d.second_order) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.5 * (A.u(a, 0, 0, 0) + A.u(a, ni, nj, nk));
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      fc[a] = -UC[p] * 0.0625 * (-A.u(a, oL * ni, oL * nj, oL * nk) + 9. * A.u(a, 0, 0, 0) + 9. * A.u(a, ni, nj, nk) - A.u(a, oR * ni, oR * nj, oR * nk));
+  }
+  if (nvp + nvn > 0.1 && (d.immersed == 3 || !d.immersed)) fc[0] = fc[1] = fc[2] = 0;
+
+  // ---- viscous + SGS flux (momentum.c:856-902) ----
+  const double nu = 1. / d.ren;
+  fv[0] = fv[1] = fv[2] = 0;
+  if (d.les) {
+    const double *nt = d.s[S_NUT];
+    double nu_t;
+    if ((!REGULAR && c == 0 && !per) || nvp > 0.1) nu_t = nt[pn];
+    else if ((!REGULAR && c == m - 2 && !per) || nvn > 0.1) nu_t = nt[p];
+    else nu_t = 0.5 * (nt[p] + nt[pn]);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      fv[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu_t;
+  }
+  if (d.laplacian) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + 0. * n.x + 0. * n.y + 0. * n.z) * ajc * nu;
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu;
+  }
+}
+
 template <int D> struct FaceFlux {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
-    const long st[3] = {1, d.sj, d.sk};
-    const long sn = st[D];
-    const int c = (D == 0 ? i : (D == 1 ? j : kg));
-    const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
-    const int per = (D == 0 ? d.perx : (D == 1 ? d.pery : d.perz));
-    const long p = d.idx(i, j, k), pn = p + sn;
-    const double *nv = d.s[S_NV];
-    const double *U[3] = {d.s[S_U0], d.s[S_U1], d.s[S_U2]};
-
-    // face metrics (metrics.c:589-592 and j/k twins)
-    const V3 cs = face3(d, S_CSI0, p, pn), et = face3(d, S_ETA0, p, pn), ze = face3(d, S_ZET0, p, pn);
-    const double ajc = 2. / (1. / d.s[S_AJ][p] + 1. / d.s[S_AJ][pn]);
-    const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
-
-    // du[a][b] = d u_a / d xi_b  (b: csi, eta, zet)
-    double du[3][3];
-    for (int a = 0; a < 3; a++) {
-      for (int b = 0; b < 3; b++) {
-        if (b == D) du[a][b] = U[a][pn] - U[a][p];
-        else du[a][b] = dtan(U[a], nv, p, pn, st[b]);
-      }
-    }
-    const double g1 = cs.x * n.x + cs.y * n.y + cs.z * n.z;
-    const double g2 = et.x * n.x + et.y * n.y + et.z * n.z;
-    const double g3 = ze.x * n.x + ze.y * n.y + ze.z * n.z;
-    // r[a][b] = du_a/dx_b * J   (momentum.c:686-696)
-    double r[3][3];
-    for (int a = 0; a < 3; a++) {
-      r[a][0] = du[a][0] * cs.x + du[a][1] * et.x + du[a][2] * ze.x;
-      r[a][1] = du[a][0] * cs.y + du[a][1] * et.y + du[a][2] * ze.y;
-      r[a][2] = du[a][0] * cs.z + du[a][1] * et.z + du[a][2] * ze.z;
-    }
-
-    // ---- convective flux (momentum.c:700-813) ----
-    long pL = p - sn, pR = p + 2 * sn;
-    if (c == 0 || c == m - 2) {
-      if (per && c == m - 2) pR = p + 4 * sn;          // index m+2
-      else if (per && c == 0) pL = p - 3 * sn;         // index -3
-      else pL = p, pR = pn;
-    } else if (nv[pL] + nv[pR] > 0.1) pL = p, pR = pn;
-    if (d.second_order) pL = p, pR = pn;
-
-    const double *UC = d.s[S_UC0 + D];
-    double ucon = UC[p];
-    if (per && c == 0) ucon = UC[p - 2 * sn];
-    if (D == 2 && c == m - 2 && d.bc[5] == 4 && (int)nv[p] == 0) ucon = UC[p - sn];
-    const double up = -0.5 * (ucon + fabs(ucon));
-    const double um = -0.5 * (ucon - fabs(ucon));
-    double fc[3];
-    if (d.immersed && c != m - 2 && nv[p] > 0.1) {
-      for (int a = 0; a < 3; a++)
-        fc[a] = um * (0.125 * (-U[a][p + 2 * sn] - 2. * U[a][pn] + 3. * U[a][p]) + U[a][pn]) +
-                up * (0.125 * (-U[a][p] - 2. * U[a][p] + 3. * U[a][pn]) + U[a][p]);
-    } else if (d.immersed && c != 0 && nv[pn] > 0.1) {
-      for (int a = 0; a < 3; a++)
-        fc[a] = um * (0.125 * (-U[a][pn] - 2. * U[a][pn] + 3. * U[a][p]) + U[a][pn]) +
-                up * (0.125 * (-U[a][p - sn] - 2. * U[a][p] + 3. * U[a][pn]) + U[a][p]);
-    } else if (d.second_order) {
-      for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.5 * (U[a][p] + U[a][pn]);
-    } else {
-      for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.0625 * (-U[a][pL] + 9. * U[a][p] + 9. * U[a][pn] - U[a][pR]);
-    }
-    if (nv[p] + nv[pn] > 0.1 && (d.immersed == 3 || !d.immersed)) fc[0] = fc[1] = fc[2] = 0;
-
-    // ---- viscous + SGS flux (momentum.c:856-902) ----
-    const double nu = 1. / d.ren;
-    double fv[3] = {0, 0, 0};
-    if (d.les) {
-      const double *nt = d.s[S_NUT];
-      double nu_t;
-      if ((c == 0 && !per) || nv[p] > 0.1) nu_t = nt[pn];
-      else if ((c == m - 2 && !per) || nv[pn] > 0.1) nu_t = nt[p];
-      else nu_t = 0.5 * (nt[p] + nt[pn]);
-      for (int a = 0; a < 3; a++)
-        fv[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu_t;
-    }
-    if (d.laplacian) {
-      for (int a = 0; a < 3; a++)
-        fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + 0. * n.x + 0. * n.y + 0. * n.z) * ajc * nu;
-    } else {
-      for (int a = 0; a < 3; a++)
-        fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu;
-    }
+    const int c = (D == 0 ? i : (D == 1 ? j : k + d.kofs));
+    const long p = d.idx(i, j, k);
+    GlobalAcc A = {d, p};
+    double fc[3], fv[3];
+    face_flux_core<D, false>(d, A, p, c, fc, fv);
     const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D;
     for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
   }
