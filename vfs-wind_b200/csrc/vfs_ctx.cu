@@ -52,6 +52,7 @@ struct vfs_ctx {
   CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
 #endif
   bool tma_ok = false;
+  bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
 };
 
 static void set_err(vfs_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_err = m; }
@@ -278,6 +279,7 @@ extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
 }
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
@@ -328,6 +330,7 @@ static int run_les_derive_boundary(vfs_ctx *c, const Box &b, void *) { LesDerive
 
 static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
+  c->sabs_valid = false;
   Grp gu = grp(S_U0, 3);
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // rhs.c:129-156
   ev_rec(c, 2 * VFS_T_C2C);
@@ -475,11 +478,19 @@ static int zero_scalars(vfs_ctx *c, int s0, int n) {
 static int les_cs(vfs_ctx *c) {
   const VfsDev &d = c->d;
   Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
+  c->sabs_valid = false;
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   ev_rec(c, 2 * VFS_T_LES1);
+#ifndef VFS_EMU
+  if (c->fused && c->tma_ok && !d.testfilter_ik) {
+    Box bi = box_interior(c);
+    if (launch_les1_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "les1 tile kernel launch failed"); return VFS_ERR_CUDA; }
+  } else
+#endif
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
+  c->sabs_valid = true;
   RUN(for_boundary_planes(c, run_les_derive_boundary, 0));
   Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
   RUN(g2l(c, g1));                                                    // les.c:254-267
@@ -499,6 +510,19 @@ static int les_cs(vfs_ctx *c) {
   RUN(g2l(c, g2));                                                    // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
   ev_rec(c, 2 * VFS_T_LES3);
+#ifndef VFS_EMU
+  if (c->fused && c->tma_ok && !d.testfilter_ik) {
+    Box bi = box_interior(c);
+    if (launch_les3_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 tile kernel launch failed"); return VFS_ERR_CUDA; }
+    LesPass3 f = {d};      // cells next to a periodic plane (ghost-image fetches): thin slabs
+    if (d.perx) { Box b0 = bi, b1 = bi; b0.i1 = 2; b1.i0 = d.mx - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    if (d.pery) { Box b0 = bi, b1 = bi; b0.j1 = 2; b1.j0 = d.my - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    if (d.perz) {
+      Box b0 = bi, b1 = bi; b0.k0 = klo(c, 1); b0.k1 = klo(c, 2); b1.k0 = klo(c, d.mz - 2); b1.k1 = klo(c, d.mz - 1);
+      RUN(launch(c, b0, f)); RUN(launch(c, b1, f));
+    }
+  } else
+#endif
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
   { LesClip f = {d}; RUN(launch(c, box_owned(c), f)); }              // les.c:967-980
@@ -510,7 +534,8 @@ static int les_cs(vfs_ctx *c) {
 static int les_nut(vfs_ctx *c) {
   const VfsDev &d = c->d;
   ev_rec(c, 2 * VFS_T_NUT);
-  { NuT f = {d}; RUN(launch(c, box_interior(c), f)); }
+  if (c->sabs_valid) { NuT<true> f = {d}; RUN(launch(c, box_interior(c), f)); }
+  else { NuT<false> f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_NUT + 1);
   Grp g = grp(S_NUT, 1);
   RUN(g2l(c, g));                                                     // les.c:1320-1321

@@ -67,136 +67,37 @@ static inline int vfs_make_tensor_map(CUtensorMap *map, void *pool, const VfsDev
 }
 
 // ---- generic ring of TMA-staged planes ----------------------------------------------------------------
-// NS scalars per plane, each tile padded to a 128-byte multiple (TMA destination alignment).
-template <int TX, int TY, int NS, int STAGES, int HX = 2, int HY = 2> struct PlaneRing {
+// NS scalars per plane; tile of (TX+HX) x (TY+HY) nodes whose origin is (OX, OY) nodes before the
+// block's first cell; each scalar tile is padded to a 128-byte multiple (TMA destination alignment).
+template <int TX_, int TY_, int NS_, int STAGES_, int HX, int HY, int OX_, int OY_, int PB_, int PA_> struct Ring {
+  static constexpr int TX = TX_, TY = TY_, NS = NS_, STAGES = STAGES_, OX = OX_, OY = OY_, PB = PB_, PA = PA_;
   static constexpr int NXP = TX + HX, NYP = TY + HY, NN = NXP * NYP;
   static constexpr int TILE_B = ((NN * 8 + 127) / 128) * 128;
   static constexpr int TILE_D = TILE_B / 8;                 // doubles per padded scalar tile
   static constexpr int PLANE_D = TILE_D * NS;
   static constexpr size_t BYTES = (size_t)STAGES * PLANE_D * 8 + STAGES * 8;
+  static_assert(STAGES >= PB + PA + 1, "ring too short");
+  static_assert((NXP * 8) % 16 == 0, "TMA box inner extent must be a multiple of 16 bytes");
 };
+struct SidList { int n; int sid[16]; };
 
-// ---- LES pass 2 (les.c:308-669) --------------------------------------------------------------------------
-// staged scalars per node: ucat(3), w, U(3), |S|S_ij(6)  (vfs_les_kernels.h: les_derive_store)
-template <int TX, int TY, int STAGES>
-__global__ void __launch_bounds__(TX *TY, 2) k_les2_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
-  typedef PlaneRing<TX, TY, 13, STAGES> R;
-  extern __shared__ __align__(128) unsigned char smraw[];
-  double *sm = reinterpret_cast<double *>(smraw);
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw + (size_t)STAGES * R::PLANE_D * 8);
-  constexpr int NXP = R::NXP, TD = R::TILE_D, NV = VFS_LES2_NV;
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-  const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
-  const int ka = kbeg + blockIdx.z * kchunk;
-  const int kb = min(kend, ka + kchunk);
-  if (ka >= kb) return;
-  const int i = i0 + tx, j = j0 + ty;
-  const bool active = (i <= d.mx - 2) && (j <= d.my - 2);
-  const int sid[13] = {S_U0, S_U1, S_U2, S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5};
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  // plane kk lives in slot (kk - (ka-1)) % STAGES; its barrier completes phase ((kk-(ka-1))/STAGES)&1
-  auto issue = [&](int kk) {
-    const int n = kk - (ka - 1), slot = n % STAGES;
-    double *dst = sm + (size_t)slot * R::PLANE_D;
-    mbar_expect_tx(&bars[slot], 13 * R::NN * 8);
-#pragma unroll
-    for (int s = 0; s < 13; s++) tma_load_tile(dst + s * TD, &tmap, i0 - 1 + VFS_G, j0 - 1 + VFS_G, kk + VFS_G, sid[s], &bars[slot]);
-  };
-  auto wait_plane = [&](int kk) {
-    const int n = kk - (ka - 1);
-    mbar_wait(&bars[n % STAGES], (n / STAGES) & 1);
-  };
-  if (tid == 0) {
-    for (int kk = ka - 1; kk < ka - 1 + STAGES && kk <= kb; kk++) issue(kk);
-  }
-  wait_plane(ka - 1);
-  wait_plane(ka);
-  for (int k = ka; k < kb; k++) {
-    wait_plane(k + 1);
-    if (active) {
-      const long p = d.idx(i, j, k);
-      if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; }
-      else {
-        double fs[NV], sum_weight = 0;
-#pragma unroll
-        for (int a = 0; a < NV; a++) fs[a] = 0;
-#pragma unroll
-        for (int r = -1; r <= 1; r++) {
-          const double *pl = sm + (size_t)((k + r - (ka - 1)) % STAGES) * R::PLANE_D;
-#pragma unroll
-          for (int q = -1; q <= 1; q++) {
-#pragma unroll
-            for (int pp = -1; pp <= 1; pp++) {
-              const int n = (ty + 1 + q) * NXP + (tx + 1 + pp);
-              const double w = pl[3 * TD + n];
-              sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));
-              const double sw = simpson_w(r, q, pp) * w;
-              fs[0] += sw;
-              const double u0 = pl[n], u1 = pl[TD + n], u2 = pl[2 * TD + n];
-              const double U0 = pl[4 * TD + n], U1 = pl[5 * TD + n], U2 = pl[6 * TD + n];
-              fs[1] += sw * (U0 * u0); fs[2] += sw * (U0 * u1); fs[3] += sw * (U0 * u2);
-              fs[4] += sw * (U1 * u0); fs[5] += sw * (U1 * u1); fs[6] += sw * (U1 * u2);
-              fs[7] += sw * (U2 * u0); fs[8] += sw * (U2 * u1); fs[9] += sw * (U2 * u2);
-#pragma unroll
-              for (int a = 0; a < 6; a++) fs[10 + a] += sw * pl[(7 + a) * TD + n];
-            }
-          }
-        }
-        les2_finish(d, i, j, k + d.kofs, p, fs, sum_weight);
-      }
-    }
-    __syncthreads();                         // everyone is done reading plane k-1: its slot is free
-    if (tid == 0) {
-      const int kn = k - 1 + STAGES;         // next plane for that slot
-      if (kn <= kb) { fence_proxy_async(); issue(kn); }
-    }
-  }
-}
-
-static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *launches) {
-  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = 3;   // 3 x 36.6 KB: two blocks per SM
-  if (k1 <= k0) return 0;
-  const size_t smem = PlaneRing<TX, TY, 13, STAGES>::BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_les2_tma<TX, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-    attr_set = true;
-  }
-  const int kchunk = 64;
-  dim3 grd((d.mx - 2 + TX - 1) / TX, (d.my - 2 + TY - 1) / TY, (k1 - k0 + kchunk - 1) / kchunk), blk(TX, TY, 1);
-  k_les2_tma<TX, TY, STAGES><<<grd, blk, smem, st>>>(tmap, d, k0, k1, kchunk);
-  (*launches)++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-// ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
-// One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
-// planes P-1..P+2 staged by TMA: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets
-// -1..TX+2 in i (4th-order stencil of the i-face) and -1..TY+1 in j.  Faces with index 0 or m-2 along
-// their normal (domain-end / periodic-end stencils) are left to the staged FaceFlux<D> kernels, which
-// the host runs on those thin slabs only.
-#define VFS_FLUX_HX 4
-#define VFS_FLUX_HY 3
-template <int TX, int TY, int STAGES> struct SmemAcc {
-  typedef PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY> R;
-  const double *sm; int n0, x, y;      // n0: ring index of the node's own plane; (x,y): tile position incl. halo
+// accessor over the ring: scalar slot s at node offset (di,dj,dk) from the thread's cell
+template <class R> struct TileAcc {
+  const double *sm; int n0, x, y;      // n0: ring index of the cell's own plane; (x,y): tile position incl. halo
   __device__ __forceinline__ double get(int s, int di, int dj, int dk) const {
-    return sm[(size_t)((n0 + dk) % STAGES) * R::PLANE_D + s * R::TILE_D + (y + dj) * R::NXP + (x + di)];
+    return sm[(size_t)((n0 + dk) % R::STAGES) * R::PLANE_D + s * R::TILE_D + (y + dj) * R::NXP + (x + di)];
   }
-  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return get(a, di, dj, dk); }
-  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return get(3, di, dj, dk); }
 };
 
-template <int TX, int TY, int STAGES>
-__global__ void __launch_bounds__(TX *TY, 2) k_flux_tma(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk) {
-  typedef PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY> R;
+// Block = (i,j) tile, marches k in [ka,kb).  At step k planes k-PB..k+PA are resident; the slot of
+// plane k-PB is refilled (plane k-PB+STAGES) as soon as the whole block has finished step k.
+template <class R, class Body>
+__global__ void __launch_bounds__(R::TX *R::TY, 2)
+k_tile_march(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk, SidList sl, Body body) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double *sm = reinterpret_cast<double *>(smraw);
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw + (size_t)STAGES * R::PLANE_D * 8);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw + (size_t)R::STAGES * R::PLANE_D * 8);
+  constexpr int TX = R::TX, TY = R::TY, STAGES = R::STAGES, PB = R::PB, PA = R::PA;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
   const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
   const int ka = kbeg + blockIdx.z * kchunk;
@@ -204,76 +105,178 @@ __global__ void __launch_bounds__(TX *TY, 2) k_flux_tma(const __grid_constant__ 
   if (ka >= kb) return;
   const int i = i0 + tx, j = j0 + ty;
   const bool active = (i <= d.mx - 2) && (j <= d.my - 2);
-  const int sid[4] = {S_U0, S_U1, S_U2, S_NV};
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  // ring index n = kk - (ka-1): plane kk in slot n % STAGES, barrier phase (n / STAGES) & 1
+  const int kfirst = ka - PB, klast = kb - 1 + PA;
+  // ring index n = kk - kfirst: plane kk in slot n % STAGES, barrier phase (n / STAGES) & 1
   auto issue = [&](int kk) {
-    const int n = kk - (ka - 1), slot = n % STAGES;
+    const int n = kk - kfirst, slot = n % STAGES;
     double *dst = sm + (size_t)slot * R::PLANE_D;
-    mbar_expect_tx(&bars[slot], 4 * R::NN * 8);
-#pragma unroll
-    for (int s = 0; s < 4; s++) tma_load_tile(dst + s * R::TILE_D, &tmap, i0 - 1 + VFS_G, j0 - 1 + VFS_G, kk + VFS_G, sid[s], &bars[slot]);
+    mbar_expect_tx(&bars[slot], R::NS * R::NN * 8);
+    for (int s = 0; s < R::NS; s++) tma_load_tile(dst + s * R::TILE_D, &tmap, i0 - R::OX + VFS_G, j0 - R::OY + VFS_G, kk + VFS_G, sl.sid[s], &bars[slot]);
   };
   auto wait_plane = [&](int kk) {
-    const int n = kk - (ka - 1);
+    const int n = kk - kfirst;
     mbar_wait(&bars[n % STAGES], (n / STAGES) & 1);
   };
-  const int klast = kb - 1 + 2;                   // last plane any step needs
   if (tid == 0) {
-    for (int kk = ka - 1; kk < ka - 1 + STAGES && kk <= klast; kk++) issue(kk);
+    for (int kk = kfirst; kk < kfirst + STAGES && kk <= klast; kk++) issue(kk);
   }
-  wait_plane(ka - 1); wait_plane(ka); wait_plane(ka + 1);
+  for (int kk = kfirst; kk < ka + PA; kk++) wait_plane(kk);
   for (int k = ka; k < kb; k++) {
-    wait_plane(k + 2);
+    wait_plane(k + PA);
     if (active) {
-      const int kg = k + d.kofs;
-      const long p = d.idx(i, j, k);
-      SmemAcc<TX, TY, STAGES> A = {sm, k - (ka - 1), tx + 1, ty + 1};
-      double fc[3], fv[3];
-      if (i <= d.mx - 3) {
-        face_flux_core<0, true>(d, A, p, i, fc, fv);
-#pragma unroll
-        for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
-      }
-      if (j <= d.my - 3) {
-        face_flux_core<1, true>(d, A, p, j, fc, fv);
-#pragma unroll
-        for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
-      }
-      if (kg <= d.mz - 3) {
-        face_flux_core<2, true>(d, A, p, kg, fc, fv);
-#pragma unroll
-        for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
-      }
+      TileAcc<R> A = {sm, k - kfirst, tx + R::OX, ty + R::OY};
+      body(d, A, i, j, k);
     }
-    __syncthreads();                         // plane k-1 is no longer needed by anyone
+    __syncthreads();                         // plane k-PB is no longer needed by anyone
     if (tid == 0) {
-      const int kn = k - 1 + STAGES;
+      const int kn = k - PB + STAGES;
       if (kn <= klast) { fence_proxy_async(); issue(kn); }
     }
   }
 }
 
-#define VFS_FLUX_STAGES 5
-static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *launches) {
-  constexpr int TX = VFS_TILE_TX, TY = VFS_TILE_TY, STAGES = VFS_FLUX_STAGES;
+template <class R, class Body>
+static inline int launch_tile_march(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, int kchunk, const SidList &sl, const Body &body, long *launches) {
   if (k1 <= k0) return 0;
-  const size_t smem = PlaneRing<TX, TY, 4, STAGES, VFS_FLUX_HX, VFS_FLUX_HY>::BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_flux_tma<TX, TY, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(k_tile_march<R, Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::BYTES) != cudaSuccess) return -2;
     attr_set = true;
   }
-  const int kchunk = 64;
-  dim3 grd((d.mx - 2 + TX - 1) / TX, (d.my - 2 + TY - 1) / TY, (k1 - k0 + kchunk - 1) / kchunk), blk(TX, TY, 1);
-  k_flux_tma<TX, TY, STAGES><<<grd, blk, smem, st>>>(tmap, d, k0, k1, kchunk);
+  dim3 grd((d.mx - 2 + R::TX - 1) / R::TX, (d.my - 2 + R::TY - 1) / R::TY, (k1 - k0 + kchunk - 1) / kchunk), blk(R::TX, R::TY, 1);
+  k_tile_march<R, Body><<<grd, blk, R::BYTES, st>>>(tmap, d, k0, k1, kchunk, sl, body);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ---- LES pass 1 (les.c:199-246): staged ucat(3), aj, nvert; 27-point box ------------------------------
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 5, 4, 2, 2, 1, 1, 1, 1> RingLes1;
+struct Les1Acc {
+  TileAcc<RingLes1> T;
+  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
+  __device__ __forceinline__ double aj(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(4, di, dj, dk); }
+};
+struct Les1Body {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k) const {
+    Les1Acc A = {T};
+    les1_core(d, A, i, j, k + d.kofs, d.idx(i, j, k));
+  }
+};
+
+// ---- LES pass 2 (les.c:308-669): staged ucat(3), w, U(3), |S|S_ij(6) -----------------------------------
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 13, 3, 2, 2, 1, 1, 1, 1> RingLes2;
+struct Les2Body {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes2> &T, int i, int j, int k) const {
+    constexpr int NV = VFS_LES2_NV;
+    const long p = d.idx(i, j, k);
+    if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
+    double fs[NV], sum_weight = 0;
+#pragma unroll
+    for (int a = 0; a < NV; a++) fs[a] = 0;
+#pragma unroll
+    for (int r = -1; r <= 1; r++)
+#pragma unroll
+      for (int q = -1; q <= 1; q++)
+#pragma unroll
+        for (int pp = -1; pp <= 1; pp++) {
+          const double w = T.get(3, pp, q, r);
+          sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));
+          const double sw = simpson_w(r, q, pp) * w;
+          fs[0] += sw;
+          const double u0 = T.get(0, pp, q, r), u1 = T.get(1, pp, q, r), u2 = T.get(2, pp, q, r);
+          const double U0 = T.get(4, pp, q, r), U1 = T.get(5, pp, q, r), U2 = T.get(6, pp, q, r);
+          fs[1] += sw * (U0 * u0); fs[2] += sw * (U0 * u1); fs[3] += sw * (U0 * u2);
+          fs[4] += sw * (U1 * u0); fs[5] += sw * (U1 * u1); fs[6] += sw * (U1 * u2);
+          fs[7] += sw * (U2 * u0); fs[8] += sw * (U2 * u1); fs[9] += sw * (U2 * u2);
+#pragma unroll
+          for (int a = 0; a < 6; a++) fs[10 + a] += sw * T.get(7 + a, pp, q, r);
+        }
+    les2_finish(d, i, j, k + d.kofs, p, fs, sum_weight);
+  }
+};
+
+// ---- LES pass 3 (les.c:716-796): staged LM, MM, aj, nvert; cells not next to a periodic plane ----------
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 4, 2, 2, 1, 1, 1, 1> RingLes3;
+struct Les3Acc {
+  TileAcc<RingLes3> T;
+  __device__ __forceinline__ double lm(int di, int dj, int dk) const { return T.get(0, di, dj, dk); }
+  __device__ __forceinline__ double mm(int di, int dj, int dk) const { return T.get(1, di, dj, dk); }
+  __device__ __forceinline__ double aj(int di, int dj, int dk) const { return T.get(2, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+};
+VFS_HD bool les3_regular(const VfsDev &d, int i, int j, int kg) {
+  return !(d.perx && (i == 1 || i == d.mx - 2)) && !(d.pery && (j == 1 || j == d.my - 2)) && !(d.perz && (kg == 1 || kg == d.mz - 2));
+}
+struct Les3Body {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    if (!les3_regular(d, i, j, kg)) return;          // done by the staged kernel on thin slabs
+    Les3Acc A = {T};
+    les3_core<true>(d, A, i, j, kg, d.idx(i, j, k));
+  }
+};
+
+// ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
+// One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
+// planes k-1..k+2: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets -1..TX+2 in i
+// (4th-order stencil of the i-face) and -1..TY+1 in j.  Faces with index 0 or m-2 along their normal
+// (domain-end / periodic-end stencils) are left to the staged FaceFlux<D> kernels, which the host runs
+// on those thin slabs only.
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 5, 4, 3, 1, 1, 1, 2> RingFlux;
+struct FluxAcc {
+  TileAcc<RingFlux> T;
+  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+};
+struct FluxBody {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    FluxAcc A = {T};
+    double fc[3], fv[3];
+    if (i <= d.mx - 3) {
+      face_flux_core<0, true>(d, A, p, i, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
+    }
+    if (j <= d.my - 3) {
+      face_flux_core<1, true>(d, A, p, j, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
+    }
+    if (kg <= d.mz - 3) {
+      face_flux_core<2, true>(d, A, p, kg, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
+    }
+  }
+};
+
+static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q = 0; q < n; q++) s.sid[q] = v[q]; return s; }
+static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
+  const int v[5] = {S_U0, S_U1, S_U2, S_AJ, S_NV};
+  return launch_tile_march<RingLes1>(st, tmap, d, k0, k1, 64, sids(5, v), Les1Body(), L);
+}
+static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
+  const int v[13] = {S_U0, S_U1, S_U2, S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5};
+  return launch_tile_march<RingLes2>(st, tmap, d, k0, k1, 64, sids(13, v), Les2Body(), L);
+}
+static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
+  const int v[4] = {S_LM, S_MM, S_AJ, S_NV};
+  return launch_tile_march<RingLes3>(st, tmap, d, k0, k1, 64, sids(4, v), Les3Body(), L);
+}
+static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
+  const int v[4] = {S_U0, S_U1, S_U2, S_NV};
+  return launch_tile_march<RingFlux>(st, tmap, d, k0, k1, 64, sids(4, v), FluxBody(), L);
+}
+#define VFS_FLUX_HX 4
+#define VFS_FLUX_HY 3
 #endif  // !VFS_EMU
 
 // fused residual kernel: not built yet (the staged FaceFlux/FpCell/Project kernels are used)

@@ -19,29 +19,44 @@
 #define VFS_CBRT(x) pow((x), 1. / 3.)
 #endif
 
-// centre difference along stride s (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
-VFS_HD double dcen(const double *u, const double *nv, long p, long s, int c, int m, int per, int lowc) {
-  if (nv[p + s] > VFS_SOLID || (!per && c == m - 2)) return u[p] - u[p - s];
-  else if (nv[p - s] > VFS_SOLID || (!per && c == lowc)) return u[p + s] - u[p];
-  else return (u[p + s] - u[p - s]) * 0.5;
+// Accessors: u(a,di,dj,dk), nv(di,dj,dk), aj(di,dj,dk) at node offsets relative to the cell.
+// GlobalAccS reads velocity-like field S0..S0+2 from the global padded arrays; the tiled kernels
+// provide the same interface over TMA-staged shared-memory planes.
+template <int S0> struct GlobalAccS {
+  const VfsDev &d; long p;
+  VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S0 + a][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double aj(int di, int dj, int dk) const { return d.s[S_AJ][p + di + dj * d.sj + dk * d.sk]; }
+};
+
+// centre difference of component a along direction T (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
+// 
+template <int T, class Acc> VFS_HD double dcen(const Acc &A, int a, int c, int m, int per, int lowc) {
+  constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
+  if (A.nv(ti, tj, tk) > VFS_SOLID || (!per && c == m - 2)) return A.u(a, 0, 0, 0) - A.u(a, -ti, -tj, -tk);
+  else if (A.nv(-ti, -tj, -tk) > VFS_SOLID || (!per && c == lowc)) return A.u(a, ti, tj, tk) - A.u(a, 0, 0, 0);
+  else return (A.u(a, ti, tj, tk) - A.u(a, -ti, -tj, -tk)) * 0.5;
 }
 
 // velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)
-VFS_HD void grad_center(const VfsDev &d, int su, int i, int j, int kg, long p, double g[3][3]) {
-  const double *nv = d.s[S_NV];
+template <class Acc> VFS_HD void grad_center_a(const VfsDev &d, const Acc &A, int i, int j, int kg, long p, double g[3][3]) {
   const double ajc = d.s[S_AJ][p];
   const double c0 = d.s[S_CSI0][p], c1 = d.s[S_CSI1][p], c2 = d.s[S_CSI2][p];
   const double e0 = d.s[S_ETA0][p], e1 = d.s[S_ETA1][p], e2 = d.s[S_ETA2][p];
   const double z0 = d.s[S_ZET0][p], z1 = d.s[S_ZET1][p], z2 = d.s[S_ZET2][p];
+#pragma unroll
   for (int a = 0; a < 3; a++) {
-    const double *u = d.s[su + a];
-    const double dc = dcen(u, nv, p, 1, i, d.mx, d.perx, 1);
-    const double de = dcen(u, nv, p, d.sj, j, d.my, d.pery, 1);
-    const double dz = dcen(u, nv, p, d.sk, kg, d.mz, d.perz, 0);
+    const double dc = dcen<0>(A, a, i, d.mx, d.perx, 1);
+    const double de = dcen<1>(A, a, j, d.my, d.pery, 1);
+    const double dz = dcen<2>(A, a, kg, d.mz, d.perz, 0);
     g[a][0] = (dc * c0 + de * e0 + dz * z0) * ajc;
     g[a][1] = (dc * c1 + de * e1 + dz * z1) * ajc;
     g[a][2] = (dc * c2 + de * e2 + dz * z2) * ajc;
   }
+}
+VFS_HD void grad_center(const VfsDev &d, int su, int i, int j, int kg, long p, double g[3][3]) {
+  if (su == S_U0) { GlobalAccS<S_U0> A = {d, p}; grad_center_a(d, A, i, j, kg, p, g); }
+  else { GlobalAccS<S_UF0> A = {d, p}; grad_center_a(d, A, i, j, kg, p, g); }
 }
 
 VFS_HD double sabs_of(const double g[3][3]) {
@@ -81,42 +96,48 @@ struct LesDeriveBoundary {
 };
 
 // les.c:199-246: grad u, |S| and the test-filtered velocity (+ the per-node derived quantities)
+template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
+  if (A.nv(0, 0, 0) > 1.1) {   // skipped by the reference: its zero-initialised work vectors keep 0 here
+    const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    d.s[S_SABS][p] = 0;
+    for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = 0;
+    les_derive_store(d, p, z, 0.);
+    return;
+  }
+  double g[3][3];
+  grad_center_a(d, A, i, j, kg, p, g);
+  const double S = sabs_of(g);
+  d.s[S_SABS][p] = S;
+  les_derive_store(d, p, g, S);
+  double uf[3];
+  if (d.testfilter_ik) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      uf[a] = ((A.u(a, -1, 0, -1) + A.u(a, -1, 0, 1) + A.u(a, 1, 0, -1) + A.u(a, 1, 0, 1)) + 4. * (A.u(a, 0, 0, -1) + A.u(a, -1, 0, 0) + A.u(a, 0, 0, 1) + A.u(a, 1, 0, 0)) + 16. * A.u(a, 0, 0, 0)) / 36.;
+  } else {
+    double ws = 0, vs[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = -1; r <= 1; r++)
+#pragma unroll
+      for (int q = -1; q <= 1; q++)
+#pragma unroll
+        for (int pp = -1; pp <= 1; pp++) {
+          const double w = (A.nv(pp, q, r) > 0.1) ? 0. : 1. / A.aj(pp, q, r);
+          const double sw = simpson_w(r, q, pp) * w;
+          ws += sw;
+#pragma unroll
+          for (int a = 0; a < 3; a++) vs[a] += sw * A.u(a, pp, q, r);
+        }
+    for (int a = 0; a < 3; a++) uf[a] = vs[a] / ws;
+  }
+  for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = uf[a];
+}
 struct LesPass1 {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
-    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
-    if (nv[p] > 1.1) {   // skipped by the reference: its zero-initialised work vectors keep 0 here
-      const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      d.s[S_SABS][p] = 0;
-      for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = 0;
-      les_derive_store(d, p, z, 0.);
-      return;
-    }
-    double g[3][3];
-    grad_center(d, S_U0, i, j, kg, p, g);
-    const double S = sabs_of(g);
-    d.s[S_SABS][p] = S;
-    les_derive_store(d, p, g, S);
-    double uf[3];
-    if (d.testfilter_ik) {
-      for (int a = 0; a < 3; a++) {
-        const double *u = d.s[S_U0 + a];
-        uf[a] = ((u[p - d.sk - 1] + u[p + d.sk - 1] + u[p - d.sk + 1] + u[p + d.sk + 1]) + 4. * (u[p - d.sk] + u[p - 1] + u[p + d.sk] + u[p + 1]) + 16. * u[p]) / 36.;
-      }
-    } else {
-      double ws = 0, vs[3] = {0, 0, 0};
-      for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
-        const long n = p + r * d.sk + q * d.sj + pp;
-        const double w = (nv[n] > 0.1) ? 0. : 1. / aj[n];
-        const double sw = simpson_w(r, q, pp) * w;
-        ws += sw;
-        for (int a = 0; a < 3; a++) vs[a] += sw * d.s[S_U0 + a][n];
-      }
-      for (int a = 0; a < 3; a++) uf[a] = vs[a] / ws;
-    }
-    for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = uf[a];
+    GlobalAccS<S_U0> A = {d, p};
+    les1_core(d, A, i, j, k + d.kofs, p);
   }
 };
 
@@ -211,49 +232,67 @@ struct LesPass2 {
 };
 
 // les.c:716-796: Simpson-filter LM, MM (weights zeroed at solid cells and non-periodic domain
-// ghosts, with the J==0-only quirk of les.c:756), C = 0.5 LM/(MM + 1e-4), Cs = max(C,0)
+// ghosts, with the J==0-only quirk of les.c:756), C = 0.5 LM/(MM + 1e-4), Cs = max(C,0).
+// REGULAR = true: the cell is not adjacent to a periodic boundary plane, so no neighbour index is
+// remapped to a ghost image (les.c:738-768) and all fetches are at offsets -1..1.
+struct GlobalAcc3 {
+  const VfsDev &d; long p;
+  VFS_HD double lm(int di, int dj, int dk) const { return d.s[S_LM][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double mm(int di, int dj, int dk) const { return d.s[S_MM][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double aj(int di, int dj, int dk) const { return d.s[S_AJ][p + di + dj * d.sj + dk * d.sk]; }
+};
+template <bool REGULAR, class Acc> VFS_HD void les3_core(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
+  if (A.nv(0, 0, 0) > 1.1) { d.s[S_CS][p] = 0; return; }
+  double LM_avg, MM_avg;
+  if (d.testfilter_ik) {
+    // integrate_testfilter_simpson defers to the weight-free i-k rule (rhs2.c:504-506)
+    double l9 = 0, m9 = 0;
+#pragma unroll
+    for (int c = -1; c <= 1; c++)
+#pragma unroll
+      for (int a = -1; a <= 1; a++) {
+        int I = i + a, K = kg + c, da = a, dc = c;
+        if (!REGULAR) {
+          if (d.perx) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; }
+          if (d.perz) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; }
+        }
+        const double cf = (c == 0 ? 4. : 1.) * (a == 0 ? 4. : 1.);
+        l9 += cf * A.lm(da, 0, dc); m9 += cf * A.mm(da, 0, dc);
+      }
+    LM_avg = l9 / 36.; MM_avg = m9 / 36.;
+  } else {
+    double ws = 0, lm = 0, mmv = 0;
+#pragma unroll
+    for (int c = -1; c <= 1; c++)
+#pragma unroll
+      for (int b = -1; b <= 1; b++)
+#pragma unroll
+        for (int a = -1; a <= 1; a++) {
+          const int I = i + a, J = j + b, K = kg + c;
+          double w = 1. / A.aj(a, b, c);
+          if (A.nv(a, b, c) > 1.1) w = 0;
+          int da = a, db = b, dc = c;      // fetch offsets after the periodic remap
+          if (d.perx) { if (!REGULAR) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; } }
+          else if (I == 0 || I == d.mx - 1) w = 0;
+          if (d.pery) { if (!REGULAR) { if (J == 0) db = b - 2; else if (J == d.my - 1) db = b + 2; } }
+          else if (J == 0) w = 0;
+          if (d.perz) { if (!REGULAR) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; } }
+          else if (K == 0 || K == d.mz - 1) w = 0;
+          const double sw = simpson_w(c, b, a) * w;
+          ws += sw; lm += sw * A.lm(da, db, dc); mmv += sw * A.mm(da, db, dc);
+        }
+    LM_avg = lm / ws; MM_avg = mmv / ws;
+  }
+  const double C = 0.5 * LM_avg / (MM_avg + 1.e-4);
+  d.s[S_CS][p] = C > 0 ? C : 0;
+}
 struct LesPass3 {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
-    const double *nv = d.s[S_NV], *aj = d.s[S_AJ];
-    if (nv[p] > 1.1) { d.s[S_CS][p] = 0; return; }
-    double ws = 0, lm = 0, mmv = 0;
-    for (int c = -1; c <= 1; c++) for (int b = -1; b <= 1; b++) for (int a = -1; a <= 1; a++) {
-      int I = i + a, J = j + b, K = kg + c;
-      const long n = p + c * d.sk + b * d.sj + a;
-      double w = 1. / aj[n];
-      if (nv[n] > 1.1) w = 0;
-      int da = a, db = b, dc = c;      // fetch offsets after the periodic remap
-      if (d.perx) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; }
-      else if (I == 0 || I == d.mx - 1) w = 0;
-      if (d.pery) { if (J == 0) db = b - 2; else if (J == d.my - 1) db = b + 2; }
-      else if (J == 0) w = 0;
-      if (d.perz) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; }
-      else if (K == 0 || K == d.mz - 1) w = 0;
-      const long f = p + dc * d.sk + db * d.sj + da;
-      const double sw = simpson_w(c, b, a) * w;
-      ws += sw; lm += sw * d.s[S_LM][f]; mmv += sw * d.s[S_MM][f];
-    }
-    double LM_avg, MM_avg;
-    if (d.testfilter_ik) {
-      // integrate_testfilter_simpson defers to the weight-free i-k rule (rhs2.c:504-506)
-      const double *L = d.s[S_LM], *M = d.s[S_MM];
-      // same remapped fetches, J offset 0 only
-      double l9 = 0, m9 = 0;
-      for (int c = -1; c <= 1; c++) for (int a = -1; a <= 1; a++) {
-        int I = i + a, K = kg + c, da = a, dc = c;
-        if (d.perx) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; }
-        if (d.perz) { if (K == 0) dc = c - 2; else if (K == d.mz - 1) dc = c + 2; }
-        const long f = p + dc * d.sk + da;
-        const double cf = (c == 0 ? 4. : 1.) * (a == 0 ? 4. : 1.);
-        l9 += cf * L[f]; m9 += cf * M[f];
-      }
-      LM_avg = l9 / 36.; MM_avg = m9 / 36.;
-    } else { LM_avg = lm / ws; MM_avg = mmv / ws; }
-    const double C = 0.5 * LM_avg / (MM_avg + 1.e-4);
-    d.s[S_CS][p] = C > 0 ? C : 0;
+    GlobalAcc3 A = {d, p};
+    les3_core<false>(d, A, i, j, k + d.kofs, p);
   }
 };
 
@@ -275,17 +314,18 @@ struct LesClip {
   }
 };
 
-// les.c:1185-1211: nu_t = Cs * Delta^2 * |S|
-struct NuT {
+// les.c:1185-1211: nu_t = Cs * Delta^2 * |S|.  FROM_S: |S| was stored by pass 1 of vfs_les_cs from
+// the same ucat (identical arithmetic), so it is read back instead of being recomputed.
+template <bool FROM_S> struct NuT {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
     const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
     const double *nv = d.s[S_NV];
     if (nv[p] > 1.1) { d.s[S_NUT][p] = 0; return; }
-    double g[3][3];
-    grad_center(d, S_U0, i, j, kg, p, g);
-    const double Sabs = sabs_of(g);
+    double Sabs;
+    if (FROM_S) Sabs = d.s[S_SABS][p];
+    else { double g[3][3]; grad_center(d, S_U0, i, j, kg, p, g); Sabs = sabs_of(g); }
     const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
     double v = d.s[S_CS][p] * (filter * filter) * Sabs;
     if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
