@@ -121,7 +121,9 @@ long vfs_launch_count(vfs_ctx *c);
  * group; 0 if it has not run.  Valid after vfs_sync / any synchronous entry point. */
 enum vfs_timer { VFS_T_TOTAL = 0, VFS_T_C2C, VFS_T_FLUX, VFS_T_FP, VFS_T_PROJECT, VFS_T_LES1, VFS_T_LES2, VFS_T_LES3, VFS_T_NUT, VFS_T_COUNT };
 double vfs_last_ms(vfs_ctx *c, int which);
-/* tuning switches: key 0 = use the fused RHS kernel when applicable (default 1) */
+/* tuning switches: key 0 = use the TMA-staged tiled kernels (default 1; 0 = staged one-thread-per-cell
+ * kernels, same results bit for bit); key 1 = replay vfs_rhs_les_fused / vfs_formfunction_snes_dev as a
+ * CUDA graph (default 0; single rank only; per-kernel timers are not updated while replaying) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus

@@ -119,3 +119,26 @@ def test_tiled_equals_staged(pkg):
             ctx.close()
         for n in outs[0]:
             assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
+
+
+def test_graph_replay_equals_eager(pkg):
+    """vfs_rhs_les_fused replayed as a CUDA graph gives bitwise the same fields as eager launches."""
+    capi, cases = pkg.capi, pkg.cases
+    cfg = cases.scaled(cases.CONFIGS["c2_box256"], 70, 37, 45)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    res = []
+    for graph in (0, 1):
+        ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+        ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
+        met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+        f = cases.make_fields(cfg, met)
+        for k, n in pc.FIELDS_IN:
+            ctx.upload(n, f[k])
+        ctx.set_option(1, graph)
+        for _ in range(4):          # eager, capture, replay, replay
+            ctx.upload("UCONT", f["ucont"])
+            ctx.rhs_les_fused()
+        res.append({n: ctx.download(n) for n in ("RHS", "UCAT", "CS", "NU_T")})
+        ctx.close()
+    for n in res[0]:
+        assert np.array_equal(res[0][n], res[1][n]), n

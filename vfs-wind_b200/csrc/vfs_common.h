@@ -44,6 +44,7 @@ enum {
   S_LM, S_MM,
   // LES per-node derived quantities entering the test filters (contiguous: w, U(3), |S|S_ij(6))
   S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5,
+  S_IAJ,                                                                 // 1/aj (cell volume), filter weight
   S_COUNT
 };
 

@@ -52,9 +52,17 @@ struct vfs_ctx {
   CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
 #endif
   bool tma_ok = false;
+  // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
+  int use_graph = 0; bool capturing = false;
+  int graph_calls[2] = {0, 0};
+#ifndef VFS_EMU
+  cudaGraphExec_t gexec[2] = {0, 0};
+#endif
+  bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
 };
 
+static void graph_reset(vfs_ctx *c);
 static void set_err(vfs_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_err = m; }
 
 template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
@@ -78,6 +86,7 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
 
 static void ev_rec(vfs_ctx *c, int n) {
 #ifndef VFS_EMU
+  if (c->capturing) return;       // events recorded inside a graph cannot be used for timing
   if (c->ev[n]) cudaEventRecord(c->ev[n], c->stream);
   c->ev_valid[n / 2] = true;
 #endif
@@ -202,6 +211,7 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
 #ifndef VFS_EMU
   cudaStreamSynchronize(c->stream);
   cudaFree(c->pool); cudaFree(c->stage);
+  graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
@@ -214,6 +224,7 @@ extern "C" int vfs_set_params(vfs_ctx *c, const vfs_params *p) {
   if (!c || !p) return VFS_ERR_ARG;
   if (p->mx != c->prm.mx || p->my != c->prm.my || p->mz != c->prm.mz || p->nzl != c->prm.nzl || p->kofs != c->prm.kofs || p->nranks != c->prm.nranks) { set_err(c, "geometry cannot change"); return VFS_ERR_ARG; }
   std::string why; int r = check_params(p, why); if (r) { set_err(c, why); return r; }
+  graph_reset(c);
   c->prm = *p; double *sv[S_COUNT]; memcpy(sv, c->d.s, sizeof(sv)); fill_dev(c); memcpy(c->d.s, sv, sizeof(sv)); return 0;
 }
 extern "C" int vfs_set_stream(vfs_ctx *c, void *s) {
@@ -223,6 +234,7 @@ extern "C" int vfs_set_stream(vfs_ctx *c, void *s) {
   if (c->own_stream) cudaStreamDestroy(c->stream);
   c->own_stream = false;
 #endif
+  graph_reset(c);
   c->stream = (cudaStream_t)s; return 0;
 }
 extern "C" int vfs_set_halo_callback(vfs_ctx *c, vfs_halo_fn fn, void *user) { if (!c) return VFS_ERR_ARG; c->halo_fn = fn; c->halo_user = user; return 0; }
@@ -251,7 +263,44 @@ extern "C" double vfs_last_ms(vfs_ctx *c, int which) {
   return 0;
 #endif
 }
-extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) { if (!c) return VFS_ERR_ARG; if (key == 0) c->fused = value; return 0; }
+static void graph_reset(vfs_ctx *c) {
+#ifndef VFS_EMU
+  for (int q = 0; q < 2; q++) { if (c->gexec[q]) cudaGraphExecDestroy(c->gexec[q]); c->gexec[q] = 0; c->graph_calls[q] = 0; }
+#endif
+}
+extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
+  if (!c) return VFS_ERR_ARG;
+  if (key == 0) c->fused = value;
+  else if (key == 1) c->use_graph = value;
+  graph_reset(c);
+  return 0;
+}
+// Run `body` (a pure launch sequence on c->stream) eagerly the first time, capture it into a CUDA
+// graph the second time and replay the graph afterwards.  Kernel arguments (VfsDev by value) are
+// baked into the graph, so every parameter/stream/option change resets it.
+template <class F> static int run_graphed(vfs_ctx *c, int key, F body) {
+#ifndef VFS_EMU
+  if (c->use_graph && c->prm.nranks == 1) {
+    if (c->gexec[key]) { CK(cudaGraphLaunch(c->gexec[key], c->stream)); return 0; }
+    if (c->graph_calls[key]++ >= 1) {
+      cudaGraph_t g = 0;
+      CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      c->capturing = true;
+      int r = body();
+      c->capturing = false;
+      cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+      if (r) { if (g) cudaGraphDestroy(g); return r; }
+      if (e != cudaSuccess || !g) { set_err(c, std::string("graph capture: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+      e = cudaGraphInstantiate(&c->gexec[key], g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { c->gexec[key] = 0; set_err(c, std::string("graph instantiate: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+      CK(cudaGraphLaunch(c->gexec[key], c->stream));
+      return 0;
+    }
+  }
+#endif
+  return body();
+}
 
 // ---- transfers ------------------------------------------------------------------------------------
 static int h2d_stage(vfs_ctx *c, const double *host, int dof) {
@@ -279,6 +328,7 @@ extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
 }
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  if (field == VFS_AJ) c->iaj_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
@@ -306,6 +356,7 @@ extern "C" int vfs_form_metrics(vfs_ctx *c) {
   Grp g = grp(S_CSI0, 10);
   RUN(g2l(c, g));
   if (any_per(c)) { RUN(node_copy(c, g)); RUN(g2l(c, g)); }
+  c->iaj_valid = false; c->sabs_valid = false;
   return vfs_sync(c);
 }
 
@@ -450,8 +501,10 @@ static int snes_core(vfs_ctx *c) {
 extern "C" int vfs_formfunction_snes_dev(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
   ev_rec(c, 2 * VFS_T_TOTAL);
-  { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
-  RUN(snes_core(c));
+  RUN(run_graphed(c, 0, [&]() -> int {
+    { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+    return snes_core(c);
+  }));
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);
 }
@@ -481,6 +534,10 @@ static int les_cs(vfs_ctx *c) {
   c->sabs_valid = false;
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
+  if (!c->iaj_valid) {       // whole padded array: the filters read ghost nodes too
+    InvAj f = {d}; Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
+    RUN(launch(c, all, f)); c->iaj_valid = true;
+  }
   ev_rec(c, 2 * VFS_T_LES1);
 #ifndef VFS_EMU
   if (c->fused && c->tma_ok && !d.testfilter_ik) {
@@ -550,11 +607,13 @@ extern "C" int vfs_les_nut(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_nut
 extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
   ev_rec(c, 2 * VFS_T_TOTAL);
-  RUN(g2l(c, grp(S_UC0, 3)));
-  RUN(contra2cart(c));
-  if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
-  { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
-  RUN(snes_core(c));
+  RUN(run_graphed(c, 1, [&]() -> int {
+    RUN(g2l(c, grp(S_UC0, 3)));
+    RUN(contra2cart(c));
+    if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
+    { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+    return snes_core(c);
+  }));
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);
 }

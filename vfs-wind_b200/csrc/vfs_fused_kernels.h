@@ -159,7 +159,7 @@ typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 5, 4, 2, 2, 1, 1, 1, 1> RingLes1;
 struct Les1Acc {
   TileAcc<RingLes1> T;
   __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
-  __device__ __forceinline__ double aj(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+  __device__ __forceinline__ double iaj(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(4, di, dj, dk); }
 };
 struct Les1Body {
@@ -207,7 +207,7 @@ struct Les3Acc {
   TileAcc<RingLes3> T;
   __device__ __forceinline__ double lm(int di, int dj, int dk) const { return T.get(0, di, dj, dk); }
   __device__ __forceinline__ double mm(int di, int dj, int dk) const { return T.get(1, di, dj, dk); }
-  __device__ __forceinline__ double aj(int di, int dj, int dk) const { return T.get(2, di, dj, dk); }
+  __device__ __forceinline__ double iaj(int di, int dj, int dk) const { return T.get(2, di, dj, dk); }
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
 };
 VFS_HD bool les3_regular(const VfsDev &d, int i, int j, int kg) {
@@ -260,7 +260,7 @@ struct FluxBody {
 
 static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q = 0; q < n; q++) s.sid[q] = v[q]; return s; }
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
-  const int v[5] = {S_U0, S_U1, S_U2, S_AJ, S_NV};
+  const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};
   return launch_tile_march<RingLes1>(st, tmap, d, k0, k1, 64, sids(5, v), Les1Body(), L);
 }
 static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
@@ -268,7 +268,7 @@ static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, cons
   return launch_tile_march<RingLes2>(st, tmap, d, k0, k1, 64, sids(13, v), Les2Body(), L);
 }
 static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
-  const int v[4] = {S_LM, S_MM, S_AJ, S_NV};
+  const int v[4] = {S_LM, S_MM, S_IAJ, S_NV};
   return launch_tile_march<RingLes3>(st, tmap, d, k0, k1, 64, sids(4, v), Les3Body(), L);
 }
 static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {

@@ -26,7 +26,7 @@ template <int S0> struct GlobalAccS {
   const VfsDev &d; long p;
   VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S0 + a][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
-  VFS_HD double aj(int di, int dj, int dk) const { return d.s[S_AJ][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double iaj(int di, int dj, int dk) const { return d.s[S_IAJ][p + di + dj * d.sj + dk * d.sk]; }
 };
 
 // centre difference of component a along direction T (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
@@ -74,11 +74,18 @@ VFS_HD double simpson_w(int r, int q, int pp) {
   return s;
 }
 
+// 1/aj = cell volume: the weight of every test filter (get_weight, les.c:31-40; les.c:737).  It only
+// changes with the grid, so it is computed once per metrics upload instead of 27 times per cell.
+struct InvAj {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const { long p = d.idx(i, j, k); d.s[S_IAJ][p] = 1. / d.s[S_AJ][p]; }
+};
+
 // per-node quantities that pass 2 filters over the 27-point neighbourhood (les.c:354-439):
 // w = 1/aj (0 where nvert > 0.1), contravariant U = [csi;eta;zet] u, and |S| S_ij.  Written once
 // per node instead of being recomputed 27 times by every neighbour.
 VFS_HD void les_derive_store(const VfsDev &d, long n, const double g[3][3], double S) {
-  d.s[S_LW][n] = (d.s[S_NV][n] > 0.1) ? 0. : 1. / d.s[S_AJ][n];
+  d.s[S_LW][n] = (d.s[S_NV][n] > 0.1) ? 0. : d.s[S_IAJ][n];
   const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
   d.s[S_LU0][n] = u0 * d.s[S_CSI0][n] + u1 * d.s[S_CSI1][n] + u2 * d.s[S_CSI2][n];
   d.s[S_LU1][n] = u0 * d.s[S_ETA0][n] + u1 * d.s[S_ETA1][n] + u2 * d.s[S_ETA2][n];
@@ -122,7 +129,7 @@ template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i,
       for (int q = -1; q <= 1; q++)
 #pragma unroll
         for (int pp = -1; pp <= 1; pp++) {
-          const double w = (A.nv(pp, q, r) > 0.1) ? 0. : 1. / A.aj(pp, q, r);
+          const double w = (A.nv(pp, q, r) > 0.1) ? 0. : A.iaj(pp, q, r);
           const double sw = simpson_w(r, q, pp) * w;
           ws += sw;
 #pragma unroll
@@ -240,7 +247,7 @@ struct GlobalAcc3 {
   VFS_HD double lm(int di, int dj, int dk) const { return d.s[S_LM][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double mm(int di, int dj, int dk) const { return d.s[S_MM][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
-  VFS_HD double aj(int di, int dj, int dk) const { return d.s[S_AJ][p + di + dj * d.sj + dk * d.sk]; }
+  VFS_HD double iaj(int di, int dj, int dk) const { return d.s[S_IAJ][p + di + dj * d.sj + dk * d.sk]; }
 };
 template <bool REGULAR, class Acc> VFS_HD void les3_core(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
   if (A.nv(0, 0, 0) > 1.1) { d.s[S_CS][p] = 0; return; }
@@ -270,7 +277,7 @@ template <bool REGULAR, class Acc> VFS_HD void les3_core(const VfsDev &d, const 
 #pragma unroll
         for (int a = -1; a <= 1; a++) {
           const int I = i + a, J = j + b, K = kg + c;
-          double w = 1. / A.aj(a, b, c);
+          double w = A.iaj(a, b, c);
           if (A.nv(a, b, c) > 1.1) w = 0;
           int da = a, db = b, dc = c;      // fetch offsets after the periodic remap
           if (d.perx) { if (!REGULAR) { if (I == 0) da = a - 2; else if (I == d.mx - 1) da = a + 2; } }
