@@ -130,6 +130,8 @@ def run_ours(args):
     torch.cuda.set_device(lrank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    # a non-default stream: CUDA graphs cannot be captured on the legacy default stream
+    torch.cuda.set_stream(torch.cuda.Stream())
     pkg = load_package()
     pkg.capi.load()
     cfg = workload_cfg(pkg.cases, args.workload, world)
