@@ -189,6 +189,13 @@ class VfsContext:
         self._ck(self.lib.vfs_download(self.h, FIELD_ID[field], out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def upload_ptr(self, field, host_ptr):
+        """Upload from a raw host address (e.g. pinned memory) holding [nzl][my][mx][dof] doubles."""
+        self._ck(self.lib.vfs_upload(self.h, FIELD_ID[field], C.c_void_p(host_ptr)))
+
+    def download_ptr(self, field, host_ptr):
+        self._ck(self.lib.vfs_download(self.h, FIELD_ID[field], C.c_void_p(host_ptr)))
+
     def halo_exchange(self, field):
         self._ck(self.lib.vfs_halo_exchange(self.h, FIELD_ID[field]))
 

@@ -559,6 +559,7 @@ static int les_cs(vfs_ctx *c) {
   if (c->fused && c->tma_ok && !d.testfilter_ik) {
     Box bi = box_interior(c);
     if (launch_les2_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "k_les2_tma launch failed"); return VFS_ERR_CUDA; }
+    { Les2Finish f = {d}; RUN(launch(c, bi, f)); }
   } else
 #endif
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }

@@ -170,7 +170,7 @@ struct Les1Body {
 };
 
 // ---- LES pass 2 (les.c:308-669): staged ucat(3), w, U(3), |S|S_ij(6) -----------------------------------
-typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 13, 3, 2, 2, 1, 1, 1, 1> RingLes2;
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 13, 3, 2, 2, 1, 1, 1, 1> RingLes2;   // 3 x 36.6 KB: two blocks per SM
 struct Les2Body {
   __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes2> &T, int i, int j, int k) const {
     constexpr int NV = VFS_LES2_NV;
@@ -197,7 +197,23 @@ struct Les2Body {
 #pragma unroll
           for (int a = 0; a < 6; a++) fs[10 + a] += sw * T.get(7 + a, pp, q, r);
         }
-    les2_finish(d, i, j, k + d.kofs, p, fs, sum_weight);
+    // filtered sums -> work arrays (the face-flux arrays are free during the LES update); the
+    // tensor algebra of les.c:441-669 runs in the streaming kernel Les2Finish, which keeps this
+    // kernel's register footprint small enough for 4 resident blocks per SM
+#pragma unroll
+    for (int a = 0; a < NV; a++) d.s[S_FC1 + a][p] = fs[a];
+    d.s[S_FC1 + NV][p] = sum_weight;
+  }
+};
+struct Les2Finish {
+  VfsDev d;
+  __device__ __forceinline__ void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    if (d.s[S_NV][p] > 1.1) return;      // LM = MM = 0 already written by the filter kernel
+    double fs[VFS_LES2_NV];
+#pragma unroll
+    for (int a = 0; a < VFS_LES2_NV; a++) fs[a] = d.s[S_FC1 + a][p];
+    les2_finish(d, i, j, k + d.kofs, p, fs, d.s[S_FC1 + VFS_LES2_NV][p]);
   }
 };
 
