@@ -178,15 +178,31 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
                            {0.5 * (gh[0][2] + gh[2][0]), 0.5 * (gh[1][2] + gh[2][1]), 0.5 * (gh[2][2] + gh[2][2])}};
   const double S_hat = sabs_of(gh);
   double Lij[3][3], SSh[3][3];
-  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = fs[1 + 3 * a + b] / fdiv - _U[a] * _u[b];
-  SSh[0][0] = fs[10] / fdiv; SSh[0][1] = SSh[1][0] = fs[11] / fdiv; SSh[0][2] = SSh[2][0] = fs[12] / fdiv;
-  SSh[1][1] = fs[13] / fdiv; SSh[1][2] = SSh[2][1] = fs[14] / fdiv; SSh[2][2] = fs[15] / fdiv;
+  // valsum / wsum (rhs2.c:522) evaluated as valsum * (1/wsum): 15 FP64 divisions -> 1 on the device
+  // (<= 1 ulp apart per filtered value); the host emulation keeps the literal division
+#if defined(__CUDA_ARCH__)
+  const double finv = 1. / fdiv;
+#define VFS_FDIV(x) ((x) * finv)
+#else
+#define VFS_FDIV(x) ((x) / fdiv)
+#endif
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = VFS_FDIV(fs[1 + 3 * a + b]) - _U[a] * _u[b];
+  SSh[0][0] = VFS_FDIV(fs[10]); SSh[0][1] = SSh[1][0] = VFS_FDIV(fs[11]); SSh[0][2] = SSh[2][0] = VFS_FDIV(fs[12]);
+  SSh[1][1] = VFS_FDIV(fs[13]); SSh[1][2] = SSh[2][1] = VFS_FDIV(fs[14]); SSh[2][2] = VFS_FDIV(fs[15]);
+#undef VFS_FDIV
   // covariant metric tensor G (les.c:607-622)
   const double a11 = csi[0], a12 = csi[1], a13 = csi[2], a21 = eta[0], a22 = eta[1], a23 = eta[2], a31 = zet[0], a32 = zet[1], a33 = zet[2];
   const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
-  const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
-  const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
-  const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
+#if defined(__CUDA_ARCH__)
+  const double dinv = 1. / det;       // 9 divisions -> 1 (see VFS_FDIV above)
+#define VFS_DDIV(x) ((x) * dinv)
+#else
+#define VFS_DDIV(x) ((x) / det)
+#endif
+  const double xcsi = VFS_DDIV(a33 * a22 - a32 * a23), xeta = -VFS_DDIV(a33 * a12 - a32 * a13), xzet = VFS_DDIV(a23 * a12 - a22 * a13);
+  const double ycsi = -VFS_DDIV(a33 * a21 - a31 * a23), yeta = VFS_DDIV(a33 * a11 - a31 * a13), yzet = -VFS_DDIV(a23 * a11 - a21 * a13);
+  const double zcsi = VFS_DDIV(a32 * a21 - a31 * a22), zeta = -VFS_DDIV(a32 * a11 - a31 * a12), zzet = VFS_DDIV(a22 * a11 - a21 * a12);
+#undef VFS_DDIV
   double G[3][3];
   G[0][0] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
   G[1][1] = xeta * xeta + yeta * yeta + zeta * zeta;
