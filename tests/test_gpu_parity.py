@@ -100,10 +100,12 @@ def test_cuda_matches_golden_fixture(pkg, name):
 
 
 def test_tiled_equals_staged(pkg):
-    """The shared-memory tiled kernels and the one-thread-per-cell staged kernels share their
-    arithmetic and summation order: results must be bitwise identical."""
+    """The tiled / marching kernels against the one-thread-per-cell staged kernels.  Kernels that share
+    arithmetic and summation order with the staged form must agree bitwise (Ucat, Ucont, metrics);
+    the marching kernels that re-associate sums (separable test filters, fused residual) must agree
+    to rounding, far inside the 1e-12 parity tolerance."""
     capi, cases = pkg.capi, pkg.cases
-    for cfgname, dims in (("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41))):
+    for cfgname, dims in (("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41)), ("c2_box256", (101, 67, 50))):
         cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
         mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
         outs = []
@@ -118,7 +120,11 @@ def test_tiled_equals_staged(pkg):
             outs.append(pc.run_path(ctx, pc.krylov_x(f["ucont"])))
             ctx.close()
         for n in outs[0]:
-            assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
+            if n in ("F", "CS", "NU_T"):
+                assert pc.relerr(outs[1][n], outs[0][n]) <= 1e-13, (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
+                assert np.array_equal(outs[0][n] == 0, outs[1][n] == 0), (cfgname, n)
+            else:
+                assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
 
 
 def test_graph_replay_equals_eager(pkg):

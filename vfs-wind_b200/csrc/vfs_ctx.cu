@@ -11,6 +11,7 @@
 #include "vfs_rhs_kernels.h"
 #include "vfs_les_kernels.h"
 #include "vfs_fused_kernels.h"
+#include "vfs_march_kernels.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -555,13 +556,11 @@ static int les_cs(vfs_ctx *c) {
   // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
   if (any_per(c)) RUN(node_copy(c, grp_cat(grp(S_UF0, 3), grp(S_LU0, 9))));   // les.c:275-306
   ev_rec(c, 2 * VFS_T_LES2);
-#ifndef VFS_EMU
-  if (c->fused && c->tma_ok && !d.testfilter_ik) {
+  if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    if (launch_les2_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "k_les2_tma launch failed"); return VFS_ERR_CUDA; }
-    { Les2Finish f = {d}; RUN(launch(c, bi, f)); }
+    Les2Sep prog = {d};
+    if (run_block_march(c->stream, prog, les2_sep_grid(d, bi.k0, bi.k1), &c->launches)) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
-#endif
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES2 + 1);
   Grp g2 = grp(S_LM, 2);

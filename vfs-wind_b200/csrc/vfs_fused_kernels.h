@@ -169,54 +169,6 @@ struct Les1Body {
   }
 };
 
-// ---- LES pass 2 (les.c:308-669): staged ucat(3), w, U(3), |S|S_ij(6) -----------------------------------
-typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 13, 3, 2, 2, 1, 1, 1, 1> RingLes2;   // 3 x 36.6 KB: two blocks per SM
-struct Les2Body {
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes2> &T, int i, int j, int k) const {
-    constexpr int NV = VFS_LES2_NV;
-    const long p = d.idx(i, j, k);
-    if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
-    double fs[NV], sum_weight = 0;
-#pragma unroll
-    for (int a = 0; a < NV; a++) fs[a] = 0;
-#pragma unroll
-    for (int r = -1; r <= 1; r++)
-#pragma unroll
-      for (int q = -1; q <= 1; q++)
-#pragma unroll
-        for (int pp = -1; pp <= 1; pp++) {
-          const double w = T.get(3, pp, q, r);
-          sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));
-          const double sw = simpson_w(r, q, pp) * w;
-          fs[0] += sw;
-          const double u0 = T.get(0, pp, q, r), u1 = T.get(1, pp, q, r), u2 = T.get(2, pp, q, r);
-          const double U0 = T.get(4, pp, q, r), U1 = T.get(5, pp, q, r), U2 = T.get(6, pp, q, r);
-          fs[1] += sw * (U0 * u0); fs[2] += sw * (U0 * u1); fs[3] += sw * (U0 * u2);
-          fs[4] += sw * (U1 * u0); fs[5] += sw * (U1 * u1); fs[6] += sw * (U1 * u2);
-          fs[7] += sw * (U2 * u0); fs[8] += sw * (U2 * u1); fs[9] += sw * (U2 * u2);
-#pragma unroll
-          for (int a = 0; a < 6; a++) fs[10 + a] += sw * T.get(7 + a, pp, q, r);
-        }
-    // filtered sums -> work arrays (the face-flux arrays are free during the LES update); the
-    // tensor algebra of les.c:441-669 runs in the streaming kernel Les2Finish, which keeps this
-    // kernel's register footprint small enough for 4 resident blocks per SM
-#pragma unroll
-    for (int a = 0; a < NV; a++) d.s[S_FC1 + a][p] = fs[a];
-    d.s[S_FC1 + NV][p] = sum_weight;
-  }
-};
-struct Les2Finish {
-  VfsDev d;
-  __device__ __forceinline__ void operator()(int i, int j, int k) const {
-    const long p = d.idx(i, j, k);
-    if (d.s[S_NV][p] > 1.1) return;      // LM = MM = 0 already written by the filter kernel
-    double fs[VFS_LES2_NV];
-#pragma unroll
-    for (int a = 0; a < VFS_LES2_NV; a++) fs[a] = d.s[S_FC1 + a][p];
-    les2_finish(d, i, j, k + d.kofs, p, fs, d.s[S_FC1 + VFS_LES2_NV][p]);
-  }
-};
-
 // ---- LES pass 3 (les.c:716-796): staged LM, MM, aj, nvert; cells not next to a periodic plane ----------
 typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 4, 2, 2, 1, 1, 1, 1> RingLes3;
 struct Les3Acc {
@@ -278,10 +230,6 @@ static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};
   return launch_tile_march<RingLes1>(st, tmap, d, k0, k1, 64, sids(5, v), Les1Body(), L);
-}
-static inline int launch_les2_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
-  const int v[13] = {S_U0, S_U1, S_U2, S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5};
-  return launch_tile_march<RingLes2>(st, tmap, d, k0, k1, 64, sids(13, v), Les2Body(), L);
 }
 static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[4] = {S_LM, S_MM, S_IAJ, S_NV};
