@@ -141,6 +141,9 @@ def run_ours(args):
     ctx, f, (mx, my, mz, kofs, nzl) = build_case_on_device(pkg, cfg, rank, world, lrank, halo)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    for key, env in ((2, "VFS_LES2_TY"),):            # tuning knobs (see vfs_set_option)
+        if os.environ.get(env):
+            ctx.set_option(key, int(os.environ[env]))
     cells_total = (mx - 2) * (my - 2) * (mz - 2)
     k_int = [k for k in range(kofs, kofs + nzl) if 1 <= k <= mz - 2]
     cells_rank = (mx - 2) * (my - 2) * len(k_int)

@@ -122,7 +122,8 @@ def test_tiled_equals_staged(pkg):
         for n in outs[0]:
             if n in ("F", "CS", "NU_T"):
                 assert pc.relerr(outs[1][n], outs[0][n]) <= 1e-13, (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
-                assert np.array_equal(outs[0][n] == 0, outs[1][n] == 0), (cfgname, n)
+                if n == "F":       # mask-driven zeros are exact; Cs = max(C, 0) may flip at C ~ 0
+                    assert np.array_equal(outs[0][n] == 0, outs[1][n] == 0), (cfgname, n)
             else:
                 assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
 

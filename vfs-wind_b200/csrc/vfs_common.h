@@ -21,6 +21,13 @@
 
 #define VFS_G 4
 
+// hint: bring the line holding *p into L2 (no register, no stall); no-op in the host emulation
+#if defined(__CUDA_ARCH__)
+#define VFS_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define VFS_PREFETCH_L2(p) ((void)0)
+#endif
+
 // internal scalar ids ------------------------------------------------------------------------
 enum {
   S_X = 0, S_Y, S_Z,                                  // node coordinates
@@ -45,6 +52,9 @@ enum {
   // LES per-node derived quantities entering the test filters (contiguous: w, U(3), |S|S_ij(6))
   S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5,
   S_IAJ,                                                                 // 1/aj (cell volume), filter weight
+  // LES factors that depend on the grid and the nvert mask only (LesGeo, vfs_les_kernels.h):
+  // 1/sum(s*w), test_filter^2, filter^2 and the covariant metric tensor G (00,11,22,01,02,12)
+  S_LFINV, S_LTF2, S_LF2, S_LG0, S_LG1, S_LG2, S_LG3, S_LG4, S_LG5,
   S_COUNT
 };
 

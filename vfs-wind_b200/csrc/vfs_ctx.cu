@@ -50,7 +50,7 @@ struct vfs_ctx {
   int fused = 1;                 // use the TMA-staged tiled kernels when applicable
 #ifndef VFS_EMU
   CUtensorMap tmap;              // 4-D map over the scalar pool, box (TX+2, TY+2, 1, 1)
-  CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
+  CUtensorMap tmap_rhs;          // same pool, box of the residual marching kernel
 #endif
   bool tma_ok = false;
   // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
@@ -61,6 +61,8 @@ struct vfs_ctx {
 #endif
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
+  int les2_ty = 16;              // tile height of the LES pass-2 marching kernel (option key 2: 8 or 16)
+  bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
 };
 
 static void graph_reset(vfs_ctx *c);
@@ -201,7 +203,7 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
 #ifndef VFS_EMU
   c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
-              vfs_make_tensor_map(&c->tmap_flux, c->pool, c->d, c->scalar_len, VFS_TILE_TX + VFS_FLUX_HX, VFS_TILE_TY + VFS_FLUX_HY) == 0;
+              vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0;
 #endif
   *out = c;
   return 0;
@@ -273,6 +275,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   if (!c) return VFS_ERR_ARG;
   if (key == 0) c->fused = value;
   else if (key == 1) c->use_graph = value;
+  else if (key == 2) c->les2_ty = value == 8 ? 8 : 16;
   graph_reset(c);
   return 0;
 }
@@ -330,6 +333,7 @@ extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
   if (field == VFS_AJ) c->iaj_valid = false;
+  if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
@@ -357,7 +361,7 @@ extern "C" int vfs_form_metrics(vfs_ctx *c) {
   Grp g = grp(S_CSI0, 10);
   RUN(g2l(c, g));
   if (any_per(c)) { RUN(node_copy(c, g)); RUN(g2l(c, g)); }
-  c->iaj_valid = false; c->sabs_valid = false;
+  c->iaj_valid = false; c->sabs_valid = false; c->lesgeo_valid = false;
   return vfs_sync(c);
 }
 
@@ -424,46 +428,88 @@ static int ib_bc(vfs_ctx *c) {
 extern "C" int vfs_ib_bc(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(ib_bc(c)); return vfs_sync(c); }
 
 // ---- Formfunction_2 ------------------------------------------------------------------------------------
+static Box box_clip(Box b, const Box &lim) {
+  if (b.i0 < lim.i0) b.i0 = lim.i0; if (b.i1 > lim.i1) b.i1 = lim.i1;
+  if (b.j0 < lim.j0) b.j0 = lim.j0; if (b.j1 > lim.j1) b.j1 = lim.j1;
+  if (b.k0 < lim.k0) b.k0 = lim.k0; if (b.k1 > lim.k1) b.k1 = lim.k1;
+  return b;
+}
+static bool box_empty(const Box &b) { return b.i1 <= b.i0 || b.j1 <= b.j0 || b.k1 <= b.k0; }
+// The staged chain on the owned nodes outside the regular region R of the marching kernel: six
+// disjoint projection slabs; Fp on each slab grown by one cell, face fluxes on that grown by
+// (-2,+1) along the face normal (the reach of the 4th-order divergence, momentum.c:1565-1637).
+struct ShellBoxes { int n; Box proj[6], fp[6], fl[6][3]; };
+static ShellBoxes shell_boxes(const vfs_ctx *c, const Box &R) {
+  const VfsDev &d = c->d;
+  ShellBoxes S; S.n = 0;
+  const Box own = {0, d.mx, 0, d.my, 0, d.nzl};
+  const Box cells = box_interior(c);
+  const int k0f = klo(c, 0), k1f = klo(c, d.mz - 1);
+  const Box cand[6] = {{0, d.mx, 0, d.my, 0, R.k0},         {0, d.mx, 0, d.my, R.k1, d.nzl},
+                       {0, d.mx, 0, R.j0, R.k0, R.k1},      {0, d.mx, R.j1, d.my, R.k0, R.k1},
+                       {0, R.i0, R.j0, R.j1, R.k0, R.k1},   {R.i1, d.mx, R.j0, R.j1, R.k0, R.k1}};
+  for (int q = 0; q < 6; q++) {
+    const Box pb = box_clip(cand[q], own);
+    if (box_empty(pb)) continue;
+    const int n = S.n++;
+    S.proj[n] = pb;
+    const Box grown = {pb.i0 - 1, pb.i1 + 1, pb.j0 - 1, pb.j1 + 1, pb.k0 - 1, pb.k1 + 1};
+    const Box fb = box_clip(grown, cells);
+    S.fp[n] = fb;
+    const Box fi = {fb.i0 - 2, fb.i1 + 1, fb.j0, fb.j1, fb.k0, fb.k1}, li = {0, d.mx - 1, 1, d.my - 1, cells.k0, cells.k1};
+    const Box fj = {fb.i0, fb.i1, fb.j0 - 2, fb.j1 + 1, fb.k0, fb.k1}, lj = {1, d.mx - 1, 0, d.my - 1, cells.k0, cells.k1};
+    const Box fk = {fb.i0, fb.i1, fb.j0, fb.j1, fb.k0 - 2, fb.k1 + 1}, lk = {1, d.mx - 1, 1, d.my - 1, k0f, k1f};
+    S.fl[n][0] = box_clip(fi, li); S.fl[n][1] = box_clip(fj, lj); S.fl[n][2] = box_clip(fk, lk);
+  }
+  return S;
+}
+
 // mode 0: rhs[s0] += scale*R, masks (Formfunction_2) ; mode 1: full SNES assembly into S_R0
 static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const VfsDev &d = c->d;
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
-  ev_rec(c, 2 * VFS_T_FLUX);
-  if (c->fused && fused_rhs_applicable(d)) {
-    RUN(launch_fused_rhs(c->stream, d, mode, s0, scale, &c->launches));
-    ev_rec(c, 2 * VFS_T_FLUX + 1);
-    return 0;
-  }
+  Box R;
+  bool march = c->fused && RhsMarch::region(d, R);
 #ifndef VFS_EMU
-  if (c->fused && c->tma_ok) {
-    // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
-    if (launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, &c->launches)) { set_err(c, "k_flux_tma launch failed"); return VFS_ERR_CUDA; }
-    { FaceFlux<0> f = {d}; Box b0 = {0, 1, 1, d.my - 1, k1, k2}, b1 = {d.mx - 2, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-    { FaceFlux<1> f = {d}; Box b0 = {1, d.mx - 1, 0, 1, k1, k2}, b1 = {1, d.mx - 1, d.my - 2, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-    { FaceFlux<2> f = {d};
-      Box b0 = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), klo(c, 1)}, b1 = {1, d.mx - 1, 1, d.my - 1, klo(c, d.mz - 2), klo(c, d.mz - 1)};
-      RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-  } else
+  march = march && c->tma_ok;
 #endif
-  {
-    { FaceFlux<0> f = {d}; Box b = {0, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
-    { FaceFlux<1> f = {d}; Box b = {1, d.mx - 1, 0, d.my - 1, k1, k2}; RUN(launch(c, b, f)); }
-    { FaceFlux<2> f = {d}; Box b = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2}; RUN(launch(c, b, f)); }
+  ShellBoxes S; S.n = 1;
+  S.proj[0] = box_owned(c); S.fp[0] = box_interior(c);
+  { Box f0 = {0, d.mx - 1, 1, d.my - 1, k1, k2}, f1 = {1, d.mx - 1, 0, d.my - 1, k1, k2}, f2 = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), k2};
+    S.fl[0][0] = f0; S.fl[0][1] = f1; S.fl[0][2] = f2; }
+  ev_rec(c, 2 * VFS_T_FLUX);
+  if (march) {
+    // regular interior: one marching kernel, fluxes and Fp stay on chip
+    RhsMarch P = {d, mode, s0, scale, R};
+#ifndef VFS_EMU
+    if (run_rhs_march(c->stream, c->tmap_rhs, P, &c->launches)) { set_err(c, "k_rhs_march launch failed"); return VFS_ERR_CUDA; }
+#else
+    run_rhs_march(c->stream, P, &c->launches);
+#endif
+    S = shell_boxes(c, R);
   }
   ev_rec(c, 2 * VFS_T_FLUX + 1);
+  // staged chain: the whole domain, or the boundary slabs around R
+  ev_rec(c, 2 * VFS_T_FP);
+  for (int n = 0; n < S.n; n++) {
+    { FaceFlux<0> f = {d}; RUN(launch(c, S.fl[n][0], f)); }
+    { FaceFlux<1> f = {d}; RUN(launch(c, S.fl[n][1], f)); }
+    { FaceFlux<2> f = {d}; RUN(launch(c, S.fl[n][2], f)); }
+  }
   Grp gf = grp(S_FC1, 18);
   RUN(g2l(c, gf));                                                    // momentum.c:1458-1496
   if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
-  ev_rec(c, 2 * VFS_T_FP);
-  { FpCell f = {d}; RUN(launch(c, box_interior(c), f)); }            // momentum.c:1548-1678
+  for (int n = 0; n < S.n; n++) { FpCell f = {d}; RUN(launch(c, S.fp[n], f)); }   // momentum.c:1548-1678
   ev_rec(c, 2 * VFS_T_FP + 1);
   Grp gp = grp(S_FP0, 3);
   RUN(g2l(c, gp));
   if (any_per(c)) RUN(node_copy(c, gp));                              // momentum.c:1687-1713
   ev_rec(c, 2 * VFS_T_PROJECT);
-  if (mode == 0) { ProjectAdd f = {d, s0, scale}; RUN(launch(c, box_owned(c), f)); }
-  else { ProjectSNES f = {d}; RUN(launch(c, box_owned(c), f)); }
+  for (int n = 0; n < S.n; n++) {
+    if (mode == 0) { ProjectAdd f = {d, s0, scale}; RUN(launch(c, S.proj[n], f)); }
+    else { ProjectSNES f = {d}; RUN(launch(c, S.proj[n], f)); }
+  }
   ev_rec(c, 2 * VFS_T_PROJECT + 1);
   return 0;
 }
@@ -558,8 +604,11 @@ static int les_cs(vfs_ctx *c) {
   ev_rec(c, 2 * VFS_T_LES2);
   if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    Les2Sep prog = {d};
-    if (run_block_march(c->stream, prog, les2_sep_grid(d, bi.k0, bi.k1), &c->launches)) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
+    if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
+    int r;
+    if (c->les2_ty == 8) { Les2Sep<8> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<8>>(d, bi.k0, bi.k1), &c->launches); }
+    else { Les2Sep<16> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<16>>(d, bi.k0, bi.k1), &c->launches); }
+    if (r) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES2 + 1);

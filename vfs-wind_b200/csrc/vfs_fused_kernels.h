@@ -190,42 +190,6 @@ struct Les3Body {
   }
 };
 
-// ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
-// One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
-// planes k-1..k+2: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets -1..TX+2 in i
-// (4th-order stencil of the i-face) and -1..TY+1 in j.  Faces with index 0 or m-2 along their normal
-// (domain-end / periodic-end stencils) are left to the staged FaceFlux<D> kernels, which the host runs
-// on those thin slabs only.
-typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 5, 4, 3, 1, 1, 1, 2> RingFlux;
-struct FluxAcc {
-  TileAcc<RingFlux> T;
-  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
-  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
-};
-struct FluxBody {
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
-    const int kg = k + d.kofs;
-    const long p = d.idx(i, j, k);
-    FluxAcc A = {T};
-    double fc[3], fv[3];
-    if (i <= d.mx - 3) {
-      face_flux_core<0, true>(d, A, p, i, fc, fv);
-#pragma unroll
-      for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
-    }
-    if (j <= d.my - 3) {
-      face_flux_core<1, true>(d, A, p, j, fc, fv);
-#pragma unroll
-      for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
-    }
-    if (kg <= d.mz - 3) {
-      face_flux_core<2, true>(d, A, p, kg, fc, fv);
-#pragma unroll
-      for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
-    }
-  }
-};
-
 static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q = 0; q < n; q++) s.sid[q] = v[q]; return s; }
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};
@@ -235,15 +199,6 @@ static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, cons
   const int v[4] = {S_LM, S_MM, S_IAJ, S_NV};
   return launch_tile_march<RingLes3>(st, tmap, d, k0, k1, 64, sids(4, v), Les3Body(), L);
 }
-static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
-  const int v[4] = {S_U0, S_U1, S_U2, S_NV};
-  return launch_tile_march<RingFlux>(st, tmap, d, k0, k1, 64, sids(4, v), FluxBody(), L);
-}
-#define VFS_FLUX_HX 4
-#define VFS_FLUX_HY 3
 #endif  // !VFS_EMU
 
-// fused residual kernel: not built yet (the staged FaceFlux/FpCell/Project kernels are used)
-static inline bool fused_rhs_applicable(const VfsDev &) { return false; }
-template <class S> static inline int launch_fused_rhs(S, const VfsDev &, int, int, double, long *) { return -3; }
 #endif

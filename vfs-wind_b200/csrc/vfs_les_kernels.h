@@ -33,9 +33,12 @@ template <int S0> struct GlobalAccS {
 // 
 template <int T, class Acc> VFS_HD double dcen(const Acc &A, int a, int c, int m, int per, int lowc) {
   constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
-  if (A.nv(ti, tj, tk) > VFS_SOLID || (!per && c == m - 2)) return A.u(a, 0, 0, 0) - A.u(a, -ti, -tj, -tk);
-  else if (A.nv(-ti, -tj, -tk) > VFS_SOLID || (!per && c == lowc)) return A.u(a, ti, tj, tk) - A.u(a, 0, 0, 0);
-  else return (A.u(a, ti, tj, tk) - A.u(a, -ti, -tj, -tk)) * 0.5;
+  // all operands are fetched unconditionally (independent loads, one memory round trip) and the
+  // stencil is chosen by selects: a load -> compare -> branch -> load chain serialises latency
+  const double up = A.u(a, ti, tj, tk), u0 = A.u(a, 0, 0, 0), um = A.u(a, -ti, -tj, -tk);
+  const bool hi = A.nv(ti, tj, tk) > VFS_SOLID || (!per && c == m - 2);
+  const bool lo = A.nv(-ti, -tj, -tk) > VFS_SOLID || (!per && c == lowc);
+  return hi ? u0 - um : (lo ? up - u0 : (up - um) * 0.5);
 }
 
 // velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)
@@ -221,6 +224,87 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
   double num = 0, den = 0;
   for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) num += Lij[b][a] * M[a][q] * G[b][q];
   for (int m = 0; m < 3; m++) for (int n = 0; n < 3; n++) for (int l = 0; l < 3; l++) den += M[n][m] * M[n][l] * G[m][l];
+  d.s[S_LM][p] = num; d.s[S_MM][p] = den;
+}
+
+// ---- marching-kernel form of the same algebra -------------------------------------------------------
+// Everything in les.c:441-468,607-626 that depends on the grid and the nvert mask only — the Simpson
+// weight sum (the divisor of every test filter, rhs2.c:522), filter = (1/aj)^(1/3), test_filter =
+// (sum coef*w)^(1/3) and the covariant metric tensor G — is computed once per grid/mask upload
+// instead of once per cell per step: two cbrt, three divisions, ~150 multiply-adds and two of the
+// seventeen filters leave the per-step kernel.  Sums are accumulated in the reference's order.
+struct LesGeo {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    double fdiv = 0, sum_weight = 0;
+    for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
+      const long n = p + r * d.sk + q * d.sj + pp;
+      const double w = (d.s[S_NV][n] > 0.1) ? 0. : d.s[S_IAJ][n];
+      sum_weight += w * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));
+      fdiv += simpson_w(r, q, pp) * w;
+    }
+    const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
+    const double test_filter = VFS_CBRT(sum_weight);
+    d.s[S_LFINV][p] = 1. / fdiv; d.s[S_LTF2][p] = test_filter * test_filter; d.s[S_LF2][p] = filter * filter;
+    const double a11 = d.s[S_CSI0][p], a12 = d.s[S_CSI1][p], a13 = d.s[S_CSI2][p];
+    const double a21 = d.s[S_ETA0][p], a22 = d.s[S_ETA1][p], a23 = d.s[S_ETA2][p];
+    const double a31 = d.s[S_ZET0][p], a32 = d.s[S_ZET1][p], a33 = d.s[S_ZET2][p];
+    const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+    const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
+    const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
+    const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
+    d.s[S_LG0][p] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
+    d.s[S_LG1][p] = xeta * xeta + yeta * yeta + zeta * zeta;
+    d.s[S_LG2][p] = xzet * xzet + yzet * yzet + zzet * zzet;
+    d.s[S_LG3][p] = xeta * xcsi + yeta * ycsi + zeta * zcsi;
+    d.s[S_LG4][p] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
+    d.s[S_LG5][p] = xeta * xzet + yeta * yzet + zeta * zzet;
+  }
+};
+
+// les.c:470-669 given the 15 filtered sums f[0..8] = sum sw U_a u_b (a-major), f[9..14] = sum sw |S|S_ij
+// and the precomputed factors above.  M^c is symmetric (S, S^ are), and the two triple sums
+// LM = L_ba M_aq G_bq, MM = M_nm M_nl G_ml are evaluated as (L M):G and (M^T M):G — 63 multiply-adds
+// instead of 162; the result differs from the literal triple loops by rounding only.
+VFS_HD void les2_finish_geo(const VfsDev &d, int i, int j, int kg, long p, const double *f) {
+  const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
+  const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
+  const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
+  const double finv = d.s[S_LFINV][p], tf2 = d.s[S_LTF2][p], f2 = d.s[S_LF2][p];
+  const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
+  const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
+  double gh[3][3];
+  grad_center(d, S_UF0, i, j, kg, p, gh);
+  const double S_hat = sabs_of(gh);
+  const double tS = -tf2 * S_hat;
+  // symmetric M^c: xx, xy, xz, yy, yz, zz
+  const double mc0 = tS * (0.5 * (gh[0][0] + gh[0][0])) + f2 * (f[9] * finv), mc1 = tS * (0.5 * (gh[0][1] + gh[1][0])) + f2 * (f[10] * finv);
+  const double mc2 = tS * (0.5 * (gh[0][2] + gh[2][0])) + f2 * (f[11] * finv), mc3 = tS * (0.5 * (gh[1][1] + gh[1][1])) + f2 * (f[12] * finv);
+  const double mc4 = tS * (0.5 * (gh[1][2] + gh[2][1])) + f2 * (f[13] * finv), mc5 = tS * (0.5 * (gh[2][2] + gh[2][2])) + f2 * (f[14] * finv);
+  const double Mc[3][3] = {{mc0, mc1, mc2}, {mc1, mc3, mc4}, {mc2, mc4, mc5}};
+  double M[3][3], L[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
+    M[a][1] = Mc[a][0] * eta[0] + Mc[a][1] * eta[1] + Mc[a][2] * eta[2];
+    M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
+#pragma unroll
+    for (int b = 0; b < 3; b++) L[a][b] = f[3 * a + b] * finv - _U[a] * _u[b];
+  }
+  const double G[3][3] = {{d.s[S_LG0][p], d.s[S_LG3][p], d.s[S_LG4][p]}, {d.s[S_LG3][p], d.s[S_LG1][p], d.s[S_LG5][p]}, {d.s[S_LG4][p], d.s[S_LG5][p], d.s[S_LG2][p]}};
+  double num = 0, den = 0;
+#pragma unroll
+  for (int b = 0; b < 3; b++)
+#pragma unroll
+    for (int q = 0; q < 3; q++) num += (L[b][0] * M[0][q] + L[b][1] * M[1][q] + L[b][2] * M[2][q]) * G[b][q];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int l = m; l < 3; l++) {
+      const double n = M[0][m] * M[0][l] + M[1][m] * M[1][l] + M[2][m] * M[2][l];
+      den += (l == m ? n : 2. * n) * G[m][l];
+    }
   d.s[S_LM][p] = num; d.s[S_MM][p] = den;
 }
 

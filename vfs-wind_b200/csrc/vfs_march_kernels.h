@@ -39,7 +39,7 @@ template <class P, int PH> struct PhaseSeq {
     if constexpr (PH + 1 < P::NPH) PhaseSeq<P, PH + 1>::run(prog, st, tid, bx, by, k, sm);
   }
 };
-template <class P> __global__ void __launch_bounds__(P::NT, 1) k_block_march(const P prog, int kbeg, int kend, int kchunk) {
+template <class P> __global__ void __launch_bounds__(P::NT, P::MINB) k_block_march(const P prog, int kbeg, int kend, int kchunk) {
   extern __shared__ __align__(16) double vfs_march_sm[];
   const int tid = threadIdx.x;
   const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
@@ -86,17 +86,18 @@ template <class P> static inline int run_block_march(void *, const P &prog, cons
 #endif
 
 // ---- LES pass 2 (les.c:308-669): separable Simpson test filters + Germano contraction ---------------
-// The reference filters 16 per-node products (w, w U_a u_b, w |S|S_ij) with the 27-point
-// (1,4,1)^3 Simpson stencil, one 27-term sum per product and cell (rhs2.c:499-523).  The stencil is
-// a tensor product, so the same sums are formed here as three 3-point passes: along k from the
-// thread's own column (global loads, coalesced along i), along i and along j through two
-// shared-memory exchange buffers — 4 shared loads + 2 stores per product and cell instead of 27
-// loads, which is what bounded the 27-term form (shared-memory bandwidth, profiles/r01c).  The
-// summation order differs from the reference's, i.e. results agree to rounding (~1e-15 relative),
-// not bitwise.  sum_weight (les.c:441-468, coefficients (1,2,1)^3/8) rides along as product 16.
-// The tensor algebra that follows the filters (les2_finish) runs in the last phase.
-struct Les2Sep {
-  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 17, NPH = 3, LEAD = 0;
+// The reference filters per-node products (w U_a u_b, w |S|S_ij) with the 27-point (1,4,1)^3 Simpson
+// stencil, one 27-term sum per product and cell (rhs2.c:499-523).  The stencil is a tensor product,
+// so the same sums are formed here as three 3-point passes: along k from the thread's own column
+// (global loads, coalesced along i), along i and along j through two shared-memory exchange
+// buffers — 4 shared loads + 2 stores per product and cell instead of 27 loads, which is what
+// bounded the 27-term form (shared-memory bandwidth, profiles/r01c).  The summation order differs
+// from the reference's, i.e. results agree to rounding (~1e-14 relative), not bitwise.  The weight
+// sum and sum_weight (les.c:441-468) depend on the grid and mask only and come from LesGeo.
+// The tensor algebra that follows the filters (les2_finish_geo) runs in the last phase.
+template <int TY_> struct Les2Sep {
+  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15, NPH = 3, LEAD = 0;
+  static constexpr int MINB = TY <= 8 ? 2 : 1;     // resident blocks per SM the launch bounds ask for
   static constexpr bool SYNC_AFTER_LAST = false;   // phase 0 of the next step does not touch what phase 2 reads
   static constexpr long SMEM_D = 2L * NV * NT;
   struct State { double v[NV]; };
@@ -114,20 +115,29 @@ struct Les2Sep {
       for (int a = 0; a < NV; a++) K[a] = 0;
       if (i <= d.mx - 1 && j <= d.my - 1) {
         const long p = d.idx(i, j, k);
+        {   // the planes the NEXT step touches first: raw products at k+2, finish operands at k+1 (UF also k+2)
+          const long n2 = p + 2 * d.sk, n1 = p + d.sk;
+          VFS_PREFETCH_L2(d.s[S_LW] + n2);
+#pragma unroll
+          for (int a = 0; a < 3; a++) { VFS_PREFETCH_L2(d.s[S_U0 + a] + n2); VFS_PREFETCH_L2(d.s[S_LU0 + a] + n2); VFS_PREFETCH_L2(d.s[S_UF0 + a] + n2); }
+#pragma unroll
+          for (int a = 0; a < 6; a++) { VFS_PREFETCH_L2(d.s[S_LSS0 + a] + n2); VFS_PREFETCH_L2(d.s[S_LG0 + a] + n1); }
+#pragma unroll
+          for (int a = 0; a < 10; a++) VFS_PREFETCH_L2(d.s[S_CSI0 + a] + n1);
+          VFS_PREFETCH_L2(d.s[S_LFINV] + n1); VFS_PREFETCH_L2(d.s[S_LTF2] + n1); VFS_PREFETCH_L2(d.s[S_LF2] + n1);
+        }
 #pragma unroll
         for (int dk = -1; dk <= 1; dk++) {
           const long n = p + dk * d.sk;
           const double w = d.s[S_LW][n];
           const double sw = dk == 0 ? 4. * w : w;
           const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
-          const double U0 = d.s[S_LU0][n], U1 = d.s[S_LU1][n], U2 = d.s[S_LU2][n];
-          K[0] += sw;
-          K[1] += sw * (U0 * u0); K[2] += sw * (U0 * u1); K[3] += sw * (U0 * u2);
-          K[4] += sw * (U1 * u0); K[5] += sw * (U1 * u1); K[6] += sw * (U1 * u2);
-          K[7] += sw * (U2 * u0); K[8] += sw * (U2 * u1); K[9] += sw * (U2 * u2);
+          const double U0 = sw * d.s[S_LU0][n], U1 = sw * d.s[S_LU1][n], U2 = sw * d.s[S_LU2][n];
+          K[0] += U0 * u0; K[1] += U0 * u1; K[2] += U0 * u2;
+          K[3] += U1 * u0; K[4] += U1 * u1; K[5] += U1 * u2;
+          K[6] += U2 * u0; K[7] += U2 * u1; K[8] += U2 * u2;
 #pragma unroll
-          for (int a = 0; a < 6; a++) K[10 + a] += sw * d.s[S_LSS0 + a][n];
-          K[16] += dk == 0 ? w : 0.5 * w;
+          for (int a = 0; a < 6; a++) K[9 + a] += sw * d.s[S_LSS0 + a][n];
         }
       }
 #pragma unroll
@@ -136,26 +146,318 @@ struct Les2Sep {
       const int l = tx > 0 ? tid - 1 : tid, r = tx < TX - 1 ? tid + 1 : tid;
 #pragma unroll
       for (int a = 0; a < NV; a++) {
-        const double A = a < 16 ? sK[a * NT + l] + 4. * st.v[a] + sK[a * NT + r] : 0.5 * sK[a * NT + l] + st.v[a] + 0.5 * sK[a * NT + r];
+        const double A = sK[a * NT + l] + 4. * st.v[a] + sK[a * NT + r];
         st.v[a] = A; sA[a * NT + tid] = A;
       }
-    } else {                  // j pass + les.c:441-669 for the inner nodes of the tile
+    } else {                  // j pass + les.c:470-669 for the inner nodes of the tile
       if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
       const long p = d.idx(i, j, k);
       if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
       const int up = tid - TX, dn = tid + TX;
-      double fs[16];
+      double f[NV];
 #pragma unroll
-      for (int a = 0; a < 16; a++) fs[a] = sA[a * NT + up] + 4. * st.v[a] + sA[a * NT + dn];
-      const double sum_weight = 0.5 * sA[16 * NT + up] + st.v[16] + 0.5 * sA[16 * NT + dn];
-      les2_finish(d, i, j, k + d.kofs, p, fs, sum_weight);
+      for (int a = 0; a < NV; a++) f[a] = sA[a * NT + up] + 4. * st.v[a] + sA[a * NT + dn];
+      les2_finish_geo(d, i, j, k + d.kofs, p, f);
     }
   }
 };
-static inline MarchGrid les2_sep_grid(const VfsDev &d, int k0, int k1) {
-  MarchGrid g = {Les2Sep::tiles_x(d), Les2Sep::tiles_y(d), k0, k1, 1};
-  g.kchunk = pick_kchunk(g.nbx * g.nby, k1 - k0, 16);
+template <class P> static inline MarchGrid les2_sep_grid(const VfsDev &d, int k0, int k1) {
+  MarchGrid g = {P::tiles_x(d), P::tiles_y(d), k0, k1, 1};
+  g.kchunk = pick_kchunk(g.nbx * g.nby, k1 - k0, 16, 148 * P::MINB);
   return g;
 }
+
+// ---- fused residual: face fluxes -> Fp -> projection -> assembly (regular interior) ----------------
+// Replaces, for the cells whose whole dependency cone is free of domain-end special cases, the staged
+// chain FaceFlux<0,1,2> -> FpCell -> ProjectSNES/ProjectAdd (momentum.c:669-1938, 2297-2331): the 18
+// face-flux arrays and Fp never reach HBM.  Cells within 2 (low side) / 3 (high side) layers of a
+// domain boundary keep the staged kernels (run on thin slabs by the host), which carry the
+// reference's end-of-domain and periodic ghost-copy semantics verbatim.
+//
+// One thread per node of a TX x TY tile (overlapped tiling), marching k.  At step q a thread computes
+// the i- and j-face fluxes of its node on plane q and the k-face flux of face q+1 (one plane ahead:
+// the 4th-order divergence of plane q reaches face q+1), all with face_flux_core — the same
+// arithmetic as the staged kernels.  ucat and nvert come from a 5-plane shared-memory ring (planes
+// q-1..q+3, box (TX+4)x(TY+3)) fed by TMA one step ahead; centre metrics, aj and nu_t of plane q are
+// exchanged through shared memory (each node loaded once, coalesced); i-/j-face fluxes and Fp are
+// exchanged through shared memory; the k-face flux history (faces q-2..q+1) lives in registers.
+// Emission: components x,y of plane q and component z of plane q-1 (needs Fp of planes q-1 and q).
+struct RhsMarch {
+  static constexpr int TX = 32, TY = 16, NT = TX * TY;
+  static constexpr int NXP = TX + 4, NYP = TY + 3, NN = NXP * NYP;
+  static constexpr int TILE_D = ((NN * 8 + 127) / 128) * 16, NSC = 4, PLANE_D = NSC * TILE_D, STAGES = 5;
+  static constexpr int MXP = TX + 1, MYP = TY + 1, MT_D = ((MXP * MYP + 15) / 16) * 16, NM = 11;
+  static constexpr int OFF_M = STAGES * PLANE_D, OFF_F1 = OFF_M + NM * MT_D, OFF_F2 = OFF_F1 + 6 * NT, OFF_FP = OFF_F2 + 6 * NT, OFF_BAR = OFF_FP + 3 * NT;
+  static constexpr long SMEM_D = OFF_BAR + 8;
+  static constexpr int OX = TX - 4, OY = TY - 4;      // outputs per tile
+  struct State { double c3[3][3], v3[2][3], cn[3], vn[3], fp[3], zdot, ajz; };
+  VfsDev d; int mode, s0; double scale; Box R;        // R: regular output region, local k, upper bounds exclusive
+
+  static bool region(const VfsDev &d, Box &R) {
+    R.i0 = 3; R.i1 = d.mx - 4; R.j0 = 3; R.j1 = d.my - 4;
+    int k0 = 3 - d.kofs, k1 = d.mz - 4 - d.kofs;
+    R.k0 = k0 < 0 ? 0 : k0; R.k1 = k1 > d.nzl ? d.nzl : k1;
+    return R.i1 > R.i0 && R.j1 > R.j0 && R.k1 > R.k0;
+  }
+  int tiles_x() const { return (R.i1 - R.i0 + OX - 1) / OX; }
+  int tiles_y() const { return (R.j1 - R.j0 + OY - 1) / OY; }
+  VFS_HD int iorg(int bx) const { return R.i0 - 2 + bx * OX; }
+  VFS_HD int jorg(int by) const { return R.j0 - 2 + by * OY; }
+  VFS_HD static int slot_off(int kk, int q0) { return ((kk - q0) % STAGES) * PLANE_D; }
+
+  struct RingView {
+    const double *ring; int so[4]; int xy;
+    VFS_HD double u(int a, int di, int dj, int dk) const { return ring[so[dk + 1] + a * TILE_D + xy + dj * NXP + di]; }
+    VFS_HD double nv(int di, int dj, int dk) const { return ring[so[dk + 1] + 3 * TILE_D + xy + dj * NXP + di]; }
+  };
+  struct AccSM {       // metrics / nu_t of plane q from the exchange buffer
+    RingView V; const double *m; int nb; double ucv;
+    VFS_HD double u(int a, int di, int dj, int dk) const { return V.u(a, di, dj, dk); }
+    VFS_HD double nv(int di, int dj, int dk) const { return V.nv(di, dj, dk); }
+    template <int D> VFS_HD double met(int s, int side) const { return m[s * MT_D + side * nb]; }
+    template <int D> VFS_HD double aj(int side) const { return m[9 * MT_D + side * nb]; }
+    template <int D> VFS_HD double nut(int side) const { return m[10 * MT_D + side * nb]; }
+    template <int D> VFS_HD double uc(int) const { return ucv; }
+  };
+  struct AccReg {      // metrics / nu_t of the thread's own column on two planes, in registers
+    RingView V; double m0[11], m1[11]; double ucv;
+    VFS_HD double u(int a, int di, int dj, int dk) const { return V.u(a, di, dj, dk); }
+    VFS_HD double nv(int di, int dj, int dk) const { return V.nv(di, dj, dk); }
+    template <int D> VFS_HD double met(int s, int side) const { return side ? m1[s] : m0[s]; }
+    template <int D> VFS_HD double aj(int side) const { return side ? m1[9] : m0[9]; }
+    template <int D> VFS_HD double nut(int side) const { return side ? m1[10] : m0[10]; }
+    template <int D> VFS_HD double uc(int) const { return ucv; }
+  };
+
+  VFS_HD void begin(State &st) const {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { st.c3[0][a] = st.c3[1][a] = st.c3[2][a] = 0; st.v3[0][a] = st.v3[1][a] = 0; st.cn[a] = st.vn[a] = st.fp[a] = 0; }
+    st.zdot = 0; st.ajz = 1;
+  }
+  VFS_HD void load_met(double *sM, int slot, int ii, int jj, int q) const {
+    const bool inb = ii < d.mx + VFS_G && jj < d.my + VFS_G;
+    const long n = inb ? d.idx(ii, jj, q) : d.idx(0, 0, q);
+#pragma unroll
+    for (int s = 0; s < 10; s++) sM[s * MT_D + slot] = d.s[S_CSI0 + s][n];
+    sM[10 * MT_D + slot] = d.s[S_NUT][n];
+  }
+  // phase 0: centre metrics, aj, nu_t of plane q -> exchange buffer (tile + one extra column and row)
+  VFS_HD void phase0(int tid, int bx, int by, int q, int ka, double *sm) const {
+    if (q < ka) return;
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    double *sM = sm + OFF_M;
+    load_met(sM, ty * MXP + tx, i, j, q);
+    if (tx == TX - 1) load_met(sM, ty * MXP + TX, i + 1, j, q);
+    if (ty == TY - 1) load_met(sM, TY * MXP + tx, i, j + 1, q);
+  }
+  VFS_HD RingView view(const double *sm, int tx, int ty, int kc, int q0, int nlo, int nhi) const {
+    RingView V; V.ring = sm; V.xy = (ty + 1) * NXP + tx + 1;
+#pragma unroll
+    for (int dk = -1; dk <= 2; dk++) V.so[dk + 1] = (dk >= nlo && dk <= nhi) ? slot_off(kc + dk, q0) : 0;
+    return V;
+  }
+  // phase 1a: i- and j-face fluxes of plane q -> exchange buffers
+  VFS_HD void phase1a(int tid, int bx, int by, int q, int ka, double *sm) const {
+    if (q < ka) return;
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    const bool need1 = ty >= 2 && ty <= TY - 2 && j <= R.j1 && i <= R.i1 + 1;
+    const bool need2 = tx >= 2 && tx <= TX - 2 && i <= R.i1 && j <= R.j1 + 1;
+    if (!need1 && !need2) return;
+    const long p = d.idx(i, j, q);
+    const RingView V = view(sm, tx, ty, q, ka - 3, -1, 1);
+    const double *m = sm + OFF_M + ty * MXP + tx;
+    double fc[3], fv[3];
+    if (need1) {
+      AccSM A = {V, m, 1, d.s[S_UC0][p]};
+      face_flux_core<0, true>(d, A, 0, fc, fv);
+      double *sF = sm + OFF_F1;
+#pragma unroll
+      for (int a = 0; a < 3; a++) { sF[a * NT + tid] = fc[a]; sF[(3 + a) * NT + tid] = fv[a]; }
+    }
+    if (need2) {
+      AccSM A = {V, m, MXP, d.s[S_UC1][p]};
+      face_flux_core<1, true>(d, A, 0, fc, fv);
+      double *sF = sm + OFF_F2;
+#pragma unroll
+      for (int a = 0; a < 3; a++) { sF[a * NT + tid] = fc[a]; sF[(3 + a) * NT + tid] = fv[a]; }
+    }
+  }
+  VFS_HD bool need_fp(int tx, int ty, int i, int j) const { return tx >= 2 && tx <= TX - 2 && ty >= 2 && ty <= TY - 2 && i <= R.i1 && j <= R.j1; }
+  // phase 1b: k-face flux of face q+1 (between planes q+1 and q+2) -> registers
+  VFS_HD void phase1b(State &st, int tid, int bx, int by, int q, int ka, const double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (!need_fp(tx, ty, i, j)) return;
+    const long p = d.idx(i, j, q + 1);
+    AccReg A;
+    A.V = view(sm, tx, ty, q + 1, ka - 3, -1, 2);
+#pragma unroll
+    for (int s = 0; s < 10; s++) { A.m0[s] = d.s[S_CSI0 + s][p]; A.m1[s] = d.s[S_CSI0 + s][p + d.sk]; }
+    A.m0[10] = d.s[S_NUT][p]; A.m1[10] = d.s[S_NUT][p + d.sk];
+    A.ucv = d.s[S_UC2][p];
+    face_flux_core<2, true>(d, A, 0, st.cn, st.vn);
+  }
+  // phase 2: Fp of plane q (momentum.c:1548-1678, regular branch) -> registers + exchange buffer; shift the k history
+  VFS_HD void phase2(State &st, int tid, int bx, int by, int q, int ka, double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (q >= ka && need_fp(tx, ty, i, j)) {
+      const RingView V = view(sm, tx, ty, q, ka - 3, -1, 1);
+      const double *F1 = sm + OFF_F1 + tid, *F2 = sm + OFF_F2 + tid;
+      const double nv0 = V.nv(0, 0, 0);
+      const bool c1 = V.nv(-1, 0, 0) + nv0 + V.nv(1, 0, 0) > 0.1, c2 = V.nv(0, -1, 0) + nv0 + V.nv(0, 1, 0) > 0.1, c3 = V.nv(0, 0, -1) + nv0 + V.nv(0, 0, 1) > 0.1;
+      double *sFp = sm + OFF_FP;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const double f1 = F1[a * NT], f1m = F1[a * NT - 1], f2 = F2[a * NT], f2m = F2[a * NT - TX];
+        const double div = (f1 - f1m + f2 - f2m + st.c3[2][a] - st.c3[1][a]);
+        const double vis = (F1[(3 + a) * NT] - F1[(3 + a) * NT - 1] + F2[(3 + a) * NT] - F2[(3 + a) * NT - TX] + st.v3[1][a] - st.v3[0][a]);
+        double fp;
+        if (!d.second_order) {
+          double div4 = 0;
+          div4 += c1 ? (f1 - f1m) * 1. : (F1[a * NT + 1] - F1[a * NT - 2]) * (1. / 3.);
+          div4 += c2 ? (f2 - f2m) * 1. : (F2[a * NT + TX] - F2[a * NT - 2 * TX]) * (1. / 3.);
+          div4 += c3 ? (st.c3[2][a] - st.c3[1][a]) * 1. : (st.cn[a] - st.c3[0][a]) * (1. / 3.);
+          fp = (9. / 8.) * div + (-1. / 8.) * div4 + vis;
+        } else fp = div + vis;
+        st.fp[a] = fp; sFp[a * NT + tid] = fp;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) { st.c3[0][a] = st.c3[1][a]; st.c3[1][a] = st.c3[2][a]; st.c3[2][a] = st.cn[a]; st.v3[0][a] = st.v3[1][a]; st.v3[1][a] = st.vn[a]; }
+  }
+  VFS_HD void emit(int a, long p, bool masked, double r) const {
+    if (mode == 0) d.s[s0 + a][p] = masked ? 0. : d.s[s0 + a][p] + scale * r;
+    else d.s[S_R0 + a][p] = snes_assemble(d, a, p, masked, r);
+  }
+  // phase 3: projection (momentum.c:1733-1735), masks (:1833-1841) and assembly: x,y of plane q, z of plane q-1
+  VFS_HD void phase3(State &st, int tid, int bx, int by, int q, int ka, int kb, const double *sm) const {
+    if (q < ka) return;
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (!(tx >= 2 && tx <= TX - 3 && ty >= 2 && ty <= TY - 3 && i < R.i1 && j < R.j1)) return;
+    const RingView V = view(sm, tx, ty, q, ka - 3, -1, 1);
+    const double *m = sm + OFF_M + ty * MXP + tx, *sFp = sm + OFF_FP + tid;
+    const double f0 = st.fp[0], f1 = st.fp[1], f2 = st.fp[2];
+    const double aj = m[9 * MT_D], nv0 = V.nv(0, 0, 0);
+    const long p = d.idx(i, j, q);
+    if (q < kb) {
+      {
+        const double iaj = 2. / (1. / aj + 1. / m[9 * MT_D + 1]);
+        const double r = (0.5 * (m[0] * f0 + m[MT_D] * f1 + m[2 * MT_D] * f2) +
+                          0.5 * (m[1] * sFp[1] + m[MT_D + 1] * sFp[NT + 1] + m[2 * MT_D + 1] * sFp[2 * NT + 1])) * iaj;
+        emit(0, p, nv0 + V.nv(1, 0, 0) > 0.1, r);
+      }
+      {
+        const double jaj = 2. / (1. / aj + 1. / m[9 * MT_D + MXP]);
+        const double r = (0.5 * (m[3 * MT_D] * f0 + m[4 * MT_D] * f1 + m[5 * MT_D] * f2) +
+                          0.5 * (m[3 * MT_D + MXP] * sFp[TX] + m[4 * MT_D + MXP] * sFp[NT + TX] + m[5 * MT_D + MXP] * sFp[2 * NT + TX])) * jaj;
+        emit(1, p, nv0 + V.nv(0, 1, 0) > 0.1, r);
+      }
+    }
+    const double zd = 0.5 * (m[6 * MT_D] * f0 + m[7 * MT_D] * f1 + m[8 * MT_D] * f2);
+    if (q > ka) {
+      const double kaj = 2. / (1. / st.ajz + 1. / aj);
+      const double r = (st.zdot + zd) * kaj;
+      emit(2, p - d.sk, V.nv(0, 0, -1) + nv0 > 0.1, r);
+    }
+    st.zdot = zd; st.ajz = aj;
+  }
+};
+
+#ifndef VFS_EMU
+#include "vfs_fused_kernels.h"
+__global__ void __launch_bounds__(RhsMarch::NT, 1) k_rhs_march(const __grid_constant__ CUtensorMap tmap, const RhsMarch P, int kchunk) {
+  extern __shared__ __align__(128) double vfs_rhs_sm[];
+  double *sm = vfs_rhs_sm;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + RhsMarch::OFF_BAR);
+  constexpr int STAGES = RhsMarch::STAGES;
+  const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+  const int ka = P.R.k0 + blockIdx.z * kchunk, kb = min(P.R.k1, ka + kchunk);
+  if (ka >= kb) return;
+  const int q0 = ka - 3, klast = kb + 3;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int kk) {
+    const int slot = (kk - q0) % STAGES;
+    double *dst = sm + slot * RhsMarch::PLANE_D;
+    mbar_expect_tx(&bars[slot], RhsMarch::NSC * RhsMarch::NN * 8);
+    const int sid[4] = {S_U0, S_U1, S_U2, S_NV};
+#pragma unroll
+    for (int s = 0; s < 4; s++) tma_load_tile(dst + s * RhsMarch::TILE_D, &tmap, P.iorg(bx) - 1 + VFS_G, P.jorg(by) - 1 + VFS_G, kk + VFS_G, sid[s], &bars[slot]);
+  };
+  auto wait_plane = [&](int kk) { const int n = kk - q0; mbar_wait(&bars[n % STAGES], (n / STAGES) & 1); };
+  if (tid == 0) for (int kk = q0; kk <= q0 + 4 && kk <= klast; kk++) issue(kk);
+  RhsMarch::State st;
+  P.begin(st);
+  for (int kk = q0; kk < q0 + 3; kk++) wait_plane(kk);
+  for (int q = q0; q <= kb; q++) {
+    P.phase0(tid, bx, by, q, ka, sm);
+    __syncthreads();
+    P.phase1a(tid, bx, by, q, ka, sm);
+    wait_plane(q + 3);
+    P.phase1b(st, tid, bx, by, q, ka, sm);
+    __syncthreads();
+    P.phase2(st, tid, bx, by, q, ka, sm);
+    __syncthreads();
+    P.phase3(st, tid, bx, by, q, ka, kb, sm);
+    __syncthreads();
+    if (tid == 0 && q > q0 && q + 4 <= klast) { fence_proxy_async(); issue(q + 4); }
+  }
+}
+static inline int run_rhs_march(cudaStream_t stream, const CUtensorMap &tmap, const RhsMarch &P, long *launches) {
+  static bool attr_set = false;
+  const int bytes = (int)(RhsMarch::SMEM_D * sizeof(double));
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_rhs_march, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  const int ntx = P.tiles_x(), nty = P.tiles_y(), nk = P.R.k1 - P.R.k0;
+  const int kchunk = pick_kchunk(ntx * nty, nk, 24);
+  dim3 grd(ntx, nty, (nk + kchunk - 1) / kchunk);
+  k_rhs_march<<<grd, RhsMarch::NT, bytes, stream>>>(tmap, P, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#else
+static inline int run_rhs_march(void *, const RhsMarch &P, long *launches) {
+  typedef RhsMarch M;
+  std::vector<double> smv(M::SMEM_D);
+  std::vector<M::State> st(M::NT);
+  double *sm = smv.data();
+  const VfsDev &d = P.d;
+  const int ntx = P.tiles_x(), nty = P.tiles_y(), nk = P.R.k1 - P.R.k0;
+  const int kchunk = pick_kchunk(ntx * nty, nk, 4, 7);      // small odd chunks: exercise the chunk seams
+  for (int bz = 0; bz * kchunk < nk; bz++)
+    for (int by = 0; by < nty; by++)
+      for (int bx = 0; bx < ntx; bx++) {
+        const int ka = P.R.k0 + bz * kchunk, kb = P.R.k1 < ka + kchunk ? P.R.k1 : ka + kchunk;
+        const int q0 = ka - 3, klast = kb + 3;
+        auto issue = [&](int kk) {      // what the TMA unit does: box copy with zero fill outside the padded array
+          double *dst = sm + ((kk - q0) % M::STAGES) * M::PLANE_D;
+          const int sid[4] = {S_U0, S_U1, S_U2, S_NV};
+          for (int s = 0; s < 4; s++)
+            for (int y = 0; y < M::NYP; y++)
+              for (int x = 0; x < M::NXP; x++) {
+                const int X = P.iorg(bx) - 1 + VFS_G + x, Y = P.jorg(by) - 1 + VFS_G + y, Z = kk + VFS_G;
+                const bool in = X >= 0 && X < d.pitch && Y >= 0 && Y < d.ny && Z >= 0 && Z < d.nzt;
+                dst[s * M::TILE_D + y * M::NXP + x] = in ? d.s[sid[s]][(long)Z * d.sk + (long)Y * d.sj + X] : 0.;
+              }
+        };
+        for (int kk = q0; kk <= q0 + 4 && kk <= klast; kk++) issue(kk);
+        for (int t = 0; t < M::NT; t++) P.begin(st[t]);
+        for (int q = q0; q <= kb; q++) {
+          for (int t = 0; t < M::NT; t++) P.phase0(t, bx, by, q, ka, sm);
+          for (int t = 0; t < M::NT; t++) P.phase1a(t, bx, by, q, ka, sm);
+          for (int t = 0; t < M::NT; t++) P.phase1b(st[t], t, bx, by, q, ka, sm);
+          for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, q, ka, sm);
+          for (int t = 0; t < M::NT; t++) P.phase3(st[t], t, bx, by, q, ka, kb, sm);
+          if (q > q0 && q + 4 <= klast) issue(q + 4);
+        }
+      }
+  (*launches)++;
+  return 0;
+}
+#endif
 
 #endif

@@ -12,13 +12,20 @@
 
 #define VFS_SOLID 0.1
 
-// Accessor over the global padded arrays: offsets (di,dj,dk) are relative to the face's node p.
-// The tiled kernels (vfs_fused_kernels.h) supply an accessor over TMA-staged shared-memory planes
-// with the same interface, so both forms run the identical arithmetic below.
+// Accessor over the global padded arrays: offsets (di,dj,dk) are relative to the face's node p;
+// met/aj/nut/uc give the centre metrics (scalar S_CSI0+s), aj, nu_t at p (side 0) or p + e_D
+// (side 1) and the contravariant flux component D at p + off*e_D.  The marching kernels
+// (vfs_march_kernels.h) supply accessors with the same interface over TMA-staged shared-memory
+// planes and exchange buffers, so every form runs the identical arithmetic below.
 struct GlobalAcc {
   const VfsDev &d; long p;
   VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S_U0 + a][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
+  template <int D> VFS_HD long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
+  template <int D> VFS_HD double met(int s, int side) const { return d.s[S_CSI0 + s][p + side * sn<D>()]; }
+  template <int D> VFS_HD double aj(int side) const { return d.s[S_AJ][p + side * sn<D>()]; }
+  template <int D> VFS_HD double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
+  template <int D> VFS_HD double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
 };
 
 // tangential difference of component a along unit direction T at the face between node offset
@@ -26,30 +33,32 @@ struct GlobalAcc {
 template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a) {
   constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);      // pn = p + n
   constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
-  if (A.nv(ti, tj, tk) > VFS_SOLID || A.nv(ni + ti, nj + tj, nk + tk) > VFS_SOLID)
-    return (A.u(a, ni, nj, nk) + A.u(a, 0, 0, 0) - A.u(a, ni - ti, nj - tj, nk - tk) - A.u(a, -ti, -tj, -tk)) * 0.5;
-  else if (A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID)
-    return (A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk) - A.u(a, ni, nj, nk) - A.u(a, 0, 0, 0)) * 0.5;
-  else
-    return (A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk) - A.u(a, ni - ti, nj - tj, nk - tk) - A.u(a, -ti, -tj, -tk)) * 0.25;
+  // operands fetched unconditionally, stencil chosen by selects (see dcen in vfs_les_kernels.h)
+  const double a0 = A.u(a, 0, 0, 0), an = A.u(a, ni, nj, nk);
+  const double p0 = A.u(a, ti, tj, tk), pn = A.u(a, ni + ti, nj + tj, nk + tk);
+  const double m0 = A.u(a, -ti, -tj, -tk), mn = A.u(a, ni - ti, nj - tj, nk - tk);
+  const bool hi = A.nv(ti, tj, tk) > VFS_SOLID || A.nv(ni + ti, nj + tj, nk + tk) > VFS_SOLID;
+  const bool lo = A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID;
+  return hi ? (an + a0 - mn - m0) * 0.5 : (lo ? (pn + p0 - an - a0) * 0.5 : (pn + p0 - mn - m0) * 0.25);
 }
 
 // One face of family D (0/1/2 = i-/j-/k-face) between node p and p + e_D, stored at p ("upper
 // integer node", momentum.c:508-509).  c = index of p along D (global), m = node count along D.
 // REGULAR = true compiles out the domain-end / periodic-end special cases (faces 1..m-3 only).
-// Metrics, nu_t and ucont are read from the global arrays at p and p + e_D.
+// Metrics, nu_t and ucont come through the accessor (at p and p + e_D).
 template <int D, bool REGULAR, class Acc>
-VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, long p, int c, double fc[3], double fv[3]) {
+VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], double fv[3]) {
   constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);
-  const long sn = (D == 0 ? 1 : (D == 1 ? d.sj : d.sk));
   const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
   const int per = (D == 0 ? d.perx : (D == 1 ? d.pery : d.perz));
-  const long pn = p + sn;
   const double nvp = A.nv(0, 0, 0), nvn = A.nv(ni, nj, nk);
 
-  // face metrics (metrics.c:589-592 and j/k twins)
-  const V3 cs = face3(d, S_CSI0, p, pn), et = face3(d, S_ETA0, p, pn), ze = face3(d, S_ZET0, p, pn);
-  const double ajc = 2. / (1. / d.s[S_AJ][p] + 1. / d.s[S_AJ][pn]);
+  // face metrics (metrics.c:589-592 and j/k twins): 0.5*centre + 0.5*centre, harmonic mean for aj
+#define VFS_F3(s0) mk3(0.5 * A.template met<D>(s0, 0) + 0.5 * A.template met<D>(s0, 1), 0.5 * A.template met<D>(s0 + 1, 0) + 0.5 * A.template met<D>(s0 + 1, 1), \
+                       0.5 * A.template met<D>(s0 + 2, 0) + 0.5 * A.template met<D>(s0 + 2, 1))
+  const V3 cs = VFS_F3(0), et = VFS_F3(3), ze = VFS_F3(6);
+#undef VFS_F3
+  const double ajc = 2. / (1. / A.template aj<D>(0) + 1. / A.template aj<D>(1));
   const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
 
   // du[a][b] = d u_a / d xi_b  (b: csi, eta, zet)
@@ -74,19 +83,22 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, long p, int c, double 
   }
 
   // ---- convective flux (momentum.c:700-813) ----
-  int oL = -1, oR = 2;                                   // offsets along D of the outer stencil nodes
+  // offsets along D of the outer stencil nodes; regular faces use fixed offsets and a select
+  // (`coll`: the stencil collapses to the two face nodes), so no accessor is indexed dynamically
+  int oL = -1, oR = 2;
+  bool coll = false;
   if (!REGULAR && (c == 0 || c == m - 2)) {
     if (per && c == m - 2) oR = 4;                       // index m+2
     else if (per && c == 0) oL = -3;                     // index -3
     else oL = 0, oR = 1;
-  } else if (A.nv(oL * ni, oL * nj, oL * nk) + A.nv(oR * ni, oR * nj, oR * nk) > 0.1) oL = 0, oR = 1;
-  if (d.second_order) oL = 0, oR = 1;
+  } else if (A.nv(-ni, -nj, -nk) + A.nv(2 * ni, 2 * nj, 2 * nk) > 0.1) { oL = 0, oR = 1; coll = true; }
+  if (d.second_order) { oL = 0, oR = 1; coll = true; }
 
-  const double *UC = d.s[S_UC0 + D];
-  double ucon = UC[p];
+  const double uc0 = A.template uc<D>(0);
+  double ucon = uc0;
   if (!REGULAR) {
-    if (per && c == 0) ucon = UC[p - 2 * sn];
-    if (D == 2 && c == m - 2 && d.bc[5] == 4 && (int)nvp == 0) ucon = UC[p - sn];
+    if (per && c == 0) ucon = A.template uc<D>(-2);
+    if (D == 2 && c == m - 2 && d.bc[5] == 4 && (int)nvp == 0) ucon = A.template uc<D>(-1);
   }
   const double up = -0.5 * (ucon + fabs(ucon));
   const double um = -0.5 * (ucon - fabs(ucon));
@@ -104,11 +116,16 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, long p, int c, double 
     }
   } else if (d.second_order) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) fc[a] = -UC[p] * 0.5 * (A.u(a, 0, 0, 0) + A.u(a, ni, nj, nk));
+    for (int a = 0; a < 3; a++) fc[a] = -uc0 * 0.5 * (A.u(a, 0, 0, 0) + A.u(a, ni, nj, nk));
   } else {
 #pragma unroll
-    for (int a = 0; a < 3; a++)
-      fc[a] = -UC[p] * 0.0625 * (-A.u(a, oL * ni, oL * nj, oL * nk) + 9. * A.u(a, 0, 0, 0) + 9. * A.u(a, ni, nj, nk) - A.u(a, oR * ni, oR * nj, oR * nk));
+    for (int a = 0; a < 3; a++) {
+      const double u0 = A.u(a, 0, 0, 0), u1 = A.u(a, ni, nj, nk);
+      double uL, uR;
+      if (REGULAR) { uL = A.u(a, -ni, -nj, -nk); uR = A.u(a, 2 * ni, 2 * nj, 2 * nk); uL = coll ? u0 : uL; uR = coll ? u1 : uR; }
+      else { uL = A.u(a, oL * ni, oL * nj, oL * nk); uR = A.u(a, oR * ni, oR * nj, oR * nk); }
+      fc[a] = -uc0 * 0.0625 * (-uL + 9. * u0 + 9. * u1 - uR);
+    }
   }
   if (nvp + nvn > 0.1 && (d.immersed == 3 || !d.immersed)) fc[0] = fc[1] = fc[2] = 0;
 
@@ -116,11 +133,10 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, long p, int c, double 
   const double nu = 1. / d.ren;
   fv[0] = fv[1] = fv[2] = 0;
   if (d.les) {
-    const double *nt = d.s[S_NUT];
     double nu_t;
-    if ((!REGULAR && c == 0 && !per) || nvp > 0.1) nu_t = nt[pn];
-    else if ((!REGULAR && c == m - 2 && !per) || nvn > 0.1) nu_t = nt[p];
-    else nu_t = 0.5 * (nt[p] + nt[pn]);
+    if ((!REGULAR && c == 0 && !per) || nvp > 0.1) nu_t = A.template nut<D>(1);
+    else if ((!REGULAR && c == m - 2 && !per) || nvn > 0.1) nu_t = A.template nut<D>(0);
+    else nu_t = 0.5 * (A.template nut<D>(0) + A.template nut<D>(1));
 #pragma unroll
     for (int a = 0; a < 3; a++)
       fv[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu_t;
@@ -143,7 +159,7 @@ template <int D> struct FaceFlux {
     const long p = d.idx(i, j, k);
     GlobalAcc A = {d, p};
     double fc[3], fv[3];
-    face_flux_core<D, false>(d, A, p, c, fc, fv);
+    face_flux_core<D, false>(d, A, c, fc, fv);
     const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D;
     for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
   }
@@ -242,6 +258,25 @@ struct ProjectAdd {
 //   Rhs = mask( (-U + U_o)/dt + 0.5 R(U) ) + 0.5 RHS_o - dP [+ F_eul]        (time_coeff()==1)
 //   Rhs = mask( (-1.5U + 2U_o - 0.5U_rm1)/dt + R(U) ) - dP [+ F_eul]         (BDF2)
 // mask() = the Formfunction_2 zeroing, applied before the last three terms.
+VFS_HD double snes_assemble(const VfsDev &d, int a, long p, bool masked, double r) {
+  const double dt = d.dt;
+  double v;
+  if (masked) v = 0.;
+  else if (!d.bdf2) {
+    v = (-1. / dt) * d.s[S_UC0 + a][p];
+    v += (1. / dt) * d.s[S_UCO0 + a][p];
+    v += 0.5 * r;
+  } else {
+    v = (-1.5 / dt) * d.s[S_UC0 + a][p];
+    v += (2. / dt) * d.s[S_UCO0 + a][p];
+    v += (-0.5 / dt) * d.s[S_UCM0 + a][p];
+    v += 1.0 * r;
+  }
+  if (!d.bdf2) v += 0.5 * d.s[S_RO0 + a][p];
+  v += -1. * d.s[S_DP0 + a][p];
+  if (d.has_feul) v += 1. * d.s[S_FE0 + a][p];
+  return v;
+}
 struct ProjectSNES {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
@@ -251,25 +286,7 @@ struct ProjectSNES {
     V3 r = mk3(0, 0, 0);
     if (m != 7) r = project_fp(d, p);
     const double rr[3] = {r.x, r.y, r.z};
-    const double dt = d.dt;
-    for (int a = 0; a < 3; a++) {
-      double v;
-      if (m & (1 << a)) v = 0.;
-      else if (!d.bdf2) {
-        v = (-1. / dt) * d.s[S_UC0 + a][p];
-        v += (1. / dt) * d.s[S_UCO0 + a][p];
-        v += 0.5 * rr[a];
-      } else {
-        v = (-1.5 / dt) * d.s[S_UC0 + a][p];
-        v += (2. / dt) * d.s[S_UCO0 + a][p];
-        v += (-0.5 / dt) * d.s[S_UCM0 + a][p];
-        v += 1.0 * rr[a];
-      }
-      if (!d.bdf2) v += 0.5 * d.s[S_RO0 + a][p];
-      v += -1. * d.s[S_DP0 + a][p];
-      if (d.has_feul) v += 1. * d.s[S_FE0 + a][p];
-      d.s[S_R0 + a][p] = v;
-    }
+    for (int a = 0; a < 3; a++) d.s[S_R0 + a][p] = snes_assemble(d, a, p, (m >> a) & 1, rr[a]);
   }
 };
 
