@@ -64,12 +64,14 @@ def ref_setup(cfg, refdrv):
     return ref, xyz, fields, met
 
 
-def dev_setup(cfg, xyz, fields, lib=None, device=0):
+def dev_setup(cfg, xyz, fields, lib=None, device=0, options=None):
     pkg = load_package()
     capi = pkg.capi
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
     p = capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], device=device)
     ctx = capi.VfsContext(p, lib=lib)
+    for key, val in (options or {}).items():
+        ctx.set_option(key, val)
     ctx.upload("COOR", xyz)
     ctx.FormMetrics()
     ctx.upload("NVERT", fields["nvert"])
@@ -84,10 +86,10 @@ def dev_setup(cfg, xyz, fields, lib=None, device=0):
     return ctx
 
 
-def run_parity(cfg, refdrv, lib=None, device=0, verbose=False):
+def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None):
     """Full path comparison.  Returns dict name -> relative error."""
     ref, xyz, fields, met = ref_setup(cfg, refdrv)
-    ctx = dev_setup(cfg, xyz, fields, lib=lib, device=device)
+    ctx = dev_setup(cfg, xyz, fields, lib=lib, device=device, options=options)
     err = {}
     for nm, key in (("CSI", "csi"), ("ETA", "eta"), ("ZET", "zet"), ("AJ", "aj")):
         err["metrics_" + nm] = relerr(ctx.download(nm), met[key])

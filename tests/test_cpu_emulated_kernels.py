@@ -34,3 +34,23 @@ def test_emulated_flag_variants(pkg, refdrv, emu):
         assert err.pop("FormFunction_SNES_zero_pattern") == 0, extra
         bad = {k: v for k, v in err.items() if not (v <= TOL)}
         assert not bad, (extra, bad)
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (45, 30, 27)), ("c3_turbine", (41, 33, 25))])
+def test_emulated_fused_residual_option(pkg, refdrv, emu, name, dims):
+    """Option 0 = 2: the fully fused residual marching kernel (interior) + staged boundary slabs, several
+    tiles and k-chunks wide, against the oracle."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = pc.run_parity(cfg, refdrv, lib=emu, options={0: 2})
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def test_emulated_staged_option(pkg, refdrv, emu):
+    """Option 0 = 0: the one-thread-per-cell staged kernels only (the literal restatement)."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 21, 17, 19)
+    err = pc.run_parity(cfg, refdrv, lib=emu, options={0: 0})
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad

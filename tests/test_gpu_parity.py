@@ -26,6 +26,17 @@ def test_path_matches_reference(pkg, refdrv, name, dims):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("name,dims", [("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41))])
+def test_fused_residual_option_matches_reference(pkg, refdrv, name, dims):
+    """Option 0 = 2: the fully fused residual marching kernel (TMA ring, fluxes and Fp on chip) on the
+    regular interior + staged boundary slabs."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = pc.run_parity(cfg, refdrv, device=0, options={0: 2})
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
 def test_flag_variants(pkg, refdrv):
     base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 25, 19, 23)
     for extra in (dict(second_order=1), dict(laplacian=1), dict(immersed=3), dict(les=1), dict(les=0), dict(testfilter_ik=1),

@@ -21,13 +21,6 @@
 
 #define VFS_G 4
 
-// hint: bring the line holding *p into L2 (no register, no stall); no-op in the host emulation
-#if defined(__CUDA_ARCH__)
-#define VFS_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
-#else
-#define VFS_PREFETCH_L2(p) ((void)0)
-#endif
-
 // internal scalar ids ------------------------------------------------------------------------
 enum {
   S_X = 0, S_Y, S_Z,                                  // node coordinates

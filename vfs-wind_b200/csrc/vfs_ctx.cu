@@ -50,6 +50,7 @@ struct vfs_ctx {
   int fused = 1;                 // use the TMA-staged tiled kernels when applicable
 #ifndef VFS_EMU
   CUtensorMap tmap;              // 4-D map over the scalar pool, box (TX+2, TY+2, 1, 1)
+  CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
   CUtensorMap tmap_rhs;          // same pool, box of the residual marching kernel
 #endif
   bool tma_ok = false;
@@ -61,6 +62,7 @@ struct vfs_ctx {
 #endif
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
+  int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
   int les2_ty = 16;              // tile height of the LES pass-2 marching kernel (option key 2: 8 or 16)
   bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
 };
@@ -203,6 +205,7 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
 #ifndef VFS_EMU
   c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
+              vfs_make_tensor_map(&c->tmap_flux, c->pool, c->d, c->scalar_len, VFS_TILE_TX + VFS_FLUX_HX, VFS_TILE_TY + VFS_FLUX_HY) == 0 &&
               vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0;
 #endif
   *out = c;
@@ -275,7 +278,8 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   if (!c) return VFS_ERR_ARG;
   if (key == 0) c->fused = value;
   else if (key == 1) c->use_graph = value;
-  else if (key == 2) c->les2_ty = value == 8 ? 8 : 16;
+  else if (key == 2) c->les2_ty = value;
+  else if (key == 3) c->flux_minb = value;
   graph_reset(c);
   return 0;
 }
@@ -464,13 +468,23 @@ static ShellBoxes shell_boxes(const vfs_ctx *c, const Box &R) {
   return S;
 }
 
+// S_IAJ = 1/aj over the whole padded array (filter weights; harmonic-mean face Jacobians)
+static int ensure_iaj(vfs_ctx *c) {
+  if (c->iaj_valid) return 0;
+  const VfsDev &d = c->d;
+  InvAj f = {d}; Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
+  RUN(launch(c, all, f)); c->iaj_valid = true;
+  return 0;
+}
+
 // mode 0: rhs[s0] += scale*R, masks (Formfunction_2) ; mode 1: full SNES assembly into S_R0
 static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const VfsDev &d = c->d;
+  RUN(ensure_iaj(c));
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
   Box R;
-  bool march = c->fused && RhsMarch::region(d, R);
+  bool march = c->fused == 2 && RhsMarch::region(d, R);     // experimental fully fused residual (option 0 = 2)
 #ifndef VFS_EMU
   march = march && c->tma_ok;
 #endif
@@ -489,14 +503,25 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
 #endif
     S = shell_boxes(c, R);
   }
-  ev_rec(c, 2 * VFS_T_FLUX + 1);
   // staged chain: the whole domain, or the boundary slabs around R
-  ev_rec(c, 2 * VFS_T_FP);
+#ifndef VFS_EMU
+  if (!march && c->fused && c->tma_ok) {
+    // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
+    if (launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, c->flux_minb, &c->launches)) { set_err(c, "k_flux_tma launch failed"); return VFS_ERR_CUDA; }
+    { FaceFlux<0> f = {d}; Box b0 = {0, 1, 1, d.my - 1, k1, k2}, b1 = {d.mx - 2, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    { FaceFlux<1> f = {d}; Box b0 = {1, d.mx - 1, 0, 1, k1, k2}, b1 = {1, d.mx - 1, d.my - 2, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    { FaceFlux<2> f = {d};
+      Box b0 = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), klo(c, 1)}, b1 = {1, d.mx - 1, 1, d.my - 1, klo(c, d.mz - 2), klo(c, d.mz - 1)};
+      RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+  } else
+#endif
   for (int n = 0; n < S.n; n++) {
     { FaceFlux<0> f = {d}; RUN(launch(c, S.fl[n][0], f)); }
     { FaceFlux<1> f = {d}; RUN(launch(c, S.fl[n][1], f)); }
     { FaceFlux<2> f = {d}; RUN(launch(c, S.fl[n][2], f)); }
   }
+  ev_rec(c, 2 * VFS_T_FLUX + 1);
+  ev_rec(c, 2 * VFS_T_FP);
   Grp gf = grp(S_FC1, 18);
   RUN(g2l(c, gf));                                                    // momentum.c:1458-1496
   if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
@@ -581,10 +606,7 @@ static int les_cs(vfs_ctx *c) {
   c->sabs_valid = false;
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
-  if (!c->iaj_valid) {       // whole padded array: the filters read ghost nodes too
-    InvAj f = {d}; Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
-    RUN(launch(c, all, f)); c->iaj_valid = true;
-  }
+  RUN(ensure_iaj(c));
   ev_rec(c, 2 * VFS_T_LES1);
 #ifndef VFS_EMU
   if (c->fused && c->tma_ok && !d.testfilter_ik) {
@@ -606,8 +628,12 @@ static int les_cs(vfs_ctx *c) {
     Box bi = box_interior(c);
     if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
     int r;
-    if (c->les2_ty == 8) { Les2Sep<8> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<8>>(d, bi.k0, bi.k1), &c->launches); }
-    else { Les2Sep<16> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<16>>(d, bi.k0, bi.k1), &c->launches); }
+#define VFS_LES2_RUN(TY, MB) { Les2Sep<TY, MB> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<TY, MB>>(d, bi.k0, bi.k1), &c->launches); }
+    if (c->les2_ty == 8) VFS_LES2_RUN(8, 2)
+    else if (c->les2_ty == 83) VFS_LES2_RUN(8, 3)
+    else if (c->les2_ty == 84) VFS_LES2_RUN(8, 4)
+    else VFS_LES2_RUN(16, 1)
+#undef VFS_LES2_RUN
     if (r) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }

@@ -91,8 +91,8 @@ template <class R> struct TileAcc {
 
 // Block = (i,j) tile, marches k in [ka,kb).  At step k planes k-PB..k+PA are resident; the slot of
 // plane k-PB is refilled (plane k-PB+STAGES) as soon as the whole block has finished step k.
-template <class R, class Body>
-__global__ void __launch_bounds__(R::TX *R::TY, 2)
+template <class R, class Body, int MINB = 2>
+__global__ void __launch_bounds__(R::TX *R::TY, MINB)
 k_tile_march(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int kend, int kchunk, SidList sl, Body body) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double *sm = reinterpret_cast<double *>(smraw);
@@ -140,16 +140,16 @@ k_tile_march(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int k
   }
 }
 
-template <class R, class Body>
+template <class R, class Body, int MINB = 2>
 static inline int launch_tile_march(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, int kchunk, const SidList &sl, const Body &body, long *launches) {
   if (k1 <= k0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_tile_march<R, Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::BYTES) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(k_tile_march<R, Body, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::BYTES) != cudaSuccess) return -2;
     attr_set = true;
   }
   dim3 grd((d.mx - 2 + R::TX - 1) / R::TX, (d.my - 2 + R::TY - 1) / R::TY, (k1 - k0 + kchunk - 1) / kchunk), blk(R::TX, R::TY, 1);
-  k_tile_march<R, Body><<<grd, blk, R::BYTES, st>>>(tmap, d, k0, k1, kchunk, sl, body);
+  k_tile_march<R, Body, MINB><<<grd, blk, R::BYTES, st>>>(tmap, d, k0, k1, kchunk, sl, body);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -190,6 +190,47 @@ struct Les3Body {
   }
 };
 
+// ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
+// One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
+// planes k-1..k+2: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets -1..TX+2 in i
+// (4th-order stencil of the i-face) and -1..TY+1 in j.  No redundant work: every face is computed
+// exactly once.  Faces with index 0 or m-2 along their normal (domain-end / periodic-end stencils) are
+// left to the staged FaceFlux<D> kernels, which the host runs on those thin slabs only.
+typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 5, 4, 3, 1, 1, 1, 2> RingFlux;
+struct FluxAcc {
+  TileAcc<RingFlux> T; const VfsDev &d; long p;
+  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+  template <int D> __device__ __forceinline__ long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
+  template <int D> __device__ __forceinline__ double met(int s, int side) const { return d.s[S_CSI0 + s][p + side * sn<D>()]; }
+  template <int D> __device__ __forceinline__ double iaj(int side) const { return d.s[S_IAJ][p + side * sn<D>()]; }
+  template <int D> __device__ __forceinline__ double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
+  template <int D> __device__ __forceinline__ double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
+};
+struct FluxBody {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    FluxAcc A = {T, d, p};
+    double fc[3], fv[3];
+    if (i <= d.mx - 3) {
+      face_flux_core<0, true>(d, A, i, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
+    }
+    if (j <= d.my - 3) {
+      face_flux_core<1, true>(d, A, j, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
+    }
+    if (kg <= d.mz - 3) {
+      face_flux_core<2, true>(d, A, kg, fc, fv);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
+    }
+  }
+};
+
 static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q = 0; q < n; q++) s.sid[q] = v[q]; return s; }
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};
@@ -199,6 +240,14 @@ static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, cons
   const int v[4] = {S_LM, S_MM, S_IAJ, S_NV};
   return launch_tile_march<RingLes3>(st, tmap, d, k0, k1, 64, sids(4, v), Les3Body(), L);
 }
+static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, int minb, long *L) {
+  const int v[4] = {S_U0, S_U1, S_U2, S_NV};
+  if (minb == 3) return launch_tile_march<RingFlux, FluxBody, 3>(st, tmap, d, k0, k1, 64, sids(4, v), FluxBody(), L);
+  if (minb == 4) return launch_tile_march<RingFlux, FluxBody, 4>(st, tmap, d, k0, k1, 64, sids(4, v), FluxBody(), L);
+  return launch_tile_march<RingFlux, FluxBody, 2>(st, tmap, d, k0, k1, 64, sids(4, v), FluxBody(), L);
+}
+#define VFS_FLUX_HX 4
+#define VFS_FLUX_HY 3
 #endif  // !VFS_EMU
 
 #endif

@@ -33,12 +33,13 @@ template <int S0> struct GlobalAccS {
 // 
 template <int T, class Acc> VFS_HD double dcen(const Acc &A, int a, int c, int m, int per, int lowc) {
   constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
-  // all operands are fetched unconditionally (independent loads, one memory round trip) and the
-  // stencil is chosen by selects: a load -> compare -> branch -> load chain serialises latency
+  // one-sided (u0 - um), (up - u0) or centred (up - um)/2 (k-omega.c:318-430) as (P - M) * c:
+  // operands fetched unconditionally (independent loads, one memory round trip), chosen by selects;
+  // bitwise the reference's value (one subtraction, exact scaling)
   const double up = A.u(a, ti, tj, tk), u0 = A.u(a, 0, 0, 0), um = A.u(a, -ti, -tj, -tk);
   const bool hi = A.nv(ti, tj, tk) > VFS_SOLID || (!per && c == m - 2);
-  const bool lo = A.nv(-ti, -tj, -tk) > VFS_SOLID || (!per && c == lowc);
-  return hi ? u0 - um : (lo ? up - u0 : (up - um) * 0.5);
+  const bool lo = !hi && (A.nv(-ti, -tj, -tk) > VFS_SOLID || (!per && c == lowc));
+  return ((hi ? u0 : up) - (lo ? u0 : um)) * ((hi || lo) ? 1.0 : 0.5);
 }
 
 // velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)

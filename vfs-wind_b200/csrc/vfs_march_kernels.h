@@ -95,9 +95,9 @@ template <class P> static inline int run_block_march(void *, const P &prog, cons
 // from the reference's, i.e. results agree to rounding (~1e-14 relative), not bitwise.  The weight
 // sum and sum_weight (les.c:441-468) depend on the grid and mask only and come from LesGeo.
 // The tensor algebra that follows the filters (les2_finish_geo) runs in the last phase.
-template <int TY_> struct Les2Sep {
+template <int TY_, int MINB_> struct Les2Sep {
   static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15, NPH = 3, LEAD = 0;
-  static constexpr int MINB = TY <= 8 ? 2 : 1;     // resident blocks per SM the launch bounds ask for
+  static constexpr int MINB = MINB_;               // resident blocks per SM the launch bounds ask for
   static constexpr bool SYNC_AFTER_LAST = false;   // phase 0 of the next step does not touch what phase 2 reads
   static constexpr long SMEM_D = 2L * NV * NT;
   struct State { double v[NV]; };
@@ -115,17 +115,6 @@ template <int TY_> struct Les2Sep {
       for (int a = 0; a < NV; a++) K[a] = 0;
       if (i <= d.mx - 1 && j <= d.my - 1) {
         const long p = d.idx(i, j, k);
-        {   // the planes the NEXT step touches first: raw products at k+2, finish operands at k+1 (UF also k+2)
-          const long n2 = p + 2 * d.sk, n1 = p + d.sk;
-          VFS_PREFETCH_L2(d.s[S_LW] + n2);
-#pragma unroll
-          for (int a = 0; a < 3; a++) { VFS_PREFETCH_L2(d.s[S_U0 + a] + n2); VFS_PREFETCH_L2(d.s[S_LU0 + a] + n2); VFS_PREFETCH_L2(d.s[S_UF0 + a] + n2); }
-#pragma unroll
-          for (int a = 0; a < 6; a++) { VFS_PREFETCH_L2(d.s[S_LSS0 + a] + n2); VFS_PREFETCH_L2(d.s[S_LG0 + a] + n1); }
-#pragma unroll
-          for (int a = 0; a < 10; a++) VFS_PREFETCH_L2(d.s[S_CSI0 + a] + n1);
-          VFS_PREFETCH_L2(d.s[S_LFINV] + n1); VFS_PREFETCH_L2(d.s[S_LTF2] + n1); VFS_PREFETCH_L2(d.s[S_LF2] + n1);
-        }
 #pragma unroll
         for (int dk = -1; dk <= 1; dk++) {
           const long n = p + dk * d.sk;
@@ -187,7 +176,7 @@ struct RhsMarch {
   static constexpr int NXP = TX + 4, NYP = TY + 3, NN = NXP * NYP;
   static constexpr int TILE_D = ((NN * 8 + 127) / 128) * 16, NSC = 4, PLANE_D = NSC * TILE_D, STAGES = 5;
   static constexpr int MXP = TX + 1, MYP = TY + 1, MT_D = ((MXP * MYP + 15) / 16) * 16, NM = 11;
-  static constexpr int OFF_M = STAGES * PLANE_D, OFF_F1 = OFF_M + NM * MT_D, OFF_F2 = OFF_F1 + 6 * NT, OFF_FP = OFF_F2 + 6 * NT, OFF_BAR = OFF_FP + 3 * NT;
+  static constexpr int OFF_M = STAGES * PLANE_D, OFF_F1 = OFF_M + NM * MT_D, OFF_F2 = OFF_F1 + 6 * NT, OFF_FP = OFF_F2 + 6 * NT, OFF_BAR = OFF_FP + 2 * NT;
   static constexpr long SMEM_D = OFF_BAR + 8;
   static constexpr int OX = TX - 4, OY = TY - 4;      // outputs per tile
   struct State { double c3[3][3], v3[2][3], cn[3], vn[3], fp[3], zdot, ajz; };
@@ -215,7 +204,7 @@ struct RhsMarch {
     VFS_HD double u(int a, int di, int dj, int dk) const { return V.u(a, di, dj, dk); }
     VFS_HD double nv(int di, int dj, int dk) const { return V.nv(di, dj, dk); }
     template <int D> VFS_HD double met(int s, int side) const { return m[s * MT_D + side * nb]; }
-    template <int D> VFS_HD double aj(int side) const { return m[9 * MT_D + side * nb]; }
+    template <int D> VFS_HD double iaj(int side) const { return m[9 * MT_D + side * nb]; }
     template <int D> VFS_HD double nut(int side) const { return m[10 * MT_D + side * nb]; }
     template <int D> VFS_HD double uc(int) const { return ucv; }
   };
@@ -224,7 +213,7 @@ struct RhsMarch {
     VFS_HD double u(int a, int di, int dj, int dk) const { return V.u(a, di, dj, dk); }
     VFS_HD double nv(int di, int dj, int dk) const { return V.nv(di, dj, dk); }
     template <int D> VFS_HD double met(int s, int side) const { return side ? m1[s] : m0[s]; }
-    template <int D> VFS_HD double aj(int side) const { return side ? m1[9] : m0[9]; }
+    template <int D> VFS_HD double iaj(int side) const { return side ? m1[9] : m0[9]; }
     template <int D> VFS_HD double nut(int side) const { return side ? m1[10] : m0[10]; }
     template <int D> VFS_HD double uc(int) const { return ucv; }
   };
@@ -238,13 +227,14 @@ struct RhsMarch {
     const bool inb = ii < d.mx + VFS_G && jj < d.my + VFS_G;
     const long n = inb ? d.idx(ii, jj, q) : d.idx(0, 0, q);
 #pragma unroll
-    for (int s = 0; s < 10; s++) sM[s * MT_D + slot] = d.s[S_CSI0 + s][n];
+    for (int s = 0; s < 9; s++) sM[s * MT_D + slot] = d.s[S_CSI0 + s][n];
+    sM[9 * MT_D + slot] = d.s[S_IAJ][n];
     sM[10 * MT_D + slot] = d.s[S_NUT][n];
   }
   // phase 0: centre metrics, aj, nu_t of plane q -> exchange buffer (tile + one extra column and row)
   VFS_HD void phase0(int tid, int bx, int by, int q, int ka, double *sm) const {
-    if (q < ka) return;
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (q < ka) return;
     double *sM = sm + OFF_M;
     load_met(sM, ty * MXP + tx, i, j, q);
     if (tx == TX - 1) load_met(sM, ty * MXP + TX, i + 1, j, q);
@@ -291,7 +281,8 @@ struct RhsMarch {
     AccReg A;
     A.V = view(sm, tx, ty, q + 1, ka - 3, -1, 2);
 #pragma unroll
-    for (int s = 0; s < 10; s++) { A.m0[s] = d.s[S_CSI0 + s][p]; A.m1[s] = d.s[S_CSI0 + s][p + d.sk]; }
+    for (int s = 0; s < 9; s++) { A.m0[s] = d.s[S_CSI0 + s][p]; A.m1[s] = d.s[S_CSI0 + s][p + d.sk]; }
+    A.m0[9] = d.s[S_IAJ][p]; A.m1[9] = d.s[S_IAJ][p + d.sk];
     A.m0[10] = d.s[S_NUT][p]; A.m1[10] = d.s[S_NUT][p + d.sk];
     A.ucv = d.s[S_UC2][p];
     face_flux_core<2, true>(d, A, 0, st.cn, st.vn);
@@ -318,47 +309,46 @@ struct RhsMarch {
           div4 += c3 ? (st.c3[2][a] - st.c3[1][a]) * 1. : (st.cn[a] - st.c3[0][a]) * (1. / 3.);
           fp = (9. / 8.) * div + (-1. / 8.) * div4 + vis;
         } else fp = div + vis;
-        st.fp[a] = fp; sFp[a * NT + tid] = fp;
+        st.fp[a] = fp;
       }
+      // own half of the projection (momentum.c:1733-1735): 0.5 * (metric . Fp); x and y halves are exchanged
+      const double *m = sm + OFF_M + ty * MXP + tx;
+      const double f0 = st.fp[0], f1 = st.fp[1], f2 = st.fp[2];
+      st.fp[0] = 0.5 * (m[0] * f0 + m[MT_D] * f1 + m[2 * MT_D] * f2);
+      st.fp[1] = 0.5 * (m[3 * MT_D] * f0 + m[4 * MT_D] * f1 + m[5 * MT_D] * f2);
+      st.fp[2] = 0.5 * (m[6 * MT_D] * f0 + m[7 * MT_D] * f1 + m[8 * MT_D] * f2);
+      sFp[tid] = st.fp[0]; sFp[NT + tid] = st.fp[1];
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) { st.c3[0][a] = st.c3[1][a]; st.c3[1][a] = st.c3[2][a]; st.c3[2][a] = st.cn[a]; st.v3[0][a] = st.v3[1][a]; st.v3[1][a] = st.vn[a]; }
   }
-  VFS_HD void emit(int a, long p, bool masked, double r) const {
-    if (mode == 0) d.s[s0 + a][p] = masked ? 0. : d.s[s0 + a][p] + scale * r;
-    else d.s[S_R0 + a][p] = snes_assemble(d, a, p, masked, r);
-  }
-  // phase 3: projection (momentum.c:1733-1735), masks (:1833-1841) and assembly: x,y of plane q, z of plane q-1
+  // phase 3: projection, masks (momentum.c:1833-1841) and assembly: x,y of plane q, z of plane q-1
   VFS_HD void phase3(State &st, int tid, int bx, int by, int q, int ka, int kb, const double *sm) const {
     if (q < ka) return;
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     if (!(tx >= 2 && tx <= TX - 3 && ty >= 2 && ty <= TY - 3 && i < R.i1 && j < R.j1)) return;
+    const long p = d.idx(i, j, q);
+    const bool exy = q < kb, ez = q > ka;
+    // all global operands first (independent loads), arithmetic and stores afterwards
+    SnesIn in0, in1, in2; double old0 = 0, old1 = 0, old2 = 0;
+    in0.uc = in0.uco = in0.ucm = in0.ro = in0.dp = in0.fe = 0; in1 = in0; in2 = in0;
+    if (mode == 0) { if (exy) { old0 = d.s[s0][p]; old1 = d.s[s0 + 1][p]; } if (ez) old2 = d.s[s0 + 2][p - d.sk]; }
+    else { if (exy) { in0 = snes_inputs(d, 0, p); in1 = snes_inputs(d, 1, p); } if (ez) in2 = snes_inputs(d, 2, p - d.sk); }
     const RingView V = view(sm, tx, ty, q, ka - 3, -1, 1);
     const double *m = sm + OFF_M + ty * MXP + tx, *sFp = sm + OFF_FP + tid;
-    const double f0 = st.fp[0], f1 = st.fp[1], f2 = st.fp[2];
-    const double aj = m[9 * MT_D], nv0 = V.nv(0, 0, 0);
-    const long p = d.idx(i, j, q);
-    if (q < kb) {
-      {
-        const double iaj = 2. / (1. / aj + 1. / m[9 * MT_D + 1]);
-        const double r = (0.5 * (m[0] * f0 + m[MT_D] * f1 + m[2 * MT_D] * f2) +
-                          0.5 * (m[1] * sFp[1] + m[MT_D + 1] * sFp[NT + 1] + m[2 * MT_D + 1] * sFp[2 * NT + 1])) * iaj;
-        emit(0, p, nv0 + V.nv(1, 0, 0) > 0.1, r);
-      }
-      {
-        const double jaj = 2. / (1. / aj + 1. / m[9 * MT_D + MXP]);
-        const double r = (0.5 * (m[3 * MT_D] * f0 + m[4 * MT_D] * f1 + m[5 * MT_D] * f2) +
-                          0.5 * (m[3 * MT_D + MXP] * sFp[TX] + m[4 * MT_D + MXP] * sFp[NT + TX] + m[5 * MT_D + MXP] * sFp[2 * NT + TX])) * jaj;
-        emit(1, p, nv0 + V.nv(0, 1, 0) > 0.1, r);
-      }
+    const double ia = m[9 * MT_D], nv0 = V.nv(0, 0, 0);
+    const double r0 = (st.fp[0] + sFp[1]) * (2. / (ia + m[9 * MT_D + 1]));
+    const double r1 = (st.fp[1] + sFp[NT + TX]) * (2. / (ia + m[9 * MT_D + MXP]));
+    const double r2 = (st.zdot + st.fp[2]) * (2. / (st.ajz + ia));
+    const bool k0 = nv0 + V.nv(1, 0, 0) > 0.1, k1 = nv0 + V.nv(0, 1, 0) > 0.1, k2 = V.nv(0, 0, -1) + nv0 > 0.1;
+    st.zdot = st.fp[2]; st.ajz = ia;
+    if (mode == 0) {
+      if (exy) { d.s[s0][p] = k0 ? 0. : old0 + scale * r0; d.s[s0 + 1][p] = k1 ? 0. : old1 + scale * r1; }
+      if (ez) d.s[s0 + 2][p - d.sk] = k2 ? 0. : old2 + scale * r2;
+    } else {
+      if (exy) { d.s[S_R0][p] = snes_combine(d, in0, k0, r0); d.s[S_R1][p] = snes_combine(d, in1, k1, r1); }
+      if (ez) d.s[S_R2][p - d.sk] = snes_combine(d, in2, k2, r2);
     }
-    const double zd = 0.5 * (m[6 * MT_D] * f0 + m[7 * MT_D] * f1 + m[8 * MT_D] * f2);
-    if (q > ka) {
-      const double kaj = 2. / (1. / st.ajz + 1. / aj);
-      const double r = (st.zdot + zd) * kaj;
-      emit(2, p - d.sk, V.nv(0, 0, -1) + nv0 > 0.1, r);
-    }
-    st.zdot = zd; st.ajz = aj;
   }
 };
 

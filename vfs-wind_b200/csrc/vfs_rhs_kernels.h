@@ -13,7 +13,7 @@
 #define VFS_SOLID 0.1
 
 // Accessor over the global padded arrays: offsets (di,dj,dk) are relative to the face's node p;
-// met/aj/nut/uc give the centre metrics (scalar S_CSI0+s), aj, nu_t at p (side 0) or p + e_D
+// met/iaj/nut/uc give the centre metrics (scalar S_CSI0+s), 1/aj, nu_t at p (side 0) or p + e_D
 // (side 1) and the contravariant flux component D at p + off*e_D.  The marching kernels
 // (vfs_march_kernels.h) supply accessors with the same interface over TMA-staged shared-memory
 // planes and exchange buffers, so every form runs the identical arithmetic below.
@@ -23,7 +23,7 @@ struct GlobalAcc {
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
   template <int D> VFS_HD long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
   template <int D> VFS_HD double met(int s, int side) const { return d.s[S_CSI0 + s][p + side * sn<D>()]; }
-  template <int D> VFS_HD double aj(int side) const { return d.s[S_AJ][p + side * sn<D>()]; }
+  template <int D> VFS_HD double iaj(int side) const { return d.s[S_IAJ][p + side * sn<D>()]; }
   template <int D> VFS_HD double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
   template <int D> VFS_HD double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
 };
@@ -33,13 +33,19 @@ struct GlobalAcc {
 template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a) {
   constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);      // pn = p + n
   constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
-  // operands fetched unconditionally, stencil chosen by selects (see dcen in vfs_les_kernels.h)
-  const double a0 = A.u(a, 0, 0, 0), an = A.u(a, ni, nj, nk);
-  const double p0 = A.u(a, ti, tj, tk), pn = A.u(a, ni + ti, nj + tj, nk + tk);
-  const double m0 = A.u(a, -ti, -tj, -tk), mn = A.u(a, ni - ti, nj - tj, nk - tk);
+  // The reference picks one of three stencils (k-omega.c:56-311):
+  //   row +t solid : (u_n + u_0 - u_{n-t} - u_{-t}) / 2
+  //   row -t solid : (u_{n+t} + u_t - u_n - u_0) / 2
+  //   otherwise    : (u_{n+t} + u_t - u_{n-t} - u_{-t}) / 4
+  // i.e. (P - M) * c with P, M pair sums chosen by two predicates.  All operands are fetched
+  // unconditionally (independent loads, one memory round trip) and chosen by selects; pair sums
+  // re-associate the reference's left-to-right sum (rounding-level difference, ~1e-16 relative).
+  const double s0 = A.u(a, ni, nj, nk) + A.u(a, 0, 0, 0);
+  const double sp = A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk);
+  const double sm = A.u(a, ni - ti, nj - tj, nk - tk) + A.u(a, -ti, -tj, -tk);
   const bool hi = A.nv(ti, tj, tk) > VFS_SOLID || A.nv(ni + ti, nj + tj, nk + tk) > VFS_SOLID;
-  const bool lo = A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID;
-  return hi ? (an + a0 - mn - m0) * 0.5 : (lo ? (pn + p0 - an - a0) * 0.5 : (pn + p0 - mn - m0) * 0.25);
+  const bool lo = !hi && (A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID);
+  return ((hi ? s0 : sp) - (lo ? s0 : sm)) * ((hi || lo) ? 0.5 : 0.25);
 }
 
 // One face of family D (0/1/2 = i-/j-/k-face) between node p and p + e_D, stored at p ("upper
@@ -58,7 +64,8 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], d
                        0.5 * A.template met<D>(s0 + 2, 0) + 0.5 * A.template met<D>(s0 + 2, 1))
   const V3 cs = VFS_F3(0), et = VFS_F3(3), ze = VFS_F3(6);
 #undef VFS_F3
-  const double ajc = 2. / (1. / A.template aj<D>(0) + 1. / A.template aj<D>(1));
+  // 2/(1/aj_p + 1/aj_n) with the stored 1/aj (S_IAJ = 1./aj, the same correctly-rounded quotient): 1 division, not 3
+  const double ajc = 2. / (A.template iaj<D>(0) + A.template iaj<D>(1));
   const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
 
   // du[a][b] = d u_a / d xi_b  (b: csi, eta, zet)
@@ -204,23 +211,23 @@ struct FpCell {
 // three contravariant components (before scale and masks)
 VFS_HD V3 project_fp(const VfsDev &d, long p) {
   const double f0 = d.s[S_FP0][p], f1 = d.s[S_FP1][p], f2 = d.s[S_FP2][p];
-  const double aj = d.s[S_AJ][p];
+  const double ia = d.s[S_IAJ][p];          // 1/aj; face Jacobian = 2/(1/aj_p + 1/aj_q)
   V3 r;
   {
     long q = p + 1;
-    double iaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    double iaj = 2. / (ia + d.s[S_IAJ][q]);
     r.x = (0.5 * (d.s[S_CSI0][p] * f0 + d.s[S_CSI1][p] * f1 + d.s[S_CSI2][p] * f2) +
            0.5 * (d.s[S_CSI0][q] * d.s[S_FP0][q] + d.s[S_CSI1][q] * d.s[S_FP1][q] + d.s[S_CSI2][q] * d.s[S_FP2][q])) * iaj;
   }
   {
     long q = p + d.sj;
-    double jaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    double jaj = 2. / (ia + d.s[S_IAJ][q]);
     r.y = (0.5 * (d.s[S_ETA0][p] * f0 + d.s[S_ETA1][p] * f1 + d.s[S_ETA2][p] * f2) +
            0.5 * (d.s[S_ETA0][q] * d.s[S_FP0][q] + d.s[S_ETA1][q] * d.s[S_FP1][q] + d.s[S_ETA2][q] * d.s[S_FP2][q])) * jaj;
   }
   {
     long q = p + d.sk;
-    double kaj = 2. / (1. / aj + 1. / d.s[S_AJ][q]);
+    double kaj = 2. / (ia + d.s[S_IAJ][q]);
     r.z = (0.5 * (d.s[S_ZET0][p] * f0 + d.s[S_ZET1][p] * f1 + d.s[S_ZET2][p] * f2) +
            0.5 * (d.s[S_ZET0][q] * d.s[S_FP0][q] + d.s[S_ZET1][q] * d.s[S_FP1][q] + d.s[S_ZET2][q] * d.s[S_FP2][q])) * kaj;
   }
@@ -258,25 +265,35 @@ struct ProjectAdd {
 //   Rhs = mask( (-U + U_o)/dt + 0.5 R(U) ) + 0.5 RHS_o - dP [+ F_eul]        (time_coeff()==1)
 //   Rhs = mask( (-1.5U + 2U_o - 0.5U_rm1)/dt + R(U) ) - dP [+ F_eul]         (BDF2)
 // mask() = the Formfunction_2 zeroing, applied before the last three terms.
-VFS_HD double snes_assemble(const VfsDev &d, int a, long p, bool masked, double r) {
+// inputs of the assembly for component a at node p, fetched together so the loads overlap
+struct SnesIn { double uc, uco, ucm, ro, dp, fe; };
+VFS_HD SnesIn snes_inputs(const VfsDev &d, int a, long p) {
+  SnesIn v;
+  v.uc = d.s[S_UC0 + a][p]; v.uco = d.s[S_UCO0 + a][p]; v.dp = d.s[S_DP0 + a][p];
+  v.ucm = d.bdf2 ? d.s[S_UCM0 + a][p] : 0.; v.ro = d.bdf2 ? 0. : d.s[S_RO0 + a][p];
+  v.fe = d.has_feul ? d.s[S_FE0 + a][p] : 0.;
+  return v;
+}
+VFS_HD double snes_combine(const VfsDev &d, const SnesIn &in, bool masked, double r) {
   const double dt = d.dt;
   double v;
   if (masked) v = 0.;
   else if (!d.bdf2) {
-    v = (-1. / dt) * d.s[S_UC0 + a][p];
-    v += (1. / dt) * d.s[S_UCO0 + a][p];
+    v = (-1. / dt) * in.uc;
+    v += (1. / dt) * in.uco;
     v += 0.5 * r;
   } else {
-    v = (-1.5 / dt) * d.s[S_UC0 + a][p];
-    v += (2. / dt) * d.s[S_UCO0 + a][p];
-    v += (-0.5 / dt) * d.s[S_UCM0 + a][p];
+    v = (-1.5 / dt) * in.uc;
+    v += (2. / dt) * in.uco;
+    v += (-0.5 / dt) * in.ucm;
     v += 1.0 * r;
   }
-  if (!d.bdf2) v += 0.5 * d.s[S_RO0 + a][p];
-  v += -1. * d.s[S_DP0 + a][p];
-  if (d.has_feul) v += 1. * d.s[S_FE0 + a][p];
+  if (!d.bdf2) v += 0.5 * in.ro;
+  v += -1. * in.dp;
+  if (d.has_feul) v += 1. * in.fe;
   return v;
 }
+VFS_HD double snes_assemble(const VfsDev &d, int a, long p, bool masked, double r) { return snes_combine(d, snes_inputs(d, a, p), masked, r); }
 struct ProjectSNES {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
