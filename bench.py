@@ -102,7 +102,11 @@ def build_case_on_device(pkg, cfg, rank, nranks, device, halo=None):
     kofs, nzl = capi.slab_partition(mz, nranks)[rank]
     p = capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], kofs=kofs, nzl=nzl, rank=rank, nranks=nranks, device=device)
     ctx = capi.VfsContext(p)
-    if halo is not None:
+    if halo == "nccl":
+        import torch
+        import torch.distributed as dist
+        ctx.nccl_init(dist, device=torch.device("cuda", device))
+    elif halo is not None:
         halo.attach(ctx)
     # grid: the slab's node planes of the global grid (coordinates depend on global indices only)
     sub = dict(cfg)
@@ -136,8 +140,9 @@ def run_ours(args):
     pkg.capi.load()
     cfg = workload_cfg(pkg.cases, args.workload, world)
     halo = None
-    if world > 1:
-        halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank))
+    if world > 1:       # in-library NCCL k-halo layer (VFS_HALO=torch: the torch.distributed callback instead)
+        halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank)) \
+            if os.environ.get("VFS_HALO") == "torch" else "nccl"
     ctx, f, (mx, my, mz, kofs, nzl) = build_case_on_device(pkg, cfg, rank, world, lrank, halo)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -155,9 +160,9 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident metric ("value") ----
-    # single rank: the ~100-launch step is replayed as a CUDA graph (1st warm-up step eager,
-    # 2nd captured); multi rank: eager, the halo callback is host code
-    use_graph = (world == 1) and not args.no_graph
+    # the ~100-launch step is replayed as a CUDA graph (1st warm-up step eager, 2nd captured); the
+    # in-library NCCL halo exchanges are captured with it
+    use_graph = (world == 1 or halo == "nccl") and not args.no_graph
     ctx.set_option(1, 1 if use_graph else 0)
     for _ in range(max(args.warmup, 3)):
         ctx.rhs_les_fused()

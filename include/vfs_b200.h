@@ -87,6 +87,15 @@ const char *vfs_last_error(vfs_ctx *c);          /* c may be NULL: last create()
 int vfs_set_params(vfs_ctx *c, const vfs_params *p); /* update run-time switches (ti, dt, ...) */
 int vfs_set_stream(vfs_ctx *c, void *cuda_stream);   /* run on a caller stream (cudaStream_t) */
 int vfs_set_halo_callback(vfs_ctx *c, vfs_halo_fn fn, void *user);
+/* In-library halo layer (the default on GPUs): NCCL point-to-point between k-neighbours, issued on the
+ * context's stream straight from / into the padded arrays (replaces DAGlobalToLocal/DALocalToLocal
+ * between ranks, init.c:131-160).  Rank 0 obtains a 128-byte ncclUniqueId with vfs_nccl_unique_id and
+ * distributes it by any means (MPI_Bcast in the reference's host code, torch.distributed in bench.py);
+ * every rank then calls vfs_nccl_init (collective).  When set, it takes precedence over the callback. */
+int vfs_nccl_unique_id(char *out128);
+int vfs_nccl_init(vfs_ctx *c, const char *id128);
+/* number of k-halo exchanges performed by this context (and bytes sent, if bytes != NULL) */
+long vfs_halo_count(vfs_ctx *c, long *bytes);
 int vfs_sync(vfs_ctx *c);
 
 /* layout[0..7] = G (ghost width), pitch, ny (=my+2G), nzt (=nzl+2G), plane doubles (=ny*pitch),

@@ -36,8 +36,11 @@ def main():
         kofs, nzl = capi.slab_partition(mz, world)[rank]
         p = capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], kofs=kofs, nzl=nzl, rank=rank, nranks=world, device=lrank)
         ctx = capi.VfsContext(p)
-        halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank))
-        halo.attach(ctx)
+        if os.environ.get("VFS_HALO") == "torch":      # the torch.distributed callback layer
+            halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank))
+            halo.attach(ctx)
+        else:                                           # in-library NCCL halo layer (default)
+            ctx.nccl_init(dist, device=torch.device("cuda", lrank))
         sl = slice(kofs, kofs + nzl)
         ctx.upload("COOR", xyz[sl]); ctx.FormMetrics()
         for k, n in FIELDS_IN:

@@ -20,7 +20,7 @@ FIELD_DOF = {"COOR": 3, "CSI": 3, "ETA": 3, "ZET": 3, "AJ": 1, "NVERT": 1, "UCON
              "UCONT_RM1": 3, "RHS_O": 3, "DP": 3, "F_EUL": 3, "RHS": 3, "CS": 1, "NU_T": 1, "USTAR": 1}
 
 EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs_set_stream", "vfs_set_halo_callback", "vfs_sync",
-           "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
+           "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms"]
 
@@ -51,6 +51,10 @@ def _bind(lib):
     lib.vfs_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.vfs_set_halo_callback.argtypes = [C.c_void_p, HALO_FN, C.c_void_p]
     lib.vfs_sync.argtypes = [C.c_void_p]
+    lib.vfs_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.vfs_nccl_init.argtypes = [C.c_void_p, C.c_char_p]
+    lib.vfs_halo_count.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+    lib.vfs_halo_count.restype = C.c_long
     lib.vfs_layout.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
     lib.vfs_field_scalar_id.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.vfs_scalar_ptr.argtypes = [C.c_void_p, C.c_int]
@@ -168,6 +172,26 @@ class VfsContext:
                 return 1
         self._cb = HALO_FN(tramp)
         self._ck(self.lib.vfs_set_halo_callback(self.h, self._cb, None))
+
+    def nccl_init(self, dist, device=None):
+        """Collective: set up the in-library NCCL halo layer.  `dist` is an initialised
+        torch.distributed module, used only to broadcast rank 0's 128-byte ncclUniqueId."""
+        import torch
+        buf = C.create_string_buffer(128)
+        if self.p.rank == 0:
+            r = self.lib.vfs_nccl_unique_id(buf)
+            if r:
+                raise VfsError("vfs_nccl_unique_id failed (%d): %s" % (r, self.lib.vfs_last_error(None).decode()))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0)
+        self._ck(self.lib.vfs_nccl_init(self.h, bytes(t.cpu().tolist())))
+
+    def halo_count(self):
+        b = C.c_long(0)
+        n = self.lib.vfs_halo_count(self.h, C.byref(b))
+        return int(n), int(b.value)
 
     def scalar_ptr(self, sid):
         return self.lib.vfs_scalar_ptr(self.h, sid)

@@ -19,6 +19,39 @@
 
 #ifndef VFS_EMU
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: the library is resolved at run time (dlopen), no link dependency
+// NCCL entry points used by the k-halo layer.  Resolved from the libnccl.so.2 already loaded in the
+// process (torch's bundled copy under Python) or the system one.
+struct NcclApi {
+  void *h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi &nccl_api() {
+  static NcclApi a;
+  if (a.h) return a;
+  a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!a.h) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!a.h) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+  a.Send = (decltype(a.Send))dlsym(a.h, "ncclSend");
+  a.Recv = (decltype(a.Recv))dlsym(a.h, "ncclRecv");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetErrorString;
+  return a;
+}
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(c, std::string(#call) + ": " + cudaGetErrorString(e_)); return VFS_ERR_CUDA; } } while (0)
 template <class F> __global__ void __launch_bounds__(256) k_box(F f, Box b) {
   int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,6 +87,11 @@ struct vfs_ctx {
   CUtensorMap tmap_rhs;          // same pool, box of the residual marching kernel
 #endif
   bool tma_ok = false;
+#ifndef VFS_EMU
+  ncclComm_t comm = nullptr;     // k-neighbour halo exchange inside the library (vfs_nccl_init)
+  double *hbuf = nullptr;        // packed send (hi, lo) and receive (lo, hi) staging, VFS_MAXGRP scalars each
+#endif
+  long halo_exchanges = 0, halo_bytes = 0;
   // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
   int use_graph = 0; bool capturing = false;
   int graph_calls[2] = {0, 0};
@@ -117,12 +155,69 @@ static int wrap_ij(vfs_ctx *c, const Grp &g) {
   if (d.pery) { WrapFill f = {d, g, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
   return 0;
 }
+#ifndef VFS_EMU
+// k-halo exchange with the neighbouring slabs.  The G boundary planes of every requested scalar are
+// packed into ONE message per neighbour (a few 2 MB messages per peer only reach ~70 GB/s over NVLink,
+// one 10-50 MB message is spread over all of NCCL's P2P channels), exchanged with one grouped
+// ncclSend/ncclRecv pair per neighbour on the context's stream (stream ordered, graph capturable) and
+// unpacked into the ghost planes.  With lo == hi (2 ranks, periodic k) the first send to the peer pairs
+// with the peer's first receive: [send hi, send lo, recv lo, recv hi] on both sides is consistent.
+struct HaloPtrs { double *s[VFS_MAXGRP]; };
+__global__ void k_halo_pack(HaloPtrs P, int n, long cnt, long off_hi, long off_lo, double2 *__restrict__ buf_hi, double2 *__restrict__ buf_lo) {
+  const long c2 = cnt / 2, tot = (long)n * c2;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+    const int q = (int)(t / c2); const long e = t - (long)q * c2;
+    if (buf_hi) buf_hi[t] = reinterpret_cast<const double2 *>(P.s[q] + off_hi)[e];
+    if (buf_lo) buf_lo[t] = reinterpret_cast<const double2 *>(P.s[q] + off_lo)[e];
+  }
+}
+__global__ void k_halo_unpack(HaloPtrs P, int n, long cnt, long off_hi, long off_lo, const double2 *__restrict__ buf_hi, const double2 *__restrict__ buf_lo) {
+  const long c2 = cnt / 2, tot = (long)n * c2;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+    const int q = (int)(t / c2); const long e = t - (long)q * c2;
+    if (buf_hi) reinterpret_cast<double2 *>(P.s[q] + off_hi)[e] = buf_hi[t];
+    if (buf_lo) reinterpret_cast<double2 *>(P.s[q] + off_lo)[e] = buf_lo[t];
+  }
+}
+static int nccl_halo(vfs_ctx *c, const Grp &g) {
+  NcclApi &N = nccl_api();
+  const VfsDev &d = c->d;
+  const int r = c->prm.rank, n = c->prm.nranks;
+  const int lo = r > 0 ? r - 1 : (d.perz ? n - 1 : -1), hi = r < n - 1 ? r + 1 : (d.perz ? 0 : -1);
+  const long cnt = (long)VFS_G * d.sk;                       // doubles per scalar and side (sk is a multiple of 16)
+  if (!c->hbuf) {
+    CK(cudaMalloc((void **)&c->hbuf, (size_t)4 * VFS_MAXGRP * cnt * sizeof(double)));
+  }
+  double *sb_hi = c->hbuf, *sb_lo = c->hbuf + (size_t)VFS_MAXGRP * cnt, *rb_lo = c->hbuf + (size_t)2 * VFS_MAXGRP * cnt, *rb_hi = c->hbuf + (size_t)3 * VFS_MAXGRP * cnt;
+  HaloPtrs P; for (int q = 0; q < g.n; q++) P.s[q] = c->d.s[g.sid[q]];
+  const size_t msg = (size_t)g.n * cnt;
+  const int blocks = 148 * 4;
+  k_halo_pack<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt, (long)d.nzl * d.sk, (long)VFS_G * d.sk, hi >= 0 ? (double2 *)sb_hi : nullptr, lo >= 0 ? (double2 *)sb_lo : nullptr);
+  ncclResult_t e = N.GroupStart();
+  if (hi >= 0 && e == ncclSuccess) e = N.Send(sb_hi, msg, ncclDouble, hi, c->comm, c->stream);
+  if (lo >= 0 && e == ncclSuccess) e = N.Send(sb_lo, msg, ncclDouble, lo, c->comm, c->stream);
+  if (lo >= 0 && e == ncclSuccess) e = N.Recv(rb_lo, msg, ncclDouble, lo, c->comm, c->stream);
+  if (hi >= 0 && e == ncclSuccess) e = N.Recv(rb_hi, msg, ncclDouble, hi, c->comm, c->stream);
+  ncclResult_t e2 = N.GroupEnd();
+  if (e == ncclSuccess) e = e2;
+  if (e != ncclSuccess) { set_err(c, std::string("NCCL halo exchange: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
+  k_halo_unpack<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt, (long)(d.nzl + VFS_G) * d.sk, 0L, hi >= 0 ? (const double2 *)rb_hi : nullptr, lo >= 0 ? (const double2 *)rb_lo : nullptr);
+  CK(cudaGetLastError());
+  c->halo_exchanges++; c->halo_bytes += (long)msg * 8 * ((hi >= 0) + (lo >= 0));
+  c->launches += 3;
+  return 0;
+}
+#endif
 static int halo_k(vfs_ctx *c, const Grp &g) {
   const VfsDev &d = c->d;
   if (c->prm.nranks > 1) {
-    if (!c->halo_fn) { set_err(c, "nranks > 1 but no halo callback registered"); return VFS_ERR_HALO; }
+#ifndef VFS_EMU
+    if (c->comm) return nccl_halo(c, g);
+#endif
+    if (!c->halo_fn) { set_err(c, "nranks > 1 but neither vfs_nccl_init nor a halo callback was set up"); return VFS_ERR_HALO; }
     int r = c->halo_fn(c->halo_user, g.n, g.sid);
     if (r) { set_err(c, "halo callback failed"); return VFS_ERR_HALO; }
+    c->halo_exchanges++;
     return 0;
   }
   if (d.perz) { WrapFill f = {d, g, 2}; Box b = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, 0, 2 * VFS_G}; RUN(launch(c, b, f)); }
@@ -216,6 +311,8 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
 #ifndef VFS_EMU
   cudaStreamSynchronize(c->stream);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
+  if (c->hbuf) cudaFree(c->hbuf);
   cudaFree(c->pool); cudaFree(c->stage);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -244,6 +341,36 @@ extern "C" int vfs_set_stream(vfs_ctx *c, void *s) {
   c->stream = (cudaStream_t)s; return 0;
 }
 extern "C" int vfs_set_halo_callback(vfs_ctx *c, vfs_halo_fn fn, void *user) { if (!c) return VFS_ERR_ARG; c->halo_fn = fn; c->halo_user = user; return 0; }
+extern "C" int vfs_nccl_unique_id(char *out128) {
+#ifndef VFS_EMU
+  NcclApi &N = nccl_api();
+  if (!out128) return VFS_ERR_ARG;
+  if (!N.ok) { g_create_err = "libnccl.so.2 not found"; return VFS_ERR_HALO; }
+  ncclUniqueId id;
+  if (N.GetUniqueId(&id) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return VFS_ERR_HALO; }
+  memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return 0;
+#else
+  (void)out128; return VFS_ERR_UNSUPPORTED;
+#endif
+}
+extern "C" int vfs_nccl_init(vfs_ctx *c, const char *id128) {
+#ifndef VFS_EMU
+  if (!c || !id128) return VFS_ERR_ARG;
+  NcclApi &N = nccl_api();
+  if (!N.ok) { set_err(c, "libnccl.so.2 not found"); return VFS_ERR_HALO; }
+  if (c->comm) { N.CommDestroy(c->comm); c->comm = nullptr; }
+  graph_reset(c);
+  ncclUniqueId id; memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+  CK(cudaSetDevice(c->prm.device));
+  ncclResult_t e = N.CommInitRank(&c->comm, c->prm.nranks, id, c->prm.rank);
+  if (e != ncclSuccess) { c->comm = nullptr; set_err(c, std::string("ncclCommInitRank: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
+  return 0;
+#else
+  (void)c; (void)id128; return VFS_ERR_UNSUPPORTED;
+#endif
+}
+extern "C" long vfs_halo_count(vfs_ctx *c, long *bytes) { if (!c) return 0; if (bytes) *bytes = c->halo_bytes; return c->halo_exchanges; }
 extern "C" int vfs_sync(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
 #ifndef VFS_EMU
@@ -288,7 +415,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
 // baked into the graph, so every parameter/stream/option change resets it.
 template <class F> static int run_graphed(vfs_ctx *c, int key, F body) {
 #ifndef VFS_EMU
-  if (c->use_graph && c->prm.nranks == 1) {
+  if (c->use_graph && (c->prm.nranks == 1 || c->comm)) {
     if (c->gexec[key]) { CK(cudaGraphLaunch(c->gexec[key], c->stream)); return 0; }
     if (c->graph_calls[key]++ >= 1) {
       cudaGraph_t g = 0;
@@ -523,7 +650,10 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   ev_rec(c, 2 * VFS_T_FLUX + 1);
   ev_rec(c, 2 * VFS_T_FP);
   Grp gf = grp(S_FC1, 18);
-  RUN(g2l(c, gf));                                                    // momentum.c:1458-1496
+  // momentum.c:1458-1496.  Between ranks only the k-face family is exchanged: FpCell reads the i- and
+  // j-face fluxes on the cell's own k plane only, so their k ghosts are never consumed.
+  RUN(wrap_ij(c, gf));
+  RUN(halo_k(c, c->prm.nranks > 1 ? grp_cat(grp(S_FC3, 3), grp(S_FV3, 3)) : gf));
   if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
   for (int n = 0; n < S.n; n++) { FpCell f = {d}; RUN(launch(c, S.fp[n], f)); }   // momentum.c:1548-1678
   ev_rec(c, 2 * VFS_T_FP + 1);
