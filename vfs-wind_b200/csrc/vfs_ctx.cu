@@ -85,6 +85,7 @@ struct vfs_ctx {
   CUtensorMap tmap;              // 4-D map over the scalar pool, box (TX+2, TY+2, 1, 1)
   CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
   CUtensorMap tmap_rhs;          // same pool, box of the residual marching kernel
+  CUtensorMap tmap_les2;         // same pool, box (32, 16): operand tiles of the LES pass-2 marching kernel
 #endif
   bool tma_ok = false;
 #ifndef VFS_EMU
@@ -101,7 +102,6 @@ struct vfs_ctx {
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
-  int les2_ty = 16;              // tile height of the LES pass-2 marching kernel (option key 2: 8 or 16)
   bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
 };
 
@@ -301,7 +301,8 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
 #ifndef VFS_EMU
   c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
               vfs_make_tensor_map(&c->tmap_flux, c->pool, c->d, c->scalar_len, VFS_TILE_TX + VFS_FLUX_HX, VFS_TILE_TY + VFS_FLUX_HY) == 0 &&
-              vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0;
+              vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY) == 0;
 #endif
   *out = c;
   return 0;
@@ -405,7 +406,6 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   if (!c) return VFS_ERR_ARG;
   if (key == 0) c->fused = value;
   else if (key == 1) c->use_graph = value;
-  else if (key == 2) c->les2_ty = value;
   else if (key == 3) c->flux_minb = value;
   graph_reset(c);
   return 0;
@@ -730,6 +730,13 @@ static int zero_scalars(vfs_ctx *c, int s0, int n) {
 #endif
   return 0;
 }
+static bool les2_march_ok(const vfs_ctx *c) {
+#ifndef VFS_EMU
+  return c->tma_ok;
+#else
+  (void)c; return true;
+#endif
+}
 static int les_cs(vfs_ctx *c) {
   const VfsDev &d = c->d;
   Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
@@ -754,16 +761,15 @@ static int les_cs(vfs_ctx *c) {
   // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
   if (any_per(c)) RUN(node_copy(c, grp_cat(grp(S_UF0, 3), grp(S_LU0, 9))));   // les.c:275-306
   ev_rec(c, 2 * VFS_T_LES2);
-  if (c->fused && !d.testfilter_ik) {
+  if (c->fused && !d.testfilter_ik && les2_march_ok(c)) {
     Box bi = box_interior(c);
     if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
-    int r;
-#define VFS_LES2_RUN(TY, MB) { Les2Sep<TY, MB> prog = {d}; r = run_block_march(c->stream, prog, les2_sep_grid<Les2Sep<TY, MB>>(d, bi.k0, bi.k1), &c->launches); }
-    if (c->les2_ty == 8) VFS_LES2_RUN(8, 2)
-    else if (c->les2_ty == 83) VFS_LES2_RUN(8, 3)
-    else if (c->les2_ty == 84) VFS_LES2_RUN(8, 4)
-    else VFS_LES2_RUN(16, 1)
-#undef VFS_LES2_RUN
+    Les2March prog = {d};
+#ifndef VFS_EMU
+    int r = run_les2_march(c->stream, c->tmap_les2, prog, bi.k0, bi.k1, &c->launches);
+#else
+    int r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches);
+#endif
     if (r) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }

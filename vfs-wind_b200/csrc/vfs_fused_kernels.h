@@ -157,15 +157,18 @@ static inline int launch_tile_march(cudaStream_t st, const CUtensorMap &tmap, co
 // ---- LES pass 1 (les.c:199-246): staged ucat(3), aj, nvert; 27-point box ------------------------------
 typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 5, 4, 2, 2, 1, 1, 1, 1> RingLes1;
 struct Les1Acc {
-  TileAcc<RingLes1> T;
+  TileAcc<RingLes1> T; const VfsDev &d; long p;
+  __device__ __forceinline__ double met(int s) const { return d.s[S_CSI0 + s][p]; }
+  __device__ __forceinline__ double aj() const { return d.s[S_AJ][p]; }
   __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
   __device__ __forceinline__ double iaj(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(4, di, dj, dk); }
 };
 struct Les1Body {
   __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k) const {
-    Les1Acc A = {T};
-    les1_core(d, A, i, j, k + d.kofs, d.idx(i, j, k));
+    const long p = d.idx(i, j, k);
+    Les1Acc A = {T, d, p};
+    les1_core(d, A, i, j, k + d.kofs, p);
   }
 };
 

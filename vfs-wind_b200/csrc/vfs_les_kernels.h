@@ -27,6 +27,10 @@ template <int S0> struct GlobalAccS {
   VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S0 + a][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double iaj(int di, int dj, int dk) const { return d.s[S_IAJ][p + di + dj * d.sj + dk * d.sk]; }
+  // the cell's own centre metrics (s = 0..8: csi, eta, zet), aj, and LES grid factors (q = 0..8: S_LFINV..S_LG5)
+  VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
+  VFS_HD double aj() const { return d.s[S_AJ][p]; }
+  VFS_HD double geo(int q) const { return d.s[S_LFINV + q][p]; }
 };
 
 // centre difference of component a along direction T (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
@@ -43,11 +47,11 @@ template <int T, class Acc> VFS_HD double dcen(const Acc &A, int a, int c, int m
 }
 
 // velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)
-template <class Acc> VFS_HD void grad_center_a(const VfsDev &d, const Acc &A, int i, int j, int kg, long p, double g[3][3]) {
-  const double ajc = d.s[S_AJ][p];
-  const double c0 = d.s[S_CSI0][p], c1 = d.s[S_CSI1][p], c2 = d.s[S_CSI2][p];
-  const double e0 = d.s[S_ETA0][p], e1 = d.s[S_ETA1][p], e2 = d.s[S_ETA2][p];
-  const double z0 = d.s[S_ZET0][p], z1 = d.s[S_ZET1][p], z2 = d.s[S_ZET2][p];
+template <class Acc> VFS_HD void grad_center_a(const VfsDev &d, const Acc &A, int i, int j, int kg, long, double g[3][3]) {
+  const double ajc = A.aj();
+  const double c0 = A.met(0), c1 = A.met(1), c2 = A.met(2);
+  const double e0 = A.met(3), e1 = A.met(4), e2 = A.met(5);
+  const double z0 = A.met(6), z1 = A.met(7), z2 = A.met(8);
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     const double dc = dcen<0>(A, a, i, d.mx, d.perx, 1);
@@ -268,15 +272,15 @@ struct LesGeo {
 // and the precomputed factors above.  M^c is symmetric (S, S^ are), and the two triple sums
 // LM = L_ba M_aq G_bq, MM = M_nm M_nl G_ml are evaluated as (L M):G and (M^T M):G — 63 multiply-adds
 // instead of 162; the result differs from the literal triple loops by rounding only.
-VFS_HD void les2_finish_geo(const VfsDev &d, int i, int j, int kg, long p, const double *f) {
-  const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
-  const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
-  const double zet[3] = {d.s[S_ZET0][p], d.s[S_ZET1][p], d.s[S_ZET2][p]};
-  const double finv = d.s[S_LFINV][p], tf2 = d.s[S_LTF2][p], f2 = d.s[S_LF2][p];
-  const double _u[3] = {d.s[S_UF0][p], d.s[S_UF1][p], d.s[S_UF2][p]};
+template <class Ops> VFS_HD void les2_finish_geo(const VfsDev &d, const Ops &O, int i, int j, int kg, long p, const double *f) {
+  const double csi[3] = {O.met(0), O.met(1), O.met(2)};
+  const double eta[3] = {O.met(3), O.met(4), O.met(5)};
+  const double zet[3] = {O.met(6), O.met(7), O.met(8)};
+  const double finv = O.geo(0), tf2 = O.geo(1), f2 = O.geo(2);
+  const double _u[3] = {O.u(0, 0, 0, 0), O.u(1, 0, 0, 0), O.u(2, 0, 0, 0)};
   const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
   double gh[3][3];
-  grad_center(d, S_UF0, i, j, kg, p, gh);
+  grad_center_a(d, O, i, j, kg, p, gh);
   const double S_hat = sabs_of(gh);
   const double tS = -tf2 * S_hat;
   // symmetric M^c: xx, xy, xz, yy, yz, zz
@@ -293,7 +297,8 @@ VFS_HD void les2_finish_geo(const VfsDev &d, int i, int j, int kg, long p, const
 #pragma unroll
     for (int b = 0; b < 3; b++) L[a][b] = f[3 * a + b] * finv - _U[a] * _u[b];
   }
-  const double G[3][3] = {{d.s[S_LG0][p], d.s[S_LG3][p], d.s[S_LG4][p]}, {d.s[S_LG3][p], d.s[S_LG1][p], d.s[S_LG5][p]}, {d.s[S_LG4][p], d.s[S_LG5][p], d.s[S_LG2][p]}};
+  const double g0 = O.geo(3), g1 = O.geo(4), g2 = O.geo(5), g3 = O.geo(6), g4 = O.geo(7), g5 = O.geo(8);
+  const double G[3][3] = {{g0, g3, g4}, {g3, g1, g5}, {g4, g5, g2}};
   double num = 0, den = 0;
 #pragma unroll
   for (int b = 0; b < 3; b++)

@@ -31,60 +31,6 @@ static inline int pick_kchunk(int ntiles, int nk, int min_chunk, int nsm = 148) 
   return best < 1 ? 1 : best;
 }
 
-#ifndef VFS_EMU
-template <class P, int PH> struct PhaseSeq {
-  static __device__ __forceinline__ void run(const P &prog, typename P::State &st, int tid, int bx, int by, int k, double *sm) {
-    prog.template phase<PH>(st, tid, bx, by, k, sm);
-    if (PH + 1 < P::NPH || P::SYNC_AFTER_LAST) __syncthreads();
-    if constexpr (PH + 1 < P::NPH) PhaseSeq<P, PH + 1>::run(prog, st, tid, bx, by, k, sm);
-  }
-};
-template <class P> __global__ void __launch_bounds__(P::NT, P::MINB) k_block_march(const P prog, int kbeg, int kend, int kchunk) {
-  extern __shared__ __align__(16) double vfs_march_sm[];
-  const int tid = threadIdx.x;
-  const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
-  if (ka >= kb) return;
-  typename P::State st;
-  prog.begin(st, tid, blockIdx.x, blockIdx.y, ka, kb, vfs_march_sm);
-  for (int k = ka - P::LEAD; k < kb; k++) PhaseSeq<P, 0>::run(prog, st, tid, blockIdx.x, blockIdx.y, k, vfs_march_sm);
-}
-template <class P> static inline int run_block_march(cudaStream_t st, const P &prog, const MarchGrid &g, long *launches) {
-  if (g.kend <= g.kbeg || g.nbx <= 0 || g.nby <= 0) return 0;
-  static bool attr_set = false;
-  const int bytes = (int)(P::SMEM_D * sizeof(double));
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_block_march<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
-    attr_set = true;
-  }
-  dim3 grd(g.nbx, g.nby, (g.kend - g.kbeg + g.kchunk - 1) / g.kchunk), blk(P::NT, 1, 1);
-  k_block_march<P><<<grd, blk, bytes, st>>>(prog, g.kbeg, g.kend, g.kchunk);
-  (*launches)++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-#else
-template <class P, int PH> struct PhaseSeqEmu {
-  static void run(const P &prog, std::vector<typename P::State> &st, int bx, int by, int k, double *sm) {
-    for (int tid = 0; tid < P::NT; tid++) prog.template phase<PH>(st[tid], tid, bx, by, k, sm);
-    if constexpr (PH + 1 < P::NPH) PhaseSeqEmu<P, PH + 1>::run(prog, st, bx, by, k, sm);
-  }
-};
-template <class P> static inline int run_block_march(void *, const P &prog, const MarchGrid &g, long *launches) {
-  if (g.kend <= g.kbeg || g.nbx <= 0 || g.nby <= 0) return 0;
-  std::vector<double> sm(P::SMEM_D);
-  std::vector<typename P::State> st(P::NT);
-  const int nz = (g.kend - g.kbeg + g.kchunk - 1) / g.kchunk;
-  for (int bz = 0; bz < nz; bz++)
-    for (int by = 0; by < g.nby; by++)
-      for (int bx = 0; bx < g.nbx; bx++) {
-        const int ka = g.kbeg + bz * g.kchunk, kb = g.kend < ka + g.kchunk ? g.kend : ka + g.kchunk;
-        for (int tid = 0; tid < P::NT; tid++) prog.begin(st[tid], tid, bx, by, ka, kb, sm.data());
-        for (int k = ka - P::LEAD; k < kb; k++) PhaseSeqEmu<P, 0>::run(prog, st, bx, by, k, sm.data());
-      }
-  (*launches)++;
-  return 0;
-}
-#endif
-
 // ---- LES pass 2 (les.c:308-669): separable Simpson test filters + Germano contraction ---------------
 // The reference filters per-node products (w U_a u_b, w |S|S_ij) with the 27-point (1,4,1)^3 Simpson
 // stencil, one 27-term sum per product and cell (rhs2.c:499-523).  The stencil is a tensor product,
@@ -94,67 +40,182 @@ template <class P> static inline int run_block_march(void *, const P &prog, cons
 // bounded the 27-term form (shared-memory bandwidth, profiles/r01c).  The summation order differs
 // from the reference's, i.e. results agree to rounding (~1e-14 relative), not bitwise.  The weight
 // sum and sum_weight (les.c:441-468) depend on the grid and mask only and come from LesGeo.
-// The tensor algebra that follows the filters (les2_finish_geo) runs in the last phase.
-template <int TY_, int MINB_> struct Les2Sep {
-  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15, NPH = 3, LEAD = 0;
-  static constexpr int MINB = MINB_;               // resident blocks per SM the launch bounds ask for
-  static constexpr bool SYNC_AFTER_LAST = false;   // phase 0 of the next step does not touch what phase 2 reads
-  static constexpr long SMEM_D = 2L * NV * NT;
-  struct State { double v[NV]; };
+// The tensor algebra that follows the filters (les2_finish_geo) runs in the last phase; its 23
+// per-node operands (centre metrics, aj, grid factors, filtered velocity, nvert) of the tile's plane
+// are staged by TMA into shared memory while phases 0 and 1 run: the warp that finishes phase 2 last
+// issues the copies for the next plane, so nobody waits to refill the single buffer and the ~30
+// scattered global loads that stalled the finish (profiles/r01j) become shared-memory reads.
+struct Les2March {
+  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 15, NOP = 23;
+  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_BAR = OFF_OP + NOP * NT;
+  static constexpr long SMEM_D = OFF_BAR + 2;
+  // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..18 LFINV,LTF2,LF2,LG0..5 | 19..21 UF | 22 nvert
+  VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 19 ? S_LFINV + (q - 10) : (q < 22 ? S_UF0 + (q - 19) : S_NV)); }
+  struct State { double v[NV]; double ufk[6]; double nvk[2]; };
   VfsDev d;
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
   static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
-  VFS_HD void begin(State &, int, int, int, int, int, double *) const {}
-  template <int PH> VFS_HD void phase(State &st, int tid, int bx, int by, int k, double *sm) const {
-    const int tx = tid % TX, ty = tid / TX;
-    const int i = bx * (TX - 2) + tx, j = by * (TY - 2) + ty;      // node of this thread (tile halo included)
-    double *sK = sm, *sA = sm + NV * NT;
-    if (PH == 0) {            // k pass over the thread's own column
-      double K[NV];
+  VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
+  VFS_HD static int jorg(int by) { return by * (TY - 2); }
+  struct Ops {        // finish operands: plane k from the staged buffer, planes k-1/k+1 of UF and nvert from registers
+    const double *op; double ufk[6], nvk[2];
+    VFS_HD double met(int s) const { return op[s * NT]; }
+    VFS_HD double aj() const { return op[9 * NT]; }
+    VFS_HD double geo(int q) const { return op[(10 + q) * NT]; }
+    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? op[(19 + a) * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
+    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? op[22 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
+  };
+  // phase 0: k pass over the thread's own column (+ the k-neighbours of UF / nvert the finish needs)
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    double K[NV];
 #pragma unroll
-      for (int a = 0; a < NV; a++) K[a] = 0;
-      if (i <= d.mx - 1 && j <= d.my - 1) {
-        const long p = d.idx(i, j, k);
-#pragma unroll
-        for (int dk = -1; dk <= 1; dk++) {
-          const long n = p + dk * d.sk;
-          const double w = d.s[S_LW][n];
-          const double sw = dk == 0 ? 4. * w : w;
-          const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
-          const double U0 = sw * d.s[S_LU0][n], U1 = sw * d.s[S_LU1][n], U2 = sw * d.s[S_LU2][n];
-          K[0] += U0 * u0; K[1] += U0 * u1; K[2] += U0 * u2;
-          K[3] += U1 * u0; K[4] += U1 * u1; K[5] += U1 * u2;
-          K[6] += U2 * u0; K[7] += U2 * u1; K[8] += U2 * u2;
-#pragma unroll
-          for (int a = 0; a < 6; a++) K[9 + a] += sw * d.s[S_LSS0 + a][n];
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < NV; a++) { st.v[a] = K[a]; sK[a * NT + tid] = K[a]; }
-    } else if (PH == 1) {     // i pass (tile-edge columns produce unused values)
-      const int l = tx > 0 ? tid - 1 : tid, r = tx < TX - 1 ? tid + 1 : tid;
-#pragma unroll
-      for (int a = 0; a < NV; a++) {
-        const double A = sK[a * NT + l] + 4. * st.v[a] + sK[a * NT + r];
-        st.v[a] = A; sA[a * NT + tid] = A;
-      }
-    } else {                  // j pass + les.c:470-669 for the inner nodes of the tile
-      if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
+    for (int a = 0; a < NV; a++) K[a] = 0;
+    if (i <= d.mx - 1 && j <= d.my - 1) {
       const long p = d.idx(i, j, k);
-      if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
-      const int up = tid - TX, dn = tid + TX;
-      double f[NV];
 #pragma unroll
-      for (int a = 0; a < NV; a++) f[a] = sA[a * NT + up] + 4. * st.v[a] + sA[a * NT + dn];
-      les2_finish_geo(d, i, j, k + d.kofs, p, f);
+      for (int a = 0; a < 3; a++) { st.ufk[a] = d.s[S_UF0 + a][p - d.sk]; st.ufk[3 + a] = d.s[S_UF0 + a][p + d.sk]; }
+      st.nvk[0] = d.s[S_NV][p - d.sk]; st.nvk[1] = d.s[S_NV][p + d.sk];
+#pragma unroll
+      for (int dk = -1; dk <= 1; dk++) {
+        const long n = p + dk * d.sk;
+        const double w = d.s[S_LW][n];
+        const double sw = dk == 0 ? 4. * w : w;
+        const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
+        const double U0 = sw * d.s[S_LU0][n], U1 = sw * d.s[S_LU1][n], U2 = sw * d.s[S_LU2][n];
+        K[0] += U0 * u0; K[1] += U0 * u1; K[2] += U0 * u2;
+        K[3] += U1 * u0; K[4] += U1 * u1; K[5] += U1 * u2;
+        K[6] += U2 * u0; K[7] += U2 * u1; K[8] += U2 * u2;
+#pragma unroll
+        for (int a = 0; a < 6; a++) K[9 + a] += sw * d.s[S_LSS0 + a][n];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NV; a++) { st.v[a] = K[a]; sm[a * NT + tid] = K[a]; }
+  }
+  // phase 1: i pass (tile-edge columns produce unused values)
+  VFS_HD void phase1(State &st, int tid, double *sm) const {
+    const int tx = tid % TX;
+    const int l = tx > 0 ? tid - 1 : tid, r = tx < TX - 1 ? tid + 1 : tid;
+    double *sA = sm + OFF_A;
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const double A = sm[a * NT + l] + 4. * st.v[a] + sm[a * NT + r];
+      st.v[a] = A; sA[a * NT + tid] = A;
     }
   }
+  // phase 2: j pass + les.c:470-669 for the inner nodes of the tile
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
+    const long p = d.idx(i, j, k);
+    Ops O; O.op = sm + OFF_OP + tid;
+    if (O.nv(0, 0, 0) > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
+#pragma unroll
+    for (int a = 0; a < 6; a++) O.ufk[a] = st.ufk[a];
+    O.nvk[0] = st.nvk[0]; O.nvk[1] = st.nvk[1];
+    const double *sA = sm + OFF_A;
+    const int up = tid - TX, dn = tid + TX;
+    double f[NV];
+#pragma unroll
+    for (int a = 0; a < NV; a++) f[a] = sA[a * NT + up] + 4. * st.v[a] + sA[a * NT + dn];
+    les2_finish_geo(d, O, i, j, k + d.kofs, p, f);
+  }
 };
-template <class P> static inline MarchGrid les2_sep_grid(const VfsDev &d, int k0, int k1) {
-  MarchGrid g = {P::tiles_x(d), P::tiles_y(d), k0, k1, 1};
-  g.kchunk = pick_kchunk(g.nbx * g.nby, k1 - k0, 16, 148 * P::MINB);
-  return g;
+
+#ifndef VFS_EMU
+#include "vfs_fused_kernels.h"
+__global__ void __launch_bounds__(Les2March::NT, 1) k_les2_march(const __grid_constant__ CUtensorMap tmap, const Les2March P, int kbeg, int kend, int kchunk) {
+  extern __shared__ __align__(128) double vfs_les2_sm[];
+  double *sm = vfs_les2_sm;
+  typedef Les2March M;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR);
+  unsigned *cnt = reinterpret_cast<unsigned *>(bar + 1);
+  const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+  const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
+  if (ka >= kb) return;
+  auto issue = [&](int k) {       // one thread: the 23 operand tiles of plane k -> shared memory
+    mbar_expect_tx(bar, M::NOP * M::NT * 8);
+#pragma unroll 1
+    for (int q = 0; q < M::NOP; q++) tma_load_tile(sm + M::OFF_OP + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(q), bar);
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1); *cnt = 0;
+    fence_mbar_init();
+    issue(ka);
+  }
+  __syncthreads();
+  M::State st;
+  for (int k = ka; k < kb; k++) {
+    P.phase0(st, tid, bx, by, k, sm);
+    __syncthreads();
+    P.phase1(st, tid, sm);
+    __syncthreads();
+    mbar_wait(bar, (k - ka) & 1);
+    P.phase2(st, tid, bx, by, k, sm);
+    // the warp that leaves phase 2 last refills the operand buffer for the next plane
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(cnt, 1u) == M::NT / 32 - 1) {
+        *reinterpret_cast<volatile unsigned *>(cnt) = 0;
+        __threadfence_block();
+        if (k + 1 < kb) { fence_proxy_async(); issue(k + 1); }
+      }
+    }
+  }
 }
+static inline int run_les2_march(cudaStream_t stream, const CUtensorMap &tmap, const Les2March &P, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  static bool attr_set = false;
+  const int bytes = (int)(Les2March::SMEM_D * sizeof(double));
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_les2_march, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  const int ntx = Les2March::tiles_x(P.d), nty = Les2March::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16);
+  dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk);
+  k_les2_march<<<grd, Les2March::NT, bytes, stream>>>(tmap, P, k0, k1, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#else
+static inline int run_les2_march(void *, const Les2March &P, int k0, int k1, long *launches) {
+  typedef Les2March M;
+  if (k1 <= k0) return 0;
+  std::vector<double> smv(M::SMEM_D);
+  std::vector<M::State> st(M::NT);
+  double *sm = smv.data();
+  const VfsDev &d = P.d;
+  const int ntx = M::tiles_x(d), nty = M::tiles_y(d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 4, 7);
+  for (int bz = 0; bz * kchunk < k1 - k0; bz++)
+    for (int by = 0; by < nty; by++)
+      for (int bx = 0; bx < ntx; bx++) {
+        const int ka = k0 + bz * kchunk, kb = k1 < ka + kchunk ? k1 : ka + kchunk;
+        auto issue = [&](int k) {       // what the TMA unit does: box copy with zero fill outside the padded array
+          for (int q = 0; q < M::NOP; q++)
+            for (int y = 0; y < M::TY; y++)
+              for (int x = 0; x < M::TX; x++) {
+                const int X = M::iorg(bx) + VFS_G + x, Y = M::jorg(by) + VFS_G + y, Z = k + VFS_G;
+                const bool in = X >= 0 && X < d.pitch && Y >= 0 && Y < d.ny && Z >= 0 && Z < d.nzt;
+                sm[M::OFF_OP + q * M::NT + y * M::TX + x] = in ? d.s[M::op_sid(q)][(long)Z * d.sk + (long)Y * d.sj + X] : 0.;
+              }
+        };
+        issue(ka);
+        for (int k = ka; k < kb; k++) {
+          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, sm);
+          for (int t = 0; t < M::NT; t++) P.phase1(st[t], t, sm);
+          // phase 1 reads its neighbours' phase-0 values from the exchange buffer while updating st.v in place
+          for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, sm);
+          if (k + 1 < kb) issue(k + 1);
+        }
+      }
+  (*launches)++;
+  return 0;
+}
+#endif
 
 // ---- fused residual: face fluxes -> Fp -> projection -> assembly (regular interior) ----------------
 // Replaces, for the cells whose whole dependency cone is free of domain-end special cases, the staged
@@ -353,7 +414,6 @@ struct RhsMarch {
 };
 
 #ifndef VFS_EMU
-#include "vfs_fused_kernels.h"
 __global__ void __launch_bounds__(RhsMarch::NT, 1) k_rhs_march(const __grid_constant__ CUtensorMap tmap, const RhsMarch P, int kchunk) {
   extern __shared__ __align__(128) double vfs_rhs_sm[];
   double *sm = vfs_rhs_sm;
