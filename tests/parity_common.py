@@ -114,6 +114,8 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None):
     ctx.Formfunction_2("RHS_O", 1.0)
     rhs_o_ref = np.array(ref.owned("RHS_o"))
     err["Formfunction_2"] = relerr(ctx.download("RHS_O"), rhs_o_ref)
+    if cfg["flags"].get("viscosity_wallmodel"):      # Cabot wall law: friction velocity at the first cells (momentum.c:1150)
+        err["Ustar"] = relerr(ctx.download("USTAR")[:, 1], np.array(ref.owned("lUstar"))[:, 1])
     # one Krylov-iteration residual
     x = krylov_x(fields["ucont"])
     ref.new_vec("X", 3, False)

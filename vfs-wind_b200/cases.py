@@ -15,7 +15,7 @@ import numpy as np
 CONFIGS = {
     # C1: Test_10 channel, shipped grid 121x41x61 (uniform in x,z; generated identically here)
     "c1_test10": dict(IM=121, JM=41, KM=61, grid="test10", seed=101, ren=62500.0, dt=1e-3, bctype=[100, 100, 1, 10, 100, 100],
-                      flags=dict(les=2, laplacian=1, second_order=1, ii_periodic=1, kk_periodic=1, max_cs=0.2)),
+                      flags=dict(les=2, laplacian=1, second_order=1, ii_periodic=1, kk_periodic=1, viscosity_wallmodel=1, max_cs=0.2)),
     # C2: synthetic stretched curvilinear box 256^3 with dynamic Smagorinsky (bench workload)
     "c2_box256": dict(IM=255, JM=255, KM=255, grid="stretched", seed=202, ren=62500.0, dt=1e-3, bctype=[100, 100, 1, 10, 100, 100],
                       flags=dict(les=2, ii_periodic=1, kk_periodic=1, max_cs=0.2)),

@@ -48,6 +48,7 @@ enum {
   // LES factors that depend on the grid and the nvert mask only (LesGeo, vfs_les_kernels.h):
   // 1/sum(s*w), test_filter^2, filter^2 and the covariant metric tensor G (00,11,22,01,02,12)
   S_LFINV, S_LTF2, S_LF2, S_LG0, S_LG1, S_LG2, S_LG3, S_LG4, S_LG5,
+  S_WM,                                                                  // wall-model nu_t of the j = 0 faces (plane j = 0 only)
   S_COUNT
 };
 

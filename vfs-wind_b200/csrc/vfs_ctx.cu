@@ -10,6 +10,7 @@
 #include "vfs_c2c_kernels.h"
 #include "vfs_rhs_kernels.h"
 #include "vfs_les_kernels.h"
+#include "vfs_wm_kernels.h"
 #include "vfs_fused_kernels.h"
 #include "vfs_march_kernels.h"
 #include <stdio.h>
@@ -102,6 +103,7 @@ struct vfs_ctx {
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
+  double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
 };
 
@@ -255,7 +257,6 @@ static int check_params(const vfs_params *p, std::string &why) {
   if (p->i_homo_filter || p->j_homo_filter || p->k_homo_filter) { why = "homogeneous-plane Cs averaging not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
-  if (p->viscosity_wallmodel) { why = "viscosity_wallmodel (Cabot wall law) not built yet"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 0; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2 || p->bctype[q] == 11) { why = "wall-function / cylinder boundary types (-1,-2,11) not supported"; return VFS_ERR_UNSUPPORTED; }
   if (!(p->ren > 0) || !(p->dt > 0)) { why = "ren and dt must be positive"; return VFS_ERR_ARG; }
   return 0;
@@ -314,12 +315,13 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
+  if (c->wm_table) cudaFree(c->wm_table);
   cudaFree(c->pool); cudaFree(c->stage);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage);
+  free(c->pool); free(c->stage); free(c->wm_table);
 #endif
   delete c; return 0;
 }
@@ -604,10 +606,31 @@ static int ensure_iaj(vfs_ctx *c) {
   return 0;
 }
 
+// Cabot wall model at the j = 0 faces (viscosity_wallmodel, momentum.c:1139-1154): table once, then one
+// Newton solve per face of the plane, before the flux kernels read the override
+static int wall_model(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  if (!c->wm_table) {
+    const size_t bytes = (size_t)(VFS_WM_NYP + 1) * sizeof(double);
+#ifndef VFS_EMU
+    if (c->capturing) { set_err(c, "wall-model table must be built before graph capture"); return VFS_ERR_CUDA; }
+    CK(cudaMalloc((void **)&c->wm_table, bytes));
+#else
+    c->wm_table = (double *)malloc(bytes);
+#endif
+    { WmTableIntervals f = {c->wm_table}; Box b = {0, VFS_WM_NYP + 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
+    { WmTableScan f = {c->wm_table}; Box b = {0, 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
+  }
+  WallModelPlane f = {d, c->wm_table};
+  Box b = {1, d.mx - 1, 0, 1, klo(c, 1), klo(c, d.mz - 1)};
+  return launch(c, b, f);
+}
+
 // mode 0: rhs[s0] += scale*R, masks (Formfunction_2) ; mode 1: full SNES assembly into S_R0
 static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const VfsDev &d = c->d;
   RUN(ensure_iaj(c));
+  if (d.visc_wm && d.les) RUN(wall_model(c));
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
   Box R;

@@ -26,6 +26,7 @@ struct GlobalAcc {
   template <int D> VFS_HD double iaj(int side) const { return d.s[S_IAJ][p + side * sn<D>()]; }
   template <int D> VFS_HD double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
   template <int D> VFS_HD double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
+  VFS_HD double wm() const { return d.s[S_WM][p]; }        // wall-model SGS viscosity of the j = 0 face (vfs_wm_kernels.h)
 };
 
 // tangential difference of component a along unit direction T at the face between node offset
@@ -144,6 +145,7 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], d
     if ((!REGULAR && c == 0 && !per) || nvp > 0.1) nu_t = A.template nut<D>(1);
     else if ((!REGULAR && c == m - 2 && !per) || nvn > 0.1) nu_t = A.template nut<D>(0);
     else nu_t = 0.5 * (A.template nut<D>(0) + A.template nut<D>(1));
+    if constexpr (!REGULAR && D == 1) { if (c == 0 && d.visc_wm) nu_t = A.wm(); }     // momentum.c:1139-1154
 #pragma unroll
     for (int a = 0; a < 3; a++)
       fv[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu_t;
