@@ -104,6 +104,7 @@ struct vfs_ctx {
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
+  bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
   bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
 };
 
@@ -128,6 +129,53 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
   return 0;
 }
 #define RUN(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+// All domain-boundary nodes of the slab (i, j or global k equal to 0 or m-1) in ONE launch, as three
+// disjoint index ranges: the two i planes (j, k full), the two j planes (i inner) and the owned global
+// k = 0 / mz-1 planes (i, j inner).  [ka, kb) is the local k range of the i- and j-plane parts (it may
+// reach into the k ghost planes, see node_copy).  Replaces 4-6 thin launches per boundary operation.
+struct Shell { int mx, my, ka, nk, kp[2], nkp; long nA, nB, nC; };
+static Shell make_shell(const VfsDev &d, int ka, int kb) {
+  Shell s; s.mx = d.mx; s.my = d.my; s.ka = ka; s.nk = kb - ka; s.nkp = 0;
+  if (d.kofs == 0) s.kp[s.nkp++] = 0;
+  if (d.kofs + d.nzl == d.mz) s.kp[s.nkp++] = d.nzl - 1;
+  s.nA = 2L * d.my * s.nk; s.nB = 2L * (d.mx - 2) * s.nk; s.nC = (long)s.nkp * (d.mx - 2) * (d.my - 2);
+  return s;
+}
+template <class F> VFS_HD void shell_visit(const F &f, const Shell &s, long t) {
+  if (t < s.nA) {
+    const long per = (long)s.my * s.nk; const int side = (int)(t / per); const long r = t - side * per;
+    f(side ? s.mx - 1 : 0, (int)(r % s.my), s.ka + (int)(r / s.my));
+  } else if (t < s.nA + s.nB) {
+    t -= s.nA;
+    const long per = (long)(s.mx - 2) * s.nk; const int side = (int)(t / per); const long r = t - side * per;
+    f(1 + (int)(r % (s.mx - 2)), side ? s.my - 1 : 0, s.ka + (int)(r / (s.mx - 2)));
+  } else {
+    t -= s.nA + s.nB;
+    const long per = (long)(s.mx - 2) * (s.my - 2); const int q = (int)(t / per); const long r = t - q * per;
+    f(1 + (int)(r % (s.mx - 2)), 1 + (int)(r / (s.mx - 2)), s.kp[q]);
+  }
+}
+#ifndef VFS_EMU
+template <class F> __global__ void __launch_bounds__(256) k_shell(F f, Shell s) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < s.nA + s.nB + s.nC) shell_visit(f, s, t);
+}
+#endif
+template <class F> static int launch_shell(vfs_ctx *c, int ka, int kb, const F &f) {
+  const Shell s = make_shell(c->d, ka, kb);
+  const long n = s.nA + s.nB + s.nC;
+  if (n <= 0) return 0;
+  c->launches++;
+#ifndef VFS_EMU
+  k_shell<F><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(f, s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(c, std::string("kernel launch: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+#else
+  for (long t = 0; t < n; t++) shell_visit(f, s, t);
+#endif
+  return 0;
+}
 
 static void ev_rec(vfs_ctx *c, int n) {
 #ifndef VFS_EMU
@@ -235,13 +283,7 @@ static int node_copy(vfs_ctx *c, const Grp &g) {
   // planes in a single-rank run, where this copy updates them; apply it there too so that the
   // result does not depend on the number of ranks (wrap-around ghosts stay stale, as in 1 rank).
   const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;
-  if (d.perx) { Box b0 = {0, 1, 0, d.my, ka, kb}, b1 = {d.mx - 1, d.mx, 0, d.my, ka, kb}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-  if (d.pery) { Box b0 = {0, d.mx, 0, 1, ka, kb}, b1 = {0, d.mx, d.my - 1, d.my, ka, kb}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
-  if (d.perz) {
-    if (d.kofs == 0) { Box b0 = {0, d.mx, 0, d.my, 0, 1}; RUN(launch(c, b0, f)); }
-    if (d.kofs + d.nzl == d.mz) { Box b1 = {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}; RUN(launch(c, b1, f)); }
-  }
-  return 0;
+  return launch_shell(c, ka, kb, f);      // the functor acts on nodes of periodic boundary planes only
 }
 static bool any_per(const vfs_ctx *c) { return c->d.perx || c->d.pery || c->d.perz; }
 
@@ -468,6 +510,12 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_AJ) c->iaj_valid = false;
   if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
+  if (field == VFS_NVERT) {       // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep
+    const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx;
+    bool any = false;
+    for (size_t q = 0; q < n && !any; q++) any = ((int)(host[q] + 0.1) == 3);
+    c->has_solid = any;
+  }
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
@@ -501,21 +549,9 @@ extern "C" int vfs_form_metrics(vfs_ctx *c) {
 // ---- Contra2Cart ------------------------------------------------------------------------------------
 struct CopyScalar3 { VfsDev d; int from, to; VFS_HD void operator()(int i, int j, int k) const { long p = d.idx(i, j, k); for (int a = 0; a < 3; a++) d.s[to + a][p] = d.s[from + a][p]; } };
 
-static int for_boundary_planes(vfs_ctx *c, int (*fn)(vfs_ctx *, const Box &, void *), void *arg) {
-  const VfsDev &d = c->d;
-  Box b[6] = {{0, 1, 0, d.my, 0, d.nzl}, {d.mx - 1, d.mx, 0, d.my, 0, d.nzl}, {0, d.mx, 0, 1, 0, d.nzl}, {0, d.mx, d.my - 1, d.my, 0, d.nzl},
-              {0, d.mx, 0, d.my, 0, 1}, {0, d.mx, 0, d.my, d.nzl - 1, d.nzl}};
-  for (int q = 0; q < 6; q++) {
-    if (q == 4 && d.kofs != 0) continue;
-    if (q == 5 && d.kofs + d.nzl != d.mz) continue;
-    RUN(fn(c, b[q], arg));
-  }
-  return 0;
-}
-static int run_snapshot(vfs_ctx *c, const Box &b, void *) { CopyScalar3 f = {c->d, S_U0, S_FP0}; return launch(c, b, f); }
-static int run_ghost_rules(vfs_ctx *c, const Box &b, void *) { C2CGhostRules f = {c->d}; return launch(c, b, f); }
-
-static int run_les_derive_boundary(vfs_ctx *c, const Box &b, void *) { LesDeriveBoundary f = {c->d}; return launch(c, b, f); }
+static int run_snapshot(vfs_ctx *c) { CopyScalar3 f = {c->d, S_U0, S_FP0}; return launch_shell(c, 0, c->d.nzl, f); }
+static int run_ghost_rules(vfs_ctx *c) { C2CGhostRules f = {c->d}; return launch_shell(c, 0, c->d.nzl, f); }
+static int run_les_derive_boundary(vfs_ctx *c) { LesDeriveBoundary f = {c->d}; return launch_shell(c, 0, c->d.nzl, f); }
 
 static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
@@ -527,9 +563,19 @@ static int contra2cart(vfs_ctx *c) {
   ev_rec(c, 2 * VFS_T_C2C + 1);
   RUN(g2l(c, gu));
   if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:254-291
-  RUN(for_boundary_planes(c, run_snapshot, 0));                      // lUcat snapshot read by the rules
-  RUN(for_boundary_planes(c, run_ghost_rules, 0));                   // rhs.c:302-682 (boundary nodes)
-  { C2CInteriorFix f = {d}; RUN(launch(c, box_interior(c), f)); }   // rhs.c:305-308,676-681 (interior nodes)
+  RUN(run_snapshot(c));                      // lUcat snapshot read by the rules
+  RUN(run_ghost_rules(c));                   // rhs.c:302-682 (boundary nodes)
+  {                                                                  // rhs.c:305-308,676-681 (interior nodes)
+    C2CInteriorFix f = {d};
+    const Box bi = box_interior(c);
+    if (c->has_solid) RUN(launch(c, bi, f));                         // solid cells -> 0: the whole interior
+    else {                                                           // only the "corner" lines can change
+      const int *bc = d.bc;
+      const bool cor[4] = {bc[0] <= 1 && bc[2] <= 1, bc[1] <= 1 && bc[2] <= 1, bc[0] <= 1 && bc[3] <= 1, bc[1] <= 1 && bc[3] <= 1};
+      const int ci[4] = {1, d.mx - 2, 1, d.mx - 2}, cj[4] = {1, 1, d.my - 2, d.my - 2};
+      for (int q = 0; q < 4; q++) if (cor[q]) { Box b = {ci[q], ci[q] + 1, cj[q], cj[q] + 1, bi.k0, bi.k1}; RUN(launch(c, b, f)); }
+    }
+  }
   RUN(g2l(c, gu));
   if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:712-748
   return 0;
@@ -717,6 +763,25 @@ struct ZeroNormal {   // wall-normal zeroing applied to an Ucont that is already
     d.s[S_UC0][p] = tmp[0]; d.s[S_UC1][p] = tmp[1]; d.s[S_UC2][p] = tmp[2];
   }
 };
+// wall-normal flux zeroing (momentum.c:2264-2289) of an Ucont already on the device: only the planes
+// whose boundary type asks for it are touched
+static int zero_normal(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  ZeroNormal f = {d};
+  const int *bc = d.bc;
+  const bool need[6] = {bc[0] == 1 || bc[0] == 10, bc[1] == 1 || bc[1] == 10, bc[2] == 1 || bc[2] == 12 || bc[2] == 10,
+                        bc[3] == 1 || bc[3] == 2 || bc[3] == 12 || bc[3] == 10 || bc[3] == -10, bc[4] == 1, bc[5] == 1};
+  const int plane[6] = {0, d.mx - 2, 0, d.my - 2, 0, d.mz - 2};
+  for (int q = 0; q < 6; q++) {
+    if (!need[q]) continue;
+    Box b = box_owned(c);
+    if (q < 2) { b.i0 = plane[q]; b.i1 = b.i0 + 1; }
+    else if (q < 4) { b.j0 = plane[q]; b.j1 = b.j0 + 1; }
+    else { const int k = plane[q] - d.kofs; if (k < 0 || k >= d.nzl) continue; b.k0 = k; b.k1 = k + 1; }
+    RUN(launch(c, b, f));
+  }
+  return 0;
+}
 static int snes_core(vfs_ctx *c) {
   RUN(g2l(c, grp(S_UC0, 3)));                                         // momentum.c:2293-2294
   RUN(contra2cart(c));
@@ -727,7 +792,7 @@ extern "C" int vfs_formfunction_snes_dev(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
   ev_rec(c, 2 * VFS_T_TOTAL);
   RUN(run_graphed(c, 0, [&]() -> int {
-    { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+    RUN(zero_normal(c));
     return snes_core(c);
   }));
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
@@ -777,7 +842,7 @@ static int les_cs(vfs_ctx *c) {
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
   c->sabs_valid = true;
-  RUN(for_boundary_planes(c, run_les_derive_boundary, 0));
+  RUN(run_les_derive_boundary(c));
   Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
   RUN(g2l(c, g1));                                                    // les.c:254-267
   // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
@@ -816,7 +881,7 @@ static int les_cs(vfs_ctx *c) {
 #endif
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
-  { LesClip f = {d}; RUN(launch(c, box_owned(c), f)); }              // les.c:967-980
+  { LesClipBoundary f = {d}; RUN(launch_shell(c, 0, d.nzl, f)); }     // les.c:967-980 (boundary nodes; interior clip is in pass 3)
   Grp g3 = grp(S_CS, 1);
   RUN(g2l(c, g3));                                                    // les.c:1026-1027
   if (any_per(c)) RUN(node_copy(c, g3));
@@ -845,7 +910,7 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
     RUN(g2l(c, grp(S_UC0, 3)));
     RUN(contra2cart(c));
     if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
-    { ZeroNormal f = {c->d}; RUN(launch(c, box_owned(c), f)); }
+    RUN(zero_normal(c));
     return snes_core(c);
   }));
   ev_rec(c, 2 * VFS_T_TOTAL + 1);

@@ -398,7 +398,13 @@ template <bool REGULAR, class Acc> VFS_HD void les3_core(const VfsDev &d, const 
     LM_avg = lm / ws; MM_avg = mmv / ws;
   }
   const double C = 0.5 * LM_avg / (MM_avg + 1.e-4);
-  d.s[S_CS][p] = C > 0 ? C : 0;
+  double cs = C > 0 ? C : 0;
+  // clip chain of les.c:967-980 for interior nodes (boundary nodes are zeroed by LesClipBoundary)
+  const double nvc = A.nv(0, 0, 0);
+  if (nvc > 0.1 && nvc < 1.1) cs = cs > 0.001 ? cs : 0.001;
+  cs = cs > 0 ? cs : 0;
+  cs = cs < d.max_cs ? cs : d.max_cs;
+  d.s[S_CS][p] = cs;
 }
 struct LesPass3 {
   VfsDev d;
@@ -409,22 +415,10 @@ struct LesPass3 {
   }
 };
 
-// les.c:967-980 clip chain, over every owned node
-struct LesClip {
+// les.c:967-980: Cs = 0 on the domain-boundary nodes (the interior part of the clip chain is in les3_core)
+struct LesClipBoundary {
   VfsDev d;
-  VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
-    const long p = d.idx(i, j, k);
-    const double nv = d.s[S_NV][p];
-    double cs = d.s[S_CS][p];
-    if (nv > 1.1 || kg == 0 || kg == d.mz - 1 || j == 0 || j == d.my - 1 || i == 0 || i == d.mx - 1) cs = 0;
-    else {
-      if (nv > 0.1 && nv < 1.1) cs = cs > 0.001 ? cs : 0.001;
-      cs = cs > 0 ? cs : 0;
-      cs = cs < d.max_cs ? cs : d.max_cs;
-    }
-    d.s[S_CS][p] = cs;
-  }
+  VFS_HD void operator()(int i, int j, int k) const { d.s[S_CS][d.idx(i, j, k)] = 0; }
 };
 
 // les.c:1185-1211: nu_t = Cs * Delta^2 * |S|.  FROM_S: |S| was stored by pass 1 of vfs_les_cs from
