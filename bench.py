@@ -25,17 +25,32 @@ from __graft_entry__ import load_package  # noqa: E402
 # algorithmic (compulsory) HBM bytes per cell; derivation in DESIGN.md section 5
 BYTES_STEP = 248.0          # fused RHS+LES unit, SURVEY 8(d): 23 doubles read + 8 written
 BYTES_STEP_FEUL = 272.0
-KERNEL_BYTES = {            # per-kernel-group compulsory traffic of the staged round-1 kernels
-    "flux": 36 * 8.0,       # r: ucat3 ucont3 metrics10 nvert1 nu_t1, w: Fc9 Fv9
+KERNEL_BYTES = {            # per-kernel-group compulsory traffic (doubles read + written per cell) * 8
+    "flux": 36 * 8.0,       # r: ucat3 nvert1 ucont3 metrics9 1/aj nu_t1, w: Fc9 Fv9
     "fp": 22 * 8.0,         # r: Fc9 Fv9 nvert1, w: Fp3
-    "project": 29 * 8.0,    # r: Fp3 metrics10 nvert1 ucont3 ucont_o3 rhs_o3 dp3, w: rhs3
-    "c2c": 17 * 8.0,        # r: ucont3 metrics10 nvert1, w: ucat3
-    "les1": 30 * 8.0,       # r: ucat3 metrics10 nvert1, w: grad9 |S|1 ucat_f3 (+3 rounding)
-    "les2": 29 * 8.0,       # r: ucat3 metrics10 nvert1 grad9 |S|1 ucat_f3, w: LM MM
-    "les3": 5 * 8.0,        # r: LM MM aj nvert, w: Cs
-    "nut": 16 * 8.0,        # r: ucat3 metrics10 nvert1 Cs1, w: nu_t
+    "project": 29 * 8.0,    # r: Fp3 metrics9 1/aj nvert1 ucont3 ucont_o3 rhs_o3 dp3, w: rhs3
+    "c2c": 17 * 8.0,        # r: ucont3 metrics9 aj nvert1, w: ucat3
+    "les1": 29 * 8.0,       # r: ucat3 metrics9 aj 1/aj nvert1, w: |S|1 ucat_f3 w1 U3 |S|S_ij6
+    "les2": 38 * 8.0,       # r: ucat3 w1 U3 |S|S_ij6 metrics9 aj gridfactors9 ucat_f3 nvert1, w: LM MM
+    "les3": 5 * 8.0,        # r: LM MM 1/aj nvert, w: Cs
+    "nut": 5 * 8.0,         # r: Cs |S| aj nvert, w: nu_t
 }
+# kernel that dominates each timer group (names as they appear in the ncu launch list / profiles/)
+KERNEL_NAME = {"flux": "k_tile_march<RingFlux, FluxBody>", "fp": "k_box<FpCell>", "project": "k_box<ProjectSNES>", "c2c": "k_box<C2CInterior>",
+               "les1": "k_tile_march<RingLes1, Les1Body>", "les2": "k_les2_march", "les3": "k_tile_march<RingLes3, Les3Body>", "nut": "k_box<NuT>"}
 TIMER = {"total": 0, "c2c": 1, "flux": 2, "fp": 3, "project": 4, "les1": 5, "les2": 6, "les3": 7, "nut": 8}
+
+
+def measured_traffic(kernel_group, workload):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the group's dominant kernel, from the
+    committed `ncu --set full` capture summarised in profiles/traffic.json (same workload, one launch)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    if t.get("workload") != workload:
+        return None
+    return t.get("dram_bytes_per_launch", {}).get(kernel_group)
 
 
 def peaks():
@@ -178,6 +193,25 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    # the two halves of the unit on their own (the Krylov solver calls the residual 10-50x per LES update)
+    def timed(fn, n):
+        fn(); barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream); barrier()
+        t = a.elapsed_time(b) / n
+        if world > 1:
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+    ms_rhs = timed(ctx.FormFunction_SNES_dev, args.steps)
+
+    def les_only():
+        ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+    ms_les = timed(les_only, args.steps)
     # per-kernel CUDA-event timers and the launch count come from eager steps of the same work
     ctx.set_option(1, 0)
     tsum = {k: 0.0 for k in TIMER}
@@ -243,7 +277,8 @@ def run_ours(args):
     ach = KERNEL_BYTES[dom] * cells_rank / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
     bytes_step = BYTES_STEP_FEUL if cfg.get("forcing") else BYTES_STEP
     ach_step = bytes_step * value / world / 1e9
-    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    roof = {"bound": "hbm", "kernel": dom, "kernel_name": KERNEL_NAME[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": measured_traffic(dom, args.workload) if world == 1 else None,
             "peak_source": peak_src, "algorithmic_bytes_per_cell": KERNEL_BYTES[dom], "ms_per_launch_group": per[dom]}
     roof_step = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak, "algorithmic_bytes_per_cell": bytes_step,
                  "note": "whole fused RHS+LES step at SURVEY 8(d) bytes, per GPU"}
@@ -256,6 +291,12 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
             "roofline": roof, "roofline_step": roof_step,
+            "rhs_only": {"value": cells_total / (ms_rhs * 1e-3), "unit": "cell-updates/s", "ms": ms_rhs, "algorithmic_bytes_per_cell": 240.0,
+                         "roofline_frac": 240.0 * cells_total / world / (ms_rhs * 1e-3) / 1e9 / peak, "what": "one FormFunction_SNES residual (X device resident)"},
+            "les_only": {"value": cells_total / (ms_les * 1e-3), "unit": "cell-updates/s", "ms": ms_les, "algorithmic_bytes_per_cell": 128.0,
+                         "roofline_frac": 128.0 * cells_total / world / (ms_les * 1e-3) / 1e9 / peak, "what": "Contra2Cart + dynamic Cs + nu_t"},
+            "halo": {"layer": "in-library NCCL send/recv" if halo == "nccl" else ("torch.distributed callback" if halo is not None else "single rank (periodic wrap kernels)"),
+                     "exchanges": ctx.halo_count()[0], "bytes_sent": ctx.halo_count()[1]},
             "kernel_ms": per}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(args.workload, cores=1, steps=2, planes=10)
