@@ -229,11 +229,16 @@ __global__ void k_halo_unpack(HaloPtrs P, int n, long cnt, long off_hi, long off
     if (buf_lo) reinterpret_cast<double2 *>(P.s[q] + off_lo)[e] = buf_lo[t];
   }
 }
-static int nccl_halo(vfs_ctx *c, const Grp &g) {
+static int nccl_halo(vfs_ctx *c, const Grp &g, bool seam_only) {
   NcclApi &N = nccl_api();
   const VfsDev &d = c->d;
   const int r = c->prm.rank, n = c->prm.nranks;
-  const int lo = r > 0 ? r - 1 : (d.perz ? n - 1 : -1), hi = r < n - 1 ? r + 1 : (d.perz ? 0 : -1);
+  int lo = r > 0 ? r - 1 : (d.perz ? n - 1 : -1), hi = r < n - 1 ? r + 1 : (d.perz ? 0 : -1);
+  if (seam_only) {            // only the periodic seam rank 0 <-> rank n-1 (see g2l_after_copy)
+    if (r > 0) lo = -1;
+    if (r < n - 1) hi = -1;
+    if (lo < 0 && hi < 0) return 0;
+  }
   const long cnt = (long)VFS_G * d.sk;                       // doubles per scalar and side (sk is a multiple of 16)
   if (!c->hbuf) {
     CK(cudaMalloc((void **)&c->hbuf, (size_t)4 * VFS_MAXGRP * cnt * sizeof(double)));
@@ -258,11 +263,11 @@ static int nccl_halo(vfs_ctx *c, const Grp &g) {
   return 0;
 }
 #endif
-static int halo_k(vfs_ctx *c, const Grp &g) {
+static int halo_k(vfs_ctx *c, const Grp &g, bool seam_only = false) {
   const VfsDev &d = c->d;
   if (c->prm.nranks > 1) {
 #ifndef VFS_EMU
-    if (c->comm) return nccl_halo(c, g);
+    if (c->comm) return nccl_halo(c, g, seam_only);
 #endif
     if (!c->halo_fn) { set_err(c, "nranks > 1 but neither vfs_nccl_init nor a halo callback was set up"); return VFS_ERR_HALO; }
     int r = c->halo_fn(c->halo_user, g.n, g.sid);
@@ -275,6 +280,10 @@ static int halo_k(vfs_ctx *c, const Grp &g) {
 }
 // DAGlobalToLocal / DALocalToLocal
 static int g2l(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return halo_k(c, g); }
+// The refresh that follows a node_copy of a field whose ghosts were refreshed just before it: the
+// copy has already been applied to the ghost planes of interior slab boundaries (see node_copy), so
+// between ranks only the periodic seam (global planes 0 / mz-1 changed by the k copies) must travel.
+static int g2l_after_copy(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return c->d.perz ? halo_k(c, g, true) : 0; }
 // the "if(periodic) ... f[k][j][i] = f[c][b][a]" loops
 static int node_copy(vfs_ctx *c, const Grp &g) {
   const VfsDev &d = c->d;
@@ -562,7 +571,7 @@ static int contra2cart(vfs_ctx *c) {
   { C2CInterior f = {d}; RUN(launch(c, box_interior(c), f)); }      // rhs.c:158-247
   ev_rec(c, 2 * VFS_T_C2C + 1);
   RUN(g2l(c, gu));
-  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:254-291
+  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l_after_copy(c, gu)); }   // rhs.c:254-291
   RUN(run_snapshot(c));                      // lUcat snapshot read by the rules
   RUN(run_ghost_rules(c));                   // rhs.c:302-682 (boundary nodes)
   {                                                                  // rhs.c:305-308,676-681 (interior nodes)
@@ -577,7 +586,7 @@ static int contra2cart(vfs_ctx *c) {
     }
   }
   RUN(g2l(c, gu));
-  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l(c, gu)); }        // rhs.c:712-748
+  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l_after_copy(c, gu)); }   // rhs.c:712-748
   return 0;
 }
 extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return vfs_sync(c); }
