@@ -132,7 +132,7 @@ def test_tiled_equals_staged(pkg):
             ctx.close()
         for n in outs[0]:
             if n in ("F", "CS", "NU_T"):
-                assert pc.relerr(outs[1][n], outs[0][n]) <= 1e-13, (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
+                assert pc.relerr(outs[1][n], outs[0][n]) <= 5e-13, (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
                 if n == "F":       # mask-driven zeros are exact; Cs = max(C, 0) may flip at C ~ 0
                     assert np.array_equal(outs[0][n] == 0, outs[1][n] == 0), (cfgname, n)
             else:

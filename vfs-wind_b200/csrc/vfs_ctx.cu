@@ -842,12 +842,11 @@ static int les_cs(vfs_ctx *c) {
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   RUN(ensure_iaj(c));
   ev_rec(c, 2 * VFS_T_LES1);
-#ifndef VFS_EMU
-  if (c->fused && c->tma_ok && !d.testfilter_ik) {
+  if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    if (launch_les1_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "les1 tile kernel launch failed"); return VFS_ERR_CUDA; }
+    Les1March prog = {d};
+    if (run_filter_march<Les1March, 1>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les1 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
-#endif
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
   c->sabs_valid = true;
@@ -875,10 +874,10 @@ static int les_cs(vfs_ctx *c) {
   RUN(g2l(c, g2));                                                    // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
   ev_rec(c, 2 * VFS_T_LES3);
-#ifndef VFS_EMU
-  if (c->fused && c->tma_ok && !d.testfilter_ik) {
+  if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    if (launch_les3_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 tile kernel launch failed"); return VFS_ERR_CUDA; }
+    Les3March prog = {d};
+    if (run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
     LesPass3 f = {d};      // cells next to a periodic plane (ghost-image fetches): thin slabs
     if (d.perx) { Box b0 = bi, b1 = bi; b0.i1 = 2; b1.i0 = d.mx - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     if (d.pery) { Box b0 = bi, b1 = bi; b0.j1 = 2; b1.j0 = d.my - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
@@ -887,7 +886,6 @@ static int les_cs(vfs_ctx *c) {
       RUN(launch(c, b0, f)); RUN(launch(c, b1, f));
     }
   } else
-#endif
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
   { LesClipBoundary f = {d}; RUN(launch_shell(c, 0, d.nzl, f)); }     // les.c:967-980 (boundary nodes; interior clip is in pass 3)

@@ -217,6 +217,210 @@ static inline int run_les2_march(void *, const Les2March &P, int k0, int k1, lon
 }
 #endif
 
+// ---- LES pass 1 (les.c:199-246): grad u, |S|, test-filtered velocity + the per-node products of pass 2 ----
+// Same block-program shape: the test filter of u (weights w = 1/aj, 0 where nvert > 0.1) is four separable
+// (1,4,1)^3 sums (w, w u_a); the centre-difference stencil of grad u takes its i/j neighbours from a third
+// exchange buffer holding the plane's u and nvert and its k neighbours from the thread's own column.
+struct Les1March {
+  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 4;
+  static constexpr int OFF_A = NV * NT, OFF_U = 2 * NV * NT;
+  static constexpr long SMEM_D = 3L * NV * NT;
+  struct State { double v[NV]; double uk[6], nvk[2], iaj0; };
+  VfsDev d;
+  static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
+  static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
+  VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
+  VFS_HD static int jorg(int by) { return by * (TY - 2); }
+  struct Acc {        // u / nvert of plane k from the exchange buffer, planes k-1/k+1 from registers; own metrics from global
+    const double *su; double uk[6], nvk[2]; const VfsDev &d; long p;
+    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? su[a * NT + dj * TX + di] : (dk < 0 ? uk[a] : uk[3 + a]); }
+    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? su[3 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
+    VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
+    VFS_HD double aj() const { return d.s[S_AJ][p]; }
+  };
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    double K[NV] = {0, 0, 0, 0}, u0[3] = {0, 0, 0}, nv0 = 0;
+    st.iaj0 = 0;
+    if (i <= d.mx - 1 && j <= d.my - 1) {
+      const long p = d.idx(i, j, k);
+#pragma unroll
+      for (int dk = -1; dk <= 1; dk++) {
+        const long n = p + dk * d.sk;
+        const double nv = d.s[S_NV][n], ia = d.s[S_IAJ][n];
+        const double u[3] = {d.s[S_U0][n], d.s[S_U1][n], d.s[S_U2][n]};
+        const double w = nv > 0.1 ? 0. : ia;
+        const double sw = dk == 0 ? 4. * w : w;
+        K[0] += sw; K[1] += sw * u[0]; K[2] += sw * u[1]; K[3] += sw * u[2];
+        if (dk == 0) { u0[0] = u[0]; u0[1] = u[1]; u0[2] = u[2]; nv0 = nv; st.iaj0 = ia; }
+        else { const int o = dk < 0 ? 0 : 3; st.uk[o] = u[0]; st.uk[o + 1] = u[1]; st.uk[o + 2] = u[2]; st.nvk[dk < 0 ? 0 : 1] = nv; }
+      }
+    }
+    double *sU = sm + OFF_U;
+#pragma unroll
+    for (int a = 0; a < NV; a++) { st.v[a] = K[a]; sm[a * NT + tid] = K[a]; }
+    sU[tid] = u0[0]; sU[NT + tid] = u0[1]; sU[2 * NT + tid] = u0[2]; sU[3 * NT + tid] = nv0;
+  }
+  VFS_HD void phase1(State &st, int tid, double *sm) const {
+    const int tx = tid % TX;
+    const int l = tx > 0 ? tid - 1 : tid, r = tx < TX - 1 ? tid + 1 : tid;
+    double *sA = sm + OFF_A;
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const double A = sm[a * NT + l] + 4. * st.v[a] + sm[a * NT + r];
+      st.v[a] = A; sA[a * NT + tid] = A;
+    }
+  }
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
+    const long p = d.idx(i, j, k);
+    Acc A = {sm + OFF_U + tid, {st.uk[0], st.uk[1], st.uk[2], st.uk[3], st.uk[4], st.uk[5]}, {st.nvk[0], st.nvk[1]}, d, p};
+    const double nv0 = A.nv(0, 0, 0);
+    const double u0 = A.u(0, 0, 0, 0), u1 = A.u(1, 0, 0, 0), u2 = A.u(2, 0, 0, 0);
+    double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, S = 0, uf[3] = {0, 0, 0};
+    if (!(nv0 > 1.1)) {      // skipped cells keep the zeros of the reference's freshly created work vectors
+      grad_center_a(d, A, i, j, k + d.kofs, p, g);
+      S = sabs_of(g);
+      const double *sA = sm + OFF_A;
+      const int up = tid - TX, dn = tid + TX;
+      const double ws = sA[up] + 4. * st.v[0] + sA[dn];
+#pragma unroll
+      for (int a = 0; a < 3; a++) uf[a] = (sA[(1 + a) * NT + up] + 4. * st.v[1 + a] + sA[(1 + a) * NT + dn]) / ws;
+    }
+    d.s[S_SABS][p] = S;
+#pragma unroll
+    for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = uf[a];
+    // per-node quantities pass 2 filters (les_derive_store)
+    d.s[S_LW][p] = nv0 > 0.1 ? 0. : st.iaj0;
+    d.s[S_LU0][p] = u0 * A.met(0) + u1 * A.met(1) + u2 * A.met(2);
+    d.s[S_LU1][p] = u0 * A.met(3) + u1 * A.met(4) + u2 * A.met(5);
+    d.s[S_LU2][p] = u0 * A.met(6) + u1 * A.met(7) + u2 * A.met(8);
+    d.s[S_LSS0][p] = (0.5 * (g[0][0] + g[0][0])) * S; d.s[S_LSS1][p] = (0.5 * (g[0][1] + g[1][0])) * S; d.s[S_LSS2][p] = (0.5 * (g[0][2] + g[2][0])) * S;
+    d.s[S_LSS3][p] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][p] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][p] = (0.5 * (g[2][2] + g[2][2])) * S;
+  }
+};
+#ifndef VFS_EMU
+template <class M, int MINB> __global__ void __launch_bounds__(M::NT, MINB) k_filter_march(const M P, int kbeg, int kend, int kchunk) {
+  extern __shared__ __align__(16) double vfs_fm_sm[];
+  double *sm = vfs_fm_sm;
+  const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+  const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
+  typename M::State st;
+  for (int k = ka; k < kb; k++) {
+    P.phase0(st, tid, bx, by, k, sm);
+    __syncthreads();
+    P.phase1(st, tid, sm);
+    __syncthreads();
+    P.phase2(st, tid, bx, by, k, sm);
+    if (M::SMEM_D > 2L * M::NV * M::NT) __syncthreads();      // a third buffer written in phase 0 is still read in phase 2
+  }
+}
+template <class M, int MINB> static inline int run_filter_march(cudaStream_t stream, const M &P, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  const int bytes = (int)(M::SMEM_D * sizeof(double));
+  static bool attr_set = false;
+  if (!attr_set && bytes > 48 * 1024) {
+    if (cudaFuncSetAttribute(k_filter_march<M, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  const int ntx = M::tiles_x(P.d), nty = M::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16, 148 * MINB);
+  dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk);
+  k_filter_march<M, MINB><<<grd, M::NT, bytes, stream>>>(P, k0, k1, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#else
+template <class M, int MINB> static inline int run_filter_march(void *, const M &P, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  std::vector<double> smv(M::SMEM_D);
+  std::vector<typename M::State> st(M::NT);
+  const int ntx = M::tiles_x(P.d), nty = M::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 4, 7);
+  for (int bz = 0; bz * kchunk < k1 - k0; bz++)
+    for (int by = 0; by < nty; by++)
+      for (int bx = 0; bx < ntx; bx++) {
+        const int ka = k0 + bz * kchunk, kb = k1 < ka + kchunk ? k1 : ka + kchunk;
+        for (int k = ka; k < kb; k++) {
+          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, smv.data());
+          for (int t = 0; t < M::NT; t++) P.phase1(st[t], t, smv.data());
+          for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, smv.data());
+        }
+      }
+  (*launches)++;
+  return 0;
+}
+#endif
+
+// ---- LES pass 3 (les.c:716-796, 967-980): Simpson filter of LM, MM -> Cs, separable ---------------------
+// The weight of a neighbour node in this filter depends on that node alone (1/aj, zero where nvert > 1.1 or
+// on non-periodic domain ghosts, with the J == 0-only quirk of les.c:756), so sum(s w LM), sum(s w MM) and
+// sum(s w) are three separable (1,4,1)^3 filters of per-node products: k pass from the thread's own
+// column, i and j passes through two small shared-memory exchange buffers (the 27-term gather it replaces
+// was bound by shared-memory bandwidth, profiles/r01m).  Cells next to a periodic plane (ghost-image
+// fetches, les.c:738-768) are skipped here and done by the staged kernel on thin slabs.
+struct Les3March {
+  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 3;
+  static constexpr long SMEM_D = 2L * NV * NT;
+  struct State { double v[NV]; double nvc; };
+  VfsDev d;
+  static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
+  static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
+  VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
+  VFS_HD static int jorg(int by) { return by * (TY - 2); }
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    double K[NV] = {0, 0, 0};
+    st.nvc = 0;
+    if (i <= d.mx - 1 && j <= d.my - 1) {
+      const long p = d.idx(i, j, k);
+      const bool zij = (!d.perx && (i == 0 || i == d.mx - 1)) || (!d.pery && j == 0);
+#pragma unroll
+      for (int dk = -1; dk <= 1; dk++) {
+        const long n = p + dk * d.sk;
+        const int K_ = k + dk + d.kofs;
+        const double nv = d.s[S_NV][n];
+        double w = d.s[S_IAJ][n];
+        if (nv > 1.1 || zij || (!d.perz && (K_ == 0 || K_ == d.mz - 1))) w = 0;
+        const double sw = dk == 0 ? 4. * w : w;
+        K[0] += sw; K[1] += sw * d.s[S_LM][n]; K[2] += sw * d.s[S_MM][n];
+        if (dk == 0) st.nvc = nv;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NV; a++) { st.v[a] = K[a]; sm[a * NT + tid] = K[a]; }
+  }
+  VFS_HD void phase1(State &st, int tid, double *sm) const {
+    const int tx = tid % TX;
+    const int l = tx > 0 ? tid - 1 : tid, r = tx < TX - 1 ? tid + 1 : tid;
+    double *sA = sm + NV * NT;
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const double A = sm[a * NT + l] + 4. * st.v[a] + sm[a * NT + r];
+      st.v[a] = A; sA[a * NT + tid] = A;
+    }
+  }
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
+    const int kg = k + d.kofs;
+    if ((d.perx && (i == 1 || i == d.mx - 2)) || (d.pery && (j == 1 || j == d.my - 2)) || (d.perz && (kg == 1 || kg == d.mz - 2))) return;
+    const long p = d.idx(i, j, k);
+    if (st.nvc > 1.1) { d.s[S_CS][p] = 0; return; }
+    const double *sA = sm + NV * NT;
+    const int up = tid - TX, dn = tid + TX;
+    const double ws = sA[up] + 4. * st.v[0] + sA[dn];
+    const double lm = sA[NT + up] + 4. * st.v[1] + sA[NT + dn];
+    const double mmv = sA[2 * NT + up] + 4. * st.v[2] + sA[2 * NT + dn];
+    const double C = 0.5 * (lm / ws) / (mmv / ws + 1.e-4);
+    double cs = C > 0 ? C : 0;
+    if (st.nvc > 0.1 && st.nvc < 1.1) cs = cs > 0.001 ? cs : 0.001;      // clip chain, les.c:967-980
+    cs = cs > 0 ? cs : 0;
+    cs = cs < d.max_cs ? cs : d.max_cs;
+    d.s[S_CS][p] = cs;
+  }
+};
 // ---- fused residual: face fluxes -> Fp -> projection -> assembly (regular interior) ----------------
 // Replaces, for the cells whose whole dependency cone is free of domain-end special cases, the staged
 // chain FaceFlux<0,1,2> -> FpCell -> ProjectSNES/ProjectAdd (momentum.c:669-1938, 2297-2331): the 18
