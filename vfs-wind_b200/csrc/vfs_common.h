@@ -21,6 +21,14 @@
 
 #define VFS_G 4
 
+// warp-uniform "does any active lane see x": the mask-free fast paths branch on it so a warp never
+// diverges; the host emulation (one "thread" at a time) just tests its own value
+#if defined(__CUDA_ARCH__)
+#define VFS_WARP_ANY(x) (__any_sync(__activemask(), (x)) != 0)
+#else
+#define VFS_WARP_ANY(x) (x)
+#endif
+
 // internal scalar ids ------------------------------------------------------------------------
 enum {
   S_X = 0, S_Y, S_Z,                                  // node coordinates
@@ -46,8 +54,9 @@ enum {
   S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5,
   S_IAJ,                                                                 // 1/aj (cell volume), filter weight
   // LES factors that depend on the grid and the nvert mask only (LesGeo, vfs_les_kernels.h):
-  // 1/sum(s*w), test_filter^2, filter^2 and the covariant metric tensor G (00,11,22,01,02,12)
-  S_LFINV, S_LTF2, S_LF2, S_LG0, S_LG1, S_LG2, S_LG3, S_LG4, S_LG5,
+  // 1/sum(s*w), test_filter^2, filter^2 and the inverse of [csi;eta;zet] (row-major x_csi x_eta x_zet y_csi ...;
+  // rhs2.c:595-611 builds the covariant metric tensor G from it, les.c:607-622)
+  S_LFINV, S_LTF2, S_LF2, S_LG0, S_LG1, S_LG2, S_LG3, S_LG4, S_LG5, S_LG6, S_LG7, S_LG8,
   S_WM,                                                                  // wall-model nu_t of the j = 0 faces (plane j = 0 only)
   S_COUNT
 };
@@ -65,6 +74,10 @@ struct VfsDev {
   int ti, tistart, rstart_flg, bdf2, single_rank;
   double ren, dt, max_cs;
   double *s[S_COUNT];
+  // near[p] != 0: some node within +-2 of p (any direction) has nvert != 0 (NearSolid, vfs_c2c_kernels.h).
+  // Warps whose nodes are all "far" run mask-free specialisations of the stencil code (same arithmetic:
+  // every nvert comparison is known to be false), see VFS_WARP_ANY.
+  const unsigned char *near;
   VFS_HD long idx(int i, int j, int k) const { return org + (long)k * sk + (long)j * sj + i; }
 };
 

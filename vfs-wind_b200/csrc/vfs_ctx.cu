@@ -87,6 +87,8 @@ struct vfs_ctx {
   CUtensorMap tmap_flux;         // same pool, box (TX+4, TY+3, 1, 1)
   CUtensorMap tmap_rhs;          // same pool, box of the residual marching kernel
   CUtensorMap tmap_les2;         // same pool, box (32, 16): operand tiles of the LES pass-2 marching kernel
+  CUtensorMap tmap_les2_8;       // same pool, box (32, 8)
+  CUtensorMap tmap_les2_12;      // same pool, box (32, 12)
 #endif
   bool tma_ok = false;
 #ifndef VFS_EMU
@@ -103,9 +105,15 @@ struct vfs_ctx {
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
+  int les2_ty = 12;              // tile height of the LES pass-2 block program: 16 (1 block/SM) or 8 (2 blocks/SM) (option key 2)
+  int les1_var = 1;              // LES pass 1: 0 = block program 32x16, 1 = TMA tile march, 2 = block program 32x8 x2/SM, 3 = 32x16 x2/SM (option key 4)
+  int les3_var = 0;              // LES pass 3: 0 = block program 32x16 x2/SM, 1 = TMA tile march (option key 5)
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
   bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
+  unsigned char *near = nullptr; // near-solid byte mask (VfsDev::near), one byte per padded node
+  bool near_valid = false;
+  int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
 };
 
 static void graph_reset(vfs_ctx *c);
@@ -342,19 +350,25 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   if (e != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (no CPU fallback exists)"; delete c; return VFS_ERR_CUDA; }
   e = cudaMalloc((void **)&c->pool, bytes);
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->stage, sbytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&c->near, (size_t)c->scalar_len);
   if (e != cudaSuccess) { g_create_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); delete c; return VFS_ERR_CUDA; }
   cudaMemset(c->pool, 0, bytes);
+  cudaMemset(c->near, 1, (size_t)c->scalar_len);
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true;
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) cudaEventCreate(&c->ev[q]);
 #else
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
+  c->near = (unsigned char *)malloc((size_t)c->scalar_len); memset(c->near, 1, (size_t)c->scalar_len);
 #endif
   for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
+  c->d.near = c->near;
 #ifndef VFS_EMU
   c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
               vfs_make_tensor_map(&c->tmap_flux, c->pool, c->d, c->scalar_len, VFS_TILE_TX + VFS_FLUX_HX, VFS_TILE_TY + VFS_FLUX_HY) == 0 &&
               vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0 &&
-              vfs_make_tensor_map(&c->tmap_les2, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY) == 0;
+              vfs_make_tensor_map(&c->tmap_les2, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2_8, c->pool, c->d, c->scalar_len, Les2March8::TX, Les2March8::TY) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2_12, c->pool, c->d, c->scalar_len, Les2March12::TX, Les2March12::TY) == 0;
 #endif
   *out = c;
   return 0;
@@ -367,12 +381,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); cudaFree(c->stage);
+  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage); free(c->wm_table);
+  free(c->pool); free(c->stage); free(c->wm_table); free(c->near);
 #endif
   delete c; return 0;
 }
@@ -382,7 +396,7 @@ extern "C" int vfs_set_params(vfs_ctx *c, const vfs_params *p) {
   if (p->mx != c->prm.mx || p->my != c->prm.my || p->mz != c->prm.mz || p->nzl != c->prm.nzl || p->kofs != c->prm.kofs || p->nranks != c->prm.nranks) { set_err(c, "geometry cannot change"); return VFS_ERR_ARG; }
   std::string why; int r = check_params(p, why); if (r) { set_err(c, why); return r; }
   graph_reset(c);
-  c->prm = *p; double *sv[S_COUNT]; memcpy(sv, c->d.s, sizeof(sv)); fill_dev(c); memcpy(c->d.s, sv, sizeof(sv)); return 0;
+  c->prm = *p; double *sv[S_COUNT]; memcpy(sv, c->d.s, sizeof(sv)); fill_dev(c); memcpy(c->d.s, sv, sizeof(sv)); c->d.near = c->near; return 0;
 }
 extern "C" int vfs_set_stream(vfs_ctx *c, void *s) {
   if (!c) return VFS_ERR_ARG;
@@ -459,7 +473,11 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   if (!c) return VFS_ERR_ARG;
   if (key == 0) c->fused = value;
   else if (key == 1) c->use_graph = value;
+  else if (key == 2) c->les2_ty = value;
   else if (key == 3) c->flux_minb = value;
+  else if (key == 4) c->les1_var = value;
+  else if (key == 5) c->les3_var = value;
+  else if (key == 6) { c->fastpath = value; c->near_valid = false; }
   graph_reset(c);
   return 0;
 }
@@ -519,6 +537,7 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_AJ) c->iaj_valid = false;
   if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
+  if (field == VFS_NVERT) c->near_valid = false;
   if (field == VFS_NVERT) {       // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep
     const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx;
     bool any = false;
@@ -661,6 +680,21 @@ static int ensure_iaj(vfs_ctx *c) {
   return 0;
 }
 
+// near-solid byte mask (see NearSolid); with the fast paths switched off every node reads "near"
+static int ensure_near(vfs_ctx *c) {
+  if (c->near_valid) return 0;
+  const VfsDev &d = c->d;
+#ifndef VFS_EMU
+  if (c->capturing) { set_err(c, "near-solid mask must be built before graph capture"); return VFS_ERR_CUDA; }
+  CK(cudaMemsetAsync(c->near, 1, (size_t)c->scalar_len, c->stream));
+#else
+  memset(c->near, 1, (size_t)c->scalar_len);
+#endif
+  if (c->fastpath) { NearSolid f = {d, c->near}; Box b = {-2, d.mx + 2, -2, d.my + 2, -2, d.nzl + 2}; RUN(launch(c, b, f)); }
+  c->near_valid = true;
+  return 0;
+}
+
 // Cabot wall model at the j = 0 faces (viscosity_wallmodel, momentum.c:1139-1154): table once, then one
 // Newton solve per face of the plane, before the flux kernels read the override
 static int wall_model(vfs_ctx *c) {
@@ -685,6 +719,7 @@ static int wall_model(vfs_ctx *c) {
 static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const VfsDev &d = c->d;
   RUN(ensure_iaj(c));
+  RUN(ensure_near(c));
   if (d.visc_wm && d.les) RUN(wall_model(c));
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
@@ -841,11 +876,19 @@ static int les_cs(vfs_ctx *c) {
   if (d.ti < 2 && d.tistart == 0 && !d.rstart_flg) { FillScalar f = {d, S_CS, 0.0}; return launch(c, all, f); }   // les.c:77-80
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   RUN(ensure_iaj(c));
+  RUN(ensure_near(c));
   ev_rec(c, 2 * VFS_T_LES1);
   if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    Les1March prog = {d};
-    if (run_filter_march<Les1March, 1>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les1 march kernel launch failed"); return VFS_ERR_CUDA; }
+    int r;
+#ifndef VFS_EMU
+    if (c->les1_var == 1 && c->tma_ok) r = launch_les1_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches);
+    else if (c->les1_var == 2) { Les1March8 prog = {d}; r = run_filter_march<Les1March8, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
+    else if (c->les1_var == 3) { Les1March prog = {d}; r = run_filter_march<Les1March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
+    else
+#endif
+    { Les1March prog = {d}; r = run_filter_march<Les1March, 1>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
+    if (r) { set_err(c, "les1 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else
   { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
@@ -860,11 +903,15 @@ static int les_cs(vfs_ctx *c) {
   if (c->fused && !d.testfilter_ik && les2_march_ok(c)) {
     Box bi = box_interior(c);
     if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
-    Les2March prog = {d};
+    int r;
 #ifndef VFS_EMU
-    int r = run_les2_march(c->stream, c->tmap_les2, prog, bi.k0, bi.k1, &c->launches);
+    if (c->les2_ty == 8) { Les2March8 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_8, prog, bi.k0, bi.k1, &c->launches); }
+    else if (c->les2_ty == 12) { Les2March12 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_12, prog, bi.k0, bi.k1, &c->launches); }
+    else { Les2March prog = {d}; r = run_les2_march(c->stream, c->tmap_les2, prog, bi.k0, bi.k1, &c->launches); }
 #else
-    int r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches);
+    if (c->les2_ty == 8) { Les2March8 prog = {d}; r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches); }
+    else if (c->les2_ty == 12) { Les2March12 prog = {d}; r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches); }
+    else { Les2March prog = {d}; r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches); }
 #endif
     if (r) { set_err(c, "les2 march kernel launch failed"); return VFS_ERR_CUDA; }
   } else

@@ -200,21 +200,23 @@ struct Les3Body {
 // exactly once.  Faces with index 0 or m-2 along their normal (domain-end / periodic-end stencils) are
 // left to the staged FaceFlux<D> kernels, which the host runs on those thin slabs only.
 typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 5, 4, 3, 1, 1, 1, 2> RingFlux;
-struct FluxAcc {
+// FLUID = true: every nvert the face stencils read is known to be 0 (VfsDev::near), so nv() is the
+// literal 0 and the compiler drops the stencil switches, the QUICK / collapse branches and the
+// one-sided nu_t picks; the surviving arithmetic is the masked code's with all predicates false.
+template <bool FLUID> struct FluxAccT {
   TileAcc<RingFlux> T; const VfsDev &d; long p;
   __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
-  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return FLUID ? 0. : T.get(3, di, dj, dk); }
   template <int D> __device__ __forceinline__ long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
   template <int D> __device__ __forceinline__ double met(int s, int side) const { return d.s[S_CSI0 + s][p + side * sn<D>()]; }
   template <int D> __device__ __forceinline__ double iaj(int side) const { return d.s[S_IAJ][p + side * sn<D>()]; }
   template <int D> __device__ __forceinline__ double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
   template <int D> __device__ __forceinline__ double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
 };
+typedef FluxAccT<false> FluxAcc;
 struct FluxBody {
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
-    const int kg = k + d.kofs;
-    const long p = d.idx(i, j, k);
-    FluxAcc A = {T, d, p};
+  template <bool FLUID> __device__ __forceinline__ void run(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int kg, long p) const {
+    FluxAccT<FLUID> A = {T, d, p};
     double fc[3], fv[3];
     if (i <= d.mx - 3) {
       face_flux_core<0, true>(d, A, i, fc, fv);
@@ -231,6 +233,11 @@ struct FluxBody {
 #pragma unroll
       for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
     }
+  }
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    if (VFS_WARP_ANY(d.near[p] != 0)) run<false>(d, T, i, j, k + d.kofs, p);
+    else run<true>(d, T, i, j, k + d.kofs, p);
   }
 };
 

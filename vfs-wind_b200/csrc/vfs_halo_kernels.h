@@ -79,6 +79,20 @@ struct NodeCopy {
   }
 };
 
+// near-solid byte mask (VfsDev::near): 1 where any node of the 5x5x5 cube around the node has nvert != 0.
+// Evaluated on the owned nodes grown by 2 (the cube then stays inside the G = 4 ghost frame, whose
+// nvert values are the wrap / neighbour-rank images); everything outside keeps the initial 1.
+struct NearSolid {
+  VfsDev d; unsigned char *out;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    const double *nv = d.s[S_NV];
+    bool any = false;
+    for (int c = -2; c <= 2; c++) for (int b = -2; b <= 2; b++) for (int a = -2; a <= 2; a++) any = any || (nv[p + c * d.sk + b * d.sj + a] != 0.);
+    out[p] = any ? 1 : 0;
+  }
+};
+
 struct FillScalar {
   VfsDev d; int sid; double v;
   VFS_HD void operator()(int i, int j, int k) const { d.s[sid][d.idx(i, j, k)] = v; }

@@ -27,7 +27,7 @@ template <int S0> struct GlobalAccS {
   VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S0 + a][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double iaj(int di, int dj, int dk) const { return d.s[S_IAJ][p + di + dj * d.sj + dk * d.sk]; }
-  // the cell's own centre metrics (s = 0..8: csi, eta, zet), aj, and LES grid factors (q = 0..8: S_LFINV..S_LG5)
+  // the cell's own centre metrics (s = 0..8: csi, eta, zet), aj, and LES grid factors (q = 0..11: S_LFINV..S_LG8)
   VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
   VFS_HD double aj() const { return d.s[S_AJ][p]; }
   VFS_HD double geo(int q) const { return d.s[S_LFINV + q][p]; }
@@ -47,20 +47,31 @@ template <int T, class Acc> VFS_HD double dcen(const Acc &A, int a, int c, int m
 }
 
 // velocity gradient at a cell centre: g[a][b] = d u_a / d x_b  (k-omega.c:605-618)
-template <class Acc> VFS_HD void grad_center_a(const VfsDev &d, const Acc &A, int i, int j, int kg, long, double g[3][3]) {
+// PLAIN = true: the caller knows that no stencil switch fires (no nvert != 0 nearby, not next to a
+// domain end), so every difference is the centred one — the value the selects would produce.
+template <bool PLAIN = false, class Acc> VFS_HD void grad_center_a(const VfsDev &d, const Acc &A, int i, int j, int kg, long, double g[3][3]) {
   const double ajc = A.aj();
   const double c0 = A.met(0), c1 = A.met(1), c2 = A.met(2);
   const double e0 = A.met(3), e1 = A.met(4), e2 = A.met(5);
   const double z0 = A.met(6), z1 = A.met(7), z2 = A.met(8);
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    const double dc = dcen<0>(A, a, i, d.mx, d.perx, 1);
-    const double de = dcen<1>(A, a, j, d.my, d.pery, 1);
-    const double dz = dcen<2>(A, a, kg, d.mz, d.perz, 0);
+    double dc, de, dz;
+    if (PLAIN) {
+      dc = (A.u(a, 1, 0, 0) - A.u(a, -1, 0, 0)) * 0.5; de = (A.u(a, 0, 1, 0) - A.u(a, 0, -1, 0)) * 0.5; dz = (A.u(a, 0, 0, 1) - A.u(a, 0, 0, -1)) * 0.5;
+    } else {
+      dc = dcen<0>(A, a, i, d.mx, d.perx, 1); de = dcen<1>(A, a, j, d.my, d.pery, 1); dz = dcen<2>(A, a, kg, d.mz, d.perz, 0);
+    }
     g[a][0] = (dc * c0 + de * e0 + dz * z0) * ajc;
     g[a][1] = (dc * c1 + de * e1 + dz * z1) * ajc;
     g[a][2] = (dc * c2 + de * e2 + dz * z2) * ajc;
   }
+}
+// warp-uniform choice between the two (VfsDev::near, VFS_WARP_ANY)
+template <class Acc> VFS_HD void grad_center_auto(const VfsDev &d, const Acc &A, int i, int j, int kg, long p, double g[3][3]) {
+  const bool special = d.near[p] != 0 || i <= 1 || i >= d.mx - 2 || j <= 1 || j >= d.my - 2 || kg <= 1 || kg >= d.mz - 2;
+  if (VFS_WARP_ANY(special)) grad_center_a<false>(d, A, i, j, kg, p, g);
+  else grad_center_a<true>(d, A, i, j, kg, p, g);
 }
 VFS_HD void grad_center(const VfsDev &d, int su, int i, int j, int kg, long p, double g[3][3]) {
   if (su == S_U0) { GlobalAccS<S_U0> A = {d, p}; grad_center_a(d, A, i, j, kg, p, g); }
@@ -120,7 +131,7 @@ template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i,
     return;
   }
   double g[3][3];
-  grad_center_a(d, A, i, j, kg, p, g);
+  grad_center_auto(d, A, i, j, kg, p, g);
   const double S = sabs_of(g);
   d.s[S_SABS][p] = S;
   les_derive_store(d, p, g, S);
@@ -259,58 +270,41 @@ struct LesGeo {
     const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
     const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
     const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
-    d.s[S_LG0][p] = xcsi * xcsi + ycsi * ycsi + zcsi * zcsi;
-    d.s[S_LG1][p] = xeta * xeta + yeta * yeta + zeta * zeta;
-    d.s[S_LG2][p] = xzet * xzet + yzet * yzet + zzet * zzet;
-    d.s[S_LG3][p] = xeta * xcsi + yeta * ycsi + zeta * zcsi;
-    d.s[S_LG4][p] = xzet * xcsi + yzet * ycsi + zzet * zcsi;
-    d.s[S_LG5][p] = xeta * xzet + yeta * yzet + zeta * zzet;
+    d.s[S_LG0][p] = xcsi; d.s[S_LG1][p] = xeta; d.s[S_LG2][p] = xzet;
+    d.s[S_LG3][p] = ycsi; d.s[S_LG4][p] = yeta; d.s[S_LG5][p] = yzet;
+    d.s[S_LG6][p] = zcsi; d.s[S_LG7][p] = zeta; d.s[S_LG8][p] = zzet;
   }
 };
 
 // les.c:470-669 given the 15 filtered sums f[0..8] = sum sw U_a u_b (a-major), f[9..14] = sum sw |S|S_ij
-// and the precomputed factors above.  M^c is symmetric (S, S^ are), and the two triple sums
-// LM = L_ba M_aq G_bq, MM = M_nm M_nl G_ml are evaluated as (L M):G and (M^T M):G — 63 multiply-adds
-// instead of 162; the result differs from the literal triple loops by rounding only.
+// and the precomputed factors above.  With A = [csi;eta;zet], the reference rotates the symmetric
+// Cartesian tensor M^c to M = M^c A^T and contracts with the covariant metric tensor G = (A A^T)^-1:
+//   MM = sum M_nm M_nl G_ml  = tr(A M^cT M^c A^T (A A^T)^-1) = |M^c|_F^2          (A^T (A A^T)^-1 A = I)
+//   LM = sum L_ba M_aq G_bq  = tr(L M^c A^T (A A^T)^-1)      = tr(L M^c A^-1)     (A^T (A A^T)^-1 = A^-1)
+// so neither M nor G is formed: 6 + 36 multiply-adds instead of the 162 of the literal triple loops,
+// and the metric-independent MM loses the rounding of the rotation.  Agrees with the reference to
+// rounding (tests: <= 1e-12 on Cs, nu_t).
 template <class Ops> VFS_HD void les2_finish_geo(const VfsDev &d, const Ops &O, int i, int j, int kg, long p, const double *f) {
-  const double csi[3] = {O.met(0), O.met(1), O.met(2)};
-  const double eta[3] = {O.met(3), O.met(4), O.met(5)};
-  const double zet[3] = {O.met(6), O.met(7), O.met(8)};
   const double finv = O.geo(0), tf2 = O.geo(1), f2 = O.geo(2);
-  const double _u[3] = {O.u(0, 0, 0, 0), O.u(1, 0, 0, 0), O.u(2, 0, 0, 0)};
-  const double _U[3] = {_u[0] * csi[0] + _u[1] * csi[1] + _u[2] * csi[2], _u[0] * eta[0] + _u[1] * eta[1] + _u[2] * eta[2], _u[0] * zet[0] + _u[1] * zet[1] + _u[2] * zet[2]};
   double gh[3][3];
-  grad_center_a(d, O, i, j, kg, p, gh);
+  grad_center_auto(d, O, i, j, kg, p, gh);
   const double S_hat = sabs_of(gh);
   const double tS = -tf2 * S_hat;
   // symmetric M^c: xx, xy, xz, yy, yz, zz
   const double mc0 = tS * (0.5 * (gh[0][0] + gh[0][0])) + f2 * (f[9] * finv), mc1 = tS * (0.5 * (gh[0][1] + gh[1][0])) + f2 * (f[10] * finv);
   const double mc2 = tS * (0.5 * (gh[0][2] + gh[2][0])) + f2 * (f[11] * finv), mc3 = tS * (0.5 * (gh[1][1] + gh[1][1])) + f2 * (f[12] * finv);
   const double mc4 = tS * (0.5 * (gh[1][2] + gh[2][1])) + f2 * (f[13] * finv), mc5 = tS * (0.5 * (gh[2][2] + gh[2][2])) + f2 * (f[14] * finv);
+  const double den = (mc0 * mc0 + mc3 * mc3 + mc5 * mc5) + 2. * (mc1 * mc1 + mc2 * mc2 + mc4 * mc4);
   const double Mc[3][3] = {{mc0, mc1, mc2}, {mc1, mc3, mc4}, {mc2, mc4, mc5}};
-  double M[3][3], L[3][3];
+  const double _u[3] = {O.u(0, 0, 0, 0), O.u(1, 0, 0, 0), O.u(2, 0, 0, 0)};
+  double num = 0;
 #pragma unroll
-  for (int a = 0; a < 3; a++) {
-    M[a][0] = Mc[a][0] * csi[0] + Mc[a][1] * csi[1] + Mc[a][2] * csi[2];
-    M[a][1] = Mc[a][0] * eta[0] + Mc[a][1] * eta[1] + Mc[a][2] * eta[2];
-    M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
+  for (int b = 0; b < 3; b++) {
+    const double Ub = _u[0] * O.met(3 * b) + _u[1] * O.met(3 * b + 1) + _u[2] * O.met(3 * b + 2);     // filtered contravariant velocity
+    const double L0 = f[3 * b] * finv - Ub * _u[0], L1 = f[3 * b + 1] * finv - Ub * _u[1], L2 = f[3 * b + 2] * finv - Ub * _u[2];
 #pragma unroll
-    for (int b = 0; b < 3; b++) L[a][b] = f[3 * a + b] * finv - _U[a] * _u[b];
+    for (int c = 0; c < 3; c++) num += (L0 * Mc[0][c] + L1 * Mc[1][c] + L2 * Mc[2][c]) * O.geo(3 + 3 * c + b);   // A^-1[c][b]
   }
-  const double g0 = O.geo(3), g1 = O.geo(4), g2 = O.geo(5), g3 = O.geo(6), g4 = O.geo(7), g5 = O.geo(8);
-  const double G[3][3] = {{g0, g3, g4}, {g3, g1, g5}, {g4, g5, g2}};
-  double num = 0, den = 0;
-#pragma unroll
-  for (int b = 0; b < 3; b++)
-#pragma unroll
-    for (int q = 0; q < 3; q++) num += (L[b][0] * M[0][q] + L[b][1] * M[1][q] + L[b][2] * M[2][q]) * G[b][q];
-#pragma unroll
-  for (int m = 0; m < 3; m++)
-#pragma unroll
-    for (int l = m; l < 3; l++) {
-      const double n = M[0][m] * M[0][l] + M[1][m] * M[1][l] + M[2][m] * M[2][l];
-      den += (l == m ? n : 2. * n) * G[m][l];
-    }
   d.s[S_LM][p] = num; d.s[S_MM][p] = den;
 }
 

@@ -45,13 +45,15 @@ static inline int pick_kchunk(int ntiles, int nk, int min_chunk, int nsm = 148) 
 // are staged by TMA into shared memory while phases 0 and 1 run: the warp that finishes phase 2 last
 // issues the copies for the next plane, so nobody waits to refill the single buffer and the ~30
 // scattered global loads that stalled the finish (profiles/r01j) become shared-memory reads.
-struct Les2March {
-  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 15, NOP = 23;
+template <int TY_> struct Les2MarchT {
+  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15, NOP = 26;
+  static constexpr int MINB = TY_ <= 8 ? 2 : 1;                      // resident blocks per SM the tile is sized for
   static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_BAR = OFF_OP + NOP * NT;
   static constexpr long SMEM_D = OFF_BAR + 2;
-  // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..18 LFINV,LTF2,LF2,LG0..5 | 19..21 UF | 22 nvert
-  VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 19 ? S_LFINV + (q - 10) : (q < 22 ? S_UF0 + (q - 19) : S_NV)); }
-  struct State { double v[NV]; double ufk[6]; double nvk[2]; };
+  // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..21 LFINV,LTF2,LF2,LG0..8 | 22..24 UF | 25 nvert
+  VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 22 ? S_LFINV + (q - 10) : (q < 25 ? S_UF0 + (q - 22) : S_NV)); }
+  static constexpr int NRAW = 13;
+  struct State { double v[NV]; double ufk[6]; double nvk[2]; double win[2][NRAW]; };
   VfsDev d;
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
   static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
@@ -62,33 +64,45 @@ struct Les2March {
     VFS_HD double met(int s) const { return op[s * NT]; }
     VFS_HD double aj() const { return op[9 * NT]; }
     VFS_HD double geo(int q) const { return op[(10 + q) * NT]; }
-    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? op[(19 + a) * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
-    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? op[22 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
+    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? op[(22 + a) * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
+    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? op[25 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
   };
-  // phase 0: k pass over the thread's own column (+ the k-neighbours of UF / nvert the finish needs)
-  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+  // phase 0: k pass over the thread's own column (+ the k-neighbours of UF / nvert the finish needs).
+  // The per-node inputs of planes k-1 and k are carried in registers from the previous step (st.win),
+  // so each step fetches one new plane (13 values) instead of three: this kernel's limiter was the
+  // L2 -> SM traffic of re-reading every plane three times (profiles/r01l: 12.4 GB through L2 in 2.3 ms).
+  VFS_HD static void load_raw(const VfsDev &d, long n, double *r) {
+    r[0] = d.s[S_LW][n];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { r[1 + a] = d.s[S_U0 + a][n]; r[4 + a] = d.s[S_LU0 + a][n]; }
+#pragma unroll
+    for (int a = 0; a < 6; a++) r[7 + a] = d.s[S_LSS0 + a][n];
+  }
+  VFS_HD static void add_plane(double *K, const double *r, bool mid) {
+    const double sw = mid ? 4. * r[0] : r[0];
+    const double U0 = sw * r[4], U1 = sw * r[5], U2 = sw * r[6];
+    K[0] += U0 * r[1]; K[1] += U0 * r[2]; K[2] += U0 * r[3];
+    K[3] += U1 * r[1]; K[4] += U1 * r[2]; K[5] += U1 * r[3];
+    K[6] += U2 * r[1]; K[7] += U2 * r[2]; K[8] += U2 * r[3];
+#pragma unroll
+    for (int a = 0; a < 6; a++) K[9 + a] += sw * r[7 + a];
+  }
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, bool first, double *sm) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     double K[NV];
 #pragma unroll
     for (int a = 0; a < NV; a++) K[a] = 0;
     if (i <= d.mx - 1 && j <= d.my - 1) {
       const long p = d.idx(i, j, k);
+      if (first) { load_raw(d, p - d.sk, st.win[0]); load_raw(d, p, st.win[1]); }
+      double nw[NRAW];
+      load_raw(d, p + d.sk, nw);
 #pragma unroll
       for (int a = 0; a < 3; a++) { st.ufk[a] = d.s[S_UF0 + a][p - d.sk]; st.ufk[3 + a] = d.s[S_UF0 + a][p + d.sk]; }
       st.nvk[0] = d.s[S_NV][p - d.sk]; st.nvk[1] = d.s[S_NV][p + d.sk];
+      add_plane(K, st.win[0], false); add_plane(K, st.win[1], true); add_plane(K, nw, false);
 #pragma unroll
-      for (int dk = -1; dk <= 1; dk++) {
-        const long n = p + dk * d.sk;
-        const double w = d.s[S_LW][n];
-        const double sw = dk == 0 ? 4. * w : w;
-        const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
-        const double U0 = sw * d.s[S_LU0][n], U1 = sw * d.s[S_LU1][n], U2 = sw * d.s[S_LU2][n];
-        K[0] += U0 * u0; K[1] += U0 * u1; K[2] += U0 * u2;
-        K[3] += U1 * u0; K[4] += U1 * u1; K[5] += U1 * u2;
-        K[6] += U2 * u0; K[7] += U2 * u1; K[8] += U2 * u2;
-#pragma unroll
-        for (int a = 0; a < 6; a++) K[9 + a] += sw * d.s[S_LSS0 + a][n];
-      }
+      for (int a = 0; a < NRAW; a++) { st.win[0][a] = st.win[1][a]; st.win[1][a] = nw[a]; }
     }
 #pragma unroll
     for (int a = 0; a < NV; a++) { st.v[a] = K[a]; sm[a * NT + tid] = K[a]; }
@@ -122,13 +136,15 @@ struct Les2March {
     les2_finish_geo(d, O, i, j, k + d.kofs, p, f);
   }
 };
+typedef Les2MarchT<16> Les2March;      // one 512-thread block per SM
+typedef Les2MarchT<12> Les2March12;    // 384 threads: 170 registers per thread hold the k window without spills
+typedef Les2MarchT<8> Les2March8;      // two 256-thread blocks per SM: the phases of one block overlap the other's
 
 #ifndef VFS_EMU
 #include "vfs_fused_kernels.h"
-__global__ void __launch_bounds__(Les2March::NT, 1) k_les2_march(const __grid_constant__ CUtensorMap tmap, const Les2March P, int kbeg, int kend, int kchunk) {
+template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_march(const __grid_constant__ CUtensorMap tmap, const M P, int kbeg, int kend, int kchunk) {
   extern __shared__ __align__(128) double vfs_les2_sm[];
   double *sm = vfs_les2_sm;
-  typedef Les2March M;
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR);
   unsigned *cnt = reinterpret_cast<unsigned *>(bar + 1);
   const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
@@ -145,9 +161,9 @@ __global__ void __launch_bounds__(Les2March::NT, 1) k_les2_march(const __grid_co
     issue(ka);
   }
   __syncthreads();
-  M::State st;
+  typename M::State st;
   for (int k = ka; k < kb; k++) {
-    P.phase0(st, tid, bx, by, k, sm);
+    P.phase0(st, tid, bx, by, k, k == ka, sm);
     __syncthreads();
     P.phase1(st, tid, sm);
     __syncthreads();
@@ -165,27 +181,26 @@ __global__ void __launch_bounds__(Les2March::NT, 1) k_les2_march(const __grid_co
     }
   }
 }
-static inline int run_les2_march(cudaStream_t stream, const CUtensorMap &tmap, const Les2March &P, int k0, int k1, long *launches) {
+template <class M> static inline int run_les2_march(cudaStream_t stream, const CUtensorMap &tmap, const M &P, int k0, int k1, long *launches) {
   if (k1 <= k0) return 0;
   static bool attr_set = false;
-  const int bytes = (int)(Les2March::SMEM_D * sizeof(double));
+  const int bytes = (int)(M::SMEM_D * sizeof(double));
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_les2_march, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(k_les2_march<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -2;
     attr_set = true;
   }
-  const int ntx = Les2March::tiles_x(P.d), nty = Les2March::tiles_y(P.d);
-  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16);
+  const int ntx = M::tiles_x(P.d), nty = M::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16, 148 * M::MINB);
   dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk);
-  k_les2_march<<<grd, Les2March::NT, bytes, stream>>>(tmap, P, k0, k1, kchunk);
+  k_les2_march<M><<<grd, M::NT, bytes, stream>>>(tmap, P, k0, k1, kchunk);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 #else
-static inline int run_les2_march(void *, const Les2March &P, int k0, int k1, long *launches) {
-  typedef Les2March M;
+template <class M> static inline int run_les2_march(void *, const M &P, int k0, int k1, long *launches) {
   if (k1 <= k0) return 0;
   std::vector<double> smv(M::SMEM_D);
-  std::vector<M::State> st(M::NT);
+  std::vector<typename M::State> st(M::NT);
   double *sm = smv.data();
   const VfsDev &d = P.d;
   const int ntx = M::tiles_x(d), nty = M::tiles_y(d);
@@ -205,7 +220,7 @@ static inline int run_les2_march(void *, const Les2March &P, int k0, int k1, lon
         };
         issue(ka);
         for (int k = ka; k < kb; k++) {
-          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, sm);
+          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, k == ka, sm);
           for (int t = 0; t < M::NT; t++) P.phase1(st[t], t, sm);
           // phase 1 reads its neighbours' phase-0 values from the exchange buffer while updating st.v in place
           for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, sm);
@@ -221,8 +236,8 @@ static inline int run_les2_march(void *, const Les2March &P, int k0, int k1, lon
 // Same block-program shape: the test filter of u (weights w = 1/aj, 0 where nvert > 0.1) is four separable
 // (1,4,1)^3 sums (w, w u_a); the centre-difference stencil of grad u takes its i/j neighbours from a third
 // exchange buffer holding the plane's u and nvert and its k neighbours from the thread's own column.
-struct Les1March {
-  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 4;
+template <int TY_> struct Les1MarchT {
+  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 4;
   static constexpr int OFF_A = NV * NT, OFF_U = 2 * NV * NT;
   static constexpr long SMEM_D = 3L * NV * NT;
   struct State { double v[NV]; double uk[6], nvk[2], iaj0; };
@@ -280,7 +295,7 @@ struct Les1March {
     const double u0 = A.u(0, 0, 0, 0), u1 = A.u(1, 0, 0, 0), u2 = A.u(2, 0, 0, 0);
     double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, S = 0, uf[3] = {0, 0, 0};
     if (!(nv0 > 1.1)) {      // skipped cells keep the zeros of the reference's freshly created work vectors
-      grad_center_a(d, A, i, j, k + d.kofs, p, g);
+      grad_center_auto(d, A, i, j, k + d.kofs, p, g);
       S = sabs_of(g);
       const double *sA = sm + OFF_A;
       const int up = tid - TX, dn = tid + TX;
@@ -300,6 +315,8 @@ struct Les1March {
     d.s[S_LSS3][p] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][p] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][p] = (0.5 * (g[2][2] + g[2][2])) * S;
   }
 };
+typedef Les1MarchT<16> Les1March;
+typedef Les1MarchT<8> Les1March8;
 #ifndef VFS_EMU
 template <class M, int MINB> __global__ void __launch_bounds__(M::NT, MINB) k_filter_march(const M P, int kbeg, int kend, int kchunk) {
   extern __shared__ __align__(16) double vfs_fm_sm[];
