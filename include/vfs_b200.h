@@ -50,6 +50,8 @@ enum vfs_field {
   VFS_CS,           /* lCs (dof 1) output of vfs_les_cs                              */
   VFS_NU_T,         /* lNu_t (dof 1) output of vfs_les_nut                           */
   VFS_USTAR,        /* lUstar (dof 1) wall-model friction velocity                   */
+  VFS_CONV,         /* Conv (dof 3) output of vfs_convection (download only)           */
+  VFS_VISC,         /* Visc (dof 3) output of vfs_viscous (download only)              */
   VFS_NFIELDS_PUBLIC
 };
 
@@ -117,6 +119,12 @@ int vfs_les_cs(vfs_ctx *c);
 int vfs_les_nut(vfs_ctx *c);
 /* Rhs (device field `rhs_field`, VFS_RHS or VFS_RHS_O) += scale * R(Ucont, Ucat) */
 int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale);
+/* Legacy explicit-solver pieces, Convection(UserCtx*,Vec Ucont,Vec Ucat,Vec Conv) Source/rhs.c:751 and
+ * Viscous(UserCtx*,Vec,Vec,Vec Visc) Source/rhs.c:1071 (callers timeadvancing1.c:75-76): QUICK
+ * flux-difference convection and the (nu + nu_t) viscous term of the current VFS_UCONT / VFS_UCAT
+ * (+ VFS_NU_T when les) into VFS_CONV / VFS_VISC.  Like the reference they ignore periodicity. */
+int vfs_convection(vfs_ctx *c);
+int vfs_viscous(vfs_ctx *c);
 /* F = residual(X); X, F host arrays [nzl][my][mx][3] (pinned or pageable) */
 int vfs_formfunction_snes(vfs_ctx *c, const double *x_host, double *f_host);
 /* same with X already in VFS_UCONT and F left in VFS_RHS (device resident Krylov vectors) */

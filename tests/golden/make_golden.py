@@ -31,6 +31,10 @@ def reference_outputs(cfg):
     out["cs"] = np.array(ref.owned("lCs"))
     ref.Compute_eddy_viscosity_LES()
     out["nu_t"] = np.array(ref.owned("lNu_t"))
+    ref.new_vec("Conv", 3, False); ref.new_vec("Visc", 3, False)       # legacy Convection / Viscous (rhs.c:751, 1071)
+    ref.Convection("Conv"); ref.Viscous("Visc")
+    out["conv"] = np.array(ref.view("Conv")) * pc.conv_defined(cfg, fields)
+    out["visc"] = np.array(ref.view("Visc"))
     ref.IB_BC()
     out["ucont_after_ibbc"] = np.array(ref.owned("lUcont"))
     ref.view("RHS_o")[...] = 0

@@ -37,6 +37,20 @@ def krylov_x(ucont):
     return ucont + 1e-4 * np.abs(ucont).max() * np.cos(np.arange(ucont.size).reshape(ucont.shape) * 0.37)
 
 
+def conv_defined(cfg, fields):
+    """Cells where the reference's Convection output is defined: the interior, minus rhs.c:903,977 — at the
+    last face of a non-periodic i/j direction whose lower neighbour is an IB/solid node the reference reads
+    ucat[..][m], past the end of its array.  Shape (mz, my, mx, 1) of 0/1."""
+    nv, fl = fields["nvert"], cfg["flags"]
+    ok = np.zeros(nv.shape, bool)
+    ok[1:-1, 1:-1, 1:-1] = True
+    if not fl.get("ii_periodic"):
+        ok[:, :, -2] &= ~(nv[:, :, -3] > 0.1)
+    if not fl.get("jj_periodic"):
+        ok[:, -2, :] &= ~(nv[:, -3, :] > 0.1)
+    return ok[..., None].astype(float)
+
+
 def ref_setup(cfg, refdrv):
     """Create the reference context, metrics and input state for cfg.  Returns (ref, xyz, fields)."""
     pkg = load_package()
@@ -86,7 +100,7 @@ def dev_setup(cfg, xyz, fields, lib=None, device=0, options=None):
     return ctx
 
 
-def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None):
+def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, legacy=True):
     """Full path comparison.  Returns dict name -> relative error."""
     ref, xyz, fields, met = ref_setup(cfg, refdrv)
     ctx = dev_setup(cfg, xyz, fields, lib=lib, device=device, options=options)
@@ -104,6 +118,18 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None):
         ref.Compute_eddy_viscosity_LES()
         ctx.Compute_eddy_viscosity_LES()
         err["nu_t"] = relerr(ctx.download("NU_T"), ref.owned("lNu_t"))
+    # legacy explicit-solver terms on the same state (rhs.c:751, 1071).  Conv is only defined
+    # on the interior cells (the reference leaves the rest of its output Vec untouched).
+    if legacy:
+        ref.new_vec("Conv", 3, False)
+        ref.new_vec("Visc", 3, False)
+        ref.Convection("Conv")
+        ref.Viscous("Visc")
+        ctx.Convection()
+        ctx.Viscous()
+        ok = conv_defined(cfg, fields)
+        err["Convection"] = relerr(ctx.download("CONV") * ok, np.array(ref.view("Conv")) * ok)
+        err["Viscous"] = relerr(ctx.download("VISC"), ref.view("Visc"))
     # RHS_o = Formfunction_2(U) with scale 1 (solvers.c:628-629)
     ref.IB_BC()
     ctx.IB_BC()
@@ -169,6 +195,10 @@ def run_golden(cfg, gold, lib=None, device=0):
         err["Cs"] = relerr(ctx.download("CS"), gold["cs"])
         ctx.Compute_eddy_viscosity_LES()
         err["nu_t"] = relerr(ctx.download("NU_T"), gold["nu_t"])
+    if "conv" in gold.files:
+        ctx.Convection(); ctx.Viscous()
+        err["Convection"] = relerr(ctx.download("CONV") * conv_defined(cfg, fields), gold["conv"])
+        err["Viscous"] = relerr(ctx.download("VISC"), gold["visc"])
     ctx.IB_BC()
     err["IB_BC_ucont"] = relerr(ctx.download("UCONT"), gold["ucont_after_ibbc"])
     ctx.upload("RHS_O", np.zeros_like(fields["rhs_o"]))

@@ -44,6 +44,12 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     err["lCs"] = pc.relerr(glue.owned("lCs"), ref.owned("lCs"))
     ref.Compute_eddy_viscosity_LES(); glue.Compute_eddy_viscosity_LES()
     err["lNu_t"] = pc.relerr(glue.owned("lNu_t"), ref.owned("lNu_t"))
+    for d in (ref, glue):      # legacy explicit-solver terms, Vec arguments as in timeadvancing1.c:75-76
+        d.new_vec("Conv", 3, False); d.new_vec("Visc", 3, False)
+        d.Convection("Conv"); d.Viscous("Visc")
+    ok = pc.conv_defined(cfg, fields)
+    err["Convection"] = pc.relerr(np.array(glue.view("Conv")) * ok, np.array(ref.view("Conv")) * ok)
+    err["Viscous"] = pc.relerr(glue.view("Visc"), ref.view("Visc"))
     ref.IB_BC(); glue.IB_BC()
     # Nodes lying on two or more domain-boundary planes are excluded: there IB_BC's component-wise
     # periodic copy (momentum.c:2210-2221) reads ghost images that the reference has not refreshed

@@ -47,7 +47,8 @@ enum {
   S_FC1, S_FC1b, S_FC1c, S_FC2, S_FC2b, S_FC2c, S_FC3, S_FC3b, S_FC3c,   // convective face fluxes (Div1-3)
   S_FV1, S_FV1b, S_FV1c, S_FV2, S_FV2b, S_FV2c, S_FV3, S_FV3b, S_FV3c,   // viscous+SGS face fluxes (Visc1-3)
   S_FP0, S_FP1, S_FP2,                                                   // Fp
-  S_AX0, S_AX1, S_AX2, S_AY0, S_AY1, S_AY2, S_AZ0, S_AZ1, S_AZ2, S_SABS, // LES: grad u, |S|
+  S_CONV0, S_CONV1, S_CONV2, S_VISC0, S_VISC1, S_VISC2,                  // legacy Convection / Viscous results (rhs.c:751,1071)
+  S_SABS,                                                                // LES: |S|
   S_UF0, S_UF1, S_UF2,                                                   // LES: test-filtered ucat
   S_LM, S_MM,
   // LES per-node derived quantities entering the test filters (contiguous: w, U(3), |S|S_ij(6))

@@ -196,7 +196,7 @@ static void ev_rec(vfs_ctx *c, int n) {
 // ---- public field table -----------------------------------------------------------------------
 static const struct { int s0, dof; } FIELD[VFS_NFIELDS_PUBLIC] = {
   {S_X, 3}, {S_CSI0, 3}, {S_ETA0, 3}, {S_ZET0, 3}, {S_AJ, 1}, {S_NV, 1}, {S_UC0, 3}, {S_U0, 3}, {S_UO0, 3},
-  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}};
+  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}, {S_CONV0, 3}, {S_VISC0, 3}};
 
 static Grp grp(int s0, int n) { Grp g; g.n = n; for (int q = 0; q < n; q++) g.sid[q] = s0 + q; return g; }
 static Grp grp_cat(const Grp &a, const Grp &b) { Grp g = a; for (int q = 0; q < b.n; q++) g.sid[g.n++] = b.sid[q]; return g; }
@@ -787,6 +787,36 @@ extern "C" int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale) {
   return vfs_sync(c);
 }
 
+static int zero_scalars(vfs_ctx *c, int s0, int n) {
+#ifndef VFS_EMU
+  CK(cudaMemsetAsync(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double), c->stream));
+#else
+  memset(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double));
+#endif
+  return 0;
+}
+
+// ---- legacy Convection / Viscous (rhs.c:751, 1071) --------------------------------------------------------
+// Face fluxes on i in [0, mx-2] (j, k interior) and twins, then the flux difference on the interior
+// cells; the k-face plane just below an interior slab boundary is computed locally from the ucat /
+// nu_t / metric ghost planes, so no exchange is needed (the reference's DALocalToLocal of Fp1-3,
+// rhs.c:1471-1478, only refreshes ghosts nobody reads).
+template <bool VISC> static int legacy_term(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  RUN(ensure_iaj(c));
+  const Box bi = box_interior(c);
+  if (box_empty(bi)) return 0;
+  { LegacyFlux<0, VISC> f = {d}; Box b = bi; b.i0 = 0; RUN(launch(c, b, f)); }
+  { LegacyFlux<1, VISC> f = {d}; Box b = bi; b.j0 = 0; RUN(launch(c, b, f)); }
+  { LegacyFlux<2, VISC> f = {d}; Box b = bi; b.k0 = bi.k0 - 1; RUN(launch(c, b, f)); }
+  const int so = VISC ? S_VISC0 : S_CONV0;
+  RUN(zero_scalars(c, so, 3));                                        // boundary nodes: rhs.c:1506-1560 (Visc), untouched zeros (Conv)
+  { LegacyDiv f = {d, VISC ? S_FV1 : S_FC1, so}; RUN(launch(c, bi, f)); }
+  return 0;
+}
+extern "C" int vfs_convection(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(legacy_term<false>(c)); return vfs_sync(c); }
+extern "C" int vfs_viscous(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(legacy_term<true>(c)); return vfs_sync(c); }
+
 // ---- FormFunction_SNES -----------------------------------------------------------------------------------
 struct ZeroNormal {   // wall-normal zeroing applied to an Ucont that is already on the device
   VfsDev d;
@@ -854,14 +884,6 @@ extern "C" int vfs_formfunction_snes(vfs_ctx *c, const double *x, double *fout) 
 }
 
 // ---- LES ---------------------------------------------------------------------------------------------------
-static int zero_scalars(vfs_ctx *c, int s0, int n) {
-#ifndef VFS_EMU
-  CK(cudaMemsetAsync(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double), c->stream));
-#else
-  memset(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double));
-#endif
-  return 0;
-}
 static bool les2_march_ok(const vfs_ctx *c) {
 #ifndef VFS_EMU
   return c->tma_ok;

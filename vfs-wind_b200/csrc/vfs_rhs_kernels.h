@@ -31,7 +31,7 @@ struct GlobalAcc {
 
 // tangential difference of component a along unit direction T at the face between node offset
 // (0,0,0) and its neighbour in direction D  (k-omega.c:56-311, `solid` = 0.1)
-template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a) {
+template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a, const double solid = VFS_SOLID) {
   constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);      // pn = p + n
   constexpr int ti = (T == 0), tj = (T == 1), tk = (T == 2);
   // The reference picks one of three stencils (k-omega.c:56-311):
@@ -44,8 +44,8 @@ template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a) {
   const double s0 = A.u(a, ni, nj, nk) + A.u(a, 0, 0, 0);
   const double sp = A.u(a, ni + ti, nj + tj, nk + tk) + A.u(a, ti, tj, tk);
   const double sm = A.u(a, ni - ti, nj - tj, nk - tk) + A.u(a, -ti, -tj, -tk);
-  const bool hi = A.nv(ti, tj, tk) > VFS_SOLID || A.nv(ni + ti, nj + tj, nk + tk) > VFS_SOLID;
-  const bool lo = !hi && (A.nv(-ti, -tj, -tk) > VFS_SOLID || A.nv(ni - ti, nj - tj, nk - tk) > VFS_SOLID);
+  const bool hi = A.nv(ti, tj, tk) > solid || A.nv(ni + ti, nj + tj, nk + tk) > solid;
+  const bool lo = !hi && (A.nv(-ti, -tj, -tk) > solid || A.nv(ni - ti, nj - tj, nk - tk) > solid);
   return ((hi ? s0 : sp) - (lo ? s0 : sm)) * ((hi || lo) ? 0.5 : 0.25);
 }
 
@@ -171,6 +171,90 @@ template <int D> struct FaceFlux {
     face_flux_core<D, false>(d, A, c, fc, fv);
     const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D;
     for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
+  }
+};
+
+
+// ---- legacy Convection / Viscous (Source/rhs.c:751-1069 and :1071-1582) -------------
+// The explicit solvers' (RungeKutta / timeadvancing1.c FormFunctionSNES) Cartesian right-hand-side
+// pieces: QUICK flux-difference convection and the (nu + nu_t) viscous term with the inline stencil
+// switch at `solid = 0.5` (rhs.c:1105).  Neither handles periodic directions (the reference code does
+// not); face fluxes land in the same work arrays as Formfunction_2's (Div1-3 / Visc1-3 twins), the
+// results in two free work triplets exposed as the public fields VFS_CONV / VFS_VISC.
+template <int D, class Acc> VFS_HD void legacy_conv_flux(const VfsDev &d, const Acc &A, int c, double f[3]) {
+  constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);
+  const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
+  const double coef = 0.125;
+  const double ucon = A.template uc<D>(0) * 0.5;
+  const double up = ucon + fabs(ucon), um = ucon - fabs(ucon);
+  const double nvm = A.nv(-ni, -nj, -nk), nvq = A.nv(ni, nj, nk);
+  int br;          // 0: interior stencil, 1: low side collapsed, 2: high side collapsed, 3: untouched (rhs.c:886-935, 1003-1040)
+  if (c > 0 && c < m - 2 && nvq < 0.1 && nvm < 0.1) br = 0;
+  else if (D == 2 ? (c < m - 2 && (c == 0 || nvm > 0.1)) : (c == 0 || nvm > 0.1)) br = 1;
+  else if (D == 2 ? (c > 0 && (c == m - 2 || nvq > 0.1)) : (c == m - 2 || nvq > 0.1)) br = 2;
+  else br = 3;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const double u0 = A.u(a, 0, 0, 0), u1 = A.u(a, ni, nj, nk);
+    const double uR = br == 2 ? u1 : A.u(a, 2 * ni, 2 * nj, 2 * nk);
+    const double uL = br == 1 ? u0 : A.u(a, -ni, -nj, -nk);
+    const double v = um * (coef * (-uR - 2. * u1 + 3. * u0) + u1) + up * (coef * (-uL - 2. * u0 + 3. * u1) + u0);
+    f[a] = br == 3 ? 0. : v;
+  }
+}
+template <int D, class Acc> VFS_HD void legacy_visc_flux(const VfsDev &d, const Acc &A, double f[3]) {
+  constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);
+  const double solid = 0.5;                                    // rhs.c:1105
+#define VFS_F3(s0) mk3(0.5 * A.template met<D>(s0, 0) + 0.5 * A.template met<D>(s0, 1), 0.5 * A.template met<D>(s0 + 1, 0) + 0.5 * A.template met<D>(s0 + 1, 1), \
+                       0.5 * A.template met<D>(s0 + 2, 0) + 0.5 * A.template met<D>(s0 + 2, 1))
+  const V3 cs = VFS_F3(0), et = VFS_F3(3), ze = VFS_F3(6);
+#undef VFS_F3
+  const double ajc = 2. / (A.template iaj<D>(0) + A.template iaj<D>(1));
+  const V3 n = (D == 0 ? cs : (D == 1 ? et : ze));
+  double du[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const double dn = A.u(a, ni, nj, nk) - A.u(a, 0, 0, 0);
+    if (D == 0) { du[a][0] = dn; du[a][1] = dtan<D, 1>(A, a, solid); du[a][2] = dtan<D, 2>(A, a, solid); }
+    else if (D == 1) { du[a][0] = dtan<D, 0>(A, a, solid); du[a][1] = dn; du[a][2] = dtan<D, 2>(A, a, solid); }
+    else { du[a][0] = dtan<D, 0>(A, a, solid); du[a][1] = dtan<D, 1>(A, a, solid); du[a][2] = dn; }
+  }
+  const double g1 = cs.x * n.x + cs.y * n.y + cs.z * n.z;
+  const double g2 = et.x * n.x + et.y * n.y + et.z * n.z;
+  const double g3 = ze.x * n.x + ze.y * n.y + ze.z * n.z;
+  double r[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    r[a][0] = du[a][0] * cs.x + du[a][1] * et.x + du[a][2] * ze.x;
+    r[a][1] = du[a][0] * cs.y + du[a][1] * et.y + du[a][2] * ze.y;
+    r[a][2] = du[a][0] * cs.z + du[a][1] * et.z + du[a][2] * ze.z;
+  }
+  const double nu = 1. / d.ren;
+  const double nu_t = d.les ? 0.5 * (A.template nut<D>(0) + A.template nut<D>(1)) : 0.;      // rhs.c:1220-1226
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+    f[a] = (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * (nu + nu_t);
+}
+// VISC = false: Convection's Fp1-3 into S_FC1.., VISC = true: Viscous's into S_FV1..
+template <int D, bool VISC> struct LegacyFlux {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    GlobalAcc A = {d, p};
+    double f[3];
+    if (VISC) legacy_visc_flux<D>(d, A, f);
+    else legacy_conv_flux<D>(d, A, (D == 0 ? i : (D == 1 ? j : k + d.kofs)), f);
+    const int s0 = (VISC ? S_FV1 : S_FC1) + 3 * D;
+    for (int a = 0; a < 3; a++) d.s[s0 + a][p] = f[a];
+  }
+};
+// flux difference at the cell centres (rhs.c:1044-1061, 1487-1493)
+struct LegacyDiv {
+  VfsDev d; int sf, so;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    for (int a = 0; a < 3; a++)
+      d.s[so + a][p] = d.s[sf + a][p] - d.s[sf + a][p - 1] + d.s[sf + 3 + a][p] - d.s[sf + 3 + a][p - d.sj] + d.s[sf + 6 + a][p] - d.s[sf + 6 + a][p - d.sk];
   }
 };
 

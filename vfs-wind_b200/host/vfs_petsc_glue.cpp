@@ -12,6 +12,7 @@
 //   FormFunction_SNES                Source/momentum.c:2237   -> vfs_formfunction_snes
 //   Compute_Smagorinsky_Constant_1   Source/les.c:75          -> vfs_les_cs
 //   Compute_eddy_viscosity_LES       Source/les.c:1143        -> vfs_les_nut
+//   Convection / Viscous (legacy)    Source/rhs.c:751,1071    -> vfs_convection / vfs_viscous
 //
 // Data contract: the UserCtx Vecs stay the source of truth on the host (the rest of VFS-Wind —
 // Poisson solve, IBM, turbine models, I/O — keeps reading them), so each entry point uploads the
@@ -191,6 +192,25 @@ void Compute_eddy_viscosity_LES(UserCtx *user) {
   push(user, s, user->lUcat, 3, VFS_UCAT); push(user, s, user->lCs, 1, VFS_CS);
   ck(s, vfs_les_nut(s->ctx), "vfs_les_nut");
   pull(user, s, VFS_NU_T, 1, user->lNu_t, true);
+}
+
+// legacy explicit-solver terms (callers: timeadvancing1.c:75-76 FormFunctionSNES, Prediction)
+PetscErrorCode Convection(UserCtx *user, Vec Ucont, Vec Ucat, Vec Conv) {
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, Ucont, 3, VFS_UCONT); push(user, s, Ucat, 3, VFS_UCAT);
+  ck(s, vfs_convection(s->ctx), "vfs_convection");
+  pull(user, s, VFS_CONV, 3, Conv, false);
+  return 0;
+}
+PetscErrorCode Viscous(UserCtx *user, Vec Ucont, Vec Ucat, Vec Visc) {
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, Ucont, 3, VFS_UCONT); push(user, s, Ucat, 3, VFS_UCAT);
+  if (les) push(user, s, user->lNu_t, 1, VFS_NU_T);
+  ck(s, vfs_viscous(s->ctx), "vfs_viscous");
+  pull(user, s, VFS_VISC, 3, Visc, false);
+  return 0;
 }
 
 PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
