@@ -46,11 +46,12 @@ def _worker(rank, world, port, tmp, cfgname, dims, flags_extra, bctype):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfgname,dims,extra,bctype", [
-    ("c2_box256", (13, 11, 19), {}, None),                       # kk periodic: rank 0 <-> rank 1 wrap
-    ("c3_turbine", (17, 13, 21), {}, None),                      # non-periodic k, IBM masks, F_eul
+@pytest.mark.parametrize("cfgname,dims,extra,bctype,world", [
+    ("c2_box256", (13, 11, 19), {}, None, 2),                    # kk periodic: rank 0 <-> rank 1 wrap
+    ("c3_turbine", (17, 13, 21), {}, None, 2),                   # non-periodic k, IBM masks, F_eul
+    ("c2_box256", (13, 11, 23), {}, None, 3),                    # a rank with two interior slab boundaries + the periodic seam
 ])
-def test_two_ranks_bitwise_equal_single_rank(pkg, refdrv, tmp_path, cfgname, dims, extra, bctype):
+def test_two_ranks_bitwise_equal_single_rank(pkg, refdrv, tmp_path, cfgname, dims, extra, bctype, world):
     capi, cases = pkg.capi, pkg.cases
     lib = emu_loader.load(capi)
     cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
@@ -68,8 +69,9 @@ def test_two_ranks_bitwise_equal_single_rank(pkg, refdrv, tmp_path, cfgname, dim
     ctx.close()
     np.savez(os.path.join(tmp_path, "global.npz"), xyz=xyz, x=x, **f)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), cfgname, dims, extra, bctype), nprocs=2, join=True)
-    parts = [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(2)]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), cfgname, dims, extra, bctype), nprocs=world, join=True)
+    parts = [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)]
+    print("exchanges per rank:", [int(pp["nex"]) for pp in parts])
     assert int(parts[0]["nex"]) > 5
     for n in ("F", "UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ"):
         multi = np.concatenate([pp[n] for pp in parts], axis=0)

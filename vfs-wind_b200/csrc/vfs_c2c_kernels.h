@@ -9,6 +9,7 @@ struct C2CInterior {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
     long p = d.idx(i, j, k);
+    { const int kg = d.kglob(k); if (kg < 1 || kg > d.mz - 2) return; }      // see C2CInteriorFix
     if (!(d.s[S_NV][p] < 0.1)) return;
     const double m00 = d.s[S_CSI0][p], m01 = d.s[S_CSI1][p], m02 = d.s[S_CSI2][p];
     const double m10 = d.s[S_ETA0][p], m11 = d.s[S_ETA1][p], m12 = d.s[S_ETA2][p];
@@ -55,7 +56,7 @@ VFS_HD V3 slip_ghost(const VfsDev &d, long pn, int col, double sgn) {
 struct C2CGhostRules {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int mx = d.mx, my = d.my, mz = d.mz, kg = k + d.kofs;
+    const int mx = d.mx, my = d.my, mz = d.mz, kg = d.kglob(k);
     if (!(i == 0 || i == mx - 1 || j == 0 || j == my - 1 || kg == 0 || kg == mz - 1)) return;
     long p = d.idx(i, j, k);
     const int *bc = d.bc;
@@ -97,7 +98,8 @@ struct C2CGhostRules {
 struct C2CInteriorFix {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int mx = d.mx, my = d.my, mz = d.mz, kg = k + d.kofs;
+    const int mx = d.mx, my = d.my, mz = d.mz, kg = d.kglob(k);
+    if (kg < 1 || kg > mz - 2) return;          // image of a boundary plane inside an extended k range (see contra2cart)
     long p = d.idx(i, j, k);
     if ((int)(d.s[S_NV][p] + 0.1) == 3) { st3(d, S_U0, p, mk3(0, 0, 0)); return; }
     if (j != my - 2 && kg != mz - 2) {

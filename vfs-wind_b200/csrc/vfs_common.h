@@ -80,6 +80,9 @@ struct VfsDev {
   // every nvert comparison is known to be false), see VFS_WARP_ANY.
   const unsigned char *near;
   VFS_HD long idx(int i, int j, int k) const { return org + (long)k * sk + (long)j * sj + i; }
+  // global k of local plane k; a ghost plane across the periodic seam maps to the plane it images
+  // (-1 -> mz-1, mz -> 0, ...), which is what the owner of that plane evaluates its boundary logic with
+  VFS_HD int kglob(int k) const { int kg = k + kofs; if (perz) { if (kg < 0) kg += mz; else if (kg >= mz) kg -= mz; } return kg; }
 };
 
 struct Box { int i0, i1, j0, j1, k0, k1; };

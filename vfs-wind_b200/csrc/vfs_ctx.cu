@@ -142,11 +142,17 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
 // disjoint index ranges: the two i planes (j, k full), the two j planes (i inner) and the owned global
 // k = 0 / mz-1 planes (i, j inner).  [ka, kb) is the local k range of the i- and j-plane parts (it may
 // reach into the k ghost planes, see node_copy).  Replaces 4-6 thin launches per boundary operation.
-struct Shell { int mx, my, ka, nk, kp[2], nkp; long nA, nB, nC; };
-static Shell make_shell(const VfsDev &d, int ka, int kb) {
+struct Shell { int mx, my, ka, nk, kp[4], nkp; long nA, nB, nC; };
+// images: also visit the ghost planes that image the global k = 0 / mz-1 planes across the periodic seam
+// (local plane -1 on the first rank, nzl on the last), for the operations contra2cart replays on ghost planes
+static Shell make_shell(const VfsDev &d, int ka, int kb, bool images = false) {
   Shell s; s.mx = d.mx; s.my = d.my; s.ka = ka; s.nk = kb - ka; s.nkp = 0;
   if (d.kofs == 0) s.kp[s.nkp++] = 0;
   if (d.kofs + d.nzl == d.mz) s.kp[s.nkp++] = d.nzl - 1;
+  if (images && d.perz && !d.single_rank) {
+    if (d.kofs == 0 && ka <= -1) s.kp[s.nkp++] = -1;
+    if (d.kofs + d.nzl == d.mz && kb >= d.nzl + 1) s.kp[s.nkp++] = d.nzl;
+  }
   s.nA = 2L * d.my * s.nk; s.nB = 2L * (d.mx - 2) * s.nk; s.nC = (long)s.nkp * (d.mx - 2) * (d.my - 2);
   return s;
 }
@@ -170,8 +176,8 @@ template <class F> __global__ void __launch_bounds__(256) k_shell(F f, Shell s) 
   if (t < s.nA + s.nB + s.nC) shell_visit(f, s, t);
 }
 #endif
-template <class F> static int launch_shell(vfs_ctx *c, int ka, int kb, const F &f) {
-  const Shell s = make_shell(c->d, ka, kb);
+template <class F> static int launch_shell(vfs_ctx *c, int ka, int kb, const F &f, bool images = false) {
+  const Shell s = make_shell(c->d, ka, kb, images);
   const long n = s.nA + s.nB + s.nC;
   if (n <= 0) return 0;
   c->launches++;
@@ -207,10 +213,11 @@ static int klo(const vfs_ctx *c, int kg) { int k = kg - c->d.kofs; return k < 0 
 static Box box_interior(const vfs_ctx *c) { Box b = {1, c->d.mx - 1, 1, c->d.my - 1, klo(c, 1), klo(c, c->d.mz - 1)}; return b; }
 
 // ---- ghost refresh primitives -------------------------------------------------------------------
-static int wrap_ij(vfs_ctx *c, const Grp &g) {
+static int wrap_ij(vfs_ctx *c, const Grp &g, int ka = 0, int kb = -1) {
   const VfsDev &d = c->d;
-  if (d.perx) { WrapFill f = {d, g, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
-  if (d.pery) { WrapFill f = {d, g, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
+  if (kb < 0) kb = d.nzl;
+  if (d.perx) { WrapFill f = {d, g, 0}; Box b = {0, 2 * VFS_G, 0, d.my, ka, kb}; RUN(launch(c, b, f)); }
+  if (d.pery) { WrapFill f = {d, g, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, ka, kb}; RUN(launch(c, b, f)); }
   return 0;
 }
 #ifndef VFS_EMU
@@ -295,7 +302,7 @@ static int g2l_after_copy(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return
 // the "if(periodic) ... f[k][j][i] = f[c][b][a]" loops
 static int node_copy(vfs_ctx *c, const Grp &g) {
   const VfsDev &d = c->d;
-  NodeCopy f = {d, g};
+  NodeCopy f = {d, g, 0};
   // k-ghost planes received from a neighbouring rank across an INTERIOR slab boundary are owned
   // planes in a single-rank run, where this copy updates them; apply it there too so that the
   // result does not depend on the number of ranks (wrap-around ghosts stay stale, as in 1 rank).
@@ -577,25 +584,46 @@ extern "C" int vfs_form_metrics(vfs_ctx *c) {
 // ---- Contra2Cart ------------------------------------------------------------------------------------
 struct CopyScalar3 { VfsDev d; int from, to; VFS_HD void operator()(int i, int j, int k) const { long p = d.idx(i, j, k); for (int a = 0; a < 3; a++) d.s[to + a][p] = d.s[from + a][p]; } };
 
-static int run_snapshot(vfs_ctx *c) { CopyScalar3 f = {c->d, S_U0, S_FP0}; return launch_shell(c, 0, c->d.nzl, f); }
-static int run_ghost_rules(vfs_ctx *c) { C2CGhostRules f = {c->d}; return launch_shell(c, 0, c->d.nzl, f); }
 static int run_les_derive_boundary(vfs_ctx *c) { LesDeriveBoundary f = {c->d}; return launch_shell(c, 0, c->d.nzl, f); }
 
+// Contra2Cart_2 (rhs.c:65-749).  Between ranks, ucat's ghost planes are not exchanged: every operation
+// of the function is REPLAYED on the three ghost planes either side of the slab (C2C_EXT), from the
+// ucont / metric / nvert ghosts that are already there, exactly as the owner of those planes runs it
+// (same inputs, same code: bitwise the owner's values).  A ghost plane across the periodic seam is
+// evaluated as the global plane it images (VfsDev::kglob): images of interior planes are recomputed,
+// the image of the boundary plane mz-1 (0) receives the periodic node copy of local plane 1 (nzl-2),
+// which is what its owner copies into it.  This removes 4 (8 at the seam ranks) of the 17 inter-rank
+// exchanges of one RHS+LES unit; a single rank keeps the wrap-fill path (no ghost planes to replay).
+#define C2C_EXT 3
 static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
   c->sabs_valid = false;
   Grp gu = grp(S_U0, 3);
-  if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // rhs.c:129-156
+  const bool multi = c->prm.nranks > 1;
+  const int ka = multi && (d.kofs > 0 || d.perz) ? -C2C_EXT : 0;
+  const int kb = multi && (d.kofs + d.nzl < d.mz || d.perz) ? d.nzl + C2C_EXT : d.nzl;
+  // refresh of the periodic i/j ghosts (+ the k wrap of a single rank) and the periodic node copies, on [ka, kb)
+  auto refresh = [&](bool after_copy) -> int {
+    if (!multi) return after_copy ? g2l_after_copy(c, gu) : g2l(c, gu);
+    return wrap_ij(c, gu, ka, kb);
+  };
+  auto copy_nodes = [&](const Grp &g) -> int {
+    if (!multi) return node_copy(c, g);
+    NodeCopy f = {d, g, 1};
+    return launch_shell(c, ka, kb, f, true);
+  };
+  if (any_per(c)) RUN(copy_nodes(grp(S_UC0, 3)));                    // rhs.c:129-156
   ev_rec(c, 2 * VFS_T_C2C);
-  { C2CInterior f = {d}; RUN(launch(c, box_interior(c), f)); }      // rhs.c:158-247
+  Box bi = box_interior(c);
+  if (multi) { bi.k0 = ka; bi.k1 = kb; }                             // the functors skip planes that are not interior (kglob)
+  { C2CInterior f = {d}; RUN(launch(c, bi, f)); }                    // rhs.c:158-247
   ev_rec(c, 2 * VFS_T_C2C + 1);
-  RUN(g2l(c, gu));
-  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l_after_copy(c, gu)); }   // rhs.c:254-291
-  RUN(run_snapshot(c));                      // lUcat snapshot read by the rules
-  RUN(run_ghost_rules(c));                   // rhs.c:302-682 (boundary nodes)
+  RUN(refresh(false));
+  if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }       // rhs.c:254-291
+  { CopyScalar3 f = {d, S_U0, S_FP0}; RUN(launch_shell(c, ka, kb, f, true)); }     // lUcat snapshot read by the rules
+  { C2CGhostRules f = {d}; RUN(launch_shell(c, ka, kb, f, true)); }                // rhs.c:302-682 (boundary nodes)
   {                                                                  // rhs.c:305-308,676-681 (interior nodes)
     C2CInteriorFix f = {d};
-    const Box bi = box_interior(c);
     if (c->has_solid) RUN(launch(c, bi, f));                         // solid cells -> 0: the whole interior
     else {                                                           // only the "corner" lines can change
       const int *bc = d.bc;
@@ -604,8 +632,8 @@ static int contra2cart(vfs_ctx *c) {
       for (int q = 0; q < 4; q++) if (cor[q]) { Box b = {ci[q], ci[q] + 1, cj[q], cj[q] + 1, bi.k0, bi.k1}; RUN(launch(c, b, f)); }
     }
   }
-  RUN(g2l(c, gu));
-  if (any_per(c)) { RUN(node_copy(c, gu)); RUN(g2l_after_copy(c, gu)); }   // rhs.c:712-748
+  RUN(refresh(false));
+  if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }       // rhs.c:712-748
   return 0;
 }
 extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return vfs_sync(c); }

@@ -66,9 +66,9 @@ struct WrapFill {
 // "if(flag) f[k][j][i] = f[c][b][a]" with a=-2 / mx+1 etc.  Sources are always ghost nodes, so
 // the copy is race-free in place.  Launched on the two boundary planes of each periodic direction.
 struct NodeCopy {
-  VfsDev d; Grp g;
+  VfsDev d; Grp g; int kw;      // kw: evaluate ghost planes across the periodic seam as the planes they image (VfsDev::kglob)
   VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
+    const int kg = kw ? d.kglob(k) : k + d.kofs;
     int a = i, b = j, c = k, flag = 0;
     if (d.perx) { if (i == 0) a = -2, flag = 1; else if (i == d.mx - 1) a = d.mx + 1, flag = 1; }
     if (d.pery) { if (j == 0) b = -2, flag = 1; else if (j == d.my - 1) b = d.my + 1, flag = 1; }
