@@ -89,6 +89,7 @@ struct vfs_ctx {
   CUtensorMap tmap_les2;         // same pool, box (32, 16): operand tiles of the LES pass-2 marching kernel
   CUtensorMap tmap_les2_8;       // same pool, box (32, 8)
   CUtensorMap tmap_les2_12;      // same pool, box (32, 12)
+  CUtensorMap tmap_fluxA, tmap_fluxB;   // boxes of k_flux_march: ucat (36, 19), metrics (34, 17)
 #endif
   bool tma_ok = false;
 #ifndef VFS_EMU
@@ -107,6 +108,7 @@ struct vfs_ctx {
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
   int les2_ty = 12;              // tile height of the LES pass-2 block program: 16 (1 block/SM) or 8 (2 blocks/SM) (option key 2)
   int les1_var = 1;              // LES pass 1: 0 = block program 32x16, 1 = TMA tile march, 2 = block program 32x8 x2/SM, 3 = 32x16 x2/SM (option key 4)
+  int flux_var = 1;              // regular face fluxes: 1 = k_flux_march (metric planes staged too), 0 = k_tile_march<RingFlux> (option key 7)
   int les3_var = 0;              // LES pass 3: 0 = block program 32x16 x2/SM, 1 = TMA tile march (option key 5)
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
@@ -375,7 +377,9 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
               vfs_make_tensor_map(&c->tmap_rhs, c->pool, c->d, c->scalar_len, RhsMarch::NXP, RhsMarch::NYP) == 0 &&
               vfs_make_tensor_map(&c->tmap_les2, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY) == 0 &&
               vfs_make_tensor_map(&c->tmap_les2_8, c->pool, c->d, c->scalar_len, Les2March8::TX, Les2March8::TY) == 0 &&
-              vfs_make_tensor_map(&c->tmap_les2_12, c->pool, c->d, c->scalar_len, Les2March12::TX, Les2March12::TY) == 0;
+              vfs_make_tensor_map(&c->tmap_les2_12, c->pool, c->d, c->scalar_len, Les2March12::TX, Les2March12::TY) == 0 &&
+              vfs_make_tensor_map(&c->tmap_fluxA, c->pool, c->d, c->scalar_len, FluxMarch::AX, FluxMarch::AY) == 0 &&
+              vfs_make_tensor_map(&c->tmap_fluxB, c->pool, c->d, c->scalar_len, FluxMarch::BX, FluxMarch::BY) == 0;
 #endif
   *out = c;
   return 0;
@@ -485,6 +489,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 4) c->les1_var = value;
   else if (key == 5) c->les3_var = value;
   else if (key == 6) { c->fastpath = value; c->near_valid = false; }
+  else if (key == 7) c->flux_var = value;
   graph_reset(c);
   return 0;
 }
@@ -775,7 +780,8 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
 #ifndef VFS_EMU
   if (!march && c->fused && c->tma_ok) {
     // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
-    if (launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, c->flux_minb, &c->launches)) { set_err(c, "k_flux_tma launch failed"); return VFS_ERR_CUDA; }
+    if (c->flux_var == 1 ? launch_flux_march(c->stream, c->tmap_fluxA, c->tmap_fluxB, d, k1, k2, &c->launches)
+                         : launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, c->flux_minb, &c->launches)) { set_err(c, "flux kernel launch failed"); return VFS_ERR_CUDA; }
     { FaceFlux<0> f = {d}; Box b0 = {0, 1, 1, d.my - 1, k1, k2}, b1 = {d.mx - 2, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     { FaceFlux<1> f = {d}; Box b0 = {1, d.mx - 1, 0, 1, k1, k2}, b1 = {1, d.mx - 1, d.my - 2, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     { FaceFlux<2> f = {d};

@@ -241,6 +241,118 @@ struct FluxBody {
   }
 };
 
+
+// ---- face fluxes, second form: metric planes staged too ------------------------------------------------
+// profiles/r01p: with the mask-free fast path the tiled flux kernel waits on its ~69 scattered global
+// loads per node (centre metrics and 1/aj at p, p+1, p+sj, p+sk: long-scoreboard 6.6 of 12.8 stall
+// cycles per issued instruction).  Here the ten metric scalars of planes k and k+1 are a second
+// TMA-fed ring (box (TX+2) x (TY+1) from node i0-1: the inner start coordinate of every box stays even, i.e.
+// 16-byte aligned, like all other boxes here; three stages: one plane of prefetch), so a node's metric reads
+// are shared-memory loads and every metric value crosses L2 -> SM once per tile instead of up to
+// four times.  To make room the tile is 32 x 16 (one 512-thread block per SM, the same 16 warps),
+// and nvert leaves the ring: only the masked path reads it (from global memory).
+struct FluxMarch {
+  static constexpr int TX = 32, TY = 16, NT = TX * TY;
+  static constexpr int AX = TX + 4, AY = TY + 3, A_NS = 3, A_ST = 5, A_TILE = ((AX * AY * 8 + 127) / 128) * 16, A_PLANE = A_TILE * A_NS;
+  static constexpr int BX = TX + 2, BY = TY + 1, B_NS = 10, B_ST = 3, B_TILE = ((BX * BY * 8 + 127) / 128) * 16, B_PLANE = B_TILE * B_NS;
+  static constexpr int OFF_B = A_ST * A_PLANE, OFF_BAR = OFF_B + B_ST * B_PLANE;
+  static constexpr size_t BYTES = (size_t)(OFF_BAR + A_ST + B_ST) * 8;
+  VFS_HD static int b_sid(int q) { return q < 9 ? S_CSI0 + q : S_IAJ; }
+};
+template <bool FLUID> struct FluxAcc2 {
+  const double *sa[4];      // ucat planes k-1, k, k+1, k+2 at the thread's node
+  const double *sb[2];      // metric planes k, k+1 at the thread's node
+  const VfsDev &d; long p;
+  __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return sa[dk + 1][a * FluxMarch::A_TILE + dj * FluxMarch::AX + di]; }
+  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return FLUID ? 0. : d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
+  template <int D> __device__ __forceinline__ long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
+  template <int D> __device__ __forceinline__ double met(int s, int side) const {
+    return sb[D == 2 ? side : 0][s * FluxMarch::B_TILE + (D == 1 ? side * FluxMarch::BX : 0) + (D == 0 ? side : 0)];
+  }
+  template <int D> __device__ __forceinline__ double iaj(int side) const { return met<D>(9, side); }
+  template <int D> __device__ __forceinline__ double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
+  template <int D> __device__ __forceinline__ double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
+};
+template <bool FLUID, class Acc> __device__ __forceinline__ void flux_node(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
+  double fc[3], fv[3];
+  if (i <= d.mx - 3) {
+    face_flux_core<0, true>(d, A, i, fc, fv);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = fc[a]; d.s[S_FV1 + a][p] = fv[a]; }
+  }
+  if (j <= d.my - 3) {
+    face_flux_core<1, true>(d, A, j, fc, fv);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = fc[a]; d.s[S_FV2 + a][p] = fv[a]; }
+  }
+  if (kg <= d.mz - 3) {
+    face_flux_core<2, true>(d, A, kg, fc, fv);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
+  }
+}
+__global__ void __launch_bounds__(FluxMarch::NT, 1)
+k_flux_march(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, VfsDev d, int kbeg, int kend, int kchunk) {
+  typedef FluxMarch M;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *sm = reinterpret_cast<double *>(smraw);
+  unsigned long long *barA = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR), *barB = barA + M::A_ST;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * M::TX + tx;
+  const int i0 = 1 + blockIdx.x * M::TX, j0 = 1 + blockIdx.y * M::TY;
+  const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
+  if (ka >= kb) return;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = (i <= d.mx - 2) && (j <= d.my - 2);
+  if (tid == 0) {
+    for (int s = 0; s < M::A_ST + M::B_ST; s++) mbar_init(&barA[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int kfa = ka - 1, kla = kb + 1;       // ucat planes ka-1 .. kb+1
+  const int kfb = ka, klb = kb;               // metric planes ka .. kb
+  auto issueA = [&](int kk) {
+    const int slot = (kk - kfa) % M::A_ST;
+    mbar_expect_tx(&barA[slot], M::A_NS * M::AX * M::AY * 8);
+    for (int s = 0; s < M::A_NS; s++) tma_load_tile(sm + slot * M::A_PLANE + s * M::A_TILE, &tmapA, i0 - 1 + VFS_G, j0 - 1 + VFS_G, kk + VFS_G, S_U0 + s, &barA[slot]);
+  };
+  auto issueB = [&](int kk) {
+    const int slot = (kk - kfb) % M::B_ST;
+    mbar_expect_tx(&barB[slot], M::B_NS * M::BX * M::BY * 8);
+    for (int s = 0; s < M::B_NS; s++) tma_load_tile(sm + M::OFF_B + slot * M::B_PLANE + s * M::B_TILE, &tmapB, i0 - 1 + VFS_G, j0 + VFS_G, kk + VFS_G, M::b_sid(s), &barB[slot]);
+  };
+  if (tid == 0) {
+    for (int kk = kfa; kk < kfa + M::A_ST && kk <= kla; kk++) issueA(kk);
+    for (int kk = kfb; kk < kfb + M::B_ST && kk <= klb; kk++) issueB(kk);
+  }
+  for (int kk = kfa; kk < ka + 2; kk++) mbar_wait(&barA[(kk - kfa) % M::A_ST], ((kk - kfa) / M::A_ST) & 1);
+  mbar_wait(&barB[0], 0);
+  for (int k = ka; k < kb; k++) {
+    mbar_wait(&barA[(k + 2 - kfa) % M::A_ST], ((k + 2 - kfa) / M::A_ST) & 1);
+    mbar_wait(&barB[(k + 1 - kfb) % M::B_ST], ((k + 1 - kfb) / M::B_ST) & 1);
+    if (active) {
+      const long p = d.idx(i, j, k);
+      const double *ta = sm + (ty + 1) * M::AX + (tx + 1), *tb = sm + M::OFF_B + ty * M::BX + tx + 1;
+      const int na = k - kfa, nb = k - kfb;
+      if (VFS_WARP_ANY(d.near[p] != 0)) {
+        FluxAcc2<false> A = {{ta + ((na - 1) % M::A_ST) * M::A_PLANE, ta + (na % M::A_ST) * M::A_PLANE, ta + ((na + 1) % M::A_ST) * M::A_PLANE, ta + ((na + 2) % M::A_ST) * M::A_PLANE},
+                             {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p};
+        flux_node<false>(d, A, i, j, k + d.kofs, p);
+      } else {
+        FluxAcc2<true> A = {{ta + ((na - 1) % M::A_ST) * M::A_PLANE, ta + (na % M::A_ST) * M::A_PLANE, ta + ((na + 1) % M::A_ST) * M::A_PLANE, ta + ((na + 2) % M::A_ST) * M::A_PLANE},
+                            {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p};
+        flux_node<true>(d, A, i, j, k + d.kofs, p);
+      }
+    }
+    __syncthreads();                         // ucat plane k-1 and metric plane k are no longer needed by anyone
+    if (tid == 0) {
+      fence_proxy_async();
+      const int kna = k - 1 + M::A_ST, knb = k + M::B_ST;
+      if (kna <= kla) issueA(kna);
+      if (knb <= klb) issueB(knb);
+    }
+  }
+}
+
 static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q = 0; q < n; q++) s.sid[q] = v[q]; return s; }
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};

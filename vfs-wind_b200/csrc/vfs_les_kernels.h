@@ -415,6 +415,14 @@ struct LesClipBoundary {
   VFS_HD void operator()(int i, int j, int k) const { d.s[S_CS][d.idx(i, j, k)] = 0; }
 };
 
+// nu_t of one interior cell from its Cs and |S| (les.c:1206-1211)
+VFS_HD double nut_value(const VfsDev &d, long p, double cs, double Sabs) {
+  const double *nv = d.s[S_NV];
+  const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
+  double v = cs * (filter * filter) * Sabs;
+  if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
+  return v;
+}
 // les.c:1185-1211: nu_t = Cs * Delta^2 * |S|.  FROM_S: |S| was stored by pass 1 of vfs_les_cs from
 // the same ucat (identical arithmetic), so it is read back instead of being recomputed.
 template <bool FROM_S> struct NuT {
@@ -427,10 +435,7 @@ template <bool FROM_S> struct NuT {
     double Sabs;
     if (FROM_S) Sabs = d.s[S_SABS][p];
     else { double g[3][3]; grad_center(d, S_U0, i, j, kg, p, g); Sabs = sabs_of(g); }
-    const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
-    double v = d.s[S_CS][p] * (filter * filter) * Sabs;
-    if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
-    d.s[S_NUT][p] = v;
+    d.s[S_NUT][p] = nut_value(d, p, d.s[S_CS][p], Sabs);
   }
 };
 

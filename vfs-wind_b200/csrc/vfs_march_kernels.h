@@ -232,6 +232,24 @@ template <class M> static inline int run_les2_march(void *, const M &P, int k0, 
 }
 #endif
 
+#ifndef VFS_EMU
+// face fluxes with TMA-staged ucat AND metric planes (k_flux_march, vfs_fused_kernels.h)
+static inline int launch_flux_march(cudaStream_t st, const CUtensorMap &tmapA, const CUtensorMap &tmapB, const VfsDev &d, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_flux_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FluxMarch::BYTES) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  const int ntx = (d.mx - 2 + FluxMarch::TX - 1) / FluxMarch::TX, nty = (d.my - 2 + FluxMarch::TY - 1) / FluxMarch::TY;
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16);
+  dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk), blk(FluxMarch::TX, FluxMarch::TY, 1);
+  k_flux_march<<<grd, blk, FluxMarch::BYTES, st>>>(tmapA, tmapB, d, k0, k1, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#endif
+
 // ---- LES pass 1 (les.c:199-246): grad u, |S|, test-filtered velocity + the per-node products of pass 2 ----
 // Same block-program shape: the test filter of u (weights w = 1/aj, 0 where nvert > 0.1) is four separable
 // (1,4,1)^3 sums (w, w u_a); the centre-difference stencil of grad u takes its i/j neighbours from a third
@@ -253,7 +271,7 @@ template <int TY_> struct Les1MarchT {
     VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
     VFS_HD double aj() const { return d.s[S_AJ][p]; }
   };
-  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, bool, double *sm) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     double K[NV] = {0, 0, 0, 0}, u0[3] = {0, 0, 0}, nv0 = 0;
     st.iaj0 = 0;
@@ -325,7 +343,7 @@ template <class M, int MINB> __global__ void __launch_bounds__(M::NT, MINB) k_fi
   const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
   typename M::State st;
   for (int k = ka; k < kb; k++) {
-    P.phase0(st, tid, bx, by, k, sm);
+    P.phase0(st, tid, bx, by, k, k == ka, sm);
     __syncthreads();
     P.phase1(st, tid, sm);
     __syncthreads();
@@ -360,7 +378,7 @@ template <class M, int MINB> static inline int run_filter_march(void *, const M 
       for (int bx = 0; bx < ntx; bx++) {
         const int ka = k0 + bz * kchunk, kb = k1 < ka + kchunk ? k1 : ka + kchunk;
         for (int k = ka; k < kb; k++) {
-          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, smv.data());
+          for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, k == ka, smv.data());
           for (int t = 0; t < M::NT; t++) P.phase1(st[t], t, smv.data());
           for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, smv.data());
         }
@@ -380,13 +398,16 @@ template <class M, int MINB> static inline int run_filter_march(void *, const M 
 struct Les3March {
   static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 3;
   static constexpr long SMEM_D = 2L * NV * NT;
+  // (a register window over k, as in Les2MarchT, was measured slower here: 0.50 vs 0.44 ms at 256^3 — the three
+  // planes' twelve loads are independent L2 hits, the window adds a loop-carried chain; writing nu_t from this
+  // kernel as well cost what the separate NuT kernel costs, 0.14 ms, so it stays separate)
   struct State { double v[NV]; double nvc; };
   VfsDev d;
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
   static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
   VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
   VFS_HD static int jorg(int by) { return by * (TY - 2); }
-  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, double *sm) const {
+  VFS_HD void phase0(State &st, int tid, int bx, int by, int k, bool, double *sm) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     double K[NV] = {0, 0, 0};
     st.nvc = 0;
