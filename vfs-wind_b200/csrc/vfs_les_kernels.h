@@ -112,6 +112,16 @@ VFS_HD void les_derive_store(const VfsDev &d, long n, const double g[3][3], doub
   d.s[S_LSS0][n] = (0.5 * (g[0][0] + g[0][0])) * S; d.s[S_LSS1][n] = (0.5 * (g[0][1] + g[1][0])) * S; d.s[S_LSS2][n] = (0.5 * (g[0][2] + g[2][0])) * S;
   d.s[S_LSS3][n] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][n] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][n] = (0.5 * (g[2][2] + g[2][2])) * S;
 }
+// same with the node's centre metrics already in registers
+VFS_HD void les_derive_store_m(const VfsDev &d, long n, const double g[3][3], double S, const double *m) {
+  d.s[S_LW][n] = (d.s[S_NV][n] > 0.1) ? 0. : d.s[S_IAJ][n];
+  const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
+  d.s[S_LU0][n] = u0 * m[0] + u1 * m[1] + u2 * m[2];
+  d.s[S_LU1][n] = u0 * m[3] + u1 * m[4] + u2 * m[5];
+  d.s[S_LU2][n] = u0 * m[6] + u1 * m[7] + u2 * m[8];
+  d.s[S_LSS0][n] = (0.5 * (g[0][0] + g[0][0])) * S; d.s[S_LSS1][n] = (0.5 * (g[0][1] + g[1][0])) * S; d.s[S_LSS2][n] = (0.5 * (g[0][2] + g[2][0])) * S;
+  d.s[S_LSS3][n] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][n] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][n] = (0.5 * (g[2][2] + g[2][2])) * S;
+}
 // domain-boundary nodes: grad u and |S| are zero there in the reference (VecSet, les.c:183-186)
 struct LesDeriveBoundary {
   VfsDev d;
@@ -121,20 +131,30 @@ struct LesDeriveBoundary {
   }
 };
 
+// accessor adaptor: the cell's own metrics fetched up front (their global-load latency then overlaps the
+// shared-memory test filter that does not need them), everything else forwarded
+template <class Acc> struct PreMet {
+  const Acc &A; double m[9], ajv;
+  VFS_HD PreMet(const Acc &a) : A(a) {
+#pragma unroll
+    for (int s = 0; s < 9; s++) m[s] = a.met(s);
+    ajv = a.aj();
+  }
+  VFS_HD double met(int s) const { return m[s]; }
+  VFS_HD double aj() const { return ajv; }
+  VFS_HD double u(int a, int di, int dj, int dk) const { return A.u(a, di, dj, dk); }
+  VFS_HD double nv(int di, int dj, int dk) const { return A.nv(di, dj, dk); }
+};
 // les.c:199-246: grad u, |S| and the test-filtered velocity (+ the per-node derived quantities)
-template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
-  if (A.nv(0, 0, 0) > 1.1) {   // skipped by the reference: its zero-initialised work vectors keep 0 here
+template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A0, int i, int j, int kg, long p) {
+  if (A0.nv(0, 0, 0) > 1.1) {   // skipped by the reference: its zero-initialised work vectors keep 0 here
     const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     d.s[S_SABS][p] = 0;
     for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = 0;
     les_derive_store(d, p, z, 0.);
     return;
   }
-  double g[3][3];
-  grad_center_auto(d, A, i, j, kg, p, g);
-  const double S = sabs_of(g);
-  d.s[S_SABS][p] = S;
-  les_derive_store(d, p, g, S);
+  const PreMet<Acc> A(A0);
   double uf[3];
   if (d.testfilter_ik) {
 #pragma unroll
@@ -148,7 +168,7 @@ template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i,
       for (int q = -1; q <= 1; q++)
 #pragma unroll
         for (int pp = -1; pp <= 1; pp++) {
-          const double w = (A.nv(pp, q, r) > 0.1) ? 0. : A.iaj(pp, q, r);
+          const double w = (A0.nv(pp, q, r) > 0.1) ? 0. : A0.iaj(pp, q, r);
           const double sw = simpson_w(r, q, pp) * w;
           ws += sw;
 #pragma unroll
@@ -157,6 +177,11 @@ template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A, int i,
     for (int a = 0; a < 3; a++) uf[a] = vs[a] / ws;
   }
   for (int a = 0; a < 3; a++) d.s[S_UF0 + a][p] = uf[a];
+  double g[3][3];
+  grad_center_auto(d, A, i, j, kg, p, g);
+  const double S = sabs_of(g);
+  d.s[S_SABS][p] = S;
+  les_derive_store_m(d, p, g, S, A.m);
 }
 struct LesPass1 {
   VfsDev d;

@@ -71,6 +71,7 @@ template <int TY_> struct Les2MarchT {
   // The per-node inputs of planes k-1 and k are carried in registers from the previous step (st.win),
   // so each step fetches one new plane (13 values) instead of three: this kernel's limiter was the
   // L2 -> SM traffic of re-reading every plane three times (profiles/r01l: 12.4 GB through L2 in 2.3 ms).
+  // (Staging the new plane by TMA one step ahead instead of loading it here was measured slower, 2.04 vs 1.92 ms.)
   VFS_HD static void load_raw(const VfsDev &d, long n, double *r) {
     r[0] = d.s[S_LW][n];
 #pragma unroll
