@@ -55,9 +55,8 @@ enum {
   S_LW, S_LU0, S_LU1, S_LU2, S_LSS0, S_LSS1, S_LSS2, S_LSS3, S_LSS4, S_LSS5,
   S_IAJ,                                                                 // 1/aj (cell volume), filter weight
   // LES factors that depend on the grid and the nvert mask only (LesGeo, vfs_les_kernels.h):
-  // 1/sum(s*w), test_filter^2, filter^2 and the inverse of [csi;eta;zet] (row-major x_csi x_eta x_zet y_csi ...;
-  // rhs2.c:595-611 builds the covariant metric tensor G from it, les.c:607-622)
-  S_LFINV, S_LTF2, S_LF2, S_LG0, S_LG1, S_LG2, S_LG3, S_LG4, S_LG5, S_LG6, S_LG7, S_LG8,
+  // 1/sum(s*w), test_filter^2, filter^2
+  S_LFINV, S_LTF2, S_LF2,
   S_WM,                                                                  // wall-model nu_t of the j = 0 faces (plane j = 0 only)
   S_COUNT
 };

@@ -89,6 +89,7 @@ struct vfs_ctx {
   CUtensorMap tmap_les2;         // same pool, box (32, 16): operand tiles of the LES pass-2 marching kernel
   CUtensorMap tmap_les2_8;       // same pool, box (32, 8)
   CUtensorMap tmap_les2_12;      // same pool, box (32, 12)
+  CUtensorMap tmap_les2i, tmap_les2i_8, tmap_les2i_12;   // inner-row boxes (32, TY - 2) of the LES pass-2 tiles
   CUtensorMap tmap_fluxA, tmap_fluxB;   // boxes of k_flux_march: ucat (36, 19), metrics (34, 17)
 #endif
   bool tma_ok = false;
@@ -112,7 +113,7 @@ struct vfs_ctx {
   int les3_var = 0;              // LES pass 3: 0 = block program 32x16 x2/SM, 1 = TMA tile march (option key 5)
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
-  bool lesgeo_valid = false;     // S_LFINV..S_LG5 match the current metrics and nvert mask
+  bool lesgeo_valid = false;     // S_LFINV..S_LF2 match the current metrics and nvert mask
   unsigned char *near = nullptr; // near-solid byte mask (VfsDev::near), one byte per padded node
   bool near_valid = false;
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
@@ -378,6 +379,9 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
               vfs_make_tensor_map(&c->tmap_les2, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY) == 0 &&
               vfs_make_tensor_map(&c->tmap_les2_8, c->pool, c->d, c->scalar_len, Les2March8::TX, Les2March8::TY) == 0 &&
               vfs_make_tensor_map(&c->tmap_les2_12, c->pool, c->d, c->scalar_len, Les2March12::TX, Les2March12::TY) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2i, c->pool, c->d, c->scalar_len, Les2March::TX, Les2March::TY - 2) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2i_8, c->pool, c->d, c->scalar_len, Les2March8::TX, Les2March8::TY - 2) == 0 &&
+              vfs_make_tensor_map(&c->tmap_les2i_12, c->pool, c->d, c->scalar_len, Les2March12::TX, Les2March12::TY - 2) == 0 &&
               vfs_make_tensor_map(&c->tmap_fluxA, c->pool, c->d, c->scalar_len, FluxMarch::AX, FluxMarch::AY) == 0 &&
               vfs_make_tensor_map(&c->tmap_fluxB, c->pool, c->d, c->scalar_len, FluxMarch::BX, FluxMarch::BY) == 0;
 #endif
@@ -961,9 +965,9 @@ static int les_cs(vfs_ctx *c) {
     if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
     int r;
 #ifndef VFS_EMU
-    if (c->les2_ty == 8) { Les2March8 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_8, prog, bi.k0, bi.k1, &c->launches); }
-    else if (c->les2_ty == 12) { Les2March12 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_12, prog, bi.k0, bi.k1, &c->launches); }
-    else { Les2March prog = {d}; r = run_les2_march(c->stream, c->tmap_les2, prog, bi.k0, bi.k1, &c->launches); }
+    if (c->les2_ty == 8) { Les2March8 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_8, c->tmap_les2i_8, prog, bi.k0, bi.k1, &c->launches); }
+    else if (c->les2_ty == 12) { Les2March12 prog = {d}; r = run_les2_march(c->stream, c->tmap_les2_12, c->tmap_les2i_12, prog, bi.k0, bi.k1, &c->launches); }
+    else { Les2March prog = {d}; r = run_les2_march(c->stream, c->tmap_les2, c->tmap_les2i, prog, bi.k0, bi.k1, &c->launches); }
 #else
     if (c->les2_ty == 8) { Les2March8 prog = {d}; r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches); }
     else if (c->les2_ty == 12) { Les2March12 prog = {d}; r = run_les2_march(c->stream, prog, bi.k0, bi.k1, &c->launches); }

@@ -27,7 +27,7 @@ template <int S0> struct GlobalAccS {
   VFS_HD double u(int a, int di, int dj, int dk) const { return d.s[S0 + a][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double nv(int di, int dj, int dk) const { return d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
   VFS_HD double iaj(int di, int dj, int dk) const { return d.s[S_IAJ][p + di + dj * d.sj + dk * d.sk]; }
-  // the cell's own centre metrics (s = 0..8: csi, eta, zet), aj, and LES grid factors (q = 0..11: S_LFINV..S_LG8)
+  // the cell's own centre metrics (s = 0..8: csi, eta, zet), aj, and LES grid factors (q = 0..2: S_LFINV, S_LTF2, S_LF2)
   VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
   VFS_HD double aj() const { return d.s[S_AJ][p]; }
   VFS_HD double geo(int q) const { return d.s[S_LFINV + q][p]; }
@@ -288,16 +288,6 @@ struct LesGeo {
     const double filter = VFS_CBRT(1. / d.s[S_AJ][p]);
     const double test_filter = VFS_CBRT(sum_weight);
     d.s[S_LFINV][p] = 1. / fdiv; d.s[S_LTF2][p] = test_filter * test_filter; d.s[S_LF2][p] = filter * filter;
-    const double a11 = d.s[S_CSI0][p], a12 = d.s[S_CSI1][p], a13 = d.s[S_CSI2][p];
-    const double a21 = d.s[S_ETA0][p], a22 = d.s[S_ETA1][p], a23 = d.s[S_ETA2][p];
-    const double a31 = d.s[S_ZET0][p], a32 = d.s[S_ZET1][p], a33 = d.s[S_ZET2][p];
-    const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
-    const double xcsi = (a33 * a22 - a32 * a23) / det, xeta = -(a33 * a12 - a32 * a13) / det, xzet = (a23 * a12 - a22 * a13) / det;
-    const double ycsi = -(a33 * a21 - a31 * a23) / det, yeta = (a33 * a11 - a31 * a13) / det, yzet = -(a23 * a11 - a21 * a13) / det;
-    const double zcsi = (a32 * a21 - a31 * a22) / det, zeta = -(a32 * a11 - a31 * a12) / det, zzet = (a22 * a11 - a21 * a12) / det;
-    d.s[S_LG0][p] = xcsi; d.s[S_LG1][p] = xeta; d.s[S_LG2][p] = xzet;
-    d.s[S_LG3][p] = ycsi; d.s[S_LG4][p] = yeta; d.s[S_LG5][p] = yzet;
-    d.s[S_LG6][p] = zcsi; d.s[S_LG7][p] = zeta; d.s[S_LG8][p] = zzet;
   }
 };
 
@@ -306,9 +296,10 @@ struct LesGeo {
 // Cartesian tensor M^c to M = M^c A^T and contracts with the covariant metric tensor G = (A A^T)^-1:
 //   MM = sum M_nm M_nl G_ml  = tr(A M^cT M^c A^T (A A^T)^-1) = |M^c|_F^2          (A^T (A A^T)^-1 A = I)
 //   LM = sum L_ba M_aq G_bq  = tr(L M^c A^T (A A^T)^-1)      = tr(L M^c A^-1)     (A^T (A A^T)^-1 = A^-1)
-// so neither M nor G is formed: 6 + 36 multiply-adds instead of the 162 of the literal triple loops,
-// and the metric-independent MM loses the rounding of the rotation.  Agrees with the reference to
-// rounding (tests: <= 1e-12 on Cs, nu_t).
+// so neither M nor G is formed.  A^-1 = adj(A) / det(A) (rhs2.c:595-611) is built from the centre metrics the
+// kernel holds anyway — nine cofactors, the reference's determinant expression and ONE division applied to the
+// contracted sum — rather than read as nine more per-node operands (the marching kernel is bound by its
+// L2 -> SM operand traffic, profiles/r01p).  Agrees with the reference to rounding (tests: <= 1e-12 on Cs, nu_t).
 template <class Ops> VFS_HD void les2_finish_geo(const VfsDev &d, const Ops &O, int i, int j, int kg, long p, const double *f) {
   const double finv = O.geo(0), tf2 = O.geo(1), f2 = O.geo(2);
   double gh[3][3];
@@ -322,15 +313,22 @@ template <class Ops> VFS_HD void les2_finish_geo(const VfsDev &d, const Ops &O, 
   const double den = (mc0 * mc0 + mc3 * mc3 + mc5 * mc5) + 2. * (mc1 * mc1 + mc2 * mc2 + mc4 * mc4);
   const double Mc[3][3] = {{mc0, mc1, mc2}, {mc1, mc3, mc4}, {mc2, mc4, mc5}};
   const double _u[3] = {O.u(0, 0, 0, 0), O.u(1, 0, 0, 0), O.u(2, 0, 0, 0)};
+  const double a11 = O.met(0), a12 = O.met(1), a13 = O.met(2), a21 = O.met(3), a22 = O.met(4), a23 = O.met(5), a31 = O.met(6), a32 = O.met(7), a33 = O.met(8);
+  const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+  // adj[c][b] = det * A^-1[c][b]: (x,y,z)_c by (csi,eta,zet)_b
+  const double adj[3][3] = {{(a33 * a22 - a32 * a23), -(a33 * a12 - a32 * a13), (a23 * a12 - a22 * a13)},
+                            {-(a33 * a21 - a31 * a23), (a33 * a11 - a31 * a13), -(a23 * a11 - a21 * a13)},
+                            {(a32 * a21 - a31 * a22), -(a32 * a11 - a31 * a12), (a22 * a11 - a21 * a12)}};
+  const double A[3][3] = {{a11, a12, a13}, {a21, a22, a23}, {a31, a32, a33}};
   double num = 0;
 #pragma unroll
   for (int b = 0; b < 3; b++) {
-    const double Ub = _u[0] * O.met(3 * b) + _u[1] * O.met(3 * b + 1) + _u[2] * O.met(3 * b + 2);     // filtered contravariant velocity
+    const double Ub = _u[0] * A[b][0] + _u[1] * A[b][1] + _u[2] * A[b][2];     // filtered contravariant velocity
     const double L0 = f[3 * b] * finv - Ub * _u[0], L1 = f[3 * b + 1] * finv - Ub * _u[1], L2 = f[3 * b + 2] * finv - Ub * _u[2];
 #pragma unroll
-    for (int c = 0; c < 3; c++) num += (L0 * Mc[0][c] + L1 * Mc[1][c] + L2 * Mc[2][c]) * O.geo(3 + 3 * c + b);   // A^-1[c][b]
+    for (int c = 0; c < 3; c++) num += (L0 * Mc[0][c] + L1 * Mc[1][c] + L2 * Mc[2][c]) * adj[c][b];
   }
-  d.s[S_LM][p] = num; d.s[S_MM][p] = den;
+  d.s[S_LM][p] = num / det; d.s[S_MM][p] = den;
 }
 
 // les.c:308-669: Germano identity contracted with the covariant metric tensor -> LM, MM

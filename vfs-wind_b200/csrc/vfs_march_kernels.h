@@ -46,12 +46,15 @@ static inline int pick_kchunk(int ntiles, int nk, int min_chunk, int nsm = 148) 
 // issues the copies for the next plane, so nobody waits to refill the single buffer and the ~30
 // scattered global loads that stalled the finish (profiles/r01j) become shared-memory reads.
 template <int TY_> struct Les2MarchT {
-  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15, NOP = 26;
+  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 15;
+  // finish operands: NOPI scalars read at the node itself (staged for the tile's inner rows only, NTI nodes) and
+  // NOPF scalars whose i/j neighbours are read too (whole tile)
+  static constexpr int NOPI = 13, NOPF = 4, NOP = NOPI + NOPF, NTI = TX * (TY - 2);
   static constexpr int MINB = TY_ <= 8 ? 2 : 1;                      // resident blocks per SM the tile is sized for
-  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_BAR = OFF_OP + NOP * NT;
+  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_OPF = OFF_OP + NOPI * NTI, OFF_BAR = OFF_OPF + NOPF * NT;
   static constexpr long SMEM_D = OFF_BAR + 2;
-  // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..21 LFINV,LTF2,LF2,LG0..8 | 22..24 UF | 25 nvert
-  VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 22 ? S_LFINV + (q - 10) : (q < 25 ? S_UF0 + (q - 22) : S_NV)); }
+  // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..12 LFINV,LTF2,LF2 || 13..15 UF | 16 nvert
+  VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 13 ? S_LFINV + (q - 10) : (q < 16 ? S_UF0 + (q - 13) : S_NV)); }
   static constexpr int NRAW = 13;
   struct State { double v[NV]; double ufk[6]; double nvk[2]; double win[2][NRAW]; };
   VfsDev d;
@@ -60,12 +63,12 @@ template <int TY_> struct Les2MarchT {
   VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
   VFS_HD static int jorg(int by) { return by * (TY - 2); }
   struct Ops {        // finish operands: plane k from the staged buffer, planes k-1/k+1 of UF and nvert from registers
-    const double *op; double ufk[6], nvk[2];
-    VFS_HD double met(int s) const { return op[s * NT]; }
-    VFS_HD double aj() const { return op[9 * NT]; }
-    VFS_HD double geo(int q) const { return op[(10 + q) * NT]; }
-    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? op[(22 + a) * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
-    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? op[25 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
+    const double *op, *opf; double ufk[6], nvk[2];      // op: inner-row tiles at the node, opf: whole-tile tiles at the node
+    VFS_HD double met(int s) const { return op[s * NTI]; }
+    VFS_HD double aj() const { return op[9 * NTI]; }
+    VFS_HD double geo(int q) const { return op[(10 + q) * NTI]; }
+    VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? opf[a * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
+    VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? opf[3 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
   };
   // phase 0: k pass over the thread's own column (+ the k-neighbours of UF / nvert the finish needs).
   // The per-node inputs of planes k-1 and k are carried in registers from the previous step (st.win),
@@ -124,7 +127,7 @@ template <int TY_> struct Les2MarchT {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
     const long p = d.idx(i, j, k);
-    Ops O; O.op = sm + OFF_OP + tid;
+    Ops O; O.op = sm + OFF_OP + (tid - TX); O.opf = sm + OFF_OPF + tid;
     if (O.nv(0, 0, 0) > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
 #pragma unroll
     for (int a = 0; a < 6; a++) O.ufk[a] = st.ufk[a];
@@ -143,7 +146,8 @@ typedef Les2MarchT<8> Les2March8;      // two 256-thread blocks per SM: the phas
 
 #ifndef VFS_EMU
 #include "vfs_fused_kernels.h"
-template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_march(const __grid_constant__ CUtensorMap tmap, const M P, int kbeg, int kend, int kchunk) {
+// tmap: box (TX, TY) = the whole tile; tmapi: box (TX, TY-2) = its inner rows
+template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapi, const M P, int kbeg, int kend, int kchunk) {
   extern __shared__ __align__(128) double vfs_les2_sm[];
   double *sm = vfs_les2_sm;
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR);
@@ -151,10 +155,12 @@ template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_marc
   const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
   const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
   if (ka >= kb) return;
-  auto issue = [&](int k) {       // one thread: the 23 operand tiles of plane k -> shared memory
-    mbar_expect_tx(bar, M::NOP * M::NT * 8);
+  auto issue = [&](int k) {       // one thread: the operand tiles of plane k -> shared memory
+    mbar_expect_tx(bar, (M::NOPI * M::NTI + M::NOPF * M::NT) * 8);
 #pragma unroll 1
-    for (int q = 0; q < M::NOP; q++) tma_load_tile(sm + M::OFF_OP + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(q), bar);
+    for (int q = 0; q < M::NOPI; q++) tma_load_tile(sm + M::OFF_OP + q * M::NTI, &tmapi, M::iorg(bx) + VFS_G, M::jorg(by) + 1 + VFS_G, k + VFS_G, M::op_sid(q), bar);
+#pragma unroll 1
+    for (int q = 0; q < M::NOPF; q++) tma_load_tile(sm + M::OFF_OPF + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(M::NOPI + q), bar);
   };
   if (tid == 0) {
     mbar_init(bar, 1); *cnt = 0;
@@ -182,7 +188,7 @@ template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_marc
     }
   }
 }
-template <class M> static inline int run_les2_march(cudaStream_t stream, const CUtensorMap &tmap, const M &P, int k0, int k1, long *launches) {
+template <class M> static inline int run_les2_march(cudaStream_t stream, const CUtensorMap &tmap, const CUtensorMap &tmapi, const M &P, int k0, int k1, long *launches) {
   if (k1 <= k0) return 0;
   static bool attr_set = false;
   const int bytes = (int)(M::SMEM_D * sizeof(double));
@@ -193,7 +199,7 @@ template <class M> static inline int run_les2_march(cudaStream_t stream, const C
   const int ntx = M::tiles_x(P.d), nty = M::tiles_y(P.d);
   const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16, 148 * M::MINB);
   dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk);
-  k_les2_march<M><<<grd, M::NT, bytes, stream>>>(tmap, P, k0, k1, kchunk);
+  k_les2_march<M><<<grd, M::NT, bytes, stream>>>(tmap, tmapi, P, k0, k1, kchunk);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -211,13 +217,16 @@ template <class M> static inline int run_les2_march(void *, const M &P, int k0, 
       for (int bx = 0; bx < ntx; bx++) {
         const int ka = k0 + bz * kchunk, kb = k1 < ka + kchunk ? k1 : ka + kchunk;
         auto issue = [&](int k) {       // what the TMA unit does: box copy with zero fill outside the padded array
-          for (int q = 0; q < M::NOP; q++)
-            for (int y = 0; y < M::TY; y++)
+          for (int q = 0; q < M::NOP; q++) {
+            const bool inner = q < M::NOPI;       // inner-row box (rows 1 .. TY-2) or the whole tile
+            double *dst = inner ? sm + M::OFF_OP + q * M::NTI : sm + M::OFF_OPF + (q - M::NOPI) * M::NT;
+            for (int y = 0; y < (inner ? M::TY - 2 : M::TY); y++)
               for (int x = 0; x < M::TX; x++) {
-                const int X = M::iorg(bx) + VFS_G + x, Y = M::jorg(by) + VFS_G + y, Z = k + VFS_G;
+                const int X = M::iorg(bx) + VFS_G + x, Y = M::jorg(by) + VFS_G + y + (inner ? 1 : 0), Z = k + VFS_G;
                 const bool in = X >= 0 && X < d.pitch && Y >= 0 && Y < d.ny && Z >= 0 && Z < d.nzt;
-                sm[M::OFF_OP + q * M::NT + y * M::TX + x] = in ? d.s[M::op_sid(q)][(long)Z * d.sk + (long)Y * d.sj + X] : 0.;
+                dst[y * M::TX + x] = in ? d.s[M::op_sid(q)][(long)Z * d.sk + (long)Y * d.sj + X] : 0.;
               }
+          }
         };
         issue(ka);
         for (int k = ka; k < kb; k++) {
