@@ -127,10 +127,12 @@ k_tile_march(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int k
   }
   for (int kk = kfirst; kk < ka + PA; kk++) wait_plane(kk);
   for (int k = ka; k < kb; k++) {
+    // operands the body reads from global memory at its own node are requested before the TMA wait
+    const auto pf = body.prefetch(d, active ? i : 1, active ? j : 1, k);
     wait_plane(k + PA);
     if (active) {
       TileAcc<R> A = {sm, k - kfirst, tx + R::OX, ty + R::OY};
-      body(d, A, i, j, k);
+      body(d, A, i, j, k, pf);
     }
     __syncthreads();                         // plane k-PB is no longer needed by anyone
     if (tid == 0) {
@@ -156,18 +158,28 @@ static inline int launch_tile_march(cudaStream_t st, const CUtensorMap &tmap, co
 
 // ---- LES pass 1 (les.c:199-246): staged ucat(3), aj, nvert; 27-point box ------------------------------
 typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 5, 4, 2, 2, 1, 1, 1, 1> RingLes1;
+struct Les1Pre { double m[9], aj; unsigned char nearv; };
 struct Les1Acc {
-  TileAcc<RingLes1> T; const VfsDev &d; long p;
-  __device__ __forceinline__ double met(int s) const { return d.s[S_CSI0 + s][p]; }
-  __device__ __forceinline__ double aj() const { return d.s[S_AJ][p]; }
+  TileAcc<RingLes1> T; const VfsDev &d; long p; const Les1Pre &pf;
+  __device__ __forceinline__ double met(int s) const { return pf.m[s]; }
+  __device__ __forceinline__ double aj() const { return pf.aj; }
+  __device__ __forceinline__ unsigned char nearv(const VfsDev &, long) const { return pf.nearv; }
   __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return T.get(a, di, dj, dk); }
   __device__ __forceinline__ double iaj(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(4, di, dj, dk); }
 };
 struct Les1Body {
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k) const {
+  __device__ __forceinline__ Les1Pre prefetch(const VfsDev &d, int i, int j, int k) const {
     const long p = d.idx(i, j, k);
-    Les1Acc A = {T, d, p};
+    Les1Pre f;
+#pragma unroll
+    for (int s = 0; s < 9; s++) f.m[s] = d.s[S_CSI0 + s][p];
+    f.aj = d.s[S_AJ][p]; f.nearv = d.near[p];
+    return f;
+  }
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k, const Les1Pre &pf) const {
+    const long p = d.idx(i, j, k);
+    Les1Acc A = {T, d, p, pf};
     les1_core(d, A, i, j, k + d.kofs, p);
   }
 };
@@ -184,8 +196,10 @@ struct Les3Acc {
 VFS_HD bool les3_regular(const VfsDev &d, int i, int j, int kg) {
   return !(d.perx && (i == 1 || i == d.mx - 2)) && !(d.pery && (j == 1 || j == d.my - 2)) && !(d.perz && (kg == 1 || kg == d.mz - 2));
 }
+struct NoPrefetch {};
 struct Les3Body {
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k) const {
+  __device__ __forceinline__ NoPrefetch prefetch(const VfsDev &, int, int, int) const { return NoPrefetch(); }
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k, const NoPrefetch &) const {
     const int kg = k + d.kofs;
     if (!les3_regular(d, i, j, kg)) return;          // done by the staged kernel on thin slabs
     Les3Acc A = {T};
@@ -234,7 +248,8 @@ struct FluxBody {
       for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
     }
   }
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k) const {
+  __device__ __forceinline__ NoPrefetch prefetch(const VfsDev &, int, int, int) const { return NoPrefetch(); }
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k, const NoPrefetch &) const {
     const long p = d.idx(i, j, k);
     if (VFS_WARP_ANY(d.near[p] != 0)) run<false>(d, T, i, j, k + d.kofs, p);
     else run<true>(d, T, i, j, k + d.kofs, p);
@@ -263,6 +278,7 @@ template <bool FLUID> struct FluxAcc2 {
   const double *sa[4];      // ucat planes k-1, k, k+1, k+2 at the thread's node
   const double *sb[2];      // metric planes k, k+1 at the thread's node
   const VfsDev &d; long p;
+  double ucv[3], nutv[4];   // ucont (x, y, z) at p and nu_t at p, p+1, p+sj, p+sk: fetched before the TMA waits (see k_flux_march)
   __device__ __forceinline__ double u(int a, int di, int dj, int dk) const { return sa[dk + 1][a * FluxMarch::A_TILE + dj * FluxMarch::AX + di]; }
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return FLUID ? 0. : d.s[S_NV][p + di + dj * d.sj + dk * d.sk]; }
   template <int D> __device__ __forceinline__ long sn() const { return D == 0 ? 1 : (D == 1 ? d.sj : d.sk); }
@@ -270,8 +286,8 @@ template <bool FLUID> struct FluxAcc2 {
     return sb[D == 2 ? side : 0][s * FluxMarch::B_TILE + (D == 1 ? side * FluxMarch::BX : 0) + (D == 0 ? side : 0)];
   }
   template <int D> __device__ __forceinline__ double iaj(int side) const { return met<D>(9, side); }
-  template <int D> __device__ __forceinline__ double nut(int side) const { return d.s[S_NUT][p + side * sn<D>()]; }
-  template <int D> __device__ __forceinline__ double uc(int off) const { return d.s[S_UC0 + D][p + off * sn<D>()]; }
+  template <int D> __device__ __forceinline__ double nut(int side) const { return side ? nutv[1 + D] : nutv[0]; }
+  template <int D> __device__ __forceinline__ double uc(int off) const { return off == 0 ? ucv[D] : d.s[S_UC0 + D][p + off * sn<D>()]; }
 };
 template <bool FLUID, class Acc> __device__ __forceinline__ void flux_node(const VfsDev &d, const Acc &A, int i, int j, int kg, long p) {
   double fc[3], fv[3];
@@ -327,19 +343,24 @@ k_flux_march(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
   for (int kk = kfa; kk < ka + 2; kk++) mbar_wait(&barA[(kk - kfa) % M::A_ST], ((kk - kfa) / M::A_ST) & 1);
   mbar_wait(&barB[0], 0);
   for (int k = ka; k < kb; k++) {
+    // the few operands that stay in global memory are requested first: their latency overlaps the TMA waits
+    // and the stencil differences (profiles/r01q: issued at their point of use they cost 5.6 of 13 stall cycles)
+    const long p = d.idx(active ? i : 1, active ? j : 1, k);
+    const unsigned char nearv = d.near[p];
+    const double uc0 = d.s[S_UC0][p], uc1 = d.s[S_UC1][p], uc2 = d.s[S_UC2][p];
+    const double nt0 = d.s[S_NUT][p], nt1 = d.s[S_NUT][p + 1], nt2 = d.s[S_NUT][p + d.sj], nt3 = d.s[S_NUT][p + d.sk];
     mbar_wait(&barA[(k + 2 - kfa) % M::A_ST], ((k + 2 - kfa) / M::A_ST) & 1);
     mbar_wait(&barB[(k + 1 - kfb) % M::B_ST], ((k + 1 - kfb) / M::B_ST) & 1);
     if (active) {
-      const long p = d.idx(i, j, k);
       const double *ta = sm + (ty + 1) * M::AX + (tx + 1), *tb = sm + M::OFF_B + ty * M::BX + tx + 1;
       const int na = k - kfa, nb = k - kfb;
-      if (VFS_WARP_ANY(d.near[p] != 0)) {
+      if (VFS_WARP_ANY(nearv != 0)) {
         FluxAcc2<false> A = {{ta + ((na - 1) % M::A_ST) * M::A_PLANE, ta + (na % M::A_ST) * M::A_PLANE, ta + ((na + 1) % M::A_ST) * M::A_PLANE, ta + ((na + 2) % M::A_ST) * M::A_PLANE},
-                             {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p};
+                             {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p, {uc0, uc1, uc2}, {nt0, nt1, nt2, nt3}};
         flux_node<false>(d, A, i, j, k + d.kofs, p);
       } else {
         FluxAcc2<true> A = {{ta + ((na - 1) % M::A_ST) * M::A_PLANE, ta + (na % M::A_ST) * M::A_PLANE, ta + ((na + 1) % M::A_ST) * M::A_PLANE, ta + ((na + 2) % M::A_ST) * M::A_PLANE},
-                            {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p};
+                            {tb + (nb % M::B_ST) * M::B_PLANE, tb + ((nb + 1) % M::B_ST) * M::B_PLANE}, d, p, {uc0, uc1, uc2}, {nt0, nt1, nt2, nt3}};
         flux_node<true>(d, A, i, j, k + d.kofs, p);
       }
     }

@@ -31,6 +31,7 @@ template <int S0> struct GlobalAccS {
   VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
   VFS_HD double aj() const { return d.s[S_AJ][p]; }
   VFS_HD double geo(int q) const { return d.s[S_LFINV + q][p]; }
+  VFS_HD unsigned char nearv(const VfsDev &dd, long pp) const { return dd.near[pp]; }
 };
 
 // centre difference of component a along direction T (k-omega.c:318-430); lowc = 1 for i/j, 0 for k
@@ -69,7 +70,7 @@ template <bool PLAIN = false, class Acc> VFS_HD void grad_center_a(const VfsDev 
 }
 // warp-uniform choice between the two (VfsDev::near, VFS_WARP_ANY)
 template <class Acc> VFS_HD void grad_center_auto(const VfsDev &d, const Acc &A, int i, int j, int kg, long p, double g[3][3]) {
-  const bool special = d.near[p] != 0 || i <= 1 || i >= d.mx - 2 || j <= 1 || j >= d.my - 2 || kg <= 1 || kg >= d.mz - 2;
+  const bool special = A.nearv(d, p) != 0 || i <= 1 || i >= d.mx - 2 || j <= 1 || j >= d.my - 2 || kg <= 1 || kg >= d.mz - 2;
   if (VFS_WARP_ANY(special)) grad_center_a<false>(d, A, i, j, kg, p, g);
   else grad_center_a<true>(d, A, i, j, kg, p, g);
 }
@@ -113,9 +114,8 @@ VFS_HD void les_derive_store(const VfsDev &d, long n, const double g[3][3], doub
   d.s[S_LSS3][n] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][n] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][n] = (0.5 * (g[2][2] + g[2][2])) * S;
 }
 // same with the node's centre metrics already in registers
-VFS_HD void les_derive_store_m(const VfsDev &d, long n, const double g[3][3], double S, const double *m) {
-  d.s[S_LW][n] = (d.s[S_NV][n] > 0.1) ? 0. : d.s[S_IAJ][n];
-  const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
+VFS_HD void les_derive_store_m(const VfsDev &d, long n, const double g[3][3], double S, const double *m, double nv, double iaj, double u0, double u1, double u2) {
+  d.s[S_LW][n] = (nv > 0.1) ? 0. : iaj;
   d.s[S_LU0][n] = u0 * m[0] + u1 * m[1] + u2 * m[2];
   d.s[S_LU1][n] = u0 * m[3] + u1 * m[4] + u2 * m[5];
   d.s[S_LU2][n] = u0 * m[6] + u1 * m[7] + u2 * m[8];
@@ -144,6 +144,7 @@ template <class Acc> struct PreMet {
   VFS_HD double aj() const { return ajv; }
   VFS_HD double u(int a, int di, int dj, int dk) const { return A.u(a, di, dj, dk); }
   VFS_HD double nv(int di, int dj, int dk) const { return A.nv(di, dj, dk); }
+  VFS_HD unsigned char nearv(const VfsDev &dd, long pp) const { return A.nearv(dd, pp); }
 };
 // les.c:199-246: grad u, |S| and the test-filtered velocity (+ the per-node derived quantities)
 template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A0, int i, int j, int kg, long p) {
@@ -181,7 +182,7 @@ template <class Acc> VFS_HD void les1_core(const VfsDev &d, const Acc &A0, int i
   grad_center_auto(d, A, i, j, kg, p, g);
   const double S = sabs_of(g);
   d.s[S_SABS][p] = S;
-  les_derive_store_m(d, p, g, S, A.m);
+  les_derive_store_m(d, p, g, S, A.m, A0.nv(0, 0, 0), A0.iaj(0, 0, 0), A.u(0, 0, 0, 0), A.u(1, 0, 0, 0), A.u(2, 0, 0, 0));
 }
 struct LesPass1 {
   VfsDev d;

@@ -69,6 +69,7 @@ template <int TY_> struct Les2MarchT {
     VFS_HD double geo(int q) const { return op[(10 + q) * NTI]; }
     VFS_HD double u(int a, int di, int dj, int dk) const { return dk == 0 ? opf[a * NT + dj * TX + di] : (dk < 0 ? ufk[a] : ufk[3 + a]); }
     VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? opf[3 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
+    VFS_HD unsigned char nearv(const VfsDev &dd, long pp) const { return dd.near[pp]; }
   };
   // phase 0: k pass over the thread's own column (+ the k-neighbours of UF / nvert the finish needs).
   // The per-node inputs of planes k-1 and k are carried in registers from the previous step (st.win),
@@ -280,6 +281,7 @@ template <int TY_> struct Les1MarchT {
     VFS_HD double nv(int di, int dj, int dk) const { return dk == 0 ? su[3 * NT + dj * TX + di] : (dk < 0 ? nvk[0] : nvk[1]); }
     VFS_HD double met(int s) const { return d.s[S_CSI0 + s][p]; }
     VFS_HD double aj() const { return d.s[S_AJ][p]; }
+    VFS_HD unsigned char nearv(const VfsDev &dd, long pp) const { return dd.near[pp]; }
   };
   VFS_HD void phase0(State &st, int tid, int bx, int by, int k, bool, double *sm) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
