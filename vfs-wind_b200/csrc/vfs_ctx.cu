@@ -116,6 +116,7 @@ struct vfs_ctx {
   bool lesgeo_valid = false;     // S_LFINV..S_LF2 match the current metrics and nvert mask
   unsigned char *near = nullptr; // near-solid byte mask (VfsDev::near), one byte per padded node
   bool near_valid = false;
+  int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
 };
 
@@ -216,6 +217,7 @@ static int klo(const vfs_ctx *c, int kg) { int k = kg - c->d.kofs; return k < 0 
 static Box box_interior(const vfs_ctx *c) { Box b = {1, c->d.mx - 1, 1, c->d.my - 1, klo(c, 1), klo(c, c->d.mz - 1)}; return b; }
 
 // ---- ghost refresh primitives -------------------------------------------------------------------
+static bool any_per_d(const VfsDev &d) { return d.perx || d.pery || d.perz; }
 static int wrap_ij(vfs_ctx *c, const Grp &g, int ka = 0, int kb = -1) {
   const VfsDev &d = c->d;
   if (kb < 0) kb = d.nzl;
@@ -296,8 +298,37 @@ static int halo_k(vfs_ctx *c, const Grp &g, bool seam_only = false) {
   if (d.perz) { WrapFill f = {d, g, 2}; Box b = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, 0, 2 * VFS_G}; RUN(launch(c, b, f)); }
   return 0;
 }
+#ifndef VFS_EMU
+template <class F> __global__ void __launch_bounds__(256) k_linear(F f, long n) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) f(t);
+}
+#endif
+// single rank: the whole refresh (mode 1: g2l, mode 3: g2l + node_copy + g2l) as one launch, see RefreshFused
+static int refresh_fused(vfs_ctx *c, const Grp &g, int mode) {
+  const VfsDev &d = c->d;
+  if (!any_per_d(d)) return 0;
+  RefreshSlabs S;
+  S.ext[0] = d.perx ? d.mx + 2 * VFS_G : d.mx; S.ext[1] = d.pery ? d.my + 2 * VFS_G : d.my; S.ext[2] = d.perz ? d.mz + 2 * VFS_G : d.mz;
+  const long W = 2 * VFS_G + 2;
+  S.n[0] = d.perx ? W * S.ext[1] * S.ext[2] : 0; S.n[1] = d.pery ? W * S.ext[0] * S.ext[2] : 0; S.n[2] = d.perz ? W * S.ext[0] * S.ext[1] : 0;
+  const long n = S.n[0] + S.n[1] + S.n[2];
+  RefreshFused f = {d, g, mode, S};
+  c->launches++;
+#ifndef VFS_EMU
+  k_linear<RefreshFused><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(f, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err(c, std::string("kernel launch: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+#else
+  for (long t = 0; t < n; t++) f(t);
+#endif
+  return 0;
+}
 // DAGlobalToLocal / DALocalToLocal
-static int g2l(vfs_ctx *c, const Grp &g) { RUN(wrap_ij(c, g)); return halo_k(c, g); }
+static int g2l(vfs_ctx *c, const Grp &g) {
+  if (c->prm.nranks == 1 && c->fuse_refresh) return refresh_fused(c, g, 1);
+  RUN(wrap_ij(c, g)); return halo_k(c, g);
+}
 // The refresh that follows a node_copy of a field whose ghosts were refreshed just before it: the
 // copy has already been applied to the ghost planes of interior slab boundaries (see node_copy), so
 // between ranks only the periodic seam (global planes 0 / mz-1 changed by the k copies) must travel.
@@ -494,6 +525,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 5) c->les3_var = value;
   else if (key == 6) { c->fastpath = value; c->near_valid = false; }
   else if (key == 7) c->flux_var = value;
+  else if (key == 8) c->fuse_refresh = value;
   graph_reset(c);
   return 0;
 }
@@ -621,14 +653,20 @@ static int contra2cart(vfs_ctx *c) {
     NodeCopy f = {d, g, 1};
     return launch_shell(c, ka, kb, f, true);
   };
+  // ghost refresh, periodic node copies, ghost refresh
+  auto refresh3 = [&]() -> int {
+    if (!multi && c->fuse_refresh) return refresh_fused(c, gu, 3);
+    RUN(refresh(false));
+    if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }
+    return 0;
+  };
   if (any_per(c)) RUN(copy_nodes(grp(S_UC0, 3)));                    // rhs.c:129-156
   ev_rec(c, 2 * VFS_T_C2C);
   Box bi = box_interior(c);
   if (multi) { bi.k0 = ka; bi.k1 = kb; }                             // the functors skip planes that are not interior (kglob)
   { C2CInterior f = {d}; RUN(launch(c, bi, f)); }                    // rhs.c:158-247
   ev_rec(c, 2 * VFS_T_C2C + 1);
-  RUN(refresh(false));
-  if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }       // rhs.c:254-291
+  RUN(refresh3());                                                   // rhs.c:251-291
   { CopyScalar3 f = {d, S_U0, S_FP0}; RUN(launch_shell(c, ka, kb, f, true)); }     // lUcat snapshot read by the rules
   { C2CGhostRules f = {d}; RUN(launch_shell(c, ka, kb, f, true)); }                // rhs.c:302-682 (boundary nodes)
   {                                                                  // rhs.c:305-308,676-681 (interior nodes)
@@ -641,8 +679,7 @@ static int contra2cart(vfs_ctx *c) {
       for (int q = 0; q < 4; q++) if (cor[q]) { Box b = {ci[q], ci[q] + 1, cj[q], cj[q] + 1, bi.k0, bi.k1}; RUN(launch(c, b, f)); }
     }
   }
-  RUN(refresh(false));
-  if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }       // rhs.c:712-748
+  RUN(refresh3());                                                   // rhs.c:690-748
   return 0;
 }
 extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return vfs_sync(c); }
@@ -800,12 +837,20 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   }
   ev_rec(c, 2 * VFS_T_FLUX + 1);
   ev_rec(c, 2 * VFS_T_FP);
-  Grp gf = grp(S_FC1, 18);
-  // momentum.c:1458-1496.  Between ranks only the k-face family is exchanged: FpCell reads the i- and
-  // j-face fluxes on the cell's own k plane only, so their k ghosts are never consumed.
-  RUN(wrap_ij(c, gf));
-  RUN(halo_k(c, c->prm.nranks > 1 ? grp_cat(grp(S_FC3, 3), grp(S_FV3, 3)) : gf));
-  if (any_per(c)) RUN(node_copy(c, gf));                              // momentum.c:1506-1546
+  // momentum.c:1458-1496, 1506-1546.  FpCell reads the fluxes of face family D along direction D only, at the
+  // cell's own other two indices, so each family is refreshed in its own direction only (a third of the data;
+  // between ranks only the k-face family travels).
+  {
+    const Grp gi = grp_cat(grp(S_FC1, 3), grp(S_FV1, 3)), gj = grp_cat(grp(S_FC2, 3), grp(S_FV2, 3)), gk = grp_cat(grp(S_FC3, 3), grp(S_FV3, 3));
+    if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
+    if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
+    RUN(halo_k(c, gk));
+    if (any_per(c)) {
+      NodeCopyFlux f = {d};
+      const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
+      RUN(launch_shell(c, ka, kb, f));
+    }
+  }
   for (int n = 0; n < S.n; n++) { FpCell f = {d}; RUN(launch(c, S.fp[n], f)); }   // momentum.c:1548-1678
   ev_rec(c, 2 * VFS_T_FP + 1);
   Grp gp = grp(S_FP0, 3);

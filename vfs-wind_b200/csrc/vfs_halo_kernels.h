@@ -79,6 +79,70 @@ struct NodeCopy {
   }
 };
 
+// Single-rank ghost refresh in ONE launch.  mode 1 = DALocalToLocal (wrap fill of every periodic direction);
+// mode 3 = wrap fill, periodic node copies (NodeCopy), wrap fill again — the sequence that follows most
+// updates in the reference (e.g. rhs.c:251-291).  Each destination node (a ghost, or for mode 3 also a node of
+// a periodic boundary plane) takes its final value straight from the interior node the sequence would have
+// propagated it from: per periodic direction, ghost x -> x -+ m, then (mode 3) 0 -> m-2 and m-1 -> 1.  Sources
+// are interior in every periodic direction and destinations are not, so the in-place update is race-free.
+// Visited as three slabs (one per direction: its 2G ghost planes + 2 boundary planes, full extent of the other
+// directions); a node in two slabs is written twice with the same value.
+struct RefreshSlabs { long n[3]; int ext[3]; };       // nodes per slab; extent (incl. ghosts if periodic) per direction
+struct RefreshFused {
+  VfsDev d; Grp g; int mode; RefreshSlabs S;
+  VFS_HD static int map1(int x, int m) { return x < 0 ? x + m : (x >= m ? x - m : x); }
+  VFS_HD void node(int i, int j, int k) const {
+    int a = i, b = j, c = k;
+    if (d.perx) { a = map1(a, d.mx); if (mode == 3) a = a == 0 ? d.mx - 2 : (a == d.mx - 1 ? 1 : a); }
+    if (d.pery) { b = map1(b, d.my); if (mode == 3) b = b == 0 ? d.my - 2 : (b == d.my - 1 ? 1 : b); }
+    if (d.perz) { c = map1(c, d.mz); if (mode == 3) c = c == 0 ? d.mz - 2 : (c == d.mz - 1 ? 1 : c); }
+    if (a == i && b == j && c == k) return;
+    const long p = d.idx(i, j, k), q = d.idx(a, b, c);
+    for (int n = 0; n < g.n; n++) d.s[g.sid[n]][p] = d.s[g.sid[n]][q];
+  }
+  // shell coordinate s in [0, 2G+2) of a direction with m nodes -> -G..0, m-1..m+G-1
+  VFS_HD static int shell(int s, int m) { return s <= VFS_G ? s - VFS_G : m - 1 + (s - VFS_G - 1); }
+  VFS_HD void operator()(long t) const {
+    const int lo[3] = {d.perx ? -VFS_G : 0, d.pery ? -VFS_G : 0, d.perz ? -VFS_G : 0};
+    const int W = 2 * VFS_G + 2;
+    if (t < S.n[0]) {                                   // i slab: shell x ext[1] x ext[2], shell fastest
+      const int s = (int)(t % W); const long r = t / W;
+      node(shell(s, d.mx), lo[1] + (int)(r % S.ext[1]), lo[2] + (int)(r / S.ext[1]));
+    } else if (t < S.n[0] + S.n[1]) {                   // j slab
+      t -= S.n[0];
+      const int x = (int)(t % S.ext[0]); const long r = t / S.ext[0];
+      node(lo[0] + x, shell((int)(r % W), d.my), lo[2] + (int)(r / W));
+    } else {                                            // k slab
+      t -= S.n[0] + S.n[1];
+      const int x = (int)(t % S.ext[0]); const long r = t / S.ext[0];
+      node(lo[0] + x, lo[1] + (int)(r % S.ext[1]), shell((int)(r / S.ext[1]), d.mz));
+    }
+  }
+};
+
+// The same copies for the 18 face-flux work scalars (momentum.c:1506-1546), restricted to what FpCell
+// consumes: the fluxes of face family D are only ever read along direction D at the cell's own other two
+// indices (momentum.c:1565-1668), so family D needs the copies of the D-boundary planes only.
+struct NodeCopyFlux {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    if (d.perx && (i == 0 || i == d.mx - 1)) {
+      const long q = d.idx(i == 0 ? -2 : d.mx + 1, j, k);
+      for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = d.s[S_FC1 + a][q]; d.s[S_FV1 + a][p] = d.s[S_FV1 + a][q]; }
+    }
+    if (d.pery && (j == 0 || j == d.my - 1)) {
+      const long q = d.idx(i, j == 0 ? -2 : d.my + 1, k);
+      for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = d.s[S_FC2 + a][q]; d.s[S_FV2 + a][p] = d.s[S_FV2 + a][q]; }
+    }
+    if (d.perz && (kg == 0 || kg == d.mz - 1)) {
+      const long q = d.idx(i, j, kg == 0 ? k - 2 : k + 2);
+      for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = d.s[S_FC3 + a][q]; d.s[S_FV3 + a][p] = d.s[S_FV3 + a][q]; }
+    }
+  }
+};
+
 // near-solid byte mask (VfsDev::near): 1 where any node of the 5x5x5 cube around the node has nvert != 0.
 // Evaluated on the owned nodes grown by 2 (the cube then stays inside the G = 4 ghost frame, whose
 // nvert values are the wrap / neighbour-rank images); everything outside keeps the initial 1.
