@@ -161,7 +161,7 @@ def run_ours(args):
     ctx, f, (mx, my, mz, kofs, nzl) = build_case_on_device(pkg, cfg, rank, world, lrank, halo)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    for key, env in ((0, "VFS_FUSED"), (2, "VFS_LES2_TY"), (3, "VFS_FLUX_MINB"), (4, "VFS_LES1_VAR"), (5, "VFS_LES3_VAR"), (6, "VFS_FASTPATH"), (7, "VFS_FLUX_VAR"), (8, "VFS_FUSE_REFRESH")):            # tuning knobs (see vfs_set_option)
+    for key, env in ((0, "VFS_FUSED"), (2, "VFS_LES2_TY"), (3, "VFS_FLUX_MINB"), (4, "VFS_LES1_VAR"), (5, "VFS_LES3_VAR"), (6, "VFS_FASTPATH"), (7, "VFS_FLUX_VAR"), (8, "VFS_FUSE_REFRESH"), (9, "VFS_OVERLAP")):            # tuning knobs (see vfs_set_option)
         if os.environ.get(env):
             ctx.set_option(key, int(os.environ[env]))
     cells_total = (mx - 2) * (my - 2) * (mz - 2)

@@ -172,6 +172,11 @@ def run_path(ctx, x):
     out["F"] = ctx.FormFunction_SNES(x)
     for n in ("UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ"):
         out[n] = ctx.download(n)
+    # the same unit through the single fused entry point (its own, shorter, ghost-refresh schedule)
+    ctx.upload("UCONT", x)
+    ctx.rhs_les_fused()
+    for n in ("RHS", "UCAT", "CS", "NU_T"):
+        out["FUSED_" + n] = ctx.download(n)
     return out
 
 

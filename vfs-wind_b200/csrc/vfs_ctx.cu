@@ -96,7 +96,10 @@ struct vfs_ctx {
 #ifndef VFS_EMU
   ncclComm_t comm = nullptr;     // k-neighbour halo exchange inside the library (vfs_nccl_init)
   double *hbuf = nullptr;        // packed send (hi, lo) and receive (lo, hi) staging, VFS_MAXGRP scalars each
+  cudaStream_t side = 0;         // halo exchanges that overlap interior compute run here (forked / joined by events)
+  cudaEvent_t ev_fork = 0, ev_join = 0;
 #endif
+  int overlap = 1;               // overlap the k-face-flux and Fp exchanges with the interior planes of FpCell / Project (option key 9)
   long halo_exchanges = 0, halo_bytes = 0;
   // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
   int use_graph = 0; bool capturing = false;
@@ -128,7 +131,8 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
   c->launches++;
 #ifndef VFS_EMU
   dim3 blk(64, 2, 2);
-  if (b.i1 - b.i0 <= 8) blk = dim3(8, 8, 4);
+  if (b.i1 - b.i0 == 1) blk = dim3(1, 32, 8);       // a single i plane: no idle lanes (rows are strided either way)
+  else if (b.i1 - b.i0 <= 8) blk = dim3(8, 8, 4);
   else if (b.j1 - b.j0 == 1) blk = dim3(64, 1, 4);
   else if (b.k1 - b.k0 == 1) blk = dim3(64, 4, 1);
   dim3 grd((b.i1 - b.i0 + blk.x - 1) / blk.x, (b.j1 - b.j0 + blk.y - 1) / blk.y, (b.k1 - b.k0 + blk.z - 1) / blk.z);
@@ -324,6 +328,37 @@ static int refresh_fused(vfs_ctx *c, const Grp &g, int mode) {
 #endif
   return 0;
 }
+// A k-halo exchange that overlaps compute: ovl_exchange() forks the side stream off the main stream and runs
+// the packed NCCL exchange there; the caller queues the work that does not read the ghost planes on the
+// main stream and then calls ovl_join(), after which the main stream sees the ghosts.  Event fork/join,
+// so the pattern is captured into the step's CUDA graph like everything else.
+static bool can_overlap(const vfs_ctx *c) {
+#ifndef VFS_EMU
+  return c->overlap && c->prm.nranks > 1 && c->comm && c->side;
+#else
+  (void)c; return false;
+#endif
+}
+static int ovl_exchange(vfs_ctx *c, const Grp &g) {
+#ifndef VFS_EMU
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  cudaStream_t main_stream = c->stream;
+  c->stream = c->side;
+  const int r = nccl_halo(c, g, false);
+  c->stream = main_stream;
+  return r;
+#else
+  (void)c; (void)g; return VFS_ERR_UNSUPPORTED;
+#endif
+}
+static int ovl_join(vfs_ctx *c) {
+#ifndef VFS_EMU
+  CK(cudaEventRecord(c->ev_join, c->side));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+#endif
+  (void)c; return 0;
+}
 // DAGlobalToLocal / DALocalToLocal
 static int g2l(vfs_ctx *c, const Grp &g) {
   if (c->prm.nranks == 1 && c->fuse_refresh) return refresh_fused(c, g, 1);
@@ -426,6 +461,9 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
   cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near);
   graph_reset(c);
@@ -479,6 +517,11 @@ extern "C" int vfs_nccl_init(vfs_ctx *c, const char *id128) {
   CK(cudaSetDevice(c->prm.device));
   ncclResult_t e = N.CommInitRank(&c->comm, c->prm.nranks, id, c->prm.rank);
   if (e != ncclSuccess) { c->comm = nullptr; set_err(c, std::string("ncclCommInitRank: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
+  if (!c->side) {
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
   return 0;
 #else
   (void)c; (void)id128; return VFS_ERR_UNSUPPORTED;
@@ -526,6 +569,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 6) { c->fastpath = value; c->near_valid = false; }
   else if (key == 7) c->flux_var = value;
   else if (key == 8) c->fuse_refresh = value;
+  else if (key == 9) c->overlap = value;
   graph_reset(c);
   return 0;
 }
@@ -844,22 +888,53 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     const Grp gi = grp_cat(grp(S_FC1, 3), grp(S_FV1, 3)), gj = grp_cat(grp(S_FC2, 3), grp(S_FV2, 3)), gk = grp_cat(grp(S_FC3, 3), grp(S_FV3, 3));
     if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
     if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
-    RUN(halo_k(c, gk));
-    if (any_per(c)) {
-      NodeCopyFlux f = {d};
-      const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
-      RUN(launch_shell(c, ka, kb, f));
+    const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
+    const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8;
+    FpCell fp = {d};
+    if (!ovl) {
+      RUN(halo_k(c, gk));
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      for (int n = 0; n < S.n; n++) RUN(launch(c, S.fp[n], fp));     // momentum.c:1548-1678
+    } else {
+      // Fp of a cell reads the k-face fluxes of planes k-2 .. k+1 (k-4 / k+3 across the periodic seam): the cells
+      // of local planes 2 .. nzl-3 never touch a k ghost plane and run while the exchange is in flight
+      RUN(ovl_exchange(c, gk));
+      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, ka, kb, f)); }
+      Box in = S.fp[0], lo = S.fp[0], hi = S.fp[0];
+      in.k0 = in.k0 > 2 ? in.k0 : 2; in.k1 = in.k1 < d.nzl - 2 ? in.k1 : d.nzl - 2;
+      lo.k1 = in.k0; hi.k0 = in.k1;
+      RUN(launch(c, in, fp));
+      RUN(ovl_join(c));
+      if (d.perz) { NodeCopyFlux f = {d, 2}; RUN(launch_shell(c, ka, kb, f)); }
+      RUN(launch(c, lo, fp)); RUN(launch(c, hi, fp));
     }
   }
-  for (int n = 0; n < S.n; n++) { FpCell f = {d}; RUN(launch(c, S.fp[n], f)); }   // momentum.c:1548-1678
   ev_rec(c, 2 * VFS_T_FP + 1);
   Grp gp = grp(S_FP0, 3);
-  RUN(g2l(c, gp));
-  if (any_per(c)) RUN(node_copy(c, gp));                              // momentum.c:1687-1713
-  ev_rec(c, 2 * VFS_T_PROJECT);
-  for (int n = 0; n < S.n; n++) {
-    if (mode == 0) { ProjectAdd f = {d, s0, scale}; RUN(launch(c, S.proj[n], f)); }
-    else { ProjectSNES f = {d}; RUN(launch(c, S.proj[n], f)); }
+  const bool ovl_p = can_overlap(c) && S.n == 1 && d.nzl >= 8;
+  auto project = [&](const Box &b) -> int {
+    if (mode == 0) { ProjectAdd f = {d, s0, scale}; return launch(c, b, f); }
+    ProjectSNES f = {d}; return launch(c, b, f);
+  };
+  if (!ovl_p) {
+    RUN(g2l(c, gp));
+    if (any_per(c)) RUN(node_copy(c, gp));                            // momentum.c:1687-1713
+    ev_rec(c, 2 * VFS_T_PROJECT);
+    for (int n = 0; n < S.n; n++) RUN(project(S.proj[n]));
+  } else {
+    // the projection of a node reads Fp at the node and at its +i, +j, +k neighbours: local planes 2 .. nzl-3 need
+    // neither the ghost plane nzl nor the seam copies of planes 0 / nzl-1.  The periodic node copies run twice:
+    // before (their i/j part feeds the interior planes) and again after the exchange (fresh k ghosts).
+    RUN(wrap_ij(c, gp));
+    RUN(ovl_exchange(c, gp));
+    if (any_per(c)) RUN(node_copy(c, gp));
+    ev_rec(c, 2 * VFS_T_PROJECT);
+    Box in = S.proj[0], lo = S.proj[0], hi = S.proj[0];
+    in.k0 = 2; in.k1 = d.nzl - 2; lo.k1 = 2; hi.k0 = d.nzl - 2;
+    RUN(project(in));
+    RUN(ovl_join(c));
+    if (any_per(c)) RUN(node_copy(c, gp));
+    RUN(project(lo)); RUN(project(hi));
   }
   ev_rec(c, 2 * VFS_T_PROJECT + 1);
   return 0;
@@ -906,7 +981,7 @@ struct ZeroNormal {   // wall-normal zeroing applied to an Ucont that is already
   VFS_HD void operator()(int i, int j, int k) const {
     long p = d.idx(i, j, k);
     double tmp[3] = {d.s[S_UC0][p], d.s[S_UC1][p], d.s[S_UC2][p]};
-    const int mx = d.mx, my = d.my, mz = d.mz, kg = k + d.kofs;
+    const int mx = d.mx, my = d.my, mz = d.mz, kg = d.kglob(k);
     const bool jin = (j != 0 && j != my - 1), kin = (kg != 0 && kg != mz - 1), iin = (i != 0 && i != mx - 1);
     if ((i == 0 && d.bc[0] == 1) || (i == mx - 2 && d.bc[1] == 1)) tmp[0] = 0;
     if (d.bc[0] == 10 && i == 0 && jin && kin) tmp[0] = 0;
@@ -922,9 +997,12 @@ struct ZeroNormal {   // wall-normal zeroing applied to an Ucont that is already
 };
 // wall-normal flux zeroing (momentum.c:2264-2289) of an Ucont already on the device: only the planes
 // whose boundary type asks for it are touched
-static int zero_normal(vfs_ctx *c) {
+// ghosts: also on the k ghost planes that image another rank's planes (or the periodic seam), so that the
+// ucont ghosts stay what their owners hold and need no exchange afterwards (vfs_rhs_les_fused)
+static int zero_normal(vfs_ctx *c, bool ghosts = false) {
   const VfsDev &d = c->d;
   ZeroNormal f = {d};
+  const int ka = ghosts && (d.kofs > 0 || d.perz) ? -VFS_G : 0, kb = ghosts && (d.kofs + d.nzl < d.mz || d.perz) ? d.nzl + VFS_G : d.nzl;
   const int *bc = d.bc;
   const bool need[6] = {bc[0] == 1 || bc[0] == 10, bc[1] == 1 || bc[1] == 10, bc[2] == 1 || bc[2] == 12 || bc[2] == 10,
                         bc[3] == 1 || bc[3] == 2 || bc[3] == 12 || bc[3] == 10 || bc[3] == -10, bc[4] == 1, bc[5] == 1};
@@ -932,15 +1010,19 @@ static int zero_normal(vfs_ctx *c) {
   for (int q = 0; q < 6; q++) {
     if (!need[q]) continue;
     Box b = box_owned(c);
+    b.k0 = ka; b.k1 = kb;
     if (q < 2) { b.i0 = plane[q]; b.i1 = b.i0 + 1; }
     else if (q < 4) { b.j0 = plane[q]; b.j1 = b.j0 + 1; }
-    else { const int k = plane[q] - d.kofs; if (k < 0 || k >= d.nzl) continue; b.k0 = k; b.k1 = k + 1; }
+    else { const int k = plane[q] - d.kofs; if (k < ka || k >= kb) continue; b.k0 = k; b.k1 = k + 1; }       // (non-periodic k: no seam images)
     RUN(launch(c, b, f));
   }
   return 0;
 }
-static int snes_core(vfs_ctx *c) {
-  RUN(g2l(c, grp(S_UC0, 3)));                                         // momentum.c:2293-2294
+// uc_ghosts_fresh: the k ghost planes of ucont already hold what their owners hold (vfs_rhs_les_fused: exchanged
+// at the start of the unit, every change since then replayed on the ghost planes) -> only the local wrap fill
+static int snes_core(vfs_ctx *c, bool uc_ghosts_fresh = false) {
+  if (uc_ghosts_fresh && c->prm.nranks > 1) RUN(wrap_ij(c, grp(S_UC0, 3), -VFS_G, c->d.nzl + VFS_G));
+  else RUN(g2l(c, grp(S_UC0, 3)));                                    // momentum.c:2293-2294
   RUN(contra2cart(c));
   RUN(ib_bc(c));
   return formfunction2(c, 1, S_R0, 0.5);
@@ -974,7 +1056,9 @@ static bool les2_march_ok(const vfs_ctx *c) {
   (void)c; return true;
 #endif
 }
-static int les_cs(vfs_ctx *c) {
+// defer_refresh: leave the ghost refresh of Cs (les.c:1026-1057) to les_nut(c, true), which does it together
+// with nu_t's (nu_t of an interior cell reads the cell's own Cs only, les.c:1206)
+static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   const VfsDev &d = c->d;
   Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
   c->sabs_valid = false;
@@ -1041,19 +1125,20 @@ static int les_cs(vfs_ctx *c) {
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
   { LesClipBoundary f = {d}; RUN(launch_shell(c, 0, d.nzl, f)); }     // les.c:967-980 (boundary nodes; interior clip is in pass 3)
+  if (defer_refresh) return 0;
   Grp g3 = grp(S_CS, 1);
   RUN(g2l(c, g3));                                                    // les.c:1026-1027
   if (any_per(c)) RUN(node_copy(c, g3));
   return 0;
 }
-static int les_nut(vfs_ctx *c) {
+static int les_nut(vfs_ctx *c, bool with_cs = false) {
   const VfsDev &d = c->d;
   ev_rec(c, 2 * VFS_T_NUT);
   if (c->sabs_valid) { NuT<true> f = {d}; RUN(launch(c, box_interior(c), f)); }
   else { NuT<false> f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_NUT + 1);
-  Grp g = grp(S_NUT, 1);
-  RUN(g2l(c, g));                                                     // les.c:1320-1321
+  Grp g = with_cs ? grp_cat(grp(S_CS, 1), grp(S_NUT, 1)) : grp(S_NUT, 1);
+  RUN(g2l(c, g));                                                     // les.c:1320-1321 (+ 1026-1027)
   if (any_per(c)) RUN(node_copy(c, g));
   return 0;
 }
@@ -1068,9 +1153,9 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
   RUN(run_graphed(c, 1, [&]() -> int {
     RUN(g2l(c, grp(S_UC0, 3)));
     RUN(contra2cart(c));
-    if (c->d.les) { RUN(les_cs(c)); RUN(les_nut(c)); }
-    RUN(zero_normal(c));
-    return snes_core(c);
+    if (c->d.les) { RUN(les_cs(c, true)); RUN(les_nut(c, true)); }     // Cs and nu_t ghosts refreshed together
+    RUN(zero_normal(c, true));
+    return snes_core(c, true);
   }));
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);

@@ -124,10 +124,11 @@ struct RefreshFused {
 // consumes: the fluxes of face family D are only ever read along direction D at the cell's own other two
 // indices (momentum.c:1565-1668), so family D needs the copies of the D-boundary planes only.
 struct NodeCopyFlux {
-  VfsDev d;
+  VfsDev d; int parts;      // bit 0: the i- and j-plane copies, bit 1: the k-plane copies (which read k ghost planes)
   VFS_HD void operator()(int i, int j, int k) const {
     const int kg = k + d.kofs;
     const long p = d.idx(i, j, k);
+    if (!(parts & 1)) goto kpart;
     if (d.perx && (i == 0 || i == d.mx - 1)) {
       const long q = d.idx(i == 0 ? -2 : d.mx + 1, j, k);
       for (int a = 0; a < 3; a++) { d.s[S_FC1 + a][p] = d.s[S_FC1 + a][q]; d.s[S_FV1 + a][p] = d.s[S_FV1 + a][q]; }
@@ -136,7 +137,8 @@ struct NodeCopyFlux {
       const long q = d.idx(i, j == 0 ? -2 : d.my + 1, k);
       for (int a = 0; a < 3; a++) { d.s[S_FC2 + a][p] = d.s[S_FC2 + a][q]; d.s[S_FV2 + a][p] = d.s[S_FV2 + a][q]; }
     }
-    if (d.perz && (kg == 0 || kg == d.mz - 1)) {
+  kpart:
+    if ((parts & 2) && d.perz && (kg == 0 || kg == d.mz - 1)) {
       const long q = d.idx(i, j, kg == 0 ? k - 2 : k + 2);
       for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = d.s[S_FC3 + a][q]; d.s[S_FV3 + a][p] = d.s[S_FV3 + a][q]; }
     }
