@@ -123,8 +123,41 @@ template <int TY_> struct Les2MarchT {
       st.v[a] = A; sA[a * NT + tid] = A;
     }
   }
+#if defined(__CUDACC__) && !defined(VFS_EMU)
+  // phases 0 and 1 in one, CUDA only: a tile row is exactly one warp (TX = 32), so the i pass takes its two
+  // neighbours by warp shuffle instead of through the first exchange buffer — one block barrier per plane
+  // instead of two (the barrier was this kernel's largest stall, profiles/r01q).  The lanes at the tile edge
+  // get their own value back from the shuffle, which is what phase1's clamped indices read: same bits.
+  // The j-pass buffer alternates between the two halves of the exchange area (sA), because a warp may start the
+  // next plane while others still read this one's.
+  __device__ __forceinline__ void phase01(State &st, int tid, int bx, int by, int k, bool first, double *sm, double *sA) const {
+    const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
+    double K[NV];
+#pragma unroll
+    for (int a = 0; a < NV; a++) K[a] = 0;
+    if (i <= d.mx - 1 && j <= d.my - 1) {
+      const long p = d.idx(i, j, k);
+      if (first) { load_raw(d, p - d.sk, st.win[0]); load_raw(d, p, st.win[1]); }
+      double nw[NRAW];
+      load_raw(d, p + d.sk, nw);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { st.ufk[a] = d.s[S_UF0 + a][p - d.sk]; st.ufk[3 + a] = d.s[S_UF0 + a][p + d.sk]; }
+      st.nvk[0] = d.s[S_NV][p - d.sk]; st.nvk[1] = d.s[S_NV][p + d.sk];
+      add_plane(K, st.win[0], false); add_plane(K, st.win[1], true); add_plane(K, nw, false);
+#pragma unroll
+      for (int a = 0; a < NRAW; a++) { st.win[0][a] = st.win[1][a]; st.win[1][a] = nw[a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const double l = __shfl_up_sync(0xffffffffu, K[a], 1), r = __shfl_down_sync(0xffffffffu, K[a], 1);
+      const double A = l + 4. * K[a] + r;
+      st.v[a] = A; sA[a * NT + tid] = A;
+    }
+  }
+#endif
   // phase 2: j pass + les.c:470-669 for the inner nodes of the tile
-  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const {
+  // sA: the exchange buffer holding the i-pass results of this plane (OFF_A, or the alternating buffer of phase01)
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm, const double *sA) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
     const long p = d.idx(i, j, k);
@@ -133,7 +166,6 @@ template <int TY_> struct Les2MarchT {
 #pragma unroll
     for (int a = 0; a < 6; a++) O.ufk[a] = st.ufk[a];
     O.nvk[0] = st.nvk[0]; O.nvk[1] = st.nvk[1];
-    const double *sA = sm + OFF_A;
     const int up = tid - TX, dn = tid + TX;
     double f[NV];
 #pragma unroll
@@ -171,12 +203,11 @@ template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_marc
   __syncthreads();
   typename M::State st;
   for (int k = ka; k < kb; k++) {
-    P.phase0(st, tid, bx, by, k, k == ka, sm);
-    __syncthreads();
-    P.phase1(st, tid, sm);
+    double *sA = sm + ((k - ka) & 1) * M::OFF_A;       // the two NV*NT halves of the exchange area alternate
+    P.phase01(st, tid, bx, by, k, k == ka, sm, sA);
     __syncthreads();
     mbar_wait(bar, (k - ka) & 1);
-    P.phase2(st, tid, bx, by, k, sm);
+    P.phase2(st, tid, bx, by, k, sm, sA);
     // the warp that leaves phase 2 last refills the operand buffer for the next plane
     __syncwarp();
     if ((tid & 31) == 0) {
@@ -234,7 +265,7 @@ template <class M> static inline int run_les2_march(void *, const M &P, int k0, 
           for (int t = 0; t < M::NT; t++) P.phase0(st[t], t, bx, by, k, k == ka, sm);
           for (int t = 0; t < M::NT; t++) P.phase1(st[t], t, sm);
           // phase 1 reads its neighbours' phase-0 values from the exchange buffer while updating st.v in place
-          for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, sm);
+          for (int t = 0; t < M::NT; t++) P.phase2(st[t], t, bx, by, k, sm, sm + M::OFF_A);
           if (k + 1 < kb) issue(k + 1);
         }
       }
@@ -269,6 +300,7 @@ template <int TY_> struct Les1MarchT {
   static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 4;
   static constexpr int OFF_A = NV * NT, OFF_U = 2 * NV * NT;
   static constexpr long SMEM_D = 3L * NV * NT;
+  static constexpr bool HAS01 = false;
   struct State { double v[NV]; double uk[6], nvk[2], iaj0; };
   VfsDev d;
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
@@ -355,12 +387,19 @@ template <class M, int MINB> __global__ void __launch_bounds__(M::NT, MINB) k_fi
   const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
   typename M::State st;
   for (int k = ka; k < kb; k++) {
-    P.phase0(st, tid, bx, by, k, k == ka, sm);
-    __syncthreads();
-    P.phase1(st, tid, sm);
-    __syncthreads();
-    P.phase2(st, tid, bx, by, k, sm);
-    if (M::SMEM_D > 2L * M::NV * M::NT) __syncthreads();      // a third buffer written in phase 0 is still read in phase 2
+    if constexpr (M::HAS01) {                   // one barrier per plane, alternating j-pass buffer
+      double *sA = sm + ((k - ka) & 1) * M::NV * M::NT;
+      P.phase01(st, tid, bx, by, k, k == ka, sm, sA);
+      __syncthreads();
+      P.phase2(st, tid, bx, by, k, sm, sA);
+    } else {
+      P.phase0(st, tid, bx, by, k, k == ka, sm);
+      __syncthreads();
+      P.phase1(st, tid, sm);
+      __syncthreads();
+      P.phase2(st, tid, bx, by, k, sm);
+      if (M::SMEM_D > 2L * M::NV * M::NT) __syncthreads();      // a third buffer written in phase 0 is still read in phase 2
+    }
   }
 }
 template <class M, int MINB> static inline int run_filter_march(cudaStream_t stream, const M &P, int k0, int k1, long *launches) {
@@ -410,6 +449,7 @@ template <class M, int MINB> static inline int run_filter_march(void *, const M 
 struct Les3March {
   static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 3;
   static constexpr long SMEM_D = 2L * NV * NT;
+  static constexpr bool HAS01 = true;       // phases 0 + 1 fused with a warp-shuffle i pass on the device (see Les2MarchT::phase01)
   // (a register window over k, as in Les2MarchT, was measured slower here: 0.50 vs 0.44 ms at 256^3 — the three
   // planes' twelve loads are independent L2 hits, the window adds a loop-carried chain; writing nu_t from this
   // kernel as well cost what the separate NuT kernel costs, 0.14 ms, so it stays separate)
@@ -451,14 +491,25 @@ struct Les3March {
       st.v[a] = A; sA[a * NT + tid] = A;
     }
   }
-  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const {
+#if defined(__CUDACC__) && !defined(VFS_EMU)
+  __device__ __forceinline__ void phase01(State &st, int tid, int bx, int by, int k, bool first, double *sm, double *sA) const {
+    phase0(st, tid, bx, by, k, first, sA);          // K in st.v (its copy in sA is overwritten below: only this thread wrote the slot)
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const double l = __shfl_up_sync(0xffffffffu, st.v[a], 1), r = __shfl_down_sync(0xffffffffu, st.v[a], 1);
+      const double A = l + 4. * st.v[a] + r;
+      st.v[a] = A; sA[a * NT + tid] = A;
+    }
+  }
+#endif
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm) const { phase2(st, tid, bx, by, k, sm, sm + NV * NT); }
+  VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *, const double *sA) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
     const int kg = k + d.kofs;
     if ((d.perx && (i == 1 || i == d.mx - 2)) || (d.pery && (j == 1 || j == d.my - 2)) || (d.perz && (kg == 1 || kg == d.mz - 2))) return;
     const long p = d.idx(i, j, k);
     if (st.nvc > 1.1) { d.s[S_CS][p] = 0; return; }
-    const double *sA = sm + NV * NT;
     const int up = tid - TX, dn = tid + TX;
     const double ws = sA[up] + 4. * st.v[0] + sA[dn];
     const double lm = sA[NT + up] + 4. * st.v[1] + sA[NT + dn];
