@@ -51,8 +51,11 @@ template <int TY_> struct Les2MarchT {
   // NOPF scalars whose i/j neighbours are read too (whole tile)
   static constexpr int NOPI = 13, NOPF = 4, NOP = NOPI + NOPF, NTI = TX * (TY - 2);
   static constexpr int MINB = TY_ <= 8 ? 2 : 1;                      // resident blocks per SM the tile is sized for
-  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_OPF = OFF_OP + NOPI * NTI, OFF_BAR = OFF_OPF + NOPF * NT;
-  static constexpr long SMEM_D = OFF_BAR + 2;
+  // operand buffers: two when they fit, so that plane k+1's operands are requested a whole step before they are read
+  static constexpr int OPSZ = NOPI * NTI + NOPF * NT;
+  static constexpr int NBUF = (2 * NV * NT + 2 * OPSZ) * 8 + 64 <= 227 * 1024 ? 2 : 1;
+  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_OPF = OFF_OP + NOPI * NTI, OFF_BAR = OFF_OP + NBUF * OPSZ;
+  static constexpr long SMEM_D = OFF_BAR + 3;
   // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..12 LFINV,LTF2,LF2 || 13..15 UF | 16 nvert
   VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 13 ? S_LFINV + (q - 10) : (q < 16 ? S_UF0 + (q - 13) : S_NV)); }
   static constexpr int NRAW = 13;
@@ -157,6 +160,7 @@ template <int TY_> struct Les2MarchT {
 #endif
   // phase 2: j pass + les.c:470-669 for the inner nodes of the tile
   // sA: the exchange buffer holding the i-pass results of this plane (OFF_A, or the alternating buffer of phase01)
+  // sm: here the base of the operand buffer's frame, i.e. shared-memory base + (buffer index) * OPSZ
   VFS_HD void phase2(const State &st, int tid, int bx, int by, int k, const double *sm, const double *sA) const {
     const int tx = tid % TX, ty = tid / TX, i = iorg(bx) + tx, j = jorg(by) + ty;
     if (tx < 1 || tx > TX - 2 || ty < 1 || ty > TY - 2 || i > d.mx - 2 || j > d.my - 2) return;
@@ -183,20 +187,22 @@ typedef Les2MarchT<8> Les2March8;      // two 256-thread blocks per SM: the phas
 template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_march(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapi, const M P, int kbeg, int kend, int kchunk) {
   extern __shared__ __align__(128) double vfs_les2_sm[];
   double *sm = vfs_les2_sm;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR);
-  unsigned *cnt = reinterpret_cast<unsigned *>(bar + 1);
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + M::OFF_BAR);      // bar[0], bar[1]: one per operand buffer
+  unsigned *cnt = reinterpret_cast<unsigned *>(bar + 2);
   const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
   const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
   if (ka >= kb) return;
-  auto issue = [&](int k) {       // one thread: the operand tiles of plane k -> shared memory
-    mbar_expect_tx(bar, (M::NOPI * M::NTI + M::NOPF * M::NT) * 8);
+  auto issue = [&](int k) {       // one thread: the operand tiles of plane k -> shared memory (buffer (k-ka) % NBUF)
+    const int b = (k - ka) % M::NBUF;
+    double *dst = sm + b * M::OPSZ;
+    mbar_expect_tx(&bar[b], M::OPSZ * 8);
 #pragma unroll 1
-    for (int q = 0; q < M::NOPI; q++) tma_load_tile(sm + M::OFF_OP + q * M::NTI, &tmapi, M::iorg(bx) + VFS_G, M::jorg(by) + 1 + VFS_G, k + VFS_G, M::op_sid(q), bar);
+    for (int q = 0; q < M::NOPI; q++) tma_load_tile(dst + M::OFF_OP + q * M::NTI, &tmapi, M::iorg(bx) + VFS_G, M::jorg(by) + 1 + VFS_G, k + VFS_G, M::op_sid(q), &bar[b]);
 #pragma unroll 1
-    for (int q = 0; q < M::NOPF; q++) tma_load_tile(sm + M::OFF_OPF + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(M::NOPI + q), bar);
+    for (int q = 0; q < M::NOPF; q++) tma_load_tile(dst + M::OFF_OPF + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(M::NOPI + q), &bar[b]);
   };
   if (tid == 0) {
-    mbar_init(bar, 1); *cnt = 0;
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); *cnt = 0;
     fence_mbar_init();
     issue(ka);
   }
@@ -206,16 +212,25 @@ template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_marc
     double *sA = sm + ((k - ka) & 1) * M::OFF_A;       // the two NV*NT halves of the exchange area alternate
     P.phase01(st, tid, bx, by, k, k == ka, sm, sA);
     __syncthreads();
-    mbar_wait(bar, (k - ka) & 1);
-    P.phase2(st, tid, bx, by, k, sm, sA);
-    // the warp that leaves phase 2 last refills the operand buffer for the next plane
-    __syncwarp();
-    if ((tid & 31) == 0) {
-      __threadfence_block();
-      if (atomicAdd(cnt, 1u) == M::NT / 32 - 1) {
-        *reinterpret_cast<volatile unsigned *>(cnt) = 0;
+    const int b = (k - ka) % M::NBUF;
+    if constexpr (M::NBUF == 2) {
+      // everyone is past plane k-1's finish, whose operand buffer is the one plane k+1 goes into: request it now,
+      // a whole step before it is read (profiles/r01s: 27 % of this kernel's stall samples sat on the operand wait)
+      if (tid == 0 && k + 1 < kb) { fence_proxy_async(); issue(k + 1); }
+      mbar_wait(&bar[b], ((k - ka) >> 1) & 1);
+      P.phase2(st, tid, bx, by, k, sm + b * M::OPSZ, sA);
+    } else {
+      mbar_wait(&bar[0], (k - ka) & 1);
+      P.phase2(st, tid, bx, by, k, sm, sA);
+      // the warp that leaves phase 2 last refills the operand buffer for the next plane
+      __syncwarp();
+      if ((tid & 31) == 0) {
         __threadfence_block();
-        if (k + 1 < kb) { fence_proxy_async(); issue(k + 1); }
+        if (atomicAdd(cnt, 1u) == M::NT / 32 - 1) {
+          *reinterpret_cast<volatile unsigned *>(cnt) = 0;
+          __threadfence_block();
+          if (k + 1 < kb) { fence_proxy_async(); issue(k + 1); }
+        }
       }
     }
   }
