@@ -342,11 +342,13 @@ k_flux_march(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
   }
   for (int kk = kfa; kk < ka + 2; kk++) mbar_wait(&barA[(kk - kfa) % M::A_ST], ((kk - kfa) / M::A_ST) & 1);
   mbar_wait(&barB[0], 0);
+  unsigned char near_next = d.near[d.idx(active ? i : 1, active ? j : 1, ka)];       // the branch flag is fetched one plane ahead
   for (int k = ka; k < kb; k++) {
     // the few operands that stay in global memory are requested first: their latency overlaps the TMA waits
     // and the stencil differences (profiles/r01q: issued at their point of use they cost 5.6 of 13 stall cycles)
     const long p = d.idx(active ? i : 1, active ? j : 1, k);
-    const unsigned char nearv = d.near[p];
+    const unsigned char nearv = near_next;
+    near_next = d.near[p + d.sk];
     const double uc0 = d.s[S_UC0][p], uc1 = d.s[S_UC1][p], uc2 = d.s[S_UC2][p];
     const double nt0 = d.s[S_NUT][p], nt1 = d.s[S_NUT][p + 1], nt2 = d.s[S_NUT][p + d.sj], nt3 = d.s[S_NUT][p + d.sk];
     mbar_wait(&barA[(k + 2 - kfa) % M::A_ST], ((k + 2 - kfa) / M::A_ST) & 1);

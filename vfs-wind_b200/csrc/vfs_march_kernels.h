@@ -54,11 +54,16 @@ template <int TY_> struct Les2MarchT {
   // operand buffers: two when they fit, so that plane k+1's operands are requested a whole step before they are read
   static constexpr int OPSZ = NOPI * NTI + NOPF * NT;
   static constexpr int NBUF = (2 * NV * NT + 2 * OPSZ) * 8 + 64 <= 227 * 1024 ? 2 : 1;
-  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_OPF = OFF_OP + NOPI * NTI, OFF_BAR = OFF_OP + NBUF * OPSZ;
-  static constexpr long SMEM_D = OFF_BAR + 3;
+  static constexpr int NRAW = 13;
+  // RAWS: the 13 per-node inputs of the next plane are TMA-staged one step ahead, so the k pass reads shared memory
+  // instead of waiting on a burst of global loads (1.53 -> 1.39 ms once the operands were double-buffered; the same
+  // staging had been slower, 2.04 vs 1.92 ms, while both streams shared one barrier-bound step)
+  static constexpr int RAWS = (NBUF == 2 && (2 * NV * NT + 2 * OPSZ + NRAW * NT) * 8 + 64 <= 227 * 1024) ? 1 : 0;
+  static constexpr int OFF_A = NV * NT, OFF_OP = 2 * NV * NT, OFF_OPF = OFF_OP + NOPI * NTI, OFF_RAW = OFF_OP + NBUF * OPSZ, OFF_BAR = OFF_RAW + RAWS * NRAW * NT;
+  static constexpr long SMEM_D = OFF_BAR + 4;
+  VFS_HD static int raw_sid(int q) { return q == 0 ? S_LW : (q < 4 ? S_U0 + (q - 1) : (q < 7 ? S_LU0 + (q - 4) : S_LSS0 + (q - 7))); }
   // operand slot -> scalar id: 0..9 csi,eta,zet,aj | 10..12 LFINV,LTF2,LF2 || 13..15 UF | 16 nvert
   VFS_HD static int op_sid(int q) { return q < 10 ? S_CSI0 + q : (q < 13 ? S_LFINV + (q - 10) : (q < 16 ? S_UF0 + (q - 13) : S_NV)); }
-  static constexpr int NRAW = 13;
   struct State { double v[NV]; double ufk[6]; double nvk[2]; double win[2][NRAW]; };
   VfsDev d;
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
@@ -78,7 +83,6 @@ template <int TY_> struct Les2MarchT {
   // The per-node inputs of planes k-1 and k are carried in registers from the previous step (st.win),
   // so each step fetches one new plane (13 values) instead of three: this kernel's limiter was the
   // L2 -> SM traffic of re-reading every plane three times (profiles/r01l: 12.4 GB through L2 in 2.3 ms).
-  // (Staging the new plane by TMA one step ahead instead of loading it here was measured slower, 2.04 vs 1.92 ms.)
   VFS_HD static void load_raw(const VfsDev &d, long n, double *r) {
     r[0] = d.s[S_LW][n];
 #pragma unroll
@@ -142,7 +146,10 @@ template <int TY_> struct Les2MarchT {
       const long p = d.idx(i, j, k);
       if (first) { load_raw(d, p - d.sk, st.win[0]); load_raw(d, p, st.win[1]); }
       double nw[NRAW];
-      load_raw(d, p + d.sk, nw);
+      if (RAWS) {
+#pragma unroll
+        for (int a = 0; a < NRAW; a++) nw[a] = sm[OFF_RAW + a * NT + tid];
+      } else load_raw(d, p + d.sk, nw);
 #pragma unroll
       for (int a = 0; a < 3; a++) { st.ufk[a] = d.s[S_UF0 + a][p - d.sk]; st.ufk[3 + a] = d.s[S_UF0 + a][p + d.sk]; }
       st.nvk[0] = d.s[S_NV][p - d.sk]; st.nvk[1] = d.s[S_NV][p + d.sk];
@@ -201,17 +208,26 @@ template <class M> __global__ void __launch_bounds__(M::NT, M::MINB) k_les2_marc
 #pragma unroll 1
     for (int q = 0; q < M::NOPF; q++) tma_load_tile(dst + M::OFF_OPF + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::op_sid(M::NOPI + q), &bar[b]);
   };
+  unsigned long long *bar_raw = bar + 3;
+  auto issue_raw = [&](int k) {
+    mbar_expect_tx(bar_raw, M::NRAW * M::NT * 8);
+#pragma unroll 1
+    for (int q = 0; q < M::NRAW; q++) tma_load_tile(sm + M::OFF_RAW + q * M::NT, &tmap, M::iorg(bx) + VFS_G, M::jorg(by) + VFS_G, k + VFS_G, M::raw_sid(q), bar_raw);
+  };
   if (tid == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); *cnt = 0;
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(bar_raw, 1); *cnt = 0;
     fence_mbar_init();
     issue(ka);
+    if (M::RAWS) issue_raw(ka + 1);
   }
   __syncthreads();
   typename M::State st;
   for (int k = ka; k < kb; k++) {
     double *sA = sm + ((k - ka) & 1) * M::OFF_A;       // the two NV*NT halves of the exchange area alternate
+    if (M::RAWS) mbar_wait(bar_raw, (k - ka) & 1);
     P.phase01(st, tid, bx, by, k, k == ka, sm, sA);
     __syncthreads();
+    if (M::RAWS && tid == 0 && k + 1 < kb) { fence_proxy_async(); issue_raw(k + 2); }
     const int b = (k - ka) % M::NBUF;
     if constexpr (M::NBUF == 2) {
       // everyone is past plane k-1's finish, whose operand buffer is the one plane k+1 goes into: request it now,
