@@ -164,18 +164,24 @@ static Shell make_shell(const VfsDev &d, int ka, int kb, bool images = false) {
   s.nA = 2L * d.my * s.nk; s.nB = 2L * (d.mx - 2) * s.nk; s.nC = (long)s.nkp * (d.mx - 2) * (d.my - 2);
   return s;
 }
-template <class F> VFS_HD void shell_visit(const F &f, const Shell &s, long t) {
-  if (t < s.nA) {
-    const long per = (long)s.my * s.nk; const int side = (int)(t / per); const long r = t - side * per;
-    f(side ? s.mx - 1 : 0, (int)(r % s.my), s.ka + (int)(r / s.my));
-  } else if (t < s.nA + s.nB) {
-    t -= s.nA;
-    const long per = (long)(s.mx - 2) * s.nk; const int side = (int)(t / per); const long r = t - side * per;
-    f(1 + (int)(r % (s.mx - 2)), side ? s.my - 1 : 0, s.ka + (int)(r / (s.mx - 2)));
+// (32-bit index arithmetic: 64-bit divisions cost more than the copies these kernels do; a shell never has 2^31 nodes)
+template <class F> VFS_HD void shell_visit(const F &f, const Shell &s, long tl) {
+  unsigned t = (unsigned)tl;
+  const unsigned nA = (unsigned)s.nA, nB = (unsigned)s.nB;
+  if (t < nA) {
+    const unsigned per = (unsigned)s.my * (unsigned)s.nk; const unsigned side = t >= per ? 1u : 0u; const unsigned r = t - side * per;
+    const unsigned q = r / (unsigned)s.my;
+    f(side ? s.mx - 1 : 0, (int)(r - q * (unsigned)s.my), s.ka + (int)q);
+  } else if (t < nA + nB) {
+    t -= nA;
+    const unsigned w = (unsigned)(s.mx - 2), per = w * (unsigned)s.nk; const unsigned side = t >= per ? 1u : 0u; const unsigned r = t - side * per;
+    const unsigned q = r / w;
+    f(1 + (int)(r - q * w), side ? s.my - 1 : 0, s.ka + (int)q);
   } else {
-    t -= s.nA + s.nB;
-    const long per = (long)(s.mx - 2) * (s.my - 2); const int q = (int)(t / per); const long r = t - q * per;
-    f(1 + (int)(r % (s.mx - 2)), 1 + (int)(r / (s.mx - 2)), s.kp[q]);
+    t -= nA + nB;
+    const unsigned w = (unsigned)(s.mx - 2), per = w * (unsigned)(s.my - 2); const unsigned qq = t / per; const unsigned r = t - qq * per;
+    const unsigned q = r / w;
+    f(1 + (int)(r - q * w), 1 + (int)q, s.kp[qq]);
   }
 }
 #ifndef VFS_EMU

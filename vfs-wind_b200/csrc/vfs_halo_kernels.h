@@ -102,20 +102,22 @@ struct RefreshFused {
   }
   // shell coordinate s in [0, 2G+2) of a direction with m nodes -> -G..0, m-1..m+G-1
   VFS_HD static int shell(int s, int m) { return s <= VFS_G ? s - VFS_G : m - 1 + (s - VFS_G - 1); }
-  VFS_HD void operator()(long t) const {
+  VFS_HD void operator()(long tl) const {          // 32-bit index arithmetic (the slabs have far fewer than 2^31 nodes)
     const int lo[3] = {d.perx ? -VFS_G : 0, d.pery ? -VFS_G : 0, d.perz ? -VFS_G : 0};
-    const int W = 2 * VFS_G + 2;
-    if (t < S.n[0]) {                                   // i slab: shell x ext[1] x ext[2], shell fastest
-      const int s = (int)(t % W); const long r = t / W;
-      node(shell(s, d.mx), lo[1] + (int)(r % S.ext[1]), lo[2] + (int)(r / S.ext[1]));
-    } else if (t < S.n[0] + S.n[1]) {                   // j slab
-      t -= S.n[0];
-      const int x = (int)(t % S.ext[0]); const long r = t / S.ext[0];
-      node(lo[0] + x, shell((int)(r % W), d.my), lo[2] + (int)(r / W));
+    const unsigned W = 2 * VFS_G + 2, e0 = (unsigned)S.ext[0], e1 = (unsigned)S.ext[1];
+    unsigned t = (unsigned)tl;
+    const unsigned n0 = (unsigned)S.n[0], n1 = (unsigned)S.n[1];
+    if (t < n0) {                                       // i slab: shell x ext[1] x ext[2], shell fastest
+      const unsigned r = t / W, s = t - r * W, q = r / e1;
+      node(shell((int)s, d.mx), lo[1] + (int)(r - q * e1), lo[2] + (int)q);
+    } else if (t < n0 + n1) {                           // j slab
+      t -= n0;
+      const unsigned r = t / e0, x = t - r * e0, q = r / W;
+      node(lo[0] + (int)x, shell((int)(r - q * W), d.my), lo[2] + (int)q);
     } else {                                            // k slab
-      t -= S.n[0] + S.n[1];
-      const int x = (int)(t % S.ext[0]); const long r = t / S.ext[0];
-      node(lo[0] + x, lo[1] + (int)(r % S.ext[1]), shell((int)(r / S.ext[1]), d.mz));
+      t -= n0 + n1;
+      const unsigned r = t / e0, x = t - r * e0, q = r / e1;
+      node(lo[0] + (int)x, lo[1] + (int)(r - q * e1), shell((int)q, d.mz));
     }
   }
 };
