@@ -126,13 +126,14 @@ k_tile_march(const __grid_constant__ CUtensorMap tmap, VfsDev d, int kbeg, int k
     for (int kk = kfirst; kk < kfirst + STAGES && kk <= klast; kk++) issue(kk);
   }
   for (int kk = kfirst; kk < ka + PA; kk++) wait_plane(kk);
+  typename Body::State st;                  // per-thread state a body carries along its k column (e.g. a filter window)
   for (int k = ka; k < kb; k++) {
     // operands the body reads from global memory at its own node are requested before the TMA wait
     const auto pf = body.prefetch(d, active ? i : 1, active ? j : 1, k);
     wait_plane(k + PA);
     if (active) {
       TileAcc<R> A = {sm, k - kfirst, tx + R::OX, ty + R::OY};
-      body(d, A, i, j, k, pf);
+      body(d, A, i, j, k, pf, st, k == ka);
     }
     __syncthreads();                         // plane k-PB is no longer needed by anyone
     if (tid == 0) {
@@ -169,6 +170,7 @@ struct Les1Acc {
   __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(4, di, dj, dk); }
 };
 struct Les1Body {
+  typedef Les1Win State;
   __device__ __forceinline__ Les1Pre prefetch(const VfsDev &d, int i, int j, int k) const {
     const long p = d.idx(i, j, k);
     Les1Pre f;
@@ -177,10 +179,10 @@ struct Les1Body {
     f.aj = d.s[S_AJ][p]; f.nearv = d.near[p];
     return f;
   }
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k, const Les1Pre &pf) const {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k, const Les1Pre &pf, Les1Win &st, bool first) const {
     const long p = d.idx(i, j, k);
     Les1Acc A = {T, d, p, pf};
-    les1_core(d, A, i, j, k + d.kofs, p);
+    les1_core(d, A, i, j, k + d.kofs, p, &st, first);
   }
 };
 
@@ -197,9 +199,11 @@ VFS_HD bool les3_regular(const VfsDev &d, int i, int j, int kg) {
   return !(d.perx && (i == 1 || i == d.mx - 2)) && !(d.pery && (j == 1 || j == d.my - 2)) && !(d.perz && (kg == 1 || kg == d.mz - 2));
 }
 struct NoPrefetch {};
+struct NoState {};
 struct Les3Body {
+  typedef NoState State;
   __device__ __forceinline__ NoPrefetch prefetch(const VfsDev &, int, int, int) const { return NoPrefetch(); }
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k, const NoPrefetch &) const {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k, const NoPrefetch &, NoState &, bool) const {
     const int kg = k + d.kofs;
     if (!les3_regular(d, i, j, kg)) return;          // done by the staged kernel on thin slabs
     Les3Acc A = {T};
@@ -248,8 +252,9 @@ struct FluxBody {
       for (int a = 0; a < 3; a++) { d.s[S_FC3 + a][p] = fc[a]; d.s[S_FV3 + a][p] = fv[a]; }
     }
   }
+  typedef NoState State;
   __device__ __forceinline__ NoPrefetch prefetch(const VfsDev &, int, int, int) const { return NoPrefetch(); }
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k, const NoPrefetch &) const {
+  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingFlux> &T, int i, int j, int k, const NoPrefetch &, NoState &, bool) const {
     const long p = d.idx(i, j, k);
     if (VFS_WARP_ANY(d.near[p] != 0)) run<false>(d, T, i, j, k + d.kofs, p);
     else run<true>(d, T, i, j, k + d.kofs, p);
