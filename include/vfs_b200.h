@@ -138,9 +138,17 @@ long vfs_launch_count(vfs_ctx *c);
  * group; 0 if it has not run.  Valid after vfs_sync / any synchronous entry point. */
 enum vfs_timer { VFS_T_TOTAL = 0, VFS_T_C2C, VFS_T_FLUX, VFS_T_FP, VFS_T_PROJECT, VFS_T_LES1, VFS_T_LES2, VFS_T_LES3, VFS_T_NUT, VFS_T_COUNT };
 double vfs_last_ms(vfs_ctx *c, int which);
-/* tuning switches: key 0 = use the TMA-staged tiled kernels (default 1; 0 = staged one-thread-per-cell
- * kernels, same results bit for bit); key 1 = replay vfs_rhs_les_fused / vfs_formfunction_snes_dev as a
- * CUDA graph (default 0; single rank only; per-kernel timers are not updated while replaying) */
+/* tuning switches (defaults are the measured-best settings; every setting gives the same fields to rounding):
+ *   0  kernel family: 1 = TMA-staged marching kernels (default), 0 = one-thread-per-cell staged kernels (the literal
+ *      restatement), 2 = experimental fully fused residual kernel
+ *   1  replay vfs_rhs_les_fused / vfs_formfunction_snes_dev as a CUDA graph (default 0; per-kernel timers are not
+ *      updated while replaying; with nranks > 1 only together with vfs_nccl_init)
+ *   2  LES pass-2 tile height 16 / 12 (default) / 8        3  resident blocks per SM of the one-ring flux kernel
+ *   4  LES pass-1 form: 1 = TMA tile march (default), 0 / 2 / 3 = block-program variants
+ *   6  mask-free fast paths for warps far from any nvert != 0 (default 1)
+ *   7  face-flux kernel: 1 = two TMA rings, ucat and metric planes (default), 0 = one ring
+ *   8  single-rank ghost-refresh sequences as one launch (default 1)
+ *   9  overlap the k-face-flux and Fp halo exchanges with interior planes (default 1; nranks > 1 with vfs_nccl_init) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus

@@ -113,7 +113,6 @@ struct vfs_ctx {
   int les2_ty = 12;              // tile height of the LES pass-2 block program: 16 (1 block/SM) or 8 (2 blocks/SM) (option key 2)
   int les1_var = 1;              // LES pass 1: 0 = block program 32x16, 1 = TMA tile march, 2 = block program 32x8 x2/SM, 3 = 32x16 x2/SM (option key 4)
   int flux_var = 1;              // regular face fluxes: 1 = k_flux_march (metric planes staged too), 0 = k_tile_march<RingFlux> (option key 7)
-  int les3_var = 0;              // LES pass 3: 0 = block program 32x16 x2/SM, 1 = TMA tile march (option key 5)
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
   bool lesgeo_valid = false;     // S_LFINV..S_LF2 match the current metrics and nvert mask
@@ -571,7 +570,6 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 2) c->les2_ty = value;
   else if (key == 3) c->flux_minb = value;
   else if (key == 4) c->les1_var = value;
-  else if (key == 5) c->les3_var = value;
   else if (key == 6) { c->fastpath = value; c->near_valid = false; }
   else if (key == 7) c->flux_var = value;
   else if (key == 8) c->fuse_refresh = value;
