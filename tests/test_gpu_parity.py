@@ -160,3 +160,46 @@ def test_graph_replay_equals_eager(pkg):
         ctx.close()
     for n in res[0]:
         assert np.array_equal(res[0][n], res[1][n]), n
+
+
+def test_full_size_kernel_families_agree(pkg):
+    """BASELINE.json's bench size (256^3 nodes): the oracle cannot run there in seconds, so the marching /
+    TMA kernels (what the bench times) are checked against the one-thread-per-cell staged kernels (the literal
+    restatement, itself oracle-checked at small sizes) on the same device-resident case — every tile, k-chunk
+    and the full k-march length of the benchmark configuration — plus two size-independent properties:
+    Contra2Cart is idempotent, and the whole unit is deterministic (two runs agree bitwise)."""
+    import torch
+    if torch.cuda.mem_get_info(0)[0] < 40e9:
+        pytest.skip("needs ~35 GB of free device memory")
+    capi, cases = pkg.capi, pkg.cases
+    cfg = dict(cases.CONFIGS["c2_box256"])
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    ctxs = []
+    for fused in (0, 1):
+        ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+        ctx.set_option(0, fused)
+        ctxs.append(ctx)
+    ctxs[0].upload("COOR", cases.make_grid(cfg)); ctxs[0].FormMetrics()
+    met = dict(csi=ctxs[0].download("CSI"), eta=ctxs[0].download("ETA"), zet=ctxs[0].download("ZET"), aj=ctxs[0].download("AJ"))
+    f = cases.make_fields(cfg, met)
+    ctxs[1].upload("COOR", cases.make_grid(cfg)); ctxs[1].FormMetrics()
+    outs = []
+    for ctx in ctxs:
+        for k, n in pc.FIELDS_IN:
+            ctx.upload(n, f[k])
+        ctx.rhs_les_fused()
+        outs.append({n: ctx.download(n) for n in ("RHS", "UCAT", "CS", "NU_T")})
+    for n in ("RHS", "CS", "NU_T"):
+        assert pc.relerr(outs[1][n], outs[0][n]) <= 5e-13, (n, pc.relerr(outs[1][n], outs[0][n]))
+    assert np.array_equal(outs[0]["RHS"] == 0, outs[1]["RHS"] == 0)
+    assert np.array_equal(outs[0]["UCAT"], outs[1]["UCAT"])
+    assert np.isfinite(outs[1]["RHS"]).all() and np.abs(outs[1]["RHS"]).max() > 0
+    ctx = ctxs[1]
+    ctx.Contra2Cart()                      # idempotent on its own output
+    assert np.array_equal(ctx.download("UCAT"), outs[1]["UCAT"])
+    ctx.upload("UCONT", f["ucont"])        # deterministic: the same unit again
+    ctx.rhs_les_fused()
+    for n in ("RHS", "CS", "NU_T"):
+        assert np.array_equal(ctx.download(n), outs[1][n]), n
+    for c in ctxs:
+        c.close()
