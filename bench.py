@@ -247,9 +247,12 @@ def run_ours(args):
     def e2e_step():
         ctx.upload_ptr("UCONT", xh.data_ptr())        # host lUcont -> device (what the glue does for Contra2Cart)
         ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
-        ctx.download_ptr("CS", csh.data_ptr()); ctx.download_ptr("NU_T", nuh.data_ptr())   # LES results back to the host Vecs
+        # LES results back to the host Vecs: asynchronous copies on the library's copy stream, so this device->host
+        # traffic overlaps the host->device copy of X below (PCIe is full duplex); waited for before the step ends
+        ctx.download_async("CS", csh.data_ptr(), 0); ctx.download_async("NU_T", nuh.data_ptr(), 1)
         ctx.FormFunction_SNES(xh.data_ptr(), fh.data_ptr())   # X (host) -> F (host)
-        return float(fh[nzl // 2, my // 2, mx // 2, 2])       # read the step's result on the host
+        ctx.download_wait()
+        return float(fh[nzl // 2, my // 2, mx // 2, 2]) + float(nuh[nzl // 2, my // 2, mx // 2])      # read the step's results on the host
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
     barrier()

@@ -119,6 +119,12 @@ int vfs_les_cs(vfs_ctx *c);
 int vfs_les_nut(vfs_ctx *c);
 /* Rhs (device field `rhs_field`, VFS_RHS or VFS_RHS_O) += scale * R(Ucont, Ucat) */
 int vfs_formfunction2(vfs_ctx *c, int rhs_field, double scale);
+/* Asynchronous download: the field is packed on the context's stream and copied to `host` (pinned memory for a
+ * truly asynchronous copy) on a separate copy stream, so the transfer overlaps whatever is queued next on the
+ * context (e.g. the host->device copy and kernels of vfs_formfunction_snes: PCIe is full duplex).  `host` is valid
+ * after vfs_download_wait (or vfs_destroy).  At most one scalar (dof 1) or vector field per slot, slot = 0 or 1. */
+int vfs_download_async(vfs_ctx *c, int field, double *host, int slot);
+int vfs_download_wait(vfs_ctx *c);
 /* Legacy explicit-solver pieces, Convection(UserCtx*,Vec Ucont,Vec Ucat,Vec Conv) Source/rhs.c:751 and
  * Viscous(UserCtx*,Vec,Vec,Vec Visc) Source/rhs.c:1071 (callers timeadvancing1.c:75-76): QUICK
  * flux-difference convection and the (nu + nu_t) viscous term of the current VFS_UCONT / VFS_UCAT

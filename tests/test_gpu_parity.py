@@ -87,6 +87,37 @@ def test_roundtrip_and_idempotence(pkg):
     ctx.close()
 
 
+def test_async_download_equals_download(pkg):
+    """vfs_download_async + vfs_download_wait deliver the same bytes as vfs_download, also with other work queued
+    in between (the bench's e2e leg overlaps these copies with the next call's host->device copy)."""
+    import torch
+    capi, cases = pkg.capi, pkg.cases
+    cfg = cases.scaled(cases.CONFIGS["c2_box256"], 40, 33, 37)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+    ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
+    met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+    f = cases.make_fields(cfg, met)
+    for k, n in pc.FIELDS_IN:
+        ctx.upload(n, f[k])
+    ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+    cs = torch.empty((mz, my, mx), dtype=torch.float64).pin_memory()
+    ucat = torch.empty((mz, my, mx, 3), dtype=torch.float64).pin_memory()
+    ctx.download_async("CS", cs.data_ptr(), 0); ctx.download_async("UCAT", ucat.data_ptr(), 1)
+    F = ctx.FormFunction_SNES(pc.krylov_x(f["ucont"]))      # queued behind the packs, overlapping the copies
+    ctx.download_wait()
+    assert np.array_equal(cs.numpy(), ctx.download("CS"))
+    assert np.isfinite(F).all()
+    # UCAT was packed BEFORE the residual recomputed it from the perturbed X: compare with a fresh run
+    ctx2 = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+    ctx2.upload("COOR", cases.make_grid(cfg)); ctx2.FormMetrics()
+    for k, n in pc.FIELDS_IN:
+        ctx2.upload(n, f[k])
+    ctx2.Contra2Cart()
+    assert np.array_equal(ucat.numpy(), ctx2.download("UCAT"))
+    ctx.close(); ctx2.close()
+
+
 def test_multi_gpu_bitwise_equal_single_gpu():
     """k-slab decomposition over all visible GPUs (NCCL halos) == single-GPU result, bitwise."""
     import os, subprocess, sys, torch

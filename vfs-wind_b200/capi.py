@@ -21,7 +21,7 @@ FIELD_DOF = {"COOR": 3, "CSI": 3, "ETA": 3, "ZET": 3, "AJ": 1, "NVERT": 1, "UCON
 
 EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs_set_stream", "vfs_set_halo_callback", "vfs_sync",
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
-           "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous",
+           "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_download_async", "vfs_download_wait",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms"]
 
 
@@ -61,6 +61,9 @@ def _bind(lib):
     lib.vfs_scalar_ptr.restype = C.c_void_p
     lib.vfs_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vfs_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    if hasattr(lib, "vfs_download_async"):
+        lib.vfs_download_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.vfs_download_wait.argtypes = [C.c_void_p]
     lib.vfs_halo_exchange.argtypes = [C.c_void_p, C.c_int]
     for f in ("vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_convection", "vfs_viscous"):
         getattr(lib, f).argtypes = [C.c_void_p]
@@ -219,6 +222,13 @@ class VfsContext:
 
     def download_ptr(self, field, host_ptr):
         self._ck(self.lib.vfs_download(self.h, FIELD_ID[field], C.c_void_p(host_ptr)))
+
+    def download_async(self, field, host_ptr, slot=0):
+        """Start an asynchronous download into the (pinned) host address; valid after download_wait()."""
+        self._ck(self.lib.vfs_download_async(self.h, FIELD_ID[field], C.c_void_p(host_ptr), int(slot)))
+
+    def download_wait(self):
+        self._ck(self.lib.vfs_download_wait(self.h))
 
     def halo_exchange(self, field):
         self._ck(self.lib.vfs_halo_exchange(self.h, FIELD_ID[field]))

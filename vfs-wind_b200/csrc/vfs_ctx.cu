@@ -73,6 +73,7 @@ struct vfs_ctx {
   VfsDev d;
   double *pool = nullptr;        // all scalars, contiguous
   double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
+  double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use
   long scalar_len = 0;
   cudaStream_t stream = 0;
   bool own_stream = false;
@@ -96,6 +97,8 @@ struct vfs_ctx {
 #ifndef VFS_EMU
   ncclComm_t comm = nullptr;     // k-neighbour halo exchange inside the library (vfs_nccl_init)
   double *hbuf = nullptr;        // packed send (hi, lo) and receive (lo, hi) staging, VFS_MAXGRP scalars each
+  cudaStream_t copy_stream = 0;  // vfs_download_async
+  cudaEvent_t ev_pack = 0;
   cudaStream_t side = 0;         // halo exchanges that overlap interior compute run here (forked / joined by events)
   cudaEvent_t ev_fork = 0, ev_join = 0;
 #endif
@@ -466,6 +469,9 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_pack) cudaEventDestroy(c->ev_pack);
+  for (int q = 0; q < 2; q++) if (c->stage_async[q]) cudaFree(c->stage_async[q]);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -651,6 +657,33 @@ extern "C" int vfs_download(vfs_ctx *c, int field, double *host) {
   PackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
   return d2h_stage(c, host, FIELD[field].dof);
+}
+
+extern "C" int vfs_download_async(vfs_ctx *c, int field, double *host, int slot) {
+  if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC || slot < 0 || slot > 1) return VFS_ERR_ARG;
+#ifndef VFS_EMU
+  const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * FIELD[field].dof * sizeof(double);
+  if (!c->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+  }
+  if (!c->stage_async[slot]) CK(cudaMalloc((void **)&c->stage_async[slot], (size_t)c->d.nzl * c->d.my * c->d.mx * 3 * sizeof(double)));
+  PackAoS f = {c->d, c->stage_async[slot], FIELD[field].s0, FIELD[field].dof};
+  RUN(launch(c, box_owned(c), f));
+  CK(cudaEventRecord(c->ev_pack, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_pack, 0));
+  CK(cudaMemcpyAsync(host, c->stage_async[slot], n, cudaMemcpyDeviceToHost, c->copy_stream));
+  return 0;
+#else
+  (void)slot; return vfs_download(c, field, host);
+#endif
+}
+extern "C" int vfs_download_wait(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+#ifndef VFS_EMU
+  if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+#endif
+  return 0;
 }
 
 // ---- FormMetrics ------------------------------------------------------------------------------------
