@@ -72,6 +72,7 @@ typedef struct vfs_params {
   int i_periodic, j_periodic, k_periodic;     /* legacy single-rank periodicity: must be 0   */
   int i_homo_filter, j_homo_filter, k_homo_filter; /* must be 0 (off in all configs)         */
   double ren, dt, max_cs;
+  double roughness_size; /* -roughness (main.c:319,1734): k_s of the rough-wall log law, bctype -2            */
 } vfs_params;
 
 typedef struct vfs_ctx vfs_ctx;

@@ -111,6 +111,8 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
     ref.Contra2Cart()
     ctx.Contra2Cart()
     err["Contra2Cart_ucat"] = relerr(ctx.download("UCAT"), ref.owned("Ucat"))
+    if any(b in (-1, -2) for b in cfg["bctype"][:4]):      # wall-function sides: friction velocity of the first cells (rhs.c:336,371,401,435)
+        err["Contra2Cart_ustar"] = relerr(ctx.download("USTAR")[1:-1, 1:-1, 1:-1], np.array(ref.owned("lUstar"))[1:-1, 1:-1, 1:-1])
     if cfg["flags"].get("les"):
         ref.Compute_Smagorinsky_Constant_1()
         ctx.Compute_Smagorinsky_Constant_1()
@@ -134,6 +136,7 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
     ref.IB_BC()
     ctx.IB_BC()
     err["IB_BC_ucont"] = relerr(ctx.download("UCONT"), ref.owned("lUcont"))
+    err["IB_BC_nvert_mismatches"] = float(np.count_nonzero(ctx.download("NVERT") != np.array(ref.owned("lNvert"))))     # masks: bit-exact
     ref.view("RHS_o")[...] = 0
     ref.Formfunction_2("RHS_o", 1.0)
     ctx.upload("RHS_O", np.zeros_like(fields["rhs_o"]))

@@ -54,3 +54,22 @@ def test_emulated_staged_option(pkg, refdrv, emu):
     assert err.pop("FormFunction_SNES_zero_pattern") == 0
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("bctype,extra", [
+    ([100, 100, -1, -2, 100, 100], dict(ii_periodic=1, kk_periodic=1, immersed=0, ti=5, tistart=5, roughness_size=2.e-4)),   # first step: IB_BC marks the first cells
+    ([-1, -2, -2, -1, 5, 4], dict(ii_periodic=0, kk_periodic=0, immersed=0, roughness_size=1.e-3)),                           # all four i/j sides
+    ([100, 100, -1, 10, 5, 4], dict(ii_periodic=1, kk_periodic=0)),                                                           # with immersed bodies (c3)
+])
+def test_emulated_wall_function_boundaries(pkg, refdrv, emu, bctype, extra):
+    """bctype -1 (Cabot) / -2 (rough log law): first-cell velocities of Contra2Cart_2 (rhs.c:311-440), u_tau, IB_BC's
+    first-step nvert marking and wall-face flux zeroing (momentum.c:2048-2074, 2169-2189)."""
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15)
+    cfg = dict(base)
+    cfg["flags"] = dict(base["flags"], **extra)
+    cfg["bctype"] = bctype
+    err = pc.run_parity(cfg, refdrv, lib=emu)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    assert err.pop("IB_BC_nvert_mismatches") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad

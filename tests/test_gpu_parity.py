@@ -51,6 +51,25 @@ def test_flag_variants(pkg, refdrv):
         assert not bad, (extra, bad)
 
 
+@pytest.mark.parametrize("bctype,extra", [
+    ([100, 100, -1, -2, 100, 100], dict(ii_periodic=1, kk_periodic=1, immersed=0, ti=5, tistart=5, roughness_size=2.e-4)),
+    ([-1, -2, -2, -1, 5, 4], dict(ii_periodic=0, kk_periodic=0, immersed=0, roughness_size=1.e-3)),
+    ([100, 100, -1, 10, 5, 4], dict(ii_periodic=1, kk_periodic=0)),
+])
+def test_wall_function_boundaries(pkg, refdrv, bctype, extra):
+    """bctype -1 (Cabot) / -2 (rough log law) on i/j sides: first-cell velocities and u_tau (rhs.c:311-440), IB_BC's
+    first-step nvert marking (bit-exact) and wall-face flux zeroing (momentum.c:2048-2074, 2169-2189)."""
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 45, 30, 41)
+    cfg = dict(base)
+    cfg["flags"] = dict(base["flags"], **extra)
+    cfg["bctype"] = bctype
+    err = pc.run_parity(cfg, refdrv, device=0)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    assert err.pop("IB_BC_nvert_mismatches") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
 def test_unsupported_flags_fail_loudly(pkg):
     capi = pkg.capi
     p = capi.make_params(16, 16, 16, dict(les=2, levelset=1), 100.0, 1e-3, [1] * 6)

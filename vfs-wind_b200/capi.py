@@ -32,7 +32,7 @@ class VfsParams(C.Structure):
                                        "viscosity_wallmodel", "wallfunction", "rotor_model", "nacelle_model", "IB_delta",
                                        "ti", "tistart", "rstart_flg", "levelset", "rans", "inviscid", "skew", "movefsi", "rotatefsi",
                                        "i_periodic", "j_periodic", "k_periodic", "i_homo_filter", "j_homo_filter", "k_homo_filter")] + \
-               [(n, C.c_double) for n in ("ren", "dt", "max_cs")]
+               [(n, C.c_double) for n in ("ren", "dt", "max_cs", "roughness_size")]
 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int))
@@ -100,8 +100,8 @@ def make_params(mx, my, mz, flags, ren, dt, bctype, kofs=0, nzl=None, rank=0, nr
         p.bctype[q] = int(bctype[q])
     p.ti, p.tistart, p.max_cs = 10, 0, 0.5
     for k, v in flags.items():
-        if k == "max_cs":
-            p.max_cs = float(v)
+        if k in ("max_cs", "roughness_size"):
+            setattr(p, k, float(v))
         elif hasattr(p, k):
             setattr(p, k, int(v))
         elif v:

@@ -89,6 +89,10 @@ struct C2CGhostRules {
     if (bc[5] == 4 && kg == mz - 1 && i != 0 && i != mx - 1 && j != 0 && j != my - 1) {
       if (d.s[S_NV][p - d.sk] > 0.1 || solid_flag) { u = mk3(0, 0, 0); w = true; }
     }
+    // the corner zeroing of rhs.c:675-681 also hits the k = mz-1 boundary plane (guards: j != my-2, k != 0, k != mz-2)
+    if (j != my - 2 && kg != 0 && kg != mz - 2 &&
+        ((bc[0] <= 1 && bc[2] <= 1 && i == 1 && j == 1) || (bc[1] <= 1 && bc[2] <= 1 && i == mx - 2 && j == 1) ||
+         (bc[0] <= 1 && bc[3] <= 1 && i == 1 && j == my - 2) || (bc[1] <= 1 && bc[3] <= 1 && i == mx - 2 && j == my - 2))) { u = mk3(0, 0, 0); w = true; }
     if (w) st3(d, S_U0, p, u);
   }
 };

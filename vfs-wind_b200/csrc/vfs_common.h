@@ -72,7 +72,7 @@ struct VfsDev {
   int bc[6];
   int les, second_order, laplacian, immersed, clark, testfilter_ik, visc_wm, wallfunction, has_feul;
   int ti, tistart, rstart_flg, bdf2, single_rank;
-  double ren, dt, max_cs;
+  double ren, dt, max_cs, roughness;
   double *s[S_COUNT];
   // near[p] != 0: some node within +-2 of p (any direction) has nvert != 0 (NearSolid, vfs_c2c_kernels.h).
   // Warps whose nodes are all "far" run mask-free specialisations of the stencil code (same arithmetic:

@@ -121,6 +121,7 @@ struct vfs_ctx {
   bool lesgeo_valid = false;     // S_LFINV..S_LF2 match the current metrics and nvert mask
   unsigned char *near = nullptr; // near-solid byte mask (VfsDev::near), one byte per padded node
   bool near_valid = false;
+  bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
 };
@@ -229,6 +230,7 @@ static int klo(const vfs_ctx *c, int kg) { int k = kg - c->d.kofs; return k < 0 
 static Box box_interior(const vfs_ctx *c) { Box b = {1, c->d.mx - 1, 1, c->d.my - 1, klo(c, 1), klo(c, c->d.mz - 1)}; return b; }
 
 // ---- ghost refresh primitives -------------------------------------------------------------------
+static bool has_wallfn(const VfsDev &d) { for (int q = 0; q < 4; q++) if (d.bc[q] == -1 || d.bc[q] == -2) return true; return false; }
 static bool any_per_d(const VfsDev &d) { return d.perx || d.pery || d.perz; }
 static int wrap_ij(vfs_ctx *c, const Grp &g, int ka = 0, int kb = -1) {
   const VfsDev &d = c->d;
@@ -400,7 +402,9 @@ static int check_params(const vfs_params *p, std::string &why) {
   if (p->i_homo_filter || p->j_homo_filter || p->k_homo_filter) { why = "homogeneous-plane Cs averaging not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
-  for (int q = 0; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2 || p->bctype[q] == 11) { why = "wall-function / cylinder boundary types (-1,-2,11) not supported"; return VFS_ERR_UNSUPPORTED; }
+  for (int q = 0; q < 6; q++) if (p->bctype[q] == 11) { why = "cylinder inflow boundary type 11 not supported"; return VFS_ERR_UNSUPPORTED; }
+  for (int q = 4; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2) { why = "wall-function boundary types (-1,-2) on a k side: Contra2Cart_2 has no velocity rule for them (rhs.c:311-440)"; return VFS_ERR_UNSUPPORTED; }
+  for (int q = 0; q < 4; q++) if (p->bctype[q] == -2 && !(p->roughness_size > 0)) { why = "bctype -2 (rough-wall log law) needs roughness_size > 0"; return VFS_ERR_ARG; }
   if (!(p->ren > 0) || !(p->dt > 0)) { why = "ren and dt must be positive"; return VFS_ERR_ARG; }
   return 0;
 }
@@ -417,7 +421,7 @@ static void fill_dev(vfs_ctx *c) {
   d.testfilter_ik = p.testfilter_ik; d.visc_wm = p.viscosity_wallmodel; d.wallfunction = p.wallfunction;
   d.has_feul = (p.rotor_model || p.nacelle_model || p.IB_delta) ? 1 : 0;
   d.ti = p.ti; d.tistart = p.tistart; d.rstart_flg = p.rstart_flg; d.bdf2 = 0; d.single_rank = p.nranks == 1;
-  d.ren = p.ren; d.dt = p.dt; d.max_cs = p.max_cs;
+  d.ren = p.ren; d.dt = p.dt; d.max_cs = p.max_cs; d.roughness = p.roughness_size;
 }
 
 extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
@@ -639,7 +643,7 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_AJ) c->iaj_valid = false;
   if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
-  if (field == VFS_NVERT) c->near_valid = false;
+  if (field == VFS_NVERT) { c->near_valid = false; c->wall_marked = false; }
   if (field == VFS_NVERT) {       // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep
     const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx;
     bool any = false;
@@ -717,6 +721,7 @@ static int run_les_derive_boundary(vfs_ctx *c) { LesDeriveBoundary f = {c->d}; r
 // which is what its owner copies into it.  This removes 4 (8 at the seam ranks) of the 17 inter-rank
 // exchanges of one RHS+LES unit; a single rank keeps the wrap-fill path (no ghost planes to replay).
 #define C2C_EXT 3
+static int ensure_wm_table(vfs_ctx *c);
 static int contra2cart(vfs_ctx *c) {
   const VfsDev &d = c->d;
   c->sabs_valid = false;
@@ -748,8 +753,22 @@ static int contra2cart(vfs_ctx *c) {
   { C2CInterior f = {d}; RUN(launch(c, bi, f)); }                    // rhs.c:158-247
   ev_rec(c, 2 * VFS_T_C2C + 1);
   RUN(refresh3());                                                   // rhs.c:251-291
-  { CopyScalar3 f = {d, S_U0, S_FP0}; RUN(launch_shell(c, ka, kb, f, true)); }     // lUcat snapshot read by the rules
+  const bool wallfn = has_wallfn(d);
+  if (wallfn) {                                                      // wall-function first cells read interior neighbours of the snapshot too
+    CopyScalar3 f = {d, S_U0, S_FP0}; Box b = {0, d.mx, 0, d.my, ka, kb}; RUN(launch(c, b, f));
+  } else { CopyScalar3 f = {d, S_U0, S_FP0}; RUN(launch_shell(c, ka, kb, f, true)); }     // lUcat snapshot read by the rules
   { C2CGhostRules f = {d}; RUN(launch_shell(c, ka, kb, f, true)); }                // rhs.c:302-682 (boundary nodes)
+  if (wallfn) {                                                      // rhs.c:311-440 (first interior cells of the -1 / -2 sides)
+    RUN(ensure_wm_table(c));
+    C2CWallFn f = {d, c->wm_table};
+    const int pl[4] = {1, d.mx - 2, 1, d.my - 2};
+    for (int q = 0; q < 4; q++) {
+      if (d.bc[q] != -1 && d.bc[q] != -2) continue;
+      Box b = bi; b.i0 = 1; b.i1 = d.mx - 1; b.j0 = 1; b.j1 = d.my - 1;
+      if (q < 2) { b.i0 = pl[q]; b.i1 = pl[q] + 1; } else { b.j0 = pl[q]; b.j1 = pl[q] + 1; }
+      RUN(launch(c, b, f));
+    }
+  }
   {                                                                  // rhs.c:305-308,676-681 (interior nodes)
     C2CInteriorFix f = {d};
     if (c->has_solid) RUN(launch(c, bi, f));                         // solid cells -> 0: the whole interior
@@ -768,8 +787,28 @@ extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(con
 // ---- IB_BC ---------------------------------------------------------------------------------------------
 static int ib_bc(vfs_ctx *c) {
   const VfsDev &d = c->d;
+  bool wallfn_any = false;
+  for (int q = 0; q < 6; q++) wallfn_any = wallfn_any || d.bc[q] == -1 || d.bc[q] == -2;
+  if (wallfn_any && !d.immersed && d.ti == d.tistart && !c->wall_marked) {      // momentum.c:2048-2074
+#ifndef VFS_EMU
+    if (c->capturing) { set_err(c, "the first-step nvert marking of IB_BC cannot be captured into a graph: run the step eagerly once"); return VFS_ERR_CUDA; }
+#endif
+    { IbBcMarkWall f = {d}; RUN(launch(c, box_interior(c), f)); }
+    RUN(g2l(c, grp(S_NV, 1)));
+    c->wall_marked = true; c->near_valid = false; c->lesgeo_valid = false; c->sabs_valid = false;
+  }
   if (any_per(c)) RUN(node_copy(c, grp(S_U0, 3)));                   // momentum.c:2086-2107
   if (d.immersed) { IbBcFaces f = {d}; RUN(launch(c, box_interior(c), f)); }
+  if (has_wallfn(d)) {                                               // momentum.c:2169-2189
+    IbBcWallFn f = {d};
+    const int pl[4] = {1, d.mx - 2, 1, d.my - 2};
+    for (int q = 0; q < 4; q++) {
+      if (d.bc[q] != -1 && d.bc[q] != -2) continue;
+      Box b = box_interior(c);
+      if (q < 2) { b.i0 = pl[q]; b.i1 = pl[q] + 1; } else { b.j0 = pl[q]; b.j1 = pl[q] + 1; }
+      RUN(launch(c, b, f));
+    }
+  }
   IbBcBoundary f = {d};
   const int m[3] = {d.mx, d.my, d.mz};
   const int per[3] = {d.perx, d.pery, d.perz};
@@ -852,8 +891,7 @@ static int ensure_near(vfs_ctx *c) {
 
 // Cabot wall model at the j = 0 faces (viscosity_wallmodel, momentum.c:1139-1154): table once, then one
 // Newton solve per face of the plane, before the flux kernels read the override
-static int wall_model(vfs_ctx *c) {
-  const VfsDev &d = c->d;
+static int ensure_wm_table(vfs_ctx *c) {
   if (!c->wm_table) {
     const size_t bytes = (size_t)(VFS_WM_NYP + 1) * sizeof(double);
 #ifndef VFS_EMU
@@ -865,6 +903,11 @@ static int wall_model(vfs_ctx *c) {
     { WmTableIntervals f = {c->wm_table}; Box b = {0, VFS_WM_NYP + 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
     { WmTableScan f = {c->wm_table}; Box b = {0, 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
   }
+  return 0;
+}
+static int wall_model(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  RUN(ensure_wm_table(c));
   WallModelPlane f = {d, c->wm_table};
   Box b = {1, d.mx - 1, 0, 1, klo(c, 1), klo(c, d.mz - 1)};
   return launch(c, b, f);

@@ -99,4 +99,89 @@ struct WallModelPlane {
     d.s[S_WM][p0] = nu_t;
   }
 };
+
+// ---- wall-function boundary types -1 (smooth, Cabot) and -2 (rough log law) on the i and j sides -------------
+// Contra2Cart_2 (rhs.c:311-440): the first interior cell next to such a side gets a modelled velocity: the
+// tangential part of the second cell's velocity rescaled to the wall law at the first cell's height, plus (smooth
+// law only) the normal part scaled by sb/sc (wallfunction.c:34-59 wall_function, :87-111 wall_function_roughness_
+// loglaw).  u_tau goes to lUstar.  Neighbours are read from the snapshot taken before the rules (S_FP0..2: the
+// reference reads its lUcat copy), so cells that are first cells of two walls do not see each other's update.
+VFS_HD double wm_u_loglaw_rough(double y, double utau, double ks) { return utau * (1. / 0.41 * log(y / ks) + 8.5); }   // wallfunction.c:227-238
+VFS_HD double wm_find_utau_rough(double u, double y, double guess, double ks) {                                      // wallfunction.c:429-444
+  double x = guess, x0 = guess;
+  for (int it = 0; it < 30; it++) {
+    const double eps = 1.e-7;
+    const double df = ((wm_u_loglaw_rough(y, x0 + eps, ks) - u) - (wm_u_loglaw_rough(y, x0 - eps, ks) - u)) / (2 * eps);
+    x = x0 - (wm_u_loglaw_rough(y, x0, ks) - u) / df;
+    if (fabs(x0 - x) < 1.e-10) break;
+    x0 = x;
+  }
+  return x;
+}
+struct C2CWallFn {
+  VfsDev d; const double *buf;
+  // one wall: D = 0 (i sides) / 1 (j sides), type -1 / -2, `far` = the side at m-2 (normal flipped, neighbour at -1)
+  VFS_HD void apply(long p, int D, int type, bool far) const {
+    const int sm = S_CSI0 + 3 * D;
+    const double ax = d.s[sm][p], ay = d.s[sm + 1][p], az = d.s[sm + 2][p];
+    const double area = sqrt(ax * ax + ay * ay + az * az);
+    const long nb = p + (far ? -1 : 1) * (D == 0 ? 1 : d.sj);
+    const double sb = 0.5 / d.s[S_AJ][p] / area;
+    const double sc = 2 * sb + 0.5 / d.s[S_AJ][nb] / area;
+    const V3 Uc = ld3(d, S_FP0, nb);
+    V3 n = cov_column(d, p, D);                       // Calculate_normal (rhs2.c:614-647)
+    const double sum = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+    n.x /= sum, n.y /= sum, n.z /= sum;
+    if (far) { n.x *= -1, n.y *= -1, n.z *= -1; }
+    const double nu = 1. / d.ren;
+    const double un = Uc.x * n.x + Uc.y * n.y + Uc.z * n.z;
+    double ut = Uc.x - un * n.x, vt = Uc.y - un * n.y, wt = Uc.z - un * n.z;
+    const double ut_mag = sqrt(ut * ut + vt * vt + wt * wt);
+    double ustar, mod;
+    if (type == -1) { ustar = wm_find_utau(buf, nu, ut_mag, sc, 0.01); mod = ustar * ustar * wm_integrate_F(buf, nu, ustar, sb); }
+    else { ustar = wm_find_utau_rough(ut_mag, sc, 0.01, d.roughness); mod = wm_u_loglaw_rough(sb, ustar, d.roughness); }
+    if (ut_mag > 1.e-10) { ut *= mod / ut_mag; vt *= mod / ut_mag; wt *= mod / ut_mag; }
+    else ut = vt = wt = 0;
+    V3 Ub = mk3(ut, vt, wt);
+    if (type == -1) { Ub.x = ut + sb / sc * un * n.x; Ub.y = vt + sb / sc * un * n.y; Ub.z = wt + sb / sc * un * n.z; }
+    d.s[S_USTAR][p] = ustar;
+    st3(d, S_U0, p, Ub);
+  }
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = d.kglob(k);
+    if (kg < 1 || kg > d.mz - 2) return;
+    const long p = d.idx(i, j, k);
+    if ((int)(d.s[S_NV][p] + 0.1) == 3) return;       // rhs.c:306-309: solid cells are zeroed and skipped
+    const int *bc = d.bc;
+    for (int t = -1; t >= -2; t--)                      // rhs.c:311-376: smooth, then rough, i sides
+      if ((bc[0] == t && i == 1) || (bc[1] == t && i == d.mx - 2)) apply(p, 0, t, i != 1);
+    for (int t = -1; t >= -2; t--)                      // rhs.c:378-440: j sides
+      if ((bc[2] == t && j == 1) || (bc[3] == t && j == d.my - 2)) apply(p, 1, t, j != 1);
+  }
+};
+// IB_BC (momentum.c:2048-2074): at the first time step of a run without immersed bodies the first cells next to
+// a wall-function side (k sides included) become IB nodes, nvert = 1
+struct IbBcMarkWall {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const int *bc = d.bc;
+    const bool m = ((bc[0] == -1 || bc[0] == -2) && i == 1) || ((bc[1] == -1 || bc[1] == -2) && i == d.mx - 2) ||
+                   ((bc[2] == -1 || bc[2] == -2) && j == 1) || ((bc[3] == -1 || bc[3] == -2) && j == d.my - 2) ||
+                   ((bc[4] == -1 || bc[4] == -2) && kg == 1) || ((bc[5] == -1 || bc[5] == -2) && kg == d.mz - 2);
+    if (m) d.s[S_NV][d.idx(i, j, k)] = 1;
+  }
+};
+// IB_BC (momentum.c:2169-2189): no flux through the wall face of a wall-function first cell
+struct IbBcWallFn {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    const int *bc = d.bc;
+    if (((bc[0] == -1 || bc[0] == -2) && i == 1)) d.s[S_UC0][p - 1] = 0;
+    else if (((bc[1] == -1 || bc[1] == -2) && i == d.mx - 2)) d.s[S_UC0][p] = 0;
+    if (((bc[2] == -1 || bc[2] == -2) && j == 1)) d.s[S_UC1][p - d.sj] = 0;
+    else if (((bc[3] == -1 || bc[3] == -2) && j == d.my - 2)) d.s[S_UC1][p] = 0;
+  }
+};
 #endif

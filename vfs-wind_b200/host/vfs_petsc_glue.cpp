@@ -32,6 +32,7 @@ extern PetscInt les, second_order, immersed, inviscid, movefsi, rotatefsi, rotor
 extern int laplacian, clark, central, testfilter_ik, viscosity_wallmodel, levelset, rans, skew;
 extern int i_periodic, j_periodic, k_periodic, ii_periodic, jj_periodic, kk_periodic, i_homo_filter, j_homo_filter, k_homo_filter;
 extern PetscReal max_cs;
+extern double roughness_size;
 extern PetscTruth rstart_flg;
 
 struct GlueState { vfs_ctx *ctx; bool const_valid; std::vector<double> buf; };
@@ -53,7 +54,7 @@ static void fill_params(UserCtx *user, vfs_params *p) {
   p->levelset = levelset; p->rans = rans; p->inviscid = inviscid; p->skew = skew; p->movefsi = movefsi; p->rotatefsi = rotatefsi;
   p->i_periodic = i_periodic; p->j_periodic = j_periodic; p->k_periodic = k_periodic;
   p->i_homo_filter = i_homo_filter; p->j_homo_filter = j_homo_filter; p->k_homo_filter = k_homo_filter;
-  p->ren = user->ren; p->dt = user->dt; p->max_cs = max_cs;
+  p->ren = user->ren; p->dt = user->dt; p->max_cs = max_cs; p->roughness_size = roughness_size;
 }
 
 static GlueState *state(UserCtx *user) {
