@@ -186,31 +186,8 @@ struct Les1Body {
   }
 };
 
-// ---- LES pass 3 (les.c:716-796): staged LM, MM, aj, nvert; cells not next to a periodic plane ----------
-typedef Ring<VFS_TILE_TX, VFS_TILE_TY, 4, 4, 2, 2, 1, 1, 1, 1> RingLes3;
-struct Les3Acc {
-  TileAcc<RingLes3> T;
-  __device__ __forceinline__ double lm(int di, int dj, int dk) const { return T.get(0, di, dj, dk); }
-  __device__ __forceinline__ double mm(int di, int dj, int dk) const { return T.get(1, di, dj, dk); }
-  __device__ __forceinline__ double iaj(int di, int dj, int dk) const { return T.get(2, di, dj, dk); }
-  __device__ __forceinline__ double nv(int di, int dj, int dk) const { return T.get(3, di, dj, dk); }
-};
-VFS_HD bool les3_regular(const VfsDev &d, int i, int j, int kg) {
-  return !(d.perx && (i == 1 || i == d.mx - 2)) && !(d.pery && (j == 1 || j == d.my - 2)) && !(d.perz && (kg == 1 || kg == d.mz - 2));
-}
 struct NoPrefetch {};
 struct NoState {};
-struct Les3Body {
-  typedef NoState State;
-  __device__ __forceinline__ NoPrefetch prefetch(const VfsDev &, int, int, int) const { return NoPrefetch(); }
-  __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes3> &T, int i, int j, int k, const NoPrefetch &, NoState &, bool) const {
-    const int kg = k + d.kofs;
-    if (!les3_regular(d, i, j, kg)) return;          // done by the staged kernel on thin slabs
-    Les3Acc A = {T};
-    les3_core<true>(d, A, i, j, kg, d.idx(i, j, k));
-  }
-};
-
 // ---- face fluxes of Formfunction_2 (momentum.c:669-1451), regular faces ---------------------------------
 // One thread per node computes its i-, j- and k-face fluxes (Fc, Fv: 18 doubles) from ucat/nvert
 // planes k-1..k+2: box (TX+4) x (TY+3) with origin (i0-1, j0-1), i.e. node offsets -1..TX+2 in i
@@ -387,10 +364,6 @@ static inline SidList sids(int n, const int *v) { SidList s; s.n = n; for (int q
 static inline int launch_les1_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
   const int v[5] = {S_U0, S_U1, S_U2, S_IAJ, S_NV};
   return launch_tile_march<RingLes1>(st, tmap, d, k0, k1, 64, sids(5, v), Les1Body(), L);
-}
-static inline int launch_les3_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, long *L) {
-  const int v[4] = {S_LM, S_MM, S_IAJ, S_NV};
-  return launch_tile_march<RingLes3>(st, tmap, d, k0, k1, 64, sids(4, v), Les3Body(), L);
 }
 static inline int launch_flux_tma(cudaStream_t st, const CUtensorMap &tmap, const VfsDev &d, int k0, int k1, int minb, long *L) {
   const int v[4] = {S_U0, S_U1, S_U2, S_NV};
