@@ -1,0 +1,40 @@
+"""Randomised parity sweep on the CPU: kernel logic (host emulation, test-only) against the oracle over random
+boundary-type / flag combinations on small grids.  python tests/fuzz_parity_cpu.py [n] [seed]"""
+import os, sys, random
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import parity_common as pc, emu_loader, refdrv
+pkg = pc.load_package(); emu = emu_loader.load(pkg.capi)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+WALL_I = [1, 10, -1, -2, 100]
+WALL_JLO = [1, 10, 12, -1, -2]
+WALL_JHI = [1, 2, 4, 10, -10, 12, 13, 14, -1, -2]
+bad_cases = []
+for t in range(n):
+    base = pkg.cases.scaled(pkg.cases.CONFIGS[rng.choice(["c3_turbine", "c2_box256"])], rng.randint(9, 15), rng.randint(8, 13), rng.randint(9, 14))
+    per = [rng.random() < 0.4, rng.random() < 0.15, rng.random() < 0.4]
+    bc = [100] * 6
+    if not per[0]: bc[0], bc[1] = rng.choice(WALL_I), rng.choice(WALL_I)
+    if not per[1]: bc[2], bc[3] = rng.choice(WALL_JLO), rng.choice(WALL_JHI)
+    if not per[2]: bc[4], bc[5] = rng.choice([1, 5, 100]), rng.choice([1, 4, 100])
+    fl = dict(base["flags"], ii_periodic=int(per[0]), jj_periodic=int(per[1]), kk_periodic=int(per[2]),
+              second_order=rng.randint(0, 1), laplacian=rng.randint(0, 1), immersed=rng.choice([0, 1, 3]),
+              les=rng.choice([0, 1, 2, 2]), testfilter_ik=int(rng.random() < 0.15), roughness_size=1e-3,
+              rotor_model=rng.randint(0, 1))
+    if rng.random() < 0.2: fl.update(ti=5, tistart=5)
+    if bc[2] in (1,) and rng.random() < 0.3: fl["viscosity_wallmodel"] = 1
+    cfg = dict(base); cfg["flags"] = fl; cfg["bctype"] = bc
+    try:
+        err = pc.run_parity(cfg, refdrv, lib=emu)
+    except Exception as e:      # unsupported combination rejected by vfs_create, etc.
+        print(t, "SKIP", bc, {k: v for k, v in fl.items() if v}, str(e)[:80]); continue
+    zp = err.pop("FormFunction_SNES_zero_pattern"); nvm = err.pop("IB_BC_nvert_mismatches")
+    bad = {k: v for k, v in err.items() if not (v <= 1e-12)}
+    if bad or zp or nvm:
+        bad_cases.append((bc, fl, bad, zp, nvm))
+        print(t, "FAIL", bc, {k: v for k, v in fl.items() if v}, (cfg["IM"], cfg["JM"], cfg["KM"]), {k: "%.1e" % v for k, v in bad.items()}, zp, nvm, flush=True)
+    else:
+        print(t, "ok", bc, flush=True)
+print("failures:", len(bad_cases))

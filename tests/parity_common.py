@@ -24,8 +24,17 @@ def load_package():
 
 
 def relerr(a, b):
-    a = np.asarray(a)
-    b = np.asarray(b)
+    """max|a-b| / max|b| over the finite entries; non-finite entries (the reference itself divides by zero in
+    degenerate set-ups, e.g. the wall model at a zeroed corner cell) must coincide exactly, else inf."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    if not (fa.all() and fb.all()):
+        if not np.array_equal(fa, fb) or not np.array_equal(np.isnan(a), np.isnan(b)) or not np.array_equal(a[~fa & ~np.isnan(a)], b[~fb & ~np.isnan(b)]):
+            return float("inf")
+        a, b = a[fa], b[fb]
+        if a.size == 0:
+            return 0.0
     den = np.abs(b).max()
     if den == 0:
         return float(np.abs(a).max())

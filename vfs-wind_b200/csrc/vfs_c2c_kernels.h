@@ -55,9 +55,11 @@ VFS_HD V3 slip_ghost(const VfsDev &d, long pn, int col, double sgn) {
 // Wall-function boundary types (-1/-2) are rejected at vfs_create.
 struct C2CGhostRules {
   VfsDev d;
+  int jtop;      // -1: every boundary node; 0: all but the j = my-1 plane; 1: the j = my-1 plane only (see below)
   VFS_HD void operator()(int i, int j, int k) const {
     const int mx = d.mx, my = d.my, mz = d.mz, kg = d.kglob(k);
     if (!(i == 0 || i == mx - 1 || j == 0 || j == my - 1 || kg == 0 || kg == mz - 1)) return;
+    if (jtop >= 0 && (j == my - 1) != (jtop == 1)) return;
     long p = d.idx(i, j, k);
     const int *bc = d.bc;
     // neighbours of an edge/corner node are boundary nodes themselves: read them from the
@@ -66,8 +68,11 @@ struct C2CGhostRules {
     const int SU = nb >= 2 ? S_FP0 : S_U0;
     if ((int)(d.s[S_NV][p] + 0.1) == 3) { st3(d, S_U0, p, mk3(0, 0, 0)); return; }
     bool w = false; V3 u = mk3(0, 0, 0);
-    if (bc[3] == 13 && j == my - 1) { V3 a = ld3(d, SU, p - d.sj); u = mk3(a.x, -a.y, a.z); w = true; }
-    if (bc[3] == 14 && j == my - 1) { V3 a = ld3(d, SU, p - d.sj); u = mk3(a.x, a.y, -a.z); w = true; }
+    // the mirror rules 13 / 14 are the only ones that read the array being written (ucat[k][j-1][i], rhs.c:443-452),
+    // i.e. the j-1 node AFTER its own rules (solid / wall-function / ghost rules): the host runs the j = my-1 plane
+    // in a second pass, after the interior kernels, when one of them is active
+    if (bc[3] == 13 && j == my - 1) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(a.x, -a.y, a.z); w = true; }
+    if (bc[3] == 14 && j == my - 1) { V3 a = ld3(d, S_U0, p - d.sj); u = mk3(a.x, a.y, -a.z); w = true; }
     if (bc[0] == 10 && i == 0 && j != 0 && kg != 0) { u = slip_ghost(d, p + 1, 0, -1.); w = true; }
     if (bc[1] == 10 && i == mx - 1 && j != 0 && kg != 0) { u = slip_ghost(d, p - 1, 0, 1.); w = true; }
     if (bc[2] == 10 && j == 0 && i != 0 && kg != 0) { u = slip_ghost(d, p + d.sj, 1, -1.); w = true; }

@@ -757,7 +757,8 @@ static int contra2cart(vfs_ctx *c) {
   if (wallfn) {                                                      // wall-function first cells read interior neighbours of the snapshot too
     CopyScalar3 f = {d, S_U0, S_FP0}; Box b = {0, d.mx, 0, d.my, ka, kb}; RUN(launch(c, b, f));
   } else { CopyScalar3 f = {d, S_U0, S_FP0}; RUN(launch_shell(c, ka, kb, f, true)); }     // lUcat snapshot read by the rules
-  { C2CGhostRules f = {d}; RUN(launch_shell(c, ka, kb, f, true)); }                // rhs.c:302-682 (boundary nodes)
+  const bool mirror_top = d.bc[3] == 13 || d.bc[3] == 14;
+  { C2CGhostRules f = {d, mirror_top ? 0 : -1}; RUN(launch_shell(c, ka, kb, f, true)); }     // rhs.c:302-682 (boundary nodes)
   if (wallfn) {                                                      // rhs.c:311-440 (first interior cells of the -1 / -2 sides)
     RUN(ensure_wm_table(c));
     C2CWallFn f = {d, c->wm_table};
@@ -779,6 +780,7 @@ static int contra2cart(vfs_ctx *c) {
       for (int q = 0; q < 4; q++) if (cor[q]) { Box b = {ci[q], ci[q] + 1, cj[q], cj[q] + 1, bi.k0, bi.k1}; RUN(launch(c, b, f)); }
     }
   }
+  if (mirror_top) { C2CGhostRules f = {d, 1}; RUN(launch_shell(c, ka, kb, f, true)); }      // the j = my-1 plane, after its j-1 neighbours are final
   RUN(refresh3());                                                   // rhs.c:690-748
   return 0;
 }

@@ -449,12 +449,14 @@ template <bool REGULAR, class Acc> VFS_HD void les3_core(const VfsDev &d, const 
     LM_avg = lm / ws; MM_avg = mmv / ws;
   }
   const double C = 0.5 * LM_avg / (MM_avg + 1.e-4);
-  double cs = C > 0 ? C : 0;
+  // PetscMax(a,b) = (a<b)?b:a, PetscMin(a,b) = (a<b)?a:b, written out so that a NaN C (0/0 when every filter weight
+  // around the cell is zero) ends like the reference's: max_cs, or 0.001 at an IB node
+  double cs = (C < 0) ? 0 : C;                                   // les.c:795
   // clip chain of les.c:967-980 for interior nodes (boundary nodes are zeroed by LesClipBoundary)
   const double nvc = A.nv(0, 0, 0);
-  if (nvc > 0.1 && nvc < 1.1) cs = cs > 0.001 ? cs : 0.001;
-  cs = cs > 0 ? cs : 0;
-  cs = cs < d.max_cs ? cs : d.max_cs;
+  if (nvc > 0.1 && nvc < 1.1) cs = (0.001 < cs) ? cs : 0.001;
+  cs = (cs < 0) ? 0 : cs;
+  cs = (cs < d.max_cs) ? cs : d.max_cs;
   d.s[S_CS][p] = cs;
 }
 struct LesPass3 {

@@ -546,10 +546,10 @@ struct Les3March {
     const double lm = sA[NT + up] + 4. * st.v[1] + sA[NT + dn];
     const double mmv = sA[2 * NT + up] + 4. * st.v[2] + sA[2 * NT + dn];
     const double C = 0.5 * (lm / ws) / (mmv / ws + 1.e-4);
-    double cs = C > 0 ? C : 0;
-    if (st.nvc > 0.1 && st.nvc < 1.1) cs = cs > 0.001 ? cs : 0.001;      // clip chain, les.c:967-980
-    cs = cs > 0 ? cs : 0;
-    cs = cs < d.max_cs ? cs : d.max_cs;
+    double cs = (C < 0) ? 0 : C;                                           // comparisons as in les3_core (NaN-faithful)
+    if (st.nvc > 0.1 && st.nvc < 1.1) cs = (0.001 < cs) ? cs : 0.001;      // clip chain, les.c:967-980
+    cs = (cs < 0) ? 0 : cs;
+    cs = (cs < d.max_cs) ? cs : d.max_cs;
     d.s[S_CS][p] = cs;
   }
 };
