@@ -13,7 +13,11 @@ WALL_JLO = [1, 10, 12, -1, -2]
 WALL_JHI = [1, 2, 4, 10, -10, 12, 13, 14, -1, -2]
 bad_cases = []
 for t in range(n):
-    base = pkg.cases.scaled(pkg.cases.CONFIGS[rng.choice(["c3_turbine", "c2_box256"])], rng.randint(9, 15), rng.randint(8, 13), rng.randint(9, 14))
+    if os.environ.get("FUZZ_BIG"):     # several marching tiles wide and high (tile strides 30 x 10/14), several k-chunks
+        dims = (rng.randint(31, 45), rng.randint(13, 20), rng.randint(17, 22))
+    else:
+        dims = (rng.randint(9, 15), rng.randint(8, 13), rng.randint(9, 14))
+    base = pkg.cases.scaled(pkg.cases.CONFIGS[rng.choice(["c3_turbine", "c2_box256"])], *dims)
     per = [rng.random() < 0.4, rng.random() < 0.15, rng.random() < 0.4]
     bc = [100] * 6
     if not per[0]: bc[0], bc[1] = rng.choice(WALL_I), rng.choice(WALL_I)
