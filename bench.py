@@ -244,6 +244,7 @@ def run_ours(args):
     csh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
     nuh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
 
+    ctx.set_option(11, 1)      # asynchronous compute-only entry points: X's upload (own stream) overlaps the LES kernels
     def e2e_step():
         ctx.upload_ptr("UCONT", xh.data_ptr())        # host lUcont -> device (what the glue does for Contra2Cart)
         ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()

@@ -73,6 +73,7 @@ struct vfs_ctx {
   VfsDev d;
   double *pool = nullptr;        // all scalars, contiguous
   double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
+  double *stage_x = nullptr;     // staging of vfs_formfunction_snes' X, filled on the upload stream (allocated on first use)
   double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use
   long scalar_len = 0;
   cudaStream_t stream = 0;
@@ -99,9 +100,12 @@ struct vfs_ctx {
   double *hbuf = nullptr;        // packed send (hi, lo) and receive (lo, hi) staging, VFS_MAXGRP scalars each
   cudaStream_t copy_stream = 0;  // vfs_download_async
   cudaEvent_t ev_pack = 0;
+  cudaStream_t up_stream = 0;    // host->device copy of X in vfs_formfunction_snes (overlaps kernels still queued on `stream`)
+  cudaEvent_t ev_up = 0;
   cudaStream_t side = 0;         // halo exchanges that overlap interior compute run here (forked / joined by events)
   cudaEvent_t ev_fork = 0, ev_join = 0;
 #endif
+  int async_api = 0;             // compute-only entry points return without synchronising (option key 11)
   int overlap = 1;               // overlap the k-face-flux and Fp exchanges with the interior planes of FpCell / Project (option key 9)
   long halo_exchanges = 0, halo_bytes = 0;
   // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
@@ -474,6 +478,9 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
+  if (c->ev_up) cudaEventDestroy(c->ev_up);
+  if (c->stage_x) cudaFree(c->stage_x);
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   for (int q = 0; q < 2; q++) if (c->stage_async[q]) cudaFree(c->stage_async[q]);
   if (c->side) cudaStreamDestroy(c->side);
@@ -550,6 +557,10 @@ extern "C" int vfs_sync(vfs_ctx *c) {
 #endif
   return 0;
 }
+// end of a compute-only entry point: synchronous by default; with option 11 the call returns as soon as its work is
+// queued (errors then surface at the next synchronising call), so a following vfs_formfunction_snes can start
+// copying X while these kernels still run
+static int api_end(vfs_ctx *c) { return c->async_api ? 0 : vfs_sync(c); }
 extern "C" int vfs_layout(vfs_ctx *c, long *L) {
   if (!c || !L) return VFS_ERR_ARG;
   L[0] = VFS_G; L[1] = c->d.pitch; L[2] = c->d.ny; L[3] = c->d.nzt; L[4] = c->d.sk; L[5] = c->scalar_len; L[6] = S_COUNT; L[7] = 1; return 0;
@@ -584,6 +595,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 7) c->flux_var = value;
   else if (key == 8) c->fuse_refresh = value;
   else if (key == 9) c->overlap = value;
+  else if (key == 11) c->async_api = value;
   graph_reset(c);
   return 0;
 }
@@ -784,7 +796,7 @@ static int contra2cart(vfs_ctx *c) {
   RUN(refresh3());                                                   // rhs.c:690-748
   return 0;
 }
-extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return vfs_sync(c); }
+extern "C" int vfs_contra2cart(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(contra2cart(c)); return api_end(c); }
 
 // ---- IB_BC ---------------------------------------------------------------------------------------------
 static int ib_bc(vfs_ctx *c) {
@@ -828,7 +840,7 @@ static int ib_bc(vfs_ctx *c) {
   }
   return g2l(c, grp(S_UC0, 3));                                      // momentum.c:2231-2232
 }
-extern "C" int vfs_ib_bc(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(ib_bc(c)); return vfs_sync(c); }
+extern "C" int vfs_ib_bc(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(ib_bc(c)); return api_end(c); }
 
 // ---- Formfunction_2 ------------------------------------------------------------------------------------
 static Box box_clip(Box b, const Box &lim) {
@@ -1122,8 +1134,24 @@ extern "C" int vfs_formfunction_snes_dev(vfs_ctx *c) {
 extern "C" int vfs_formfunction_snes(vfs_ctx *c, const double *x, double *fout) {
   if (!c || !x || !fout) return VFS_ERR_ARG;
   ev_rec(c, 2 * VFS_T_TOTAL);
+#ifndef VFS_EMU
+  {   // X travels on its own stream into its own staging buffer: the copy does not queue behind kernels of earlier
+      // (asynchronous) calls; the main stream waits for it before unpacking
+    const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * 3 * sizeof(double);
+    if (!c->up_stream) {
+      CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    }
+    if (!c->stage_x) CK(cudaMalloc((void **)&c->stage_x, n));
+    CK(cudaMemcpyAsync(c->stage_x, x, n, cudaMemcpyHostToDevice, c->up_stream));
+    CK(cudaEventRecord(c->ev_up, c->up_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    UnpackX f = {c->d, c->stage_x}; RUN(launch(c, box_owned(c), f));
+  }
+#else
   RUN(h2d_stage(c, x, 3));
   { UnpackX f = {c->d, c->stage}; RUN(launch(c, box_owned(c), f)); }
+#endif
   RUN(snes_core(c));
   { PackAoS f = {c->d, c->stage, S_R0, 3}; RUN(launch(c, box_owned(c), f)); }
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
@@ -1224,8 +1252,8 @@ static int les_nut(vfs_ctx *c, bool with_cs = false) {
   if (any_per(c)) RUN(node_copy(c, g));
   return 0;
 }
-extern "C" int vfs_les_cs(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_cs(c)); return vfs_sync(c); }
-extern "C" int vfs_les_nut(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_nut(c)); return vfs_sync(c); }
+extern "C" int vfs_les_cs(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_cs(c)); return api_end(c); }
+extern "C" int vfs_les_nut(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(les_nut(c)); return api_end(c); }
 
 // one cell-update unit: Flow_Solver's LES block (solvers.c:365-371) followed by one
 // residual evaluation
