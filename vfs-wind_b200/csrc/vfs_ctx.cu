@@ -366,6 +366,27 @@ static int ovl_exchange(vfs_ctx *c, const Grp &g) {
   (void)c; (void)g; return VFS_ERR_UNSUPPORTED;
 #endif
 }
+// Thin-slab launches that are independent of a big kernel queued right before them run on the side stream,
+// concurrently with it (same event fork / join): side_begin() ... launches ... side_end(); the caller joins with
+// ovl_join() once the big kernel has been queued on the main stream.
+struct SideScope { cudaStream_t main_stream; };
+static int side_begin(vfs_ctx *c, SideScope *s) {
+#ifndef VFS_EMU
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  s->main_stream = c->stream; c->stream = c->side;
+#else
+  (void)c; (void)s;
+#endif
+  return 0;
+}
+static void side_end(vfs_ctx *c, const SideScope *s) {
+#ifndef VFS_EMU
+  c->stream = s->main_stream;
+#else
+  (void)c; (void)s;
+#endif
+}
 static int ovl_join(vfs_ctx *c) {
 #ifndef VFS_EMU
   CK(cudaEventRecord(c->ev_join, c->side));
@@ -447,6 +468,8 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   cudaMemset(c->pool, 0, bytes);
   cudaMemset(c->near, 1, (size_t)c->scalar_len);
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true;
+  cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) cudaEventCreate(&c->ev[q]);
 #else
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
@@ -539,11 +562,6 @@ extern "C" int vfs_nccl_init(vfs_ctx *c, const char *id128) {
   CK(cudaSetDevice(c->prm.device));
   ncclResult_t e = N.CommInitRank(&c->comm, c->prm.nranks, id, c->prm.rank);
   if (e != ncclSuccess) { c->comm = nullptr; set_err(c, std::string("ncclCommInitRank: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
-  if (!c->side) {
-    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  }
   return 0;
 #else
   (void)c; (void)id128; return VFS_ERR_UNSUPPORTED;
@@ -959,13 +977,17 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
 #ifndef VFS_EMU
   if (!march && c->fused && c->tma_ok) {
     // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
-    if (c->flux_var == 1 ? launch_flux_march(c->stream, c->tmap_fluxA, c->tmap_fluxB, d, k1, k2, &c->launches)
-                         : launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, c->flux_minb, &c->launches)) { set_err(c, "flux kernel launch failed"); return VFS_ERR_CUDA; }
+    // the six thin slabs write faces the marching kernel does not: they run beside it on the side stream
+    SideScope sc; RUN(side_begin(c, &sc));
     { FaceFlux<0> f = {d}; Box b0 = {0, 1, 1, d.my - 1, k1, k2}, b1 = {d.mx - 2, d.mx - 1, 1, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     { FaceFlux<1> f = {d}; Box b0 = {1, d.mx - 1, 0, 1, k1, k2}, b1 = {1, d.mx - 1, d.my - 2, d.my - 1, k1, k2}; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     { FaceFlux<2> f = {d};
       Box b0 = {1, d.mx - 1, 1, d.my - 1, klo(c, 0), klo(c, 1)}, b1 = {1, d.mx - 1, 1, d.my - 1, klo(c, d.mz - 2), klo(c, d.mz - 1)};
       RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    side_end(c, &sc);
+    if (c->flux_var == 1 ? launch_flux_march(c->stream, c->tmap_fluxA, c->tmap_fluxB, d, k1, k2, &c->launches)
+                         : launch_flux_tma(c->stream, c->tmap_flux, d, k1, k2, c->flux_minb, &c->launches)) { set_err(c, "flux kernel launch failed"); return VFS_ERR_CUDA; }
+    RUN(ovl_join(c));
   } else
 #endif
   for (int n = 0; n < S.n; n++) {
@@ -1222,8 +1244,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   ev_rec(c, 2 * VFS_T_LES3);
   if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
-    Les3March prog = {d};
-    if (run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
+    SideScope sc; RUN(side_begin(c, &sc));       // the thin slabs next to periodic planes run beside the marching kernel
     LesPass3 f = {d};      // cells next to a periodic plane (ghost-image fetches): thin slabs
     if (d.perx) { Box b0 = bi, b1 = bi; b0.i1 = 2; b1.i0 = d.mx - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
     if (d.pery) { Box b0 = bi, b1 = bi; b0.j1 = 2; b1.j0 = d.my - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
@@ -1231,6 +1252,10 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
       Box b0 = bi, b1 = bi; b0.k0 = klo(c, 1); b0.k1 = klo(c, 2); b1.k0 = klo(c, d.mz - 2); b1.k1 = klo(c, d.mz - 1);
       RUN(launch(c, b0, f)); RUN(launch(c, b1, f));
     }
+    side_end(c, &sc);
+    Les3March prog = {d};
+    if (run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
+    RUN(ovl_join(c));
   } else
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
