@@ -1,11 +1,12 @@
 """Randomised parity sweep on the CPU: kernel logic (host emulation, test-only) against the oracle over random
-boundary-type / flag combinations on small grids.  python tests/fuzz_parity_cpu.py [n] [seed]"""
+boundary-type / flag combinations on small grids.  python tests/fuzz_parity_cpu.py [n] [seed]
+FUZZ_GPU=1: the same sweep through the CUDA library on cuda:0 instead of the emulation (FUZZ_BIG=1: multi-tile sizes)."""
 import os, sys, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import parity_common as pc, emu_loader, refdrv
-pkg = pc.load_package(); emu = emu_loader.load(pkg.capi)
+pkg = pc.load_package(); emu = None if os.environ.get("FUZZ_GPU") else emu_loader.load(pkg.capi)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 WALL_I = [1, 10, -1, -2, 100]
