@@ -40,6 +40,8 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     ref.Contra2Cart(); glue.Contra2Cart()
     err["Contra2Cart_Ucat"] = pc.relerr(glue.owned("Ucat"), ref.owned("Ucat"))
     err["Contra2Cart_lUcat_ghosts"] = pc.relerr(glue.view("lUcat"), ref.view("lUcat"))
+    if any(b in (-1, -2) for b in cfg["bctype"][:4]):
+        err["Contra2Cart_lUstar"] = pc.relerr(np.array(glue.owned("lUstar"))[1:-1, 1:-1, 1:-1], np.array(ref.owned("lUstar"))[1:-1, 1:-1, 1:-1])
     ref.Compute_Smagorinsky_Constant_1(); glue.Compute_Smagorinsky_Constant_1()
     err["lCs"] = pc.relerr(glue.owned("lCs"), ref.owned("lCs"))
     ref.Compute_eddy_viscosity_LES(); glue.Compute_eddy_viscosity_LES()
@@ -61,6 +63,8 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     kk, jj, ii = np.meshgrid(np.arange(mz_), np.arange(my_), np.arange(mx_), indexing="ij")
     nb = ((kk == 0) | (kk == mz_ - 1)).astype(int) + ((jj == 0) | (jj == my_ - 1)) + ((ii == 0) | (ii == mx_ - 1))
     err["IB_BC_lUcont"] = pc.relerr(a[nb < 2], b[nb < 2])
+    err["IB_BC_Nvert_mismatches"] = float(np.count_nonzero(np.array(glue.owned("Nvert")) != np.array(ref.owned("Nvert")))
+                                          + np.count_nonzero(np.array(glue.owned("lNvert")) != np.array(ref.owned("lNvert"))))
     for d in (ref, glue):
         d.view("RHS_o")[...] = 0
         d.Formfunction_2("RHS_o", 1.0)
@@ -76,11 +80,16 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     return err
 
 
-@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17))])
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("wallfn", (13, 11, 15))])
 def test_glue_dropin_emulated(pkg, refdrv, name, dims):
     import emu_loader
     emu_loader.build()
-    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    if name == "wallfn":       # wall-function sides, first time step: IB_BC rewrites lNvert / Nvert on the host too
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c2_box256"], *dims)
+        cfg["flags"] = dict(cfg["flags"], ti=5, tistart=5, roughness_size=2.e-4)
+        cfg["bctype"] = [100, 100, -1, -2, 100, 100]
+    else:
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     err = run_dropin(refdrv, pkg, "libvfsglue_emu.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad

@@ -169,6 +169,7 @@ void Contra2Cart_2(UserCtx *user) {
   if (ii_periodic || jj_periodic || kk_periodic) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156 rewrites lUcont's periodic nodes
   pull(user, s, VFS_UCAT, 3, user->Ucat, false);
   DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
+  for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }   // rhs.c:336,371,401,435
 }
 void Contra2Cart(UserCtx *user) { Contra2Cart_2(user); }
 
@@ -178,6 +179,14 @@ void IB_BC(UserCtx *user) {
   push(user, s, user->lUcont, 3, VFS_UCONT); push(user, s, user->lUcat, 3, VFS_UCAT);
   ck(s, vfs_ib_bc(s->ctx), "vfs_ib_bc");
   pull(user, s, VFS_UCONT, 3, user->lUcont, true);
+  // first time step without immersed bodies: IB_BC marks the first cells of wall-function sides nvert = 1
+  // (momentum.c:2048-2074) in lNvert and Nvert
+  bool wallfn = false;
+  for (int q = 0; q < 6; q++) wallfn = wallfn || user->bctype[q] == -1 || user->bctype[q] == -2;
+  if (wallfn && !immersed && ti == tistart) {
+    pull(user, s, VFS_NVERT, 1, user->lNvert, true);
+    DALocalToGlobal(user->da, user->lNvert, INSERT_VALUES, user->Nvert);
+  }
 }
 
 void Compute_Smagorinsky_Constant_1(UserCtx *user, Vec Ucont, Vec Ucat) {
@@ -222,6 +231,7 @@ PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
   push(user, s, Rhs, 3, VFS_RHS);
   ck(s, vfs_formfunction2(s->ctx, VFS_RHS, scale), "vfs_formfunction2");
   pull(user, s, VFS_RHS, 3, Rhs, false);
+  if (viscosity_wallmodel && les) pull(user, s, VFS_USTAR, 1, user->lUstar, false);      // momentum.c:1150
   return 0;
 }
 
@@ -243,4 +253,5 @@ extern "C" void vfs_glue_sync_state(UserCtx *user) {
   pull(user, s, VFS_UCONT, 3, user->lUcont, true);
   pull(user, s, VFS_UCAT, 3, user->Ucat, false);
   DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
+  for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }   // rhs.c:336,371,401,435
 }
