@@ -4,9 +4,15 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 One "step" = one cell-update pass over the whole grid: Contra2Cart + dynamic
-Smagorinsky Cs + eddy viscosity + one FormFunction_SNES residual.  N=1 workload: config[1] of
-BASELINE.json (synthetic stretched curvilinear box 256^3, dynamic Smagorinsky).  N>1: weak scaling,
-every rank owns a 256x256 x (256 planes) k-slab of a 256 x 256 x 256N grid, k-halos over NCCL.
+Smagorinsky Cs + eddy viscosity + one FormFunction_SNES residual.
+
+Workloads (BASELINE.json `configs`):
+  c2_box256   synthetic stretched curvilinear box 256^3, dynamic Smagorinsky — the N = 1 default (configs[1])
+  c5_weak     the weak-scaling grid 2048 x 1024 x 512: every GPU owns a 2048 x 1024 x 64 k-slab, k grows with N
+              (N = 8 is configs[4] exactly) — the N > 1 default
+  c3_turbine  512 x 256 x 256 turbine grid with IBM masks and F_eul (configs[2]), one GPU
+  c4_farm     1024 x 512 x 256 wind farm, STRONG scaling over N k-slabs (configs[3])
+  c2_weak     256 x 256 x 256N (the round-1 weak-scaling shape)
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -22,35 +28,71 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
-# algorithmic (compulsory) HBM bytes per cell; derivation in DESIGN.md section 5
-BYTES_STEP = 248.0          # fused RHS+LES unit, SURVEY 8(d): 23 doubles read + 8 written
-BYTES_STEP_FEUL = 272.0
-KERNEL_BYTES = {            # per-kernel-group compulsory traffic (doubles read + written per cell) * 8
-    "flux": 36 * 8.0,       # r: ucat3 nvert1 ucont3 metrics9 1/aj nu_t1, w: Fc9 Fv9
-    "fp": 22 * 8.0,         # r: Fc9 Fv9 nvert1, w: Fp3
-    "project": 29 * 8.0,    # r: Fp3 metrics9 1/aj nvert1 ucont3 ucont_o3 rhs_o3 dp3, w: rhs3
+# algorithmic (compulsory) HBM bytes per cell-update; derivation in DESIGN.md section 5
+BYTES_STEP = 248.0          # fused RHS+LES unit: 23 doubles read + 8 written
+BYTES_STEP_FEUL = 272.0     # + F_eul (3 doubles)
+# KERNEL-PRIVATE bytes per cell (doubles read + written by that kernel group, intermediates included) — only used for
+# the per-kernel entries of `kernels`, never for `roofline`
+KERNEL_PRIVATE_BYTES = {
     "c2c": 17 * 8.0,        # r: ucont3 metrics9 aj nvert1, w: ucat3
+    "flux": 36 * 8.0,       # r: ucat3 nvert1 ucont3 metrics9 1/aj nu_t1, w: Fc9 Fv9
+    "fp": 22 * 8.0,         # r: Fc9 Fv9 nvert1, w: Fp3   (0 when Fp is folded into the projection)
+    "project": 29 * 8.0,    # r: Fp3 metrics9 1/aj nvert1 ucont3 ucont_o3 rhs_o3 dp3, w: rhs3
     "les1": 29 * 8.0,       # r: ucat3 metrics9 aj 1/aj nvert1, w: |S|1 ucat_f3 w1 U3 |S|S_ij6
     "les2": 41 * 8.0,       # r: ucat3 w1 U3 |S|S_ij6 metrics9 aj gridfactors12 ucat_f3 nvert1, w: LM MM
     "les3": 5 * 8.0,        # r: LM MM 1/aj nvert, w: Cs
     "nut": 5 * 8.0,         # r: Cs |S| aj nvert, w: nu_t
 }
-# kernel that dominates each timer group (names as they appear in the ncu launch list / profiles/)
-KERNEL_NAME = {"flux": "k_tile_march<RingFlux, FluxBody>", "fp": "k_box<FpCell>", "project": "k_box<ProjectSNES>", "c2c": "k_box<C2CInterior>",
-               "les1": "k_tile_march<RingLes1, Les1Body>", "les2": "k_les2_march<Les2MarchT<12>>", "les3": "k_filter_march<Les3March, 2>", "nut": "k_box<NuT>"}
 TIMER = {"total": 0, "c2c": 1, "flux": 2, "fp": 3, "project": 4, "les1": 5, "les2": 6, "les3": 7, "nut": 8}
+METRIC = "RHS+LES cell-updates/s (FP64)"
 
 
-def measured_traffic(kernel_group, workload):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the group's dominant kernel, from the
-    committed `ncu --set full` capture summarised in profiles/traffic.json (same workload, one launch)."""
+# ---- workloads ---------------------------------------------------------------------------------------------
+def resolve_workload(name, world):
+    if name in (None, "auto"):
+        return "c2_box256" if world == 1 else "c5_weak"
+    return name
+
+
+def workload_cfg(cases, name, nranks):
+    """Global grid of the run and how it scales with the number of ranks."""
+    if name == "c5_weak":                    # 64 node planes per GPU; 8 GPUs = the 2048 x 1024 x 512 grid of configs[4]
+        cfg = dict(cases.CONFIGS["c5_weak"])
+        cfg["KM"] = 64 * nranks - 1
+        cfg["weak_k"] = True
+        return cfg, "weak"
+    if name == "c2_weak":
+        cfg = dict(cases.CONFIGS["c2_box256"])
+        cfg["KM"] = 256 * nranks - 1
+        cfg["weak_k"] = True
+        return cfg, "weak"
+    cfg = dict(cases.CONFIGS[name])
+    return cfg, ("strong" if nranks > 1 else "weak")
+
+
+def describe(cfg, name, world, scaling):
+    """The `config` object: identical in the `ours` and `reference` arms."""
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    fl = cfg["flags"]
+    what = {"c2_box256": "synthetic stretched curvilinear box", "c2_weak": "synthetic stretched curvilinear box, weak scaling in k",
+            "c5_weak": "weak-scaling curvilinear grid, 2048x1024x64 node k-slab per GPU (8 GPUs = 2048x1024x512)",
+            "c3_turbine": "Test_09-style turbine grid with IBM nvert masks and actuator forcing F_eul",
+            "c4_farm": "wind-farm ABL LES grid with turbine rows (IBM masks, F_eul), k-slab sharded"}.get(name, name)
+    return {"workload": "%s: %s, %dx%dx%d nodes, dynamic Smagorinsky (les=%d), %s central%s%s" % (
+                name, what, mx, my, mz, fl.get("les", 0), "2nd-order" if fl.get("second_order") else "4th-order",
+                ", ii periodic" if fl.get("ii_periodic") else "", ", kk periodic" if fl.get("kk_periodic") else ""),
+            "nodes": [mx, my, mz], "cells": (mx - 2) * (my - 2) * (mz - 2), "n_slabs": world, "scaling": scaling,
+            "l2": "inputs larger than L2: every step streams the whole FP64 state (>= 0.3 GB per scalar field per GPU)"}
+
+
+def measured_traffic(workload):
+    """profiles/traffic.json: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of every kernel
+    group and their per-step sum, from the committed `ncu --set full` capture of the same workload."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p))
-    if t.get("workload") != workload:
-        return None
-    return t.get("dram_bytes_per_launch", {}).get(kernel_group)
+    return t if t.get("workload") == workload else None
 
 
 def peaks():
@@ -101,17 +143,28 @@ class ClockSampler:
         return out
 
 
-def workload_cfg(cases, name, nranks):
-    cfg = dict(cases.CONFIGS[name])
-    if nranks > 1:                       # weak scaling: fixed 256-plane slab per GPU
-        cfg["KM"] = (cfg["KM"] + 1) * nranks - 1
-        cfg["weak_k"] = True          # keep the cell size: domain length in z grows with N
-    return cfg
+def pin_to_gpu_numa(dev):
+    """Bind this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the GPU's
+    NUMA node, so that at N = 8 the ranks' host<->device copies do not all cross one socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
-def build_case_on_device(pkg, cfg, rank, nranks, device, halo=None):
+def build_case_on_device(pkg, cfg, rank, nranks, device, halo=None, on_device=None):
     """Create the context for this rank's k-slab and fill it with the seeded synthetic state.
-    Inputs are generated per slab (seed + rank) so no host ever holds the multi-GPU grid."""
+    Inputs are generated per slab (seed + rank) so no host ever holds the multi-GPU grid; large slabs are
+    generated on the GPU itself (cases_device.py: torch, same recipe) and handed over as device pointers."""
     capi, cases = pkg.capi, pkg.cases
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
     kofs, nzl = capi.slab_partition(mz, nranks)[rank]
@@ -123,20 +176,25 @@ def build_case_on_device(pkg, cfg, rank, nranks, device, halo=None):
         ctx.nccl_init(dist, device=torch.device("cuda", device))
     elif halo is not None:
         halo.attach(ctx)
-    # grid: the slab's node planes of the global grid (coordinates depend on global indices only)
-    sub = dict(cfg)
-    xyz = cases.make_grid(cfg) if nranks == 1 else cases.make_grid_slab(cfg, kofs, nzl)
-    ctx.upload("COOR", xyz)
-    ctx.FormMetrics()
-    met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
-    sub["KM"] = nzl - 1
-    sub["seed"] = cfg["seed"] + rank
-    f = cases.make_fields(sub, met)
-    if nranks > 1:
-        f["nvert"][...] = 0.0 if not cfg.get("masks") else f["nvert"]
-    for k, n in (("nvert", "NVERT"), ("ucont", "UCONT"), ("ucat", "UCAT"), ("ucat_old", "UCAT_OLD"), ("ucont_o", "UCONT_O"),
-                 ("ucont_rm1", "UCONT_RM1"), ("rhs_o", "RHS_O"), ("dp", "DP"), ("f_eul", "F_EUL")):
-        ctx.upload(n, f[k])
+    if on_device is None:
+        on_device = nzl * my * mx > 40e6
+    if on_device:
+        f = pkg.cases_device.fill_context(ctx, cfg, kofs, nzl, rank, device)
+    else:
+        # grid: the slab's node planes of the global grid (coordinates depend on global indices only)
+        sub = dict(cfg)
+        xyz = cases.make_grid(cfg) if nranks == 1 else cases.make_grid_slab(cfg, kofs, nzl)
+        ctx.upload("COOR", xyz)
+        ctx.FormMetrics()
+        met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+        sub["KM"] = nzl - 1
+        sub["seed"] = cfg["seed"] + rank
+        if nranks > 1 and cfg.get("masks"):      # bodies placed in GLOBAL coordinates, cropped to the slab
+            sub["mask_window"] = (kofs, mz)
+        f = cases.make_fields(sub, met)
+        for k, n in (("nvert", "NVERT"), ("ucont", "UCONT"), ("ucat", "UCAT"), ("ucat_old", "UCAT_OLD"), ("ucont_o", "UCONT_O"),
+                     ("ucont_rm1", "UCONT_RM1"), ("rhs_o", "RHS_O"), ("dp", "DP"), ("f_eul", "F_EUL")):
+            ctx.upload(n, f[k])
     return ctx, f, (mx, my, mz, kofs, nzl)
 
 
@@ -147,26 +205,15 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(lrank)
+    ncpu_pinned = pin_to_gpu_numa(lrank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     # a non-default stream: CUDA graphs cannot be captured on the legacy default stream
     torch.cuda.set_stream(torch.cuda.Stream())
     pkg = load_package()
     pkg.capi.load()
-    cfg = workload_cfg(pkg.cases, args.workload, world)
-    halo = None
-    if world > 1:       # in-library NCCL k-halo layer (VFS_HALO=torch: the torch.distributed callback instead)
-        halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank)) \
-            if os.environ.get("VFS_HALO") == "torch" else "nccl"
-    ctx, f, (mx, my, mz, kofs, nzl) = build_case_on_device(pkg, cfg, rank, world, lrank, halo)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
-    for key, env in ((0, "VFS_FUSED"), (2, "VFS_LES2_TY"), (3, "VFS_FLUX_MINB"), (4, "VFS_LES1_VAR"), (5, "VFS_LES3_VAR"), (6, "VFS_FASTPATH"), (7, "VFS_FLUX_VAR"), (8, "VFS_FUSE_REFRESH"), (9, "VFS_OVERLAP")):            # tuning knobs (see vfs_set_option)
-        if os.environ.get(env):
-            ctx.set_option(key, int(os.environ[env]))
-    cells_total = (mx - 2) * (my - 2) * (mz - 2)
-    k_int = [k for k in range(kofs, kofs + nzl) if 1 <= k <= mz - 2]
-    cells_rank = (mx - 2) * (my - 2) * len(k_int)
+    wname = resolve_workload(args.workload, world)
+    cfg, scaling = workload_cfg(pkg.cases, wname, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -174,14 +221,53 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def rmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- N > 1: the N-rank result must be bitwise the 1-rank result before anything is timed ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        def make_halo(c, cf):
+            c.nccl_init(dist, device=torch.device("cuda", lrank))
+        ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo)
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity = "pass" if t.item() == 1.0 else "fail"
+        if parity == "fail":
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "multi_gpu_parity": "fail", "value": None,
+                                  "error": "N-rank result differs from the 1-rank result (vfs-wind_b200/selfcheck.py); nothing was timed"}))
+            dist.destroy_process_group()
+            sys.exit(1)
+
+    halo = None
+    if world > 1:       # in-library NCCL k-halo layer (VFS_HALO=torch: the torch.distributed callback instead)
+        halo = pkg.halo.TorchHalo(rank, world, periodic_k=bool(cfg["flags"].get("kk_periodic")), device=torch.device("cuda", lrank)) \
+            if os.environ.get("VFS_HALO") == "torch" else "nccl"
+    ctx, f, (mx, my, mz, kofs, nzl) = build_case_on_device(pkg, cfg, rank, world, lrank, halo)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    for key, env in ((0, "VFS_FUSED"), (2, "VFS_LES2_TY"), (3, "VFS_FLUX_MINB"), (4, "VFS_LES1_VAR"), (5, "VFS_LES3_VAR"), (6, "VFS_FASTPATH"), (7, "VFS_FLUX_VAR"),
+                     (8, "VFS_FUSE_REFRESH"), (9, "VFS_OVERLAP"), (12, "VFS_FP_FUSED"), (13, "VFS_LES12"), (14, "VFS_HALO_TRIM")):            # tuning knobs (see vfs_set_option)
+        if os.environ.get(env):
+            ctx.set_option(key, int(os.environ[env]))
+    cells_total = (mx - 2) * (my - 2) * (mz - 2)
+    k_int = [k for k in range(kofs, kofs + nzl) if 1 <= k <= mz - 2]
+    cells_rank = (mx - 2) * (my - 2) * len(k_int)
+
     # ---- device-resident metric ("value") ----
-    # the ~100-launch step is replayed as a CUDA graph (1st warm-up step eager, 2nd captured); the
-    # in-library NCCL halo exchanges are captured with it
+    # the step is replayed as a CUDA graph (1st warm-up step eager, 2nd captured); the in-library NCCL halo
+    # exchanges are captured with it
     use_graph = (world == 1 or halo == "nccl") and not args.no_graph
     ctx.set_option(1, 1 if use_graph else 0)
     for _ in range(max(args.warmup, 3)):
         ctx.rhs_les_fused()
     barrier()
+    h0 = ctx.halo_count()
     sampler = ClockSampler(lrank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -191,8 +277,10 @@ def run_ours(args):
         ctx.rhs_les_fused()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = rmax(e0.elapsed_time(e1))
     clocks = sampler.stop()
+    h1 = ctx.halo_count()
+
     # the two halves of the unit on their own (the Krylov solver calls the residual 10-50x per LES update)
     def timed(fn, n):
         fn(); barrier()
@@ -201,12 +289,7 @@ def run_ours(args):
         for _ in range(n):
             fn()
         b.record(stream); barrier()
-        t = a.elapsed_time(b) / n
-        if world > 1:
-            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t = float(tt.item())
-        return t
+        return rmax(a.elapsed_time(b) / n)
     ms_rhs = timed(ctx.FormFunction_SNES_dev, args.steps)
 
     def les_only():
@@ -222,88 +305,112 @@ def run_ours(args):
         ctx.rhs_les_fused()
         for k, t in TIMER.items():
             tsum[k] += ctx.last_ms(t)
-    launches = (ctx.launch_count() - l0) // nt * args.steps
+    launches_step = (ctx.launch_count() - l0) // nt
+    launches = launches_step * args.steps
     barrier()
     if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         lt = torch.tensor([launches], device="cuda", dtype=torch.float64)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     ms_step = ms / args.steps
     value = cells_total / (ms_step * 1e-3)
 
+    # ---- device-resident Newton-Krylov solve: the residual is evaluated where the Krylov vectors live ----
+    solver = None
+    if hasattr(ctx, "momentum_solve") and not args.no_solver:
+        try:
+            solver = bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, (nzl, my, mx), args)
+        except Exception as e:      # noqa
+            solver = {"error": str(e)[:200]}
+
     # ---- end-to-end through the C ABI with host buffers ("e2e") ----
-    xh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
-    fh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
-    xh.copy_(torch.from_numpy(f["ucont"]))
-    xn, fn = xh.numpy(), fh.numpy()
-    nut_bytes = 2 * nzl * my * mx * 8
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
+        fh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
+        if isinstance(f.get("ucont"), np.ndarray):
+            xh.copy_(torch.from_numpy(f["ucont"]))
+        else:
+            ctx.download_ptr("UCONT", xh.data_ptr())
+        csh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
+        nuh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
+        nut_bytes = 2 * nzl * my * mx * 8
+        ctx.set_option(11, 1)      # asynchronous compute-only entry points: X's upload (own stream) overlaps the LES kernels
 
-    csh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
-    nuh = torch.empty((nzl, my, mx), dtype=torch.float64).pin_memory()
+        def e2e_step():
+            ctx.upload_ptr("UCONT", xh.data_ptr())        # host lUcont -> device (what the glue does for Contra2Cart)
+            ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+            # LES results back to the host Vecs: asynchronous copies on the library's copy stream, so this device->host
+            # traffic overlaps the host->device copy of X below (PCIe is full duplex); waited for before the step ends
+            ctx.download_async("CS", csh.data_ptr(), 0); ctx.download_async("NU_T", nuh.data_ptr(), 1)
+            ctx.FormFunction_SNES(xh.data_ptr(), fh.data_ptr())   # X (host) -> F (host)
+            ctx.download_wait()
+            return float(fh[nzl // 2, my // 2, mx // 2, 2]) + float(nuh[nzl // 2, my // 2, mx // 2])      # read the step's results on the host
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        n_e2e = max(1, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = rmax(max(wall, e0.elapsed_time(e1)))           # host-synchronous copies: wall clock is the honest one
+        ctx.set_option(11, 0)
+        e2e = {"value": cells_total / (ms_e2e / n_e2e * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": 2 * nzl * my * mx * 3 * 8,
+               "d2h_bytes_per_step": nzl * my * mx * 3 * 8 + nut_bytes, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
+               "what": "per step: lUcont up, Contra2Cart + Cs + nu_t, Cs and nu_t down, FormFunction_SNES(X host) -> F host; pinned buffers",
+               "cpus_bound_to_gpu_numa_node": ncpu_pinned}
 
-    ctx.set_option(11, 1)      # asynchronous compute-only entry points: X's upload (own stream) overlaps the LES kernels
-    def e2e_step():
-        ctx.upload_ptr("UCONT", xh.data_ptr())        # host lUcont -> device (what the glue does for Contra2Cart)
-        ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
-        # LES results back to the host Vecs: asynchronous copies on the library's copy stream, so this device->host
-        # traffic overlaps the host->device copy of X below (PCIe is full duplex); waited for before the step ends
-        ctx.download_async("CS", csh.data_ptr(), 0); ctx.download_async("NU_T", nuh.data_ptr(), 1)
-        ctx.FormFunction_SNES(xh.data_ptr(), fh.data_ptr())   # X (host) -> F (host)
-        ctx.download_wait()
-        return float(fh[nzl // 2, my // 2, mx // 2, 2]) + float(nuh[nzl // 2, my // 2, mx // 2])      # read the step's results on the host
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    n_e2e = max(1, min(args.steps, 5))
-    for _ in range(n_e2e):
-        e2e_step()
-    e1.record(stream)
-    barrier()
-    wall = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(wall, e0.elapsed_time(e1))           # host-synchronous copies: wall clock is the honest one
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = cells_total / (ms_e2e / n_e2e * 1e-3)
-    h2d = 2 * nzl * my * mx * 3 * 8
-    d2h = nzl * my * mx * 3 * 8 + nut_bytes
-
-    # ---- roofline of the dominant kernel group (rank 0's timers) ----
+    # ---- roofline of the whole step at the SURVEY 8(d) bytes (rank 0's share of the cells) ----
     peak, peak_src = peaks()
     per = {k: tsum[k] / nt for k in TIMER}
-    dom = max((k for k in TIMER if k != "total"), key=lambda k: per[k])
-    ach = KERNEL_BYTES[dom] * cells_rank / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
     bytes_step = BYTES_STEP_FEUL if cfg.get("forcing") else BYTES_STEP
-    ach_step = bytes_step * value / world / 1e9
-    roof = {"bound": "hbm", "kernel": dom, "kernel_name": KERNEL_NAME[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": measured_traffic(dom, args.workload) if world == 1 else None,
-            "peak_source": peak_src, "algorithmic_bytes_per_cell": KERNEL_BYTES[dom], "ms_per_launch_group": per[dom]}
-    roof_step = {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak, "algorithmic_bytes_per_cell": bytes_step,
-                 "note": "whole fused RHS+LES step at SURVEY 8(d) bytes, per GPU"}
+    ach_step = bytes_step * cells_rank / (ms_step * 1e-3) / 1e9
+    tr = measured_traffic(wname) if world == 1 else None
+    step_traffic = tr.get("dram_bytes_per_step") if tr else None
+    roof = {"bound": "hbm", "kernel": "whole RHS+LES step (%d launches replayed as one CUDA graph)" % launches_step, "achieved": ach_step, "peak": peak, "unit": "GB/s",
+            "frac": ach_step / peak, "traffic": step_traffic, "peak_source": peak_src, "algorithmic_bytes_per_cell": bytes_step, "cells_per_launch": cells_rank,
+            "wasted_traffic_ratio": (step_traffic / (bytes_step * cells_rank)) if step_traffic else None,
+            "formula": "algorithmic_bytes_per_cell * cells_per_launch / ms_per_step / peak (SURVEY 8d)"}
+    kernels = {}
+    for k in TIMER:
+        if k == "total" or per[k] <= 0:
+            continue
+        kernels[k] = {"ms": per[k], "kernel_private_bytes_per_cell": KERNEL_PRIVATE_BYTES[k],
+                      "kernel_private_GBps": KERNEL_PRIVATE_BYTES[k] * cells_rank / (per[k] * 1e-3) / 1e9,
+                      "dram_bytes_measured": (tr or {}).get("dram_bytes_per_launch", {}).get(k)}
+    kernels["note"] = "kernel-private bytes count each kernel's own reads and writes (intermediates included); they are NOT the roofline figure"
 
-    line = {"metric": "RHS+LES cell-updates/s (FP64)", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: synthetic stretched curvilinear box %dx%dx%d nodes, dynamic Smagorinsky (les=2), 4th-order central, ii+kk periodic" % (args.workload, mx, my, mz),
-                       "cells": cells_total, "k_slab_per_gpu": nzl, "l2": "inputs larger than L2 (%.1f GB resident state per GPU; every kernel streams >= 0.5 GB)" % (ctx.scalar_len * 8 * ctx.nscalars / 1e9),
-                       "dynamic_freq": 1, "cuda_graph": bool(use_graph)},
+    config = describe(cfg, wname, world, scaling)
+    line = {"metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "run": {"k_slab_per_gpu": nzl, "resident_GB_per_gpu": ctx.scalar_len * 8 * ctx.nscalars / 1e9, "cuda_graph": bool(use_graph), "dynamic_freq": 1,
+                    "inputs": "generated on the device (torch)" if not isinstance(f.get("ucont"), np.ndarray) else "generated on the host (numpy), uploaded"},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
-            "roofline": roof, "roofline_step": roof_step,
+            "roofline": roof, "kernels": kernels,
             "rhs_only": {"value": cells_total / (ms_rhs * 1e-3), "unit": "cell-updates/s", "ms": ms_rhs, "algorithmic_bytes_per_cell": 240.0,
-                         "roofline_frac": 240.0 * cells_total / world / (ms_rhs * 1e-3) / 1e9 / peak, "what": "one FormFunction_SNES residual (X device resident)"},
+                         "roofline_frac": 240.0 * cells_rank / (ms_rhs * 1e-3) / 1e9 / peak, "what": "one FormFunction_SNES residual (X device resident)"},
             "les_only": {"value": cells_total / (ms_les * 1e-3), "unit": "cell-updates/s", "ms": ms_les, "algorithmic_bytes_per_cell": 128.0,
-                         "roofline_frac": 128.0 * cells_total / world / (ms_les * 1e-3) / 1e9 / peak, "what": "Contra2Cart + dynamic Cs + nu_t"},
+                         "roofline_frac": 128.0 * cells_rank / (ms_les * 1e-3) / 1e9 / peak, "what": "Contra2Cart + dynamic Cs + nu_t"},
             "halo": {"layer": "in-library NCCL send/recv" if halo == "nccl" else ("torch.distributed callback" if halo is not None else "single rank (periodic wrap kernels)"),
-                     "exchanges": ctx.halo_count()[0], "bytes_sent": ctx.halo_count()[1]},
-            "kernel_ms": per}
+                     "exchanges_per_step": (h1[0] - h0[0]) / args.steps, "bytes_sent_per_step": (h1[1] - h0[1]) / args.steps,
+                     "exchanges": ctx.halo_count()[0], "bytes_sent": ctx.halo_count()[1]}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if solver is not None:
+        line["solver"] = solver
+    if parity is not None:
+        line["multi_gpu_parity"] = parity
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(args.workload, cores=1, steps=2, planes=10)
+        line["cpu_baseline"] = cpu_reference_sample(wname, planes=10, steps=2)
+        try:
+            line["cpu_baseline_c1"] = cpu_reference_c1()
+        except Exception as e:      # noqa
+            line["cpu_baseline_c1"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     ctx.close()
@@ -311,18 +418,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, shape, args):
+    """One implicit momentum solve per step through vfs_momentum_solve (device-resident GMRES + MFFD + Newton):
+    Ucont uploaded from pinned host memory, solution downloaded, LES update once per step."""
+    nzl, my, mx = shape
+    xh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
+    ctx.download_ptr("UCONT", xh.data_ptr())
+    x0 = xh.clone().pin_memory()
+    out = torch.empty_like(xh).pin_memory()
+
+    def step():
+        ctx.upload_ptr("UCONT", x0.data_ptr())
+        ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+        info = ctx.momentum_solve(max_newton=args.solver_newton, max_krylov=args.solver_krylov, rtol=1e-30, atol=0.0)
+        ctx.download_ptr("UCONT", out.data_ptr())
+        return info
+    info = step()
+    barrier()
+    n = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        info = step()
+    barrier()
+    ms = rmax((time.perf_counter() - t0) * 1e3 / n)
+    ctx.upload_ptr("UCONT", x0.data_ptr())
+    nres = info["residual_evals"]
+    return {"what": "per time step: lUcont up (pinned), LES update, Newton-GMRES(restart %d) with MFFD residuals on the device, Ucont down" % args.solver_krylov,
+            "ms_per_time_step": ms, "residual_evals_per_step": nres, "krylov_iterations": info["krylov_iterations"], "newton_iterations": info["newton_iterations"],
+            "ms_per_residual_eval_e2e": ms / max(1, nres), "rhs_cell_updates_per_s_e2e": cells_total * nres / (ms * 1e-3),
+            "h2d_bytes_per_step": nzl * my * mx * 3 * 8, "d2h_bytes_per_step": nzl * my * mx * 3 * 8}
+
+
 # ---- the reference's own CPU implementation (oracle/_ref), timed on the host cores -------------
-def _ref_worker(a):
-    workload, planes, steps, seed = a
+def _ref_case(workload, kofs, layers, seed):
+    """Reference context for the k-slab of `layers` interior cell layers starting at global node plane `kofs` of the
+    workload's grid (its own two boundary planes included; periodic k wraps the slab on itself: zero communication)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refdrv
     import parity_common as pc
     pkg = load_package()
-    cfg = dict(pkg.cases.CONFIGS[workload])
-    cfg["KM"] = planes + 1            # k-slab crop: planes interior cell layers, same i-j extent
+    cases = pkg.cases
+    full = dict(cases.CONFIGS[workload])
+    cfg = dict(full)
+    cfg["KM"] = layers + 1
     cfg["seed"] = seed
-    ref, xyz, f, met = pc.ref_setup(cfg, refdrv)
+    xyz = cases.make_grid(full, kofs, layers + 2) if kofs is not None else None
+    ref, xyz, f, met = pc.ref_setup(cfg, refdrv, xyz=xyz)
     ref.new_vec("X", 3, False); ref.new_vec("F", 3, False)
     ref.view("X")[...] = f["ucont"]
     cells = (cfg["IM"] - 1) * (cfg["JM"] - 1) * (cfg["KM"] - 1)
@@ -331,51 +473,130 @@ def _ref_worker(a):
         ref.global_to_local("Ucont", "lUcont")
         ref.Contra2Cart(); ref.Compute_Smagorinsky_Constant_1(); ref.Compute_eddy_viscosity_LES()
         ref.FormFunction_SNES("X", "F")
-    step()
+    return step, cells
+
+
+class quiet_stdout:
+    """The reference printf()s diagnostics (wall model: "nu_t=...,ustar=...") to fd 1; bench.py's stdout is ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        nul = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(nul, 1)
+        os.close(nul)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def _slab_worker(a):
+    with quiet_stdout():
+        return _slab_worker_(a)
+
+
+def _slab_worker_(a):
+    workload, kofs, layers, seed, warmup, steps, bar = a
+    step, cells = _ref_case(workload, kofs, layers, seed)
+    for _ in range(warmup):
+        step()
+    if bar is not None:
+        bar.wait()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    dt = time.perf_counter() - t0
-    return cells * steps / dt, cells
+    return time.perf_counter() - t0, cells
 
 
-def cpu_reference(workload, cores, steps, planes):
+def cpu_reference_sample(workload, planes, steps):
+    """Bounded 1-core sample for the `cpu_baseline` of the GPU arm."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refdrv
     if not refdrv.available():
         return {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libvfsref.so not present"}
-    if cores == 1:
-        rate, cells = _ref_worker((workload, planes, steps, 202))
-        rates = [rate]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_ref_worker, [(workload, planes, steps, 202 + q) for q in range(cores)])
-        rates = [r for r, _ in res]; cells = res[0][1]
-    return {"value": float(sum(rates)), "unit": "cell-updates/s", "cores": cores, "kind": "reference",
-            "sample": "reference sources (oracle/_ref) on %d independent %d-cell-layer k-slab crop(s) of the %s grid (%d cells each), %d timed steps each, zero communication cost" % (cores, planes, workload, cells, steps)}
+    dt, cells = _slab_worker((workload if workload in ("c2_box256", "c3_turbine") else "c2_box256", 100, planes, 202, 1, steps, None))
+    return {"value": cells * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
+            "sample": "reference sources (oracle/_ref) on one %d-cell-layer k-slab of the %s grid (%d cells), %d timed steps, 1 core" % (planes, workload, cells, steps)}
+
+
+def run_partitioned(workload, layers_total, kofs0, cores, warmup, steps):
+    """The grid's `layers_total` interior cell layers split into `cores` contiguous k-slabs, one reference process per
+    slab, all stepping concurrently; returns (seconds per step = slowest process, cells per step)."""
+    import multiprocessing as mp
+    cores = max(1, min(cores, layers_total // 2))
+    base, rem = divmod(layers_total, cores)
+    ctxm = mp.get_context("fork")
+    mgr = ctxm.Manager()
+    bar = mgr.Barrier(cores)
+    jobs, k = [], kofs0
+    for q in range(cores):
+        n = base + (1 if q < rem else 0)
+        jobs.append((workload, k, n, 202 + q, warmup, steps, bar))
+        k += n
+    with ctxm.Pool(cores) as pool:
+        res = pool.map(_slab_worker, jobs, chunksize=1)
+    return max(r[0] for r in res) / steps, sum(r[1] for r in res), cores
+
+
+def cpu_reference_c1():
+    """the reference on C1 exactly (Test_10 channel on its shipped 122x42x62-node grid), 1 core and P cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdrv
+    if not refdrv.available():
+        return {"value": None, "sample": "oracle/_ref/libvfsref.so not present"}
+    with quiet_stdout():
+        step, cells = _ref_case("c1_test10", None, 60, 101)
+        step()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            step()
+        one = cells * n / (time.perf_counter() - t0)
+    P = min(os.cpu_count() or 1, 64)
+    sec, cellsP, used = run_partitioned("c1_test10", 60, 0, P, 1, 3)
+    return {"unit": "cell-updates/s", "kind": "reference", "grid": "Test_10_ChannelFlow_Retau3000 shipped grid, 122x42x62 nodes (%d cells), wall model on" % cells,
+            "value_1core": one, "value_Pcores": cellsP / sec, "cores": used, "note": "P independent k-slab processes, zero communication cost (upper bound of an MPI run)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    cores = min(cores, 64)
-    t0 = time.perf_counter()
-    cb = cpu_reference(args.workload, cores=cores, steps=max(1, min(args.steps, 3)), planes=6)
-    if cb["value"] is None:
-        print(json.dumps({"impl": "reference", "unavailable": cb["sample"]}))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdrv
+    if not refdrv.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvfsref.so not present"}))
         return
     world = int(os.environ.get("WORLD_SIZE", 1))
+    cores = min(os.cpu_count() or 1, 64)
     pkg = load_package()
-    cfg = workload_cfg(pkg.cases, args.workload, world)
-    cells_total = (cfg["IM"] - 1) * (cfg["JM"] - 1) * (cfg["KM"] - 1)
-    ms_equiv = cells_total / cb["value"] * 1e3        # one pass over the arm's whole grid at the sampled host rate
-    line = {"impl": "reference", "metric": "RHS+LES cell-updates/s (FP64)", "value": cb["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_equiv, "ms_per_step_note": "whole %d-cell grid at the rate measured on the bounded sample" % cells_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + " (bounded k-slab sample, see cpu_baseline.sample)"}, "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": time.perf_counter() - t0}
+    wname = resolve_workload(args.workload, world)
+    cfg, scaling = workload_cfg(pkg.cases, wname, world)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    cells_total = (mx - 2) * (my - 2) * (mz - 2)
+    t0 = time.perf_counter()
+    # the whole grid when one pass over it takes the host cores a few seconds (c2_box256: ~2 s), otherwise a bounded
+    # contiguous k-range of it (the per-cell work does not depend on the number of layers)
+    base = {"c5_weak": "c5_weak", "c2_weak": "c2_box256"}.get(wname, wname)
+    est_rate = 5.0e5 * cores
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    layers_all = mz - 2
+    layers = layers_all
+    if cells_total / est_rate > budget_s:
+        layers = max(2 * cores if (mx - 2) * (my - 2) < 1e6 else cores, int(budget_s * est_rate / ((mx - 2) * (my - 2))))
+        layers = min(layers, layers_all)
+    sec, cells, used = run_partitioned(base, layers, 0, cores, args.warmup, args.steps)
+    value = cells / sec
+    full = layers == layers_all
+    sample = "reference sources (oracle/_ref): %s, %d of %d cell layers (%d cells per step) split into %d contiguous k-slabs, one process per core, " \
+             "%d warm-up + %d timed steps, measured wall per step = slowest process; zero communication cost" % (
+                 "the WHOLE grid" if full else "a bounded k-range of the grid", layers, layers_all, cells, used, args.warmup, args.steps)
+    cb = {"value": value, "unit": "cell-updates/s", "cores": used, "kind": "reference", "sample": sample, "whole_grid": full}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(cfg, wname, world, scaling), "cells_per_step": cells, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
 
 
@@ -385,9 +606,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_box256")
+    ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-solver", action="store_true")
+    ap.add_argument("--solver-newton", type=int, default=1)
+    ap.add_argument("--solver-krylov", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

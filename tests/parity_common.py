@@ -60,13 +60,15 @@ def conv_defined(cfg, fields):
     return ok[..., None].astype(float)
 
 
-def ref_setup(cfg, refdrv):
-    """Create the reference context, metrics and input state for cfg.  Returns (ref, xyz, fields)."""
+def ref_setup(cfg, refdrv, xyz=None):
+    """Create the reference context, metrics and input state for cfg (node coordinates `xyz`, default: cfg's own
+    grid).  Returns (ref, xyz, fields, metrics)."""
     pkg = load_package()
     cases = pkg.cases
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
     ref = refdrv.RefCase(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"])
-    xyz = cases.make_grid(cfg)
+    if xyz is None:
+        xyz = cases.make_grid(cfg)
     ref.set_coords(xyz)
     ref.FormMetrics()
     met = dict(csi=np.array(ref.owned("lCsi")), eta=np.array(ref.owned("lEta")), zet=np.array(ref.owned("lZet")), aj=np.array(ref.owned("lAj")))

@@ -3,7 +3,7 @@
 The directory name contains a hyphen (it mirrors the reference's repository name), so it is
 loaded by path: `from __graft_entry__ import load_package; pkg = load_package()`.
 """
-from . import capi, cases, petsc_io  # noqa: F401
+from . import capi, cases, petsc_io, selfcheck  # noqa: F401
 
 
 def __getattr__(name):

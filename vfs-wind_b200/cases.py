@@ -92,11 +92,15 @@ def make_masks(cfg, rng):
     """Nvert: 3 inside tower/nacelle boxes and ellipsoids, 1 on their one-cell fluid-side shell,
     0 elsewhere (integers stored as doubles, Source/ibm.c:231-232,518-519)."""
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
-    nv = np.zeros((mz, my, mx))
+    nzl = mz
+    nv = np.zeros((nzl, my, mx))
     if not cfg.get("masks"):
         return nv
-    k, j, i = np.meshgrid(np.arange(mz), np.arange(my), np.arange(mx), indexing="ij")
-    solid = np.zeros((mz, my, mx), bool)
+    kofs = 0
+    if cfg.get("mask_window"):          # k-slab of a larger grid: bodies are placed in GLOBAL k (kofs, global mz)
+        kofs, mz = cfg["mask_window"]
+    k, j, i = np.meshgrid(np.arange(nzl) + kofs, np.arange(my), np.arange(mx), indexing="ij")
+    solid = np.zeros((nzl, my, mx), bool)
     nrow = 4 if mx > 600 else 1
     ncol = 8 if mx > 600 else 2
     for r in range(nrow):
@@ -107,8 +111,9 @@ def make_masks(cfg, rng):
             tw = max(1, mx // 128)
             solid |= (abs(i - ci) <= tw) & (abs(k - ck) <= tw) & (j >= 1) & (j <= hub)           # tower (box)
             solid |= (((i - ci) / (2.0 * tw + 1)) ** 2 + ((j - hub) / (1.5 * tw + 1)) ** 2 + ((k - ck) / (3.0 * tw + 2)) ** 2) <= 1.0  # nacelle (ellipsoid)
+    kend = (k == 0) | (k == mz - 1)
     solid[:, 0, :] = solid[:, -1, :] = False
-    solid[0] = solid[-1] = False
+    solid[kend] = False
     solid[:, :, 0] = solid[:, :, -1] = False
     near = np.zeros_like(solid)
     for ax in range(3):
@@ -116,7 +121,7 @@ def make_masks(cfg, rng):
     nv[solid] = 3.0
     shell = near & ~solid
     shell[:, 0, :] = shell[:, -1, :] = False
-    shell[0] = shell[-1] = False
+    shell[kend] = False
     shell[:, :, 0] = shell[:, :, -1] = False
     nv[shell] = 1.0
     return nv
@@ -161,7 +166,8 @@ def make_fields(cfg, metrics):
     if cfg.get("forcing"):
         # actuator-disk style forcing: smoothed 2h delta (Source/rotor_model.c:5130 dfunc_2h) around
         # rotor planes at hub height, projected on the face area vectors like Calc_F_eul (:3785-3829)
-        k, j, i = np.meshgrid(np.arange(mz), np.arange(my), np.arange(mx), indexing="ij")
+        kofs, mzg = cfg.get("mask_window") or (0, mz)
+        k, j, i = np.meshgrid(np.arange(mz) + kofs, np.arange(my), np.arange(mx), indexing="ij")
         nrow = 4 if mx > 600 else 1
         ncol = 8 if mx > 600 else 2
         hub = max(4, int(0.35 * my))
@@ -169,7 +175,7 @@ def make_fields(cfg, metrics):
         for r in range(nrow):
             for c in range(ncol):
                 ci = int(mx * (c + 0.5) / ncol)
-                ck = int(mz * (0.25 + 0.5 * (r + 0.5) / nrow)) - max(3, mz // 32)
+                ck = int(mzg * (0.25 + 0.5 * (r + 0.5) / nrow)) - max(3, mzg // 32)
                 rad = np.sqrt((i - ci) ** 2.0 + (j - hub) ** 2.0)
                 d = np.abs(k - ck) / 2.0
                 delta = np.where(d < 1.0, 0.5 * (1.0 + np.cos(np.pi * d)) / 2.0, 0.0)
