@@ -157,7 +157,8 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *   8  single-rank ghost-refresh sequences as one launch (default 1)
  *   9  overlap the k-face-flux and Fp halo exchanges with interior planes (default 1; nranks > 1 with vfs_nccl_init)
  *  11  asynchronous compute-only entry points (vfs_contra2cart, vfs_ib_bc, vfs_les_cs, vfs_les_nut return once their work
- *      is queued; default 0): a following vfs_formfunction_snes then copies X while those kernels still run */
+ *      is queued; default 0): a following vfs_formfunction_snes then copies X while those kernels still run
+ *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus

@@ -73,3 +73,28 @@ def test_emulated_wall_function_boundaries(pkg, refdrv, emu, bctype, extra):
     assert err.pop("IB_BC_nvert_mismatches") == 0
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
+
+
+def test_emulated_fp_in_projection_bitwise(pkg, emu):
+    """Option 12 (Fp evaluated inside the projection block program) against FpCell + Fp planes + Project: bitwise."""
+    import numpy as np
+    capi, cases = pkg.capi, pkg.cases
+    for cfgname, dims in (("c2_box256", (37, 19, 23)), ("c3_turbine", (35, 21, 19))):
+        cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
+        mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+        outs = []
+        for val in (0, 1):
+            ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]), lib=emu)
+            ctx.set_option(12, val)
+            ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+            for k, n in pc.FIELDS_IN:
+                ctx.upload(n, f[k])
+            o = pc.run_path(ctx, pc.krylov_x(f["ucont"]))
+            ctx.upload("RHS_O", f["rhs_o"]); ctx.Formfunction_2("RHS_O", 0.7)
+            o["FF2"] = ctx.download("RHS_O")
+            outs.append(o)
+            ctx.close()
+        for n in outs[0]:
+            assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)

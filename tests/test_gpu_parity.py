@@ -189,6 +189,32 @@ def test_tiled_equals_staged(pkg):
                 assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
 
 
+@pytest.mark.parametrize("key", [12])
+def test_fused_variants_bitwise_equal_staged_chain(pkg, key):
+    """Option 12: Fp evaluated inside the projection kernel (ProjFpMarch) == FpCell + Fp planes + Project, bitwise
+    (same arithmetic, same operand order), on a multi-tile grid with periodic i and k, and on the masked c3 case."""
+    capi, cases = pkg.capi, pkg.cases
+    for cfgname, dims in (("c2_box256", (101, 67, 50)), ("c3_turbine", (70, 37, 45))):
+        cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
+        mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+        outs = []
+        for val in (0, 1):
+            ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+            ctx.set_option(key, val)
+            ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+            for k, n in pc.FIELDS_IN:
+                ctx.upload(n, f[k])
+            o = pc.run_path(ctx, pc.krylov_x(f["ucont"]))
+            ctx.upload("RHS_O", f["rhs_o"]); ctx.Formfunction_2("RHS_O", 0.7)
+            o["FF2"] = ctx.download("RHS_O")
+            outs.append(o)
+            ctx.close()
+        for n in outs[0]:
+            assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
+
+
 def test_graph_replay_equals_eager(pkg):
     """vfs_rhs_les_fused replayed as a CUDA graph gives bitwise the same fields as eager launches."""
     capi, cases = pkg.capi, pkg.cases

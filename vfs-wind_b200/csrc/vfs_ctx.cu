@@ -128,6 +128,8 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
+  int fp_fused = 0;              // Fp evaluated inside the projection kernel (ProjFpMarch) instead of FpCell + Fp planes in HBM (option key 12;
+                                 // bitwise the staged result, measured slower on B200: 2.20 vs 0.72 + 0.76 ms at 256^3, gpurun_out r02a)
 };
 
 static void graph_reset(vfs_ctx *c);
@@ -614,6 +616,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 8) c->fuse_refresh = value;
   else if (key == 9) c->overlap = value;
   else if (key == 11) c->async_api = value;
+  else if (key == 12) c->fp_fused = value;
   graph_reset(c);
   return 0;
 }
@@ -996,15 +999,55 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     { FaceFlux<2> f = {d}; RUN(launch(c, S.fl[n][2], f)); }
   }
   ev_rec(c, 2 * VFS_T_FLUX + 1);
+  const Grp gi = grp_cat(grp(S_FC1, 3), grp(S_FV1, 3)), gj = grp_cat(grp(S_FC2, 3), grp(S_FV2, 3)), gk = grp_cat(grp(S_FC3, 3), grp(S_FV3, 3));
+  const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
+  if (c->fused == 1 && c->fp_fused && S.n == 1) {
+    // ---- Fp folded into the projection (ProjFpMarch, vfs_march_kernels.h) ----
+    // Flux ghosts as below; between ranks ALL face-flux families travel (Fp of the first ghost plane is evaluated
+    // locally from them), in ONE exchange instead of the k-family + Fp exchanges of the staged chain.
+    ev_rec(c, 2 * VFS_T_FP);
+    if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
+    if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
+    const bool multi = c->prm.nranks > 1;
+    const Grp gall = grp_cat(grp_cat(gi, gj), gk);
+    ProjFpMarch P = {d, mode, s0, scale};
+    auto shell_nodes = [&]() -> int {          // boundary nodes of the slab: every component masked, no Fp read
+      if (mode == 0) { ProjectAdd f = {d, s0, scale}; return launch_shell(c, 0, d.nzl, f); }
+      ProjectSNES f = {d}; return launch_shell(c, 0, d.nzl, f);
+    };
+    auto march = [&](int q0, int q1) -> int {
+      if (run_projfp_march(c->stream, P, q0 < k1 ? k1 : q0, q1 > k2 ? k2 : q1, &c->launches)) { set_err(c, "projection kernel launch failed"); return VFS_ERR_CUDA; }
+      return 0;
+    };
+    const bool ovl = multi && can_overlap(c) && d.nzl >= 10;
+    ev_rec(c, 2 * VFS_T_FP + 1);
+    ev_rec(c, 2 * VFS_T_PROJECT);
+    if (!ovl) {
+      RUN(halo_k(c, multi ? gall : gk));
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      RUN(shell_nodes());
+      RUN(march(k1, k2));
+    } else {
+      // the i/j-plane copies of the owned planes go first (they are part of what the neighbours receive); the cells
+      // of local planes 2 .. nzl-4 and the Fp planes up to nzl-3 touch no k ghost plane and no seam copy
+      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, 0, d.nzl, f)); }
+      RUN(ovl_exchange(c, gall));
+      RUN(shell_nodes());
+      RUN(march(2, d.nzl - 3));
+      RUN(ovl_join(c));
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      RUN(march(0, 2)); RUN(march(d.nzl - 3, d.nzl));
+    }
+    ev_rec(c, 2 * VFS_T_PROJECT + 1);
+    return 0;
+  }
   ev_rec(c, 2 * VFS_T_FP);
   // momentum.c:1458-1496, 1506-1546.  FpCell reads the fluxes of face family D along direction D only, at the
   // cell's own other two indices, so each family is refreshed in its own direction only (a third of the data;
   // between ranks only the k-face family travels).
   {
-    const Grp gi = grp_cat(grp(S_FC1, 3), grp(S_FV1, 3)), gj = grp_cat(grp(S_FC2, 3), grp(S_FV2, 3)), gk = grp_cat(grp(S_FC3, 3), grp(S_FV3, 3));
     if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
     if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
-    const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
     const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8;
     FpCell fp = {d};
     if (!ovl) {

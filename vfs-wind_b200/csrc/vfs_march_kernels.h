@@ -553,6 +553,126 @@ struct Les3March {
     d.s[S_CS][p] = cs;
   }
 };
+// ---- Fp folded into the projection (momentum.c:1548-1678 + 1687-1735 + 1833-1841 [+ 2297-2331]) ---------
+// The staged chain wrote Fp (FpCell), refreshed its ghosts, applied the periodic node copies and read it back four
+// times in the projection (at p, p+1, p+sj, p+sk).  Here a block marches an (i,j) tile along k: every step it
+// evaluates Fp of plane k+1 once per tile node (+ one halo column and row) from the 18 face-flux scalars into one
+// of three rotating shared-memory planes, then projects plane k from the Fp planes k and k+1 — Fp never reaches
+// HBM, the Fp ghost refresh / node copies / inter-rank exchange disappear, and the bytes are the 18 flux planes
+// read once.  The periodic copies of Fp (node m-1 takes the value of node 1, momentum.c:1687-1713) become an index
+// remap of the cell whose Fp is evaluated; non-periodic boundary nodes' Fp is never used (their components are
+// masked, momentum.c:1833-1841).  Arithmetic and operand order are FpCell's and project_fp's: bitwise the staged
+// result.  Boundary NODES of the slab (mask 7: no projection) are assembled by the staged functor on the shell.
+struct ProjFpMarch {
+  static constexpr int TX = 32, TY = 8, NT = TX * TY, FX = TX + 1, FY = TY + 1, FN = FX * FY, NBUF = 3;
+  static constexpr long SMEM_D = (long)NBUF * 3 * FN;
+  VfsDev d; int mode, s0; double scale;
+  static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 1) / TX; }
+  static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 1) / TY; }
+  VFS_HD void fp_slot(double *buf, int slot, int i, int j, int k) const {
+    double f[3] = {0, 0, 0};
+    bool ok = i <= d.mx - 1 && j <= d.my - 1;
+    int kg = k + d.kofs;
+    if (ok && i == d.mx - 1) { if (d.perx) i = 1; else ok = false; }
+    if (ok && j == d.my - 1) { if (d.pery) j = 1; else ok = false; }
+    if (ok && kg == d.mz - 1) {
+      // the image of global plane 1: the plane itself on a single rank, the ghost plane two above on the last rank
+      if (d.perz) { k = d.single_rank ? 1 : k + 2; kg = 1; } else ok = false;
+    }
+    if (ok) fp_cell_value(d, i, j, kg, d.idx(i, j, k), f);
+    buf[slot] = f[0]; buf[FN + slot] = f[1]; buf[2 * FN + slot] = f[2];
+  }
+  // phase A: Fp of plane kq -> buffer kq mod 3 (tile nodes + the halo column i0+TX and row j0+TY)
+  VFS_HD void phaseA(int tid, int bx, int by, int kq, int kref, double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i0 = 1 + bx * TX, j0 = 1 + by * TY;
+    double *buf = sm + ((kq - kref) % NBUF) * 3 * FN;
+    fp_slot(buf, ty * FX + tx, i0 + tx, j0 + ty, kq);
+    if (tid < TY) fp_slot(buf, tid * FX + TX, i0 + TX, j0 + tid, kq);
+    else if (tid < TY + TX) fp_slot(buf, TY * FX + (tid - TY), i0 + (tid - TY), j0 + TY, kq);
+  }
+  // phase B: projection, masks and assembly of plane k
+  VFS_HD void phaseB(int tid, int bx, int by, int k, int kref, const double *sm) const {
+    const int tx = tid % TX, ty = tid / TX, i = 1 + bx * TX + tx, j = 1 + by * TY + ty;
+    if (i > d.mx - 2 || j > d.my - 2) return;
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const double *b0 = sm + ((k - kref) % NBUF) * 3 * FN + ty * FX + tx, *b1 = sm + ((k + 1 - kref) % NBUF) * 3 * FN + ty * FX + tx;
+    const int m = rhs_mask(d, i, j, kg, p);
+    const double f0 = b0[0], f1 = b0[FN], f2 = b0[2 * FN];
+    const double ia = d.s[S_IAJ][p];
+    double rr[3];
+    {
+      const long q = p + 1;
+      const double iaj = 2. / (ia + d.s[S_IAJ][q]);
+      rr[0] = (0.5 * (d.s[S_CSI0][p] * f0 + d.s[S_CSI1][p] * f1 + d.s[S_CSI2][p] * f2) +
+               0.5 * (d.s[S_CSI0][q] * b0[1] + d.s[S_CSI1][q] * b0[FN + 1] + d.s[S_CSI2][q] * b0[2 * FN + 1])) * iaj;
+    }
+    {
+      const long q = p + d.sj;
+      const double jaj = 2. / (ia + d.s[S_IAJ][q]);
+      rr[1] = (0.5 * (d.s[S_ETA0][p] * f0 + d.s[S_ETA1][p] * f1 + d.s[S_ETA2][p] * f2) +
+               0.5 * (d.s[S_ETA0][q] * b0[FX] + d.s[S_ETA1][q] * b0[FN + FX] + d.s[S_ETA2][q] * b0[2 * FN + FX])) * jaj;
+    }
+    {
+      const long q = p + d.sk;
+      const double kaj = 2. / (ia + d.s[S_IAJ][q]);
+      rr[2] = (0.5 * (d.s[S_ZET0][p] * f0 + d.s[S_ZET1][p] * f1 + d.s[S_ZET2][p] * f2) +
+               0.5 * (d.s[S_ZET0][q] * b1[0] + d.s[S_ZET1][q] * b1[FN] + d.s[S_ZET2][q] * b1[2 * FN])) * kaj;
+    }
+    if (mode == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) d.s[s0 + a][p] = ((m >> a) & 1) ? 0. : d.s[s0 + a][p] + scale * rr[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++) d.s[S_R0 + a][p] = snes_assemble(d, a, p, (m >> a) & 1, rr[a]);
+    }
+  }
+};
+#ifndef VFS_EMU
+__global__ void __launch_bounds__(ProjFpMarch::NT, 4) k_projfp_march(const ProjFpMarch P, int kbeg, int kend, int kchunk) {
+  __shared__ double sm[ProjFpMarch::SMEM_D];
+  const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+  const int ka = kbeg + blockIdx.z * kchunk, kb = min(kend, ka + kchunk);
+  if (ka >= kb) return;
+  P.phaseA(tid, bx, by, ka, ka, sm);
+  for (int k = ka; k < kb; k++) {
+    P.phaseA(tid, bx, by, k + 1, ka, sm);
+    __syncthreads();
+    P.phaseB(tid, bx, by, k, ka, sm);
+  }
+}
+static inline int run_projfp_march(cudaStream_t stream, const ProjFpMarch &P, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  const int ntx = ProjFpMarch::tiles_x(P.d), nty = ProjFpMarch::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 16, 148 * 4);
+  dim3 grd(ntx, nty, (k1 - k0 + kchunk - 1) / kchunk);
+  k_projfp_march<<<grd, ProjFpMarch::NT, 0, stream>>>(P, k0, k1, kchunk);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#else
+static inline int run_projfp_march(void *, const ProjFpMarch &P, int k0, int k1, long *launches) {
+  if (k1 <= k0) return 0;
+  typedef ProjFpMarch M;
+  std::vector<double> smv(M::SMEM_D);
+  double *sm = smv.data();
+  const int ntx = M::tiles_x(P.d), nty = M::tiles_y(P.d);
+  const int kchunk = pick_kchunk(ntx * nty, k1 - k0, 4, 7);
+  for (int bz = 0; bz * kchunk < k1 - k0; bz++)
+    for (int by = 0; by < nty; by++)
+      for (int bx = 0; bx < ntx; bx++) {
+        const int ka = k0 + bz * kchunk, kb = k1 < ka + kchunk ? k1 : ka + kchunk;
+        for (int t = 0; t < M::NT; t++) P.phaseA(t, bx, by, ka, ka, sm);
+        for (int k = ka; k < kb; k++) {
+          for (int t = 0; t < M::NT; t++) P.phaseA(t, bx, by, k + 1, ka, sm);
+          for (int t = 0; t < M::NT; t++) P.phaseB(t, bx, by, k, ka, sm);
+        }
+      }
+  (*launches)++;
+  return 0;
+}
+#endif
+
 // ---- fused residual: face fluxes -> Fp -> projection -> assembly (regular interior) ----------------
 // Replaces, for the cells whose whole dependency cone is free of domain-end special cases, the staged
 // chain FaceFlux<0,1,2> -> FpCell -> ProjectSNES/ProjectAdd (momentum.c:669-1938, 2297-2331): the 18

@@ -258,38 +258,43 @@ struct LegacyDiv {
   }
 };
 
-// momentum.c:1548-1678: flux divergence with 4th-order correction + viscous divergence -> Fp
+// momentum.c:1548-1678: flux divergence with 4th-order correction + viscous divergence -> Fp of the cell at
+// node p = (i, j, k); kg = global k of the cell (for a ghost plane across the periodic seam: the plane it images)
+VFS_HD void fp_cell_value(const VfsDev &d, int i, int j, int kg, long p, double out[3]) {
+  const long st[3] = {1, d.sj, d.sk};
+  const int cc[3] = {i, j, kg}, mm[3] = {d.mx, d.my, d.mz}, pp[3] = {d.perx, d.pery, d.perz};
+  const double *nv = d.s[S_NV];
+  double div[3] = {0, 0, 0}, div4[3] = {0, 0, 0}, vis[3] = {0, 0, 0};
+  // accumulate in the reference's order: i-, j-, k-family
+  for (int a = 0; a < 3; a++) {
+    div[a] = (d.s[S_FC1 + a][p] - d.s[S_FC1 + a][p - 1] + d.s[S_FC2 + a][p] - d.s[S_FC2 + a][p - d.sj] + d.s[S_FC3 + a][p] - d.s[S_FC3 + a][p - d.sk]);
+    vis[a] = (d.s[S_FV1 + a][p] - d.s[S_FV1 + a][p - 1] + d.s[S_FV2 + a][p] - d.s[S_FV2 + a][p - d.sj] + d.s[S_FV3 + a][p] - d.s[S_FV3 + a][p - d.sk]);
+  }
+  if (!d.second_order) {
+    for (int D = 0; D < 3; D++) {
+      const int c = cc[D], m = mm[D], per = pp[D];
+      const long s = st[D];
+      long pR = p + s, pL = p - 2 * s;
+      double den = 3.;
+      if (c == 1) { if (per) pL = p - 4 * s; else pR = p, pL = p - s, den = 1.; }
+      else if (c == 2 || c == m - 3) { if (!per) pR = p, pL = p - s, den = 1.; }
+      else if (c == m - 2) { if (per) pR = p + 3 * s; else pR = p, pL = p - s, den = 1.; }
+      if (nv[p - s] + nv[p] + nv[p + s] > 0.1) pR = p, pL = p - s, den = 1.;
+      const double inv = 1. / den;
+      for (int a = 0; a < 3; a++) div4[a] += (d.s[S_FC1 + 3 * D + a][pR] - d.s[S_FC1 + 3 * D + a][pL]) * inv;
+    }
+    for (int a = 0; a < 3; a++) out[a] = (9. / 8.) * div[a] + (-1. / 8.) * div4[a] + vis[a];
+  } else {
+    for (int a = 0; a < 3; a++) out[a] = div[a] + vis[a];
+  }
+}
 struct FpCell {
   VfsDev d;
   VFS_HD void operator()(int i, int j, int k) const {
-    const int kg = k + d.kofs;
-    const long st[3] = {1, d.sj, d.sk};
-    const int cc[3] = {i, j, kg}, mm[3] = {d.mx, d.my, d.mz}, pp[3] = {d.perx, d.pery, d.perz};
     const long p = d.idx(i, j, k);
-    const double *nv = d.s[S_NV];
-    double div[3] = {0, 0, 0}, div4[3] = {0, 0, 0}, vis[3] = {0, 0, 0};
-    // accumulate in the reference's order: i-, j-, k-family
-    for (int a = 0; a < 3; a++) {
-      div[a] = (d.s[S_FC1 + a][p] - d.s[S_FC1 + a][p - 1] + d.s[S_FC2 + a][p] - d.s[S_FC2 + a][p - d.sj] + d.s[S_FC3 + a][p] - d.s[S_FC3 + a][p - d.sk]);
-      vis[a] = (d.s[S_FV1 + a][p] - d.s[S_FV1 + a][p - 1] + d.s[S_FV2 + a][p] - d.s[S_FV2 + a][p - d.sj] + d.s[S_FV3 + a][p] - d.s[S_FV3 + a][p - d.sk]);
-    }
-    if (!d.second_order) {
-      for (int D = 0; D < 3; D++) {
-        const int c = cc[D], m = mm[D], per = pp[D];
-        const long s = st[D];
-        long pR = p + s, pL = p - 2 * s;
-        double den = 3.;
-        if (c == 1) { if (per) pL = p - 4 * s; else pR = p, pL = p - s, den = 1.; }
-        else if (c == 2 || c == m - 3) { if (!per) pR = p, pL = p - s, den = 1.; }
-        else if (c == m - 2) { if (per) pR = p + 3 * s; else pR = p, pL = p - s, den = 1.; }
-        if (nv[p - s] + nv[p] + nv[p + s] > 0.1) pR = p, pL = p - s, den = 1.;
-        const double inv = 1. / den;
-        for (int a = 0; a < 3; a++) div4[a] += (d.s[S_FC1 + 3 * D + a][pR] - d.s[S_FC1 + 3 * D + a][pL]) * inv;
-      }
-      for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = (9. / 8.) * div[a] + (-1. / 8.) * div4[a] + vis[a];
-    } else {
-      for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = div[a] + vis[a];
-    }
+    double f[3];
+    fp_cell_value(d, i, j, k + d.kofs, p, f);
+    for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = f[a];
   }
 };
 
