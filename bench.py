@@ -430,7 +430,9 @@ def bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, shape, args)
     def step():
         ctx.upload_ptr("UCONT", x0.data_ptr())
         ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
-        info = ctx.momentum_solve(max_newton=args.solver_newton, max_krylov=args.solver_krylov, rtol=1e-30, atol=0.0)
+        # a fixed amount of work: `solver_newton` Newton steps of exactly `solver_krylov` GMRES iterations each
+        info = ctx.momentum_solve(max_newton=args.solver_newton, max_krylov=args.solver_krylov, restart=args.solver_krylov, rtol=1e-30, atol=0.0,
+                                  use_ew=0, ksp_rtol=1e-30)
         ctx.download_ptr("UCONT", out.data_ptr())
         return info
     info = step()

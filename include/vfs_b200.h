@@ -11,6 +11,7 @@
  *   vfs_les_cs              <- Compute_Smagorinsky_Constant_1(UserCtx*,Vec,Vec)  les.c:75
  *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
  *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
+ *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4302
  *
  * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
  * the context owns every device buffer; host arrays are borrowed for the duration of a call.
@@ -138,6 +139,33 @@ int vfs_formfunction_snes(vfs_ctx *c, const double *x_host, double *f_host);
 int vfs_formfunction_snes_dev(vfs_ctx *c);
 /* one cell-update unit: vfs_contra2cart + vfs_les_cs + vfs_les_nut + vfs_formfunction_snes_dev */
 int vfs_rhs_les_fused(vfs_ctx *c);
+
+/* Device-resident implicit momentum solve: replaces the SNESSolve of Implicit_MatrixFree
+ * (Source/implicitsolver.c:4203-4302) — SNES trust region + Eisenstat-Walker v3, matrix-free Jacobian by forward
+ * differences of FormFunction_SNES, restarted GMRES without preconditioner.  In/out: VFS_UCONT on the device
+ * (U = Ucont before, Ucont = U after, :4300,4310); the Krylov basis and all work vectors stay in HBM, dot products
+ * are summed over the ranks with ncclAllReduce (needs vfs_nccl_init when nranks > 1).  PETSc 3.1, where the
+ * reference's solver lives, is not part of the reference tree: its published algorithms are restated
+ * (vfs-wind_b200/csrc/vfs_solver.h). */
+typedef struct vfs_solver_params {
+  int max_newton;                       /* SNESSetTolerances maxit = 50            implicitsolver.c:4257 */
+  int restart;                          /* KSPGMRES restart (PETSc default 30)                            */
+  int max_krylov;                       /* KSPSetTolerances maxits = 1000          implicitsolver.c:4279 */
+  double snes_atol, snes_rtol, snes_stol;   /* SNESSetTolerances(PETSC_DEFAULT, imp_free_tol, ...) :4257 */
+  double ksp_rtol, ksp_atol, ksp_dtol;  /* KSPSetTolerances(imp_free_tol, ...) :4277; rtol superseded by Eisenstat-Walker */
+  int use_ew;                           /* SNESKSPSetUseEW + version 3             implicitsolver.c:4254-4255 */
+  int trust_region;                     /* 1 = SNESTR (:4251); 0 = full Newton steps                       */
+} vfs_solver_params;
+typedef struct vfs_solver_info {
+  int newton_iterations, krylov_iterations, residual_evals;
+  int reason;                           /* SNESConvergedReason numbering: 2 atol, 3 rtol, 4 step, 7 tr delta, < 0 diverged */
+  double fnorm0, fnorm, xnorm, delta;
+  int n_history;                        /* entries of fnorm_history (|F| before the first and after every Newton step) */
+  double fnorm_history[17];
+  int ksp_its_history[16];
+} vfs_solver_info;
+int vfs_solver_defaults(vfs_solver_params *p);
+int vfs_momentum_solve(vfs_ctx *c, const vfs_solver_params *p, vfs_solver_info *info);
 
 /* number of kernels launched by this context since creation (bench `gpu_launches`) */
 long vfs_launch_count(vfs_ctx *c);

@@ -22,7 +22,8 @@ FIELD_DOF = {"COOR": 3, "CSI": 3, "ETA": 3, "ZET": 3, "AJ": 1, "NVERT": 1, "UCON
 EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs_set_stream", "vfs_set_halo_callback", "vfs_sync",
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_download_async", "vfs_download_wait",
-           "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms"]
+           "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms",
+           "vfs_solver_defaults", "vfs_momentum_solve", "vfs_set_option"]
 
 
 class VfsParams(C.Structure):
@@ -33,6 +34,19 @@ class VfsParams(C.Structure):
                                        "ti", "tistart", "rstart_flg", "levelset", "rans", "inviscid", "skew", "movefsi", "rotatefsi",
                                        "i_periodic", "j_periodic", "k_periodic", "i_homo_filter", "j_homo_filter", "k_homo_filter")] + \
                [(n, C.c_double) for n in ("ren", "dt", "max_cs", "roughness_size")]
+
+
+class VfsSolverParams(C.Structure):
+    _fields_ = [("max_newton", C.c_int), ("restart", C.c_int), ("max_krylov", C.c_int),
+                ("snes_atol", C.c_double), ("snes_rtol", C.c_double), ("snes_stol", C.c_double),
+                ("ksp_rtol", C.c_double), ("ksp_atol", C.c_double), ("ksp_dtol", C.c_double),
+                ("use_ew", C.c_int), ("trust_region", C.c_int)]
+
+
+class VfsSolverInfo(C.Structure):
+    _fields_ = [("newton_iterations", C.c_int), ("krylov_iterations", C.c_int), ("residual_evals", C.c_int), ("reason", C.c_int),
+                ("fnorm0", C.c_double), ("fnorm", C.c_double), ("xnorm", C.c_double), ("delta", C.c_double),
+                ("n_history", C.c_int), ("fnorm_history", C.c_double * 17), ("ksp_its_history", C.c_int * 16)]
 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int))
@@ -75,6 +89,8 @@ def _bind(lib):
     lib.vfs_last_ms.restype = C.c_double
     if hasattr(lib, "vfs_set_option"):
         lib.vfs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.vfs_solver_defaults.argtypes = [C.POINTER(VfsSolverParams)]
+    lib.vfs_momentum_solve.argtypes = [C.c_void_p, C.POINTER(VfsSolverParams), C.POINTER(VfsSolverInfo)]
     return lib
 
 
@@ -274,6 +290,22 @@ class VfsContext:
 
     def FormFunction_SNES_dev(self):
         self._ck(self.lib.vfs_formfunction_snes_dev(self.h))
+
+    def momentum_solve(self, max_newton=None, max_krylov=None, restart=None, rtol=None, atol=None, ksp_rtol=None, use_ew=None, trust_region=None):
+        """Implicit_MatrixFree's SNESSolve on the device (Source/implicitsolver.c:4203-4302): VFS_UCONT in/out.
+        Defaults are the reference's / PETSc's; returns the vfs_solver_info fields as a dict."""
+        sp = VfsSolverParams()
+        self.lib.vfs_solver_defaults(C.byref(sp))
+        for k, v in (("max_newton", max_newton), ("max_krylov", max_krylov), ("restart", restart), ("snes_rtol", rtol), ("snes_atol", atol),
+                     ("ksp_rtol", ksp_rtol), ("use_ew", use_ew), ("trust_region", trust_region)):
+            if v is not None:
+                setattr(sp, k, v)
+        info = VfsSolverInfo()
+        self._ck(self.lib.vfs_momentum_solve(self.h, C.byref(sp), C.byref(info)))
+        out = {k: getattr(info, k) for k, _ in VfsSolverInfo._fields_ if not k.endswith("history")}
+        out["fnorm_history"] = [info.fnorm_history[q] for q in range(info.n_history)]
+        out["ksp_its_history"] = [info.ksp_its_history[q] for q in range(max(0, min(16, info.n_history - 1)))]
+        return out
 
     def rhs_les_fused(self):
         self._ck(self.lib.vfs_rhs_les_fused(self.h))

@@ -31,6 +31,7 @@ struct NcclApi {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -47,6 +48,7 @@ static NcclApi &nccl_api() {
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
   a.Send = (decltype(a.Send))dlsym(a.h, "ncclSend");
   a.Recv = (decltype(a.Recv))dlsym(a.h, "ncclRecv");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
   a.GroupStart = (decltype(a.GroupStart))dlsym(a.h, "ncclGroupStart");
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.h, "ncclGroupEnd");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
@@ -67,6 +69,7 @@ typedef void *cudaEvent_t;
 #endif
 
 static std::string g_create_err;
+struct VfsSolver;
 
 struct vfs_ctx {
   vfs_params prm;
@@ -110,10 +113,11 @@ struct vfs_ctx {
   long halo_exchanges = 0, halo_bytes = 0;
   // CUDA graphs of the launch-bound call sequences (single rank only: the halo callback is host code)
   int use_graph = 0; bool capturing = false;
-  int graph_calls[2] = {0, 0};
+  int graph_calls[3] = {0, 0, 0};
 #ifndef VFS_EMU
-  cudaGraphExec_t gexec[2] = {0, 0};
+  cudaGraphExec_t gexec[3] = {0, 0, 0};      // 0: residual, 1: RHS+LES unit, 2: the solver's residual (vfs_solver.h)
 #endif
+  VfsSolver *solver = nullptr;   // Krylov vectors of vfs_momentum_solve, allocated on first use
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
   int flux_minb = 2;             // resident blocks per SM requested for the tiled flux kernel (option key 3)
@@ -133,6 +137,7 @@ struct vfs_ctx {
 };
 
 static void graph_reset(vfs_ctx *c);
+static void ks_free(vfs_ctx *c);
 static void set_err(vfs_ctx *c, const std::string &m) { if (c) c->err = m; else g_create_err = m; }
 
 template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
@@ -500,6 +505,9 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
 #ifndef VFS_EMU
   cudaStreamSynchronize(c->stream);
+#endif
+  ks_free(c);
+#ifndef VFS_EMU
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -601,7 +609,7 @@ extern "C" double vfs_last_ms(vfs_ctx *c, int which) {
 }
 static void graph_reset(vfs_ctx *c) {
 #ifndef VFS_EMU
-  for (int q = 0; q < 2; q++) { if (c->gexec[q]) cudaGraphExecDestroy(c->gexec[q]); c->gexec[q] = 0; c->graph_calls[q] = 0; }
+  for (int q = 0; q < 3; q++) { if (c->gexec[q]) cudaGraphExecDestroy(c->gexec[q]); c->gexec[q] = 0; c->graph_calls[q] = 0; }
 #endif
 }
 extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
@@ -1338,3 +1346,5 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
   ev_rec(c, 2 * VFS_T_TOTAL + 1);
   return vfs_sync(c);
 }
+
+#include "vfs_solver.h"
