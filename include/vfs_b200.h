@@ -11,7 +11,7 @@
  *   vfs_les_cs              <- Compute_Smagorinsky_Constant_1(UserCtx*,Vec,Vec)  les.c:75
  *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
  *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
- *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4302
+ *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4299
  *
  * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
  * the context owns every device buffer; host arrays are borrowed for the duration of a call.
@@ -74,6 +74,10 @@ typedef struct vfs_params {
   int i_homo_filter, j_homo_filter, k_homo_filter; /* must be 0 (off in all configs)         */
   double ren, dt, max_cs;
   double roughness_size; /* -roughness (main.c:319,1734): k_s of the rough-wall log law, bctype -2            */
+  /* switches that reroute this path in the reference and are not built: must be 0 (momentum.c:754,1015,1301 select
+   * weno3 on levelset_weno even without levelset; freesurface_wallmodel / air_flow_levelset change the wall model and
+   * the boundary fluxes).  `central` only matters together with rans, which is rejected. */
+  int levelset_weno, freesurface_wallmodel, air_flow_levelset;
 } vfs_params;
 
 typedef struct vfs_ctx vfs_ctx;
@@ -86,6 +90,10 @@ typedef struct vfs_ctx vfs_ctx;
 typedef int (*vfs_halo_fn)(void *user, int nfields, const int *scalar_ids);
 
 int vfs_create(const vfs_params *p, vfs_ctx **out);
+/* helpers for host glue that does not link the CUDA runtime itself: page-locked staging memory, visible devices */
+void *vfs_host_alloc(unsigned long bytes);
+void vfs_host_free(void *p);
+int vfs_device_count(void);
 int vfs_destroy(vfs_ctx *c);
 const char *vfs_last_error(vfs_ctx *c);          /* c may be NULL: last create() error      */
 int vfs_set_params(vfs_ctx *c, const vfs_params *p); /* update run-time switches (ti, dt, ...) */
@@ -100,6 +108,9 @@ int vfs_nccl_unique_id(char *out128);
 int vfs_nccl_init(vfs_ctx *c, const char *id128);
 /* number of k-halo exchanges performed by this context (and bytes sent, if bytes != NULL) */
 long vfs_halo_count(vfs_ctx *c, long *bytes);
+/* inside a halo callback: how many ghost planes below (lo) / above (hi) the slab the exchange in progress must fill
+ * (the fields are read no deeper before their next refresh; G, the full ghost width, is always valid) */
+int vfs_halo_layers(vfs_ctx *c, int *lo, int *hi);
 int vfs_sync(vfs_ctx *c);
 
 /* layout[0..7] = G (ghost width), pitch, ny (=my+2G), nzt (=nzl+2G), plane doubles (=ny*pitch),
@@ -108,7 +119,7 @@ int vfs_layout(vfs_ctx *c, long *layout8);
 int vfs_field_scalar_id(vfs_ctx *c, int field, int comp);  /* public field -> internal scalar  */
 void *vfs_scalar_ptr(vfs_ctx *c, int scalar_id);           /* device pointer of padded scalar  */
 
-/* host <-> device, host layout [nzl][my][mx][dof] */
+/* host <-> device, host layout [nzl][my][mx][dof]; `host` may also be a device pointer (unified addressing) */
 int vfs_upload(vfs_ctx *c, int field, const double *host);
 int vfs_download(vfs_ctx *c, int field, double *host);
 /* refresh ghosts (i/j wrap + k halo) of one public field, as DAGlobalToLocal would */
@@ -141,20 +152,20 @@ int vfs_formfunction_snes_dev(vfs_ctx *c);
 int vfs_rhs_les_fused(vfs_ctx *c);
 
 /* Device-resident implicit momentum solve: replaces the SNESSolve of Implicit_MatrixFree
- * (Source/implicitsolver.c:4203-4302) — SNES trust region + Eisenstat-Walker v3, matrix-free Jacobian by forward
+ * (Source/implicitsolver.c:4203-4299) — SNES trust region + Eisenstat-Walker v3, matrix-free Jacobian by forward
  * differences of FormFunction_SNES, restarted GMRES without preconditioner.  In/out: VFS_UCONT on the device
- * (U = Ucont before, Ucont = U after, :4300,4310); the Krylov basis and all work vectors stay in HBM, dot products
+ * (U = Ucont before, Ucont = U after, :4297,4307); the Krylov basis and all work vectors stay in HBM, dot products
  * are summed over the ranks with ncclAllReduce (needs vfs_nccl_init when nranks > 1).  PETSc 3.1, where the
  * reference's solver lives, is not part of the reference tree: its published algorithms are restated
  * (vfs-wind_b200/csrc/vfs_solver.h). */
 typedef struct vfs_solver_params {
-  int max_newton;                       /* SNESSetTolerances maxit = 50            implicitsolver.c:4257 */
+  int max_newton;                       /* SNESSetTolerances maxit = 50            implicitsolver.c:4254 */
   int restart;                          /* KSPGMRES restart (PETSc default 30)                            */
   int max_krylov;                       /* KSPSetTolerances maxits = 1000          implicitsolver.c:4279 */
-  double snes_atol, snes_rtol, snes_stol;   /* SNESSetTolerances(PETSC_DEFAULT, imp_free_tol, ...) :4257 */
+  double snes_atol, snes_rtol, snes_stol;   /* SNESSetTolerances(PETSC_DEFAULT, imp_free_tol, ...) :4254 */
   double ksp_rtol, ksp_atol, ksp_dtol;  /* KSPSetTolerances(imp_free_tol, ...) :4277; rtol superseded by Eisenstat-Walker */
-  int use_ew;                           /* SNESKSPSetUseEW + version 3             implicitsolver.c:4254-4255 */
-  int trust_region;                     /* 1 = SNESTR (:4251); 0 = full Newton steps                       */
+  int use_ew;                           /* SNESKSPSetUseEW + version 3             implicitsolver.c:4251-4252 */
+  int trust_region;                     /* 1 = SNESTR (:4247); 0 = full Newton steps                       */
 } vfs_solver_params;
 typedef struct vfs_solver_info {
   int newton_iterations, krylov_iterations, residual_evals;
@@ -166,6 +177,8 @@ typedef struct vfs_solver_info {
 } vfs_solver_info;
 int vfs_solver_defaults(vfs_solver_params *p);
 int vfs_momentum_solve(vfs_ctx *c, const vfs_solver_params *p, vfs_solver_info *info);
+/* free the Krylov basis and work vectors (restart + 8 vectors of nzl*my*mx*3 doubles, kept between solves) */
+int vfs_momentum_release(vfs_ctx *c);
 
 /* number of kernels launched by this context since creation (bench `gpu_launches`) */
 long vfs_launch_count(vfs_ctx *c);
@@ -186,6 +199,7 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *   9  overlap the k-face-flux and Fp halo exchanges with interior planes (default 1; nranks > 1 with vfs_nccl_init)
  *  11  asynchronous compute-only entry points (vfs_contra2cart, vfs_ib_bc, vfs_les_cs, vfs_les_nut return once their work
  *      is queued; default 0): a following vfs_formfunction_snes then copies X while those kernels still run
+ *  14  exchange only the ghost layers each refresh is read at (default 1; 0 = always the full ghost width G)
  *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 

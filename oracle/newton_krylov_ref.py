@@ -2,9 +2,9 @@
 
 The reference solves its implicit momentum step with PETSc 3.1 (Source/makefile:26-28 names the
 version; PETSc is an external dependency, absent from /root/reference): Implicit_MatrixFree,
-Source/implicitsolver.c:4203-4302, sets up SNESTR (:4251) with Eisenstat-Walker version 3 (:4254-4255),
-a matrix-free Jacobian (MatCreateSNESMF, :4246), GMRES without preconditioner (:4264,4274) and the
-tolerances of :4257 / :4277-4279.  The published PETSc 3.1 algorithms are restated here in numpy:
+Source/implicitsolver.c:4203-4299, sets up SNESTR (:4251) with Eisenstat-Walker version 3 (:4251-4252),
+a matrix-free Jacobian (MatCreateSNESMF, :4242), GMRES without preconditioner (:4260,4273) and the
+tolerances of :4254 / :4277-4279.  The published PETSc 3.1 algorithms are restated here in numpy:
 
   SNESSolve_TR           src/snes/impls/tr/tr.c      trust region, More' step-length test on the Krylov iterates
   MatMFFD "wp"           src/mat/impls/mffd/wp.c     h = error_rel * sqrt(1 + |u|) / |a|, error_rel = sqrt(eps)

@@ -32,6 +32,7 @@ typedef int MPI_Op;
 #define PETSC_COMM_SELF 1
 #define MPI_DOUBLE 1
 #define MPI_INT 2
+#define MPI_CHAR 3
 #define MPI_SUM 1
 #define MPI_MAX 2
 #define MPI_MIN 3

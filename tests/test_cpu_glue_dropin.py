@@ -37,9 +37,27 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     err = {}
     for nm in ("lCsi", "lEta", "lZet", "lAj", "lICsi", "lJEta", "lKZet", "lIAj", "lKAj"):
         err["FormMetrics_" + nm] = pc.relerr(glue.owned(nm)[1:-1, 1:-1, 1:-1], ref.owned(nm)[1:-1, 1:-1, 1:-1])
+    # side outputs of FormMetrics read by host code outside the path (metrics.c:89-107, 420-497)
+    for nm in ("Cent", "lCent", "GridSpace", "lGridSpace"):
+        err["FormMetrics_" + nm] = pc.relerr(glue.view(nm), ref.view(nm))
     ref.Contra2Cart(); glue.Contra2Cart()
     err["Contra2Cart_Ucat"] = pc.relerr(glue.owned("Ucat"), ref.owned("Ucat"))
     err["Contra2Cart_lUcat_ghosts"] = pc.relerr(glue.view("lUcat"), ref.view("lUcat"))
+    # The host rewrites Ucat at IB / solid cells and boundary nodes between two calls (FormBCS, ibm_interpolation_advanced,
+    # implicitsolver.c:4406-4444) WITHOUT the once-per-step invalidate: the reference keeps those values where no rule
+    # touches them, so must the glue.
+    rng = np.random.default_rng(7)
+    nvm = np.array(ref.owned("Nvert")) > 0.1
+    bnd = np.zeros(nvm.shape, bool)
+    bnd[0] = bnd[-1] = True; bnd[:, 0] = bnd[:, -1] = True; bnd[:, :, 0] = bnd[:, :, -1] = True
+    sel = nvm | bnd
+    bump = 0.01 * rng.uniform(-1, 1, np.array(ref.owned("Ucat")).shape)
+    for d in (ref, glue):
+        u = np.array(d.owned("Ucat")); u[sel] += bump[sel]
+        d.set_owned("Ucat", u)
+        d.Contra2Cart()
+    err["Contra2Cart_2nd_call_Ucat"] = pc.relerr(glue.owned("Ucat"), ref.owned("Ucat"))
+    err["Contra2Cart_2nd_call_lUcat"] = pc.relerr(glue.view("lUcat"), ref.view("lUcat"))
     if any(b in (-1, -2) for b in cfg["bctype"][:4]):
         err["Contra2Cart_lUstar"] = pc.relerr(np.array(glue.owned("lUstar"))[1:-1, 1:-1, 1:-1], np.array(ref.owned("lUstar"))[1:-1, 1:-1, 1:-1])
     ref.Compute_Smagorinsky_Constant_1(); glue.Compute_Smagorinsky_Constant_1()
@@ -76,6 +94,25 @@ def run_dropin(refdrv, pkg, so_name, cfg):
         gd.lib().vfs_glue_invalidate(C.c_void_p(glue.u)) if d is glue else None
         d.FormFunction_SNES("X", "F")
     err["FormFunction_SNES_F"] = pc.relerr(glue.view("F"), ref.view("F"))
+    # side effects of FormFunction_SNES on the UserCtx Vecs (momentum.c:2240-2295), read by the reference right after
+    # SNESSolve (implicitsolver.c:4360-4376, 4440): materialised by the documented vfs_glue_sync_state call
+    gd.lib().vfs_glue_sync_state(C.c_void_p(glue.u))
+    for nm in ("Ucont", "Ucat", "Nvert"):
+        err["SNES_side_effect_" + nm] = pc.relerr(glue.view(nm), ref.view(nm))
+    err["SNES_side_effect_lUcat"] = pc.relerr(glue.view("lUcat"), ref.view("lUcat"))
+    err["SNES_side_effect_lNvert"] = pc.relerr(glue.owned("lNvert"), ref.owned("lNvert"))
+    a, b = np.array(glue.owned("lUcont")), np.array(ref.owned("lUcont"))
+    err["SNES_side_effect_lUcont"] = pc.relerr(a[nb < 2], b[nb < 2])
+    # the same with the eager switch: every evaluation mirrors its side effects, no explicit sync
+    gd.lib().vfs_glue_set_eager(1)
+    x2 = x * (1.0 + 1e-3)
+    for d in (ref, glue):
+        d.view("X")[...] = x2
+        d.FormFunction_SNES("X", "F")
+    gd.lib().vfs_glue_set_eager(0)
+    err["eager_F"] = pc.relerr(glue.view("F"), ref.view("F"))
+    for nm in ("Ucont", "Ucat"):
+        err["eager_side_effect_" + nm] = pc.relerr(glue.view(nm), ref.view(nm))
     gd.lib().vfs_glue_release(C.c_void_p(glue.u))
     return err
 
@@ -92,4 +129,66 @@ def test_glue_dropin_emulated(pkg, refdrv, name, dims):
         cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     err = run_dropin(refdrv, pkg, "libvfsglue_emu.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def run_glue_solver(refdrv, pkg, so_name, cfg):
+    """vfs_glue_snes_solve — the one-line replacement of SNESSolve in Implicit_MatrixFree (implicitsolver.c:4299) —
+    against the numpy restatement of the PETSc algorithms driving the REFERENCE residual; also the UserCtx Vecs it
+    leaves behind (Ucont, Ucat) against the reference's after its last residual evaluation."""
+    import importlib.util
+    import newton_krylov_ref as nk
+    so = os.path.join(pc.ROOT, "oracle", "_ref", so_name)
+    if not os.path.exists(so):
+        pytest.skip(so_name + " not built")
+    spec = importlib.util.spec_from_file_location("refdrv_glue2", os.path.join(pc.ROOT, "oracle", "refdrv.py"))
+    gd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gd)
+    gd.SO = so
+    gd._GLOBALS_JSON = os.path.join(pc.ROOT, "oracle", "_ref", "globals_glue_%s.json" % so_name.split("_")[1].split(".")[0])
+    ref, xyz, fields, met = pc.ref_setup(cfg, refdrv)
+    glue, _, _, _ = pc.ref_setup(cfg, gd)
+    ref.new_vec("X", 3, False); ref.new_vec("F", 3, False)
+    for nm in ("RHS_o", "dP", "F_eul"):
+        ref.view(nm)[...] = 0
+    ref.Contra2Cart(); ref.Compute_Smagorinsky_Constant_1(); ref.Compute_eddy_viscosity_LES()
+    ref.view("X")[...] = fields["ucont"]
+    ref.FormFunction_SNES("X", "F")
+    live = (np.array(ref.view("F")) != 0).astype(float)          # see tests/solver_common.py
+    for key, nm in (("rhs_o", "RHS_o"), ("dp", "dP"), ("f_eul", "F_eul")):
+        for d in (ref, glue):
+            d.set_owned(nm, fields[key] * live)
+    for d in (ref, glue):
+        d.set_owned("Ucont", fields["ucont"]); d.global_to_local("Ucont", "lUcont")
+        d.set_owned("Ucat", fields["ucat"]); d.global_to_local("Ucat", "lUcat")
+        d.Contra2Cart(); d.Compute_Smagorinsky_Constant_1(); d.Compute_eddy_viscosity_LES()
+
+    def residual(x):
+        ref.view("X")[...] = x
+        ref.FormFunction_SNES("X", "F")
+        return np.array(ref.view("F"))
+    u_ref, info_ref = nk.snes_tr(residual, fields["ucont"])
+    residual(u_ref)                                               # the reference's Vecs after its last evaluation
+    L = gd.lib()
+    sp = pkg.capi.VfsSolverParams(); info = pkg.capi.VfsSolverInfo()
+    emu_or_cuda = C.CDLL(os.path.join(pc.ROOT, "tests", "emu", "libvfs_emu.so") if "emu" in so_name else pkg.capi.LIB_PATH)
+    emu_or_cuda.vfs_solver_defaults(C.byref(sp))
+    glue.new_vec("U", 3, False)
+    glue.view("U")[...] = fields["ucont"]
+    L.vfs_glue_invalidate(C.c_void_p(glue.u))
+    L.vfs_glue_snes_solve.restype = C.c_double
+    fn = L.vfs_glue_snes_solve(C.c_void_p(glue.u), C.c_void_p(glue.vec("U")), C.byref(sp), C.byref(info))
+    err = {"U": pc.relerr(glue.view("U"), u_ref), "fnorm": abs(fn - info_ref["fnorm_history"][-1]) / info_ref["fnorm_history"][0],
+           "krylov_its_differ": float([info.ksp_its_history[q] for q in range(info.n_history - 1)] != info_ref["ksp_its_history"]),
+           "Ucont": pc.relerr(glue.view("Ucont"), ref.view("Ucont")), "Ucat": pc.relerr(glue.view("Ucat"), ref.view("Ucat"))}
+    L.vfs_glue_release(C.c_void_p(glue.u))
+    return err
+
+
+def test_glue_snes_solve_emulated(pkg, refdrv):
+    import emu_loader
+    emu_loader.build()
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15)
+    err = run_glue_solver(refdrv, pkg, "libvfsglue_emu.so", cfg)
+    bad = {k: v for k, v in err.items() if not (v <= 1e-10)}
     assert not bad, bad

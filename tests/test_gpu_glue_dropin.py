@@ -11,3 +11,11 @@ def test_glue_dropin_cuda(pkg, refdrv, name, dims):
     err = run_dropin(refdrv, pkg, "libvfsglue_cuda.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
+
+
+def test_glue_snes_solve_cuda(pkg, refdrv):
+    from test_cpu_glue_dropin import run_glue_solver
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 29, 21, 25)
+    err = run_glue_solver(refdrv, pkg, "libvfsglue_cuda.so", cfg)
+    bad = {k: v for k, v in err.items() if not (v <= 1e-10)}
+    assert not bad, bad

@@ -7,7 +7,7 @@ from . import capi, cases, petsc_io, selfcheck  # noqa: F401
 
 
 def __getattr__(name):
-    if name == "halo":            # imports torch; only needed for multi-GPU runs
+    if name in ("halo", "cases_device"):            # import torch; only needed for multi-GPU runs / large on-device cases
         import importlib
-        return importlib.import_module(__name__ + ".halo")
+        return importlib.import_module(__name__ + "." + name)
     raise AttributeError(name)

@@ -23,7 +23,7 @@ EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_download_async", "vfs_download_wait",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms",
-           "vfs_solver_defaults", "vfs_momentum_solve", "vfs_set_option"]
+           "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count"]
 
 
 class VfsParams(C.Structure):
@@ -33,7 +33,8 @@ class VfsParams(C.Structure):
                                        "viscosity_wallmodel", "wallfunction", "rotor_model", "nacelle_model", "IB_delta",
                                        "ti", "tistart", "rstart_flg", "levelset", "rans", "inviscid", "skew", "movefsi", "rotatefsi",
                                        "i_periodic", "j_periodic", "k_periodic", "i_homo_filter", "j_homo_filter", "k_homo_filter")] + \
-               [(n, C.c_double) for n in ("ren", "dt", "max_cs", "roughness_size")]
+               [(n, C.c_double) for n in ("ren", "dt", "max_cs", "roughness_size")] + \
+               [(n, C.c_int) for n in ("levelset_weno", "freesurface_wallmodel", "air_flow_levelset")]
 
 
 class VfsSolverParams(C.Structure):
@@ -89,8 +90,10 @@ def _bind(lib):
     lib.vfs_last_ms.restype = C.c_double
     if hasattr(lib, "vfs_set_option"):
         lib.vfs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.vfs_halo_layers.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vfs_solver_defaults.argtypes = [C.POINTER(VfsSolverParams)]
     lib.vfs_momentum_solve.argtypes = [C.c_void_p, C.POINTER(VfsSolverParams), C.POINTER(VfsSolverInfo)]
+    lib.vfs_momentum_release.argtypes = [C.c_void_p]
     return lib
 
 
@@ -207,6 +210,12 @@ class VfsContext:
         dist.broadcast(t, src=0)
         self._ck(self.lib.vfs_nccl_init(self.h, bytes(t.cpu().tolist())))
 
+    def halo_layers(self):
+        """(lo, hi) ghost planes the exchange in progress must fill (valid inside a halo callback)."""
+        lo, hi = C.c_int(0), C.c_int(0)
+        self.lib.vfs_halo_layers(self.h, C.byref(lo), C.byref(hi))
+        return int(lo.value), int(hi.value)
+
     def halo_count(self):
         b = C.c_long(0)
         n = self.lib.vfs_halo_count(self.h, C.byref(b))
@@ -292,7 +301,7 @@ class VfsContext:
         self._ck(self.lib.vfs_formfunction_snes_dev(self.h))
 
     def momentum_solve(self, max_newton=None, max_krylov=None, restart=None, rtol=None, atol=None, ksp_rtol=None, use_ew=None, trust_region=None):
-        """Implicit_MatrixFree's SNESSolve on the device (Source/implicitsolver.c:4203-4302): VFS_UCONT in/out.
+        """Implicit_MatrixFree's SNESSolve on the device (Source/implicitsolver.c:4203-4299): VFS_UCONT in/out.
         Defaults are the reference's / PETSc's; returns the vfs_solver_info fields as a dict."""
         sp = VfsSolverParams()
         self.lib.vfs_solver_defaults(C.byref(sp))
@@ -306,6 +315,9 @@ class VfsContext:
         out["fnorm_history"] = [info.fnorm_history[q] for q in range(info.n_history)]
         out["ksp_its_history"] = [info.ksp_its_history[q] for q in range(max(0, min(16, info.n_history - 1)))]
         return out
+
+    def momentum_release(self):
+        self._ck(self.lib.vfs_momentum_release(self.h))
 
     def rhs_les_fused(self):
         self._ck(self.lib.vfs_rhs_les_fused(self.h))

@@ -77,7 +77,8 @@ struct vfs_ctx {
   double *pool = nullptr;        // all scalars, contiguous
   double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
   double *stage_x = nullptr;     // staging of vfs_formfunction_snes' X, filled on the upload stream (allocated on first use)
-  double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use
+  double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use (sized for the field)
+  size_t stage_async_bytes[2] = {0, 0};
   long scalar_len = 0;
   cudaStream_t stream = 0;
   bool own_stream = false;
@@ -132,6 +133,9 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
+  int halo_trim = 1;             // exchange only the ghost layers each refresh is read at (option key 14); 0: always G layers
+  int cur_lo = VFS_G, cur_hi = VFS_G;   // layers of the exchange in progress (vfs_halo_layers)
+  int *d_flag = nullptr;         // device scratch flag (has_solid scan)
   int fp_fused = 0;              // Fp evaluated inside the projection kernel (ProjFpMarch) instead of FpCell + Fp planes in HBM (option key 12;
                                  // bitwise the staged result, measured slower on B200: 2.20 vs 0.72 + 0.76 ms at 256^3, gpurun_out r02a)
 };
@@ -258,23 +262,21 @@ static int wrap_ij(vfs_ctx *c, const Grp &g, int ka = 0, int kb = -1) {
 // unpacked into the ghost planes.  With lo == hi (2 ranks, periodic k) the first send to the peer pairs
 // with the peer's first receive: [send hi, send lo, recv lo, recv hi] on both sides is consistent.
 struct HaloPtrs { double *s[VFS_MAXGRP]; };
-__global__ void k_halo_pack(HaloPtrs P, int n, long cnt, long off_hi, long off_lo, double2 *__restrict__ buf_hi, double2 *__restrict__ buf_lo) {
-  const long c2 = cnt / 2, tot = (long)n * c2;
+// one message: n scalars x cnt doubles, scalar q's block taken from / stored to P.s[q] + off
+__global__ void k_halo_copy(HaloPtrs P, int n, long cntA, long offA, double2 *__restrict__ bufA, long cntB, long offB, double2 *__restrict__ bufB, int unpack) {
+  const long a2 = bufA ? cntA / 2 : 0, b2 = bufB ? cntB / 2 : 0, totA = (long)n * a2, tot = totA + (long)n * b2;
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
-    const int q = (int)(t / c2); const long e = t - (long)q * c2;
-    if (buf_hi) buf_hi[t] = reinterpret_cast<const double2 *>(P.s[q] + off_hi)[e];
-    if (buf_lo) buf_lo[t] = reinterpret_cast<const double2 *>(P.s[q] + off_lo)[e];
+    const bool isA = t < totA;
+    const long u = isA ? t : t - totA, c2 = isA ? a2 : b2;
+    const int q = (int)(u / c2); const long e = u - (long)q * c2;
+    double2 *g = reinterpret_cast<double2 *>(P.s[q] + (isA ? offA : offB)) + e;
+    double2 *b = (isA ? bufA : bufB) + u;
+    if (unpack) *g = *b; else *b = *g;
   }
 }
-__global__ void k_halo_unpack(HaloPtrs P, int n, long cnt, long off_hi, long off_lo, const double2 *__restrict__ buf_hi, const double2 *__restrict__ buf_lo) {
-  const long c2 = cnt / 2, tot = (long)n * c2;
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
-    const int q = (int)(t / c2); const long e = t - (long)q * c2;
-    if (buf_hi) reinterpret_cast<double2 *>(P.s[q] + off_hi)[e] = buf_hi[t];
-    if (buf_lo) reinterpret_cast<double2 *>(P.s[q] + off_lo)[e] = buf_lo[t];
-  }
-}
-static int nccl_halo(vfs_ctx *c, const Grp &g, bool seam_only) {
+// nlo / nhi: ghost planes to fill below / above the slab (every rank uses the same pair for a given exchange): the
+// hi neighbour receives my top nlo planes into its low ghosts, the lo neighbour my bottom nhi planes into its high ghosts
+static int nccl_halo(vfs_ctx *c, const Grp &g, bool seam_only, int nlo, int nhi) {
   NcclApi &N = nccl_api();
   const VfsDev &d = c->d;
   const int r = c->prm.rank, n = c->prm.nranks;
@@ -284,38 +286,48 @@ static int nccl_halo(vfs_ctx *c, const Grp &g, bool seam_only) {
     if (r < n - 1) hi = -1;
     if (lo < 0 && hi < 0) return 0;
   }
-  const long cnt = (long)VFS_G * d.sk;                       // doubles per scalar and side (sk is a multiple of 16)
+  const long cmax = (long)VFS_G * d.sk;                      // doubles per scalar and side at full width (sk is a multiple of 16)
   if (!c->hbuf) {
-    CK(cudaMalloc((void **)&c->hbuf, (size_t)4 * VFS_MAXGRP * cnt * sizeof(double)));
+    CK(cudaMalloc((void **)&c->hbuf, (size_t)4 * VFS_MAXGRP * cmax * sizeof(double)));
   }
-  double *sb_hi = c->hbuf, *sb_lo = c->hbuf + (size_t)VFS_MAXGRP * cnt, *rb_lo = c->hbuf + (size_t)2 * VFS_MAXGRP * cnt, *rb_hi = c->hbuf + (size_t)3 * VFS_MAXGRP * cnt;
+  double *sb_hi = c->hbuf, *sb_lo = c->hbuf + (size_t)VFS_MAXGRP * cmax, *rb_lo = c->hbuf + (size_t)2 * VFS_MAXGRP * cmax, *rb_hi = c->hbuf + (size_t)3 * VFS_MAXGRP * cmax;
   HaloPtrs P; for (int q = 0; q < g.n; q++) P.s[q] = c->d.s[g.sid[q]];
-  const size_t msg = (size_t)g.n * cnt;
+  const long cnt_lo = (long)nlo * d.sk, cnt_hi = (long)nhi * d.sk;
+  const size_t msg_up = (size_t)g.n * cnt_lo, msg_dn = (size_t)g.n * cnt_hi;      // to the hi neighbour / to the lo neighbour
   const int blocks = 148 * 4;
-  k_halo_pack<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt, (long)d.nzl * d.sk, (long)VFS_G * d.sk, hi >= 0 ? (double2 *)sb_hi : nullptr, lo >= 0 ? (double2 *)sb_lo : nullptr);
+  // pack: top nlo owned planes -> sb_hi, bottom nhi owned planes -> sb_lo
+  k_halo_copy<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt_lo, (long)(VFS_G + d.nzl - nlo) * d.sk, hi >= 0 ? (double2 *)sb_hi : nullptr,
+                                             cnt_hi, (long)VFS_G * d.sk, lo >= 0 ? (double2 *)sb_lo : nullptr, 0);
   ncclResult_t e = N.GroupStart();
-  if (hi >= 0 && e == ncclSuccess) e = N.Send(sb_hi, msg, ncclDouble, hi, c->comm, c->stream);
-  if (lo >= 0 && e == ncclSuccess) e = N.Send(sb_lo, msg, ncclDouble, lo, c->comm, c->stream);
-  if (lo >= 0 && e == ncclSuccess) e = N.Recv(rb_lo, msg, ncclDouble, lo, c->comm, c->stream);
-  if (hi >= 0 && e == ncclSuccess) e = N.Recv(rb_hi, msg, ncclDouble, hi, c->comm, c->stream);
+  if (hi >= 0 && e == ncclSuccess) e = N.Send(sb_hi, msg_up, ncclDouble, hi, c->comm, c->stream);
+  if (lo >= 0 && e == ncclSuccess) e = N.Send(sb_lo, msg_dn, ncclDouble, lo, c->comm, c->stream);
+  if (lo >= 0 && e == ncclSuccess) e = N.Recv(rb_lo, msg_up, ncclDouble, lo, c->comm, c->stream);
+  if (hi >= 0 && e == ncclSuccess) e = N.Recv(rb_hi, msg_dn, ncclDouble, hi, c->comm, c->stream);
   ncclResult_t e2 = N.GroupEnd();
   if (e == ncclSuccess) e = e2;
   if (e != ncclSuccess) { set_err(c, std::string("NCCL halo exchange: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
-  k_halo_unpack<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt, (long)(d.nzl + VFS_G) * d.sk, 0L, hi >= 0 ? (const double2 *)rb_hi : nullptr, lo >= 0 ? (const double2 *)rb_lo : nullptr);
+  // unpack: rb_lo -> ghost planes [-nlo, 0), rb_hi -> ghost planes [nzl, nzl + nhi)
+  k_halo_copy<<<blocks, 256, 0, c->stream>>>(P, g.n, cnt_lo, (long)(VFS_G - nlo) * d.sk, lo >= 0 ? (double2 *)rb_lo : nullptr,
+                                             cnt_hi, (long)(VFS_G + d.nzl) * d.sk, hi >= 0 ? (double2 *)rb_hi : nullptr, 1);
   CK(cudaGetLastError());
-  c->halo_exchanges++; c->halo_bytes += (long)msg * 8 * ((hi >= 0) + (lo >= 0));
+  c->halo_exchanges++; c->halo_bytes += (long)8 * ((hi >= 0 ? msg_up : 0) + (lo >= 0 ? msg_dn : 0));
   c->launches += 3;
   return 0;
 }
 #endif
-static int halo_k(vfs_ctx *c, const Grp &g, bool seam_only = false) {
+// lo / hi: how many ghost planes below / above the slab the refreshed field is read at before its next refresh
+// (1-2 layers for most fields); G when trimming is off.  A host callback learns them from vfs_halo_layers.
+static int halo_k(vfs_ctx *c, const Grp &g, bool seam_only = false, int lo = VFS_G, int hi = VFS_G) {
   const VfsDev &d = c->d;
+  if (!c->halo_trim) lo = hi = VFS_G;
   if (c->prm.nranks > 1) {
 #ifndef VFS_EMU
-    if (c->comm) return nccl_halo(c, g, seam_only);
+    if (c->comm) return nccl_halo(c, g, seam_only, lo, hi);
 #endif
     if (!c->halo_fn) { set_err(c, "nranks > 1 but neither vfs_nccl_init nor a halo callback was set up"); return VFS_ERR_HALO; }
+    c->cur_lo = lo; c->cur_hi = hi;
     int r = c->halo_fn(c->halo_user, g.n, g.sid);
+    c->cur_lo = c->cur_hi = VFS_G;
     if (r) { set_err(c, "halo callback failed"); return VFS_ERR_HALO; }
     c->halo_exchanges++;
     return 0;
@@ -323,6 +335,7 @@ static int halo_k(vfs_ctx *c, const Grp &g, bool seam_only = false) {
   if (d.perz) { WrapFill f = {d, g, 2}; Box b = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, 0, 2 * VFS_G}; RUN(launch(c, b, f)); }
   return 0;
 }
+extern "C" int vfs_halo_layers(vfs_ctx *c, int *lo, int *hi) { if (!c || !lo || !hi) return VFS_ERR_ARG; *lo = c->cur_lo; *hi = c->cur_hi; return 0; }
 #ifndef VFS_EMU
 template <class F> __global__ void __launch_bounds__(256) k_linear(F f, long n) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,17 +373,18 @@ static bool can_overlap(const vfs_ctx *c) {
   (void)c; return false;
 #endif
 }
-static int ovl_exchange(vfs_ctx *c, const Grp &g) {
+static int ovl_exchange(vfs_ctx *c, const Grp &g, int lo = VFS_G, int hi = VFS_G) {
 #ifndef VFS_EMU
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
   cudaStream_t main_stream = c->stream;
   c->stream = c->side;
-  const int r = nccl_halo(c, g, false);
+  if (!c->halo_trim) lo = hi = VFS_G;
+  const int r = nccl_halo(c, g, false, lo, hi);
   c->stream = main_stream;
   return r;
 #else
-  (void)c; (void)g; return VFS_ERR_UNSUPPORTED;
+  (void)c; (void)g; (void)lo; (void)hi; return VFS_ERR_UNSUPPORTED;
 #endif
 }
 // Thin-slab launches that are independent of a big kernel queued right before them run on the side stream,
@@ -402,9 +416,9 @@ static int ovl_join(vfs_ctx *c) {
   (void)c; return 0;
 }
 // DAGlobalToLocal / DALocalToLocal
-static int g2l(vfs_ctx *c, const Grp &g) {
+static int g2l(vfs_ctx *c, const Grp &g, int lo = VFS_G, int hi = VFS_G) {
   if (c->prm.nranks == 1 && c->fuse_refresh) return refresh_fused(c, g, 1);
-  RUN(wrap_ij(c, g)); return halo_k(c, g);
+  RUN(wrap_ij(c, g)); return halo_k(c, g, false, lo, hi);
 }
 // The refresh that follows a node_copy of a field whose ghosts were refreshed just before it: the
 // copy has already been applied to the ghost planes of interior slab boundaries (see node_copy), so
@@ -433,6 +447,7 @@ static int check_params(const vfs_params *p, std::string &why) {
   if (p->i_periodic || p->j_periodic || p->k_periodic) { why = "legacy i/j/k_periodic not supported (use ii/jj/kk_periodic)"; return VFS_ERR_UNSUPPORTED; }
   if (p->i_homo_filter || p->j_homo_filter || p->k_homo_filter) { why = "homogeneous-plane Cs averaging not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
+  if (p->levelset_weno || p->freesurface_wallmodel || p->air_flow_levelset) { why = "levelset_weno / freesurface_wallmodel / air_flow_levelset reroute the flux and wall-model code in the reference (momentum.c:754,1015,1301) and are not built"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 0; q < 6; q++) if (p->bctype[q] == 11) { why = "cylinder inflow boundary type 11 not supported"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 4; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2) { why = "wall-function boundary types (-1,-2) on a k side: Contra2Cart_2 has no velocity rule for them (rhs.c:311-440)"; return VFS_ERR_UNSUPPORTED; }
@@ -501,6 +516,28 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   return 0;
 }
 
+extern "C" void *vfs_host_alloc(unsigned long bytes) {
+#ifndef VFS_EMU
+  void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+#else
+  return malloc(bytes);
+#endif
+}
+extern "C" void vfs_host_free(void *p) {
+#ifndef VFS_EMU
+  if (p) cudaFreeHost(p);
+#else
+  free(p);
+#endif
+}
+extern "C" int vfs_device_count(void) {
+#ifndef VFS_EMU
+  int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+#else
+  return 1;
+#endif
+}
+
 extern "C" int vfs_destroy(vfs_ctx *c) {
   if (!c) return VFS_ERR_ARG;
 #ifndef VFS_EMU
@@ -520,12 +557,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near);
+  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage); free(c->wm_table); free(c->near);
+  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag);
 #endif
   delete c; return 0;
 }
@@ -625,6 +662,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 9) c->overlap = value;
   else if (key == 11) c->async_api = value;
   else if (key == 12) c->fp_fused = value;
+  else if (key == 14) c->halo_trim = value;
   graph_reset(c);
   return 0;
 }
@@ -656,10 +694,11 @@ template <class F> static int run_graphed(vfs_ctx *c, int key, F body) {
 }
 
 // ---- transfers ------------------------------------------------------------------------------------
+struct HasSolid { VfsDev d; int *flag; VFS_HD void operator()(int i, int j, int k) const { if ((int)(d.s[S_NV][d.idx(i, j, k)] + 0.1) == 3) *flag = 1; } };
 static int h2d_stage(vfs_ctx *c, const double *host, int dof) {
   size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * dof * sizeof(double);
 #ifndef VFS_EMU
-  CK(cudaMemcpyAsync(c->stage, host, n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->stage, host, n, cudaMemcpyDefault, c->stream));      // `host` may also be a device pointer (unified addressing)
 #else
   memcpy(c->stage, host, n);
 #endif
@@ -668,7 +707,7 @@ static int h2d_stage(vfs_ctx *c, const double *host, int dof) {
 static int d2h_stage(vfs_ctx *c, double *host, int dof) {
   size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * dof * sizeof(double);
 #ifndef VFS_EMU
-  CK(cudaMemcpyAsync(host, c->stage, n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(host, c->stage, n, cudaMemcpyDefault, c->stream));
   CK(cudaStreamSynchronize(c->stream));
 #else
   memcpy(host, c->stage, n);
@@ -685,16 +724,32 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   if (field == VFS_NVERT) { c->near_valid = false; c->wall_marked = false; }
-  if (field == VFS_NVERT) {       // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep
-    const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx;
-    bool any = false;
-    for (size_t q = 0; q < n && !any; q++) any = ((int)(host[q] + 0.1) == 3);
-    c->has_solid = any;
-  }
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
   RUN(vfs_halo_exchange(c, field));
+  if (field == VFS_NVERT) {
+    // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep.  Scanned on the device over the
+    // slab AND the ghost planes Contra2Cart is replayed on (a neighbour's solid cells must be zeroed there too).
+#ifndef VFS_EMU
+    if (!c->d_flag) CK(cudaMalloc((void **)&c->d_flag, sizeof(int)));
+    CK(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+#else
+    if (!c->d_flag) c->d_flag = (int *)malloc(sizeof(int));
+    *c->d_flag = 0;
+#endif
+    HasSolid hs = {c->d, c->d_flag};
+    Box b = {0, c->d.mx, 0, c->d.my, -VFS_G, c->d.nzl + VFS_G};
+    RUN(launch(c, b, hs));
+    int any = 1;
+#ifndef VFS_EMU
+    CK(cudaMemcpyAsync(&any, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+#else
+    any = *c->d_flag;
+#endif
+    c->has_solid = any != 0;
+  }
   return vfs_sync(c);
 }
 extern "C" int vfs_download(vfs_ctx *c, int field, double *host) {
@@ -712,7 +767,8 @@ extern "C" int vfs_download_async(vfs_ctx *c, int field, double *host, int slot)
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
   }
-  if (!c->stage_async[slot]) CK(cudaMalloc((void **)&c->stage_async[slot], (size_t)c->d.nzl * c->d.my * c->d.mx * 3 * sizeof(double)));
+  if (c->stage_async[slot] && c->stage_async_bytes[slot] < n) { CK(cudaStreamSynchronize(c->copy_stream)); cudaFree(c->stage_async[slot]); c->stage_async[slot] = nullptr; }
+  if (!c->stage_async[slot]) { CK(cudaMalloc((void **)&c->stage_async[slot], n)); c->stage_async_bytes[slot] = n; }
   PackAoS f = {c->d, c->stage_async[slot], FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
   CK(cudaEventRecord(c->ev_pack, c->stream));
@@ -867,7 +923,7 @@ static int ib_bc(vfs_ctx *c) {
       RUN(launch(c, b, f));
     }
   }
-  return g2l(c, grp(S_UC0, 3));                                      // momentum.c:2231-2232
+  return g2l(c, grp(S_UC0, 3), 2, 2);                                // momentum.c:2231-2232 (read next by the k-face fluxes: uc(-2) at the periodic seam)
 }
 extern "C" int vfs_ib_bc(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(ib_bc(c)); return api_end(c); }
 
@@ -1031,7 +1087,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     ev_rec(c, 2 * VFS_T_FP + 1);
     ev_rec(c, 2 * VFS_T_PROJECT);
     if (!ovl) {
-      RUN(halo_k(c, multi ? gall : gk));
+      RUN(halo_k(c, multi ? gall : gk, false, 3, 2));
       if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
       RUN(shell_nodes());
       RUN(march(k1, k2));
@@ -1039,7 +1095,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
       // the i/j-plane copies of the owned planes go first (they are part of what the neighbours receive); the cells
       // of local planes 2 .. nzl-4 and the Fp planes up to nzl-3 touch no k ghost plane and no seam copy
       if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, 0, d.nzl, f)); }
-      RUN(ovl_exchange(c, gall));
+      RUN(ovl_exchange(c, gall, 3, 2));
       RUN(shell_nodes());
       RUN(march(2, d.nzl - 3));
       RUN(ovl_join(c));
@@ -1059,13 +1115,13 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8;
     FpCell fp = {d};
     if (!ovl) {
-      RUN(halo_k(c, gk));
+      RUN(halo_k(c, gk, false, 3, 2));      // Fp reads faces k-2 .. k+1 (k-4 / k+3 across the periodic seam = ghost planes -3 / nzl+1)
       if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
       for (int n = 0; n < S.n; n++) RUN(launch(c, S.fp[n], fp));     // momentum.c:1548-1678
     } else {
       // Fp of a cell reads the k-face fluxes of planes k-2 .. k+1 (k-4 / k+3 across the periodic seam): the cells
       // of local planes 2 .. nzl-3 never touch a k ghost plane and run while the exchange is in flight
-      RUN(ovl_exchange(c, gk));
+      RUN(ovl_exchange(c, gk, 3, 2));
       if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, ka, kb, f)); }
       Box in = S.fp[0], lo = S.fp[0], hi = S.fp[0];
       in.k0 = in.k0 > 2 ? in.k0 : 2; in.k1 = in.k1 < d.nzl - 2 ? in.k1 : d.nzl - 2;
@@ -1084,7 +1140,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     ProjectSNES f = {d}; return launch(c, b, f);
   };
   if (!ovl_p) {
-    RUN(g2l(c, gp));
+    RUN(g2l(c, gp, 2, 2));                                            // the projection reads Fp at k+1, the seam copies at k+-2
     if (any_per(c)) RUN(node_copy(c, gp));                            // momentum.c:1687-1713
     ev_rec(c, 2 * VFS_T_PROJECT);
     for (int n = 0; n < S.n; n++) RUN(project(S.proj[n]));
@@ -1093,7 +1149,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     // neither the ghost plane nzl nor the seam copies of planes 0 / nzl-1.  The periodic node copies run twice:
     // before (their i/j part feeds the interior planes) and again after the exchange (fresh k ghosts).
     RUN(wrap_ij(c, gp));
-    RUN(ovl_exchange(c, gp));
+    RUN(ovl_exchange(c, gp, 2, 2));
     if (any_per(c)) RUN(node_copy(c, gp));
     ev_rec(c, 2 * VFS_T_PROJECT);
     Box in = S.proj[0], lo = S.proj[0], hi = S.proj[0];
@@ -1267,7 +1323,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   c->sabs_valid = true;
   RUN(run_les_derive_boundary(c));
   Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
-  RUN(g2l(c, g1));                                                    // les.c:254-267
+  RUN(g2l(c, g1, 2, 2));                                              // les.c:254-267 (pass 2 reads k+-1, the seam copies k+-2)
   // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
   // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
   if (any_per(c)) RUN(node_copy(c, grp_cat(grp(S_UF0, 3), grp(S_LU0, 9))));   // les.c:275-306
@@ -1290,7 +1346,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES2 + 1);
   Grp g2 = grp(S_LM, 2);
-  RUN(g2l(c, g2));                                                    // les.c:675-678
+  RUN(g2l(c, g2, 2, 2));                                              // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
   ev_rec(c, 2 * VFS_T_LES3);
   if (c->fused && !d.testfilter_ik) {
@@ -1313,7 +1369,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   { LesClipBoundary f = {d}; RUN(launch_shell(c, 0, d.nzl, f)); }     // les.c:967-980 (boundary nodes; interior clip is in pass 3)
   if (defer_refresh) return 0;
   Grp g3 = grp(S_CS, 1);
-  RUN(g2l(c, g3));                                                    // les.c:1026-1027
+  RUN(g2l(c, g3, 2, 2));                                              // les.c:1026-1027
   if (any_per(c)) RUN(node_copy(c, g3));
   return 0;
 }
@@ -1324,7 +1380,7 @@ static int les_nut(vfs_ctx *c, bool with_cs = false) {
   else { NuT<false> f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_NUT + 1);
   Grp g = with_cs ? grp_cat(grp(S_CS, 1), grp(S_NUT, 1)) : grp(S_NUT, 1);
-  RUN(g2l(c, g));                                                     // les.c:1320-1321 (+ 1026-1027)
+  RUN(g2l(c, g, 2, 2));                                               // les.c:1320-1321 (+ 1026-1027)
   if (any_per(c)) RUN(node_copy(c, g));
   return 0;
 }

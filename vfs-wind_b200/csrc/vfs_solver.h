@@ -1,9 +1,9 @@
 // vfs_solver.h — device-resident matrix-free Newton-Krylov momentum solve.
 //
-// Replaces the SNESSolve of Implicit_MatrixFree (Source/implicitsolver.c:4203-4302): SNES trust region
-// (SNESTR, :4251) with Eisenstat-Walker version 3 forcing (:4254-4255), a matrix-free Jacobian by forward
-// differences of FormFunction_SNES (MatCreateSNESMF, :4246-4247), restarted GMRES without preconditioner
-// (KSPGMRES / PCNONE, :4264,4274), tolerances of :4257 and :4277-4279.  The solver itself lives in PETSc 3.1
+// Replaces the SNESSolve of Implicit_MatrixFree (Source/implicitsolver.c:4203-4299): SNES trust region
+// (SNESTR, :4247) with Eisenstat-Walker version 3 forcing (:4251-4252), a matrix-free Jacobian by forward
+// differences of FormFunction_SNES (MatCreateSNESMF, :4242-4243), restarted GMRES without preconditioner
+// (KSPGMRES / PCNONE, :4260,4273), tolerances of :4254 and :4277-4279.  The solver itself lives in PETSc 3.1
 // (Source/makefile:26-28), which is NOT in the reference tree: its published algorithms are restated here —
 // SNESSolve_TR with the More' step-length test on the Krylov iterates, MatMFFD "wp" differencing
 // h = error_rel * sqrt(1 + |u|) / |a|, classical Gram-Schmidt GMRES with Givens rotations, the default
@@ -326,10 +326,12 @@ static int ks_gmres(vfs_ctx *c, const vfs_solver_params &sp, double rtol, double
   return 0;
 }
 
+extern "C" int vfs_momentum_release(vfs_ctx *c) { if (!c) return VFS_ERR_ARG; RUN(vfs_sync(c)); graph_reset(c); ks_free(c); return 0; }
+
 extern "C" int vfs_solver_defaults(vfs_solver_params *p) {
   if (!p) return VFS_ERR_ARG;
-  p->max_newton = 50; p->restart = 30; p->max_krylov = 1000;            // implicitsolver.c:4257,4279; KSPGMRES default restart
-  p->snes_atol = 1.e-50; p->snes_rtol = 1.e-8; p->snes_stol = 1.e-8;    // PETSc defaults; the reference passes imp_free_tol as rtol (:4257)
+  p->max_newton = 50; p->restart = 30; p->max_krylov = 1000;            // implicitsolver.c:4254,4279; KSPGMRES default restart
+  p->snes_atol = 1.e-50; p->snes_rtol = 1.e-8; p->snes_stol = 1.e-8;    // PETSc defaults; the reference passes imp_free_tol as rtol (:4254)
   p->ksp_rtol = 1.e-5; p->ksp_atol = 1.e-50; p->ksp_dtol = 1.e5;
   p->use_ew = 1; p->trust_region = 1;
   return 0;
@@ -349,7 +351,7 @@ extern "C" int vfs_momentum_solve(vfs_ctx *c, const vfs_solver_params *spp, vfs_
 #endif
   auto finish = [&](int r) -> int { c->use_graph = saved_graph; return r; };
 #define KS(x) do { int r_ = (x); if (r_) return finish(r_); } while (0)
-  // U = Ucont (VecCopy(user->Ucont, U), implicitsolver.c:4300)
+  // U = Ucont (VecCopy(user->Ucont, U), implicitsolver.c:4297)
   { PackAoS f = {c->d, S.U, S_UC0, 3}; KS(launch(c, box_owned(c), f)); }
   // SNESSolve_TR
   const double mu = 0.25, eta = 0.75, delta0 = 0.2, delta1 = 0.3, delta2 = 0.75, delta3 = 2.0, sigma = 1.e-4, deltatol = 1.e-12;
@@ -421,7 +423,7 @@ extern "C" int vfs_momentum_solve(vfs_ctx *c, const vfs_solver_params *spp, vfs_
     else if (ynorm < sp.snes_stol * xnorm) reason = 4;
   }
   if (!reason) reason = -5;            // SNES_DIVERGED_MAX_IT
-  // Ucont <- U (VecCopy(U, user->Ucont), implicitsolver.c:4310) with lUcont's ghosts refreshed (:4312-4313)
+  // Ucont <- U (VecCopy(U, user->Ucont), implicitsolver.c:4307) with lUcont's ghosts refreshed (:4309-4310)
   { UnpackAoS f = {c->d, S.U, S_UC0, 3}; KS(launch(c, box_owned(c), f)); }
   KS(g2l(c, grp(S_UC0, 3)));
   info->newton_iterations = newton; info->krylov_iterations = lits_total; info->residual_evals = (int)S.evals;

@@ -45,25 +45,26 @@ class TorchHalo:
     def exchange(self, ids):
         G, p = self.G, self.pool
         nzt = p.shape[1]
+        nlo, nhi = self.ctx.halo_layers()          # ghost planes to fill below / above the slab (<= G)
         idx = torch.as_tensor(ids, device=p.device, dtype=torch.long)
         ops, recvs = [], []
         # order matters when lo == hi (2 ranks, periodic): first send pairs with the peer's first recv
-        if self.hi is not None:
-            sb = p[idx, nzt - 2 * G:nzt - G].contiguous()
+        if self.hi is not None:                    # my top nlo owned planes -> the hi neighbour's low ghosts
+            sb = p[idx, nzt - G - nlo:nzt - G].contiguous()
             ops.append(dist.P2POp(dist.isend, sb, self.hi))
             self.bytes_sent += sb.numel() * 8
-        if self.lo is not None:
-            sb2 = p[idx, G:2 * G].contiguous()
+        if self.lo is not None:                    # my bottom nhi owned planes -> the lo neighbour's high ghosts
+            sb2 = p[idx, G:G + nhi].contiguous()
             ops.append(dist.P2POp(dist.isend, sb2, self.lo))
             self.bytes_sent += sb2.numel() * 8
         if self.lo is not None:
-            rb = torch.empty((len(ids), G, p.shape[2]), dtype=p.dtype, device=p.device)
+            rb = torch.empty((len(ids), nlo, p.shape[2]), dtype=p.dtype, device=p.device)
             ops.append(dist.P2POp(dist.irecv, rb, self.lo))
-            recvs.append((rb, slice(0, G)))
+            recvs.append((rb, slice(G - nlo, G)))
         if self.hi is not None:
-            rb2 = torch.empty((len(ids), G, p.shape[2]), dtype=p.dtype, device=p.device)
+            rb2 = torch.empty((len(ids), nhi, p.shape[2]), dtype=p.dtype, device=p.device)
             ops.append(dist.P2POp(dist.irecv, rb2, self.hi))
-            recvs.append((rb2, slice(nzt - G, nzt)))
+            recvs.append((rb2, slice(nzt - G, nzt - G + nhi)))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()

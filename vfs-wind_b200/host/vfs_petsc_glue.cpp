@@ -19,8 +19,10 @@
 // Vecs the reference function reads and downloads the Vecs it writes.  Constant inputs (metrics,
 // Nvert, Ucont_o, RHS_o, dP, F_eul, lUcat_old) are uploaded only when vfs_glue_invalidate() has
 // been called since their last upload (the time loop calls it once per step), so a Krylov
-// iteration moves exactly X down and F up.  Single rank (one GPU) in this round; the k-slab
-// multi-GPU path is driven through the C ABI + halo callback directly.
+// iteration moves exactly X down and F up.  MPI runs: one rank per GPU, the DA decomposed along k only
+// (1 x 1 x P process grid, init.c:131-160 with -da_processors_x 1 -da_processors_y 1): every rank
+// creates a context for its k-slab [info.zs, info.zs + info.zm) and the ncclUniqueId of the in-library
+// halo layer travels by MPI_Bcast.
 //
 // This file is product code: it contains no arithmetic of the path and never calls the oracle.
 #include "variables.h"
@@ -29,22 +31,37 @@
 #include <vector>
 
 extern PetscInt les, second_order, immersed, inviscid, movefsi, rotatefsi, rotor_model, nacelle_model, IB_delta, wallfunction, ti, tistart;
+extern int levelset_weno, freesurface_wallmodel, air_flow_levelset;
 extern int laplacian, clark, central, testfilter_ik, viscosity_wallmodel, levelset, rans, skew;
 extern int i_periodic, j_periodic, k_periodic, ii_periodic, jj_periodic, kk_periodic, i_homo_filter, j_homo_filter, k_homo_filter;
 extern PetscReal max_cs;
 extern double roughness_size;
 extern PetscTruth rstart_flg;
 
-struct GlueState { vfs_ctx *ctx; bool const_valid; std::vector<double> buf; };
+struct GlueState { vfs_ctx *ctx; bool const_valid; double *buf; size_t buf_doubles; int zs, zm; };
 static std::map<UserCtx *, GlueState> g_state;
+static std::map<UserCtx *, Vec> g_last_x;      // the X of the most recent FormFunction_SNES (owned by the caller's SNES)
+static int g_eager = 0;       // 1: FormFunction_SNES mirrors its side effects on the host Vecs at every call (see vfs_glue_sync_state)
 
 extern "C" void vfs_glue_invalidate(UserCtx *user) { std::map<UserCtx *, GlueState>::iterator it = g_state.find(user); if (it != g_state.end()) it->second.const_valid = false; }
-extern "C" void vfs_glue_release(UserCtx *user) { std::map<UserCtx *, GlueState>::iterator it = g_state.find(user); if (it != g_state.end()) { vfs_destroy(it->second.ctx); g_state.erase(it); } }
+extern "C" void vfs_glue_release(UserCtx *user) {
+  std::map<UserCtx *, GlueState>::iterator it = g_state.find(user);
+  if (it != g_state.end()) { vfs_destroy(it->second.ctx); vfs_host_free(it->second.buf); g_state.erase(it); }
+  g_last_x.erase(user);
+}
+extern "C" void vfs_glue_set_eager(int on) { g_eager = on; }
 
 static void fill_params(UserCtx *user, vfs_params *p) {
   memset(p, 0, sizeof(*p));
   DALocalInfo info = user->info;
-  p->mx = info.mx; p->my = info.my; p->mz = info.mz; p->kofs = 0; p->nzl = info.mz; p->rank = 0; p->nranks = 1; p->device = 0;
+  int rank = 0, size = 1;
+  MPI_Comm_rank(PETSC_COMM_WORLD, &rank); MPI_Comm_size(PETSC_COMM_WORLD, &size);
+  if (info.xm != info.mx || info.ym != info.my) {
+    PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: the DA must be decomposed along k only (run with -da_processors_x 1 -da_processors_y 1)\n"); exit(1);
+  }
+  p->mx = info.mx; p->my = info.my; p->mz = info.mz; p->kofs = info.zs; p->nzl = info.zm; p->rank = rank; p->nranks = size;
+  const int ndev = vfs_device_count();
+  p->device = ndev > 0 ? rank % ndev : 0;
   p->ii_periodic = ii_periodic; p->jj_periodic = jj_periodic; p->kk_periodic = kk_periodic;
   for (int q = 0; q < 6; q++) p->bctype[q] = user->bctype[q];
   p->les = les; p->second_order = second_order; p->laplacian = laplacian; p->immersed = immersed; p->clark = clark; p->central = central;
@@ -55,16 +72,26 @@ static void fill_params(UserCtx *user, vfs_params *p) {
   p->i_periodic = i_periodic; p->j_periodic = j_periodic; p->k_periodic = k_periodic;
   p->i_homo_filter = i_homo_filter; p->j_homo_filter = j_homo_filter; p->k_homo_filter = k_homo_filter;
   p->ren = user->ren; p->dt = user->dt; p->max_cs = max_cs; p->roughness_size = roughness_size;
+  // switches that change this path in the reference and are NOT built: the library rejects them (no silent central scheme)
+  p->levelset_weno = levelset_weno; p->freesurface_wallmodel = freesurface_wallmodel; p->air_flow_levelset = air_flow_levelset;
 }
 
 static GlueState *state(UserCtx *user) {
   std::map<UserCtx *, GlueState>::iterator it = g_state.find(user);
   vfs_params p; fill_params(user, &p);
   if (it == g_state.end()) {
-    GlueState s; s.ctx = 0; s.const_valid = false;
+    GlueState s; s.ctx = 0; s.const_valid = false; s.zs = p.kofs; s.zm = p.nzl;
     int r = vfs_create(&p, &s.ctx);
     if (r) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: cannot create device context (%d): %s\n", r, vfs_last_error(0)); exit(1); }   // no CPU fallback
-    s.buf.resize((size_t)p.mx * p.my * p.mz * 3);
+    if (p.nranks > 1) {         // in-library NCCL halo layer: rank 0's id to everybody
+      char id[128]; memset(id, 0, sizeof(id));
+      if (p.rank == 0 && vfs_nccl_unique_id(id)) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: %s\n", vfs_last_error(0)); exit(1); }
+      MPI_Bcast(id, 128, MPI_CHAR, 0, PETSC_COMM_WORLD);
+      if (vfs_nccl_init(s.ctx, id)) { PetscPrintf(PETSC_COMM_SELF, "vfs_b200: %s\n", vfs_last_error(s.ctx)); exit(1); }
+    }
+    s.buf_doubles = (size_t)p.mx * p.my * p.nzl * 3;
+    s.buf = (double *)vfs_host_alloc(s.buf_doubles * sizeof(double));       // pinned: the copies run at PCIe speed
+    if (!s.buf) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: cannot allocate the pinned staging buffer\n"); exit(1); }
     it = g_state.insert(std::make_pair(user, s)).first;
   } else if (vfs_set_params(it->second.ctx, &p)) {
     PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: %s\n", vfs_last_error(it->second.ctx)); exit(1);
@@ -73,34 +100,37 @@ static GlueState *state(UserCtx *user) {
 }
 static void ck(GlueState *s, int r, const char *what) { if (r) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: %s failed (%d): %s\n", what, r, vfs_last_error(s->ctx)); exit(1); } }
 
-// Vec (local or global, dof 1 or 3) -> owned block -> device field
+// Vec (local or global, dof 1 or 3) -> the rank's owned block [zm][my][mx][dof] -> device field.  Rows are contiguous
+// in both layouts (a ghosted local Vec only has a longer row pitch): one memcpy per row.
 static void push(UserCtx *user, GlueState *s, Vec v, int dof, int field) {
-  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, mz = info.mz;
-  double *b = s->buf.data();
+  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, zs = info.zs, ze = info.zs + info.zm;
+  double *b = s->buf;
+  const size_t row = (size_t)mx * dof;
   if (dof == 3) {
     Cmpnts ***a; DAVecGetArray(user->fda, v, &a);
-    for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) for (int i = 0; i < mx; i++) { size_t q = (((size_t)k * my + j) * mx + i) * 3; b[q] = a[k][j][i].x; b[q + 1] = a[k][j][i].y; b[q + 2] = a[k][j][i].z; }
+    for (int k = zs; k < ze; k++) for (int j = 0; j < my; j++) memcpy(b + ((size_t)(k - zs) * my + j) * row, &a[k][j][0].x, row * sizeof(double));
     DAVecRestoreArray(user->fda, v, &a);
   } else {
     PetscReal ***a; DAVecGetArray(user->da, v, &a);
-    for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) for (int i = 0; i < mx; i++) b[((size_t)k * my + j) * mx + i] = a[k][j][i];
+    for (int k = zs; k < ze; k++) for (int j = 0; j < my; j++) memcpy(b + ((size_t)(k - zs) * my + j) * row, &a[k][j][0], row * sizeof(double));
     DAVecRestoreArray(user->da, v, &a);
   }
   ck(s, vfs_upload(s->ctx, field, b), "vfs_upload");
 }
-// device field -> owned block of Vec v; if `local` is given it is refreshed from v (ghosts included)
+// device field -> owned block of Vec v; a local v has its ghosts refreshed afterwards
 static void pull(UserCtx *user, GlueState *s, int field, int dof, Vec v, bool v_is_local) {
-  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, mz = info.mz;
-  double *b = s->buf.data();
+  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, zs = info.zs, ze = info.zs + info.zm;
+  double *b = s->buf;
+  const size_t row = (size_t)mx * dof;
   ck(s, vfs_download(s->ctx, field, b), "vfs_download");
   if (dof == 3) {
     Cmpnts ***a; DAVecGetArray(user->fda, v, &a);
-    for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) for (int i = 0; i < mx; i++) { size_t q = (((size_t)k * my + j) * mx + i) * 3; a[k][j][i].x = b[q]; a[k][j][i].y = b[q + 1]; a[k][j][i].z = b[q + 2]; }
+    for (int k = zs; k < ze; k++) for (int j = 0; j < my; j++) memcpy(&a[k][j][0].x, b + ((size_t)(k - zs) * my + j) * row, row * sizeof(double));
     DAVecRestoreArray(user->fda, v, &a);
     if (v_is_local) { DALocalToLocalBegin(user->fda, v, INSERT_VALUES, v); DALocalToLocalEnd(user->fda, v, INSERT_VALUES, v); }
   } else {
     PetscReal ***a; DAVecGetArray(user->da, v, &a);
-    for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) for (int i = 0; i < mx; i++) a[k][j][i] = b[((size_t)k * my + j) * mx + i];
+    for (int k = zs; k < ze; k++) for (int j = 0; j < my; j++) memcpy(&a[k][j][0], b + ((size_t)(k - zs) * my + j) * row, row * sizeof(double));
     DAVecRestoreArray(user->da, v, &a);
     if (v_is_local) { DALocalToLocalBegin(user->da, v, INSERT_VALUES, v); DALocalToLocalEnd(user->da, v, INSERT_VALUES, v); }
   }
@@ -149,6 +179,38 @@ static void host_face_metrics(UserCtx *user) {
   }
 }
 
+// Side outputs of FormMetrics that host code outside the path reads (bcs.c:3018, fsi.c:158, ibm search): the cell
+// centres Cent / lCent (metrics.c:89-107: mean of the cell's eight corner nodes) and the grid spacings GridSpace /
+// lGridSpace (metrics.c:420-497,1059-1060: distance between the centres of opposite faces), once per grid, on the host.
+static void host_cent_gridspace(UserCtx *user) {
+  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, mz = info.mz;
+  const int lxs = 1, lxe = mx - 1, lys = 1, lye = my - 1, lzs = info.zs == 0 ? 1 : info.zs, lze = info.zs + info.zm == mz ? mz - 1 : info.zs + info.zm;
+  Vec Coor; DAGetGhostedCoordinates(user->da, &Coor);
+  Cmpnts ***coor, ***cent, ***gs;
+  DAVecGetArray(user->fda, Coor, &coor); DAVecGetArray(user->fda, user->Cent, &cent); DAVecGetArray(user->fda, user->GridSpace, &gs);
+  for (int k = lzs; k < lze; k++) for (int j = lys; j < lye; j++) for (int i = lxs; i < lxe; i++) {
+    // corner nodes of cell (i,j,k): (i-a, j-b, k-c), a,b,c in {0,1}; summed in the reference's order
+    const Cmpnts c000 = coor[k][j][i], c010 = coor[k][j - 1][i], c001 = coor[k - 1][j][i], c011 = coor[k - 1][j - 1][i];
+    const Cmpnts c100 = coor[k][j][i - 1], c110 = coor[k][j - 1][i - 1], c101 = coor[k - 1][j][i - 1], c111 = coor[k - 1][j - 1][i - 1];
+    cent[k][j][i].x = 0.125 * (c000.x + c010.x + c001.x + c011.x + c100.x + c110.x + c101.x + c111.x);
+    cent[k][j][i].y = 0.125 * (c000.y + c010.y + c001.y + c011.y + c100.y + c110.y + c101.y + c111.y);
+    cent[k][j][i].z = 0.125 * (c000.z + c010.z + c001.z + c011.z + c100.z + c110.z + c101.z + c111.z);
+    // face centres: +i face (nodes with index i), -i face (i-1), and twins; node order as in metrics.c
+#define FC(A, B, C, D, m) (0.25 * ((A).m + (B).m + (C).m + (D).m))
+#define DIST(A, B, C, D, E, F, G, H) sqrt((FC(A, B, C, D, x) - FC(E, F, G, H, x)) * (FC(A, B, C, D, x) - FC(E, F, G, H, x)) + \
+                                          (FC(A, B, C, D, y) - FC(E, F, G, H, y)) * (FC(A, B, C, D, y) - FC(E, F, G, H, y)) + \
+                                          (FC(A, B, C, D, z) - FC(E, F, G, H, z)) * (FC(A, B, C, D, z) - FC(E, F, G, H, z)))
+    gs[k][j][i].x = DIST(c000, c010, c011, c001, c100, c110, c111, c101);
+    gs[k][j][i].y = DIST(c000, c100, c001, c101, c010, c110, c011, c111);
+    gs[k][j][i].z = DIST(c000, c100, c010, c110, c001, c101, c011, c111);
+#undef DIST
+#undef FC
+  }
+  DAVecRestoreArray(user->fda, Coor, &coor); DAVecRestoreArray(user->fda, user->Cent, &cent); DAVecRestoreArray(user->fda, user->GridSpace, &gs);
+  DAGlobalToLocalBegin(user->fda, user->Cent, INSERT_VALUES, user->lCent); DAGlobalToLocalEnd(user->fda, user->Cent, INSERT_VALUES, user->lCent);
+  DAGlobalToLocalBegin(user->fda, user->GridSpace, INSERT_VALUES, user->lGridSpace); DAGlobalToLocalEnd(user->fda, user->GridSpace, INSERT_VALUES, user->lGridSpace);
+}
+
 PetscErrorCode FormMetrics(UserCtx *user) {
   GlueState *s = state(user);
   Vec coords; DAGetGhostedCoordinates(user->da, &coords);
@@ -157,6 +219,7 @@ PetscErrorCode FormMetrics(UserCtx *user) {
   pull(user, s, VFS_CSI, 3, user->lCsi, true); pull(user, s, VFS_ETA, 3, user->lEta, true); pull(user, s, VFS_ZET, 3, user->lZet, true);
   pull(user, s, VFS_AJ, 1, user->lAj, true);
   host_face_metrics(user);
+  host_cent_gridspace(user);
   s->const_valid = false;
   return 0;
 }
@@ -165,6 +228,10 @@ void Contra2Cart_2(UserCtx *user) {
   GlueState *s = state(user);
   push_constants(user, s);
   push(user, s, user->lUcont, 3, VFS_UCONT);
+  // The reference updates user->Ucat IN PLACE: fluid interior cells are recomputed, IB / solid cells and boundary nodes
+  // no rule touches keep what the host wrote since the last call (FormBCS bcs.c:2404, ibm_interpolation_advanced
+  // ibm.c:3673 are followed by Contra2Cart, implicitsolver.c:4406-4444) — so the current host Ucat goes down first.
+  push(user, s, user->Ucat, 3, VFS_UCAT);
   ck(s, vfs_contra2cart(s->ctx), "vfs_contra2cart");
   if (ii_periodic || jj_periodic || kk_periodic) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156 rewrites lUcont's periodic nodes
   pull(user, s, VFS_UCAT, 3, user->Ucat, false);
@@ -235,6 +302,52 @@ PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
   return 0;
 }
 
+// Side effects of the reference's FormFunction_SNES on the UserCtx Vecs (momentum.c:2240-2295: Ucont <- X with the
+// wall-normal fluxes zeroed, lUcont, Ucat / lUcat through Contra2Cart_2, lUstar, and on the first step IB_BC's nvert
+// marking in lNvert / Nvert).  The reference reads them right after SNESSolve (outflow BCs, VecMax(Ucat),
+// implicitsolver.c:4360-4376).  They live on the device during the Krylov iterations; this call materialises them on
+// the host.  INTEGRATION.md: call it once after SNESSolve — or switch vfs_glue_set_eager(1) on, and FormFunction_SNES
+// does it at every evaluation (a strict drop-in at three times the PCIe traffic).
+// user->Ucont <- X with the wall-normal fluxes zeroed (momentum.c:2240, 2264-2289), on the host: the global Ucont does
+// NOT receive the periodic boundary-node rewrites that Contra2Cart_2 / IB_BC apply to lUcont (the device holds lUcont)
+static void host_ucont_from_x(UserCtx *user, Vec X) {
+  VecCopy(X, user->Ucont);
+  DALocalInfo info = user->info; const int mx = info.mx, my = info.my, mz = info.mz, zs = info.zs, ze = info.zs + info.zm;
+  const int *bc = user->bctype;
+  Cmpnts ***u; DAVecGetArray(user->fda, user->Ucont, &u);
+  for (int k = zs; k < ze; k++) for (int j = 0; j < my; j++) {
+    const bool jin = j != 0 && j != my - 1, kin = k != 0 && k != mz - 1;
+    if (bc[0] == 1 || (bc[0] == 10 && jin && kin)) u[k][j][0].x = 0;
+    if (bc[1] == 1 || (bc[1] == 10 && jin && kin)) u[k][j][mx - 2].x = 0;
+  }
+  for (int k = zs; k < ze; k++) for (int i = 0; i < mx; i++) {
+    const bool iin = i != 0 && i != mx - 1, kin = k != 0 && k != mz - 1;
+    if (bc[2] == 1 || bc[2] == 12 || (bc[2] == 10 && iin && kin)) u[k][0][i].y = 0;
+    if (bc[3] == 1 || bc[3] == 2 || bc[3] == 12 || ((bc[3] == 10 || bc[3] == -10) && iin && kin)) u[k][my - 2][i].y = 0;
+  }
+  for (int j = 0; j < my; j++) for (int i = 0; i < mx; i++) {
+    if (bc[4] == 1 && zs == 0) u[0][j][i].z = 0;
+    if (bc[5] == 1 && mz - 2 >= zs && mz - 2 < ze) u[mz - 2][j][i].z = 0;
+  }
+  DAVecRestoreArray(user->fda, user->Ucont, &u);
+}
+
+extern "C" void vfs_glue_sync_state(UserCtx *user) {
+  GlueState *s = state(user);
+  std::map<UserCtx *, Vec>::iterator lx = g_last_x.find(user);
+  if (lx != g_last_x.end() && lx->second) host_ucont_from_x(user, lx->second);
+  pull(user, s, VFS_UCONT, 3, user->lUcont, true);       // lUcont: periodic boundary nodes rewritten by Contra2Cart_2 / IB_BC
+  pull(user, s, VFS_UCAT, 3, user->Ucat, false);
+  DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
+  bool wallfn = false;
+  for (int q = 0; q < 6; q++) wallfn = wallfn || user->bctype[q] == -1 || user->bctype[q] == -2;
+  if (wallfn || (viscosity_wallmodel && les)) pull(user, s, VFS_USTAR, 1, user->lUstar, false);   // rhs.c:336,371,401,435; momentum.c:1150
+  if (wallfn && !immersed && ti == tistart) {            // momentum.c:2048-2074
+    pull(user, s, VFS_NVERT, 1, user->lNvert, true);
+    DALocalToGlobal(user->da, user->lNvert, INSERT_VALUES, user->Nvert);
+  }
+}
+
 PetscErrorCode FormFunction_SNES(SNES snes, Vec Ucont, Vec Rhs, void *ptr) {
   UserCtx *user = (UserCtx *)ptr;
   GlueState *s = state(user);
@@ -243,15 +356,27 @@ PetscErrorCode FormFunction_SNES(SNES snes, Vec Ucont, Vec Rhs, void *ptr) {
   VecGetArray(Ucont, &x); VecGetArray(Rhs, &f);
   ck(s, vfs_formfunction_snes(s->ctx, x, f), "vfs_formfunction_snes");      // X down, F up: the only per-Krylov-iteration traffic
   VecRestoreArray(Ucont, &x); VecRestoreArray(Rhs, &f);
+  g_last_x[user] = Ucont;
+  if (g_eager) vfs_glue_sync_state(user);
   return 0;
 }
-// Side effects of the reference's FormFunction_SNES on user->Ucont/lUcont/Ucat/lUcat are
-// materialised on the host on demand (after the SNES solve the caller runs Contra2Cart anyway,
-// implicitsolver.c:4444); call this to mirror them explicitly.
-extern "C" void vfs_glue_sync_state(UserCtx *user) {
+
+// The one-line replacement of `SNESSolve(user->snes, PETSC_NULL, U)` in Implicit_MatrixFree (implicitsolver.c:4299):
+// the whole Newton-Krylov solve on the device (vfs_momentum_solve), U in/out, side effects mirrored on the host Vecs.
+// p == NULL: the reference's settings (vfs_solver_defaults with snes_rtol = imp_free_tol).  Returns the final |F|.
+extern "C" double vfs_glue_snes_solve(UserCtx *user, Vec U, const vfs_solver_params *p, vfs_solver_info *info_out) {
   GlueState *s = state(user);
-  pull(user, s, VFS_UCONT, 3, user->lUcont, true);
-  pull(user, s, VFS_UCAT, 3, user->Ucat, false);
-  DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
-  for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }   // rhs.c:336,371,401,435
+  push_constants(user, s);
+  push(user, s, U, 3, VFS_UCONT);
+  vfs_solver_params sp;
+  if (p) sp = *p; else { extern double imp_free_tol; vfs_solver_defaults(&sp); sp.snes_rtol = imp_free_tol; sp.ksp_rtol = imp_free_tol; }
+  vfs_solver_info info;
+  ck(s, vfs_momentum_solve(s->ctx, &sp, &info), "vfs_momentum_solve");
+  pull(user, s, VFS_UCONT, 3, U, false);
+  // FormFunction_SNES's side effects as of the last evaluation the reference's SNES would have made (the accepted iterate)
+  ck(s, vfs_formfunction_snes_dev(s->ctx), "vfs_formfunction_snes_dev");
+  g_last_x[user] = U;
+  vfs_glue_sync_state(user);
+  if (info_out) *info_out = info;
+  return info.fnorm;
 }
