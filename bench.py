@@ -317,11 +317,19 @@ def run_ours(args):
 
     # ---- device-resident Newton-Krylov solve: the residual is evaluated where the Krylov vectors live ----
     solver = None
-    need = (args.solver_krylov + 9) * nzl * my * mx * 3 * 8 * 1.05
-    if hasattr(ctx, "momentum_solve") and not args.no_solver and torch.cuda.mem_get_info()[0] < need:
-        solver = {"skipped": "Krylov basis (%d vectors, %.0f GB) does not fit beside the %.0f GB of resident state" % (args.solver_krylov + 8, need / 1e9, ctx.scalar_len * 8 * ctx.nscalars / 1e9)}
+    vec_bytes = nzl * my * mx * 3 * 8
+    free_b = torch.cuda.mem_get_info()[0]
+    if world > 1:                       # every rank must run the same number of Krylov iterations
+        t = torch.tensor([float(free_b)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        free_b = float(t.item())
+    fit = int(free_b * 0.9 / vec_bytes) - 9          # restart + 8 work vectors + the pinned-staging counterpart
+    krylov = min(args.solver_krylov, fit)
+    if hasattr(ctx, "momentum_solve") and not args.no_solver and krylov < 2:
+        solver = {"skipped": "no room for a Krylov basis beside the %.0f GB of resident state (%.1f GB free, %.1f GB per vector)" % (ctx.scalar_len * 8 * ctx.nscalars / 1e9, free_b / 1e9, vec_bytes / 1e9)}
     elif hasattr(ctx, "momentum_solve") and not args.no_solver:
         try:
+            args.solver_krylov = krylov
             solver = bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, (nzl, my, mx), args)
         except Exception as e:      # noqa
             solver = {"error": str(e)[:200]}
@@ -425,10 +433,9 @@ def bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, shape, args)
     """One implicit momentum solve per step through vfs_momentum_solve (device-resident GMRES + MFFD + Newton):
     Ucont uploaded from pinned host memory, solution downloaded, LES update once per step."""
     nzl, my, mx = shape
-    xh = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
-    ctx.download_ptr("UCONT", xh.data_ptr())
-    x0 = xh.clone().pin_memory()
-    out = torch.empty_like(xh).pin_memory()
+    x0 = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
+    ctx.download_ptr("UCONT", x0.data_ptr())
+    out = torch.empty((nzl, my, mx, 3), dtype=torch.float64).pin_memory()
 
     def step():
         ctx.upload_ptr("UCONT", x0.data_ptr())

@@ -11,6 +11,7 @@
  *   vfs_les_cs              <- Compute_Smagorinsky_Constant_1(UserCtx*,Vec,Vec)  les.c:75
  *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
  *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
+ *   vfs_pressure_gradient   <- Pressure_Gradient(UserCtx*, Vec dP)           momentum.c:203
  *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4299
  *
  * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
@@ -53,6 +54,7 @@ enum vfs_field {
   VFS_USTAR,        /* lUstar (dof 1) wall-model friction velocity                   */
   VFS_CONV,         /* Conv (dof 3) output of vfs_convection (download only)           */
   VFS_VISC,         /* Visc (dof 3) output of vfs_viscous (download only)              */
+  VFS_P,            /* P / lP (dof 1) pressure, input of vfs_pressure_gradient         */
   VFS_NFIELDS_PUBLIC
 };
 
@@ -142,6 +144,12 @@ int vfs_download_wait(vfs_ctx *c);
  * Viscous(UserCtx*,Vec,Vec,Vec Visc) Source/rhs.c:1071 (callers timeadvancing1.c:75-76): QUICK
  * flux-difference convection and the (nu + nu_t) viscous term of the current VFS_UCONT / VFS_UCAT
  * (+ VFS_NU_T when les) into VFS_CONV / VFS_VISC.  Like the reference they ignore periodicity. */
+/* Pressure_Gradient(UserCtx*, Vec dP) Source/momentum.c:203-439: dP (VFS_DP) = the contravariant
+ * pressure gradient of VFS_P on the i/j/k faces, IB-aware one-sided differences, zero on masked faces; P's ghosts and
+ * periodic boundary nodes are refreshed first, as the reference does (:247-286).  `k_forcing` is the scalar the
+ * reference adds to dP/dzeta per unit dz in k-periodic runs (:399-411): mean_pressure_gradient when dpdz_set, else
+ * (mean_k_flux - inlet_flux) / dt / mean_k_area unless inletprofile == 17; pass 0 otherwise. */
+int vfs_pressure_gradient(vfs_ctx *c, double k_forcing);
 int vfs_convection(vfs_ctx *c);
 int vfs_viscous(vfs_ctx *c);
 /* F = residual(X); X, F host arrays [nzl][my][mx][3] (pinned or pageable) */

@@ -85,6 +85,7 @@ int ref_Formfunction_2(UserCtx *u, Vec rhs, double scale) { return Formfunction_
 int ref_FormFunction_SNES(UserCtx *u, Vec x, Vec f) { return FormFunction_SNES((SNES)0, x, f, (void *)u); }
 void ref_Compute_Smagorinsky_Constant_1(UserCtx *u) { Compute_Smagorinsky_Constant_1(u, u->lUcont, u->lUcat); }
 void ref_Compute_eddy_viscosity_LES(UserCtx *u) { Compute_eddy_viscosity_LES(u); }
+void ref_Pressure_Gradient(UserCtx *u, Vec dp, double mean_k_flux, double mean_k_area) { u->mean_k_flux = mean_k_flux; u->mean_k_area = mean_k_area; Pressure_Gradient(u, dp); }
 int ref_Convection(UserCtx *u, Vec conv) { return Convection(u, u->lUcont, u->lUcat, conv); }
 int ref_Viscous(UserCtx *u, Vec visc) { return Viscous(u, u->lUcont, u->lUcat, visc); }
 Vec ref_vec_new(UserCtx *u, int dof, int local) { Vec v; DA d = dof == 3 ? u->fda : u->da;

@@ -50,6 +50,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.ref_Formfunction_2.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.ref_FormFunction_SNES.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_Pressure_Gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.ref_Convection.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Viscous.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_vec_new.restype = C.c_void_p
@@ -78,7 +79,7 @@ FLAG_DEFAULTS = dict(
     i_homo_filter=0, j_homo_filter=0, k_homo_filter=0, testfilter_ik=0, max_cs=0.5, wallfunction=0,
     viscosity_wallmodel=0, freesurface_wallmodel=0, movefsi=0, rotatefsi=0, rotor_model=0, nacelle_model=0, IB_delta=0,
     ti=10, tistart=0, rstart_flg=0, wave_momentum_source=0, air_flow_levelset=0, surface_tension=0, lowRe=0,
-    roughness_size=0.0, dthick=1.5, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
+    roughness_size=0.0, dthick=1.5, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
 )
 
 
@@ -171,6 +172,9 @@ class RefCase:
 
     def Compute_eddy_viscosity_LES(self):
         lib().ref_Compute_eddy_viscosity_LES(self.u)
+
+    def Pressure_Gradient(self, name, mean_k_flux=0.0, mean_k_area=1.0):
+        lib().ref_Pressure_Gradient(self.u, self.vec(name), mean_k_flux, mean_k_area)
 
     def Convection(self, name):
         return lib().ref_Convection(self.u, self.vec(name))

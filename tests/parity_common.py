@@ -167,6 +167,18 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
     err["FormFunction_SNES"] = relerr(f_dev, f_ref)
     err["FormFunction_SNES_zero_pattern"] = float(np.count_nonzero((f_dev == 0) != (f_ref == 0)))
     err["SNES_ucat"] = relerr(ctx.download("UCAT"), ref.owned("Ucat"))
+    # Pressure_Gradient (momentum.c:203-439) — last, because it overwrites dP.  k-periodic runs add the
+    # mean-flux forcing (mean_k_flux - inlet_flux) / dt / mean_k_area per unit dz (:399-411)
+    if "p" in fields:
+        mkf, mka, infl = 0.3, 2.0, 0.1
+        refdrv.set_global("inlet_flux", infl)
+        ref.set_owned("P", fields["p"])
+        ref.new_vec("dPg", 3, False)
+        ref.Pressure_Gradient("dPg", mkf, mka)
+        ctx.upload("P", fields["p"])
+        ctx.Pressure_Gradient((mkf - infl) / cfg["dt"] / mka if cfg["flags"].get("kk_periodic") else 0.0)
+        err["Pressure_Gradient"] = relerr(ctx.download("DP"), ref.view("dPg"))
+        err["Pressure_Gradient_P"] = relerr(ctx.download("P"), ref.owned("P"))
     if verbose:
         for k, v in err.items():
             print("%-32s %.3e" % (k, v))

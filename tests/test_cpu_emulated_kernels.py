@@ -83,7 +83,7 @@ def test_emulated_fp_in_projection_bitwise(pkg, emu):
         cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
         mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
         outs = []
-        for val in (0, 1):
+        for val in (0, 1, 2):
             ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]), lib=emu)
             ctx.set_option(12, val)
             ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
@@ -98,3 +98,4 @@ def test_emulated_fp_in_projection_bitwise(pkg, emu):
             ctx.close()
         for n in outs[0]:
             assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
+            assert np.array_equal(outs[0][n], outs[2][n]), (cfgname, n, 'box')

@@ -83,6 +83,13 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     err["IB_BC_lUcont"] = pc.relerr(a[nb < 2], b[nb < 2])
     err["IB_BC_Nvert_mismatches"] = float(np.count_nonzero(np.array(glue.owned("Nvert")) != np.array(ref.owned("Nvert")))
                                           + np.count_nonzero(np.array(glue.owned("lNvert")) != np.array(ref.owned("lNvert"))))
+    for d, drv in ((ref, refdrv), (glue, gd)):      # Pressure_Gradient (momentum.c:203), k-periodic mean-flux forcing included
+        drv.set_global("inlet_flux", 0.1)
+        d.set_owned("P", fields["p"])
+        d.new_vec("dPg", 3, False)
+        d.Pressure_Gradient("dPg", 0.3, 2.0)
+    err["Pressure_Gradient"] = pc.relerr(glue.view("dPg"), ref.view("dPg"))
+    err["Pressure_Gradient_lP"] = pc.relerr(glue.view("lP"), ref.view("lP"))
     for d in (ref, glue):
         d.view("RHS_o")[...] = 0
         d.Formfunction_2("RHS_o", 1.0)

@@ -13,7 +13,7 @@ CASES = [
     ("c2_box256", (40, 33, 37)),
     ("c3_turbine", (29, 21, 25)),     # IBM masks, QUICK at IB faces, inflow/outflow in k, F_eul
     ("c3_turbine", (45, 30, 41)),
-    ("c1_test10", (24, 16, 20)),      # 2nd-order, laplacian (wall model excluded)
+    ("c1_test10", (24, 16, 20)),      # 2nd-order, laplacian, Cabot wall model at the j = 0 faces
 ]
 
 
@@ -21,6 +21,28 @@ CASES = [
 def test_path_matches_reference(pkg, refdrv, name, dims):
     cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     err = pc.run_parity(cfg, refdrv, device=0)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def test_c1_on_its_shipped_grid(pkg, refdrv):
+    """BASELINE.json configs[0]: Test_10_ChannelFlow_Retau3000 on its shipped 122 x 42 x 62-node grid (cases.make_grid
+    reproduces the shipped xyz.dat to 1e-14, tests/test_cpu_formats.py), flags of its control.dat, wall model on:
+    the whole path through the CUDA library against the oracle at the case's real size."""
+    cfg = dict(pkg.cases.CONFIGS["c1_test10"])
+    err = pc.run_parity(cfg, refdrv, device=0)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (127, 95, 79)), ("c3_turbine", (99, 69, 89))])
+def test_multi_tile_sizes_match_reference(pkg, refdrv, name, dims):
+    """Oracle parity of the marching / TMA kernels on grids several tiles wide and several k-chunks deep
+    (128 x 96 x 80 nodes: 4 x 6 flux tiles, 5 x 10 LES-2 tiles), masks and F_eul included."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = pc.run_parity(cfg, refdrv, device=0, legacy=False)
     assert err.pop("FormFunction_SNES_zero_pattern") == 0
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
@@ -198,7 +220,7 @@ def test_fused_variants_bitwise_equal_staged_chain(pkg, key):
         cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
         mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
         outs = []
-        for val in (0, 1):
+        for val in (0, 1, 2):
             ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
             ctx.set_option(key, val)
             ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
@@ -213,6 +235,7 @@ def test_fused_variants_bitwise_equal_staged_chain(pkg, key):
             ctx.close()
         for n in outs[0]:
             assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n, pc.relerr(outs[1][n], outs[0][n]))
+            assert np.array_equal(outs[0][n], outs[2][n]), (cfgname, n, 'box', pc.relerr(outs[2][n], outs[0][n]))
 
 
 def test_graph_replay_equals_eager(pkg):

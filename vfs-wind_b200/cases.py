@@ -183,4 +183,8 @@ def make_fields(cfg, metrics):
                 f_eul[..., 0] += fz * face(zet, 2)[..., 2] * 0.0
                 f_eul[..., 2] += fz * face(zet, 0)[..., 2] * face(metrics["aj"], 0)
     out["f_eul"] = f_eul
+    # pressure: smooth random field, zero inside bodies (input of Pressure_Gradient, momentum.c:203)
+    pr = 0.5 * _smooth121(rng.uniform(-1, 1, (mz, my, mx)))
+    pr[nvert > 1.1] = 0.0
+    out["p"] = pr
     return out

@@ -58,6 +58,7 @@ enum {
   // 1/sum(s*w), test_filter^2, filter^2
   S_LFINV, S_LTF2, S_LF2,
   S_WM,                                                                  // wall-model nu_t of the j = 0 faces (plane j = 0 only)
+  S_P,                                                                   // pressure (input of Pressure_Gradient, momentum.c:203)
   S_COUNT
 };
 

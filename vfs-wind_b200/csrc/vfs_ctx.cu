@@ -234,7 +234,7 @@ static void ev_rec(vfs_ctx *c, int n) {
 // ---- public field table -----------------------------------------------------------------------
 static const struct { int s0, dof; } FIELD[VFS_NFIELDS_PUBLIC] = {
   {S_X, 3}, {S_CSI0, 3}, {S_ETA0, 3}, {S_ZET0, 3}, {S_AJ, 1}, {S_NV, 1}, {S_UC0, 3}, {S_U0, 3}, {S_UO0, 3},
-  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}, {S_CONV0, 3}, {S_VISC0, 3}};
+  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}, {S_CONV0, 3}, {S_VISC0, 3}, {S_P, 1}};
 
 static Grp grp(int s0, int n) { Grp g; g.n = n; for (int q = 0; q < n; q++) g.sid[q] = s0 + q; return g; }
 static Grp grp_cat(const Grp &a, const Grp &b) { Grp g = a; for (int q = 0; q < b.n; q++) g.sid[g.n++] = b.sid[q]; return g; }
@@ -1080,7 +1080,9 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
       ProjectSNES f = {d}; return launch_shell(c, 0, d.nzl, f);
     };
     auto march = [&](int q0, int q1) -> int {
-      if (run_projfp_march(c->stream, P, q0 < k1 ? k1 : q0, q1 > k2 ? k2 : q1, &c->launches)) { set_err(c, "projection kernel launch failed"); return VFS_ERR_CUDA; }
+      q0 = q0 < k1 ? k1 : q0; q1 = q1 > k2 ? k2 : q1;
+      if (c->fp_fused == 2) { ProjectFpBox f = {d, mode, s0, scale}; Box b = {1, d.mx - 1, 1, d.my - 1, q0, q1}; return launch(c, b, f); }
+      if (run_projfp_march(c->stream, P, q0, q1, &c->launches)) { set_err(c, "projection kernel launch failed"); return VFS_ERR_CUDA; }
       return 0;
     };
     const bool ovl = multi && can_overlap(c) && d.nzl >= 10;
@@ -1175,6 +1177,19 @@ static int zero_scalars(vfs_ctx *c, int s0, int n) {
   memset(c->d.s[s0], 0, (size_t)n * c->scalar_len * sizeof(double));
 #endif
   return 0;
+}
+
+// ---- Pressure_Gradient (momentum.c:203-439) ---------------------------------------------------------------
+extern "C" int vfs_pressure_gradient(vfs_ctx *c, double k_forcing) {
+  if (!c) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  RUN(ensure_iaj(c));
+  const Grp gp = grp(S_P, 1);
+  RUN(g2l(c, gp, 2, 2));                                              // momentum.c:247-248
+  if (any_per(c)) { RUN(node_copy(c, gp)); RUN(g2l(c, gp, 2, 2)); }    // :250-286
+  RUN(zero_scalars(c, S_DP0, 3));                                     // VecSet(dP, 0.), :313
+  { PressureGradient f = {d, k_forcing}; RUN(launch(c, box_interior(c), f)); }
+  return vfs_sync(c);
 }
 
 // ---- legacy Convection / Viscous (rhs.c:751, 1071) --------------------------------------------------------

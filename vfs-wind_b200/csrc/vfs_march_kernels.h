@@ -563,6 +563,44 @@ struct Les3March {
 // remap of the cell whose Fp is evaluated; non-periodic boundary nodes' Fp is never used (their components are
 // masked, momentum.c:1833-1841).  Arithmetic and operand order are FpCell's and project_fp's: bitwise the staged
 // result.  Boundary NODES of the slab (mask 7: no projection) are assembled by the staged functor on the shell.
+// Fp at node (i, j, k) as the projection reads it: the periodic node copies of Fp (momentum.c:1687-1713: node m-1
+// takes the value of node 1) folded into an index remap; zero where the value is never used (non-periodic boundary
+// nodes: the component that would read it is masked, momentum.c:1833-1841)
+VFS_HD void fp_as_projected(const VfsDev &d, int i, int j, int k, double f[3]) {
+  f[0] = f[1] = f[2] = 0;
+  bool ok = i <= d.mx - 1 && j <= d.my - 1;
+  int kg = k + d.kofs;
+  if (ok && i == d.mx - 1) { if (d.perx) i = 1; else ok = false; }
+  if (ok && j == d.my - 1) { if (d.pery) j = 1; else ok = false; }
+  if (ok && kg == d.mz - 1) {
+    // the image of global plane 1: the plane itself on a single rank, the ghost plane two above on the last rank
+    if (d.perz) { k = d.single_rank ? 1 : k + 2; kg = 1; } else ok = false;
+  }
+  if (ok) fp_cell_value(d, i, j, kg, d.idx(i, j, k), f);
+}
+// One-thread-per-node form of the same fusion: Fp evaluated at the node and its +i, +j, +k neighbours (the re-reads
+// hit L1 / L2), no shared memory, no barrier.
+struct ProjectFpBox {
+  VfsDev d; int mode, s0; double scale;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    const int m = rhs_mask(d, i, j, kg, p);
+    double f[3], fi[3], fj[3], fk[3];
+    fp_as_projected(d, i, j, k, f); fp_as_projected(d, i + 1, j, k, fi); fp_as_projected(d, i, j + 1, k, fj); fp_as_projected(d, i, j, k + 1, fk);
+    const double ia = d.s[S_IAJ][p];
+    double rr[3];
+    { const long q = p + 1; const double a = 2. / (ia + d.s[S_IAJ][q]);
+      rr[0] = (0.5 * (d.s[S_CSI0][p] * f[0] + d.s[S_CSI1][p] * f[1] + d.s[S_CSI2][p] * f[2]) + 0.5 * (d.s[S_CSI0][q] * fi[0] + d.s[S_CSI1][q] * fi[1] + d.s[S_CSI2][q] * fi[2])) * a; }
+    { const long q = p + d.sj; const double a = 2. / (ia + d.s[S_IAJ][q]);
+      rr[1] = (0.5 * (d.s[S_ETA0][p] * f[0] + d.s[S_ETA1][p] * f[1] + d.s[S_ETA2][p] * f[2]) + 0.5 * (d.s[S_ETA0][q] * fj[0] + d.s[S_ETA1][q] * fj[1] + d.s[S_ETA2][q] * fj[2])) * a; }
+    { const long q = p + d.sk; const double a = 2. / (ia + d.s[S_IAJ][q]);
+      rr[2] = (0.5 * (d.s[S_ZET0][p] * f[0] + d.s[S_ZET1][p] * f[1] + d.s[S_ZET2][p] * f[2]) + 0.5 * (d.s[S_ZET0][q] * fk[0] + d.s[S_ZET1][q] * fk[1] + d.s[S_ZET2][q] * fk[2])) * a; }
+    if (mode == 0) { for (int a = 0; a < 3; a++) d.s[s0 + a][p] = ((m >> a) & 1) ? 0. : d.s[s0 + a][p] + scale * rr[a]; }
+    else { for (int a = 0; a < 3; a++) d.s[S_R0 + a][p] = snes_assemble(d, a, p, (m >> a) & 1, rr[a]); }
+  }
+};
+
 struct ProjFpMarch {
   static constexpr int TX = 32, TY = 8, NT = TX * TY, FX = TX + 1, FY = TY + 1, FN = FX * FY, NBUF = 3;
   static constexpr long SMEM_D = (long)NBUF * 3 * FN;
@@ -570,16 +608,8 @@ struct ProjFpMarch {
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 1) / TX; }
   static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 1) / TY; }
   VFS_HD void fp_slot(double *buf, int slot, int i, int j, int k) const {
-    double f[3] = {0, 0, 0};
-    bool ok = i <= d.mx - 1 && j <= d.my - 1;
-    int kg = k + d.kofs;
-    if (ok && i == d.mx - 1) { if (d.perx) i = 1; else ok = false; }
-    if (ok && j == d.my - 1) { if (d.pery) j = 1; else ok = false; }
-    if (ok && kg == d.mz - 1) {
-      // the image of global plane 1: the plane itself on a single rank, the ghost plane two above on the last rank
-      if (d.perz) { k = d.single_rank ? 1 : k + 2; kg = 1; } else ok = false;
-    }
-    if (ok) fp_cell_value(d, i, j, kg, d.idx(i, j, k), f);
+    double f[3];
+    fp_as_projected(d, i, j, k, f);
     buf[slot] = f[0]; buf[FN + slot] = f[1]; buf[2 * FN + slot] = f[2];
   }
   // phase A: Fp of plane kq -> buffer kq mod 3 (tile nodes + the halo column i0+TX and row j0+TY)

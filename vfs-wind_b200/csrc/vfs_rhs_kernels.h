@@ -258,6 +258,66 @@ struct LegacyDiv {
   }
 };
 
+
+// ---- Pressure_Gradient (Source/momentum.c:203-439) ------------------------------------
+// dP_D = (dP/dcsi g_D1 + dP/deta g_D2 + dP/dzeta g_D3) * J_face on the D-face between p and p + e_D, with
+// g_Dm = (metric m at the face) . (metric D at the face); the difference along D is two-point (the periodic image
+// at index m+1 for the last face, :347,372,397), the tangential ones are the four-point averages that fall back to
+// one-sided pairs next to an IB node ((int)(nvert + 0.5) == 1) or a non-periodic domain end (:349-395).  Face
+// metrics are rebuilt from the centre metrics (NEWMETRIC), as in the flux kernels.
+struct PressureGradient {
+  VfsDev d; double kforce;
+  VFS_HD bool ib(long q) const { return (int)(d.s[S_NV][q] + 0.5) == 1; }
+  // tangential difference along T (stride t, index c of m, periodicity per) on the face between p and p + n
+  VFS_HD double tdiff(long p, long n, long t, int c, int m, int per) const {
+    const double *P = d.s[S_P];
+    if (ib(p + t) || ib(p + t + n) || (c == m - 2 && !per)) return (P[p] - P[p - t] + P[p + n] - P[p + n - t]) * 0.5;
+    if (ib(p - t) || ib(p - t + n) || (c == 1 && !per)) return (P[p + t] - P[p] + P[p + t + n] - P[p + n]) * 0.5;
+    return (P[p + t] - P[p - t] + P[p + n + t] - P[p + n - t]) * 0.25;
+  }
+  VFS_HD double ndiff(long p, long n, int c, int m, int per) const {
+    const double *P = d.s[S_P];
+    return (c == m - 2 && per) ? P[p + 3 * n] - P[p] : P[p + n] - P[p];
+  }
+  template <int D> VFS_HD void face(long p, V3 &cs, V3 &et, V3 &ze, double &aj) const {
+    GlobalAcc A = {d, p};
+#define VFS_F3(s0) mk3(0.5 * A.template met<D>(s0, 0) + 0.5 * A.template met<D>(s0, 1), 0.5 * A.template met<D>(s0 + 1, 0) + 0.5 * A.template met<D>(s0 + 1, 1), \
+                       0.5 * A.template met<D>(s0 + 2, 0) + 0.5 * A.template met<D>(s0 + 2, 1))
+    cs = VFS_F3(0); et = VFS_F3(3); ze = VFS_F3(6);
+#undef VFS_F3
+    aj = 2. / (A.template iaj<D>(0) + A.template iaj<D>(1));
+  }
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k), si = 1, sj = d.sj, sk = d.sk;
+    const double *nv = d.s[S_NV];
+    V3 cs, et, ze; double aj;
+    {
+      face<0>(p, cs, et, ze, aj);
+      const double dc = ndiff(p, si, i, d.mx, d.perx), de = tdiff(p, si, sj, j, d.my, d.pery), dz = tdiff(p, si, sk, kg, d.mz, d.perz);
+      double v = (dc * dot3(cs, cs) + de * dot3(et, cs) + dz * dot3(ze, cs)) * aj / 1.0;
+      if (nv[p] + nv[p + si] > 0.1 || (!d.perx && i == d.mx - 2)) v = 0;
+      d.s[S_DP0][p] = v;
+    }
+    {
+      face<1>(p, cs, et, ze, aj);
+      const double dc = tdiff(p, sj, si, i, d.mx, d.perx), de = ndiff(p, sj, j, d.my, d.pery), dz = tdiff(p, sj, sk, kg, d.mz, d.perz);
+      double v = (dc * dot3(cs, et) + de * dot3(et, et) + dz * dot3(ze, et)) * aj / 1.0;
+      if (nv[p] + nv[p + sj] > 0.1 || (!d.pery && j == d.my - 2)) v = 0;
+      d.s[S_DP1][p] = v;
+    }
+    {
+      face<2>(p, cs, et, ze, aj);
+      const double dc = tdiff(p, sk, si, i, d.mx, d.perx), de = tdiff(p, sk, sj, j, d.my, d.pery);
+      double dz = ndiff(p, sk, kg, d.mz, d.perz);
+      if (d.perz) dz += kforce * (1. / aj / sqrt(dot3(ze, ze)));          // momentum.c:399-411
+      double v = (dc * dot3(cs, ze) + de * dot3(et, ze) + dz * dot3(ze, ze)) * aj / 1.0;
+      if (nv[p] + nv[p + sk] > 0.1 || (!d.perz && kg == d.mz - 2)) v = 0;
+      d.s[S_DP2][p] = v;
+    }
+  }
+};
+
 // momentum.c:1548-1678: flux divergence with 4th-order correction + viscous divergence -> Fp of the cell at
 // node p = (i, j, k); kg = global k of the cell (for a ghost plane across the periodic seam: the plane it images)
 VFS_HD void fp_cell_value(const VfsDev &d, int i, int j, int kg, long p, double out[3]) {

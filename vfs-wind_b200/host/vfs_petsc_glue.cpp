@@ -13,6 +13,8 @@
 //   Compute_Smagorinsky_Constant_1   Source/les.c:75          -> vfs_les_cs
 //   Compute_eddy_viscosity_LES       Source/les.c:1143        -> vfs_les_nut
 //   Convection / Viscous (legacy)    Source/rhs.c:751,1071    -> vfs_convection / vfs_viscous
+//   Pressure_Gradient                Source/momentum.c:203    -> vfs_pressure_gradient
+//   SNESSolve in Implicit_MatrixFree Source/implicitsolver.c:4299 -> vfs_glue_snes_solve -> vfs_momentum_solve
 //
 // Data contract: the UserCtx Vecs stay the source of truth on the host (the rest of VFS-Wind —
 // Poisson solve, IBM, turbine models, I/O — keeps reading them), so each entry point uploads the
@@ -35,6 +37,9 @@ extern int levelset_weno, freesurface_wallmodel, air_flow_levelset;
 extern int laplacian, clark, central, testfilter_ik, viscosity_wallmodel, levelset, rans, skew;
 extern int i_periodic, j_periodic, k_periodic, ii_periodic, jj_periodic, kk_periodic, i_homo_filter, j_homo_filter, k_homo_filter;
 extern PetscReal max_cs;
+extern double mean_pressure_gradient, inlet_flux;
+extern PetscInt inletprofile;
+extern PetscTruth dpdz_set;
 extern double roughness_size;
 extern PetscTruth rstart_flg;
 
@@ -288,6 +293,24 @@ PetscErrorCode Viscous(UserCtx *user, Vec Ucont, Vec Ucat, Vec Visc) {
   ck(s, vfs_viscous(s->ctx), "vfs_viscous");
   pull(user, s, VFS_VISC, 3, Visc, false);
   return 0;
+}
+
+// momentum.c:203-439.  Side effects kept: lP's ghosts / periodic boundary nodes and P are refreshed (:247-286).
+void Pressure_Gradient(UserCtx *user, Vec dP) {
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, user->P, 1, VFS_P);
+  double kf = 0;                                                       // :399-411
+  if (k_periodic || kk_periodic) {
+    if (dpdz_set) kf = mean_pressure_gradient;
+    else if (inletprofile != 17) kf = (user->mean_k_flux - inlet_flux) / user->dt / user->mean_k_area;
+  }
+  ck(s, vfs_pressure_gradient(s->ctx, kf), "vfs_pressure_gradient");
+  pull(user, s, VFS_DP, 3, dP, false);
+  if (ii_periodic || jj_periodic || kk_periodic) {
+    pull(user, s, VFS_P, 1, user->lP, true);
+    DALocalToGlobal(user->da, user->lP, INSERT_VALUES, user->P);
+  } else { DAGlobalToLocalBegin(user->da, user->P, INSERT_VALUES, user->lP); DAGlobalToLocalEnd(user->da, user->P, INSERT_VALUES, user->lP); }
 }
 
 PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
