@@ -37,6 +37,7 @@ typedef int MPI_Op;
 #define MPI_MAX 2
 #define MPI_MIN 3
 #define MPIU_SCALAR MPI_DOUBLE
+#define MPIU_REAL MPI_DOUBLE
 #define MPIU_INT MPI_INT
 
 struct _p_DA; typedef struct _p_DA *DA;

@@ -128,6 +128,7 @@ struct vfs_ctx {
   double *wm_table = nullptr;    // Cabot wall law: table of int dy+/(1 + nu_t/nu), built on first use
   bool has_solid = true;         // some node has (int)(nvert + 0.1) == 3 (set when nvert is uploaded; true = unknown)
   bool lesgeo_valid = false;     // S_LFINV..S_LF2 match the current metrics and nvert mask
+  bool les_bnd_valid = false;    // the static boundary-node values of the LES intermediates (w, |S|S_ij = 0) are stored
   unsigned char *near = nullptr; // near-solid byte mask (VfsDev::near), one byte per padded node
   bool near_valid = false;
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
@@ -168,10 +169,11 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
 // disjoint index ranges: the two i planes (j, k full), the two j planes (i inner) and the owned global
 // k = 0 / mz-1 planes (i, j inner).  [ka, kb) is the local k range of the i- and j-plane parts (it may
 // reach into the k ghost planes, see node_copy).  Replaces 4-6 thin launches per boundary operation.
-struct Shell { int mx, my, ka, nk, kp[4], nkp; long nA, nB, nC; };
+struct Shell { int mx, my, ka, nk, kp[4], nkp; long nA, nB, nC; int iB, wB, iC, wC, jC, hC; };      // i range of the j planes; i, j ranges of the k planes
+#define SHELL_PERIODIC_ONLY 8       // make_shell face mask bit: only the face sets of periodic directions
 // images: also visit the ghost planes that image the global k = 0 / mz-1 planes across the periodic seam
 // (local plane -1 on the first rank, nzl on the last), for the operations contra2cart replays on ghost planes
-static Shell make_shell(const VfsDev &d, int ka, int kb, bool images = false) {
+static Shell make_shell(const VfsDev &d, int ka, int kb, bool images = false, int faces = 7) {
   Shell s; s.mx = d.mx; s.my = d.my; s.ka = ka; s.nk = kb - ka; s.nkp = 0;
   if (d.kofs == 0) s.kp[s.nkp++] = 0;
   if (d.kofs + d.nzl == d.mz) s.kp[s.nkp++] = d.nzl - 1;
@@ -179,7 +181,11 @@ static Shell make_shell(const VfsDev &d, int ka, int kb, bool images = false) {
     if (d.kofs == 0 && ka <= -1) s.kp[s.nkp++] = -1;
     if (d.kofs + d.nzl == d.mz && kb >= d.nzl + 1) s.kp[s.nkp++] = d.nzl;
   }
-  s.nA = 2L * d.my * s.nk; s.nB = 2L * (d.mx - 2) * s.nk; s.nC = (long)s.nkp * (d.mx - 2) * (d.my - 2);
+  if (faces & SHELL_PERIODIC_ONLY) faces = (d.perx ? 1 : 0) | (d.pery ? 2 : 0) | (d.perz ? 4 : 0);
+  // a face set that is left out hands its edge nodes to the sets after it (they widen to the full extent)
+  s.iB = (faces & 1) ? 1 : 0; s.wB = (faces & 1) ? d.mx - 2 : d.mx; s.iC = s.iB; s.wC = s.wB;
+  s.jC = (faces & 2) ? 1 : 0; s.hC = (faces & 2) ? d.my - 2 : d.my;
+  s.nA = (faces & 1) ? 2L * d.my * s.nk : 0; s.nB = (faces & 2) ? 2L * s.wB * s.nk : 0; s.nC = (faces & 4) ? (long)s.nkp * s.wC * s.hC : 0;
   return s;
 }
 // (32-bit index arithmetic: 64-bit divisions cost more than the copies these kernels do; a shell never has 2^31 nodes)
@@ -192,14 +198,14 @@ template <class F> VFS_HD void shell_visit(const F &f, const Shell &s, long tl) 
     f(side ? s.mx - 1 : 0, (int)(r - q * (unsigned)s.my), s.ka + (int)q);
   } else if (t < nA + nB) {
     t -= nA;
-    const unsigned w = (unsigned)(s.mx - 2), per = w * (unsigned)s.nk; const unsigned side = t >= per ? 1u : 0u; const unsigned r = t - side * per;
+    const unsigned w = (unsigned)s.wB, per = w * (unsigned)s.nk; const unsigned side = t >= per ? 1u : 0u; const unsigned r = t - side * per;
     const unsigned q = r / w;
-    f(1 + (int)(r - q * w), side ? s.my - 1 : 0, s.ka + (int)q);
+    f(s.iB + (int)(r - q * w), side ? s.my - 1 : 0, s.ka + (int)q);
   } else {
     t -= nA + nB;
-    const unsigned w = (unsigned)(s.mx - 2), per = w * (unsigned)(s.my - 2); const unsigned qq = t / per; const unsigned r = t - qq * per;
+    const unsigned w = (unsigned)s.wC, per = w * (unsigned)s.hC; const unsigned qq = t / per; const unsigned r = t - qq * per;
     const unsigned q = r / w;
-    f(1 + (int)(r - q * w), 1 + (int)q, s.kp[qq]);
+    f(s.iC + (int)(r - q * w), s.jC + (int)q, s.kp[qq]);
   }
 }
 #ifndef VFS_EMU
@@ -208,8 +214,8 @@ template <class F> __global__ void __launch_bounds__(256) k_shell(F f, Shell s) 
   if (t < s.nA + s.nB + s.nC) shell_visit(f, s, t);
 }
 #endif
-template <class F> static int launch_shell(vfs_ctx *c, int ka, int kb, const F &f, bool images = false) {
-  const Shell s = make_shell(c->d, ka, kb, images);
+template <class F> static int launch_shell(vfs_ctx *c, int ka, int kb, const F &f, bool images = false, int faces = 7) {
+  const Shell s = make_shell(c->d, ka, kb, images, faces);
   const long n = s.nA + s.nB + s.nC;
   if (n <= 0) return 0;
   c->launches++;
@@ -342,13 +348,15 @@ template <class F> __global__ void __launch_bounds__(256) k_linear(F f, long n) 
   if (t < n) f(t);
 }
 #endif
-// single rank: the whole refresh (mode 1: g2l, mode 3: g2l + node_copy + g2l) as one launch, see RefreshFused
-static int refresh_fused(vfs_ctx *c, const Grp &g, int mode) {
+// single rank: the whole refresh (mode 1: g2l, mode 3: g2l + node_copy + g2l) as one launch, see RefreshFused.
+// depth: ghost layers refreshed in every periodic direction (how deep the field is read before its next refresh)
+static int refresh_fused(vfs_ctx *c, const Grp &g, int mode, int depth = VFS_G) {
   const VfsDev &d = c->d;
   if (!any_per_d(d)) return 0;
-  RefreshSlabs S;
-  S.ext[0] = d.perx ? d.mx + 2 * VFS_G : d.mx; S.ext[1] = d.pery ? d.my + 2 * VFS_G : d.my; S.ext[2] = d.perz ? d.mz + 2 * VFS_G : d.mz;
-  const long W = 2 * VFS_G + 2;
+  if (!c->halo_trim || depth > VFS_G) depth = VFS_G;
+  RefreshSlabs S; S.depth = depth;
+  S.ext[0] = d.perx ? d.mx + 2 * depth : d.mx; S.ext[1] = d.pery ? d.my + 2 * depth : d.my; S.ext[2] = d.perz ? d.mz + 2 * depth : d.mz;
+  const long W = 2 * depth + 2;
   S.n[0] = d.perx ? W * S.ext[1] * S.ext[2] : 0; S.n[1] = d.pery ? W * S.ext[0] * S.ext[2] : 0; S.n[2] = d.perz ? W * S.ext[0] * S.ext[1] : 0;
   const long n = S.n[0] + S.n[1] + S.n[2];
   RefreshFused f = {d, g, mode, S};
@@ -417,7 +425,7 @@ static int ovl_join(vfs_ctx *c) {
 }
 // DAGlobalToLocal / DALocalToLocal
 static int g2l(vfs_ctx *c, const Grp &g, int lo = VFS_G, int hi = VFS_G) {
-  if (c->prm.nranks == 1 && c->fuse_refresh) return refresh_fused(c, g, 1);
+  if (c->prm.nranks == 1 && c->fuse_refresh) return refresh_fused(c, g, 1, lo > hi ? lo : hi);
   RUN(wrap_ij(c, g)); return halo_k(c, g, false, lo, hi);
 }
 // The refresh that follows a node_copy of a field whose ghosts were refreshed just before it: the
@@ -432,7 +440,7 @@ static int node_copy(vfs_ctx *c, const Grp &g) {
   // planes in a single-rank run, where this copy updates them; apply it there too so that the
   // result does not depend on the number of ranks (wrap-around ghosts stay stale, as in 1 rank).
   const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;
-  return launch_shell(c, ka, kb, f);      // the functor acts on nodes of periodic boundary planes only
+  return launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY);      // the functor acts on nodes of periodic boundary planes only
 }
 static bool any_per(const vfs_ctx *c) { return c->d.perx || c->d.pery || c->d.perz; }
 
@@ -721,7 +729,7 @@ extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
   if (field == VFS_AJ) c->iaj_valid = false;
-  if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = false;
+  if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = c->les_bnd_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   if (field == VFS_NVERT) { c->near_valid = false; c->wall_marked = false; }
   RUN(h2d_stage(c, host, FIELD[field].dof));
@@ -800,14 +808,18 @@ extern "C" int vfs_form_metrics(vfs_ctx *c) {
   Grp g = grp(S_CSI0, 10);
   RUN(g2l(c, g));
   if (any_per(c)) { RUN(node_copy(c, g)); RUN(g2l(c, g)); }
-  c->iaj_valid = false; c->sabs_valid = false; c->lesgeo_valid = false;
+  c->iaj_valid = false; c->sabs_valid = false; c->lesgeo_valid = c->les_bnd_valid = false;
   return vfs_sync(c);
 }
 
 // ---- Contra2Cart ------------------------------------------------------------------------------------
 struct CopyScalar3 { VfsDev d; int from, to; VFS_HD void operator()(int i, int j, int k) const { long p = d.idx(i, j, k); for (int a = 0; a < 3; a++) d.s[to + a][p] = d.s[from + a][p]; } };
 
-static int run_les_derive_boundary(vfs_ctx *c) { LesDeriveBoundary f = {c->d}; return launch_shell(c, 0, c->d.nzl, f); }
+static int run_les_derive_boundary(vfs_ctx *c) {
+  LesDeriveBoundary f = {c->d, (c->les_bnd_valid && c->halo_trim) ? 1 : 0};
+  c->les_bnd_valid = true;
+  return launch_shell(c, 0, c->d.nzl, f);
+}
 
 // Contra2Cart_2 (rhs.c:65-749).  Between ranks, ucat's ghost planes are not exchanged: every operation
 // of the function is REPLAYED on the three ghost planes either side of the slab (C2C_EXT), from the
@@ -834,11 +846,11 @@ static int contra2cart(vfs_ctx *c) {
   auto copy_nodes = [&](const Grp &g) -> int {
     if (!multi) return node_copy(c, g);
     NodeCopy f = {d, g, 1};
-    return launch_shell(c, ka, kb, f, true);
+    return launch_shell(c, ka, kb, f, true, SHELL_PERIODIC_ONLY);
   };
   // ghost refresh, periodic node copies, ghost refresh
   auto refresh3 = [&]() -> int {
-    if (!multi && c->fuse_refresh) return refresh_fused(c, gu, 3);
+    if (!multi && c->fuse_refresh) return refresh_fused(c, gu, 3, 3);      // ucat is read at most 3 deep (index -3 / m+2: the reference's DA ghost width)
     RUN(refresh(false));
     if (any_per(c)) { RUN(copy_nodes(gu)); RUN(refresh(true)); }
     return 0;
@@ -894,7 +906,7 @@ static int ib_bc(vfs_ctx *c) {
 #endif
     { IbBcMarkWall f = {d}; RUN(launch(c, box_interior(c), f)); }
     RUN(g2l(c, grp(S_NV, 1)));
-    c->wall_marked = true; c->near_valid = false; c->lesgeo_valid = false; c->sabs_valid = false;
+    c->wall_marked = true; c->near_valid = false; c->lesgeo_valid = c->les_bnd_valid = false; c->sabs_valid = false;
   }
   if (any_per(c)) RUN(node_copy(c, grp(S_U0, 3)));                   // momentum.c:2086-2107
   if (d.immersed) { IbBcFaces f = {d}; RUN(launch(c, box_interior(c), f)); }
@@ -1090,18 +1102,18 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     ev_rec(c, 2 * VFS_T_PROJECT);
     if (!ovl) {
       RUN(halo_k(c, multi ? gall : gk, false, 3, 2));
-      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
       RUN(shell_nodes());
       RUN(march(k1, k2));
     } else {
       // the i/j-plane copies of the owned planes go first (they are part of what the neighbours receive); the cells
       // of local planes 2 .. nzl-4 and the Fp planes up to nzl-3 touch no k ghost plane and no seam copy
-      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, 0, d.nzl, f)); }
+      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, 0, d.nzl, f, false, SHELL_PERIODIC_ONLY)); }
       RUN(ovl_exchange(c, gall, 3, 2));
       RUN(shell_nodes());
       RUN(march(2, d.nzl - 3));
       RUN(ovl_join(c));
-      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
       RUN(march(0, 2)); RUN(march(d.nzl - 3, d.nzl));
     }
     ev_rec(c, 2 * VFS_T_PROJECT + 1);
@@ -1118,19 +1130,19 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     FpCell fp = {d};
     if (!ovl) {
       RUN(halo_k(c, gk, false, 3, 2));      // Fp reads faces k-2 .. k+1 (k-4 / k+3 across the periodic seam = ghost planes -3 / nzl+1)
-      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f)); }
+      if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
       for (int n = 0; n < S.n; n++) RUN(launch(c, S.fp[n], fp));     // momentum.c:1548-1678
     } else {
       // Fp of a cell reads the k-face fluxes of planes k-2 .. k+1 (k-4 / k+3 across the periodic seam): the cells
       // of local planes 2 .. nzl-3 never touch a k ghost plane and run while the exchange is in flight
       RUN(ovl_exchange(c, gk, 3, 2));
-      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, ka, kb, f)); }
+      if (any_per(c)) { NodeCopyFlux f = {d, 1}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
       Box in = S.fp[0], lo = S.fp[0], hi = S.fp[0];
       in.k0 = in.k0 > 2 ? in.k0 : 2; in.k1 = in.k1 < d.nzl - 2 ? in.k1 : d.nzl - 2;
       lo.k1 = in.k0; hi.k0 = in.k1;
       RUN(launch(c, in, fp));
       RUN(ovl_join(c));
-      if (d.perz) { NodeCopyFlux f = {d, 2}; RUN(launch_shell(c, ka, kb, f)); }
+      if (d.perz) { NodeCopyFlux f = {d, 2}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
       RUN(launch(c, lo, fp)); RUN(launch(c, hi, fp));
     }
   }

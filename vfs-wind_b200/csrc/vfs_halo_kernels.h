@@ -87,7 +87,7 @@ struct NodeCopy {
 // are interior in every periodic direction and destinations are not, so the in-place update is race-free.
 // Visited as three slabs (one per direction: its 2G ghost planes + 2 boundary planes, full extent of the other
 // directions); a node in two slabs is written twice with the same value.
-struct RefreshSlabs { long n[3]; int ext[3]; };       // nodes per slab; extent (incl. ghosts if periodic) per direction
+struct RefreshSlabs { long n[3]; int ext[3]; int depth; };       // nodes per slab; extent (incl. ghosts if periodic) per direction; ghost layers refreshed
 struct RefreshFused {
   VfsDev d; Grp g; int mode; RefreshSlabs S;
   VFS_HD static int map1(int x, int m) { return x < 0 ? x + m : (x >= m ? x - m : x); }
@@ -100,11 +100,11 @@ struct RefreshFused {
     const long p = d.idx(i, j, k), q = d.idx(a, b, c);
     for (int n = 0; n < g.n; n++) d.s[g.sid[n]][p] = d.s[g.sid[n]][q];
   }
-  // shell coordinate s in [0, 2G+2) of a direction with m nodes -> -G..0, m-1..m+G-1
-  VFS_HD static int shell(int s, int m) { return s <= VFS_G ? s - VFS_G : m - 1 + (s - VFS_G - 1); }
+  // shell coordinate s in [0, 2 depth + 2) of a direction with m nodes -> -depth..0, m-1..m+depth-1
+  VFS_HD int shell(int s, int m) const { return s <= S.depth ? s - S.depth : m - 1 + (s - S.depth - 1); }
   VFS_HD void operator()(long tl) const {          // 32-bit index arithmetic (the slabs have far fewer than 2^31 nodes)
-    const int lo[3] = {d.perx ? -VFS_G : 0, d.pery ? -VFS_G : 0, d.perz ? -VFS_G : 0};
-    const unsigned W = 2 * VFS_G + 2, e0 = (unsigned)S.ext[0], e1 = (unsigned)S.ext[1];
+    const int lo[3] = {d.perx ? -S.depth : 0, d.pery ? -S.depth : 0, d.perz ? -S.depth : 0};
+    const unsigned W = 2 * S.depth + 2, e0 = (unsigned)S.ext[0], e1 = (unsigned)S.ext[1];
     unsigned t = (unsigned)tl;
     const unsigned n0 = (unsigned)S.n[0], n1 = (unsigned)S.n[1];
     if (t < n0) {                                       // i slab: shell x ext[1] x ext[2], shell fastest

@@ -123,11 +123,18 @@ VFS_HD void les_derive_store_m(const VfsDev &d, long n, const double g[3][3], do
   d.s[S_LSS3][n] = (0.5 * (g[1][1] + g[1][1])) * S; d.s[S_LSS4][n] = (0.5 * (g[1][2] + g[2][1])) * S; d.s[S_LSS5][n] = (0.5 * (g[2][2] + g[2][2])) * S;
 }
 // domain-boundary nodes: grad u and |S| are zero there in the reference (VecSet, les.c:183-186)
+// dynamic_only: only the part that changes with the velocity (U = [csi;eta;zet] u) is rewritten; the weight w (a function
+// of nvert / aj) and the zero |S|S_ij of the boundary nodes were stored when the grid / mask last changed, and nothing
+// else writes them there (the periodic node copies that follow overwrite the periodic planes' |S|S_ij every step anyway)
 struct LesDeriveBoundary {
-  VfsDev d;
+  VfsDev d; int dynamic_only;
   VFS_HD void operator()(int i, int j, int k) const {
-    const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    les_derive_store(d, d.idx(i, j, k), z, 0.);
+    const long n = d.idx(i, j, k);
+    if (!dynamic_only) { const double z[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; les_derive_store(d, n, z, 0.); return; }
+    const double u0 = d.s[S_U0][n], u1 = d.s[S_U1][n], u2 = d.s[S_U2][n];
+    d.s[S_LU0][n] = u0 * d.s[S_CSI0][n] + u1 * d.s[S_CSI1][n] + u2 * d.s[S_CSI2][n];
+    d.s[S_LU1][n] = u0 * d.s[S_ETA0][n] + u1 * d.s[S_ETA1][n] + u2 * d.s[S_ETA2][n];
+    d.s[S_LU2][n] = u0 * d.s[S_ZET0][n] + u1 * d.s[S_ZET1][n] + u2 * d.s[S_ZET2][n];
   }
 };
 
