@@ -12,6 +12,7 @@
  *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
  *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
  *   vfs_pressure_gradient   <- Pressure_Gradient(UserCtx*, Vec dP)           momentum.c:203
+ *   vfs_calc_f_eul / vfs_calc_u_lagr <- Calc_F_eul / Calc_U_lagr            rotor_model.c:3668,2937
  *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4299
  *
  * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
@@ -187,6 +188,26 @@ int vfs_solver_defaults(vfs_solver_params *p);
 int vfs_momentum_solve(vfs_ctx *c, const vfs_solver_params *p, vfs_solver_info *info);
 /* free the Krylov basis and work vectors (restart + 8 vectors of nzl*my*mx*3 doubles, kept between solves) */
 int vfs_momentum_release(vfs_ctx *c);
+
+/* Actuator forcing.  vfs_actuator = the IBMNodes fields (Source/variables.h:159,188,192) the two
+ * functions read, one per turbine / nacelle object; index windows are GLOBAL node indices, upper bounds exclusive.
+ *   vfs_calc_f_eul  <- Calc_F_eul(UserCtx*, IBMNodes*, FSInfo*, n, dh, df)   Source/rotor_model.c:3668-3960
+ *       VFS_F_EUL (+)= the elements' forces spread with the delta function `df` (0: 2h hat, 7: Gaussian of half width
+ *       halfwidth_dfunc, else the smoothed 4h function), then zeroed near solid cells and domain boundaries and its
+ *       ghosts refreshed.  accumulate = 0 zeroes F_eul first (VecSet(lF_eul, 0), solvers.c:484).
+ *   vfs_calc_u_lagr <- Calc_U_lagr(UserCtx*, IBMNodes*, FSInfo*, n)          Source/rotor_model.c:2937-3031
+ *       U_lagr_{x,y,z}[l] = sum over the element's window of VFS_UCAT * dfunc_s3h^3, summed over the ranks
+ *       (MPI_Allreduce there, ncclAllReduce here); the periodic-turbine bookkeeping that follows (:3034-3150) is
+ *       host logic and stays with the caller. */
+typedef struct vfs_actuator {
+  int n_elmt;
+  const double *cent_x, *cent_y, *cent_z, *dA;
+  const double *F_lagr_x, *F_lagr_y, *F_lagr_z;
+  double *U_lagr_x, *U_lagr_y, *U_lagr_z;
+  const int *i_min, *i_max, *j_min, *j_max, *k_min, *k_max;
+} vfs_actuator;
+int vfs_calc_f_eul(vfs_ctx *c, int n_objects, const vfs_actuator *objs, int df, double halfwidth_dfunc, int forcewidthfixed, const double *dh_fixed3, int accumulate);
+int vfs_calc_u_lagr(vfs_ctx *c, int n_objects, const vfs_actuator *objs);
 
 /* number of kernels launched by this context since creation (bench `gpu_launches`) */
 long vfs_launch_count(vfs_ctx *c);

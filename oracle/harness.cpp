@@ -86,6 +86,23 @@ int ref_FormFunction_SNES(UserCtx *u, Vec x, Vec f) { return FormFunction_SNES((
 void ref_Compute_Smagorinsky_Constant_1(UserCtx *u) { Compute_Smagorinsky_Constant_1(u, u->lUcont, u->lUcat); }
 void ref_Compute_eddy_viscosity_LES(UserCtx *u) { Compute_eddy_viscosity_LES(u); }
 void ref_Pressure_Gradient(UserCtx *u, Vec dp, double mean_k_flux, double mean_k_area) { u->mean_k_flux = mean_k_flux; u->mean_k_area = mean_k_area; Pressure_Gradient(u, dp); }
+// actuator forcing (rotor_model.c:3668, 2937): IBMNodes with just the arrays the two functions read
+IBMNodes *ref_actuator_new(int n_elmt) {
+  IBMNodes *b = (IBMNodes *)calloc(1, sizeof(IBMNodes));
+  b->n_elmt = n_elmt;
+  double **d[] = {&b->cent_x, &b->cent_y, &b->cent_z, &b->dA, &b->F_lagr_x, &b->F_lagr_y, &b->F_lagr_z, &b->U_lagr_x, &b->U_lagr_y, &b->U_lagr_z};
+  for (unsigned q = 0; q < sizeof(d) / sizeof(d[0]); q++) *d[q] = (double *)calloc(n_elmt, sizeof(double));
+  int **w[] = {&b->i_min, &b->i_max, &b->j_min, &b->j_max, &b->k_min, &b->k_max};
+  for (unsigned q = 0; q < 6; q++) *w[q] = (int *)calloc(n_elmt, sizeof(int));
+  return b;
+}
+double *ref_actuator_d(IBMNodes *b, int which) {
+  double *d[] = {b->cent_x, b->cent_y, b->cent_z, b->dA, b->F_lagr_x, b->F_lagr_y, b->F_lagr_z, b->U_lagr_x, b->U_lagr_y, b->U_lagr_z};
+  return d[which];
+}
+int *ref_actuator_i(IBMNodes *b, int which) { int *w[] = {b->i_min, b->i_max, b->j_min, b->j_max, b->k_min, b->k_max}; return w[which]; }
+int ref_Calc_F_eul(UserCtx *u, IBMNodes *b, int df) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_F_eul(u, b, f, 1, 1.0, df); free(f); return r; }
+int ref_Calc_U_lagr(UserCtx *u, IBMNodes *b) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_U_lagr(u, b, f, 1); free(f); return r; }
 int ref_Convection(UserCtx *u, Vec conv) { return Convection(u, u->lUcont, u->lUcat, conv); }
 int ref_Viscous(UserCtx *u, Vec visc) { return Viscous(u, u->lUcont, u->lUcat, visc); }
 Vec ref_vec_new(UserCtx *u, int dof, int local) { Vec v; DA d = dof == 3 ? u->fda : u->da;

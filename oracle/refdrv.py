@@ -51,6 +51,14 @@ def lib():
         L.ref_Formfunction_2.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.ref_FormFunction_SNES.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_Pressure_Gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.ref_actuator_new.restype = C.c_void_p
+        L.ref_actuator_new.argtypes = [C.c_int]
+        L.ref_actuator_d.restype = C.POINTER(C.c_double)
+        L.ref_actuator_d.argtypes = [C.c_void_p, C.c_int]
+        L.ref_actuator_i.restype = C.POINTER(C.c_int)
+        L.ref_actuator_i.argtypes = [C.c_void_p, C.c_int]
+        L.ref_Calc_F_eul.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_Calc_U_lagr.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Convection.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Viscous.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_vec_new.restype = C.c_void_p
@@ -79,7 +87,7 @@ FLAG_DEFAULTS = dict(
     i_homo_filter=0, j_homo_filter=0, k_homo_filter=0, testfilter_ik=0, max_cs=0.5, wallfunction=0,
     viscosity_wallmodel=0, freesurface_wallmodel=0, movefsi=0, rotatefsi=0, rotor_model=0, nacelle_model=0, IB_delta=0,
     ti=10, tistart=0, rstart_flg=0, wave_momentum_source=0, air_flow_levelset=0, surface_tension=0, lowRe=0,
-    roughness_size=0.0, dthick=1.5, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
+    roughness_size=0.0, dthick=1.5, forcewidthfixed=0, halfwidth_dfunc=4.0, ii_periodicWT=0, jj_periodicWT=0, kk_periodicWT=0, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
 )
 
 
@@ -175,6 +183,27 @@ class RefCase:
 
     def Pressure_Gradient(self, name, mean_k_flux=0.0, mean_k_area=1.0):
         lib().ref_Pressure_Gradient(self.u, self.vec(name), mean_k_flux, mean_k_area)
+
+    # actuator elements (IBMNodes subset): `act` = dict of numpy arrays cent (n,3), F_lagr (n,3), dA (n,), win (n,6) int32
+    def _actuator(self, act):
+        L = lib()
+        n = len(act["dA"])
+        b = L.ref_actuator_new(n)
+        cols = [act["cent"][:, 0], act["cent"][:, 1], act["cent"][:, 2], act["dA"], act["F_lagr"][:, 0], act["F_lagr"][:, 1], act["F_lagr"][:, 2]]
+        for q, a in enumerate(cols):
+            np.ctypeslib.as_array(L.ref_actuator_d(b, q), shape=(n,))[...] = a
+        for q in range(6):
+            np.ctypeslib.as_array(L.ref_actuator_i(b, q), shape=(n,))[...] = act["win"][:, q]
+        return b, n
+
+    def Calc_F_eul(self, act, df):
+        b, n = self._actuator(act)
+        return lib().ref_Calc_F_eul(self.u, b, df)
+
+    def Calc_U_lagr(self, act):
+        b, n = self._actuator(act)
+        lib().ref_Calc_U_lagr(self.u, b)
+        return np.stack([np.array(np.ctypeslib.as_array(lib().ref_actuator_d(b, 7 + q), shape=(n,))) for q in range(3)], -1)
 
     def Convection(self, name):
         return lib().ref_Convection(self.u, self.vec(name))

@@ -60,6 +60,19 @@ def conv_defined(cfg, fields):
     return ok[..., None].astype(float)
 
 
+def make_actuator(cfg, xyz, seed=5, n=40, half=3):
+    """Synthetic actuator elements near random interior nodes: centres offset from the node, index windows of
+    +-`half` cells clipped to the interior (as the reference's pre-processing leaves them), random forces and areas."""
+    rng = np.random.default_rng(seed)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    ii = rng.integers(2, mx - 3, n); jj = rng.integers(2, my - 3, n); kk = rng.integers(2, mz - 3, n)
+    h = np.linalg.norm(xyz[2, 2, 2] - xyz[1, 1, 1])
+    cent = xyz[kk, jj, ii] + 0.4 * h * rng.uniform(-1, 1, (n, 3))
+    win = np.stack([np.maximum(ii - half, 1), np.minimum(ii + half + 1, mx - 1), np.maximum(jj - half, 1), np.minimum(jj + half + 1, my - 1),
+                    np.maximum(kk - half, 1), np.minimum(kk + half + 1, mz - 1)], -1).astype(np.int32)
+    return dict(cent=cent, F_lagr=rng.uniform(-1, 1, (n, 3)), dA=rng.uniform(0.5, 1.5, n) * h * h, win=win)
+
+
 def ref_setup(cfg, refdrv, xyz=None):
     """Create the reference context, metrics and input state for cfg (node coordinates `xyz`, default: cfg's own
     grid).  Returns (ref, xyz, fields, metrics)."""
@@ -179,6 +192,17 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
         ctx.Pressure_Gradient((mkf - infl) / cfg["dt"] / mka if cfg["flags"].get("kk_periodic") else 0.0)
         err["Pressure_Gradient"] = relerr(ctx.download("DP"), ref.view("dPg"))
         err["Pressure_Gradient_P"] = relerr(ctx.download("P"), ref.owned("P"))
+    # actuator forcing (rotor_model.c:3668, 2937) — after everything else: it overwrites F_eul
+    act = make_actuator(cfg, xyz)
+    ucat_now = np.array(ref.owned("Ucat"))
+    ctx.upload("UCAT", ucat_now)
+    ref.global_to_local("Ucat", "lUcat")
+    err["Calc_U_lagr"] = relerr(ctx.Calc_U_lagr([act])[0], ref.Calc_U_lagr(act))
+    for df in (0, 7, 10):
+        ref.view("lF_eul")[...] = 0
+        ref.Calc_F_eul(act, df)
+        ctx.Calc_F_eul([act], df=df)
+        err["Calc_F_eul_df%d" % df] = relerr(ctx.download("F_EUL"), ref.view("F_eul"))
     if verbose:
         for k, v in err.items():
             print("%-32s %.3e" % (k, v))

@@ -83,6 +83,15 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     err["IB_BC_lUcont"] = pc.relerr(a[nb < 2], b[nb < 2])
     err["IB_BC_Nvert_mismatches"] = float(np.count_nonzero(np.array(glue.owned("Nvert")) != np.array(ref.owned("Nvert")))
                                           + np.count_nonzero(np.array(glue.owned("lNvert")) != np.array(ref.owned("lNvert"))))
+    act = pc.make_actuator(cfg, xyz)                 # Calc_U_lagr / Calc_F_eul (rotor_model.c:2937, 3668) with the IBMNodes arrays
+    err["Calc_U_lagr"] = pc.relerr(glue.Calc_U_lagr(act), ref.Calc_U_lagr(act))
+    for d in (ref, glue):
+        d.view("lF_eul")[...] = 0
+        d.Calc_F_eul(act, 10)
+    err["Calc_F_eul"] = pc.relerr(glue.view("F_eul"), ref.view("F_eul"))
+    err["Calc_F_eul_lF_eul"] = pc.relerr(glue.view("lF_eul"), ref.view("lF_eul"))
+    for d in (ref, glue):
+        d.set_owned("F_eul", fields["f_eul"]); d.global_to_local("F_eul", "lF_eul")
     for d, drv in ((ref, refdrv), (glue, gd)):      # Pressure_Gradient (momentum.c:203), k-periodic mean-flux forcing included
         drv.set_global("inlet_flux", 0.1)
         d.set_owned("P", fields["p"])

@@ -23,7 +23,7 @@ EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_pressure_gradient", "vfs_download_async", "vfs_download_wait",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms",
-           "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count"]
+           "vfs_calc_f_eul", "vfs_calc_u_lagr", "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count"]
 
 
 class VfsParams(C.Structure):
@@ -48,6 +48,11 @@ class VfsSolverInfo(C.Structure):
     _fields_ = [("newton_iterations", C.c_int), ("krylov_iterations", C.c_int), ("residual_evals", C.c_int), ("reason", C.c_int),
                 ("fnorm0", C.c_double), ("fnorm", C.c_double), ("xnorm", C.c_double), ("delta", C.c_double),
                 ("n_history", C.c_int), ("fnorm_history", C.c_double * 17), ("ksp_its_history", C.c_int * 16)]
+
+
+class VfsActuator(C.Structure):
+    _fields_ = [("n_elmt", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("cent_x", "cent_y", "cent_z", "dA", "F_lagr_x", "F_lagr_y", "F_lagr_z", "U_lagr_x", "U_lagr_y", "U_lagr_z")] + \
+               [(n, C.POINTER(C.c_int)) for n in ("i_min", "i_max", "j_min", "j_max", "k_min", "k_max")]
 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int))
@@ -91,6 +96,8 @@ def _bind(lib):
     lib.vfs_last_ms.restype = C.c_double
     if hasattr(lib, "vfs_set_option"):
         lib.vfs_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.vfs_calc_f_eul.argtypes = [C.c_void_p, C.c_int, C.POINTER(VfsActuator), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
+    lib.vfs_calc_u_lagr.argtypes = [C.c_void_p, C.c_int, C.POINTER(VfsActuator)]
     lib.vfs_halo_layers.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vfs_solver_defaults.argtypes = [C.POINTER(VfsSolverParams)]
     lib.vfs_momentum_solve.argtypes = [C.c_void_p, C.POINTER(VfsSolverParams), C.POINTER(VfsSolverInfo)]
@@ -280,6 +287,36 @@ class VfsContext:
     def Pressure_Gradient(self, k_forcing=0.0):
         """momentum.c:203 on the current field "P"; result in field "DP"."""
         self._ck(self.lib.vfs_pressure_gradient(self.h, float(k_forcing)))
+
+    @staticmethod
+    def _actuators(acts):
+        """acts: list of dicts with cent (n,3), F_lagr (n,3), dA (n,), win (n,6) int32 -> (array of VfsActuator, keep-alive)."""
+        arr = (VfsActuator * len(acts))()
+        keep = []
+        for q, a in enumerate(acts):
+            n = len(a["dA"])
+            cols = [np.ascontiguousarray(a["cent"][:, c], dtype=np.float64) for c in range(3)] + [np.ascontiguousarray(a["dA"], dtype=np.float64)] + \
+                   [np.ascontiguousarray(a["F_lagr"][:, c], dtype=np.float64) for c in range(3)] + [np.zeros(n) for _ in range(3)]
+            wins = [np.ascontiguousarray(a["win"][:, c], dtype=np.int32) for c in range(6)]
+            keep.append((cols, wins))
+            arr[q].n_elmt = n
+            for name, v in zip(("cent_x", "cent_y", "cent_z", "dA", "F_lagr_x", "F_lagr_y", "F_lagr_z", "U_lagr_x", "U_lagr_y", "U_lagr_z"), cols):
+                setattr(arr[q], name, v.ctypes.data_as(C.POINTER(C.c_double)))
+            for name, v in zip(("i_min", "i_max", "j_min", "j_max", "k_min", "k_max"), wins):
+                setattr(arr[q], name, v.ctypes.data_as(C.POINTER(C.c_int)))
+        return arr, keep
+
+    def Calc_F_eul(self, acts, df=10, halfwidth_dfunc=4.0, dh_fixed=None, accumulate=False):
+        """rotor_model.c:3668: spread the actuators' forces into field "F_EUL"."""
+        arr, keep = self._actuators(acts)
+        dh = (C.c_double * 3)(*(dh_fixed or (0, 0, 0)))
+        self._ck(self.lib.vfs_calc_f_eul(self.h, len(acts), arr, int(df), float(halfwidth_dfunc), int(dh_fixed is not None), dh, int(accumulate)))
+
+    def Calc_U_lagr(self, acts):
+        """rotor_model.c:2937: velocity of field "UCAT" interpolated to the actuator elements; list of (n,3) arrays."""
+        arr, keep = self._actuators(acts)
+        self._ck(self.lib.vfs_calc_u_lagr(self.h, len(acts), arr))
+        return [np.stack(k[0][7:10], -1) for k in keep]
 
     def Compute_Smagorinsky_Constant_1(self):
         self._ck(self.lib.vfs_les_cs(self.h))

@@ -13,10 +13,13 @@
 #include "vfs_wm_kernels.h"
 #include "vfs_fused_kernels.h"
 #include "vfs_march_kernels.h"
+#include "vfs_actuator_kernels.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #ifndef VFS_EMU
 #include <cuda_runtime.h>
@@ -118,6 +121,7 @@ struct vfs_ctx {
 #ifndef VFS_EMU
   cudaGraphExec_t gexec[3] = {0, 0, 0};      // 0: residual, 1: RHS+LES unit, 2: the solver's residual (vfs_solver.h)
 #endif
+  void *act_buf = nullptr; size_t act_bytes = 0;      // device copy of the actuator element arrays (vfs_calc_f_eul / vfs_calc_u_lagr)
   VfsSolver *solver = nullptr;   // Krylov vectors of vfs_momentum_solve, allocated on first use
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
   bool sabs_valid = false;       // S_SABS holds |S| of the current ucat (set by les_cs pass 1)
@@ -565,12 +569,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag);
+  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag);
+  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf);
 #endif
   delete c; return 0;
 }
@@ -1202,6 +1206,91 @@ extern "C" int vfs_pressure_gradient(vfs_ctx *c, double k_forcing) {
   RUN(zero_scalars(c, S_DP0, 3));                                     // VecSet(dP, 0.), :313
   { PressureGradient f = {d, k_forcing}; RUN(launch(c, box_interior(c), f)); }
   return vfs_sync(c);
+}
+
+// ---- actuator forcing: Calc_F_eul / Calc_U_lagr (rotor_model.c:3668, 2937) -------------------------------------
+// all objects' element arrays concatenated (reference order: object, element) into one device buffer
+static int act_upload(vfs_ctx *c, int nobj, const vfs_actuator *o, ActElems *E, double **ulagr_dev) {
+  long n = 0;
+  for (int b = 0; b < nobj; b++) n += o[b].n_elmt;
+  const size_t bytes = (size_t)n * (7 * sizeof(double) + 6 * sizeof(int) + 3 * sizeof(double)) + 64;
+  std::vector<char> h(bytes);
+  double *hd = (double *)h.data(); int *hi = (int *)(hd + 10 * n);
+  long q = 0;
+  for (int b = 0; b < nobj; b++) for (int l = 0; l < o[b].n_elmt; l++, q++) {
+    hd[q] = o[b].cent_x[l]; hd[n + q] = o[b].cent_y[l]; hd[2 * n + q] = o[b].cent_z[l]; hd[3 * n + q] = o[b].dA ? o[b].dA[l] : 0.;
+    hd[4 * n + q] = o[b].F_lagr_x ? o[b].F_lagr_x[l] : 0.; hd[5 * n + q] = o[b].F_lagr_y ? o[b].F_lagr_y[l] : 0.; hd[6 * n + q] = o[b].F_lagr_z ? o[b].F_lagr_z[l] : 0.;
+    hi[q] = o[b].i_min[l]; hi[n + q] = o[b].i_max[l]; hi[2 * n + q] = o[b].j_min[l]; hi[3 * n + q] = o[b].j_max[l]; hi[4 * n + q] = o[b].k_min[l]; hi[5 * n + q] = o[b].k_max[l];
+  }
+#ifndef VFS_EMU
+  if (c->act_bytes < bytes) { if (c->act_buf) cudaFree(c->act_buf); c->act_buf = nullptr; CK(cudaMalloc(&c->act_buf, bytes)); c->act_bytes = bytes; }
+  CK(cudaMemcpyAsync(c->act_buf, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+#else
+  if (c->act_bytes < bytes) { free(c->act_buf); c->act_buf = malloc(bytes); c->act_bytes = bytes; }
+  memcpy(c->act_buf, h.data(), bytes);
+#endif
+  const double *dd = (const double *)c->act_buf; const int *di = (const int *)(dd + 10 * n);
+  E->n = (int)n; E->cx = dd; E->cy = dd + n; E->cz = dd + 2 * n; E->dA = dd + 3 * n; E->fx = dd + 4 * n; E->fy = dd + 5 * n; E->fz = dd + 6 * n;
+  E->i0 = di; E->i1 = di + n; E->j0 = di + 2 * n; E->j1 = di + 3 * n; E->k0 = di + 4 * n; E->k1 = di + 5 * n;
+  if (ulagr_dev) *ulagr_dev = (double *)c->act_buf + 7 * n;
+  return 0;
+}
+extern "C" int vfs_calc_f_eul(vfs_ctx *c, int nobj, const vfs_actuator *objs, int df, double halfwidth, int widthfixed, const double *dhf, int accumulate) {
+  if (!c || nobj < 0 || (nobj > 0 && !objs) || (widthfixed && !dhf)) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  if (!accumulate) RUN(zero_scalars(c, S_FE0, 3));
+  ActElems E;
+  RUN(act_upload(c, nobj, objs, &E, nullptr));
+  if (E.n > 0) {
+    // bounding box of all windows, clipped to the owned interior cells (windows reach ghost nodes on other ranks' behalf)
+    Box b = {1 << 30, -(1 << 30), 1 << 30, -(1 << 30), 1 << 30, -(1 << 30)};
+    for (int o = 0; o < nobj; o++) for (int l = 0; l < objs[o].n_elmt; l++) {
+      b.i0 = std::min(b.i0, objs[o].i_min[l]); b.i1 = std::max(b.i1, objs[o].i_max[l]); b.j0 = std::min(b.j0, objs[o].j_min[l]); b.j1 = std::max(b.j1, objs[o].j_max[l]);
+      b.k0 = std::min(b.k0, objs[o].k_min[l] - d.kofs); b.k1 = std::max(b.k1, objs[o].k_max[l] - d.kofs);
+    }
+    const Box own = {0, d.mx, 0, d.my, 0, d.nzl};
+    FEulGather f = {d, E, df, widthfixed, halfwidth, {widthfixed ? dhf[0] : 0., widthfixed ? dhf[1] : 0., widthfixed ? dhf[2] : 0.}};
+    RUN(launch(c, box_clip(b, own), f));
+  }
+  { FEulMask f = {d}; RUN(launch(c, box_owned(c), f)); }                    // rotor_model.c:3832-3903
+  RUN(g2l(c, grp(S_FE0, 3), 2, 2));                                          // :3955-3957
+  return vfs_sync(c);
+}
+extern "C" int vfs_calc_u_lagr(vfs_ctx *c, int nobj, const vfs_actuator *objs) {
+  if (!c || nobj < 0 || (nobj > 0 && !objs)) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  ActElems E; double *out = nullptr;
+  RUN(act_upload(c, nobj, objs, &E, &out));
+  if (E.n == 0) return 0;
+  std::vector<double> h(3 * (size_t)E.n);
+#ifndef VFS_EMU
+  ULagrArgs A = {d, E, out};
+  k_ulagr<<<E.n, 256, 0, c->stream>>>(A);
+  c->launches++;
+  if (c->prm.nranks > 1) {
+    NcclApi &N = nccl_api();
+    if (!c->comm || !N.AllReduce) { set_err(c, "vfs_calc_u_lagr with nranks > 1 needs vfs_nccl_init (the elements' sums are added with ncclAllReduce)"); return VFS_ERR_HALO; }
+    ncclResult_t e = N.AllReduce(out, out, 3 * (size_t)E.n, ncclDouble, ncclSum, c->comm, c->stream);
+    if (e != ncclSuccess) { set_err(c, std::string("ncclAllReduce: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
+  }
+  CK(cudaMemcpyAsync(h.data(), out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+#else
+  if (c->prm.nranks > 1) { set_err(c, "the host emulation of vfs_calc_u_lagr is single rank"); return VFS_ERR_UNSUPPORTED; }
+  for (int l = 0; l < E.n; l++) {
+    double acc[3] = {0, 0, 0};
+    const int i0 = std::max(E.i0[l], 0), i1 = std::min(E.i1[l], d.mx), j0 = std::max(E.j0[l], 0), j1 = std::min(E.j1[l], d.my);
+    const int k0 = std::max(E.k0[l] - d.kofs, 0), k1 = std::min(E.k1[l] - d.kofs, d.nzl);
+    for (int k = k0; k < k1; k++) for (int j = j0; j < j1; j++) for (int i = i0; i < i1; i++) ulagr_cell(d, E, l, i, j, k, acc);
+    for (int a = 0; a < 3; a++) h[3 * l + a] = acc[a];
+  }
+#endif
+  long q = 0;
+  for (int b = 0; b < nobj; b++) for (int l = 0; l < objs[b].n_elmt; l++, q++) {
+    if (objs[b].U_lagr_x) objs[b].U_lagr_x[l] = h[3 * q]; if (objs[b].U_lagr_y) objs[b].U_lagr_y[l] = h[3 * q + 1]; if (objs[b].U_lagr_z) objs[b].U_lagr_z[l] = h[3 * q + 2];
+  }
+  return 0;
 }
 
 // ---- legacy Convection / Viscous (rhs.c:751, 1071) --------------------------------------------------------

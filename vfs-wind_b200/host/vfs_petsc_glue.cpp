@@ -14,6 +14,7 @@
 //   Compute_eddy_viscosity_LES       Source/les.c:1143        -> vfs_les_nut
 //   Convection / Viscous (legacy)    Source/rhs.c:751,1071    -> vfs_convection / vfs_viscous
 //   Pressure_Gradient                Source/momentum.c:203    -> vfs_pressure_gradient
+//   Calc_F_eul / Calc_U_lagr         Source/rotor_model.c:3668,2937 -> vfs_calc_f_eul / vfs_calc_u_lagr
 //   SNESSolve in Implicit_MatrixFree Source/implicitsolver.c:4299 -> vfs_glue_snes_solve -> vfs_momentum_solve
 //
 // Data contract: the UserCtx Vecs stay the source of truth on the host (the rest of VFS-Wind —
@@ -40,6 +41,8 @@ extern PetscReal max_cs;
 extern double mean_pressure_gradient, inlet_flux;
 extern PetscInt inletprofile;
 extern PetscTruth dpdz_set;
+extern PetscInt forcewidthfixed, ii_periodicWT, jj_periodicWT, kk_periodicWT;
+extern PetscReal dhi_fixed, dhj_fixed, dhk_fixed, halfwidth_dfunc;
 extern double roughness_size;
 extern PetscTruth rstart_flg;
 
@@ -311,6 +314,39 @@ void Pressure_Gradient(UserCtx *user, Vec dP) {
     pull(user, s, VFS_P, 1, user->lP, true);
     DALocalToGlobal(user->da, user->lP, INSERT_VALUES, user->P);
   } else { DAGlobalToLocalBegin(user->da, user->P, INSERT_VALUES, user->lP); DAGlobalToLocalEnd(user->da, user->P, INSERT_VALUES, user->lP); }
+}
+
+// rotor_model.c:3668-3960 / 2937-3150: the IBMNodes arrays go down as they are, F_eul accumulates onto the host's lF_eul
+static std::vector<vfs_actuator> actuators(IBMNodes *ibm, int n) {
+  std::vector<vfs_actuator> a(n);
+  for (int b = 0; b < n; b++) {
+    a[b].n_elmt = ibm[b].n_elmt;
+    a[b].cent_x = ibm[b].cent_x; a[b].cent_y = ibm[b].cent_y; a[b].cent_z = ibm[b].cent_z; a[b].dA = ibm[b].dA;
+    a[b].F_lagr_x = ibm[b].F_lagr_x; a[b].F_lagr_y = ibm[b].F_lagr_y; a[b].F_lagr_z = ibm[b].F_lagr_z;
+    a[b].U_lagr_x = ibm[b].U_lagr_x; a[b].U_lagr_y = ibm[b].U_lagr_y; a[b].U_lagr_z = ibm[b].U_lagr_z;
+    a[b].i_min = ibm[b].i_min; a[b].i_max = ibm[b].i_max; a[b].j_min = ibm[b].j_min; a[b].j_max = ibm[b].j_max; a[b].k_min = ibm[b].k_min; a[b].k_max = ibm[b].k_max;
+  }
+  return a;
+}
+PetscErrorCode Calc_F_eul(UserCtx *user, IBMNodes *ibm, FSInfo *fsi, PetscInt NumberOfObjects, double dh, int df) {
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, user->lF_eul, 3, VFS_F_EUL);
+  std::vector<vfs_actuator> a = actuators(ibm, NumberOfObjects);
+  const double dhf[3] = {dhi_fixed, dhj_fixed, dhk_fixed};
+  ck(s, vfs_calc_f_eul(s->ctx, NumberOfObjects, a.data(), df, halfwidth_dfunc, forcewidthfixed, dhf, 1), "vfs_calc_f_eul");
+  pull(user, s, VFS_F_EUL, 3, user->lF_eul, true);
+  DALocalToGlobal(user->fda, user->lF_eul, INSERT_VALUES, user->F_eul);
+  return 0;
+}
+PetscErrorCode Calc_U_lagr(UserCtx *user, IBMNodes *ibm, FSInfo *fsi, int NumberOfObjects) {
+  if (ii_periodicWT || jj_periodicWT || kk_periodicWT) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: Calc_U_lagr with periodic turbine arrays (ii/jj/kk_periodicWT) is not built\n"); exit(1); }
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, user->lUcat, 3, VFS_UCAT);
+  std::vector<vfs_actuator> a = actuators(ibm, NumberOfObjects);
+  ck(s, vfs_calc_u_lagr(s->ctx, NumberOfObjects, a.data()), "vfs_calc_u_lagr");
+  return 0;
 }
 
 PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
