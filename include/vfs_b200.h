@@ -74,7 +74,7 @@ typedef struct vfs_params {
   int ti, tistart, rstart_flg;
   int levelset, rans, inviscid, skew, movefsi, rotatefsi; /* must be 0 (out of scope)        */
   int i_periodic, j_periodic, k_periodic;     /* legacy single-rank periodicity: must be 0   */
-  int i_homo_filter, j_homo_filter, k_homo_filter; /* must be 0 (off in all configs)         */
+  int i_homo_filter, j_homo_filter, k_homo_filter; /* Cs from LM, MM averaged over homogeneous directions, les.c:798-965 */
   double ren, dt, max_cs;
   double roughness_size; /* -roughness (main.c:319,1734): k_s of the rough-wall log law, bctype -2            */
   /* switches that reroute this path in the reference and are not built: must be 0 (momentum.c:754,1015,1301 select

@@ -23,6 +23,8 @@ def main():
         else:                                           # in-library NCCL halo layer (default)
             ctx.nccl_init(dist, device=torch.device("cuda", lrank))
     ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo)
+    if os.environ.get("VFS_HALO") != "torch":       # homogeneous Cs averaging: ncclAllReduce of the plane sums, 1e-12
+        ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo, pkg.selfcheck.homogeneous_cases(world)) and ok
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -99,3 +99,15 @@ def test_emulated_fp_in_projection_bitwise(pkg, emu):
         for n in outs[0]:
             assert np.array_equal(outs[0][n], outs[1][n]), (cfgname, n)
             assert np.array_equal(outs[0][n], outs[2][n]), (cfgname, n, 'box')
+
+
+@pytest.mark.parametrize("extra", [dict(i_homo_filter=1, k_homo_filter=1), dict(i_homo_filter=1), dict(j_homo_filter=1), dict(k_homo_filter=1)])
+def test_emulated_homogeneous_cs_averaging(pkg, refdrv, emu, extra):
+    """les.c:798-965: Cs from LM, MM averaged over the homogeneous direction(s) (channel-flow setting: i and k)."""
+    for name, dims in (("c2_box256", (13, 11, 15)), ("c3_turbine", (17, 13, 15))):
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+        cfg["flags"] = dict(cfg["flags"], **extra)
+        err = pc.run_parity(cfg, refdrv, lib=emu, legacy=False)
+        assert err.pop("FormFunction_SNES_zero_pattern") == 0, extra
+        bad = {k: v for k, v in err.items() if not (v <= TOL)}
+        assert not bad, (extra, bad)

@@ -92,6 +92,18 @@ def test_wall_function_boundaries(pkg, refdrv, bctype, extra):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("extra", [dict(i_homo_filter=1, k_homo_filter=1), dict(i_homo_filter=1), dict(j_homo_filter=1), dict(k_homo_filter=1)])
+def test_homogeneous_cs_averaging(pkg, refdrv, extra):
+    """les.c:798-965: Cs from LM, MM averaged over the homogeneous direction(s); device reductions in a fixed order."""
+    for name, dims in (("c2_box256", (40, 33, 37)), ("c3_turbine", (45, 30, 41))):
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+        cfg["flags"] = dict(cfg["flags"], **extra)
+        err = pc.run_parity(cfg, refdrv, device=0, legacy=False)
+        assert err.pop("FormFunction_SNES_zero_pattern") == 0, extra
+        bad = {k: v for k, v in err.items() if not (v <= TOL)}
+        assert not bad, (extra, bad)
+
+
 def test_unsupported_flags_fail_loudly(pkg):
     capi = pkg.capi
     p = capi.make_params(16, 16, 16, dict(les=2, levelset=1), 100.0, 1e-3, [1] * 6)

@@ -73,6 +73,7 @@ struct VfsDev {
   int bc[6];
   int les, second_order, laplacian, immersed, clark, testfilter_ik, visc_wm, wallfunction, has_feul;
   int ti, tistart, rstart_flg, bdf2, single_rank;
+  int homo;               // homogeneous-direction averaging of LM/MM (les.c:798-965): 0 off, 1 = i and k, 2 = i, 3 = j, 4 = k
   double ren, dt, max_cs, roughness;
   double *s[S_COUNT];
   // near[p] != 0: some node within +-2 of p (any direction) has nvert != 0 (NearSolid, vfs_c2c_kernels.h).

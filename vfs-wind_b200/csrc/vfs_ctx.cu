@@ -121,6 +121,7 @@ struct vfs_ctx {
 #ifndef VFS_EMU
   cudaGraphExec_t gexec[3] = {0, 0, 0};      // 0: residual, 1: RHS+LES unit, 2: the solver's residual (vfs_solver.h)
 #endif
+  double *homo_buf = nullptr; size_t homo_doubles = 0;      // line / plane sums of the homogeneous-direction Cs averaging
   void *act_buf = nullptr; size_t act_bytes = 0;      // device copy of the actuator element arrays (vfs_calc_f_eul / vfs_calc_u_lagr)
   VfsSolver *solver = nullptr;   // Krylov vectors of vfs_momentum_solve, allocated on first use
   bool iaj_valid = false;        // S_IAJ = 1/aj is current
@@ -457,7 +458,6 @@ static int check_params(const vfs_params *p, std::string &why) {
   if (p->nranks > 1 && p->nzl < VFS_G) { why = "k-slab thinner than the ghost width"; return VFS_ERR_ARG; }
   if (p->levelset || p->rans || p->inviscid || p->skew || p->movefsi || p->rotatefsi) { why = "levelset/rans/inviscid/skew/movefsi/rotatefsi are outside the hot-path scope"; return VFS_ERR_UNSUPPORTED; }
   if (p->i_periodic || p->j_periodic || p->k_periodic) { why = "legacy i/j/k_periodic not supported (use ii/jj/kk_periodic)"; return VFS_ERR_UNSUPPORTED; }
-  if (p->i_homo_filter || p->j_homo_filter || p->k_homo_filter) { why = "homogeneous-plane Cs averaging not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
   if (p->levelset_weno || p->freesurface_wallmodel || p->air_flow_levelset) { why = "levelset_weno / freesurface_wallmodel / air_flow_levelset reroute the flux and wall-model code in the reference (momentum.c:754,1015,1301) and are not built"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
@@ -481,6 +481,7 @@ static void fill_dev(vfs_ctx *c) {
   d.has_feul = (p.rotor_model || p.nacelle_model || p.IB_delta) ? 1 : 0;
   d.ti = p.ti; d.tistart = p.tistart; d.rstart_flg = p.rstart_flg; d.bdf2 = 0; d.single_rank = p.nranks == 1;
   d.ren = p.ren; d.dt = p.dt; d.max_cs = p.max_cs; d.roughness = p.roughness_size;
+  d.homo = (p.i_homo_filter && p.k_homo_filter) ? 1 : (p.i_homo_filter ? 2 : (p.j_homo_filter ? 3 : (p.k_homo_filter ? 4 : 0)));      // les.c:799,840
 }
 
 extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
@@ -569,12 +570,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf);
+  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf);
+  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf); free(c->homo_buf);
 #endif
   delete c; return 0;
 }
@@ -1411,6 +1412,42 @@ static bool les2_march_ok(const vfs_ctx *c) {
   (void)c; return true;
 #endif
 }
+// les.c:798-965: Cs from LM, MM averaged over the homogeneous direction(s); see HomoApply (vfs_les_kernels.h)
+static int les_homo(vfs_ctx *c) {
+  const VfsDev &d = c->d;
+  const int mode = d.homo - 1;
+  const Box bi = box_interior(c);
+  const int nline = mode == 0 ? d.my : (mode == 1 ? d.nzl * d.my : (mode == 2 ? d.nzl * d.mx : d.my * d.mx));
+  const size_t need = 3 * (size_t)nline;
+  if (c->homo_doubles < need) {
+#ifndef VFS_EMU
+    if (c->capturing) { set_err(c, "the buffer of the homogeneous Cs averaging must exist before graph capture: run the step eagerly once"); return VFS_ERR_CUDA; }
+    if (c->homo_buf) cudaFree(c->homo_buf);
+    c->homo_buf = nullptr;
+    CK(cudaMalloc((void **)&c->homo_buf, need * sizeof(double)));
+#else
+    free(c->homo_buf); c->homo_buf = (double *)malloc(need * sizeof(double));
+#endif
+    c->homo_doubles = need;
+  }
+#ifndef VFS_EMU
+  if (mode <= 1) k_homo_block<<<nline, 256, 0, c->stream>>>(d, mode, bi.k0, bi.k1, c->homo_buf);
+  else k_homo_thread<<<(nline + 255) / 256, 256, 0, c->stream>>>(d, mode, nline, bi.k0, bi.k1, c->homo_buf);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (c->prm.nranks > 1 && (mode == 0 || mode == 3)) {        // the sums run across the k-slabs (les.c:822-824, 911-913)
+    NcclApi &N = nccl_api();
+    if (!c->comm || !N.AllReduce) { set_err(c, "homogeneous Cs averaging across ranks needs vfs_nccl_init (ncclAllReduce)"); return VFS_ERR_HALO; }
+    ncclResult_t e = N.AllReduce(c->homo_buf, c->homo_buf, need, ncclDouble, ncclSum, c->comm, c->stream);
+    if (e != ncclSuccess) { set_err(c, std::string("ncclAllReduce: ") + N.GetErrorString(e)); return VFS_ERR_HALO; }
+  }
+#else
+  if (c->prm.nranks > 1 && (mode == 0 || mode == 3)) { set_err(c, "the host emulation has no all-reduce: homogeneous averaging across ranks is CUDA / NCCL only"); return VFS_ERR_UNSUPPORTED; }
+  for (int l = 0; l < nline; l++) homo_line_serial(d, mode, l, bi.k0, bi.k1, c->homo_buf + 3 * l);
+#endif
+  HomoApply f = {d, mode, c->homo_buf};
+  return launch(c, bi, f);
+}
 // defer_refresh: leave the ghost refresh of Cs (les.c:1026-1057) to les_nut(c, true), which does it together
 // with nu_t's (nu_t of an interior cell reads the cell's own Cs only, les.c:1206)
 static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
@@ -1465,7 +1502,8 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   RUN(g2l(c, g2, 2, 2));                                              // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
   ev_rec(c, 2 * VFS_T_LES3);
-  if (c->fused && !d.testfilter_ik) {
+  if (d.homo) { /* no test filter of LM, MM with homogeneous averaging (les.c:776-779): Cs comes from les_homo below */ }
+  else if (c->fused && !d.testfilter_ik) {
     Box bi = box_interior(c);
     SideScope sc; RUN(side_begin(c, &sc));       // the thin slabs next to periodic planes run beside the marching kernel
     LesPass3 f = {d};      // cells next to a periodic plane (ghost-image fetches): thin slabs
@@ -1482,6 +1520,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   } else
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES3 + 1);
+  if (d.homo) RUN(les_homo(c));                                         // les.c:798-965
   { LesClipBoundary f = {d}; RUN(launch_shell(c, 0, d.nzl, f)); }     // les.c:967-980 (boundary nodes; interior clip is in pass 3)
   if (defer_refresh) return 0;
   Grp g3 = grp(S_CS, 1);

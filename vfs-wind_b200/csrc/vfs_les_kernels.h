@@ -475,6 +475,86 @@ struct LesPass3 {
   }
 };
 
+
+// ---- homogeneous-direction averaging of LM, MM (les.c:798-965) -----------------------------------------------
+// i_homo_filter && k_homo_filter: Cs of EVERY interior cell of a j plane = 0.5 <LM> / (<MM> + les_eps), the averages
+// taken over the plane's fluid cells (nvert < 0.1) of all ranks (MPI_Allreduce at :822-824).  One of i / j / k
+// alone: the same along lines of that direction, written to the fluid cells only (:840-965).  The sums are the
+// only reduction on the path: lines / planes are reduced on the device in a fixed order (results do not depend
+// on the launch), the ranks' partial sums are added with ncclAllReduce — so unlike everything else the N-rank
+// result equals the 1-rank result only to rounding (sum re-association; tolerance 1e-12 on Cs in the tests).
+// mode: 0 = i and k, 1 = i, 2 = j, 3 = k.  `line` indexes the output: mode 0: j; 1: k_local*my + j; 2: k_local*mx + i; 3: j*mx + i.
+struct HomoGeom { int mode, nline; };
+VFS_HD void homo_cell(const VfsDev &d, long p, double acc[3]) {
+  if (d.s[S_NV][p] < 0.1) { acc[0] += d.s[S_LM][p]; acc[1] += d.s[S_MM][p]; acc[2] += 1.0; }
+}
+// interior cells of this rank: i in [1, mx-1), j in [1, my-1), local k in [k1, k2)
+VFS_HD void homo_line_serial(const VfsDev &d, int mode, int line, int k1, int k2, double acc[3]) {
+  acc[0] = acc[1] = acc[2] = 0;
+  if (mode == 0) { const int j = line; if (j < 1 || j > d.my - 2) return;
+    for (int k = k1; k < k2; k++) for (int i = 1; i < d.mx - 1; i++) homo_cell(d, d.idx(i, j, k), acc); }
+  else if (mode == 1) { const int k = line / d.my, j = line % d.my; if (k < k1 || k >= k2 || j < 1 || j > d.my - 2) return;
+    for (int i = 1; i < d.mx - 1; i++) homo_cell(d, d.idx(i, j, k), acc); }
+  else if (mode == 2) { const int k = line / d.mx, i = line % d.mx; if (k < k1 || k >= k2 || i < 1 || i > d.mx - 2) return;
+    for (int j = 1; j < d.my - 1; j++) homo_cell(d, d.idx(i, j, k), acc); }
+  else { const int j = line / d.mx, i = line % d.mx; if (i < 1 || i > d.mx - 2 || j < 1 || j > d.my - 2) return;
+    for (int k = k1; k < k2; k++) homo_cell(d, d.idx(i, j, k), acc); }
+}
+// Cs from the averaged sums (buf[3*line + 0..2] = sum LM, sum MM, count over all ranks), then the clip chain of :967-980
+struct HomoApply {
+  VfsDev d; int mode; const double *buf;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    const double nvc = d.s[S_NV][p];
+    const int line = mode == 0 ? j : (mode == 1 ? k * d.my + j : (mode == 2 ? k * d.mx + i : j * d.mx + i));
+    double cs;
+    if (mode == 0 || nvc < 0.1) {
+      double lm = buf[3 * line], mm = buf[3 * line + 1]; const double cnt = buf[3 * line + 2];
+      if (cnt > 0) { lm /= cnt; mm /= cnt; }
+      cs = 0.5 * lm / (mm + 1.e-4);
+    } else {                        // cells the averages are not written to keep the UNFILTERED pointwise value (les.c:776-795)
+      const double C = 0.5 * d.s[S_LM][p] / (d.s[S_MM][p] + 1.e-4);
+      cs = (C < 0) ? 0 : C;
+    }
+    if (nvc > 1.1) cs = 0;
+    else {
+      if (nvc > 0.1 && nvc < 1.1) cs = (0.001 < cs) ? cs : 0.001;
+      cs = (cs < 0) ? 0 : cs;
+      cs = (cs < d.max_cs) ? cs : d.max_cs;
+    }
+    d.s[S_CS][p] = cs;
+  }
+};
+#if defined(__CUDACC__) && !defined(VFS_EMU)
+// modes 0 and 1: one block per line, the line's cells strided over the block, fixed-order tree reduction
+__global__ void __launch_bounds__(256) k_homo_block(VfsDev d, int mode, int k1, int k2, double *buf) {
+  const int line = blockIdx.x;
+  double acc[3] = {0, 0, 0};
+  const int ni = d.mx - 2;
+  if (mode == 0) {
+    const int j = line;
+    if (j >= 1 && j <= d.my - 2) { const long n = (long)ni * (k2 - k1);
+      for (long t = threadIdx.x; t < n; t += 256) homo_cell(d, d.idx(1 + (int)(t % ni), j, k1 + (int)(t / ni)), acc); }
+  } else {
+    const int k = line / d.my, j = line % d.my;
+    if (k >= k1 && k < k2 && j >= 1 && j <= d.my - 2) for (int t = threadIdx.x; t < ni; t += 256) homo_cell(d, d.idx(1 + t, j, k), acc);
+  }
+  __shared__ double sm[3][256];
+  for (int c = 0; c < 3; c++) sm[c][threadIdx.x] = acc[c];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) for (int c = 0; c < 3; c++) sm[c][threadIdx.x] += sm[c][threadIdx.x + s]; __syncthreads(); }
+  if (threadIdx.x < 3) buf[3 * line + threadIdx.x] = sm[threadIdx.x][0];
+}
+// modes 2 and 3: one thread per line (consecutive lines = consecutive i: coalesced), serial along the line
+__global__ void __launch_bounds__(256) k_homo_thread(VfsDev d, int mode, int nline, int k1, int k2, double *buf) {
+  const int line = blockIdx.x * 256 + threadIdx.x;
+  if (line >= nline) return;
+  double acc[3];
+  homo_line_serial(d, mode, line, k1, k2, acc);
+  buf[3 * line] = acc[0]; buf[3 * line + 1] = acc[1]; buf[3 * line + 2] = acc[2];
+}
+#endif
+
 // les.c:967-980: Cs = 0 on the domain-boundary nodes (the interior part of the clip chain is in les3_core)
 struct LesClipBoundary {
   VfsDev d;

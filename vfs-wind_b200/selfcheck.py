@@ -31,13 +31,23 @@ def default_cases(world):
     return (("c2_box256", (61, 45, 16 * world + 7)), ("c3_turbine", (53, 37, 12 * world + 9)))
 
 
+def homogeneous_cases(world):
+    """Channel-flow setting (LM, MM averaged over i and k, les.c:798-838) and k alone: the plane / line sums are the one
+    all-reduce of the path, so N ranks equal 1 rank to rounding only — (config, dims, extra flags, tolerance)."""
+    return (("c2_box256", (45, 29, 12 * world + 5), dict(i_homo_filter=1, k_homo_filter=1), 1e-12),
+            ("c3_turbine", (37, 25, 12 * world + 3), dict(k_homo_filter=1), 1e-12))
+
+
 def nrank_equals_1rank(capi, cases, rank, world, device, make_halo, case_list=None, verbose=True):
     """Every rank computes the single-rank result on its own device, then its slab of the N-rank
     run; returns True when all compared fields of this rank are bitwise equal.  `make_halo(ctx, cfg)`
     attaches the halo layer (vfs_nccl_init or a callback) to the slab context."""
     ok = True
-    for cfgname, dims in (case_list or default_cases(world)):
+    for case in (case_list or default_cases(world)):
+        cfgname, dims = case[0], case[1]
+        extra, tol = (case[2], case[3]) if len(case) > 2 else ({}, 0.0)
         cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
+        cfg["flags"] = dict(cfg["flags"], **extra)
         mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
         xyz = cases.make_grid(cfg)
         ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], device=device))
@@ -59,7 +69,8 @@ def nrank_equals_1rank(capi, cases, rank, world, device, make_halo, case_list=No
             ctx.upload(n, f[k][sl])
         out = run_path(ctx, x[sl])
         for n in sorted(out):
-            same = np.array_equal(out[n], single[n][sl])
+            a, b = out[n], single[n][sl]
+            same = np.array_equal(a, b) if tol == 0 else bool(np.abs(a - b).max() <= tol * max(np.abs(single[n]).max(), 1e-300))
             ok = ok and same
             if not same and verbose:
                 print("rank %d %s %s MISMATCH max %.3e" % (rank, cfgname, n, np.abs(out[n] - single[n][sl]).max()), flush=True)
