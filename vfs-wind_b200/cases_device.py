@@ -144,7 +144,7 @@ def fill_context(ctx, cfg, kofs, nzl, rank, device):
     scale = float(ucont.abs().max())
     up("UCONT", ucont)
     up("UCONT_O", ucont + 1e-3 * scale * _smooth121(noise(shp + (3,))))
-    up("UCONT_RM1", ucont + 2e-3 * scale * _smooth121(noise(shp + (3,))))
+    # (Ucont_rm1 is read by the BDF2 assembly only, which this path never takes: not uploaded, its scalars stay unallocated)
     del ucont
     up("DP", 0.05 * scale * _smooth121(noise(shp + (3,))))
     up("RHS_O", 0.05 * scale * _smooth121(noise(shp + (3,))))

@@ -37,7 +37,6 @@ enum {
   S_U0, S_U1, S_U2,                                   // ucat
   S_UO0, S_UO1, S_UO2,                                // ucat_old
   S_UCO0, S_UCO1, S_UCO2,                             // ucont_o
-  S_UCM0, S_UCM1, S_UCM2,                             // ucont_rm1
   S_RO0, S_RO1, S_RO2,                                // rhs_o
   S_DP0, S_DP1, S_DP2,                                // dP
   S_FE0, S_FE1, S_FE2,                                // F_eul
@@ -47,7 +46,6 @@ enum {
   S_FC1, S_FC1b, S_FC1c, S_FC2, S_FC2b, S_FC2c, S_FC3, S_FC3b, S_FC3c,   // convective face fluxes (Div1-3)
   S_FV1, S_FV1b, S_FV1c, S_FV2, S_FV2b, S_FV2c, S_FV3, S_FV3b, S_FV3c,   // viscous+SGS face fluxes (Visc1-3)
   S_FP0, S_FP1, S_FP2,                                                   // Fp
-  S_CONV0, S_CONV1, S_CONV2, S_VISC0, S_VISC1, S_VISC2,                  // legacy Convection / Viscous results (rhs.c:751,1071)
   S_SABS,                                                                // LES: |S|
   S_UF0, S_UF1, S_UF2,                                                   // LES: test-filtered ucat
   S_LM, S_MM,
@@ -59,6 +57,10 @@ enum {
   S_LFINV, S_LTF2, S_LF2,
   S_WM,                                                                  // wall-model nu_t of the j = 0 faces (plane j = 0 only)
   S_P,                                                                   // pressure (input of Pressure_Gradient, momentum.c:203)
+  // rarely used scalars: allocated on first use, outside the main pool (9 of 93 scalars = 11 GB on a 2048 x 1024 x 64 slab)
+  S_TAIL0,
+  S_UCM0 = S_TAIL0, S_UCM1, S_UCM2,                                      // ucont_rm1 (BDF2 assembly only)
+  S_CONV0, S_CONV1, S_CONV2, S_VISC0, S_VISC1, S_VISC2,                  // legacy Convection / Viscous results (rhs.c:751,1071)
   S_COUNT
 };
 

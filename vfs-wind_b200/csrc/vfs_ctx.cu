@@ -77,7 +77,8 @@ struct VfsSolver;
 struct vfs_ctx {
   vfs_params prm;
   VfsDev d;
-  double *pool = nullptr;        // all scalars, contiguous
+  double *pool = nullptr;        // scalars 0 .. S_TAIL0-1, contiguous
+  double *tail = nullptr;        // scalars S_TAIL0 .. S_COUNT-1, allocated on first use (ensure_tail)
   double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
   double *stage_x = nullptr;     // staging of vfs_formfunction_snes' X, filled on the upload stream (allocated on first use)
   double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use (sized for the field)
@@ -139,6 +140,7 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
+  int box_shape = 0;             // thread-block shape of the one-thread-per-node kernels (option key 15, tuning only)
   int halo_trim = 1;             // exchange only the ghost layers each refresh is read at (option key 14); 0: always G layers
   int cur_lo = VFS_G, cur_hi = VFS_G;   // layers of the exchange in progress (vfs_halo_layers)
   int *d_flag = nullptr;         // device scratch flag (has_solid scan)
@@ -154,7 +156,9 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
   if (b.i1 <= b.i0 || b.j1 <= b.j0 || b.k1 <= b.k0) return 0;
   c->launches++;
 #ifndef VFS_EMU
-  dim3 blk(64, 2, 2);
+  dim3 blk(128, 2, 1);      // measured best of nine 256-thread shapes for the bandwidth kernels (profiles/r02l_tune_box_shape.txt)
+  if (c->box_shape) { static const int S[9][3] = {{64, 2, 2}, {32, 4, 2}, {32, 2, 4}, {32, 8, 1}, {64, 4, 1}, {128, 2, 1}, {64, 1, 4}, {128, 1, 2}, {256, 1, 1}};
+    const int q = c->box_shape % 9; blk = dim3(S[q][0], S[q][1], S[q][2]); }
   if (b.i1 - b.i0 == 1) blk = dim3(1, 32, 8);       // a single i plane: no idle lanes (rows are strided either way)
   else if (b.i1 - b.i0 <= 8) blk = dim3(8, 8, 4);
   else if (b.j1 - b.j0 == 1) blk = dim3(64, 1, 4);
@@ -491,7 +495,7 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   vfs_ctx *c = new vfs_ctx();
   c->prm = *p; fill_dev(c);
   c->scalar_len = (long)c->d.nzt * c->d.sk;
-  size_t bytes = (size_t)c->scalar_len * S_COUNT * sizeof(double);
+  size_t bytes = (size_t)c->scalar_len * S_TAIL0 * sizeof(double);
   size_t sbytes = (size_t)p->nzl * p->my * p->mx * 3 * sizeof(double);
 #ifndef VFS_EMU
   cudaError_t e = cudaSetDevice(p->device);
@@ -510,7 +514,7 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
   c->near = (unsigned char *)malloc((size_t)c->scalar_len); memset(c->near, 1, (size_t)c->scalar_len);
 #endif
-  for (int s = 0; s < S_COUNT; s++) c->d.s[s] = c->pool + (long)s * c->scalar_len;
+  for (int s = 0; s < S_COUNT; s++) c->d.s[s] = s < S_TAIL0 ? c->pool + (long)s * c->scalar_len : nullptr;
   c->d.near = c->near;
 #ifndef VFS_EMU
   c->tma_ok = vfs_make_tensor_map(&c->tmap, c->pool, c->d, c->scalar_len, VFS_TILE_TX + 2, VFS_TILE_TY + 2) == 0 &&
@@ -570,12 +574,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
+  cudaFree(c->pool); if (c->tail) cudaFree(c->tail); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf); free(c->homo_buf);
+  free(c->pool); free(c->tail); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf); free(c->homo_buf);
 #endif
   delete c; return 0;
 }
@@ -641,13 +645,13 @@ extern "C" int vfs_sync(vfs_ctx *c) {
 static int api_end(vfs_ctx *c) { return c->async_api ? 0 : vfs_sync(c); }
 extern "C" int vfs_layout(vfs_ctx *c, long *L) {
   if (!c || !L) return VFS_ERR_ARG;
-  L[0] = VFS_G; L[1] = c->d.pitch; L[2] = c->d.ny; L[3] = c->d.nzt; L[4] = c->d.sk; L[5] = c->scalar_len; L[6] = S_COUNT; L[7] = 1; return 0;
+  L[0] = VFS_G; L[1] = c->d.pitch; L[2] = c->d.ny; L[3] = c->d.nzt; L[4] = c->d.sk; L[5] = c->scalar_len; L[6] = S_TAIL0; L[7] = 1; return 0;      // (pool scalars: the ones a halo layer can be asked for)
 }
 extern "C" int vfs_field_scalar_id(vfs_ctx *c, int field, int comp) {
   if (!c || field < 0 || field >= VFS_NFIELDS_PUBLIC || comp < 0 || comp >= FIELD[field].dof) return VFS_ERR_ARG;
   return FIELD[field].s0 + comp;
 }
-extern "C" void *vfs_scalar_ptr(vfs_ctx *c, int sid) { if (!c || sid < 0 || sid >= S_COUNT) return 0; return c->d.s[sid]; }
+extern "C" void *vfs_scalar_ptr(vfs_ctx *c, int sid) { if (!c || sid < 0 || sid >= S_COUNT) return 0; return c->d.s[sid]; }      // (null for a tail scalar nobody has used yet)
 extern "C" long vfs_launch_count(vfs_ctx *c) { return c ? c->launches : 0; }
 extern "C" double vfs_last_ms(vfs_ctx *c, int which) {
 #ifndef VFS_EMU
@@ -676,6 +680,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 11) c->async_api = value;
   else if (key == 12) c->fp_fused = value;
   else if (key == 14) c->halo_trim = value;
+  else if (key == 15) c->box_shape = value;
   graph_reset(c);
   return 0;
 }
@@ -706,6 +711,21 @@ template <class F> static int run_graphed(vfs_ctx *c, int key, F body) {
   return body();
 }
 
+// the rarely used scalars (Ucont_rm1, legacy Conv / Visc) live outside the main pool and exist only once somebody uses them
+static int ensure_tail(vfs_ctx *c) {
+  if (c->tail) return 0;
+  const size_t bytes = (size_t)c->scalar_len * (S_COUNT - S_TAIL0) * sizeof(double);
+#ifndef VFS_EMU
+  if (c->capturing) { set_err(c, "first use of a tail scalar during graph capture"); return VFS_ERR_CUDA; }
+  CK(cudaMalloc((void **)&c->tail, bytes));
+  CK(cudaMemsetAsync(c->tail, 0, bytes, c->stream));
+#else
+  c->tail = (double *)calloc(bytes, 1);
+#endif
+  for (int s = S_TAIL0; s < S_COUNT; s++) c->d.s[s] = c->tail + (long)(s - S_TAIL0) * c->scalar_len;
+  graph_reset(c);
+  return 0;
+}
 // ---- transfers ------------------------------------------------------------------------------------
 struct HasSolid { VfsDev d; int *flag; VFS_HD void operator()(int i, int j, int k) const { if ((int)(d.s[S_NV][d.idx(i, j, k)] + 0.1) == 3) *flag = 1; } };
 static int h2d_stage(vfs_ctx *c, const double *host, int dof) {
@@ -729,6 +749,7 @@ static int d2h_stage(vfs_ctx *c, double *host, int dof) {
 }
 extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
   if (!c || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  if (FIELD[field].s0 >= S_TAIL0) return 0;            // Ucont_rm1, Conv, Visc: ghosts never read
   return g2l(c, grp(FIELD[field].s0, FIELD[field].dof));
 }
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
@@ -737,10 +758,12 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->lesgeo_valid = c->les_bnd_valid = false;
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   if (field == VFS_NVERT) { c->near_valid = false; c->wall_marked = false; }
+  const bool tail = FIELD[field].s0 >= S_TAIL0;
+  if (tail) RUN(ensure_tail(c));
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
-  RUN(vfs_halo_exchange(c, field));
+  if (!tail) RUN(vfs_halo_exchange(c, field));          // (the tail fields' ghosts are never read)
   if (field == VFS_NVERT) {
     // solid-cell flag: lets Contra2Cart skip its whole-volume "solid -> 0" sweep.  Scanned on the device over the
     // slab AND the ghost planes Contra2Cart is replayed on (a neighbour's solid cells must be zeroed there too).
@@ -767,6 +790,7 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
 }
 extern "C" int vfs_download(vfs_ctx *c, int field, double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
+  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c));
   PackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
   return d2h_stage(c, host, FIELD[field].dof);
@@ -776,6 +800,7 @@ extern "C" int vfs_download_async(vfs_ctx *c, int field, double *host, int slot)
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC || slot < 0 || slot > 1) return VFS_ERR_ARG;
 #ifndef VFS_EMU
   const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * FIELD[field].dof * sizeof(double);
+  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c));
   if (!c->copy_stream) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
@@ -1017,7 +1042,20 @@ static int ensure_wm_table(vfs_ctx *c) {
     c->wm_table = (double *)malloc(bytes);
 #endif
     { WmTableIntervals f = {c->wm_table}; Box b = {0, VFS_WM_NYP + 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
+#ifndef VFS_EMU
+    {   // the running sum in index order (the reference's serial loop, wallfunction.c:291-300): 4 MB, once — on the host, where
+        // a serial scan costs a millisecond, instead of one GPU thread walking 500 001 entries
+      std::vector<double> h(VFS_WM_NYP + 1);
+      CK(cudaMemcpyAsync(h.data(), c->wm_table, bytes, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      double acc = 0.;
+      for (int i = 1; i <= VFS_WM_NYP; i++) { acc = acc + h[i]; h[i] = acc; }
+      CK(cudaMemcpyAsync(c->wm_table, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+#else
     { WmTableScan f = {c->wm_table}; Box b = {0, 1, 0, 1, 0, 1}; RUN(launch(c, b, f)); }
+#endif
   }
   return 0;
 }
@@ -1300,6 +1338,7 @@ extern "C" int vfs_calc_u_lagr(vfs_ctx *c, int nobj, const vfs_actuator *objs) {
 // nu_t / metric ghost planes, so no exchange is needed (the reference's DALocalToLocal of Fp1-3,
 // rhs.c:1471-1478, only refreshes ghosts nobody reads).
 template <bool VISC> static int legacy_term(vfs_ctx *c) {
+  RUN(ensure_tail(c));
   const VfsDev &d = c->d;
   RUN(ensure_iaj(c));
   const Box bi = box_interior(c);

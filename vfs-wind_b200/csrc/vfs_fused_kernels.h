@@ -57,7 +57,7 @@ static inline int vfs_make_tensor_map(CUtensorMap *map, void *pool, const VfsDev
   void *fn = 0;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
-  cuuint64_t gdim[4] = {(cuuint64_t)d.pitch, (cuuint64_t)d.ny, (cuuint64_t)d.nzt, (cuuint64_t)S_COUNT};
+  cuuint64_t gdim[4] = {(cuuint64_t)d.pitch, (cuuint64_t)d.ny, (cuuint64_t)d.nzt, (cuuint64_t)S_TAIL0};      // the main pool (TMA never touches the tail scalars)
   cuuint64_t gstr[3] = {(cuuint64_t)d.pitch * 8, (cuuint64_t)d.sk * 8, (cuuint64_t)scalar_len * 8};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
