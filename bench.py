@@ -442,7 +442,7 @@ def bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, shape, args)
         ctx.Contra2Cart(); ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
         # a fixed amount of work: `solver_newton` Newton steps of exactly `solver_krylov` GMRES iterations each
         info = ctx.momentum_solve(max_newton=args.solver_newton, max_krylov=args.solver_krylov, restart=args.solver_krylov, rtol=1e-30, atol=0.0,
-                                  use_ew=0, ksp_rtol=1e-30)
+                                  use_ew=0, ksp_rtol=1e-30, trust_region=0)      # (no trust-region step-length stop: the synthetic state is far from converged)
         ctx.download_ptr("UCONT", out.data_ptr())
         return info
     info = step()

@@ -140,6 +140,7 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
+  int les_replay = 1;            // between ranks: LES pass 1 replayed on the ghost planes instead of exchanging its 13 fields (option key 16)
   int box_shape = 0;             // thread-block shape of the one-thread-per-node kernels (option key 15, tuning only)
   int halo_trim = 1;             // exchange only the ghost layers each refresh is read at (option key 14); 0: always G layers
   int cur_lo = VFS_G, cur_hi = VFS_G;   // layers of the exchange in progress (vfs_halo_layers)
@@ -681,6 +682,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 12) c->fp_fused = value;
   else if (key == 14) c->halo_trim = value;
   else if (key == 15) c->box_shape = value;
+  else if (key == 16) c->les_replay = value;
   graph_reset(c);
   return 0;
 }
@@ -1498,27 +1500,50 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   RUN(ensure_iaj(c));
   RUN(ensure_near(c));
   ev_rec(c, 2 * VFS_T_LES1);
-  if (c->fused && !d.testfilter_ik) {
-    Box bi = box_interior(c);
-    int r;
+  // Between ranks the 13 pass-1 fields are NOT exchanged: pass 1 is replayed on the ghost planes pass 2 reads — plane -1
+  // / nzl across an interior slab boundary, and across the periodic seam plane -2 / nzl+1 (the images of global
+  // planes mz-2 / 1, the sources of the seam's node copies) — from the ucat ghosts Contra2Cart replays, the metric and
+  // nvert ghosts: same inputs, same code as the owner, bitwise the owner's values (as for Contra2Cart, section 7).
+  const bool multi = c->prm.nranks > 1;
+  const bool replay = multi && c->les_replay;
+  std::vector<std::pair<int, int> > k_ranges;             // pass-1 plane ranges
+  { const Box bi = box_interior(c);
+    int k0 = bi.k0, k1 = bi.k1;
+    if (replay && d.kofs > 0) k0 = -1;
+    if (replay && d.kofs + d.nzl < d.mz) k1 = d.nzl + 1;
+    k_ranges.push_back(std::make_pair(k0, k1));
+    if (replay && d.perz && d.kofs == 0) k_ranges.push_back(std::make_pair(-2, -1));
+    if (replay && d.perz && d.kofs + d.nzl == d.mz) k_ranges.push_back(std::make_pair(d.nzl + 1, d.nzl + 2)); }
+  const int ka = replay && (d.kofs > 0 || d.perz) ? -2 : 0, kb = replay && (d.kofs + d.nzl < d.mz || d.perz) ? d.nzl + 2 : d.nzl;
+  for (size_t q = 0; q < k_ranges.size(); q++) {
+    const int q0 = k_ranges[q].first, q1 = k_ranges[q].second;
+    if (c->fused && !d.testfilter_ik) {
+      int r;
 #ifndef VFS_EMU
-    if (c->les1_var == 1 && c->tma_ok) r = launch_les1_tma(c->stream, c->tmap, d, bi.k0, bi.k1, &c->launches);
-    else if (c->les1_var == 2) { Les1March8 prog = {d}; r = run_filter_march<Les1March8, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
-    else if (c->les1_var == 3) { Les1March prog = {d}; r = run_filter_march<Les1March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
-    else
+      if (c->les1_var == 1 && c->tma_ok) r = launch_les1_tma(c->stream, c->tmap, d, q0, q1, &c->launches);
+      else if (c->les1_var == 2) { Les1March8 prog = {d}; r = run_filter_march<Les1March8, 2>(c->stream, prog, q0, q1, &c->launches); }
+      else if (c->les1_var == 3) { Les1March prog = {d}; r = run_filter_march<Les1March, 2>(c->stream, prog, q0, q1, &c->launches); }
+      else
 #endif
-    { Les1March prog = {d}; r = run_filter_march<Les1March, 1>(c->stream, prog, bi.k0, bi.k1, &c->launches); }
-    if (r) { set_err(c, "les1 march kernel launch failed"); return VFS_ERR_CUDA; }
-  } else
-  { LesPass1 f = {d}; RUN(launch(c, box_interior(c), f)); }
+      { Les1March prog = {d}; r = run_filter_march<Les1March, 1>(c->stream, prog, q0, q1, &c->launches); }
+      if (r) { set_err(c, "les1 march kernel launch failed"); return VFS_ERR_CUDA; }
+    } else { LesPass1 f = {d}; Box b = box_interior(c); b.k0 = q0; b.k1 = q1; RUN(launch(c, b, f)); }
+  }
   ev_rec(c, 2 * VFS_T_LES1 + 1);
   c->sabs_valid = true;
-  RUN(run_les_derive_boundary(c));
   Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
-  RUN(g2l(c, g1, 2, 2));                                              // les.c:254-267 (pass 2 reads k+-1, the seam copies k+-2)
-  // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
-  // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
-  if (any_per(c)) RUN(node_copy(c, grp_cat(grp(S_UF0, 3), grp(S_LU0, 9))));   // les.c:275-306
+  const Grp g1c = grp_cat(grp(S_UF0, 3), grp(S_LU0, 9));
+  if (replay) {
+    { LesDeriveBoundary f = {d, (c->les_bnd_valid && c->halo_trim) ? 1 : 0}; c->les_bnd_valid = true; RUN(launch_shell(c, ka, kb, f, true)); }
+    RUN(wrap_ij(c, g1, ka, kb));                                        // les.c:254-267 without the k exchange
+    if (any_per(c)) { NodeCopy f = {d, g1c, 1}; RUN(launch_shell(c, ka, kb, f, true, SHELL_PERIODIC_ONLY)); }     // les.c:275-306
+  } else {
+    RUN(run_les_derive_boundary(c));
+    RUN(g2l(c, g1, 2, 2));                                              // les.c:254-267 (pass 2 reads k+-1, the seam copies k+-2)
+    // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
+    // periodic-copied by the reference; only the copied fields (ucat_f, grad u, |S|) are
+    if (any_per(c)) RUN(node_copy(c, g1c));                             // les.c:275-306
+  }
   ev_rec(c, 2 * VFS_T_LES2);
   if (c->fused && !d.testfilter_ik && les2_march_ok(c)) {
     Box bi = box_interior(c);

@@ -182,7 +182,7 @@ struct Les1Body {
   __device__ __forceinline__ void operator()(const VfsDev &d, const TileAcc<RingLes1> &T, int i, int j, int k, const Les1Pre &pf, Les1Win &st, bool first) const {
     const long p = d.idx(i, j, k);
     Les1Acc A = {T, d, p, pf};
-    les1_core(d, A, i, j, k + d.kofs, p, &st, first);
+    les1_core(d, A, i, j, d.kglob(k), p, &st, first);      // (kglob: a ghost plane across the periodic seam is evaluated as the plane it images)
   }
 };
 

@@ -229,7 +229,7 @@ struct LesPass1 {
   VFS_HD void operator()(int i, int j, int k) const {
     const long p = d.idx(i, j, k);
     GlobalAccS<S_U0> A = {d, p};
-    les1_core(d, A, i, j, k + d.kofs, p);
+    les1_core(d, A, i, j, d.kglob(k), p);
   }
 };
 

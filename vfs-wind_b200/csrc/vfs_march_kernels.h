@@ -388,7 +388,7 @@ template <int TY_> struct Les1MarchT {
     const double u0 = A.u(0, 0, 0, 0), u1 = A.u(1, 0, 0, 0), u2 = A.u(2, 0, 0, 0);
     double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, S = 0, uf[3] = {0, 0, 0};
     if (!(nv0 > 1.1)) {      // skipped cells keep the zeros of the reference's freshly created work vectors
-      grad_center_auto(d, A, i, j, k + d.kofs, p, g);
+      grad_center_auto(d, A, i, j, d.kglob(k), p, g);
       S = sabs_of(g);
       const double *sA = sm + OFF_A;
       const int up = tid - TX, dn = tid + TX;
