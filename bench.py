@@ -104,10 +104,12 @@ def peaks():
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms.  Started BEFORE the warm-up (nvidia-smi needs a few hundred
+    ms to come up), then only the samples whose timestamps fall inside the timed region [mark_begin, mark_end] are used."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, dev):
-        self.dev, self.p = dev, None
+        self.dev, self.p, self.t0, self.t1 = dev, None, None, None
 
     def start(self):
         try:
@@ -116,30 +118,51 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.p:
             return out
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.05)
         self.p.terminate()
         try:
             txt = self.p.communicate(timeout=5)[0]
         except Exception:
             self.p.kill()
             return out
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in txt.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if self.t0 is None or (self.t0 - 0.01 <= r[0] <= self.t1 + 0.01)]
+        note = None
+        if not inside and rows:          # a timed region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * ((self.t0 or self.t1) + self.t1)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            note = "timed region shorter than the 20 ms sampling period: nearest sample"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if inside:
+            out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)), "reasons": sorted(reasons), "samples": len(inside)}
+            if note:
+                out["note"] = note
         return out
 
 
@@ -264,18 +287,20 @@ def run_ours(args):
     # exchanges are captured with it
     use_graph = (world == 1 or halo == "nccl") and not args.no_graph
     ctx.set_option(1, 1 if use_graph else 0)
+    sampler = ClockSampler(lrank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         ctx.rhs_les_fused()
     barrier()
-    sampler = ClockSampler(lrank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(args.steps):
         ctx.rhs_les_fused()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = rmax(e0.elapsed_time(e1))
     clocks = sampler.stop()
 
@@ -463,9 +488,10 @@ def bench_solver(ctx, torch, stream, barrier, rmax, cells_total, f, shape, args)
 
 
 # ---- the reference's own CPU implementation (oracle/_ref), timed on the host cores -------------
-def _ref_case(workload, kofs, layers, seed):
+def _ref_case(workload, kofs, layers, seed, plane=None):
     """Reference context for the k-slab of `layers` interior cell layers starting at global node plane `kofs` of the
-    workload's grid (its own two boundary planes included; periodic k wraps the slab on itself: zero communication)."""
+    workload's grid (its own two boundary planes included; periodic k wraps the slab on itself: zero communication).
+    plane = (IM, JM): the same case with a reduced i-j extent (host memory: the reference keeps ~2 KB per node)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refdrv
@@ -473,6 +499,8 @@ def _ref_case(workload, kofs, layers, seed):
     pkg = load_package()
     cases = pkg.cases
     full = dict(cases.CONFIGS[workload])
+    if plane:
+        full["IM"], full["JM"] = plane
     cfg = dict(full)
     cfg["KM"] = layers + 1
     cfg["seed"] = seed
@@ -510,8 +538,8 @@ def _slab_worker(a):
 
 
 def _slab_worker_(a):
-    workload, kofs, layers, seed, warmup, steps, bar = a
-    step, cells = _ref_case(workload, kofs, layers, seed)
+    workload, kofs, layers, seed, warmup, steps, bar = a[:7]
+    step, cells = _ref_case(workload, kofs, layers, seed, a[7] if len(a) > 7 else None)
     for _ in range(warmup):
         step()
     if bar is not None:
@@ -533,7 +561,7 @@ def cpu_reference_sample(workload, planes, steps):
             "sample": "reference sources (oracle/_ref) on one %d-cell-layer k-slab of the %s grid (%d cells), %d timed steps, 1 core" % (planes, workload, cells, steps)}
 
 
-def run_partitioned(workload, layers_total, kofs0, cores, warmup, steps):
+def run_partitioned(workload, layers_total, kofs0, cores, warmup, steps, plane=None):
     """The grid's `layers_total` interior cell layers split into `cores` contiguous k-slabs, one reference process per
     slab, all stepping concurrently; returns (seconds per step = slowest process, cells per step)."""
     import multiprocessing as mp
@@ -545,7 +573,7 @@ def run_partitioned(workload, layers_total, kofs0, cores, warmup, steps):
     jobs, k = [], kofs0
     for q in range(cores):
         n = base + (1 if q < rem else 0)
-        jobs.append((workload, k, n, 202 + q, warmup, steps, bar))
+        jobs.append((workload, k, n, 202 + q, warmup, steps, bar, plane))
         k += n
     with ctxm.Pool(cores) as pool:
         res = pool.map(_slab_worker, jobs, chunksize=1)
@@ -595,16 +623,25 @@ def run_reference(args):
     est_rate = 5.0e5 * cores
     budget_s = 150.0 / max(1, args.steps + args.warmup)
     layers_all = mz - 2
+    # host memory: the reference keeps about 2 KB per node (its ~120 DA Vecs + work vectors), every slab process adds two
+    # boundary planes — planes larger than 3e5 nodes are sampled at a reduced i-j extent (same flags, same stencils)
+    plane, IMs, JMs = None, mx - 1, my - 1
+    if mx * my > 3.0e5:
+        fct = int(np.ceil(np.sqrt(mx * my / 3.0e5)))
+        IMs, JMs = (mx - 1) // fct, (my - 1) // fct
+        plane = (IMs, JMs)
+    cells_plane = (IMs - 1) * (JMs - 1)
     layers = layers_all
-    if cells_total / est_rate > budget_s:
-        layers = max(2 * cores if (mx - 2) * (my - 2) < 1e6 else cores, int(budget_s * est_rate / ((mx - 2) * (my - 2))))
-        layers = min(layers, layers_all)
-    sec, cells, used = run_partitioned(base, layers, 0, cores, args.warmup, args.steps)
+    if plane or cells_total / est_rate > budget_s:
+        layers = int(budget_s * est_rate / cells_plane)
+        layers = max(2 * cores, min(layers, layers_all, int(24.0e6 / ((IMs + 1) * (JMs + 1))) - 2 * cores))
+    sec, cells, used = run_partitioned(base, layers, 0, cores, args.warmup, args.steps, plane)
     value = cells / sec
-    full = layers == layers_all
-    sample = "reference sources (oracle/_ref): %s, %d of %d cell layers (%d cells per step) split into %d contiguous k-slabs, one process per core, " \
+    full = layers == layers_all and not plane
+    sample = "reference sources (oracle/_ref): %s, %d of %d cell layers%s (%d cells per step) split into %d contiguous k-slabs, one process per core, " \
              "%d warm-up + %d timed steps, measured wall per step = slowest process; zero communication cost" % (
-                 "the WHOLE grid" if full else "a bounded k-range of the grid", layers, layers_all, cells, used, args.warmup, args.steps)
+                 "the WHOLE grid" if full else "a bounded part of the grid", layers, layers_all,
+                 " at a reduced i-j extent of %dx%d nodes" % (IMs + 1, JMs + 1) if plane else "", cells, used, args.warmup, args.steps)
     cb = {"value": value, "unit": "cell-updates/s", "cores": used, "kind": "reference", "sample": sample, "whole_grid": full}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -25,6 +25,7 @@ def main():
     ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo)
     if os.environ.get("VFS_HALO") != "torch":       # homogeneous Cs averaging: ncclAllReduce of the plane sums, 1e-12
         ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo, pkg.selfcheck.homogeneous_cases(world)) and ok
+        ok = pkg.selfcheck.nrank_solver_and_actuators(pkg.capi, pkg.cases, rank, world, lrank, make_halo) and ok
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -76,3 +76,61 @@ def nrank_equals_1rank(capi, cases, rank, world, device, make_halo, case_list=No
                 print("rank %d %s %s MISMATCH max %.3e" % (rank, cfgname, n, np.abs(out[n] - single[n][sl]).max()), flush=True)
         ctx.close()
     return ok
+
+
+def nrank_solver_and_actuators(capi, cases, rank, world, device, make_halo, verbose=True):
+    """The pieces with a genuine all-reduce: vfs_momentum_solve (dot products and norms summed with ncclAllReduce),
+    vfs_calc_u_lagr (element sums), plus vfs_calc_f_eul and vfs_pressure_gradient on slabs.  N ranks against 1 rank:
+    same iteration counts, residual-norm history and iterate to 1e-10; F_eul and dP bitwise; U_lagr to 1e-12."""
+    ok = True
+    cfg = cases.scaled(cases.CONFIGS["c3_turbine"], 41, 29, 12 * world + 7)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    xyz = cases.make_grid(cfg)
+    rng = np.random.default_rng(11)
+    n = 24
+    ii, jj, kk = rng.integers(2, mx - 3, n), rng.integers(2, my - 3, n), rng.integers(2, mz - 3, n)
+    h = np.linalg.norm(xyz[2, 2, 2] - xyz[1, 1, 1])
+    act = dict(cent=xyz[kk, jj, ii] + 0.4 * h * rng.uniform(-1, 1, (n, 3)), F_lagr=rng.uniform(-1, 1, (n, 3)), dA=rng.uniform(0.5, 1.5, n) * h * h,
+               win=np.stack([np.maximum(ii - 3, 1), np.minimum(ii + 4, mx - 1), np.maximum(jj - 3, 1), np.minimum(jj + 4, my - 1),
+                             np.maximum(kk - 3, 1), np.minimum(kk + 4, mz - 1)], -1).astype(np.int32))
+    res = []
+    for nr in (1, world):
+        kofs, nzl = capi.slab_partition(mz, nr)[rank if nr > 1 else 0]
+        p = capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"], kofs=kofs, nzl=nzl, rank=rank if nr > 1 else 0, nranks=nr, device=device)
+        ctx = capi.VfsContext(p)
+        if nr > 1:
+            make_halo(ctx, cfg)
+        sl = slice(kofs, kofs + nzl)
+        ctx.upload("COOR", xyz[sl]); ctx.FormMetrics()
+        if nr == 1:
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+            for key in ("rhs_o", "dp", "f_eul"):       # a solvable step: no constant forcing on masked components (tests/solver_common.py)
+                f[key] = np.zeros_like(f[key])
+        for k, nm in FIELDS_IN:
+            ctx.upload(nm, f[k][sl])
+        ctx.upload("P", f["p"][sl])
+        out = {}
+        ctx.Pressure_Gradient(0.0); out["dP"] = ctx.download("DP")
+        ctx.upload("DP", f["dp"][sl])
+        ctx.Contra2Cart()
+        out["U_lagr"] = ctx.Calc_U_lagr([act])[0]
+        ctx.Calc_F_eul([act], df=10); out["F_eul"] = ctx.download("F_EUL")
+        ctx.upload("F_EUL", f["f_eul"][sl])
+        ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
+        ctx.upload("UCONT", f["ucont"][sl])
+        info = ctx.momentum_solve(max_newton=3, restart=4, use_ew=0, ksp_rtol=1e-6)
+        out["U"] = ctx.download("UCONT"); out["info"] = info
+        res.append((out, sl))
+        ctx.close()
+    (a, _), (b, sl) = res
+    checks = [("dP", np.array_equal(b["dP"], a["dP"][sl])), ("F_eul", np.array_equal(b["F_eul"], a["F_eul"][sl])),
+              ("U_lagr", bool(np.abs(b["U_lagr"] - a["U_lagr"]).max() <= 1e-12 * np.abs(a["U_lagr"]).max())),
+              ("solver iterations", a["info"]["ksp_its_history"] == b["info"]["ksp_its_history"] and a["info"]["reason"] == b["info"]["reason"]),
+              ("solver |F| history", bool(np.abs(np.array(a["info"]["fnorm_history"]) - np.array(b["info"]["fnorm_history"])).max() <= 1e-10 * a["info"]["fnorm0"])),
+              ("solver iterate", bool(np.abs(b["U"] - a["U"][sl]).max() <= 1e-10 * np.abs(a["U"]).max()))]
+    for name, good in checks:
+        ok = ok and good
+        if not good and verbose:
+            print("rank %d solver/actuator check: %s MISMATCH" % (rank, name), flush=True)
+    return ok
