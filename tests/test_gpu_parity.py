@@ -235,6 +235,7 @@ def test_fused_variants_bitwise_equal_staged_chain(pkg, key):
         for val in (0, 1, 2):
             ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
             ctx.set_option(key, val)
+            ctx.set_option(17, 0)          # the scalar FpCell: same arithmetic as the in-projection variants, instruction for instruction
             ctx.upload("COOR", cases.make_grid(cfg)); ctx.FormMetrics()
             met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
             f = cases.make_fields(cfg, met)

@@ -140,6 +140,7 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
+  int fp_pairs = 1;              // FpCell on pairs of cells with 16-byte loads (option key 17)
   int les_replay = 1;            // between ranks: LES pass 1 replayed on the ghost planes instead of exchanging its 13 fields (option key 16)
   int box_shape = 0;             // thread-block shape of the one-thread-per-node kernels (option key 15, tuning only)
   int halo_trim = 1;             // exchange only the ghost layers each refresh is read at (option key 14); 0: always G layers
@@ -563,6 +564,7 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
 #endif
   ks_free(c);
 #ifndef VFS_EMU
+  graph_reset(c);            // graph execs hold captured NCCL work: ncclCommDestroy blocks for ever while they exist
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->hbuf) cudaFree(c->hbuf);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -621,8 +623,8 @@ extern "C" int vfs_nccl_init(vfs_ctx *c, const char *id128) {
   if (!c || !id128) return VFS_ERR_ARG;
   NcclApi &N = nccl_api();
   if (!N.ok) { set_err(c, "libnccl.so.2 not found"); return VFS_ERR_HALO; }
-  if (c->comm) { N.CommDestroy(c->comm); c->comm = nullptr; }
   graph_reset(c);
+  if (c->comm) { N.CommDestroy(c->comm); c->comm = nullptr; }
   ncclUniqueId id; memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
   CK(cudaSetDevice(c->prm.device));
   ncclResult_t e = N.CommInitRank(&c->comm, c->prm.nranks, id, c->prm.rank);
@@ -683,6 +685,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 14) c->halo_trim = value;
   else if (key == 15) c->box_shape = value;
   else if (key == 16) c->les_replay = value;
+  else if (key == 17) c->fp_pairs = value;
   graph_reset(c);
   return 0;
 }
@@ -1172,11 +1175,17 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
     if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
     if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
     const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8;
-    FpCell fp = {d};
+    FpCell fp1 = {d};
+    FpCell2 fp2 = {d};
+    // two cells per thread (16-byte loads) when the box starts at the first interior cell; the functor skips i = 0 / mx-1
+    auto fp_launch = [&](const Box &b) -> int {
+      if (c->fp_pairs && b.i0 == 1 && b.i1 == d.mx - 1) { Box h = b; h.i0 = 0; h.i1 = (d.mx + 1) / 2; return launch(c, h, fp2); }
+      return launch(c, b, fp1);
+    };
     if (!ovl) {
       RUN(halo_k(c, gk, false, 3, 2));      // Fp reads faces k-2 .. k+1 (k-4 / k+3 across the periodic seam = ghost planes -3 / nzl+1)
       if (any_per(c)) { NodeCopyFlux f = {d, 3}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
-      for (int n = 0; n < S.n; n++) RUN(launch(c, S.fp[n], fp));     // momentum.c:1548-1678
+      for (int n = 0; n < S.n; n++) RUN(fp_launch(S.fp[n]));          // momentum.c:1548-1678
     } else {
       // Fp of a cell reads the k-face fluxes of planes k-2 .. k+1 (k-4 / k+3 across the periodic seam): the cells
       // of local planes 2 .. nzl-3 never touch a k ghost plane and run while the exchange is in flight
@@ -1185,10 +1194,10 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
       Box in = S.fp[0], lo = S.fp[0], hi = S.fp[0];
       in.k0 = in.k0 > 2 ? in.k0 : 2; in.k1 = in.k1 < d.nzl - 2 ? in.k1 : d.nzl - 2;
       lo.k1 = in.k0; hi.k0 = in.k1;
-      RUN(launch(c, in, fp));
+      RUN(fp_launch(in));
       RUN(ovl_join(c));
       if (d.perz) { NodeCopyFlux f = {d, 2}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
-      RUN(launch(c, lo, fp)); RUN(launch(c, hi, fp));
+      RUN(fp_launch(lo)); RUN(fp_launch(hi));
     }
   }
   ev_rec(c, 2 * VFS_T_FP + 1);

@@ -358,6 +358,76 @@ struct FpCell {
   }
 };
 
+
+// FpCell for TWO cells (i0, i0 + 1), i0 even: every operand row is read with 16-byte loads (the padded index of an
+// even i is even, rows are 128-byte aligned).  Fast path: both cells in the regular interior (3 <= c <= m-4 in every
+// direction, so none of the end-of-domain / periodic-seam cases of momentum.c:1565-1637 applies) and no nvert != 0
+// within +-2 (VfsDev::near) — the 4th-order differences then use the fixed offsets +1 / -2 and the arithmetic is
+// fp_cell_value's, operand for operand.  Everything else falls back to fp_cell_value per cell.
+#if defined(__CUDA_ARCH__)
+#define VFS_LD2(ptr) (*reinterpret_cast<const double2 *>(ptr))
+#endif
+struct FpCell2 {
+  VfsDev d;
+  VFS_HD void operator()(int ii, int j, int k) const {
+    const int i0 = 2 * ii, kg = k + d.kofs;
+    const long p = d.idx(i0, j, k);
+#if defined(__CUDA_ARCH__)
+    const bool regular = i0 >= 4 && i0 + 1 <= d.mx - 4 && j >= 3 && j <= d.my - 4 && kg >= 3 && kg <= d.mz - 4 && d.near[p] == 0 && d.near[p + 1] == 0;
+    if (regular) {
+      const long sj = d.sj, sk = d.sk;
+      double o0[3], o1[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const double *c1 = d.s[S_FC1 + a] + p, *c2 = d.s[S_FC2 + a] + p, *c3 = d.s[S_FC3 + a] + p;
+        const double *v1 = d.s[S_FV1 + a] + p, *v2 = d.s[S_FV2 + a] + p, *v3 = d.s[S_FV3 + a] + p;
+        const double2 am = VFS_LD2(c1 - 2), a0 = VFS_LD2(c1), ap = VFS_LD2(c1 + 2);          // FC1 at i0-2 .. i0+3
+        const double2 bm2 = VFS_LD2(c2 - 2 * sj), bm1 = VFS_LD2(c2 - sj), b0 = VFS_LD2(c2), bp1 = VFS_LD2(c2 + sj);
+        const double2 cm2 = VFS_LD2(c3 - 2 * sk), cm1 = VFS_LD2(c3 - sk), c0 = VFS_LD2(c3), cp1 = VFS_LD2(c3 + sk);
+        const double2 vm = VFS_LD2(v1 - 2), v0 = VFS_LD2(v1);
+        const double2 wm1 = VFS_LD2(v2 - sj), w0 = VFS_LD2(v2), xm1 = VFS_LD2(v3 - sk), x0 = VFS_LD2(v3);
+        // cell i0
+        {
+          const double div = (a0.x - am.y + b0.x - bm1.x + c0.x - cm1.x);
+          const double vis = (v0.x - vm.y + w0.x - wm1.x + x0.x - xm1.x);
+          double out;
+          if (!d.second_order) {
+            const double inv = 1. / 3.;
+            double div4 = 0;
+            div4 += (a0.y - am.x) * inv; div4 += (bp1.x - bm2.x) * inv; div4 += (cp1.x - cm2.x) * inv;
+            out = (9. / 8.) * div + (-1. / 8.) * div4 + vis;
+          } else out = div + vis;
+          o0[a] = out;
+        }
+        // cell i0 + 1
+        {
+          const double div = (a0.y - a0.x + b0.y - bm1.y + c0.y - cm1.y);
+          const double vis = (v0.y - v0.x + w0.y - wm1.y + x0.y - xm1.y);
+          double out;
+          if (!d.second_order) {
+            const double inv = 1. / 3.;
+            double div4 = 0;
+            div4 += (ap.x - am.y) * inv; div4 += (bp1.y - bm2.y) * inv; div4 += (cp1.y - cm2.y) * inv;
+            out = (9. / 8.) * div + (-1. / 8.) * div4 + vis;
+          } else out = div + vis;
+          o1[a] = out;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++) *reinterpret_cast<double2 *>(d.s[S_FP0 + a] + p) = make_double2(o0[a], o1[a]);
+      return;
+    }
+#endif
+    for (int q = 0; q < 2; q++) {
+      const int i = i0 + q;
+      if (i < 1 || i > d.mx - 2) continue;
+      double f[3];
+      fp_cell_value(d, i, j, kg, p + q, f);
+      for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p + q] = f[a];
+    }
+  }
+};
+
 // projection of Fp on the face area vectors (momentum.c:1733-1735) for one node; returns the
 // three contravariant components (before scale and masks)
 VFS_HD V3 project_fp(const VfsDev &d, long p) {

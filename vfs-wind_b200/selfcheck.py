@@ -78,6 +78,12 @@ def nrank_equals_1rank(capi, cases, rank, world, device, make_halo, case_list=No
     return ok
 
 
+def _stage(rank, msg):
+    import os, sys
+    if os.environ.get("VFS_SELFCHECK_TRACE"):
+        print("[selfcheck rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+
 def nrank_solver_and_actuators(capi, cases, rank, world, device, make_halo, verbose=True):
     """The pieces with a genuine all-reduce: vfs_momentum_solve (dot products and norms summed with ncclAllReduce),
     vfs_calc_u_lagr (element sums), plus vfs_calc_f_eul and vfs_pressure_gradient on slabs.  N ranks against 1 rank:
@@ -111,15 +117,21 @@ def nrank_solver_and_actuators(capi, cases, rank, world, device, make_halo, verb
             ctx.upload(nm, f[k][sl])
         ctx.upload("P", f["p"][sl])
         out = {}
+        _stage(rank, "nr=%d uploads done" % nr)
         ctx.Pressure_Gradient(0.0); out["dP"] = ctx.download("DP")
         ctx.upload("DP", f["dp"][sl])
+        _stage(rank, "Pressure_Gradient done")
         ctx.Contra2Cart()
         out["U_lagr"] = ctx.Calc_U_lagr([act])[0]
+        _stage(rank, "Calc_U_lagr done")
         ctx.Calc_F_eul([act], df=10); out["F_eul"] = ctx.download("F_EUL")
         ctx.upload("F_EUL", f["f_eul"][sl])
+        _stage(rank, "Calc_F_eul done")
         ctx.Compute_Smagorinsky_Constant_1(); ctx.Compute_eddy_viscosity_LES()
         ctx.upload("UCONT", f["ucont"][sl])
+        _stage(rank, "LES done, solving")
         info = ctx.momentum_solve(max_newton=3, restart=4, use_ew=0, ksp_rtol=1e-6)
+        _stage(rank, "solve done: %r" % (info,))
         out["U"] = ctx.download("UCONT"); out["info"] = info
         res.append((out, sl))
         ctx.close()
