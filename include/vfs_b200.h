@@ -228,6 +228,8 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *   9  overlap the k-face-flux and Fp halo exchanges with interior planes (default 1; nranks > 1 with vfs_nccl_init)
  *  11  asynchronous compute-only entry points (vfs_contra2cart, vfs_ib_bc, vfs_les_cs, vfs_les_nut return once their work
  *      is queued; default 0): a following vfs_formfunction_snes then copies X while those kernels still run
+ *  15  thread-block shape of the one-thread-per-node kernels (tuning)    16  LES pass 1 replayed on ghost planes between ranks (default 1)
+ *  17  FpCell on pairs of cells with 16-byte loads (default 0: measured slower than 8-byte loads, 0.82 vs 0.70 ms)
  *  14  exchange only the ghost layers each refresh is read at (default 1; 0 = always the full ghost width G)
  *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower) */
 int vfs_set_option(vfs_ctx *c, int key, int value);

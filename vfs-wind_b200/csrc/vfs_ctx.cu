@@ -140,7 +140,7 @@ struct vfs_ctx {
   bool wall_marked = false;      // IB_BC's first-step nvert = 1 marking of wall-function first cells has been applied (momentum.c:2048-2074)
   int fuse_refresh = 1;          // single rank: ghost refresh sequences as one launch (RefreshFused) (option key 8)
   int fastpath = 1;              // mask-free specialisations for warps far from any nvert != 0 (option key 6)
-  int fp_pairs = 1;              // FpCell on pairs of cells with 16-byte loads (option key 17)
+  int fp_pairs = 0;              // FpCell on pairs of cells with 16-byte loads (option key 17): measured SLOWER, 0.82 vs 0.70 ms (profiles/r02u_tune_fp_pairs.txt)
   int les_replay = 1;            // between ranks: LES pass 1 replayed on the ghost planes instead of exchanging its 13 fields (option key 16)
   int box_shape = 0;             // thread-block shape of the one-thread-per-node kernels (option key 15, tuning only)
   int halo_trim = 1;             // exchange only the ghost layers each refresh is read at (option key 14); 0: always G layers
