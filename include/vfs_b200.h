@@ -72,14 +72,18 @@ typedef struct vfs_params {
   int viscosity_wallmodel, wallfunction;
   int rotor_model, nacelle_model, IB_delta;   /* any non-zero => Rhs += F_eul (momentum.c:2329) */
   int ti, tistart, rstart_flg;
-  int levelset, rans, inviscid, skew, movefsi, rotatefsi; /* must be 0 (out of scope)        */
+  int levelset, rans, inviscid, skew, movefsi, rotatefsi; /* levelset, rans, movefsi, rotatefsi must be 0 (out of scope);
+                          * inviscid: WENO3 convection, no viscous term (momentum.c:754,1624,1663); skew: skew-symmetric
+                          * convection (:789-800,1638-1651); clark (above): mixed model in the viscous flux (:904-923)
+                          * and in the dynamic procedure (les.c:497-556,656).  These three run the one-thread-per-face
+                          * kernels instead of the marching ones.                                                    */
   int i_periodic, j_periodic, k_periodic;     /* legacy single-rank periodicity: must be 0   */
   int i_homo_filter, j_homo_filter, k_homo_filter; /* Cs from LM, MM averaged over homogeneous directions, les.c:798-965 */
   double ren, dt, max_cs;
   double roughness_size; /* -roughness (main.c:319,1734): k_s of the rough-wall log law, bctype -2            */
-  /* switches that reroute this path in the reference and are not built: must be 0 (momentum.c:754,1015,1301 select
-   * weno3 on levelset_weno even without levelset; freesurface_wallmodel / air_flow_levelset change the wall model and
-   * the boundary fluxes).  `central` only matters together with rans, which is rejected. */
+  /* levelset_weno: 0, or 5 = WENO3 convection everywhere (momentum.c:754,1015,1301 test it even without levelset);
+   * 1-4 key on the level-set field and are rejected, as are freesurface_wallmodel / air_flow_levelset (they change the
+   * wall model and the boundary fluxes).  `central` only matters together with rans, which is rejected. */
   int levelset_weno, freesurface_wallmodel, air_flow_levelset;
 } vfs_params;
 
@@ -151,6 +155,11 @@ int vfs_download_wait(vfs_ctx *c);
  * reference adds to dP/dzeta per unit dz in k-periodic runs (:399-411): mean_pressure_gradient when dpdz_set, else
  * (mean_k_flux - inlet_flux) / dt / mean_k_area unless inletprofile == 17; pass 0 otherwise. */
 int vfs_pressure_gradient(vfs_ctx *c, double k_forcing);
+/* The body-fitted-cylinder diagnostics Formfunction_2 accumulates when bctype[0] == 11 and bctype[1] == 1
+ * (Source/momentum.c:570-579, 822-849): out7 = this rank's lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl,
+ * lFvz_cyl over the wall faces i = mx-2, from the current VFS_UCAT (as the last residual evaluation left it) and VFS_P.
+ * All zero for other boundary types.  The reference adds them over ranks itself (main.c:1269-1277). */
+int vfs_cylinder_forces(vfs_ctx *c, double *out7);
 int vfs_convection(vfs_ctx *c);
 int vfs_viscous(vfs_ctx *c);
 /* F = residual(X); X, F host arrays [nzl][my][mx][3] (pinned or pageable) */

@@ -103,6 +103,10 @@ double *ref_actuator_d(IBMNodes *b, int which) {
 int *ref_actuator_i(IBMNodes *b, int which) { int *w[] = {b->i_min, b->i_max, b->j_min, b->j_max, b->k_min, b->k_max}; return w[which]; }
 int ref_Calc_F_eul(UserCtx *u, IBMNodes *b, int df) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_F_eul(u, b, f, 1, 1.0, df); free(f); return r; }
 int ref_Calc_U_lagr(UserCtx *u, IBMNodes *b) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_U_lagr(u, b, f, 1); free(f); return r; }
+// body-fitted-cylinder diagnostics Formfunction_2 leaves in the context (momentum.c:570-579, 822-849)
+void ref_cylinder_forces(UserCtx *u, double *out7) {
+  out7[0] = u->lA_cyl; out7[1] = u->lA_cyl_x; out7[2] = u->lA_cyl_z; out7[3] = u->lFpx_cyl; out7[4] = u->lFpz_cyl; out7[5] = u->lFvx_cyl; out7[6] = u->lFvz_cyl;
+}
 int ref_Convection(UserCtx *u, Vec conv) { return Convection(u, u->lUcont, u->lUcat, conv); }
 int ref_Viscous(UserCtx *u, Vec visc) { return Viscous(u, u->lUcont, u->lUcat, visc); }
 Vec ref_vec_new(UserCtx *u, int dof, int local) { Vec v; DA d = dof == 3 ? u->fda : u->da;

@@ -59,6 +59,8 @@ def lib():
         L.ref_actuator_i.argtypes = [C.c_void_p, C.c_int]
         L.ref_Calc_F_eul.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_Calc_U_lagr.argtypes = [C.c_void_p, C.c_void_p]
+        if hasattr(L, "ref_cylinder_forces"):
+            L.ref_cylinder_forces.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Convection.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Viscous.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_vec_new.restype = C.c_void_p
@@ -183,6 +185,12 @@ class RefCase:
 
     def Pressure_Gradient(self, name, mean_k_flux=0.0, mean_k_area=1.0):
         lib().ref_Pressure_Gradient(self.u, self.vec(name), mean_k_flux, mean_k_area)
+
+    def cylinder_forces(self):
+        """lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl, lFvz_cyl as the last Formfunction_2 left them."""
+        out = np.zeros(7)
+        lib().ref_cylinder_forces(self.u, out.ctypes.data_as(C.c_void_p))
+        return out
 
     # actuator elements (IBMNodes subset): `act` = dict of numpy arrays cent (n,3), F_lagr (n,3), dA (n,), win (n,6) int32
     def _actuator(self, act):

@@ -82,6 +82,8 @@ def ref_setup(cfg, refdrv, xyz=None):
     ref = refdrv.RefCase(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"])
     if xyz is None:
         xyz = cases.make_grid(cfg)
+        if cfg.get("z_shift"):      # e.g. the body-fitted cylinder rule of bctype 11 keys on the sign of z (rhs.c:627)
+            xyz[..., 2] -= cfg["z_shift"]
     ref.set_coords(xyz)
     ref.FormMetrics()
     met = dict(csi=np.array(ref.owned("lCsi")), eta=np.array(ref.owned("lEta")), zet=np.array(ref.owned("lZet")), aj=np.array(ref.owned("lAj")))
@@ -167,6 +169,13 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
     ctx.Formfunction_2("RHS_O", 1.0)
     rhs_o_ref = np.array(ref.owned("RHS_o"))
     err["Formfunction_2"] = relerr(ctx.download("RHS_O"), rhs_o_ref)
+    if cfg["bctype"][0] == 11 and cfg["bctype"][1] == 1:      # body-fitted cylinder: wall areas and pressure / viscous forces (momentum.c:822-849)
+        ref.set_owned("P", fields["p"])
+        ref.global_to_local("P", "lP")
+        ref.view("RHS_o")[...] = 0
+        ref.Formfunction_2("RHS_o", 1.0)
+        ctx.upload("P", fields["p"])
+        err["cylinder_forces"] = relerr(ctx.cylinder_forces(), ref.cylinder_forces())
     if cfg["flags"].get("viscosity_wallmodel"):      # Cabot wall law: friction velocity at the first cells (momentum.c:1150)
         err["Ustar"] = relerr(ctx.download("USTAR")[:, 1], np.array(ref.owned("lUstar"))[:, 1])
     # one Krylov-iteration residual

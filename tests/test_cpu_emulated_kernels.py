@@ -75,6 +75,47 @@ def test_emulated_wall_function_boundaries(pkg, refdrv, emu, bctype, extra):
     assert not bad, bad
 
 
+# the branches VERDICT round 1 listed as rejected: WENO3 convection (inviscid / levelset_weno = 5, momentum.c:754-770), the
+# skew-symmetric form (:789-800, 1638-1651), the Clark mixed model in the viscous flux (:904-923) and in the Germano
+# identity (les.c:420-428, 497-556, 656), each alone and combined with periodic seams / second order / the box filter
+VARIANT_FLAGS = [dict(inviscid=1), dict(levelset_weno=5), dict(skew=1), dict(skew=1, second_order=1), dict(clark=1), dict(clark=1, les=0),
+                 dict(clark=1, testfilter_ik=1), dict(skew=1, clark=1, kk_periodic=1, ii_periodic=0), dict(skew=1, jj_periodic=1, levelset_weno=5),
+                 dict(inviscid=1, immersed=3)]
+
+
+def _variant_cfg(base, extra):
+    cfg = dict(base)
+    cfg["flags"] = dict(base["flags"], **extra)
+    if extra.get("kk_periodic") or extra.get("jj_periodic"):
+        cfg["bctype"] = [1, 1, 1, 1, 100, 100] if extra.get("kk_periodic") else [100, 100, 100, 100, 5, 4]
+    return cfg
+
+
+@pytest.mark.parametrize("extra", VARIANT_FLAGS)
+def test_emulated_weno_skew_clark_variants(pkg, refdrv, emu, extra):
+    cfg = _variant_cfg(pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15), extra)
+    err = pc.run_parity(cfg, refdrv, lib=emu)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
+def test_emulated_cylinder_inflow_boundary(pkg, refdrv, emu):
+    """bctype[0] = 11 (body-fitted cylinder, rhs.c:626-634): the inflow mirror at the i = 0 nodes whose cell centre has
+    z <= 0 (the grid is shifted so that about half of them do), and the wall-force diagnostics Formfunction_2 accumulates
+    over the i = mx-2 faces (momentum.c:570-579, 822-849)."""
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15)
+    cfg = dict(base)
+    cfg["flags"] = dict(base["flags"], ii_periodic=0, kk_periodic=0)
+    cfg["bctype"] = [11, 1, 1, 1, 5, 4]
+    cfg["z_shift"] = 1.4
+    err = pc.run_parity(cfg, refdrv, lib=emu)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    assert "cylinder_forces" in err
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
 def test_emulated_fp_in_projection_bitwise(pkg, emu):
     """Option 12 (Fp evaluated inside the projection block program) against FpCell + Fp planes + Project: bitwise."""
     import numpy as np

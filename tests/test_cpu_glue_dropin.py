@@ -103,6 +103,8 @@ def run_dropin(refdrv, pkg, so_name, cfg):
         d.view("RHS_o")[...] = 0
         d.Formfunction_2("RHS_o", 1.0)
     err["Formfunction_2_RHS_o"] = pc.relerr(glue.owned("RHS_o"), ref.owned("RHS_o"))
+    if cfg["bctype"][0] == 11 and cfg["bctype"][1] == 1:      # the wall-force sums Formfunction_2 leaves in the UserCtx (momentum.c:822-849), read by main.c:1269
+        err["cylinder_forces"] = pc.relerr(glue.cylinder_forces(), ref.cylinder_forces())
     x = fields["ucont"] * (1.0 + 1e-3 * np.cos(np.arange(fields["ucont"].size).reshape(fields["ucont"].shape)))
     for d in (ref, glue):
         d.new_vec("X", 3, False); d.new_vec("F", 3, False)
@@ -133,11 +135,22 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     return err
 
 
-@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("wallfn", (13, 11, 15))])
+def variant_cfg(pkg, dims):
+    """Body-fitted cylinder boundary (bctype 11) with the skew-symmetric form and the Clark mixed model switched on."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], *dims)
+    cfg["flags"] = dict(cfg["flags"], ii_periodic=0, kk_periodic=0, skew=1, clark=1)
+    cfg["bctype"] = [11, 1, 1, 1, 5, 4]
+    cfg["z_shift"] = 1.4
+    return cfg
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("wallfn", (13, 11, 15)), ("variants", (17, 13, 15))])
 def test_glue_dropin_emulated(pkg, refdrv, name, dims):
     import emu_loader
     emu_loader.build()
-    if name == "wallfn":       # wall-function sides, first time step: IB_BC rewrites lNvert / Nvert on the host too
+    if name == "variants":
+        cfg = variant_cfg(pkg, dims)
+    elif name == "wallfn":       # wall-function sides, first time step: IB_BC rewrites lNvert / Nvert on the host too
         cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c2_box256"], *dims)
         cfg["flags"] = dict(cfg["flags"], ti=5, tistart=5, roughness_size=2.e-4)
         cfg["bctype"] = [100, 100, -1, -2, 100, 100]

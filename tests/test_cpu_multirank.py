@@ -50,11 +50,16 @@ def _worker(rank, world, port, tmp, cfgname, dims, flags_extra, bctype):
     ("c2_box256", (13, 11, 19), {}, None, 2),                    # kk periodic: rank 0 <-> rank 1 wrap
     ("c3_turbine", (17, 13, 21), {}, None, 2),                   # non-periodic k, IBM masks, F_eul
     ("c2_box256", (13, 11, 23), {}, None, 3),                    # a rank with two interior slab boundaries + the periodic seam
+    ("c2_box256", (13, 11, 19), dict(skew=1, clark=1, levelset_weno=5), None, 2),      # the flux / LES variants: Adv1-3 and the gradient planes travel too
+    ("c3_turbine", (17, 13, 21), dict(inviscid=1), None, 2),
 ])
 def test_two_ranks_bitwise_equal_single_rank(pkg, refdrv, tmp_path, cfgname, dims, extra, bctype, world):
     capi, cases = pkg.capi, pkg.cases
     lib = emu_loader.load(capi)
     cfg = cases.scaled(cases.CONFIGS[cfgname], *dims)
+    cfg["flags"] = dict(cfg["flags"], **extra)
+    if bctype:
+        cfg["bctype"] = bctype
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
     xyz = cases.make_grid(cfg)
     ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]), lib=lib)

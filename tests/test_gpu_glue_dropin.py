@@ -5,9 +5,10 @@ from test_cpu_glue_dropin import run_dropin, TOL
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,dims", [("c2_box256", (21, 17, 25)), ("c3_turbine", (29, 21, 25))])
+@pytest.mark.parametrize("name,dims", [("c2_box256", (21, 17, 25)), ("c3_turbine", (29, 21, 25)), ("variants", (29, 21, 25))])
 def test_glue_dropin_cuda(pkg, refdrv, name, dims):
-    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    from test_cpu_glue_dropin import variant_cfg
+    cfg = variant_cfg(pkg, dims) if name == "variants" else pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     err = run_dropin(refdrv, pkg, "libvfsglue_cuda.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad

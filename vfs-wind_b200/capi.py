@@ -23,7 +23,7 @@ EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_pressure_gradient", "vfs_download_async", "vfs_download_wait",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms",
-           "vfs_calc_f_eul", "vfs_calc_u_lagr", "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count"]
+           "vfs_calc_f_eul", "vfs_calc_u_lagr", "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count", "vfs_cylinder_forces"]
 
 
 class VfsParams(C.Structure):
@@ -89,6 +89,7 @@ def _bind(lib):
         getattr(lib, f).argtypes = [C.c_void_p]
     lib.vfs_formfunction2.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.vfs_pressure_gradient.argtypes = [C.c_void_p, C.c_double]
+    lib.vfs_cylinder_forces.argtypes = [C.c_void_p, C.c_void_p]
     lib.vfs_formfunction_snes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vfs_launch_count.argtypes = [C.c_void_p]
     lib.vfs_launch_count.restype = C.c_long
@@ -287,6 +288,12 @@ class VfsContext:
     def Pressure_Gradient(self, k_forcing=0.0):
         """momentum.c:203 on the current field "P"; result in field "DP"."""
         self._ck(self.lib.vfs_pressure_gradient(self.h, float(k_forcing)))
+
+    def cylinder_forces(self):
+        """momentum.c:822-849: (A_cyl, A_cyl_x, A_cyl_z, Fpx, Fpz, Fvx, Fvz) of this rank's wall faces (bctype[0] == 11)."""
+        out = np.zeros(7)
+        self._ck(self.lib.vfs_cylinder_forces(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     @staticmethod
     def _actuators(acts):

@@ -90,6 +90,13 @@ struct C2CGhostRules {
     }
     if (j == 0 && bc[2] == 12) { V3 a = ld3(d, SU, p + d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
     if (j == my - 1 && bc[3] == 12) { V3 a = ld3(d, SU, p - d.sj); u = mk3(-a.x, -a.y, 2.0 - a.z); if (solid_flag) u = mk3(0, 0, 0); w = true; }
+    // body-fitted cylinder, inflow half of the i = 0 side (rhs.c:626-634): cells whose centre lies at z <= 0 mirror to w = 1
+    // (no bctype-1 rule can have fired at these nodes — interior j and k, i = 0 — so the reference's solid_flag is false here)
+    if (bc[0] == 11 && i == 0 && j != 0 && j != my - 1 && kg != 0 && kg != mz - 1) {
+      const double *Z = d.s[S_Z];
+      const double zc = (Z[p + 1] + Z[p + 1 - d.sk] + Z[p + 1 - d.sj] + Z[p + 1 - d.sk - d.sj]) * 0.25;
+      if (zc <= 0) { V3 a = ld3(d, SU, p + 1); u = mk3(-a.x, -a.y, 2.0 - a.z); w = true; }
+    }
     if (bc[3] == 4 && j == my - 1 && i != 0 && i != mx - 1 && kg != 0 && kg != mz - 1) { u = ld3(d, SU, p - d.sj); w = true; }
     if (bc[5] == 4 && kg == mz - 1 && i != 0 && i != mx - 1 && j != 0 && j != my - 1) {
       if (d.s[S_NV][p - d.sk] > 0.1 || solid_flag) { u = mk3(0, 0, 0); w = true; }

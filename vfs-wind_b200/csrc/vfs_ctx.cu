@@ -462,12 +462,10 @@ static int check_params(const vfs_params *p, std::string &why) {
   if (p->kofs < 0 || p->nzl < 1 || p->kofs + p->nzl > p->mz) { why = "bad k-slab"; return VFS_ERR_ARG; }
   if (p->nranks == 1 && (p->kofs != 0 || p->nzl != p->mz)) { why = "single rank must own all k planes"; return VFS_ERR_ARG; }
   if (p->nranks > 1 && p->nzl < VFS_G) { why = "k-slab thinner than the ghost width"; return VFS_ERR_ARG; }
-  if (p->levelset || p->rans || p->inviscid || p->skew || p->movefsi || p->rotatefsi) { why = "levelset/rans/inviscid/skew/movefsi/rotatefsi are outside the hot-path scope"; return VFS_ERR_UNSUPPORTED; }
+  if (p->levelset || p->rans || p->movefsi || p->rotatefsi) { why = "levelset/rans/movefsi/rotatefsi are outside the hot-path scope"; return VFS_ERR_UNSUPPORTED; }
   if (p->i_periodic || p->j_periodic || p->k_periodic) { why = "legacy i/j/k_periodic not supported (use ii/jj/kk_periodic)"; return VFS_ERR_UNSUPPORTED; }
-  if (p->clark) { why = "clark model not supported"; return VFS_ERR_UNSUPPORTED; }
-  if (p->levelset_weno || p->freesurface_wallmodel || p->air_flow_levelset) { why = "levelset_weno / freesurface_wallmodel / air_flow_levelset reroute the flux and wall-model code in the reference (momentum.c:754,1015,1301) and are not built"; return VFS_ERR_UNSUPPORTED; }
+  if ((p->levelset_weno && p->levelset_weno != 5) || p->freesurface_wallmodel || p->air_flow_levelset) { why = "levelset_weno 1-4 / freesurface_wallmodel / air_flow_levelset key the flux and wall-model code on the level-set field (momentum.c:754,1015,1301) and are not built (levelset_weno = 5, WENO3 everywhere, is)"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
-  for (int q = 0; q < 6; q++) if (p->bctype[q] == 11) { why = "cylinder inflow boundary type 11 not supported"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 4; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2) { why = "wall-function boundary types (-1,-2) on a k side: Contra2Cart_2 has no velocity rule for them (rhs.c:311-440)"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 0; q < 4; q++) if (p->bctype[q] == -2 && !(p->roughness_size > 0)) { why = "bctype -2 (rough-wall log law) needs roughness_size > 0"; return VFS_ERR_ARG; }
   if (!(p->ren > 0) || !(p->dt > 0)) { why = "ren and dt must be positive"; return VFS_ERR_ARG; }
@@ -486,6 +484,7 @@ static void fill_dev(vfs_ctx *c) {
   d.testfilter_ik = p.testfilter_ik; d.visc_wm = p.viscosity_wallmodel; d.wallfunction = p.wallfunction;
   d.has_feul = (p.rotor_model || p.nacelle_model || p.IB_delta) ? 1 : 0;
   d.ti = p.ti; d.tistart = p.tistart; d.rstart_flg = p.rstart_flg; d.bdf2 = 0; d.single_rank = p.nranks == 1;
+  d.inviscid = p.inviscid; d.skew = p.skew; d.weno = p.inviscid || p.levelset_weno == 5;
   d.ren = p.ren; d.dt = p.dt; d.max_cs = p.max_cs; d.roughness = p.roughness_size;
   d.homo = (p.i_homo_filter && p.k_homo_filter) ? 1 : (p.i_homo_filter ? 2 : (p.j_homo_filter ? 3 : (p.k_homo_filter ? 4 : 0)));      // les.c:799,840
 }
@@ -1081,7 +1080,10 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   if (any_per(c)) RUN(node_copy(c, grp(S_UC0, 3)));                  // momentum.c:638-666
   const int k1 = klo(c, 1), k2 = klo(c, d.mz - 1);
   Box R;
-  bool march = c->fused == 2 && RhsMarch::region(d, R);     // experimental fully fused residual (option 0 = 2)
+  // weno / skew / clark / inviscid: the one-thread-per-face kernels with the variants compiled in (face_flux_core<.., X>)
+  const bool ex = d.weno || d.skew || d.clark || d.inviscid;
+  if (ex && d.skew) RUN(ensure_tail(c));
+  bool march = !ex && c->fused == 2 && RhsMarch::region(d, R);     // experimental fully fused residual (option 0 = 2)
 #ifndef VFS_EMU
   march = march && c->tma_ok;
 #endif
@@ -1102,7 +1104,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   }
   // staged chain: the whole domain, or the boundary slabs around R
 #ifndef VFS_EMU
-  if (!march && c->fused && c->tma_ok) {
+  if (!march && !ex && c->fused && c->tma_ok) {
     // regular faces: TMA-staged tiled kernel; faces 0 and m-2 along their normal: staged kernels on thin slabs
     // the six thin slabs write faces the marching kernel does not: they run beside it on the side stream
     SideScope sc; RUN(side_begin(c, &sc));
@@ -1118,6 +1120,12 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   } else
 #endif
   for (int n = 0; n < S.n; n++) {
+    if (ex) {
+      { FaceFluxX<0> f = {d}; RUN(launch(c, S.fl[n][0], f)); }
+      { FaceFluxX<1> f = {d}; RUN(launch(c, S.fl[n][1], f)); }
+      { FaceFluxX<2> f = {d}; RUN(launch(c, S.fl[n][2], f)); }
+      continue;
+    }
     { FaceFlux<0> f = {d}; RUN(launch(c, S.fl[n][0], f)); }
     { FaceFlux<1> f = {d}; RUN(launch(c, S.fl[n][1], f)); }
     { FaceFlux<2> f = {d}; RUN(launch(c, S.fl[n][2], f)); }
@@ -1125,7 +1133,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   ev_rec(c, 2 * VFS_T_FLUX + 1);
   const Grp gi = grp_cat(grp(S_FC1, 3), grp(S_FV1, 3)), gj = grp_cat(grp(S_FC2, 3), grp(S_FV2, 3)), gk = grp_cat(grp(S_FC3, 3), grp(S_FV3, 3));
   const int ka = d.kofs > 0 ? -VFS_G : 0, kb = d.kofs + d.nzl < d.mz ? d.nzl + VFS_G : d.nzl;      // as node_copy()
-  if (c->fused == 1 && c->fp_fused && S.n == 1) {
+  if (c->fused == 1 && c->fp_fused && S.n == 1 && !ex) {
     // ---- Fp folded into the projection (ProjFpMarch, vfs_march_kernels.h) ----
     // Flux ghosts as below; between ranks ALL face-flux families travel (Fp of the first ghost plane is evaluated
     // locally from them), in ONE exchange instead of the k-family + Fp exchanges of the staged chain.
@@ -1174,11 +1182,20 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   {
     if (d.perx) { WrapFill f = {d, gi, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
     if (d.pery) { WrapFill f = {d, gj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
-    const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8;
+    const bool ovl = can_overlap(c) && S.n == 1 && d.nzl >= 8 && !ex;
     FpCell fp1 = {d};
     FpCell2 fp2 = {d};
+    FpCellX fpx = {d};
+    if (ex && d.skew) {      // the advective half Adv1-3 travels with the fluxes (momentum.c:1470-1484, 1540-1544)
+      const Grp ai = grp(S_ADV1, 3), aj = grp(S_ADV2, 3), ak = grp(S_ADV3, 3);
+      if (d.perx) { WrapFill f = {d, ai, 0}; Box b = {0, 2 * VFS_G, 0, d.my, 0, d.nzl}; RUN(launch(c, b, f)); }
+      if (d.pery) { WrapFill f = {d, aj, 1}; Box b = {-VFS_G, d.mx + VFS_G, 0, 2 * VFS_G, 0, d.nzl}; RUN(launch(c, b, f)); }
+      RUN(halo_k(c, ak, false, 3, 2));
+      if (any_per(c)) { NodeCopyAdv f = {d}; RUN(launch_shell(c, ka, kb, f, false, SHELL_PERIODIC_ONLY)); }
+    }
     // two cells per thread (16-byte loads) when the box starts at the first interior cell; the functor skips i = 0 / mx-1
     auto fp_launch = [&](const Box &b) -> int {
+      if (ex) return launch(c, b, fpx);
       if (c->fp_pairs && b.i0 == 1 && b.i1 == d.mx - 1) { Box h = b; h.i0 = 0; h.i1 = (d.mx + 1) / 2; return launch(c, h, fp2); }
       return launch(c, b, fp1);
     };
@@ -1256,6 +1273,40 @@ extern "C" int vfs_pressure_gradient(vfs_ctx *c, double k_forcing) {
   RUN(zero_scalars(c, S_DP0, 3));                                     // VecSet(dP, 0.), :313
   { PressureGradient f = {d, k_forcing}; RUN(launch(c, box_interior(c), f)); }
   return vfs_sync(c);
+}
+
+// ---- cylinder force diagnostics of Formfunction_2 (momentum.c:570-579, 822-849) ------------------------------------
+// out[7] = this rank's lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl, lFvz_cyl from the current UCAT (as the last
+// residual evaluation left it) and P; zeros unless bctype[0] == 11 and bctype[1] == 1.  The reference sums them
+// over ranks itself (main.c:1269-1277).
+extern "C" int vfs_cylinder_forces(vfs_ctx *c, double *out7) {
+  if (!c || !out7) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  for (int q = 0; q < 7; q++) out7[q] = 0;
+  if (d.bc[0] != 11 || d.bc[1] != 1) return 0;
+  RUN(ensure_iaj(c));
+  const long nface = (long)d.nzl * d.my;
+  double *buf = 0;
+  std::vector<double> h(7 * nface);
+#ifndef VFS_EMU
+  CK(cudaMalloc((void **)&buf, 7 * nface * sizeof(double)));
+  CK(cudaMemsetAsync(buf, 0, 7 * nface * sizeof(double), c->stream));
+#else
+  buf = (double *)calloc(7 * nface, sizeof(double));
+#endif
+  int rc = 0;
+  { CylinderForce f = {d, buf, nface}; Box b = {d.mx - 2, d.mx - 1, 1, d.my - 1, klo(c, 1), klo(c, d.mz - 1)}; rc = launch(c, b, f); }
+#ifndef VFS_EMU
+  if (!rc && cudaMemcpyAsync(h.data(), buf, 7 * nface * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = VFS_ERR_CUDA;
+  if (!rc) rc = vfs_sync(c);
+  cudaFree(buf);
+#else
+  memcpy(h.data(), buf, 7 * nface * sizeof(double));
+  free(buf);
+#endif
+  if (rc) return rc;
+  for (int q = 0; q < 7; q++) { double s = 0; for (long f = 0; f < nface; f++) s += h[q * nface + f]; out7[q] = s; }
+  return 0;
 }
 
 // ---- actuator forcing: Calc_F_eul / Calc_U_lagr (rotor_model.c:3668, 2937) -------------------------------------
@@ -1508,6 +1559,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   RUN(ensure_iaj(c));
   RUN(ensure_near(c));
+  if (d.clark) RUN(ensure_tail(c));
   ev_rec(c, 2 * VFS_T_LES1);
   // Between ranks the 13 pass-1 fields are NOT exchanged: pass 1 is replayed on the ghost planes pass 2 reads — plane -1
   // / nzl across an interior slab boundary, and across the periodic seam plane -2 / nzl+1 (the images of global
@@ -1526,6 +1578,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   const int ka = replay && (d.kofs > 0 || d.perz) ? -2 : 0, kb = replay && (d.kofs + d.nzl < d.mz || d.perz) ? d.nzl + 2 : d.nzl;
   for (size_t q = 0; q < k_ranges.size(); q++) {
     const int q0 = k_ranges[q].first, q1 = k_ranges[q].second;
+    if (d.clark) { LesGradStore f = {d, 0}; Box b = box_interior(c); b.k0 = q0; b.k1 = q1; RUN(launch(c, b, f)); }
     if (c->fused && !d.testfilter_ik) {
       int r;
 #ifndef VFS_EMU
@@ -1542,11 +1595,22 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   c->sabs_valid = true;
   Grp g1 = grp_cat(grp(S_UF0, 3), grp(S_LW, 10));
   const Grp g1c = grp_cat(grp(S_UF0, 3), grp(S_LU0, 9));
+  const Grp ggr = grp(S_GR0, 9);
   if (replay) {
     { LesDeriveBoundary f = {d, (c->les_bnd_valid && c->halo_trim) ? 1 : 0}; c->les_bnd_valid = true; RUN(launch_shell(c, ka, kb, f, true)); }
     RUN(wrap_ij(c, g1, ka, kb));                                        // les.c:254-267 without the k exchange
     if (any_per(c)) { NodeCopy f = {d, g1c, 1}; RUN(launch_shell(c, ka, kb, f, true, SHELL_PERIODIC_ONLY)); }     // les.c:275-306
+    if (d.clark) {
+      { LesGradStore f = {d, 1}; RUN(launch_shell(c, ka, kb, f, true)); }
+      RUN(wrap_ij(c, ggr, ka, kb));
+      if (any_per(c)) { NodeCopy f = {d, ggr, 1}; RUN(launch_shell(c, ka, kb, f, true, SHELL_PERIODIC_ONLY)); }
+    }
   } else {
+    if (d.clark) {
+      { LesGradStore f = {d, 1}; RUN(launch_shell(c, 0, d.nzl, f)); }
+      RUN(g2l(c, ggr, 2, 2));
+      if (any_per(c)) RUN(node_copy(c, ggr));
+    }
     RUN(run_les_derive_boundary(c));
     RUN(g2l(c, g1, 2, 2));                                              // les.c:254-267 (pass 2 reads k+-1, the seam copies k+-2)
     // the weight w is a function of the node's own nvert/aj (get_weight, les.c:31-40) and is NOT
@@ -1554,7 +1618,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
     if (any_per(c)) RUN(node_copy(c, g1c));                             // les.c:275-306
   }
   ev_rec(c, 2 * VFS_T_LES2);
-  if (c->fused && !d.testfilter_ik && les2_march_ok(c)) {
+  if (c->fused && !d.testfilter_ik && !d.clark && les2_march_ok(c)) {
     Box bi = box_interior(c);
     if (!c->lesgeo_valid) { LesGeo f = {d}; RUN(launch(c, bi, f)); c->lesgeo_valid = true; }
     int r;

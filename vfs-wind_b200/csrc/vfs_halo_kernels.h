@@ -147,6 +147,18 @@ struct NodeCopyFlux {
   }
 };
 
+// the same periodic boundary-node copies for the advective half Adv1-3 of the skew-symmetric form (momentum.c:1540-1544)
+struct NodeCopyAdv {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    if (d.perx && (i == 0 || i == d.mx - 1)) { const long q = d.idx(i == 0 ? -2 : d.mx + 1, j, k); for (int a = 0; a < 3; a++) d.s[S_ADV1 + a][p] = d.s[S_ADV1 + a][q]; }
+    if (d.pery && (j == 0 || j == d.my - 1)) { const long q = d.idx(i, j == 0 ? -2 : d.my + 1, k); for (int a = 0; a < 3; a++) d.s[S_ADV2 + a][p] = d.s[S_ADV2 + a][q]; }
+    if (d.perz && (kg == 0 || kg == d.mz - 1)) { const long q = d.idx(i, j, kg == 0 ? k - 2 : k + 2); for (int a = 0; a < 3; a++) d.s[S_ADV3 + a][p] = d.s[S_ADV3 + a][q]; }
+  }
+};
+
 // near-solid byte mask (VfsDev::near): 1 where any node of the 5x5x5 cube around the node has nvert != 0.
 // Evaluated on the owned nodes grown by 2 (the cube then stays inside the G = 4 ghost frame, whose
 // nvert values are the wrap / neighbour-rank images); everything outside keeps the initial 1.

@@ -233,6 +233,19 @@ struct LesPass1 {
   }
 };
 
+// clark: the velocity gradient of every cell kept for pass 2 (lSx, lSy, lSz of les.c:181-232; zero at solid cells and,
+// unless a periodic node copy overwrites it, at the boundary nodes).  A separate small kernel so that the marching
+// pass-1 kernels keep their register budget; the mixed model runs the one-thread-per-cell pass 1 and 2 anyway.
+struct LesGradStore {
+  VfsDev d; int boundary;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    if (!boundary && !(d.s[S_NV][p] > 1.1)) grad_center(d, S_U0, i, j, d.kglob(k), p, g);
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) d.s[S_GR0 + 3 * a + b][p] = g[a][b];
+  }
+};
+
 // les.c:354-439 per-node part of pass 2: weight w and the products entering the test filters,
 // v[0] = w, v[1..9] = U_a u_b (a-major), v[10..15] = |S| S_ij (xx,xy,xz,yy,yz,zz)
 #define VFS_LES2_NV 16
@@ -246,7 +259,9 @@ VFS_HD void les2_products(const VfsDev &d, long n, double *v) {
 
 // les.c:441-669 after the filters: fs[0] = sum of Simpson weights (or 36 for testfilter_ik),
 // fs[1..15] = filtered sums of v[1..15]; sum_weight = sum of w*coef (les.c:441-468)
-VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const double *fs, double sum_weight) {
+// clark (mixed model, les.c:497-556, 656): fT = filtered sums of the six Clark-tensor components T_ab (xx,xy,xz,yy,yz,zz)
+// of the stencil nodes, h2 = the cell's squared grid lengths; null without the model
+VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const double *fs, double sum_weight, const double *fT = nullptr, const double *h2 = nullptr) {
   const double ajc = d.s[S_AJ][p];
   const double csi[3] = {d.s[S_CSI0][p], d.s[S_CSI1][p], d.s[S_CSI2][p]};
   const double eta[3] = {d.s[S_ETA0][p], d.s[S_ETA1][p], d.s[S_ETA2][p]};
@@ -274,6 +289,21 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
   for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Lij[a][b] = VFS_FDIV(fs[1 + 3 * a + b]) - _U[a] * _u[b];
   SSh[0][0] = VFS_FDIV(fs[10]); SSh[0][1] = SSh[1][0] = VFS_FDIV(fs[11]); SSh[0][2] = SSh[2][0] = VFS_FDIV(fs[12]);
   SSh[1][1] = VFS_FDIV(fs[13]); SSh[1][2] = SSh[2][1] = VFS_FDIV(fs[14]); SSh[2][2] = VFS_FDIV(fs[15]);
+  double Nij[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  if (fT) {
+    // N^c = 4 R - T^ with R the Clark tensor of the test-filtered velocity gradient, rotated like M (les.c:517-556)
+    const int ix[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    double Nc[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+      const double R = (gh[a][0] * gh[b][0] * h2[0] + gh[a][1] * gh[b][1] * h2[1] + gh[a][2] * gh[b][2] * h2[2]) / 12.;
+      Nc[a][b] = 4.0 * R - VFS_FDIV(fT[ix[a][b]]);
+    }
+    for (int a = 0; a < 3; a++) {
+      Nij[a][0] = Nc[a][0] * csi[0] + Nc[a][1] * csi[1] + Nc[a][2] * csi[2];
+      Nij[a][1] = Nc[a][0] * eta[0] + Nc[a][1] * eta[1] + Nc[a][2] * eta[2];
+      Nij[a][2] = Nc[a][0] * zet[0] + Nc[a][1] * zet[1] + Nc[a][2] * zet[2];
+    }
+  }
 #undef VFS_FDIV
   // covariant metric tensor G (les.c:607-622)
   const double a11 = csi[0], a12 = csi[1], a13 = csi[2], a21 = eta[0], a22 = eta[1], a23 = eta[2], a31 = zet[0], a32 = zet[1], a33 = zet[2];
@@ -304,7 +334,10 @@ VFS_HD void les2_finish(const VfsDev &d, int i, int j, int kg, long p, const dou
     M[a][2] = Mc[a][0] * zet[0] + Mc[a][1] * zet[1] + Mc[a][2] * zet[2];
   }
   double num = 0, den = 0;
-  for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) num += Lij[b][a] * M[a][q] * G[b][q];
+  for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+    num += Lij[b][a] * M[a][q] * G[b][q];
+    if (fT) num -= Nij[b][a] * M[a][q] * G[b][q];
+  }
   for (int m = 0; m < 3; m++) for (int n = 0; n < 3; n++) for (int l = 0; l < 3; l++) den += M[n][m] * M[n][l] * G[m][l];
   d.s[S_LM][p] = num; d.s[S_MM][p] = den;
 }
@@ -382,10 +415,25 @@ struct LesPass2 {
     if (d.s[S_NV][p] > 1.1) { d.s[S_LM][p] = 0; d.s[S_MM][p] = 0; return; }
     double fs[VFS_LES2_NV], sum_weight = 0;
     for (int a = 0; a < VFS_LES2_NV; a++) fs[a] = 0;
+    double fT[6] = {0, 0, 0, 0, 0, 0}, h2[3] = {0, 0, 0};
+    if (d.clark) {                                     // the cell's own grid lengths weigh every stencil node's gradient (les.c:347-348, 420-428)
+      double m9[9], dx, dy, dz;
+      for (int a = 0; a < 9; a++) m9[a] = d.s[S_CSI0 + a][p];
+      grid_lengths(d.s[S_AJ][p], m9, dx, dy, dz);
+      h2[0] = dx * dx; h2[1] = dy * dy; h2[2] = dz * dz;
+    }
     for (int r = -1; r <= 1; r++) for (int q = -1; q <= 1; q++) for (int pp = -1; pp <= 1; pp++) {
       const long n = p + r * d.sk + q * d.sj + pp;
       double v[VFS_LES2_NV];
       les2_products(d, n, v);
+      if (d.clark) {
+        double g[3][3];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) g[a][b] = d.s[S_GR0 + 3 * a + b][n];
+        const double cw = d.testfilter_ik ? (q != 0 ? 0. : (r == 0 ? 4. : 1.) * (pp == 0 ? 4. : 1.)) : simpson_w(r, q, pp) * v[0];
+        int t = 0;
+        for (int a = 0; a < 3; a++) for (int b = a; b < 3; b++, t++)
+          fT[t] += cw * ((g[a][0] * g[b][0] * h2[0] + g[a][1] * g[b][1] * h2[1] + g[a][2] * g[b][2] * h2[2]) / 12.);
+      }
       sum_weight += v[0] * (0.125 * (r == 0 ? 2. : 1.) * (q == 0 ? 2. : 1.) * (pp == 0 ? 2. : 1.));   // coef table les.c:441-451
       if (d.testfilter_ik) {
         if (q != 0) continue;
@@ -398,7 +446,8 @@ struct LesPass2 {
       }
     }
     if (d.testfilter_ik) fs[0] = 36.;
-    les2_finish(d, i, j, kg, p, fs, sum_weight);
+    if (d.clark) les2_finish(d, i, j, kg, p, fs, sum_weight, fT, h2);
+    else les2_finish(d, i, j, kg, p, fs, sum_weight);
   }
 };
 

@@ -53,8 +53,42 @@ template <int D, int T, class Acc> VFS_HD double dtan(const Acc &A, int a, const
 // integer node", momentum.c:508-509).  c = index of p along D (global), m = node count along D.
 // REGULAR = true compiles out the domain-end / periodic-end special cases (faces 1..m-3 only).
 // Metrics, nu_t and ucont come through the accessor (at p and p + e_D).
-template <int D, bool REGULAR, class Acc>
-VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], double fv[3]) {
+// X = true adds the rarely used variants, one-thread-per-face staged path only (never instantiated by the marching
+// kernels, whose register budget they would break): WENO3 convection (`inviscid`, levelset_weno == 5; momentum.c:754-770,
+// level.c:1352), the skew-symmetric form (`skew`: half the divergence form + the advective half in adv[], :789-800) and
+// the Clark mixed-model term of the viscous flux (`clark`, :904-923).
+// Calculate_dxdydz (rhs2.c:683-699): |sum of the three cell-edge vectors| per Cartesian direction, edge vector m = unit
+// normal of metric family m (column m of the inverse metric matrix, normalised) times vol / |metric m|
+VFS_HD void grid_lengths(double ajc, const double *m, double &dx, double &dy, double &dz) {
+  const double a11 = m[0], a12 = m[1], a13 = m[2], a21 = m[3], a22 = m[4], a23 = m[5], a31 = m[6], a32 = m[7], a33 = m[8];
+  const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+  double G[3][3];
+  G[0][0] = (a33 * a22 - a32 * a23) / det; G[0][1] = -(a33 * a12 - a32 * a13) / det; G[0][2] = (a23 * a12 - a22 * a13) / det;
+  G[1][0] = -(a33 * a21 - a31 * a23) / det; G[1][1] = (a33 * a11 - a31 * a13) / det; G[1][2] = -(a23 * a11 - a21 * a13) / det;
+  G[2][0] = (a32 * a21 - a31 * a22) / det; G[2][1] = -(a32 * a11 - a31 * a12) / det; G[2][2] = (a22 * a11 - a21 * a12) / det;
+  const double vol = 1. / ajc;
+  double e[3][3];     // e[q][x]: edge vector of family q
+  for (int q = 0; q < 3; q++) {
+    const double nx = G[0][q], ny = G[1][q], nz = G[2][q];
+    const double sum = sqrt(nx * nx + ny * ny + nz * nz);
+    const double area = sqrt(m[3 * q] * m[3 * q] + m[3 * q + 1] * m[3 * q + 1] + m[3 * q + 2] * m[3 * q + 2]);
+    const double L = vol / area;
+    e[q][0] = L * (nx / sum); e[q][1] = L * (ny / sum); e[q][2] = L * (nz / sum);
+  }
+  dx = fabs(e[0][0] + e[1][0] + e[2][0]); dy = fabs(e[0][1] + e[1][1] + e[2][1]); dz = fabs(e[0][2] + e[1][2] + e[2][2]);
+}
+VFS_HD double weno3(double f0, double f1, double f2, double f3, double wavespeed) {      // level.c:1352-1388
+  const double fL = wavespeed > 0 ? f0 : f3, fC = wavespeed > 0 ? f1 : f2, fR = wavespeed > 0 ? f2 : f1;
+  const double d0 = 2. / 3., d1 = 1. / 3., eps = 1.e-6;
+  const double beta0 = (fC - fR) * (fC - fR), beta1 = (fL - fC) * (fL - fC);          // pow(x, 2.) is exact x*x
+  const double alpha0 = d0 / ((eps + beta0) * (eps + beta0)), alpha1 = d1 / ((eps + beta1) * (eps + beta1));
+  const double sumalpha = alpha0 + alpha1;
+  const double w0 = alpha0 / sumalpha, w1 = alpha1 / sumalpha;
+  const double u0 = (fC * 0.5 + fR * 0.5), u1 = (-fL * 0.5 + fC * 1.5);
+  return w0 * u0 + w1 * u1;
+}
+template <int D, bool REGULAR, class Acc, bool X = false>
+VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], double fv[3], double *adv = nullptr) {
   constexpr int ni = (D == 0), nj = (D == 1), nk = (D == 2);
   const int m = (D == 0 ? d.mx : (D == 1 ? d.my : d.mz));
   const int per = (D == 0 ? d.perx : (D == 1 ? d.pery : d.perz));
@@ -122,6 +156,9 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], d
       const double u0 = A.u(a, 0, 0, 0), u1 = A.u(a, ni, nj, nk), um1 = A.u(a, -ni, -nj, -nk);
       fc[a] = um * (0.125 * (-u1 - 2. * u1 + 3. * u0) + u1) + up * (0.125 * (-um1 - 2. * u0 + 3. * u1) + u0);
     }
+  } else if (X && d.weno) {
+    for (int a = 0; a < 3; a++)
+      fc[a] = -uc0 * weno3(A.u(a, oL * ni, oL * nj, oL * nk), A.u(a, 0, 0, 0), A.u(a, ni, nj, nk), A.u(a, oR * ni, oR * nj, oR * nk), uc0);
   } else if (d.second_order) {
 #pragma unroll
     for (int a = 0; a < 3; a++) fc[a] = -uc0 * 0.5 * (A.u(a, 0, 0, 0) + A.u(a, ni, nj, nk));
@@ -135,7 +172,23 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], d
       fc[a] = -uc0 * 0.0625 * (-uL + 9. * u0 + 9. * u1 - uR);
     }
   }
-  if (nvp + nvn > 0.1 && (d.immersed == 3 || !d.immersed)) fc[0] = fc[1] = fc[2] = 0;
+  if (X && d.skew) {
+    // denom: 3, or 1 at a non-periodic domain end and with second_order; the nvert collapse of the stencil resets it
+    // in the k direction only (momentum.c:734 / 996 against 1258)
+    double denom = 3.;
+    if ((c == 0 || c == m - 2) && !per) denom = 1.;
+    else if (D == 2 && !(c == 0 || c == m - 2) && coll) denom = 1.;
+    if (d.second_order) denom = 1.;
+    for (int a = 0; a < 3; a++) {
+      fc[a] *= 0.5;
+      const double d4 = (A.u(a, oR * ni, oR * nj, oR * nk) - A.u(a, oL * ni, oL * nj, oL * nk)) * (1. / denom);
+      adv[a] = -0.5 * uc0 * (9. / 8. * du[a][D] - 1. / 8. * d4);
+    }
+  }
+  if (nvp + nvn > 0.1 && (d.immersed == 3 || !d.immersed)) {
+    fc[0] = fc[1] = fc[2] = 0;
+    if (X && d.skew) adv[0] = adv[1] = adv[2] = 0;
+  }
 
   // ---- viscous + SGS flux (momentum.c:856-902) ----
   const double nu = 1. / d.ren;
@@ -159,6 +212,21 @@ VFS_HD void face_flux_core(const VfsDev &d, const Acc &A, int c, double fc[3], d
     for (int a = 0; a < 3; a++)
       fv[a] += (g1 * du[a][0] + g2 * du[a][1] + g3 * du[a][2] + r[0][a] * n.x + r[1][a] * n.y + r[2][a] * n.z) * ajc * nu;
   }
+  if (X && d.clark) {
+    // grid lengths from the CENTRE metrics of node p with the face Jacobian (Calculate_dxdydz, rhs2.c:683-699)
+    double m9[9];
+    for (int q = 0; q < 9; q++) m9[q] = A.template met<D>(q, 0);
+    double dx, dy, dz;
+    grid_lengths(ajc, m9, dx, dy, dz);
+    const double h2[3] = {dx * dx, dy * dy, dz * dz};
+    double g[3][3];                       // g[a][b] = du_a/dx_b (Compute_du_dxyz)
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) g[a][b] = r[a][b] * ajc;
+    for (int a = 0; a < 3; a++) {
+      double t[3];
+      for (int b = 0; b < 3; b++) t[b] = (g[a][0] * g[b][0] * h2[0] + g[a][1] * g[b][1] * h2[1] + g[a][2] * g[b][2] * h2[2]);
+      fv[a] -= (t[0] * n.x + t[1] * n.y + t[2] * n.z) / 12.;
+    }
+  }
 }
 
 template <int D> struct FaceFlux {
@@ -171,6 +239,21 @@ template <int D> struct FaceFlux {
     face_flux_core<D, false>(d, A, c, fc, fv);
     const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D;
     for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
+  }
+};
+
+// the variants' form of the same kernel (weno / skew / clark, see face_flux_core): also stores the advective half Adv1-3
+template <int D> struct FaceFluxX {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int c = (D == 0 ? i : (D == 1 ? j : k + d.kofs));
+    const long p = d.idx(i, j, k);
+    GlobalAcc A = {d, p};
+    double fc[3], fv[3], adv[3] = {0, 0, 0};
+    face_flux_core<D, false, GlobalAcc, true>(d, A, c, fc, fv, adv);
+    const int sc = S_FC1 + 3 * D, sv = S_FV1 + 3 * D, sa = S_ADV1 + 3 * D;
+    for (int a = 0; a < 3; a++) { d.s[sc + a][p] = fc[a]; d.s[sv + a][p] = fv[a]; }
+    if (d.skew) for (int a = 0; a < 3; a++) d.s[sa + a][p] = adv[a];
   }
 };
 
@@ -318,9 +401,45 @@ struct PressureGradient {
   }
 };
 
+// ---- body-fitted cylinder diagnostics of Formfunction_2 (momentum.c:570-579, 822-849; bctype[0] == 11, bctype[1] == 1) ----
+// Per i-face of the wall plane i = mx-2: face area A = |icsi|, |icsi.x|, |icsi.z| and the pressure / viscous force
+// components along x and z with the inward unit normal (the first column of the inverse metric matrix, normalised,
+// rhs2.c:649-680) — seven numbers per face, written to out[q * nface + (k * my + j)], zero where the loop does not run.
+// The host adds them up in the reference's loop order (k, then j).  Face gradients as in face_flux_core.
+struct CylinderForce {
+  VfsDev d; double *out; long nface;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    GlobalAcc A = {d, p};
+#define VFS_F3(s0) mk3(0.5 * A.template met<0>(s0, 0) + 0.5 * A.template met<0>(s0, 1), 0.5 * A.template met<0>(s0 + 1, 0) + 0.5 * A.template met<0>(s0 + 1, 1), \
+                       0.5 * A.template met<0>(s0 + 2, 0) + 0.5 * A.template met<0>(s0 + 2, 1))
+    const V3 cs = VFS_F3(0), et = VFS_F3(3), ze = VFS_F3(6);
+#undef VFS_F3
+    const double ajc = 2. / (A.template iaj<0>(0) + A.template iaj<0>(1));
+    double du[3][3];
+    for (int a = 0; a < 3; a += 2) { du[a][0] = A.u(a, 1, 0, 0) - A.u(a, 0, 0, 0); du[a][1] = dtan<0, 1>(A, a); du[a][2] = dtan<0, 2>(A, a); }
+    const double du_dx = (du[0][0] * cs.x + du[0][1] * et.x + du[0][2] * ze.x) * ajc, du_dz = (du[0][0] * cs.z + du[0][1] * et.z + du[0][2] * ze.z) * ajc;
+    const double dw_dx = (du[2][0] * cs.x + du[2][1] * et.x + du[2][2] * ze.x) * ajc, dw_dz = (du[2][0] * cs.z + du[2][1] * et.z + du[2][2] * ze.z) * ajc;
+    const double Sxx = 0.5 * (du_dx + du_dx), Sxz = 0.5 * (du_dz + dw_dx), Szz = 0.5 * (dw_dz + dw_dz);
+    const double Ai = sqrt(cs.x * cs.x + cs.y * cs.y + cs.z * cs.z);
+    const double a11 = cs.x, a12 = cs.y, a13 = cs.z, a21 = et.x, a22 = et.y, a23 = et.z, a31 = ze.x, a32 = ze.y, a33 = ze.z;
+    const double det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+    double nx = (a33 * a22 - a32 * a23) / det, ny = -(a33 * a21 - a31 * a23) / det, nz = (a32 * a21 - a31 * a22) / det;
+    const double sum = sqrt(nx * nx + ny * ny + nz * nz);
+    nx /= sum; ny /= sum; nz /= sum;
+    nx *= -1; ny *= -1; nz *= -1;
+    const double P = 2 * d.s[S_P][p - 1] - d.s[S_P][p];
+    const long f = (long)k * d.my + j;
+    out[0 * nface + f] = Ai; out[1 * nface + f] = fabs(cs.x); out[2 * nface + f] = fabs(cs.z);
+    out[3 * nface + f] = -P * nx * Ai; out[4 * nface + f] = -P * nz * Ai;
+    out[5 * nface + f] = 2.0 * (Sxx * nx + 0 * ny + Sxz * nz) * Ai / d.ren;
+    out[6 * nface + f] = 2.0 * (Sxz * nx + 0 * ny + Szz * nz) * Ai / d.ren;
+  }
+};
+
 // momentum.c:1548-1678: flux divergence with 4th-order correction + viscous divergence -> Fp of the cell at
 // node p = (i, j, k); kg = global k of the cell (for a ghost plane across the periodic seam: the plane it images)
-VFS_HD void fp_cell_value(const VfsDev &d, int i, int j, int kg, long p, double out[3]) {
+template <bool X = false> VFS_HD void fp_cell_value(const VfsDev &d, int i, int j, int kg, long p, double out[3]) {
   const long st[3] = {1, d.sj, d.sk};
   const int cc[3] = {i, j, kg}, mm[3] = {d.mx, d.my, d.mz}, pp[3] = {d.perx, d.pery, d.perz};
   const double *nv = d.s[S_NV];
@@ -330,7 +449,35 @@ VFS_HD void fp_cell_value(const VfsDev &d, int i, int j, int kg, long p, double 
     div[a] = (d.s[S_FC1 + a][p] - d.s[S_FC1 + a][p - 1] + d.s[S_FC2 + a][p] - d.s[S_FC2 + a][p - d.sj] + d.s[S_FC3 + a][p] - d.s[S_FC3 + a][p - d.sk]);
     vis[a] = (d.s[S_FV1 + a][p] - d.s[S_FV1 + a][p - 1] + d.s[S_FV2 + a][p] - d.s[S_FV2 + a][p - d.sj] + d.s[S_FV3 + a][p] - d.s[S_FV3 + a][p - d.sk]);
   }
-  if (!d.second_order) {
+  if (X && d.inviscid) {                      // momentum.c:1624, 1663: second-order divergence only, no viscous term, no advective half
+    for (int a = 0; a < 3; a++) out[a] = div[a];
+  } else if (X && d.skew) {
+    // momentum.c:1626-1651: the divergence half as below, plus the advective half averaged to the cell with the same
+    // 9/8, -1/8 weights over the same outer faces (with second_order the outer faces collapse onto the cell's own)
+    double adv[3][3];
+    for (int D = 0; D < 3; D++) {
+      const int c = cc[D], m = mm[D], per = pp[D];
+      const long s = st[D];
+      long pR = p + s, pL = p - 2 * s;
+      double den = 3.;
+      if (c == 1) { if (per) pL = p - 4 * s; else pR = p, pL = p - s, den = 1.; }
+      else if (c == 2 || c == m - 3) { if (!per) pR = p, pL = p - s, den = 1.; }
+      else if (c == m - 2) { if (per) pR = p + 3 * s; else pR = p, pL = p - s, den = 1.; }
+      if (nv[p - s] + nv[p] + nv[p + s] > 0.1) pR = p, pL = p - s, den = 1.;
+      const double inv = 1. / den;
+      if (d.second_order) pR = p, pL = p - s;
+      else for (int a = 0; a < 3; a++) div4[a] += (d.s[S_FC1 + 3 * D + a][pR] - d.s[S_FC1 + 3 * D + a][pL]) * inv;
+      for (int a = 0; a < 3; a++) {
+        const double *A = d.s[S_ADV1 + 3 * D + a];
+        adv[D][a] = 9. / 8. * 0.5 * (A[p] + A[p - s]) - 1. / 8. * 0.5 * (A[pR] + A[pL]);
+      }
+    }
+    for (int a = 0; a < 3; a++) {
+      double v = d.second_order ? div[a] : (9. / 8.) * div[a] + (-1. / 8.) * div4[a];
+      v += adv[0][a]; v += adv[1][a]; v += adv[2][a];
+      out[a] = v + vis[a];
+    }
+  } else if (!d.second_order) {
     for (int D = 0; D < 3; D++) {
       const int c = cc[D], m = mm[D], per = pp[D];
       const long s = st[D];
@@ -354,6 +501,15 @@ struct FpCell {
     const long p = d.idx(i, j, k);
     double f[3];
     fp_cell_value(d, i, j, k + d.kofs, p, f);
+    for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = f[a];
+  }
+};
+struct FpCellX {      // with the inviscid / skew variants (staged path only)
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    double f[3];
+    fp_cell_value<true>(d, i, j, k + d.kofs, p, f);
     for (int a = 0; a < 3; a++) d.s[S_FP0 + a][p] = f[a];
   }
 };

@@ -42,8 +42,50 @@ class TorchHalo:
         self.G = G
         ctx.set_halo_callback(self.exchange)
 
+    def _tail_view(self, sid):
+        """A scalar outside the main pool (allocated on first use: Ucont_rm1, Adv1-3, the clark gradient planes)."""
+        ctx = self.ctx
+        ptr = ctx.scalar_ptr(sid)
+        if not ptr:
+            raise RuntimeError("halo exchange of scalar %d before its allocation" % sid)
+        if self.device.type == "cuda":
+            flat = torch.as_tensor(_CudaBlob(ptr, ctx.scalar_len), device=self.device)
+        else:
+            flat = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(ctx.scalar_len,)))
+        return flat.view(ctx.nzt, ctx.plane)
+
+    def _exchange_tail(self, ids):
+        """Same exchange for ids that include scalars outside the pool: gathered view by view."""
+        G = self.G
+        views = [self.pool[i] if i < self.pool.shape[0] else self._tail_view(i) for i in ids]
+        nzt = views[0].shape[0]
+        nlo, nhi = self.ctx.halo_layers()
+        ops, recvs = [], []
+        if self.hi is not None:
+            sb = torch.stack([v[nzt - G - nlo:nzt - G] for v in views]).contiguous()
+            ops.append(dist.P2POp(dist.isend, sb, self.hi)); self.bytes_sent += sb.numel() * 8
+        if self.lo is not None:
+            sb2 = torch.stack([v[G:G + nhi] for v in views]).contiguous()
+            ops.append(dist.P2POp(dist.isend, sb2, self.lo)); self.bytes_sent += sb2.numel() * 8
+        if self.lo is not None:
+            rb = torch.empty((len(ids), nlo, views[0].shape[1]), dtype=views[0].dtype, device=views[0].device)
+            ops.append(dist.P2POp(dist.irecv, rb, self.lo)); recvs.append((rb, slice(G - nlo, G)))
+        if self.hi is not None:
+            rb2 = torch.empty((len(ids), nhi, views[0].shape[1]), dtype=views[0].dtype, device=views[0].device)
+            ops.append(dist.P2POp(dist.irecv, rb2, self.hi)); recvs.append((rb2, slice(nzt - G, nzt - G + nhi)))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for rb, sl in recvs:
+            for q, v in enumerate(views):
+                v[sl] = rb[q]
+        self.nexchanges += 1
+        return 0
+
     def exchange(self, ids):
         G, p = self.G, self.pool
+        if max(ids) >= p.shape[0]:
+            return self._exchange_tail(list(ids))
         nzt = p.shape[1]
         nlo, nhi = self.ctx.halo_layers()          # ghost planes to fill below / above the slab (<= G)
         idx = torch.as_tensor(ids, device=p.device, dtype=torch.long)

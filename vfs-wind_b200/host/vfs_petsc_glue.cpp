@@ -349,6 +349,16 @@ PetscErrorCode Calc_U_lagr(UserCtx *user, IBMNodes *ibm, FSInfo *fsi, int Number
   return 0;
 }
 
+// body-fitted cylinder runs (bctype[0] == 11 with a wall at i = mx-2): the wall areas and pressure / viscous force sums
+// Formfunction_2 leaves in the context for main.c:1269-1277 (momentum.c:570-579, 822-849)
+static void cylinder_diag(UserCtx *user, GlueState *s) {
+  if (user->bctype[0] != 11 || user->bctype[1] != 1) return;
+  push(user, s, user->lP, 1, VFS_P);
+  double o[7];
+  ck(s, vfs_cylinder_forces(s->ctx, o), "vfs_cylinder_forces");
+  user->lA_cyl = o[0]; user->lA_cyl_x = o[1]; user->lA_cyl_z = o[2]; user->lFpx_cyl = o[3]; user->lFpz_cyl = o[4]; user->lFvx_cyl = o[5]; user->lFvz_cyl = o[6];
+}
+
 PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
   GlueState *s = state(user);
   push_constants(user, s);
@@ -358,6 +368,7 @@ PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
   ck(s, vfs_formfunction2(s->ctx, VFS_RHS, scale), "vfs_formfunction2");
   pull(user, s, VFS_RHS, 3, Rhs, false);
   if (viscosity_wallmodel && les) pull(user, s, VFS_USTAR, 1, user->lUstar, false);      // momentum.c:1150
+  cylinder_diag(user, s);
   return 0;
 }
 
@@ -405,6 +416,7 @@ extern "C" void vfs_glue_sync_state(UserCtx *user) {
     pull(user, s, VFS_NVERT, 1, user->lNvert, true);
     DALocalToGlobal(user->da, user->lNvert, INSERT_VALUES, user->Nvert);
   }
+  cylinder_diag(user, s);
 }
 
 PetscErrorCode FormFunction_SNES(SNES snes, Vec Ucont, Vec Rhs, void *ptr) {
