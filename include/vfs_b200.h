@@ -12,6 +12,8 @@
  *   vfs_les_nut             <- Compute_eddy_viscosity_LES(UserCtx*)          les.c:1143
  *   vfs_halo_exchange       <- DAGlobalToLocal / DALocalToLocal (k direction, between ranks)
  *   vfs_pressure_gradient   <- Pressure_Gradient(UserCtx*, Vec dP)           momentum.c:203
+ *   vfs_update_pressure     <- UpdatePressure(UserCtx*)                      poisson.c:3137
+ *   vfs_projection          <- Projection(UserCtx*)                          poisson.c:2700
  *   vfs_calc_f_eul / vfs_calc_u_lagr <- Calc_F_eul / Calc_U_lagr            rotor_model.c:3668,2937
  *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4299
  *
@@ -56,6 +58,7 @@ enum vfs_field {
   VFS_CONV,         /* Conv (dof 3) output of vfs_convection (download only)           */
   VFS_VISC,         /* Visc (dof 3) output of vfs_viscous (download only)              */
   VFS_P,            /* P / lP (dof 1) pressure, input of vfs_pressure_gradient         */
+  VFS_PHI,          /* Phi / lPhi (dof 1) pressure correction from the Poisson solver, input of vfs_update_pressure / vfs_projection */
   VFS_NFIELDS_PUBLIC
 };
 
@@ -155,6 +158,16 @@ int vfs_download_wait(vfs_ctx *c);
  * reference adds to dP/dzeta per unit dz in k-periodic runs (:399-411): mean_pressure_gradient when dpdz_set, else
  * (mean_k_flux - inlet_flux) / dt / mean_k_area unless inletprofile == 17; pass 0 otherwise. */
 int vfs_pressure_gradient(vfs_ctx *c, double k_forcing);
+/* UpdatePressure(UserCtx*) Source/poisson.c:3137-3296 and Projection(UserCtx*) Source/poisson.c:2700-3052, called back to
+ * back after the Poisson solve (solvers.c:662-663).  VFS_PHI = the solver's pressure correction (owned
+ * values; ghosts are refreshed here).  vfs_update_pressure: P += Phi at fluid cells, 0 at solid cells, periodic boundary
+ * nodes of P and Phi <- their images, ghosts of both refreshed.  vfs_projection: VFS_UCONT -= dt * st * (contravariant
+ * gradient of Phi) on every unmasked face (nvert sum < poisson_threshold; one-sided / zero tangential differences next to
+ * masked cells and non-periodic ends) and the component-wise periodic copies.  The reference's Projection ends with
+ * Contra2Cart (:3049): call vfs_contra2cart next.  `st` = user->st; time_coeff() = 1 and the density factors are 1 on
+ * this path (no levelset / RANS). */
+int vfs_update_pressure(vfs_ctx *c);
+int vfs_projection(vfs_ctx *c, double st, double poisson_threshold);
 /* The body-fitted-cylinder diagnostics Formfunction_2 accumulates when bctype[0] == 11 and bctype[1] == 1
  * (Source/momentum.c:570-579, 822-849): out7 = this rank's lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl,
  * lFvz_cyl over the wall faces i = mx-2, from the current VFS_UCAT (as the last residual evaluation left it) and VFS_P.

@@ -15,15 +15,17 @@ extern "C" int shim_vec_is_local(Vec);
 extern "C" int shim_vec_dof(Vec);
 
 // poisson.c:23-31 is the only thing the hot path needs from poisson.c (which needs HYPRE).
+#ifndef VFS_REF_HAS_POISSON      /* the reference build links poisson.c itself (Projection, UpdatePressure); the glue builds do not */
 double time_coeff() { if (levelset || rans) { if (ti == tistart) return 1.; else return 1.5; } else return 1.; }
+#endif
 
 PetscErrorCode FormFunction_SNES(SNES snes, Vec Ucont, Vec Rhs, void *ptr);
 
 #define GLOBAL3(X) X(Ucont) X(Ucat) X(Ucont_o) X(Ucont_rm1) X(RHS_o) X(dP) X(F_eul) X(Cent) X(GridSpace) X(Rhs)
-#define GLOBAL1(X) X(Nvert) X(P)
+#define GLOBAL1(X) X(Nvert) X(P) X(Phi)
 #define LOCAL3(X) X(lCsi) X(lEta) X(lZet) X(lICsi) X(lIEta) X(lIZet) X(lJCsi) X(lJEta) X(lJZet) X(lKCsi) X(lKEta) X(lKZet) \
   X(lGridSpace) X(lCent) X(lUcont) X(lUcat) X(lUcat_old) X(lUcont_o) X(lUcont_rm1) X(Fp) X(Div1) X(Div2) X(Div3) X(Visc1) X(Visc2) X(Visc3) X(lF_eul)
-#define LOCAL1(X) X(lAj) X(lIAj) X(lJAj) X(lKAj) X(lP) X(lNvert) X(lNvert_o) X(lNu_t) X(lCs) X(lUstar)
+#define LOCAL1(X) X(lAj) X(lIAj) X(lJAj) X(lKAj) X(lP) X(lPhi) X(lNvert) X(lNvert_o) X(lNu_t) X(lCs) X(lUstar)
 
 extern "C" {
 
@@ -103,6 +105,9 @@ double *ref_actuator_d(IBMNodes *b, int which) {
 int *ref_actuator_i(IBMNodes *b, int which) { int *w[] = {b->i_min, b->i_max, b->j_min, b->j_max, b->k_min, b->k_max}; return w[which]; }
 int ref_Calc_F_eul(UserCtx *u, IBMNodes *b, int df) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_F_eul(u, b, f, 1, 1.0, df); free(f); return r; }
 int ref_Calc_U_lagr(UserCtx *u, IBMNodes *b) { FSInfo *f = (FSInfo *)calloc(1, sizeof(FSInfo)); int r = Calc_U_lagr(u, b, f, 1); free(f); return r; }
+// pressure update and projection step after the Poisson solve (poisson.c:3137, 2700; solvers.c:662-663)
+int ref_UpdatePressure(UserCtx *u) { return UpdatePressure(u); }
+int ref_Projection(UserCtx *u, double st) { u->st = st; return Projection(u); }
 // body-fitted-cylinder diagnostics Formfunction_2 leaves in the context (momentum.c:570-579, 822-849)
 void ref_cylinder_forces(UserCtx *u, double *out7) {
   out7[0] = u->lA_cyl; out7[1] = u->lA_cyl_x; out7[2] = u->lA_cyl_z; out7[3] = u->lFpx_cyl; out7[4] = u->lFpz_cyl; out7[5] = u->lFvx_cyl; out7[6] = u->lFvz_cyl;

@@ -59,6 +59,8 @@ def lib():
         L.ref_actuator_i.argtypes = [C.c_void_p, C.c_int]
         L.ref_Calc_F_eul.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_Calc_U_lagr.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_UpdatePressure.argtypes = [C.c_void_p]
+        L.ref_Projection.argtypes = [C.c_void_p, C.c_double]
         if hasattr(L, "ref_cylinder_forces"):
             L.ref_cylinder_forces.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_Convection.argtypes = [C.c_void_p, C.c_void_p]
@@ -89,7 +91,7 @@ FLAG_DEFAULTS = dict(
     i_homo_filter=0, j_homo_filter=0, k_homo_filter=0, testfilter_ik=0, max_cs=0.5, wallfunction=0,
     viscosity_wallmodel=0, freesurface_wallmodel=0, movefsi=0, rotatefsi=0, rotor_model=0, nacelle_model=0, IB_delta=0,
     ti=10, tistart=0, rstart_flg=0, wave_momentum_source=0, air_flow_levelset=0, surface_tension=0, lowRe=0,
-    roughness_size=0.0, dthick=1.5, forcewidthfixed=0, halfwidth_dfunc=4.0, ii_periodicWT=0, jj_periodicWT=0, kk_periodicWT=0, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0,
+    roughness_size=0.0, dthick=1.5, forcewidthfixed=0, halfwidth_dfunc=4.0, ii_periodicWT=0, jj_periodicWT=0, kk_periodicWT=0, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0, poisson_threshold=0.1,
 )
 
 
@@ -185,6 +187,12 @@ class RefCase:
 
     def Pressure_Gradient(self, name, mean_k_flux=0.0, mean_k_area=1.0):
         lib().ref_Pressure_Gradient(self.u, self.vec(name), mean_k_flux, mean_k_area)
+
+    def UpdatePressure(self):
+        lib().ref_UpdatePressure(self.u)
+
+    def Projection(self, st=1.0):
+        lib().ref_Projection(self.u, st)
 
     def cylinder_forces(self):
         """lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl, lFvz_cyl as the last Formfunction_2 left them."""

@@ -148,6 +148,34 @@ PetscErrorCode KSPSetTolerances(KSP, PetscReal, PetscReal, PetscReal, PetscInt);
 PetscErrorCode KSPGMRESSetPreAllocateVectors(KSP);
 PetscErrorCode PCSetType(PC, PCType);
 
+/* --- poisson.c: only Projection / UpdatePressure (poisson.c:2700, 3137) are driven by the harness.  The Poisson matrix
+ * assembly and the KSP / multigrid set-up in the same file never run here; the PETSc calls they make are declared as
+ * catch-all stubs that abort if ever reached. --- */
+#ifdef __cplusplus
+#include <stdlib.h>
+#define VFS_SHIM_STUB(name) template <class... A> inline PetscErrorCode name(A...) { abort(); return 0; }
+VFS_SHIM_STUB(DACreateNaturalVector) VFS_SHIM_STUB(DAGetGlobalIndices) VFS_SHIM_STUB(DAGlobalToNaturalBegin) VFS_SHIM_STUB(DAGlobalToNaturalEnd)
+VFS_SHIM_STUB(KSPAppendOptionsPrefix) VFS_SHIM_STUB(KSPBuildResidual) VFS_SHIM_STUB(KSPCreate) VFS_SHIM_STUB(KSPDestroy) VFS_SHIM_STUB(KSPGMRESSetRestart)
+VFS_SHIM_STUB(KSPMonitorSet) VFS_SHIM_STUB(KSPSetFromOptions) VFS_SHIM_STUB(KSPSetInitialGuessNonzero) VFS_SHIM_STUB(KSPSetNullSpace) VFS_SHIM_STUB(KSPSetOperators)
+VFS_SHIM_STUB(KSPSetUp) VFS_SHIM_STUB(KSPSolve) VFS_SHIM_STUB(MatAssemblyBegin) VFS_SHIM_STUB(MatAssemblyEnd) VFS_SHIM_STUB(MatCreate) VFS_SHIM_STUB(MatCreateShell)
+VFS_SHIM_STUB(MatGetVecs) VFS_SHIM_STUB(MatMPIAIJSetPreallocation) VFS_SHIM_STUB(MatMult) VFS_SHIM_STUB(MatNullSpaceCreate) VFS_SHIM_STUB(MatNullSpaceDestroy)
+VFS_SHIM_STUB(MatNullSpaceSetFunction) VFS_SHIM_STUB(MatSetFromOptions) VFS_SHIM_STUB(MatSetSizes) VFS_SHIM_STUB(MatSetType) VFS_SHIM_STUB(MatSetValues)
+VFS_SHIM_STUB(MatShellGetContext) VFS_SHIM_STUB(MatShellSetOperation) VFS_SHIM_STUB(MatZeroEntries) VFS_SHIM_STUB(PCBJacobiGetSubKSP) VFS_SHIM_STUB(PCFactorSetShiftAmount)
+VFS_SHIM_STUB(PCFactorSetShiftType) VFS_SHIM_STUB(PCHYPRESetType) VFS_SHIM_STUB(PCMGGetCoarseSolve) VFS_SHIM_STUB(PCMGGetSmoother) VFS_SHIM_STUB(PCMGSetCycleType)
+VFS_SHIM_STUB(PCMGSetInterpolation) VFS_SHIM_STUB(PCMGSetLevels) VFS_SHIM_STUB(PCMGSetResidual) VFS_SHIM_STUB(PCMGSetRestriction) VFS_SHIM_STUB(PCMGSetRhs)
+VFS_SHIM_STUB(PCMGSetType) VFS_SHIM_STUB(PCSetFromOptions) VFS_SHIM_STUB(PCSetOperators) VFS_SHIM_STUB(PCSetUp) VFS_SHIM_STUB(PetscOptionsInsertString)
+VFS_SHIM_STUB(VecCreateMPI) VFS_SHIM_STUB(VecGetArray3d) VFS_SHIM_STUB(VecGetLocalSize) VFS_SHIM_STUB(VecRestoreArray3d) VFS_SHIM_STUB(VecScatterBegin)
+VFS_SHIM_STUB(VecScatterCreateToZero) VFS_SHIM_STUB(VecScatterDestroy) VFS_SHIM_STUB(VecScatterEnd) VFS_SHIM_STUB(VecSetValue) VFS_SHIM_STUB(VecShift) VFS_SHIM_STUB(VecSum)
+inline PetscErrorCode KSPMonitorTrueResidualNorm(KSP, PetscInt, PetscReal, void *) { abort(); return 0; }
+inline PetscErrorCode PCMGDefaultResidual(Mat, Vec, Vec, Vec) { abort(); return 0; }
+#endif
+#define KSPFGMRES "fgmres"
+#define MATMPIAIJ "mpiaij"
+#define PCBJACOBI "bjacobi"
+#define PCHYPRE "hypre"
+#define PCMG "mg"
+enum { MATOP_MULT = 3, MATOP_MULT_ADD = 4, MAT_FINAL_ASSEMBLY = 0, MAT_SHIFT_NONZERO = 1, PC_MG_CYCLE_V = 1, PC_MG_MULTIPLICATIVE = 0, PETSC_DETERMINE = -1, SCATTER_FORWARD = 0 };
+
 /* HYPRE handles referenced by prototypes in variables.h */
 typedef struct hypre_s1 *HYPRE_IJMatrix; typedef struct hypre_s2 *HYPRE_IJVector;
 typedef struct hypre_s3 *HYPRE_ParCSRMatrix; typedef struct hypre_s4 *HYPRE_ParVector;

@@ -201,6 +201,29 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
         ctx.Pressure_Gradient((mkf - infl) / cfg["dt"] / mka if cfg["flags"].get("kk_periodic") else 0.0)
         err["Pressure_Gradient"] = relerr(ctx.download("DP"), ref.view("dPg"))
         err["Pressure_Gradient_P"] = relerr(ctx.download("P"), ref.owned("P"))
+    ucat_before_projection = np.array(ref.owned("Ucat"))
+    # UpdatePressure + Projection (poisson.c:3137, 2700), called back to back after the Poisson solve
+    # (solvers.c:662-663): Phi stands in for the solver's pressure correction
+    if "p" in fields:
+        rng = np.random.default_rng(23)
+        phi = 0.05 * rng.uniform(-1, 1, fields["p"].shape)
+        phi = 0.25 * np.roll(phi, 1, 0) + 0.5 * phi + 0.25 * np.roll(phi, -1, 0)
+        st = 0.9
+        ref.set_owned("P", fields["p"]); ref.global_to_local("P", "lP")
+        ref.set_owned("Phi", phi); ref.global_to_local("Phi", "lPhi")
+        ref.set_owned("Ucont", fields["ucont"]); ref.global_to_local("Ucont", "lUcont")
+        ref.UpdatePressure()
+        ref.Projection(st)
+        ctx.upload("P", fields["p"]); ctx.upload("PHI", phi); ctx.upload("UCONT", fields["ucont"])
+        ctx.upload("UCAT", np.array(ucat_before_projection))
+        ctx.UpdatePressure()
+        err["UpdatePressure_P"] = relerr(ctx.download("P"), ref.owned("P"))
+        err["UpdatePressure_Phi"] = relerr(ctx.download("PHI"), ref.owned("Phi"))
+        ctx.Projection(st, refdrv.get_global("poisson_threshold"))
+        err["Projection_ucont"] = relerr(ctx.download("UCONT"), ref.owned("Ucont"))
+        ctx.Contra2Cart()                           # the reference's Projection ends with it (poisson.c:3049)
+        err["Projection_lucont"] = relerr(ctx.download("UCONT"), ref.owned("lUcont"))
+        err["Projection_ucat"] = relerr(ctx.download("UCAT"), ref.owned("Ucat"))
     # actuator forcing (rotor_model.c:3668, 2937) — after everything else: it overwrites F_eul
     act = make_actuator(cfg, xyz)
     ucat_now = np.array(ref.owned("Ucat"))
@@ -236,6 +259,12 @@ def run_path(ctx, x):
     ctx.rhs_les_fused()
     for n in ("RHS", "UCAT", "CS", "NU_T"):
         out["FUSED_" + n] = ctx.download(n)
+    # after the Poisson solve: UpdatePressure + Projection (poisson.c:3137, 2700) with stand-in pressure fields
+    ctx.upload("P", np.ascontiguousarray(x[..., 0])); ctx.upload("PHI", np.ascontiguousarray(0.01 * x[..., 1])); ctx.upload("UCONT", x)
+    ctx.UpdatePressure()
+    ctx.Projection(0.9, 0.1)
+    for n in ("P", "PHI", "UCONT"):
+        out["PROJ_" + n] = ctx.download(n)
     return out
 
 

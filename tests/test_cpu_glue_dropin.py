@@ -131,6 +131,19 @@ def run_dropin(refdrv, pkg, so_name, cfg):
     err["eager_F"] = pc.relerr(glue.view("F"), ref.view("F"))
     for nm in ("Ucont", "Ucat"):
         err["eager_side_effect_" + nm] = pc.relerr(glue.view(nm), ref.view(nm))
+    # after the Poisson solve: UpdatePressure + Projection (poisson.c:3137, 2700; solvers.c:662-663), every Vec they leave behind
+    phi = 0.05 * np.random.default_rng(23).uniform(-1, 1, fields["p"].shape)
+    for d in (ref, glue):
+        d.set_owned("P", fields["p"]); d.global_to_local("P", "lP")
+        d.set_owned("Phi", phi); d.global_to_local("Phi", "lPhi")
+        d.set_owned("Ucont", fields["ucont"]); d.global_to_local("Ucont", "lUcont")
+        d.UpdatePressure()
+        d.Projection(0.9)
+    for nm in ("P", "lP", "Phi", "lPhi", "Ucont", "Ucat", "lUcat"):
+        err["Projection_" + nm] = pc.relerr(glue.view(nm), ref.view(nm))
+    # lUcont: owned part only — Contra2Cart_2 rewrites lUcont's periodic boundary nodes in place (rhs.c:129-156) and the
+    # reference leaves the ghost images of those nodes stale, the glue refreshes them
+    err["Projection_lUcont"] = pc.relerr(glue.owned("lUcont"), ref.owned("lUcont"))
     gd.lib().vfs_glue_release(C.c_void_p(glue.u))
     return err
 

@@ -78,7 +78,7 @@ def test_two_ranks_bitwise_equal_single_rank(pkg, refdrv, tmp_path, cfgname, dim
     parts = [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)]
     print("exchanges per rank:", [int(pp["nex"]) for pp in parts])
     assert int(parts[0]["nex"]) > 5
-    for n in ("F", "UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ", "FUSED_RHS", "FUSED_UCAT", "FUSED_CS", "FUSED_NU_T"):
+    for n in ("F", "UCAT", "CS", "NU_T", "UCONT", "CSI", "AJ", "FUSED_RHS", "FUSED_UCAT", "FUSED_CS", "FUSED_NU_T", "PROJ_P", "PROJ_PHI", "PROJ_UCONT"):
         multi = np.concatenate([pp[n] for pp in parts], axis=0)
         assert np.array_equal(multi, single[n]), n
 

@@ -14,16 +14,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvfs_b200.so")
 
 FIELDS = ["COOR", "CSI", "ETA", "ZET", "AJ", "NVERT", "UCONT", "UCAT", "UCAT_OLD", "UCONT_O", "UCONT_RM1", "RHS_O", "DP", "F_EUL",
-          "RHS", "CS", "NU_T", "USTAR", "CONV", "VISC", "P"]
+          "RHS", "CS", "NU_T", "USTAR", "CONV", "VISC", "P", "PHI"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 FIELD_DOF = {"COOR": 3, "CSI": 3, "ETA": 3, "ZET": 3, "AJ": 1, "NVERT": 1, "UCONT": 3, "UCAT": 3, "UCAT_OLD": 3, "UCONT_O": 3,
-             "UCONT_RM1": 3, "RHS_O": 3, "DP": 3, "F_EUL": 3, "RHS": 3, "CS": 1, "NU_T": 1, "USTAR": 1, "CONV": 3, "VISC": 3, "P": 1}
+             "UCONT_RM1": 3, "RHS_O": 3, "DP": 3, "F_EUL": 3, "RHS": 3, "CS": 1, "NU_T": 1, "USTAR": 1, "CONV": 3, "VISC": 3, "P": 1, "PHI": 1}
 
 EXPORTS = ["vfs_create", "vfs_destroy", "vfs_last_error", "vfs_set_params", "vfs_set_stream", "vfs_set_halo_callback", "vfs_sync",
            "vfs_nccl_unique_id", "vfs_nccl_init", "vfs_halo_count", "vfs_layout", "vfs_field_scalar_id", "vfs_scalar_ptr", "vfs_upload", "vfs_download", "vfs_halo_exchange",
            "vfs_form_metrics", "vfs_contra2cart", "vfs_ib_bc", "vfs_les_cs", "vfs_les_nut", "vfs_formfunction2", "vfs_convection", "vfs_viscous", "vfs_pressure_gradient", "vfs_download_async", "vfs_download_wait",
            "vfs_formfunction_snes", "vfs_formfunction_snes_dev", "vfs_rhs_les_fused", "vfs_launch_count", "vfs_last_ms",
-           "vfs_calc_f_eul", "vfs_calc_u_lagr", "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count", "vfs_cylinder_forces"]
+           "vfs_calc_f_eul", "vfs_calc_u_lagr", "vfs_solver_defaults", "vfs_momentum_solve", "vfs_momentum_release", "vfs_set_option", "vfs_halo_layers", "vfs_host_alloc", "vfs_host_free", "vfs_device_count", "vfs_cylinder_forces", "vfs_update_pressure", "vfs_projection"]
 
 
 class VfsParams(C.Structure):
@@ -90,6 +90,8 @@ def _bind(lib):
     lib.vfs_formfunction2.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.vfs_pressure_gradient.argtypes = [C.c_void_p, C.c_double]
     lib.vfs_cylinder_forces.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vfs_update_pressure.argtypes = [C.c_void_p]
+    lib.vfs_projection.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.vfs_formfunction_snes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vfs_launch_count.argtypes = [C.c_void_p]
     lib.vfs_launch_count.restype = C.c_long
@@ -288,6 +290,14 @@ class VfsContext:
     def Pressure_Gradient(self, k_forcing=0.0):
         """momentum.c:203 on the current field "P"; result in field "DP"."""
         self._ck(self.lib.vfs_pressure_gradient(self.h, float(k_forcing)))
+
+    def UpdatePressure(self):
+        """poisson.c:3137 on the current fields "P", "PHI", "NVERT"."""
+        self._ck(self.lib.vfs_update_pressure(self.h))
+
+    def Projection(self, st=1.0, poisson_threshold=0.1):
+        """poisson.c:2700-3025: UCONT -= dt * st * grad(PHI), periodic copies (follow with Contra2Cart, :3049)."""
+        self._ck(self.lib.vfs_projection(self.h, float(st), float(poisson_threshold)))
 
     def cylinder_forces(self):
         """momentum.c:822-849: (A_cyl, A_cyl_x, A_cyl_z, Fpx, Fpz, Fvx, Fvz) of this rank's wall faces (bctype[0] == 11)."""

@@ -62,6 +62,7 @@ enum {
   S_UCM0 = S_TAIL0, S_UCM1, S_UCM2,                                      // ucont_rm1 (BDF2 assembly only)
   S_CONV0, S_CONV1, S_CONV2, S_VISC0, S_VISC1, S_VISC2,                  // legacy Convection / Viscous results (rhs.c:751,1071)
   S_ADV1, S_ADV1b, S_ADV1c, S_ADV2, S_ADV2b, S_ADV2c, S_ADV3, S_ADV3b, S_ADV3c,   // advective half of the skew-symmetric form (Adv1-3, momentum.c:607-615)
+  S_PHI,                                                                 // pressure correction (Phi / lPhi), input of UpdatePressure / Projection (poisson.c:3137, 2700)
   S_GR0, S_GR1, S_GR2, S_GR3, S_GR4, S_GR5, S_GR6, S_GR7, S_GR8,         // clark: du_a/dx_b at the cell centres (lSx, lSy, lSz of les.c:181-300), a-major
   S_COUNT
 };

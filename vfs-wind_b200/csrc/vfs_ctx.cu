@@ -78,7 +78,8 @@ struct vfs_ctx {
   vfs_params prm;
   VfsDev d;
   double *pool = nullptr;        // scalars 0 .. S_TAIL0-1, contiguous
-  double *tail = nullptr;        // scalars S_TAIL0 .. S_COUNT-1, allocated on first use (ensure_tail)
+#define VFS_NTAIL 4
+  double *tail[VFS_NTAIL] = {nullptr, nullptr, nullptr, nullptr};        // scalars S_TAIL0 .. S_COUNT-1 in four groups, each allocated on first use (ensure_tail)
   double *stage = nullptr;       // AoS staging (device), 3 * nzl*my*mx doubles
   double *stage_x = nullptr;     // staging of vfs_formfunction_snes' X, filled on the upload stream (allocated on first use)
   double *stage_async[2] = {nullptr, nullptr};   // staging of vfs_download_async, allocated on first use (sized for the field)
@@ -251,7 +252,7 @@ static void ev_rec(vfs_ctx *c, int n) {
 // ---- public field table -----------------------------------------------------------------------
 static const struct { int s0, dof; } FIELD[VFS_NFIELDS_PUBLIC] = {
   {S_X, 3}, {S_CSI0, 3}, {S_ETA0, 3}, {S_ZET0, 3}, {S_AJ, 1}, {S_NV, 1}, {S_UC0, 3}, {S_U0, 3}, {S_UO0, 3},
-  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}, {S_CONV0, 3}, {S_VISC0, 3}, {S_P, 1}};
+  {S_UCO0, 3}, {S_UCM0, 3}, {S_RO0, 3}, {S_DP0, 3}, {S_FE0, 3}, {S_R0, 3}, {S_CS, 1}, {S_NUT, 1}, {S_USTAR, 1}, {S_CONV0, 3}, {S_VISC0, 3}, {S_P, 1}, {S_PHI, 1}};
 
 static Grp grp(int s0, int n) { Grp g; g.n = n; for (int q = 0; q < n; q++) g.sid[q] = s0 + q; return g; }
 static Grp grp_cat(const Grp &a, const Grp &b) { Grp g = a; for (int q = 0; q < b.n; q++) g.sid[g.n++] = b.sid[q]; return g; }
@@ -576,12 +577,12 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->wm_table) cudaFree(c->wm_table);
-  cudaFree(c->pool); if (c->tail) cudaFree(c->tail); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
+  cudaFree(c->pool); for (int g = 0; g < VFS_NTAIL; g++) if (c->tail[g]) cudaFree(c->tail[g]); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
   graph_reset(c);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
 #else
-  free(c->pool); free(c->tail); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf); free(c->homo_buf);
+  free(c->pool); for (int g = 0; g < VFS_NTAIL; g++) free(c->tail[g]); free(c->stage); free(c->wm_table); free(c->near); free(c->d_flag); free(c->act_buf); free(c->homo_buf);
 #endif
   delete c; return 0;
 }
@@ -716,17 +717,22 @@ template <class F> static int run_graphed(vfs_ctx *c, int key, F body) {
 }
 
 // the rarely used scalars (Ucont_rm1, legacy Conv / Visc) live outside the main pool and exist only once somebody uses them
-static int ensure_tail(vfs_ctx *c) {
-  if (c->tail) return 0;
-  const size_t bytes = (size_t)c->scalar_len * (S_COUNT - S_TAIL0) * sizeof(double);
+// four groups, each allocated when its first user shows up: legacy (Ucont_rm1, Conv, Visc), Adv1-3 (skew), Phi
+// (UpdatePressure / Projection), the clark gradient planes
+static const int TAIL_LO[VFS_NTAIL + 1] = {S_TAIL0, S_ADV1, S_PHI, S_GR0, S_COUNT};
+static int tail_group(int sid) { int g = 0; while (g + 1 < VFS_NTAIL && sid >= TAIL_LO[g + 1]) g++; return g; }
+static int ensure_tail(vfs_ctx *c, int sid) {
+  const int g = tail_group(sid);
+  if (c->tail[g]) return 0;
+  const size_t bytes = (size_t)c->scalar_len * (TAIL_LO[g + 1] - TAIL_LO[g]) * sizeof(double);
 #ifndef VFS_EMU
   if (c->capturing) { set_err(c, "first use of a tail scalar during graph capture"); return VFS_ERR_CUDA; }
-  CK(cudaMalloc((void **)&c->tail, bytes));
-  CK(cudaMemsetAsync(c->tail, 0, bytes, c->stream));
+  CK(cudaMalloc((void **)&c->tail[g], bytes));
+  CK(cudaMemsetAsync(c->tail[g], 0, bytes, c->stream));
 #else
-  c->tail = (double *)calloc(bytes, 1);
+  c->tail[g] = (double *)calloc(bytes, 1);
 #endif
-  for (int s = S_TAIL0; s < S_COUNT; s++) c->d.s[s] = c->tail + (long)(s - S_TAIL0) * c->scalar_len;
+  for (int s = TAIL_LO[g]; s < TAIL_LO[g + 1]; s++) c->d.s[s] = c->tail[g] + (long)(s - TAIL_LO[g]) * c->scalar_len;
   graph_reset(c);
   return 0;
 }
@@ -753,7 +759,7 @@ static int d2h_stage(vfs_ctx *c, double *host, int dof) {
 }
 extern "C" int vfs_halo_exchange(vfs_ctx *c, int field) {
   if (!c || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
-  if (FIELD[field].s0 >= S_TAIL0) return 0;            // Ucont_rm1, Conv, Visc: ghosts never read
+  if (FIELD[field].s0 >= S_TAIL0) return 0;            // Ucont_rm1, Conv, Visc: ghosts never read; Phi's are refreshed by its users
   return g2l(c, grp(FIELD[field].s0, FIELD[field].dof));
 }
 extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
@@ -763,7 +769,7 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
   if (field == VFS_UCAT || field == VFS_AJ || field == VFS_CSI || field == VFS_ETA || field == VFS_ZET || field == VFS_NVERT) c->sabs_valid = false;
   if (field == VFS_NVERT) { c->near_valid = false; c->wall_marked = false; }
   const bool tail = FIELD[field].s0 >= S_TAIL0;
-  if (tail) RUN(ensure_tail(c));
+  if (tail) RUN(ensure_tail(c, FIELD[field].s0));
   RUN(h2d_stage(c, host, FIELD[field].dof));
   UnpackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
@@ -794,7 +800,7 @@ extern "C" int vfs_upload(vfs_ctx *c, int field, const double *host) {
 }
 extern "C" int vfs_download(vfs_ctx *c, int field, double *host) {
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC) return VFS_ERR_ARG;
-  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c));
+  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c, FIELD[field].s0));
   PackAoS f = {c->d, c->stage, FIELD[field].s0, FIELD[field].dof};
   RUN(launch(c, box_owned(c), f));
   return d2h_stage(c, host, FIELD[field].dof);
@@ -804,7 +810,7 @@ extern "C" int vfs_download_async(vfs_ctx *c, int field, double *host, int slot)
   if (!c || !host || field < 0 || field >= VFS_NFIELDS_PUBLIC || slot < 0 || slot > 1) return VFS_ERR_ARG;
 #ifndef VFS_EMU
   const size_t n = (size_t)c->d.nzl * c->d.my * c->d.mx * FIELD[field].dof * sizeof(double);
-  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c));
+  if (FIELD[field].s0 >= S_TAIL0) RUN(ensure_tail(c, FIELD[field].s0));
   if (!c->copy_stream) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
@@ -1082,7 +1088,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   Box R;
   // weno / skew / clark / inviscid: the one-thread-per-face kernels with the variants compiled in (face_flux_core<.., X>)
   const bool ex = d.weno || d.skew || d.clark || d.inviscid;
-  if (ex && d.skew) RUN(ensure_tail(c));
+  if (ex && d.skew) RUN(ensure_tail(c, S_ADV1));
   bool march = !ex && c->fused == 2 && RhsMarch::region(d, R);     // experimental fully fused residual (option 0 = 2)
 #ifndef VFS_EMU
   march = march && c->tma_ok;
@@ -1275,6 +1281,39 @@ extern "C" int vfs_pressure_gradient(vfs_ctx *c, double k_forcing) {
   return vfs_sync(c);
 }
 
+// ---- UpdatePressure / Projection (poisson.c:3137-3296, 2700-3040; called back to back, solvers.c:662-663) -----------
+// VFS_PHI holds the Poisson solver's pressure correction (owned values; its ghosts are refreshed here, as the solver's
+// own DAGlobalToLocal does, poisson.c:2661).
+extern "C" int vfs_update_pressure(vfs_ctx *c) {
+  if (!c) return VFS_ERR_ARG;
+  RUN(ensure_tail(c, S_PHI));
+  const Grp gp = grp(S_P, 1), gf = grp(S_PHI, 1), gpf = grp_cat(gp, gf);
+  RUN(g2l(c, gf, 2, 2));
+  { UpdateP f = {c->d}; RUN(launch(c, box_interior(c), f)); }       // :3183-3193
+  RUN(g2l(c, gp, 2, 2));                                              // :3242-3243
+  if (any_per(c)) RUN(node_copy(c, gpf));                             // :3249-3279: boundary nodes of P and Phi <- their periodic images
+  RUN(g2l(c, gpf, 2, 2));                                             // :3288-3293
+  return vfs_sync(c);
+}
+// Ucont -= dt * st * grad(Phi) on the faces and the component-wise periodic copies; the reference's Projection ends with
+// Contra2Cart (poisson.c:3049): call vfs_contra2cart next (kept separate because Contra2Cart rewrites lUcont's periodic
+// boundary nodes, rhs.c:129-156, which the reference's global Ucont does not see)
+extern "C" int vfs_projection(vfs_ctx *c, double st, double poisson_threshold) {
+  if (!c) return VFS_ERR_ARG;
+  const VfsDev &d = c->d;
+  RUN(ensure_tail(c, S_PHI));
+  RUN(ensure_iaj(c));
+  RUN(g2l(c, grp(S_PHI, 1), 2, 2));
+  { ProjectionCorr f = {d, st, poisson_threshold}; RUN(launch(c, box_interior(c), f)); }
+  const Grp gu = grp(S_UC0, 3);
+  RUN(g2l(c, gu));                                                    // :2981-2982
+  if (any_per(c)) {                                                   // :2984-3025
+    { PeriodicCompCopy f = {d}; RUN(launch_shell(c, 0, d.nzl, f, false, SHELL_PERIODIC_ONLY)); }
+    RUN(g2l(c, gu));
+  }
+  return vfs_sync(c);
+}
+
 // ---- cylinder force diagnostics of Formfunction_2 (momentum.c:570-579, 822-849) ------------------------------------
 // out[7] = this rank's lA_cyl, lA_cyl_x, lA_cyl_z, lFpx_cyl, lFpz_cyl, lFvx_cyl, lFvz_cyl from the current UCAT (as the last
 // residual evaluation left it) and P; zeros unless bctype[0] == 11 and bctype[1] == 1.  The reference sums them
@@ -1400,7 +1439,7 @@ extern "C" int vfs_calc_u_lagr(vfs_ctx *c, int nobj, const vfs_actuator *objs) {
 // nu_t / metric ghost planes, so no exchange is needed (the reference's DALocalToLocal of Fp1-3,
 // rhs.c:1471-1478, only refreshes ghosts nobody reads).
 template <bool VISC> static int legacy_term(vfs_ctx *c) {
-  RUN(ensure_tail(c));
+  RUN(ensure_tail(c, S_CONV0));
   const VfsDev &d = c->d;
   RUN(ensure_iaj(c));
   const Box bi = box_interior(c);
@@ -1559,7 +1598,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   if (d.les == 1) { FillScalar f = {d, S_CS, 0.01}; return launch(c, all, f); }                                  // les.c:82-85
   RUN(ensure_iaj(c));
   RUN(ensure_near(c));
-  if (d.clark) RUN(ensure_tail(c));
+  if (d.clark) RUN(ensure_tail(c, S_GR0));
   ev_rec(c, 2 * VFS_T_LES1);
   // Between ranks the 13 pass-1 fields are NOT exchanged: pass 1 is replayed on the ghost planes pass 2 reads — plane -1
   // / nzl across an interior slab boundary, and across the periodic seam plane -2 / nzl+1 (the images of global

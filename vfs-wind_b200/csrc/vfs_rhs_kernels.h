@@ -401,6 +401,83 @@ struct PressureGradient {
   }
 };
 
+// ---- UpdatePressure / Projection (Source/poisson.c:3137-3296, 2700-3040) -------------------------
+// P += Phi at fluid cells, 0 at solid cells (:3191-3193)
+struct UpdateP {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const long p = d.idx(i, j, k);
+    const double nv = d.s[S_NV][p];
+    if (nv < 0.1) d.s[S_P][p] += d.s[S_PHI][p];
+    if (nv > 1.1) d.s[S_P][p] = 0;
+  }
+};
+// Ucont -= dt * st * (contravariant gradient of Phi) on the three faces of cell (i,j,k) (poisson.c:2790-2960).  Same face
+// geometry as PressureGradient; the tangential differences fall back to one-sided pairs next to a non-periodic domain
+// end or a masked pair of cells (nvert sum > poisson_threshold) and to zero when both sides are blocked.
+struct ProjectionCorr {
+  VfsDev d; double st, thr;           // `* dt * st / coeff / r`: time_coeff() and the density factors are 1 on this path
+  VFS_HD double tdiff(long p, long n, long t, int c, int m, int per) const {
+    const double *F = d.s[S_PHI], *nv = d.s[S_NV];
+    if ((c == m - 2 && !per) || nv[p + t] + nv[p + t + n] > thr) {
+      if (nv[p - t] + nv[p - t + n] < thr && c != 1) return (F[p] + F[p + n] - F[p - t] - F[p - t + n]) * 0.5;
+      return 0.;
+    }
+    if ((c == 1 && !per) || nv[p - t] + nv[p - t + n] > thr) {
+      if (nv[p + t] + nv[p + t + n] < thr) return (F[p + t] + F[p + t + n] - F[p] - F[p + n]) * 0.5;
+      return 0.;
+    }
+    return (F[p + t] + F[p + t + n] - F[p - t] - F[p - t + n]) * 0.25;
+  }
+  VFS_HD double ndiff(long p, long n, int c, int m, int per) const {
+    const double *F = d.s[S_PHI];
+    return (c == m - 2 && per) ? F[p + 3 * n] - F[p] : F[p + n] - F[p];
+  }
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int kg = k + d.kofs;
+    const long p = d.idx(i, j, k), si = 1, sj = d.sj, sk = d.sk;
+    const double *nv = d.s[S_NV];
+    PressureGradient G = {d, 0.};
+    V3 cs, et, ze; double aj;
+    if (i < d.mx - 2 || d.perx) {
+      const double dc = ndiff(p, si, i, d.mx, d.perx), de = tdiff(p, si, sj, j, d.my, d.pery), dz = tdiff(p, si, sk, kg, d.mz, d.perz);
+      if (nv[p] + nv[p + si] < thr) {
+        G.face<0>(p, cs, et, ze, aj);
+        d.s[S_UC0][p] -= (dc * dot3(cs, cs) * aj + de * dot3(et, cs) * aj + dz * dot3(ze, cs) * aj) * d.dt * st;
+      }
+    }
+    if (j < d.my - 2 || d.pery) {
+      const double dc = tdiff(p, sj, si, i, d.mx, d.perx), de = ndiff(p, sj, j, d.my, d.pery), dz = tdiff(p, sj, sk, kg, d.mz, d.perz);
+      if (nv[p] + nv[p + sj] < thr || (int)(nv[p] + nv[p + sj]) == 5) {
+        G.face<1>(p, cs, et, ze, aj);
+        d.s[S_UC1][p] -= (dc * dot3(cs, et) * aj + de * dot3(et, et) * aj + dz * dot3(ze, et) * aj) * d.dt * st;
+      }
+    }
+    if (kg < d.mz - 2 || d.perz) {
+      const double dc = tdiff(p, sk, si, i, d.mx, d.perx), de = tdiff(p, sk, sj, j, d.my, d.pery), dz = ndiff(p, sk, kg, d.mz, d.perz);
+      if (nv[p] + nv[p + sk] < thr) {
+        G.face<2>(p, cs, et, ze, aj);
+        d.s[S_UC2][p] -= (dc * dot3(cs, ze) * aj + de * dot3(et, ze) * aj + dz * dot3(ze, ze) * aj) * d.dt * st;
+      }
+    }
+  }
+};
+// the component-wise periodic copies that follow (poisson.c:2997-3025; the same rule as IB_BC's, momentum.c:2210-2221)
+struct PeriodicCompCopy {
+  VfsDev d;
+  VFS_HD void operator()(int i, int j, int k) const {
+    const int mx = d.mx, my = d.my, mz = d.mz, kg = k + d.kofs;
+    const long p = d.idx(i, j, k);
+    long q = p; bool fi = false, fj = false, fk = false;
+    if (d.perx && i == 0) q += -2, fi = true; else if (d.perx && i == mx - 1) q += 2, fi = true;
+    if (d.pery && j == 0) q += -2 * d.sj, fj = true; else if (d.pery && j == my - 1) q += 2 * d.sj, fj = true;
+    if (d.perz && kg == 0) q += -2 * d.sk, fk = true; else if (d.perz && kg == mz - 1) q += 2 * d.sk, fk = true;
+    if (fi) d.s[S_UC0][p] = d.s[S_UC0][q];
+    if (fj) d.s[S_UC1][p] = d.s[S_UC1][q];
+    if (fk) d.s[S_UC2][p] = d.s[S_UC2][q];
+  }
+};
+
 // ---- body-fitted cylinder diagnostics of Formfunction_2 (momentum.c:570-579, 822-849; bctype[0] == 11, bctype[1] == 1) ----
 // Per i-face of the wall plane i = mx-2: face area A = |icsi|, |icsi.x|, |icsi.z| and the pressure / viscous force
 // components along x and z with the inward unit normal (the first column of the inverse metric matrix, normalised,

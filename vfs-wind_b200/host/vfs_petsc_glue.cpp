@@ -316,6 +316,37 @@ void Pressure_Gradient(UserCtx *user, Vec dP) {
   } else { DAGlobalToLocalBegin(user->da, user->P, INSERT_VALUES, user->lP); DAGlobalToLocalEnd(user->da, user->P, INSERT_VALUES, user->lP); }
 }
 
+// poisson.c:3137-3296: P += Phi, periodic boundary nodes of P / Phi, ghosts of lP / lPhi
+PetscErrorCode UpdatePressure(UserCtx *user) {
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, user->P, 1, VFS_P); push(user, s, user->Phi, 1, VFS_PHI);
+  ck(s, vfs_update_pressure(s->ctx), "vfs_update_pressure");
+  pull(user, s, VFS_P, 1, user->P, false); pull(user, s, VFS_PHI, 1, user->Phi, false);
+  DAGlobalToLocalBegin(user->da, user->P, INSERT_VALUES, user->lP); DAGlobalToLocalEnd(user->da, user->P, INSERT_VALUES, user->lP);
+  DAGlobalToLocalBegin(user->da, user->Phi, INSERT_VALUES, user->lPhi); DAGlobalToLocalEnd(user->da, user->Phi, INSERT_VALUES, user->lPhi);
+  DAGlobalToLocalBegin(user->fda, user->Ucont, INSERT_VALUES, user->lUcont); DAGlobalToLocalEnd(user->fda, user->Ucont, INSERT_VALUES, user->lUcont);   // :3167-3168
+  return 0;
+}
+// poisson.c:2700-3052: Ucont -= dt st grad(Phi), periodic copies, Contra2Cart (Ucat / lUcat of the corrected field)
+PetscErrorCode Projection(UserCtx *user) {
+  extern PetscReal poisson_threshold;
+  GlueState *s = state(user);
+  push_constants(user, s);
+  push(user, s, user->lPhi, 1, VFS_PHI);
+  push(user, s, user->Ucont, 3, VFS_UCONT);
+  push(user, s, user->Ucat, 3, VFS_UCAT);      // Contra2Cart updates Ucat in place (see Contra2Cart_2 above)
+  ck(s, vfs_projection(s->ctx, user->st, poisson_threshold), "vfs_projection");
+  pull(user, s, VFS_UCONT, 3, user->Ucont, false);
+  DAGlobalToLocalBegin(user->fda, user->Ucont, INSERT_VALUES, user->lUcont); DAGlobalToLocalEnd(user->fda, user->Ucont, INSERT_VALUES, user->lUcont);
+  ck(s, vfs_contra2cart(s->ctx), "vfs_contra2cart");                    // :3049, on the fields already on the device
+  if (ii_periodic || jj_periodic || kk_periodic) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156
+  pull(user, s, VFS_UCAT, 3, user->Ucat, false);
+  DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
+  for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }
+  return 0;
+}
+
 // rotor_model.c:3668-3960 / 2937-3150: the IBMNodes arrays go down as they are, F_eul accumulates onto the host's lF_eul
 static std::vector<vfs_actuator> actuators(IBMNodes *ibm, int n) {
   std::vector<vfs_actuator> a(n);

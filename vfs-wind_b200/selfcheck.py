@@ -24,6 +24,12 @@ def run_path(ctx, x):
     ctx.rhs_les_fused()
     for n in ("RHS", "UCAT", "CS", "NU_T"):
         out["FUSED_" + n] = ctx.download(n)
+    # after the Poisson solve: UpdatePressure + Projection (poisson.c:3137, 2700) with stand-in pressure fields
+    ctx.upload("P", np.ascontiguousarray(x[..., 0])); ctx.upload("PHI", np.ascontiguousarray(0.01 * x[..., 1])); ctx.upload("UCONT", x)
+    ctx.UpdatePressure()
+    ctx.Projection(0.9, 0.1)
+    for n in ("P", "PHI", "UCONT"):
+        out["PROJ_" + n] = ctx.download(n)
     return out
 
 
