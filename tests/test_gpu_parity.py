@@ -109,7 +109,7 @@ def test_homogeneous_cs_averaging(pkg, refdrv, extra):
 # identity (les.c:420-428, 497-556, 656), each alone and combined with periodic seams / second order / the box filter
 VARIANT_FLAGS = [dict(inviscid=1), dict(levelset_weno=5), dict(skew=1), dict(skew=1, second_order=1), dict(clark=1), dict(clark=1, les=0),
                  dict(clark=1, testfilter_ik=1), dict(skew=1, clark=1, kk_periodic=1, ii_periodic=0), dict(skew=1, jj_periodic=1, levelset_weno=5),
-                 dict(inviscid=1, immersed=3)]
+                 dict(inviscid=1, immersed=3), dict(wallfunction=2)]      # (wallfunction = 2: nu_t zeroed next to IB nodes, les.c:1211)
 
 
 def _variant_cfg(base, extra):
