@@ -23,6 +23,7 @@ def main():
         else:                                           # in-library NCCL halo layer (default)
             ctx.nccl_init(dist, device=torch.device("cuda", lrank))
     ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo)
+    ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo, pkg.selfcheck.variant_cases(world)) and ok
     if os.environ.get("VFS_HALO") != "torch":       # homogeneous Cs averaging: ncclAllReduce of the plane sums, 1e-12
         ok = pkg.selfcheck.nrank_equals_1rank(pkg.capi, pkg.cases, rank, world, lrank, make_halo, pkg.selfcheck.homogeneous_cases(world)) and ok
         ok = pkg.selfcheck.nrank_solver_and_actuators(pkg.capi, pkg.cases, rank, world, lrank, make_halo) and ok

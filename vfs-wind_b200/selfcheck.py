@@ -37,6 +37,13 @@ def default_cases(world):
     return (("c2_box256", (61, 45, 16 * world + 7)), ("c3_turbine", (53, 37, 12 * world + 9)))
 
 
+def variant_cases(world):
+    """The flux / LES variants whose extra planes (Adv1-3 of the skew-symmetric form, the Clark gradient planes) live outside
+    the main scalar pool and travel through the same halo layer: bitwise as well."""
+    return (("c2_box256", (45, 29, 12 * world + 5), dict(skew=1, clark=1, levelset_weno=5), 0.0),
+            ("c3_turbine", (37, 25, 12 * world + 3), dict(inviscid=1), 0.0))
+
+
 def homogeneous_cases(world):
     """Channel-flow setting (LM, MM averaged over i and k, les.c:798-838) and k alone: the plane / line sums are the one
     all-reduce of the path, so N ranks equal 1 rank to rounding only — (config, dims, extra flags, tolerance)."""
