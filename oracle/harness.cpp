@@ -112,6 +112,15 @@ int ref_Projection(UserCtx *u, double st) { u->st = st; return Projection(u); }
 void ref_cylinder_forces(UserCtx *u, double *out7) {
   out7[0] = u->lA_cyl; out7[1] = u->lA_cyl_x; out7[2] = u->lA_cyl_z; out7[3] = u->lFpx_cyl; out7[4] = u->lFpz_cyl; out7[5] = u->lFvx_cyl; out7[6] = u->lFvz_cyl;
 }
+// several objects at once (a turbine array): bodies[] from ref_actuator_new, centres xyz_c[3 * nobj] -> FSInfo.x_c/y_c/z_c
+int ref_Calc_U_lagr_multi(UserCtx *u, IBMNodes **bodies, int nobj, const double *xyz_c) {
+  IBMNodes *ibm = (IBMNodes *)calloc(nobj, sizeof(IBMNodes));
+  FSInfo *f = (FSInfo *)calloc(nobj, sizeof(FSInfo));
+  for (int b = 0; b < nobj; b++) { ibm[b] = *bodies[b]; f[b].x_c = xyz_c[3 * b]; f[b].y_c = xyz_c[3 * b + 1]; f[b].z_c = xyz_c[3 * b + 2]; }
+  int r = Calc_U_lagr(u, ibm, f, nobj);
+  free(ibm); free(f);
+  return r;
+}
 int ref_Convection(UserCtx *u, Vec conv) { return Convection(u, u->lUcont, u->lUcat, conv); }
 int ref_Viscous(UserCtx *u, Vec visc) { return Viscous(u, u->lUcont, u->lUcat, visc); }
 Vec ref_vec_new(UserCtx *u, int dof, int local) { Vec v; DA d = dof == 3 ? u->fda : u->da;

@@ -92,6 +92,7 @@ FLAG_DEFAULTS = dict(
     viscosity_wallmodel=0, freesurface_wallmodel=0, movefsi=0, rotatefsi=0, rotor_model=0, nacelle_model=0, IB_delta=0,
     ti=10, tistart=0, rstart_flg=0, wave_momentum_source=0, air_flow_levelset=0, surface_tension=0, lowRe=0,
     roughness_size=0.0, dthick=1.5, forcewidthfixed=0, halfwidth_dfunc=4.0, ii_periodicWT=0, jj_periodicWT=0, kk_periodicWT=0, dpdz_set=0, mean_pressure_gradient=0.0, inletprofile=0, inlet_flux=0.0, my_rank=0, NumberOfBodies=0, block_number=1, averaging=0, poisson_threshold=0.1,
+    MoveFrame=0, u_frame=0.0, v_frame=0.0, w_frame=0.0, Nx_WT=1, Ny_WT=1, Nz_WT=1, Sx_WT=1.0, Sy_WT=1.0, Sz_WT=1.0,
 )
 
 
@@ -220,6 +221,16 @@ class RefCase:
         b, n = self._actuator(act)
         lib().ref_Calc_U_lagr(self.u, b)
         return np.stack([np.array(np.ctypeslib.as_array(lib().ref_actuator_d(b, 7 + q), shape=(n,))) for q in range(3)], -1)
+
+    def Calc_U_lagr_multi(self, acts, centres):
+        """Several objects (a turbine array) in one call; centres (nobj, 3) -> FSInfo.x_c/y_c/z_c.  Returns a list of (n, 3)."""
+        L = lib()
+        L.ref_Calc_U_lagr_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        bs = [self._actuator(a) for a in acts]
+        arr = (C.c_void_p * len(bs))(*[b for b, _ in bs])
+        cen = np.ascontiguousarray(centres, dtype=np.float64)
+        L.ref_Calc_U_lagr_multi(self.u, arr, len(bs), cen.ctypes.data_as(C.c_void_p))
+        return [np.stack([np.array(np.ctypeslib.as_array(L.ref_actuator_d(b, 7 + q), shape=(n,))) for q in range(3)], -1) for b, n in bs]
 
     def Convection(self, name):
         return lib().ref_Convection(self.u, self.vec(name))

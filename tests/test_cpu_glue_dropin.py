@@ -174,6 +174,43 @@ def test_glue_dropin_emulated(pkg, refdrv, name, dims):
     assert not bad, bad
 
 
+def run_periodic_turbines(refdrv, pkg, so_name):
+    """Calc_U_lagr on a 2 x 1 x 2 periodic turbine array in a moving frame (rotor_model.c:3062-3138): the first / last
+    objects of the periodic directions share their sums, the frame velocity is added — host bookkeeping the glue does
+    after the device interpolation."""
+    import importlib.util
+    so = os.path.join(pc.ROOT, "oracle", "_ref", so_name)
+    if not os.path.exists(so):
+        pytest.skip(so_name + " not built")
+    spec = importlib.util.spec_from_file_location("refdrv_glue3", os.path.join(pc.ROOT, "oracle", "refdrv.py"))
+    gd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gd)
+    gd.SO = so
+    gd._GLOBALS_JSON = os.path.join(pc.ROOT, "oracle", "_ref", "globals_glue_%s.json" % so_name.split("_")[1].split(".")[0])
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 25, 17, 21)
+    cfg["flags"] = dict(cfg["flags"], ii_periodicWT=1, kk_periodicWT=1, Nx_WT=2, Ny_WT=1, Nz_WT=2, Sx_WT=0.8, Sy_WT=1.0, Sz_WT=1.1,
+                        MoveFrame=1, u_frame=0.05, v_frame=-0.02, w_frame=0.3)
+    ref, xyz, fields, met = pc.ref_setup(cfg, refdrv)
+    glue, _, _, _ = pc.ref_setup(cfg, gd)
+    acts = [pc.make_actuator(cfg, xyz, seed=11 + q, n=12) for q in range(4)]
+    centres = np.array([[0.3, 0.4, 0.5], [1.1, 0.4, 0.5], [0.3, 0.4, 1.6], [1.1, 0.4, 1.6]])      # object -> array slot (i, k): (0,0) (1,0) (0,1) (1,1)
+    for d in (ref, glue):
+        d.Contra2Cart()
+    a, b = ref.Calc_U_lagr_multi(acts, centres), glue.Calc_U_lagr_multi(acts, centres)
+    err = {"U_lagr_object_%d" % q: pc.relerr(b[q], a[q]) for q in range(4)}
+    assert np.array_equal(a[1], a[0]) and np.array_equal(a[2], a[0])      # images of the first object, as the reference leaves them
+    gd.lib().vfs_glue_release(C.c_void_p(glue.u))
+    return err
+
+
+def test_glue_periodic_turbine_array_emulated(pkg, refdrv):
+    import emu_loader
+    emu_loader.build()
+    err = run_periodic_turbines(refdrv, pkg, "libvfsglue_emu.so")
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
 def run_glue_solver(refdrv, pkg, so_name, cfg):
     """vfs_glue_snes_solve — the one-line replacement of SNESSolve in Implicit_MatrixFree (implicitsolver.c:4299) —
     against the numpy restatement of the PETSc algorithms driving the REFERENCE residual; also the UserCtx Vecs it

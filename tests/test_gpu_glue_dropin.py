@@ -20,3 +20,10 @@ def test_glue_snes_solve_cuda(pkg, refdrv):
     err = run_glue_solver(refdrv, pkg, "libvfsglue_cuda.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= 1e-10)}
     assert not bad, bad
+
+
+def test_glue_periodic_turbine_array_cuda(pkg, refdrv):
+    from test_cpu_glue_dropin import run_periodic_turbines
+    err = run_periodic_turbines(refdrv, pkg, "libvfsglue_cuda.so")
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad

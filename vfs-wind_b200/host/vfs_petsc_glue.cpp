@@ -370,13 +370,50 @@ PetscErrorCode Calc_F_eul(UserCtx *user, IBMNodes *ibm, FSInfo *fsi, PetscInt Nu
   DALocalToGlobal(user->fda, user->lF_eul, INSERT_VALUES, user->F_eul);
   return 0;
 }
+// Host bookkeeping that follows the interpolation in the reference (rotor_model.c:3062-3138), on the IBMNodes arrays only:
+// in a periodic turbine array (Nx_WT x Ny_WT x Nz_WT objects, spacing Sx/Sy/Sz_WT) the first and the last object of a
+// periodic direction are images of each other — the first receives the sum of both, then the last a copy of the first —
+// and a moving frame adds its velocity.
+static void ulagr_postprocess(IBMNodes *ibm, FSInfo *fsi, int nobj) {
+  extern PetscInt MoveFrame, Nx_WT, Ny_WT, Nz_WT;
+  extern PetscReal u_frame, v_frame, w_frame, Sx_WT, Sy_WT, Sz_WT;
+  if (ii_periodicWT || jj_periodicWT || kk_periodicWT) {
+    double cmin[3] = {1.0e6, 1.0e6, 1.0e6};
+    for (int b = 0; b < nobj; b++) { cmin[0] = PetscMin(cmin[0], fsi[b].x_c); cmin[1] = PetscMin(cmin[1], fsi[b].y_c); cmin[2] = PetscMin(cmin[2], fsi[b].z_c); }
+    const int n[3] = {(int)Nx_WT, (int)Ny_WT, (int)Nz_WT};
+    std::vector<int> ind((size_t)n[0] * n[1] * n[2], 0);
+    const double fac[3] = {1.0 / Sx_WT, 1.0 / Sy_WT, 1.0 / Sz_WT};
+    for (int b = 0; b < nobj; b++) {
+      const int ii = (int)((fsi[b].x_c - cmin[0] + 1.e-9) * fac[0]), jj = (int)((fsi[b].y_c - cmin[1] + 1.e-9) * fac[1]), kk = (int)((fsi[b].z_c - cmin[2] + 1.e-9) * fac[2]);
+      PetscPrintf(PETSC_COMM_WORLD, "ibi ii jj kk %d %d %d %d \n", b, ii, jj, kk);
+      ind[((size_t)kk * n[1] + jj) * n[0] + ii] = b;
+    }
+    const int per[3] = {(int)ii_periodicWT, (int)jj_periodicWT, (int)kk_periodicWT};
+    // pass 0: first += last (directions in the order i, j, k at every grid position); pass 1: last = first
+    for (int pass = 0; pass < 2; pass++)
+      for (int k = 0; k < n[2]; k++) for (int j = 0; j < n[1]; j++) for (int i = 0; i < n[0]; i++) {
+        const int c[3] = {i, j, k};
+        for (int D = 0; D < 3; D++) {
+          if (!per[D] || c[D] != (pass == 0 ? 0 : n[D] - 1)) continue;
+          int o[3] = {i, j, k}; o[D] = pass == 0 ? n[D] - 1 : 0;
+          IBMNodes &me = ibm[ind[((size_t)k * n[1] + j) * n[0] + i]], &other = ibm[ind[((size_t)o[2] * n[1] + o[1]) * n[0] + o[0]]];
+          for (int l = 0; l < me.n_elmt; l++) {
+            if (pass == 0) { me.U_lagr_x[l] = me.U_lagr_x[l] + other.U_lagr_x[l]; me.U_lagr_y[l] = me.U_lagr_y[l] + other.U_lagr_y[l]; me.U_lagr_z[l] = me.U_lagr_z[l] + other.U_lagr_z[l]; }
+            else { me.U_lagr_x[l] = other.U_lagr_x[l]; me.U_lagr_y[l] = other.U_lagr_y[l]; me.U_lagr_z[l] = other.U_lagr_z[l]; }
+          }
+        }
+      }
+  }
+  if (MoveFrame)
+    for (int b = 0; b < nobj; b++) for (int l = 0; l < ibm[b].n_elmt; l++) { ibm[b].U_lagr_x[l] += u_frame; ibm[b].U_lagr_y[l] += v_frame; ibm[b].U_lagr_z[l] += w_frame; }
+}
 PetscErrorCode Calc_U_lagr(UserCtx *user, IBMNodes *ibm, FSInfo *fsi, int NumberOfObjects) {
-  if (ii_periodicWT || jj_periodicWT || kk_periodicWT) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: Calc_U_lagr with periodic turbine arrays (ii/jj/kk_periodicWT) is not built\n"); exit(1); }
   GlueState *s = state(user);
   push_constants(user, s);
   push(user, s, user->lUcat, 3, VFS_UCAT);
   std::vector<vfs_actuator> a = actuators(ibm, NumberOfObjects);
-  ck(s, vfs_calc_u_lagr(s->ctx, NumberOfObjects, a.data()), "vfs_calc_u_lagr");
+  ck(s, vfs_calc_u_lagr(s->ctx, NumberOfObjects, a.data()), "vfs_calc_u_lagr");      // interpolation + the sum over ranks
+  ulagr_postprocess(ibm, fsi, NumberOfObjects);
   return 0;
 }
 
