@@ -253,7 +253,9 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *  15  thread-block shape of the one-thread-per-node kernels (tuning)    16  LES pass 1 replayed on ghost planes between ranks (default 1)
  *  17  FpCell on pairs of cells with 16-byte loads (default 0: measured slower than 8-byte loads, 0.82 vs 0.70 ms)
  *  14  exchange only the ghost layers each refresh is read at (default 1; 0 = always the full ghost width G)
- *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower) */
+ *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower)
+ *  18  vfs_rhs_les_fused, single rank: the residual's Contra2Cart + IB_BC on a second stream beside LES pass 3 / nu_t
+ *      (default 0: bitwise equal, measured gain 0.3 %) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus

@@ -313,6 +313,36 @@ def test_graph_replay_equals_eager(pkg):
         assert np.array_equal(res[0][n], res[1][n]), n
 
 
+@pytest.mark.parametrize("name,dims", [("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41))])
+def test_unit_overlap_bitwise(pkg, name, dims):
+    """Option 18 (the residual's Contra2Cart + IB_BC on a second stream beside LES pass 3 / nu_t inside vfs_rhs_les_fused)
+    changes the schedule only: results bitwise equal with it off, eagerly and as graph replays."""
+    capi, cases = pkg.capi, pkg.cases
+    cfg = cases.scaled(cases.CONFIGS[name], *dims)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    xyz = cases.make_grid(cfg)
+    res = []
+    for ovl in (0, 1):
+        ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+        ctx.set_option(18, ovl)
+        ctx.upload("COOR", xyz); ctx.FormMetrics()
+        if ovl == 0:
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+        for k, n in pc.FIELDS_IN:
+            ctx.upload(n, f[k])
+        outs = []
+        for _ in range(4):          # eager, capture, replay, replay
+            ctx.upload("UCONT", f["ucont"])
+            ctx.rhs_les_fused()
+            outs.append({n: ctx.download(n) for n in ("RHS", "UCAT", "UCONT", "CS", "NU_T")})
+        res.append(outs)
+        ctx.close()
+    for it in range(4):
+        for n in res[0][it]:
+            assert np.array_equal(res[0][it][n], res[1][it][n]), (it, n)
+
+
 def test_full_size_kernel_families_agree(pkg):
     """BASELINE.json's bench size (256^3 nodes): the oracle cannot run there in seconds, so the marching /
     TMA kernels (what the bench times) are checked against the one-thread-per-cell staged kernels (the literal

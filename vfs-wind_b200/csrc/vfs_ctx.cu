@@ -113,7 +113,11 @@ struct vfs_ctx {
   cudaEvent_t ev_up = 0;
   cudaStream_t side = 0;         // halo exchanges that overlap interior compute run here (forked / joined by events)
   cudaEvent_t ev_fork = 0, ev_join = 0;
+  cudaStream_t side2 = 0;        // vfs_rhs_les_fused: the residual's Contra2Cart + IB_BC run here beside LES pass 3 / nu_t (option 18)
+  cudaEvent_t ev_fork2 = 0, ev_join2 = 0;
 #endif
+  int unit_overlap = 0;          // option 18 (measured: 6.94 -> 6.92 ms at 256^3, profiles/r02y_tune_unit_overlap.txt; off)
+  bool fork_after_les2 = false;  // les_cs records ev_fork2 right after LES pass 2 (the last reader of ucat in the LES block)
   int async_api = 0;             // compute-only entry points return without synchronising (option key 11)
   int overlap = 1;               // overlap the k-face-flux and Fp exchanges with the interior planes of FpCell / Project (option key 9)
   long halo_exchanges = 0, halo_bytes = 0;
@@ -511,6 +515,8 @@ extern "C" int vfs_create(const vfs_params *p, vfs_ctx **out) {
   cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true;
   cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
   for (int q = 0; q < 2 * VFS_T_COUNT; q++) cudaEventCreate(&c->ev[q]);
 #else
   c->pool = (double *)calloc(bytes, 1); c->stage = (double *)calloc(sbytes, 1);
@@ -576,6 +582,9 @@ extern "C" int vfs_destroy(vfs_ctx *c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side2) cudaStreamDestroy(c->side2);
+  if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
+  if (c->ev_join2) cudaEventDestroy(c->ev_join2);
   if (c->wm_table) cudaFree(c->wm_table);
   cudaFree(c->pool); for (int g = 0; g < VFS_NTAIL; g++) if (c->tail[g]) cudaFree(c->tail[g]); cudaFree(c->stage); cudaFree(c->near); if (c->d_flag) cudaFree(c->d_flag); if (c->act_buf) cudaFree(c->act_buf); if (c->homo_buf) cudaFree(c->homo_buf);
   graph_reset(c);
@@ -686,6 +695,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 15) c->box_shape = value;
   else if (key == 16) c->les_replay = value;
   else if (key == 17) c->fp_pairs = value;
+  else if (key == 18) c->unit_overlap = value;
   graph_reset(c);
   return 0;
 }
@@ -1674,6 +1684,9 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   } else
   { LesPass2 f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_LES2 + 1);
+#ifndef VFS_EMU
+  if (c->fork_after_les2) CK(cudaEventRecord(c->ev_fork2, c->stream));      // ucat is not read again in the LES block
+#endif
   Grp g2 = grp(S_LM, 2);
   RUN(g2l(c, g2, 2, 2));                                              // les.c:675-678
   if (any_per(c)) RUN(node_copy(c, g2));
@@ -1726,6 +1739,36 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
   RUN(run_graphed(c, 1, [&]() -> int {
     RUN(g2l(c, grp(S_UC0, 3)));
     RUN(contra2cart(c));
+#ifndef VFS_EMU
+    // Single rank, dynamic model: after LES pass 2 nothing in the LES block reads ucat or ucont any more (pass 3 filters
+    // LM / MM, nu_t uses the |S| pass 1 stored), so the residual's wall-normal zeroing + Contra2Cart + IB_BC — which
+    // overwrite them — run on a second stream beside pass 3 / nu_t and their ghost refreshes (two branches of the graph),
+    // joined before the face fluxes, the first reader of nu_t.  Not between ranks (two NCCL exchanges would be in flight on
+    // one communicator), and not when IB_BC's first-step wall marking would rewrite nvert under pass 3.
+    const VfsDev &d = c->d;
+    bool wallfn_any = false;
+    for (int q = 0; q < 6; q++) wallfn_any = wallfn_any || d.bc[q] == -1 || d.bc[q] == -2;
+    const bool dynamic = d.les == 2 && !(d.ti < 2 && d.tistart == 0 && !d.rstart_flg);
+    if (c->unit_overlap && c->prm.nranks == 1 && dynamic && !wallfn_any && c->side2) {
+      c->fork_after_les2 = true;
+      int r = les_cs(c, true);
+      c->fork_after_les2 = false;
+      if (r) return r;
+      RUN(les_nut(c, true));
+      CK(cudaStreamWaitEvent(c->side2, c->ev_fork2, 0));
+      cudaStream_t main_stream = c->stream;
+      c->stream = c->side2;
+      r = zero_normal(c, true);
+      if (!r) r = g2l(c, grp(S_UC0, 3));
+      if (!r) r = contra2cart(c);
+      if (!r) r = ib_bc(c);
+      c->stream = main_stream;
+      if (r) return r;
+      CK(cudaEventRecord(c->ev_join2, c->side2));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
+      return formfunction2(c, 1, S_R0, 0.5);
+    }
+#endif
     if (c->d.les) { RUN(les_cs(c, true)); RUN(les_nut(c, true)); }     // Cs and nu_t ghosts refreshed together
     RUN(zero_normal(c, true));
     return snes_core(c, true);
