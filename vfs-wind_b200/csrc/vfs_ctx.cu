@@ -116,6 +116,7 @@ struct vfs_ctx {
   cudaStream_t side2 = 0;        // vfs_rhs_les_fused: the residual's Contra2Cart + IB_BC run here beside LES pass 3 / nu_t (option 18)
   cudaEvent_t ev_fork2 = 0, ev_join2 = 0;
 #endif
+  int les3_minb = 3;             // option 19: resident blocks per SM the LES pass-3 kernel is compiled for (3: 40 registers, 48 warps/SM; 2: 48 registers) — profiles/r02zb_tune_les3_minb.txt
   int unit_overlap = 0;          // option 18 (measured: 6.94 -> 6.92 ms at 256^3, profiles/r02y_tune_unit_overlap.txt; off)
   bool fork_after_les2 = false;  // les_cs records ev_fork2 right after LES pass 2 (the last reader of ucat in the LES block)
   int async_api = 0;             // compute-only entry points return without synchronising (option key 11)
@@ -696,6 +697,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 16) c->les_replay = value;
   else if (key == 17) c->fp_pairs = value;
   else if (key == 18) c->unit_overlap = value;
+  else if (key == 19) c->les3_minb = value;
   graph_reset(c);
   return 0;
 }
@@ -1704,7 +1706,8 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
     }
     side_end(c, &sc);
     Les3March prog = {d};
-    if (run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
+    if (c->les3_minb != 2 ? run_filter_march<Les3March, 3>(c->stream, prog, bi.k0, bi.k1, &c->launches)
+                          : run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
     RUN(ovl_join(c));
   } else
   { LesPass3 f = {d}; RUN(launch(c, box_interior(c), f)); }
