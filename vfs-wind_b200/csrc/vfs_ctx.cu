@@ -65,6 +65,14 @@ template <class F> __global__ void __launch_bounds__(256) k_box(F f, Box b) {
   int k = b.k0 + blockIdx.z * blockDim.z + threadIdx.z;
   if (i < b.i1 && j < b.j1 && k < b.k1) f(i, j, k);
 }
+// the same kernel compiled for MINB resident 256-thread blocks per SM (a register cap of 65536 / (256 MINB)): the
+// bandwidth-bound functors gain from more loads in flight as long as the cap costs no more than a few spilled words
+template <class F, int MINB> __global__ void __launch_bounds__(256, MINB) k_box_occ(F f, Box b) {
+  int i = b.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = b.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  int k = b.k0 + blockIdx.z * blockDim.z + threadIdx.z;
+  if (i < b.i1 && j < b.j1 && k < b.k1) f(i, j, k);
+}
 #else
 #define CK(call) do { } while (0)
 typedef void *cudaStream_t;
@@ -116,6 +124,7 @@ struct vfs_ctx {
   cudaStream_t side2 = 0;        // vfs_rhs_les_fused: the residual's Contra2Cart + IB_BC run here beside LES pass 3 / nu_t (option 18)
   cudaEvent_t ev_fork2 = 0, ev_join2 = 0;
 #endif
+  int box_occ = 6;               // option 20: the projection kernel compiled for 6 (default) or 8 resident blocks per SM, 0 = the plain k_box (profiles/r02zc_tune_box_occ.txt)
   int les3_minb = 3;             // option 19: resident blocks per SM the LES pass-3 kernel is compiled for (3: 40 registers, 48 warps/SM; 2: 48 registers) — profiles/r02zb_tune_les3_minb.txt
   int unit_overlap = 0;          // option 18 (measured: 6.94 -> 6.92 ms at 256^3, profiles/r02y_tune_unit_overlap.txt; off)
   bool fork_after_les2 = false;  // les_cs records ev_fork2 right after LES pass 2 (the last reader of ucat in the LES block)
@@ -179,6 +188,25 @@ template <class F> static int launch(vfs_ctx *c, const Box &b, const F &f) {
   for (int k = b.k0; k < b.k1; k++) for (int j = b.j0; j < b.j1; j++) for (int i = b.i0; i < b.i1; i++) f(i, j, k);
 #endif
   return 0;
+}
+// launch() with the occupancy the kernel is compiled for picked by option 20 (0 = the plain k_box).  Measured at 256^3
+// (profiles/r02zc_tune_box_occ.txt): the projection gains from 6 blocks per SM (0.735 -> 0.673 ms: 44 -> 40 registers, 16
+// bytes of spills), FpCell loses (0.696 -> 0.749 ms), Contra2Cart's interior is at 40 registers anyway; 8 blocks per SM
+// (32 registers) loses everywhere.  Used for the projection only.
+template <class F> static int launch_occ(vfs_ctx *c, const Box &b, const F &f) {
+#ifndef VFS_EMU
+  if (c->box_occ && b.i1 - b.i0 > 8 && b.j1 - b.j0 > 1 && b.k1 - b.k0 > 1) {
+    c->launches++;
+    dim3 blk(128, 2, 1);
+    dim3 grd((b.i1 - b.i0 + blk.x - 1) / blk.x, (b.j1 - b.j0 + blk.y - 1) / blk.y, (b.k1 - b.k0 + blk.z - 1) / blk.z);
+    if (c->box_occ >= 8) k_box_occ<F, 8><<<grd, blk, 0, c->stream>>>(f, b);
+    else k_box_occ<F, 6><<<grd, blk, 0, c->stream>>>(f, b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_err(c, std::string("kernel launch: ") + cudaGetErrorString(e)); return VFS_ERR_CUDA; }
+    return 0;
+  }
+#endif
+  return launch(c, b, f);
 }
 #define RUN(x) do { int r_ = (x); if (r_) return r_; } while (0)
 
@@ -698,6 +726,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 17) c->fp_pairs = value;
   else if (key == 18) c->unit_overlap = value;
   else if (key == 19) c->les3_minb = value;
+  else if (key == 20) c->box_occ = value;
   graph_reset(c);
   return 0;
 }
@@ -1240,7 +1269,7 @@ static int formfunction2(vfs_ctx *c, int mode, int s0, double scale) {
   const bool ovl_p = can_overlap(c) && S.n == 1 && d.nzl >= 8;
   auto project = [&](const Box &b) -> int {
     if (mode == 0) { ProjectAdd f = {d, s0, scale}; return launch(c, b, f); }
-    ProjectSNES f = {d}; return launch(c, b, f);
+    ProjectSNES f = {d}; return launch_occ(c, b, f);
   };
   if (!ovl_p) {
     RUN(g2l(c, gp, 2, 2));                                            // the projection reads Fp at k+1, the seam copies at k+-2
