@@ -256,7 +256,7 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *  12  Fp evaluated inside the projection kernel instead of FpCell + Fp planes (default 0: bitwise equal, measured slower)
  *  18  vfs_rhs_les_fused, single rank: the residual's Contra2Cart + IB_BC on a second stream beside LES pass 3 / nu_t
  *      (default 0: bitwise equal, measured gain 0.3 %)
- *  19  resident blocks per SM the LES pass-3 kernel is compiled for: 3 (default, 40 registers) or 2 (48 registers)
+ *  19  resident blocks per SM the LES pass-3 kernel is compiled for: 4 (default, 32 registers), 3 (40) or 2 (48 registers)
  *  20  resident 256-thread blocks per SM the projection kernel is compiled for: 6 (default), 8, or 0 = no cap */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 

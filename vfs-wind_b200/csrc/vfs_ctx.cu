@@ -125,7 +125,7 @@ struct vfs_ctx {
   cudaEvent_t ev_fork2 = 0, ev_join2 = 0;
 #endif
   int box_occ = 6;               // option 20: the projection kernel compiled for 6 (default) or 8 resident blocks per SM, 0 = the plain k_box (profiles/r02zc_tune_box_occ.txt)
-  int les3_minb = 3;             // option 19: resident blocks per SM the LES pass-3 kernel is compiled for (3: 40 registers, 48 warps/SM; 2: 48 registers) — profiles/r02zb_tune_les3_minb.txt
+  int les3_minb = 4;             // option 19: resident 512-thread blocks per SM the LES pass-3 kernel is compiled for (4: 32 registers, 64 warps/SM; 3: 40; 2: 48 registers) — profiles/r02zb_tune_les3_minb.txt
   int unit_overlap = 0;          // option 18 (measured: 6.94 -> 6.92 ms at 256^3, profiles/r02y_tune_unit_overlap.txt; off)
   bool fork_after_les2 = false;  // les_cs records ev_fork2 right after LES pass 2 (the last reader of ucat in the LES block)
   int async_api = 0;             // compute-only entry points return without synchronising (option key 11)
@@ -1735,7 +1735,7 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
     }
     side_end(c, &sc);
     Les3March prog = {d};
-    if (c->les3_minb != 2 ? run_filter_march<Les3March, 3>(c->stream, prog, bi.k0, bi.k1, &c->launches)
+    if (c->les3_minb == 3 ? run_filter_march<Les3March, 3>(c->stream, prog, bi.k0, bi.k1, &c->launches) : c->les3_minb != 2 ? run_filter_march<Les3March, 4>(c->stream, prog, bi.k0, bi.k1, &c->launches)
                           : run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
     RUN(ovl_join(c));
   } else
