@@ -28,9 +28,19 @@ for t in range(n):
               second_order=rng.randint(0, 1), laplacian=rng.randint(0, 1), immersed=rng.choice([0, 1, 3]),
               les=rng.choice([0, 1, 2, 2]), testfilter_ik=int(rng.random() < 0.15), roughness_size=1e-3,
               rotor_model=rng.randint(0, 1))
+    # the variants of the one-thread-per-face / per-cell kernels (momentum.c:754-923, les.c:420-656, 798-965, 1211)
+    if rng.random() < 0.25: fl["skew"] = 1
+    if rng.random() < 0.25: fl["clark"] = 1
+    r = rng.random()
+    if r < 0.12: fl["inviscid"] = 1
+    elif r < 0.3: fl["levelset_weno"] = 5
+    if rng.random() < 0.15: fl["wallfunction"] = 2
+    if fl["les"] == 2 and rng.random() < 0.2: fl.update(rng.choice([dict(i_homo_filter=1, k_homo_filter=1), dict(i_homo_filter=1), dict(j_homo_filter=1), dict(k_homo_filter=1)]))
+    if not per[0] and rng.random() < 0.15: bc[0] = 11      # body-fitted cylinder inflow half (rhs.c:626): needs z <= 0 somewhere
     if rng.random() < 0.2: fl.update(ti=5, tistart=5)
     if bc[2] in (1,) and rng.random() < 0.3: fl["viscosity_wallmodel"] = 1
     cfg = dict(base); cfg["flags"] = fl; cfg["bctype"] = bc
+    if bc[0] == 11: cfg["z_shift"] = 1.4
     try:
         err = pc.run_parity(cfg, refdrv, lib=emu)
     except Exception as e:      # unsupported combination rejected by vfs_create, etc.
