@@ -384,3 +384,35 @@ def test_full_size_kernel_families_agree(pkg):
         assert np.array_equal(ctx.download(n), outs[1][n]), n
     for c in ctxs:
         c.close()
+
+
+def test_restart_files_feed_the_device_path(pkg, tmp_path):
+    """SURVEY 8(f) row f4 end to end: a grid.dat (binary) and the restart file set of a time step are written in the
+    reference's formats, read back with petsc_io and fed to a context — the unit's results are bitwise those of the
+    context fed from memory."""
+    capi, cases, io = pkg.capi, pkg.cases, pkg.petsc_io
+    cfg = cases.scaled(cases.CONFIGS["c3_turbine"], 21, 15, 17)
+    mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
+    xyz = cases.make_grid(cfg)
+    io.write_grid_dat(str(tmp_path / "grid.dat"), [xyz], binary=True)
+    outs = []
+    for from_disk in (False, True):
+        ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
+        ctx.upload("COOR", io.read_grid_dat(str(tmp_path / "grid.dat"), binary=True)[0] if from_disk else xyz)
+        ctx.FormMetrics()
+        if not from_disk:
+            met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))
+            f = cases.make_fields(cfg, met)
+            io.write_restart(str(tmp_path), 40, dict(UCONT=f["ucont"], UCAT=f["ucat"], P=f["p"], NVERT=f["nvert"]))
+        for k, n in pc.FIELDS_IN:
+            ctx.upload(n, f[k])
+        if from_disk:      # as Ucont_Read does: Ucont_o <- Ucont, lUcat_old <- Ucat (main.c:420-428)
+            for n, a in io.read_restart(str(tmp_path), 40, mx, my, mz).items():
+                ctx.upload(n, a)
+        else:
+            ctx.upload("UCONT_O", f["ucont"]); ctx.upload("UCAT_OLD", f["ucat"]); ctx.upload("P", f["p"])
+        ctx.rhs_les_fused()
+        outs.append({n: ctx.download(n) for n in ("RHS", "UCAT", "CS", "NU_T")})
+        ctx.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n]), n
