@@ -15,6 +15,8 @@
  *   vfs_update_pressure     <- UpdatePressure(UserCtx*)                      poisson.c:3137
  *   vfs_projection          <- Projection(UserCtx*)                          poisson.c:2700
  *   vfs_calc_f_eul / vfs_calc_u_lagr <- Calc_F_eul / Calc_U_lagr            rotor_model.c:3668,2937
+ *   vfs_convection / vfs_viscous <- Convection / Viscous (legacy explicit path)   rhs.c:751,1071
+ *   vfs_cylinder_forces     <- the lA_cyl / lFp*_cyl / lFv*_cyl sums inside Formfunction_2   momentum.c:570-579,822-849
  *   vfs_momentum_solve      <- SNESSolve in Implicit_MatrixFree              implicitsolver.c:4203-4299
  *
  * Plain C, POD only, no torch / PETSc types.  All numerics are FP64.  One vfs_ctx per GPU / rank;
