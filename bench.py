@@ -275,7 +275,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     for key, env in ((0, "VFS_FUSED"), (2, "VFS_LES2_TY"), (3, "VFS_FLUX_MINB"), (4, "VFS_LES1_VAR"), (5, "VFS_LES3_VAR"), (6, "VFS_FASTPATH"), (7, "VFS_FLUX_VAR"),
-                     (8, "VFS_FUSE_REFRESH"), (9, "VFS_OVERLAP"), (12, "VFS_FP_FUSED"), (14, "VFS_HALO_TRIM"), (15, "VFS_BOX_SHAPE"), (16, "VFS_LES_REPLAY"), (17, "VFS_FP_PAIRS"), (18, "VFS_UNIT_OVERLAP"), (19, "VFS_LES3_MINB"), (20, "VFS_BOX_OCC")):            # tuning knobs (see vfs_set_option)
+                     (8, "VFS_FUSE_REFRESH"), (9, "VFS_OVERLAP"), (12, "VFS_FP_FUSED"), (14, "VFS_HALO_TRIM"), (15, "VFS_BOX_SHAPE"), (16, "VFS_LES_REPLAY"), (17, "VFS_FP_PAIRS"), (18, "VFS_UNIT_OVERLAP"), (19, "VFS_LES3_MINB"), (20, "VFS_BOX_OCC"), (21, "VFS_NUT_IN_LES3")):            # tuning knobs (see vfs_set_option)
         if os.environ.get(env):
             ctx.set_option(key, int(os.environ[env]))
     cells_total = (mx - 2) * (my - 2) * (mz - 2)

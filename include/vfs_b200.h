@@ -259,7 +259,8 @@ double vfs_last_ms(vfs_ctx *c, int which);
  *  18  vfs_rhs_les_fused, single rank: the residual's Contra2Cart + IB_BC on a second stream beside LES pass 3 / nu_t
  *      (default 0: bitwise equal, measured gain 0.3 %)
  *  19  resident blocks per SM the LES pass-3 kernel is compiled for: 4 (default, 32 registers), 3 (40) or 2 (48 registers)
- *  20  resident 256-thread blocks per SM the projection kernel is compiled for: 6 (default), 8, or 0 = no cap */
+ *  20  resident 256-thread blocks per SM the projection kernel is compiled for: 6 (default), 8, or 0 = no cap
+ *  21  vfs_rhs_les_fused: nu_t written by LES pass 3 instead of a separate pass (default 1; bitwise equal) */
 int vfs_set_option(vfs_ctx *c, int key, int value);
 
 #ifdef __cplusplus

@@ -313,10 +313,12 @@ def test_graph_replay_equals_eager(pkg):
         assert np.array_equal(res[0][n], res[1][n]), n
 
 
+@pytest.mark.parametrize("key", [18, 21])
 @pytest.mark.parametrize("name,dims", [("c2_box256", (70, 37, 45)), ("c3_turbine", (45, 30, 41))])
-def test_unit_overlap_bitwise(pkg, name, dims):
+def test_unit_overlap_bitwise(pkg, name, dims, key):
     """Option 18 (the residual's Contra2Cart + IB_BC on a second stream beside LES pass 3 / nu_t inside vfs_rhs_les_fused)
-    changes the schedule only: results bitwise equal with it off, eagerly and as graph replays."""
+    and option 21 (nu_t written by LES pass 3 inside the unit instead of a separate pass) change the schedule only:
+    results bitwise equal with the option off, eagerly and as graph replays."""
     capi, cases = pkg.capi, pkg.cases
     cfg = cases.scaled(cases.CONFIGS[name], *dims)
     mx, my, mz = cfg["IM"] + 1, cfg["JM"] + 1, cfg["KM"] + 1
@@ -324,7 +326,7 @@ def test_unit_overlap_bitwise(pkg, name, dims):
     res = []
     for ovl in (0, 1):
         ctx = capi.VfsContext(capi.make_params(mx, my, mz, cfg["flags"], cfg["ren"], cfg["dt"], cfg["bctype"]))
-        ctx.set_option(18, ovl)
+        ctx.set_option(key, ovl)
         ctx.upload("COOR", xyz); ctx.FormMetrics()
         if ovl == 0:
             met = dict(csi=ctx.download("CSI"), eta=ctx.download("ETA"), zet=ctx.download("ZET"), aj=ctx.download("AJ"))

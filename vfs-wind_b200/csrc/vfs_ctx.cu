@@ -124,6 +124,7 @@ struct vfs_ctx {
   cudaStream_t side2 = 0;        // vfs_rhs_les_fused: the residual's Contra2Cart + IB_BC run here beside LES pass 3 / nu_t (option 18)
   cudaEvent_t ev_fork2 = 0, ev_join2 = 0;
 #endif
+  int nut_in_les3 = 1;           // option 21: inside vfs_rhs_les_fused LES pass 3 also writes nu_t (no separate NuT pass over the interior)
   int box_occ = 6;               // option 20: the projection kernel compiled for 6 (default) or 8 resident blocks per SM, 0 = the plain k_box (profiles/r02zc_tune_box_occ.txt)
   int les3_minb = 4;             // option 19: resident 512-thread blocks per SM the LES pass-3 kernel is compiled for (4: 32 registers, 64 warps/SM; 3: 40; 2: 48 registers) — profiles/r02zb_tune_les3_minb.txt
   int unit_overlap = 0;          // option 18 (measured: 6.94 -> 6.92 ms at 256^3, profiles/r02y_tune_unit_overlap.txt; off)
@@ -727,6 +728,7 @@ extern "C" int vfs_set_option(vfs_ctx *c, int key, int value) {
   else if (key == 18) c->unit_overlap = value;
   else if (key == 19) c->les3_minb = value;
   else if (key == 20) c->box_occ = value;
+  else if (key == 21) c->nut_in_les3 = value;
   graph_reset(c);
   return 0;
 }
@@ -1631,7 +1633,7 @@ static int les_homo(vfs_ctx *c) {
 }
 // defer_refresh: leave the ghost refresh of Cs (les.c:1026-1057) to les_nut(c, true), which does it together
 // with nu_t's (nu_t of an interior cell reads the cell's own Cs only, les.c:1206)
-static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
+static int les_cs(vfs_ctx *c, bool defer_refresh = false, bool *nut_done = nullptr) {
   const VfsDev &d = c->d;
   Box all = {-VFS_G, d.mx + VFS_G, -VFS_G, d.my + VFS_G, -VFS_G, d.nzl + VFS_G};
   c->sabs_valid = false;
@@ -1734,7 +1736,10 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
       RUN(launch(c, b0, f)); RUN(launch(c, b1, f));
     }
     side_end(c, &sc);
-    Les3March prog = {d};
+    // vfs_rhs_les_fused (option 21): the marching kernel also writes nu_t of its cells; les_nut then only does the thin slabs
+    const bool with_nut = nut_done && c->nut_in_les3 && c->sabs_valid && c->lesgeo_valid;
+    if (nut_done) *nut_done = with_nut;
+    Les3March prog = {d, with_nut ? 1 : 0};
     if (c->les3_minb == 3 ? run_filter_march<Les3March, 3>(c->stream, prog, bi.k0, bi.k1, &c->launches) : c->les3_minb != 2 ? run_filter_march<Les3March, 4>(c->stream, prog, bi.k0, bi.k1, &c->launches)
                           : run_filter_march<Les3March, 2>(c->stream, prog, bi.k0, bi.k1, &c->launches)) { set_err(c, "les3 march kernel launch failed"); return VFS_ERR_CUDA; }
     RUN(ovl_join(c));
@@ -1749,10 +1754,22 @@ static int les_cs(vfs_ctx *c, bool defer_refresh = false) {
   if (any_per(c)) RUN(node_copy(c, g3));
   return 0;
 }
-static int les_nut(vfs_ctx *c, bool with_cs = false) {
+// interior_done: LES pass 3 of this unit already wrote nu_t of every cell its marching kernel covers (Les3March::with_nut);
+// what is left are the cells next to periodic planes, which pass 3 does on thin slabs
+static int les_nut(vfs_ctx *c, bool with_cs = false, bool interior_done = false) {
   const VfsDev &d = c->d;
   ev_rec(c, 2 * VFS_T_NUT);
-  if (c->sabs_valid) { NuT<true> f = {d}; RUN(launch(c, box_interior(c), f)); }
+  if (interior_done) {
+    const Box bi = box_interior(c);
+    NuT<true> f = {d};
+    if (d.perx) { Box b0 = bi, b1 = bi; b0.i1 = 2; b1.i0 = d.mx - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    if (d.pery) { Box b0 = bi, b1 = bi; b0.j1 = 2; b1.j0 = d.my - 2; RUN(launch(c, b0, f)); RUN(launch(c, b1, f)); }
+    if (d.perz) {
+      Box b0 = bi, b1 = bi; b0.k0 = klo(c, 1); b0.k1 = klo(c, 2); b1.k0 = klo(c, d.mz - 2); b1.k1 = klo(c, d.mz - 1);
+      RUN(launch(c, b0, f)); RUN(launch(c, b1, f));
+    }
+  }
+  else if (c->sabs_valid) { NuT<true> f = {d}; RUN(launch(c, box_interior(c), f)); }
   else { NuT<false> f = {d}; RUN(launch(c, box_interior(c), f)); }
   ev_rec(c, 2 * VFS_T_NUT + 1);
   Grp g = with_cs ? grp_cat(grp(S_CS, 1), grp(S_NUT, 1)) : grp(S_NUT, 1);
@@ -1783,10 +1800,11 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
     const bool dynamic = d.les == 2 && !(d.ti < 2 && d.tistart == 0 && !d.rstart_flg);
     if (c->unit_overlap && c->prm.nranks == 1 && dynamic && !wallfn_any && c->side2) {
       c->fork_after_les2 = true;
-      int r = les_cs(c, true);
+      bool nd = false;
+      int r = les_cs(c, true, &nd);
       c->fork_after_les2 = false;
       if (r) return r;
-      RUN(les_nut(c, true));
+      RUN(les_nut(c, true, nd));
       CK(cudaStreamWaitEvent(c->side2, c->ev_fork2, 0));
       cudaStream_t main_stream = c->stream;
       c->stream = c->side2;
@@ -1801,7 +1819,7 @@ extern "C" int vfs_rhs_les_fused(vfs_ctx *c) {
       return formfunction2(c, 1, S_R0, 0.5);
     }
 #endif
-    if (c->d.les) { RUN(les_cs(c, true)); RUN(les_nut(c, true)); }     // Cs and nu_t ghosts refreshed together
+    if (c->d.les) { bool nd = false; RUN(les_cs(c, true, &nd)); RUN(les_nut(c, true, nd)); }     // Cs and nu_t ghosts refreshed together
     RUN(zero_normal(c, true));
     return snes_core(c, true);
   }));

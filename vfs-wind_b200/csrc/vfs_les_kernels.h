@@ -618,6 +618,13 @@ VFS_HD double nut_value(const VfsDev &d, long p, double cs, double Sabs) {
   if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
   return v;
 }
+// the same with Delta^2 = filter * filter taken from LesGeo's S_LF2 (the identical product, stored): no cbrt, no aj read
+VFS_HD double nut_value_geo(const VfsDev &d, long p, double cs, double Sabs) {
+  const double *nv = d.s[S_NV];
+  double v = cs * d.s[S_LF2][p] * Sabs;
+  if (d.wallfunction == 2 && nv[p] + nv[p + 1] + nv[p - 1] + nv[p + d.sj] + nv[p - d.sj] + nv[p + d.sk] + nv[p - d.sk] > 0.1) v = 0;
+  return v;
+}
 // les.c:1185-1211: nu_t = Cs * Delta^2 * |S|.  FROM_S: |S| was stored by pass 1 of vfs_les_cs from
 // the same ucat (identical arithmetic), so it is read back instead of being recomputed.
 template <bool FROM_S> struct NuT {

@@ -483,9 +483,10 @@ struct Les3March {
   static constexpr bool HAS01 = true;       // phases 0 + 1 fused with a warp-shuffle i pass on the device (see Les2MarchT::phase01)
   // (a register window over k, as in Les2MarchT, was measured slower here: 0.50 vs 0.44 ms at 256^3 — the three
   // planes' twelve loads are independent L2 hits, the window adds a loop-carried chain; writing nu_t from this
-  // kernel as well cost what the separate NuT kernel costs, 0.14 ms, so it stays separate)
+  // kernel as well cost what the separate NuT kernel costs, 0.14 ms, at 2 resident blocks per SM — re-measured at 4, see with_nut)
   struct State { double v[NV]; double nvc; };
   VfsDev d;
+  int with_nut;      // also nu_t = Cs Delta^2 |S| of the cell (NuT<true>'s arithmetic: |S| from pass 1, Delta^2 = S_LF2 of LesGeo), vfs_rhs_les_fused only
   static int tiles_x(const VfsDev &d) { return (d.mx - 2 + TX - 3) / (TX - 2); }
   static int tiles_y(const VfsDev &d) { return (d.my - 2 + TY - 3) / (TY - 2); }
   VFS_HD static int iorg(int bx) { return bx * (TX - 2); }
@@ -540,7 +541,7 @@ struct Les3March {
     const int kg = k + d.kofs;
     if ((d.perx && (i == 1 || i == d.mx - 2)) || (d.pery && (j == 1 || j == d.my - 2)) || (d.perz && (kg == 1 || kg == d.mz - 2))) return;
     const long p = d.idx(i, j, k);
-    if (st.nvc > 1.1) { d.s[S_CS][p] = 0; return; }
+    if (st.nvc > 1.1) { d.s[S_CS][p] = 0; if (with_nut) d.s[S_NUT][p] = 0; return; }
     const int up = tid - TX, dn = tid + TX;
     const double ws = sA[up] + 4. * st.v[0] + sA[dn];
     const double lm = sA[NT + up] + 4. * st.v[1] + sA[NT + dn];
@@ -551,6 +552,7 @@ struct Les3March {
     cs = (cs < 0) ? 0 : cs;
     cs = (cs < d.max_cs) ? cs : d.max_cs;
     d.s[S_CS][p] = cs;
+    if (with_nut) d.s[S_NUT][p] = nut_value_geo(d, p, cs, d.s[S_SABS][p]);
   }
 };
 // ---- Fp folded into the projection (momentum.c:1548-1678 + 1687-1735 + 1833-1841 [+ 2297-2331]) ---------
