@@ -477,8 +477,8 @@ template <class M, int MINB> static inline int run_filter_march(void *, const M 
 // column, i and j passes through two small shared-memory exchange buffers (the 27-term gather it replaces
 // was bound by shared-memory bandwidth, profiles/r01m).  Cells next to a periodic plane (ghost-image
 // fetches, les.c:738-768) are skipped here and done by the staged kernel on thin slabs.
-struct Les3March {
-  static constexpr int TX = 32, TY = 16, NT = TX * TY, NV = 3;
+template <int TY_> struct Les3MarchT {
+  static constexpr int TX = 32, TY = TY_, NT = TX * TY, NV = 3;
   static constexpr long SMEM_D = 2L * NV * NT;
   static constexpr bool HAS01 = true;       // phases 0 + 1 fused with a warp-shuffle i pass on the device (see Les2MarchT::phase01)
   // (a register window over k, as in Les2MarchT, was measured slower here: 0.50 vs 0.44 ms at 256^3 — the three
@@ -555,6 +555,7 @@ struct Les3March {
     if (with_nut) d.s[S_NUT][p] = nut_value_geo(d, p, cs, d.s[S_SABS][p]);
   }
 };
+typedef Les3MarchT<16> Les3March;      // (32 x 32 tiles, 1024-thread blocks, 88 % instead of 82 % interior cells: measured slower, 0.43 vs 0.40 ms — the block barrier)
 // ---- Fp folded into the projection (momentum.c:1548-1678 + 1687-1735 + 1833-1841 [+ 2297-2331]) ---------
 // The staged chain wrote Fp (FpCell), refreshed its ghosts, applied the periodic node copies and read it back four
 // times in the projection (at p, p+1, p+sj, p+sk).  Here a block marches an (i,j) tile along k: every step it
