@@ -19,3 +19,12 @@ def emu(pkg):
 def test_emulated_momentum_solve_matches_host_restatement(pkg, refdrv, emu, name, dims, kw):
     cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     sc.check(*sc.run_solver_parity(cfg, refdrv, lib=emu, **kw))
+
+
+@pytest.mark.parametrize("flags", [dict(skew=1, clark=1), dict(levelset_weno=5), dict(i_homo_filter=1, k_homo_filter=1)])
+def test_emulated_momentum_solve_with_flux_variants(pkg, refdrv, emu, flags):
+    """The solver drives whatever residual the flags select: the skew-symmetric / Clark / WENO3 fluxes and the homogeneous
+    Cs averaging included (one-thread-per-face kernels, momentum.c:754-923)."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 15, 11, 13)
+    cfg["flags"] = dict(cfg["flags"], **flags)
+    sc.check(*sc.run_solver_parity(cfg, refdrv, lib=emu))
