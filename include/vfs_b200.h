@@ -82,7 +82,8 @@ typedef struct vfs_params {
                           * convection (:789-800,1638-1651); clark (above): mixed model in the viscous flux (:904-923)
                           * and in the dynamic procedure (les.c:497-556,656).  These three run the one-thread-per-face
                           * kernels instead of the marching ones.                                                    */
-  int i_periodic, j_periodic, k_periodic;     /* legacy single-rank periodicity: must be 0   */
+  int i_periodic, j_periodic, k_periodic;     /* legacy periodicity (explicit index remaps on a non-periodic DA): same images as
+                                               * ii/jj/kk, one difference in IB_BC (momentum.c:2206-2211); k_periodic single rank only */
   int i_homo_filter, j_homo_filter, k_homo_filter; /* Cs from LM, MM averaged over homogeneous directions, les.c:798-965 */
   double ren, dt, max_cs;
   double roughness_size; /* -roughness (main.c:319,1734): k_s of the rough-wall log law, bctype -2            */

@@ -24,7 +24,9 @@ for t in range(n):
     if not per[0]: bc[0], bc[1] = rng.choice(WALL_I), rng.choice(WALL_I)
     if not per[1]: bc[2], bc[3] = rng.choice(WALL_JLO), rng.choice(WALL_JHI)
     if not per[2]: bc[4], bc[5] = rng.choice([1, 5, 100]), rng.choice([1, 4, 100])
-    fl = dict(base["flags"], ii_periodic=int(per[0]), jj_periodic=int(per[1]), kk_periodic=int(per[2]),
+    leg = [rng.random() < 0.3 for _ in range(3)]      # a periodic direction through the legacy i/j/k_periodic switch instead of the DA wrap
+    fl = dict(base["flags"], ii_periodic=int(per[0] and not leg[0]), jj_periodic=int(per[1] and not leg[1]), kk_periodic=int(per[2] and not leg[2]),
+              i_periodic=int(per[0] and leg[0]), j_periodic=int(per[1] and leg[1]), k_periodic=int(per[2] and leg[2]),
               second_order=rng.randint(0, 1), laplacian=rng.randint(0, 1), immersed=rng.choice([0, 1, 3]),
               les=rng.choice([0, 1, 2, 2]), testfilter_ik=int(rng.random() < 0.15), roughness_size=1e-3,
               rotor_model=rng.randint(0, 1))

@@ -198,7 +198,7 @@ def run_parity(cfg, refdrv, lib=None, device=0, verbose=False, options=None, leg
         ref.new_vec("dPg", 3, False)
         ref.Pressure_Gradient("dPg", mkf, mka)
         ctx.upload("P", fields["p"])
-        ctx.Pressure_Gradient((mkf - infl) / cfg["dt"] / mka if cfg["flags"].get("kk_periodic") else 0.0)
+        ctx.Pressure_Gradient((mkf - infl) / cfg["dt"] / mka if (cfg["flags"].get("kk_periodic") or cfg["flags"].get("k_periodic")) else 0.0)
         err["Pressure_Gradient"] = relerr(ctx.download("DP"), ref.view("dPg"))
         err["Pressure_Gradient_P"] = relerr(ctx.download("P"), ref.owned("P"))
     ucat_before_projection = np.array(ref.owned("Ucat"))

@@ -117,6 +117,25 @@ def test_emulated_cylinder_inflow_boundary(pkg, refdrv, emu):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("extra,bctype", [
+    (dict(ii_periodic=0, kk_periodic=0, i_periodic=1, k_periodic=1), [100, 100, 1, 10, 100, 100]),
+    (dict(ii_periodic=0, kk_periodic=0, i_periodic=1), [100, 100, 1, 10, 5, 4]),
+    (dict(ii_periodic=0, kk_periodic=0, j_periodic=1, k_periodic=1, skew=1), [1, 1, 100, 100, 100, 100]),
+])
+def test_emulated_legacy_periodic_switches(pkg, refdrv, emu, extra, bctype):
+    """The legacy i/j/k_periodic switches (explicit index remaps m-2 / 1 / m-3 / 2 on a non-periodic DA, e.g.
+    momentum.c:644-651, 708-711, 1575-1601; single rank in the reference): the same ghost images as the DA wrap, except that
+    IB_BC's component copies read the interior node live instead of its stale ghost image (momentum.c:2206-2211)."""
+    base = pkg.cases.scaled(pkg.cases.CONFIGS["c3_turbine"], 17, 13, 15)
+    cfg = dict(base)
+    cfg["flags"] = dict(base["flags"], **extra)
+    cfg["bctype"] = bctype
+    err = pc.run_parity(cfg, refdrv, lib=emu)
+    assert err.pop("FormFunction_SNES_zero_pattern") == 0
+    bad = {k: v for k, v in err.items() if not (v <= TOL)}
+    assert not bad, bad
+
+
 def test_emulated_fp_in_projection_bitwise(pkg, emu):
     """Option 12 (Fp evaluated inside the projection block program) against FpCell + Fp planes + Project: bitwise."""
     import numpy as np

@@ -157,12 +157,15 @@ def variant_cfg(pkg, dims):
     return cfg
 
 
-@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("wallfn", (13, 11, 15)), ("variants", (17, 13, 15))])
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("wallfn", (13, 11, 15)), ("variants", (17, 13, 15)), ("legacy_periodic", (13, 11, 15))])
 def test_glue_dropin_emulated(pkg, refdrv, name, dims):
     import emu_loader
     emu_loader.build()
     if name == "variants":
         cfg = variant_cfg(pkg, dims)
+    elif name == "legacy_periodic":      # i/k periodic through the legacy switches: the host DA is NOT periodic, its local Vecs have no wrap ghosts
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c2_box256"], *dims)
+        cfg["flags"] = dict(cfg["flags"], ii_periodic=0, kk_periodic=0, i_periodic=1, k_periodic=1)
     elif name == "wallfn":       # wall-function sides, first time step: IB_BC rewrites lNvert / Nvert on the host too
         cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c2_box256"], *dims)
         cfg["flags"] = dict(cfg["flags"], ti=5, tistart=5, roughness_size=2.e-4)

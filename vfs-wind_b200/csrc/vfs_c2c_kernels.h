@@ -172,12 +172,14 @@ struct IbBcBoundary {
     if (d.bc[3] == 10 && j == my - 2) d.s[S_UC1][p] = 0;
     if (d.bc[4] == 10 && kg == 0) d.s[S_UC2][p] = 0;
     if (d.bc[5] == 10 && kg == mz - 2) d.s[S_UC2][p] = 0;
-    if (d.perx && i == 0) d.s[S_UC0][p] = d.s[S_UC0][d.idx(-2, j, k)];
-    if (d.perx && i == mx - 1) d.s[S_UC0][p] = d.s[S_UC0][d.idx(mx + 1, j, k)];
-    if (d.pery && j == 0) d.s[S_UC1][p] = d.s[S_UC1][d.idx(i, -2, k)];
-    if (d.pery && j == my - 1) d.s[S_UC1][p] = d.s[S_UC1][d.idx(i, my + 1, k)];
-    if (d.perz && kg == 0) d.s[S_UC2][p] = d.s[S_UC2][d.idx(i, j, k - 2)];
-    if (d.perz && kg == mz - 1) d.s[S_UC2][p] = d.s[S_UC2][d.idx(i, j, k + 2)];
+    // ii/jj/kk_periodic read the DA ghost (index -2 / m+1: the image as of the last refresh, i.e. BEFORE this call's changes);
+    // the legacy i/j/k_periodic lines read the interior node itself (m-2 / 1: its value NOW, after IbBcFaces), :2206-2211
+    if (d.perx && i == 0) d.s[S_UC0][p] = d.s[S_UC0][d.idx(d.legx ? mx - 2 : -2, j, k)];
+    if (d.perx && i == mx - 1) d.s[S_UC0][p] = d.s[S_UC0][d.idx(d.legx ? 1 : mx + 1, j, k)];
+    if (d.pery && j == 0) d.s[S_UC1][p] = d.s[S_UC1][d.idx(i, d.legy ? my - 2 : -2, k)];
+    if (d.pery && j == my - 1) d.s[S_UC1][p] = d.s[S_UC1][d.idx(i, d.legy ? 1 : my + 1, k)];
+    if (d.perz && kg == 0) d.s[S_UC2][p] = d.s[S_UC2][d.idx(i, j, d.legz ? k + (mz - 2) : k - 2)];
+    if (d.perz && kg == mz - 1) d.s[S_UC2][p] = d.s[S_UC2][d.idx(i, j, d.legz ? k - (mz - 2) : k + 2)];
   }
 };
 

@@ -78,6 +78,7 @@ struct VfsDev {
   int bc[6];
   int les, second_order, laplacian, immersed, clark, testfilter_ik, visc_wm, wallfunction, has_feul;
   int ti, tistart, rstart_flg, bdf2, single_rank;
+  int legx, legy, legz;     // the direction is periodic through the legacy i/j/k_periodic switches (explicit index remaps in the reference, no DA wrap): same ghost images, one difference in IB_BC (IbBcBoundary)
   int weno, skew, inviscid; // variants of the staged flux path only (face_flux_core<.., X = true>): WENO3 convection (inviscid or levelset_weno == 5), skew-symmetric form, no viscous term
   int homo;               // homogeneous-direction averaging of LM/MM (les.c:798-965): 0 off, 1 = i and k, 2 = i, 3 = j, 4 = k
   double ren, dt, max_cs, roughness;

@@ -492,13 +492,14 @@ static bool any_per(const vfs_ctx *c) { return c->d.perx || c->d.pery || c->d.pe
 
 // ---- creation -------------------------------------------------------------------------------------
 static int check_params(const vfs_params *p, std::string &why) {
+  // legacy k_periodic reads the interior plane mz-2 / 1 directly in IB_BC (IbBcBoundary): another rank's plane on a slab
+  if (p->k_periodic && !p->kk_periodic && p->nranks > 1) { why = "legacy k_periodic is single-rank only (as in the reference): use kk_periodic between ranks"; return VFS_ERR_UNSUPPORTED; }
   if (p->mx < 6 || p->my < 6 || p->mz < 6) { why = "grid too small (need >= 6 nodes per direction)"; return VFS_ERR_ARG; }
   if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) { why = "bad rank/nranks"; return VFS_ERR_ARG; }
   if (p->kofs < 0 || p->nzl < 1 || p->kofs + p->nzl > p->mz) { why = "bad k-slab"; return VFS_ERR_ARG; }
   if (p->nranks == 1 && (p->kofs != 0 || p->nzl != p->mz)) { why = "single rank must own all k planes"; return VFS_ERR_ARG; }
   if (p->nranks > 1 && p->nzl < VFS_G) { why = "k-slab thinner than the ghost width"; return VFS_ERR_ARG; }
   if (p->levelset || p->rans || p->movefsi || p->rotatefsi) { why = "levelset/rans/movefsi/rotatefsi are outside the hot-path scope"; return VFS_ERR_UNSUPPORTED; }
-  if (p->i_periodic || p->j_periodic || p->k_periodic) { why = "legacy i/j/k_periodic not supported (use ii/jj/kk_periodic)"; return VFS_ERR_UNSUPPORTED; }
   if ((p->levelset_weno && p->levelset_weno != 5) || p->freesurface_wallmodel || p->air_flow_levelset) { why = "levelset_weno 1-4 / freesurface_wallmodel / air_flow_levelset key the flux and wall-model code on the level-set field (momentum.c:754,1015,1301) and are not built (levelset_weno = 5, WENO3 everywhere, is)"; return VFS_ERR_UNSUPPORTED; }
   if (p->les < 0 || p->les > 2) { why = "les must be 0, 1 or 2"; return VFS_ERR_UNSUPPORTED; }
   for (int q = 4; q < 6; q++) if (p->bctype[q] == -1 || p->bctype[q] == -2) { why = "wall-function boundary types (-1,-2) on a k side: Contra2Cart_2 has no velocity rule for them (rhs.c:311-440)"; return VFS_ERR_UNSUPPORTED; }
@@ -513,7 +514,8 @@ static void fill_dev(vfs_ctx *c) {
   d.pitch = ((p.mx + 2 * VFS_G + 15) / 16) * 16; d.ny = p.my + 2 * VFS_G; d.nzt = p.nzl + 2 * VFS_G;
   d.sj = d.pitch; d.sk = (long)d.ny * d.pitch;
   d.org = (long)VFS_G * d.sk + (long)VFS_G * d.sj + VFS_G;
-  d.perx = p.ii_periodic != 0; d.pery = p.jj_periodic != 0; d.perz = p.kk_periodic != 0;
+  d.perx = (p.ii_periodic || p.i_periodic) != 0; d.pery = (p.jj_periodic || p.j_periodic) != 0; d.perz = (p.kk_periodic || p.k_periodic) != 0;
+  d.legx = p.i_periodic != 0 && !p.ii_periodic; d.legy = p.j_periodic != 0 && !p.jj_periodic; d.legz = p.k_periodic != 0 && !p.kk_periodic;
   for (int q = 0; q < 6; q++) d.bc[q] = p.bctype[q];
   d.les = p.les; d.second_order = p.second_order; d.laplacian = p.laplacian; d.immersed = p.immersed; d.clark = p.clark;
   d.testfilter_ik = p.testfilter_ik; d.visc_wm = p.viscosity_wallmodel; d.wallfunction = p.wallfunction;

@@ -49,6 +49,7 @@ extern PetscTruth rstart_flg;
 struct GlueState { vfs_ctx *ctx; bool const_valid; double *buf; size_t buf_doubles; int zs, zm; };
 static std::map<UserCtx *, GlueState> g_state;
 static std::map<UserCtx *, Vec> g_last_x;      // the X of the most recent FormFunction_SNES (owned by the caller's SNES)
+static inline bool any_periodic() { return ii_periodic || jj_periodic || kk_periodic || i_periodic || j_periodic || k_periodic; }
 static int g_eager = 0;       // 1: FormFunction_SNES mirrors its side effects on the host Vecs at every call (see vfs_glue_sync_state)
 
 extern "C" void vfs_glue_invalidate(UserCtx *user) { std::map<UserCtx *, GlueState>::iterator it = g_state.find(user); if (it != g_state.end()) it->second.const_valid = false; }
@@ -241,7 +242,7 @@ void Contra2Cart_2(UserCtx *user) {
   // ibm.c:3673 are followed by Contra2Cart, implicitsolver.c:4406-4444) — so the current host Ucat goes down first.
   push(user, s, user->Ucat, 3, VFS_UCAT);
   ck(s, vfs_contra2cart(s->ctx), "vfs_contra2cart");
-  if (ii_periodic || jj_periodic || kk_periodic) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156 rewrites lUcont's periodic nodes
+  if (any_periodic()) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156 rewrites lUcont's periodic nodes
   pull(user, s, VFS_UCAT, 3, user->Ucat, false);
   DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
   for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }   // rhs.c:336,371,401,435
@@ -310,7 +311,7 @@ void Pressure_Gradient(UserCtx *user, Vec dP) {
   }
   ck(s, vfs_pressure_gradient(s->ctx, kf), "vfs_pressure_gradient");
   pull(user, s, VFS_DP, 3, dP, false);
-  if (ii_periodic || jj_periodic || kk_periodic) {
+  if (any_periodic()) {
     pull(user, s, VFS_P, 1, user->lP, true);
     DALocalToGlobal(user->da, user->lP, INSERT_VALUES, user->P);
   } else { DAGlobalToLocalBegin(user->da, user->P, INSERT_VALUES, user->lP); DAGlobalToLocalEnd(user->da, user->P, INSERT_VALUES, user->lP); }
@@ -340,7 +341,7 @@ PetscErrorCode Projection(UserCtx *user) {
   pull(user, s, VFS_UCONT, 3, user->Ucont, false);
   DAGlobalToLocalBegin(user->fda, user->Ucont, INSERT_VALUES, user->lUcont); DAGlobalToLocalEnd(user->fda, user->Ucont, INSERT_VALUES, user->lUcont);
   ck(s, vfs_contra2cart(s->ctx), "vfs_contra2cart");                    // :3049, on the fields already on the device
-  if (ii_periodic || jj_periodic || kk_periodic) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156
+  if (any_periodic()) pull(user, s, VFS_UCONT, 3, user->lUcont, true);   // rhs.c:129-156
   pull(user, s, VFS_UCAT, 3, user->Ucat, false);
   DAGlobalToLocalBegin(user->fda, user->Ucat, INSERT_VALUES, user->lUcat); DAGlobalToLocalEnd(user->fda, user->Ucat, INSERT_VALUES, user->lUcat);
   for (int q = 0; q < 4; q++) if (user->bctype[q] == -1 || user->bctype[q] == -2) { pull(user, s, VFS_USTAR, 1, user->lUstar, false); break; }
