@@ -26,7 +26,9 @@ def main():
         if not per[0]: bc[0], bc[1] = rng.choice([1, 10, -1, -2]), rng.choice([1, 10, -1, -2])
         if not per[1]: bc[2], bc[3] = rng.choice([1, 10, 12, -1, -2]), rng.choice([1, 2, 4, 10, -10, 12, 13, 14, -1, -2])
         if not per[2]: bc[4], bc[5] = rng.choice([1, 5]), rng.choice([1, 4])
-        extra = dict(ii_periodic=int(per[0]), jj_periodic=int(per[1]), kk_periodic=int(per[2]), second_order=rng.randint(0, 1),
+        leg = [rng.random() < 0.3, rng.random() < 0.3]      # i / j periodic through the legacy switches (k_periodic is single-rank only)
+        extra = dict(ii_periodic=int(per[0] and not leg[0]), jj_periodic=int(per[1] and not leg[1]), kk_periodic=int(per[2]),
+                     i_periodic=int(per[0] and leg[0]), j_periodic=int(per[1] and leg[1]), second_order=rng.randint(0, 1),
                      laplacian=rng.randint(0, 1), immersed=rng.choice([0, 1, 3]), les=rng.choice([0, 1, 2, 2]), roughness_size=1e-3)
         if rng.random() < 0.3: extra["skew"] = 1          # Adv1-3 and the Clark gradient planes live outside the main pool and travel too
         if rng.random() < 0.3: extra["clark"] = 1
