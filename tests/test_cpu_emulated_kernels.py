@@ -204,3 +204,29 @@ def test_emulated_restart_files_feed_the_path(pkg, emu, tmp_path):
         ctx.close()
     for n in outs[0]:
         assert np.array_equal(outs[0][n], outs[1][n]), n
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (17, 13, 15)), ("c3_turbine", (21, 17, 19))])
+def test_emulated_state_carries_over_several_steps(pkg, refdrv, emu, name, dims):
+    """Persistent device state across calls (Ucat is in/out, IB and boundary values carry over): four
+    explicit pseudo-steps U <- U + 0.2 dt F(U), each = the LES block + one residual, on the reference and through the fused
+    unit of the library, nothing re-uploaded but U.  The residual of every step must agree (the iterates therefore too)."""
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    ref, xyz, fields, met = pc.ref_setup(cfg, refdrv)
+    ctx = pc.dev_setup(cfg, xyz, fields, lib=emu)
+    ref.new_vec("X", 3, False); ref.new_vec("F", 3, False)
+    x = np.array(fields["ucont"])
+    for step in range(4):
+        ref.set_owned("Ucont", x); ref.global_to_local("Ucont", "lUcont")
+        ref.Contra2Cart(); ref.Compute_Smagorinsky_Constant_1(); ref.Compute_eddy_viscosity_LES()
+        ref.view("X")[...] = x
+        ref.FormFunction_SNES("X", "F")
+        f_ref = np.array(ref.view("F"))
+        ctx.upload("UCONT", x)
+        ctx.rhs_les_fused()
+        f_dev = ctx.download("RHS")
+        assert pc.relerr(f_dev, f_ref) <= 1e-11, (step, pc.relerr(f_dev, f_ref))
+        assert pc.relerr(ctx.download("UCAT"), ref.owned("Ucat")) <= 1e-12, step
+        assert pc.relerr(ctx.download("NU_T"), ref.owned("lNu_t")) <= 1e-11, step
+        x = x + 0.2 * cfg["dt"] * f_ref
+    ctx.close()
