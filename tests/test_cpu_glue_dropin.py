@@ -214,6 +214,73 @@ def test_glue_periodic_turbine_array_emulated(pkg, refdrv):
     assert not bad, bad
 
 
+def run_two_time_steps(refdrv, pkg, so_name, cfg):
+    """Flow_Solver's call sequence (solvers.c:365-688) for two time steps, on the reference objects and on the glue, with
+    the documented once-per-step `vfs_glue_invalidate`: LES block, Pressure_Gradient, RHS_o = Formfunction_2(U), three
+    residual evaluations standing in for the Krylov iterations, a stand-in pressure correction, UpdatePressure +
+    Projection, then the host-side end-of-step bookkeeping (Ucont_o <- Ucont, lUcat_old <- Ucat).  Catches stale cached
+    constants: every Vec either side leaves behind is compared after each step."""
+    import importlib.util
+    so = os.path.join(pc.ROOT, "oracle", "_ref", so_name)
+    if not os.path.exists(so):
+        pytest.skip(so_name + " not built")
+    spec = importlib.util.spec_from_file_location("refdrv_glue4", os.path.join(pc.ROOT, "oracle", "refdrv.py"))
+    gd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gd)
+    gd.SO = so
+    gd._GLOBALS_JSON = os.path.join(pc.ROOT, "oracle", "_ref", "globals_glue_%s.json" % so_name.split("_")[1].split(".")[0])
+    ref, xyz, fields, met = pc.ref_setup(cfg, refdrv)
+    glue, _, _, _ = pc.ref_setup(cfg, gd)
+    rng = np.random.default_rng(31)
+    err = {}
+    for d in (ref, glue):
+        d.set_owned("P", fields["p"]); d.global_to_local("P", "lP")
+        d.new_vec("X", 3, False); d.new_vec("F", 3, False)
+    for step in range(2):
+        phi = 0.02 * rng.uniform(-1, 1, fields["p"].shape)
+        pert = [1e-3 * rng.uniform(-1, 1, fields["ucont"].shape) for _ in range(3)]
+        for d, drv in ((ref, refdrv), (glue, gd)):
+            drv.set_global("ti", 10 + step)
+            if d is glue:
+                gd.lib().vfs_glue_invalidate(C.c_void_p(glue.u))
+            d.global_to_local("Ucont", "lUcont")
+            d.Contra2Cart(); d.Compute_Smagorinsky_Constant_1(); d.Compute_eddy_viscosity_LES()      # solvers.c:365-370
+            d.Pressure_Gradient("dP", 0.3, 2.0)                                                        # :438 (into user->dP, as the reference calls it)
+            d.view("RHS_o")[...] = 0
+            d.Formfunction_2("RHS_o", 1.0)                                                             # :629
+            # (no second invalidate: dP and RHS_o were produced by the glue, the device copies are the fresh ones)
+            u = np.array(d.owned("Ucont"))
+            for q in range(3):                                                                         # :631 (SNESSolve)
+                d.view("X")[...] = u * (1.0 + pert[q])
+                d.FormFunction_SNES("X", "F")
+                u = u + 0.1 * cfg["dt"] * np.array(d.view("F"))
+            if d is glue:
+                gd.lib().vfs_glue_sync_state(C.c_void_p(glue.u))
+            d.set_owned("Ucont", u); d.global_to_local("Ucont", "lUcont")
+            d.set_owned("Phi", phi); d.global_to_local("Phi", "lPhi")                                  # :652 (Poisson solve, host)
+            d.UpdatePressure(); d.Projection(1.0)                                                      # :662-663
+        for nm in ("Ucont", "Ucat", "lUcat", "P", "lP", "RHS_o", "dP"):
+            err["step%d_%s" % (step, nm)] = pc.relerr(glue.view(nm), ref.view(nm))
+        for nm in ("lCs", "lNu_t", "lUcont"):
+            err["step%d_%s" % (step, nm)] = pc.relerr(glue.owned(nm), ref.owned(nm))
+        err["step%d_F" % step] = pc.relerr(glue.view("F"), ref.view("F"))
+        for d in (ref, glue):                         # end of the step: Ucont_o <- Ucont, lUcat_old <- Ucat (solvers.c / main.c)
+            d.set_owned("Ucont_o", np.array(d.owned("Ucont")))
+            d.set_owned("lUcat_old", np.array(d.owned("Ucat"))); d.wrap_fill("lUcat_old")
+    gd.lib().vfs_glue_release(C.c_void_p(glue.u))
+    return err
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17))])
+def test_glue_two_time_steps_emulated(pkg, refdrv, name, dims):
+    import emu_loader
+    emu_loader.build()
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = run_two_time_steps(refdrv, pkg, "libvfsglue_emu.so", cfg)
+    bad = {k: v for k, v in err.items() if not (v <= 1e-11)}
+    assert not bad, bad
+
+
 def run_glue_solver(refdrv, pkg, so_name, cfg):
     """vfs_glue_snes_solve — the one-line replacement of SNESSolve in Implicit_MatrixFree (implicitsolver.c:4299) —
     against the numpy restatement of the PETSc algorithms driving the REFERENCE residual; also the UserCtx Vecs it

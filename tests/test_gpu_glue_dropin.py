@@ -27,3 +27,12 @@ def test_glue_periodic_turbine_array_cuda(pkg, refdrv):
     err = run_periodic_turbines(refdrv, pkg, "libvfsglue_cuda.so")
     bad = {k: v for k, v in err.items() if not (v <= TOL)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name,dims", [("c2_box256", (21, 17, 25)), ("c3_turbine", (29, 21, 25))])
+def test_glue_two_time_steps_cuda(pkg, refdrv, name, dims):
+    from test_cpu_glue_dropin import run_two_time_steps
+    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    err = run_two_time_steps(refdrv, pkg, "libvfsglue_cuda.so", cfg)
+    bad = {k: v for k, v in err.items() if not (v <= 1e-11)}
+    assert not bad, bad

@@ -433,9 +433,13 @@ PetscErrorCode Formfunction_2(UserCtx *user, Vec Rhs, double scale) {
   push_constants(user, s);
   push(user, s, user->lUcont, 3, VFS_UCONT); push(user, s, user->lUcat, 3, VFS_UCAT);
   if (les) push(user, s, user->lNu_t, 1, VFS_NU_T);
-  push(user, s, Rhs, 3, VFS_RHS);
-  ck(s, vfs_formfunction2(s->ctx, VFS_RHS, scale), "vfs_formfunction2");
-  pull(user, s, VFS_RHS, 3, Rhs, false);
+  // RHS_o = Formfunction_2(U_o) is assembled once per step AFTER the per-step constants went down (solvers.c:629): when the
+  // target is user->RHS_o the result is accumulated in the device's RHS_o field itself, so the residual evaluations that
+  // follow read the fresh one without another upload
+  const int field = Rhs == user->RHS_o ? VFS_RHS_O : VFS_RHS;
+  push(user, s, Rhs, 3, field);
+  ck(s, vfs_formfunction2(s->ctx, field, scale), "vfs_formfunction2");
+  pull(user, s, field, 3, Rhs, false);
   if (viscosity_wallmodel && les) pull(user, s, VFS_USTAR, 1, user->lUstar, false);      // momentum.c:1150
   cylinder_diag(user, s);
   return 0;
