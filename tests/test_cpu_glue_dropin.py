@@ -271,11 +271,17 @@ def run_two_time_steps(refdrv, pkg, so_name, cfg):
     return err
 
 
-@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17))])
+@pytest.mark.parametrize("name,dims", [("c2_box256", (13, 11, 15)), ("c3_turbine", (19, 15, 17)), ("variants", (17, 13, 15)), ("legacy_periodic", (13, 11, 15))])
 def test_glue_two_time_steps_emulated(pkg, refdrv, name, dims):
     import emu_loader
     emu_loader.build()
-    cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
+    if name == "variants":
+        cfg = variant_cfg(pkg, dims)
+    elif name == "legacy_periodic":
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS["c2_box256"], *dims)
+        cfg["flags"] = dict(cfg["flags"], ii_periodic=0, kk_periodic=0, i_periodic=1, k_periodic=1)
+    else:
+        cfg = pkg.cases.scaled(pkg.cases.CONFIGS[name], *dims)
     err = run_two_time_steps(refdrv, pkg, "libvfsglue_emu.so", cfg)
     bad = {k: v for k, v in err.items() if not (v <= 1e-11)}
     assert not bad, bad
