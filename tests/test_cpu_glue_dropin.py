@@ -233,6 +233,7 @@ def run_two_time_steps(refdrv, pkg, so_name, cfg):
     glue, _, _, _ = pc.ref_setup(cfg, gd)
     rng = np.random.default_rng(31)
     err = {}
+    act = pc.make_actuator(cfg, xyz)
     for d in (ref, glue):
         d.set_owned("P", fields["p"]); d.global_to_local("P", "lP")
         d.new_vec("X", 3, False); d.new_vec("F", 3, False)
@@ -246,6 +247,11 @@ def run_two_time_steps(refdrv, pkg, so_name, cfg):
             d.global_to_local("Ucont", "lUcont")
             d.Contra2Cart(); d.Compute_Smagorinsky_Constant_1(); d.Compute_eddy_viscosity_LES()      # solvers.c:365-370
             d.Pressure_Gradient("dP", 0.3, 2.0)                                                        # :438 (into user->dP, as the reference calls it)
+            if cfg["flags"].get("rotor_model"):                                                        # :491-534: velocity at the blades -> (host aerodynamics) -> forcing
+                ul = d.Calc_U_lagr(act)
+                act_step = dict(act, F_lagr=act["F_lagr"] * (1.0 + 0.1 * step) - 0.05 * ul)
+                d.view("lF_eul")[...] = 0
+                d.Calc_F_eul(act_step, 10)
             d.view("RHS_o")[...] = 0
             d.Formfunction_2("RHS_o", 1.0)                                                             # :629
             # (no second invalidate: dP and RHS_o were produced by the glue, the device copies are the fresh ones)
@@ -259,7 +265,7 @@ def run_two_time_steps(refdrv, pkg, so_name, cfg):
             d.set_owned("Ucont", u); d.global_to_local("Ucont", "lUcont")
             d.set_owned("Phi", phi); d.global_to_local("Phi", "lPhi")                                  # :652 (Poisson solve, host)
             d.UpdatePressure(); d.Projection(1.0)                                                      # :662-663
-        for nm in ("Ucont", "Ucat", "lUcat", "P", "lP", "RHS_o", "dP"):
+        for nm in ("Ucont", "Ucat", "lUcat", "P", "lP", "RHS_o", "dP", "F_eul"):
             err["step%d_%s" % (step, nm)] = pc.relerr(glue.view(nm), ref.view(nm))
         for nm in ("lCs", "lNu_t", "lUcont"):
             err["step%d_%s" % (step, nm)] = pc.relerr(glue.owned(nm), ref.owned(nm))
