@@ -46,13 +46,16 @@ extern PetscReal dhi_fixed, dhj_fixed, dhk_fixed, halfwidth_dfunc;
 extern double roughness_size;
 extern PetscTruth rstart_flg;
 
-struct GlueState { vfs_ctx *ctx; bool const_valid; double *buf; size_t buf_doubles; int zs, zm; };
+struct GlueState { vfs_ctx *ctx; bool const_valid, metrics_valid; double *buf; size_t buf_doubles; int zs, zm; };
 static std::map<UserCtx *, GlueState> g_state;
 static std::map<UserCtx *, Vec> g_last_x;      // the X of the most recent FormFunction_SNES (owned by the caller's SNES)
 static inline bool any_periodic() { return ii_periodic || jj_periodic || kk_periodic || i_periodic || j_periodic || k_periodic; }
 static int g_eager = 0;       // 1: FormFunction_SNES mirrors its side effects on the host Vecs at every call (see vfs_glue_sync_state)
 
 extern "C" void vfs_glue_invalidate(UserCtx *user) { std::map<UserCtx *, GlueState>::iterator it = g_state.find(user); if (it != g_state.end()) it->second.const_valid = false; }
+// the grid moved or the host rewrote the centre metrics itself: they go down again with the next call (FormMetrics through
+// the glue leaves them on the device, so a fixed grid never ships its ten metric scalars per step)
+extern "C" void vfs_glue_invalidate_grid(UserCtx *user) { std::map<UserCtx *, GlueState>::iterator it = g_state.find(user); if (it != g_state.end()) it->second.const_valid = it->second.metrics_valid = false; }
 extern "C" void vfs_glue_release(UserCtx *user) {
   std::map<UserCtx *, GlueState>::iterator it = g_state.find(user);
   if (it != g_state.end()) { vfs_destroy(it->second.ctx); vfs_host_free(it->second.buf); g_state.erase(it); }
@@ -89,7 +92,7 @@ static GlueState *state(UserCtx *user) {
   std::map<UserCtx *, GlueState>::iterator it = g_state.find(user);
   vfs_params p; fill_params(user, &p);
   if (it == g_state.end()) {
-    GlueState s; s.ctx = 0; s.const_valid = false; s.zs = p.kofs; s.zm = p.nzl;
+    GlueState s; s.ctx = 0; s.const_valid = false; s.metrics_valid = false; s.zs = p.kofs; s.zm = p.nzl;
     int r = vfs_create(&p, &s.ctx);
     if (r) { PetscPrintf(PETSC_COMM_WORLD, "vfs_b200: cannot create device context (%d): %s\n", r, vfs_last_error(0)); exit(1); }   // no CPU fallback
     if (p.nranks > 1) {         // in-library NCCL halo layer: rank 0's id to everybody
@@ -146,8 +149,12 @@ static void pull(UserCtx *user, GlueState *s, int field, int dof, Vec v, bool v_
 }
 static void push_constants(UserCtx *user, GlueState *s) {
   if (s->const_valid) return;
-  push(user, s, user->lCsi, 3, VFS_CSI); push(user, s, user->lEta, 3, VFS_ETA); push(user, s, user->lZet, 3, VFS_ZET);
-  push(user, s, user->lAj, 1, VFS_AJ); push(user, s, user->lNvert, 1, VFS_NVERT);
+  if (!s->metrics_valid) {      // only when the device does not hold them yet (no FormMetrics through the glue since the context exists)
+    push(user, s, user->lCsi, 3, VFS_CSI); push(user, s, user->lEta, 3, VFS_ETA); push(user, s, user->lZet, 3, VFS_ZET);
+    push(user, s, user->lAj, 1, VFS_AJ);
+    s->metrics_valid = true;
+  }
+  push(user, s, user->lNvert, 1, VFS_NVERT);
   push(user, s, user->lUcat_old, 3, VFS_UCAT_OLD);
   push(user, s, user->Ucat, 3, VFS_UCAT);                 // persistent in/out state (IBM cells, inflow ghosts)
   push(user, s, user->Ucont_o, 3, VFS_UCONT_O);
@@ -230,6 +237,7 @@ PetscErrorCode FormMetrics(UserCtx *user) {
   host_face_metrics(user);
   host_cent_gridspace(user);
   s->const_valid = false;
+  s->metrics_valid = true;      // the device holds what the host Vecs now hold
   return 0;
 }
 
